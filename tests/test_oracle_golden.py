@@ -1,0 +1,99 @@
+"""Pins oracle/mfas_oracle.py (numpy restatement + hand-derived backward) to fixtures produced
+by executing the unmodified reference (tests/golden/gen_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN_CASES, GOLDEN_DIR, init_states, rel_err, sample_tensor, split_np
+from mfas_b200.cache import FeatureCacheLoader, synthetic_ntu_cache
+from oracle import mfas_oracle as O
+
+TOL = 1e-4      # north_star: "within 1e-4 relative fp tolerance"
+
+
+def _setup(cs):
+    train = synthetic_ntu_cache(cs["n_train"], cs["data_seed"])
+    dev = synthetic_ntu_cache(cs["n_dev"], cs["data_seed"] + 1)
+    return train, dev
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_oracle_matches_reference_fixture(name):
+    cs = GOLDEN_CASES[name]
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    train, dev = _setup(cs)
+    seed = int(g["meta/loader_seed"])
+    ltr = FeatureCacheLoader(train, cs["B"], True, seed)
+    ldv = FeatureCacheLoader(dev, cs["B"], True, seed + 50000)
+    trs, dvs = split_np(train), split_np(dev)
+    inits = init_states(cs["confs"], cs["H"], 60, cs["bn"], cs["drpt"], cs["model_seed"])
+    E, B = cs["epochs"], cs["B"]
+    for ci, conf in enumerate(cs["confs"]):
+        # --- one step: logits, loss, gradients (autograd vs hand-derived)
+        head = O.FusionHead(conf, cs["H"], 60, inits[ci], batchnorm=cs["bn"], drpt=cs["drpt"])
+        rows = ltr.order_for_pass(ci * E)[:B].numpy()
+        sk, rg, y = O._taps_of(trs, rows)
+        logits, tape = head.forward(sk, rg, train=True)
+        loss, _ = head.ce_loss(logits, y)
+        assert rel_err(logits, g[f"c{ci}/step0_logits"]) < TOL
+        assert abs(float(loss) - float(g[f"c{ci}/step0_loss"])) < TOL * abs(float(g[f"c{ci}/step0_loss"]))
+        grads = head.backward(logits, y, tape)
+        for k, v in grads.items():
+            if k.startswith("alphas"):
+                continue
+            s = sample_tensor(v)
+            ref = g[f"c{ci}/grad/{k}/sample"]
+            scale = max(float(g[f"c{ci}/grad/{k}/amax"]), 1e-12)
+            assert np.abs(s["sample"] - ref).max() / scale < TOL, k
+            assert abs(s["s2"] - float(g[f"c{ci}/grad/{k}/s2"])) <= 2 * TOL * float(g[f"c{ci}/grad/{k}/s2"]) + 1e-20
+
+        # --- full run: per-batch losses, dev accuracy, best-epoch rollback, final weights
+        head = O.FusionHead(conf, cs["H"], 60, inits[ci], batchnorm=cs["bn"], drpt=cs["drpt"])
+        sched = O.CosineRestartLR(1e-3, 1e-6, cs["Ti"], 2, cs["n_train"] / B)
+        per_batch = {"train": [], "dev": []}
+
+        def orders(phase, epoch, ci=ci):
+            return (ltr if phase == "train" else ldv).order_for_pass(ci * E + epoch).numpy()
+
+        best, stats = O.train_track_acc(head, sched, trs, dvs, B, orders, E)
+        n_tb = -(-cs["n_train"] // B)
+        exp_train_loss = (g[f"c{ci}/train_loss"] * np.minimum(B, cs["n_train"] - B * np.arange(n_tb))).sum(1) / cs["n_train"]
+        got = np.array([s["train_loss"] for s in stats])
+        # Adam's first steps divide m by sqrt(v) ~ |g|, so rounding noise in tiny gradients is
+        # amplified along the trajectory; epoch-level quantities get a looser bound than one step.
+        assert np.abs(got - exp_train_loss).max() / np.abs(exp_train_loss).max() < 20 * TOL
+        exp_dev_acc = g[f"c{ci}/dev_correct"].sum(1) / cs["n_dev"]
+        got_acc = np.array([s["dev_acc"] for s in stats])
+        assert np.abs(got_acc - exp_dev_acc).max() <= 1.0 / cs["n_dev"] + 1e-12
+        assert abs(float(best) - float(g[f"c{ci}/best_acc"])) <= 1.0 / cs["n_dev"] + 1e-12
+        for k, v in head.state.items():
+            if k.endswith("num_batches_tracked") or k.startswith("alphas"):
+                continue
+            ref = g[f"c{ci}/final/{k}/sample"]
+            scale = max(float(g[f"c{ci}/final/{k}/amax"]), 1e-12)
+            err = np.abs(sample_tensor(v)["sample"] - ref).max() / scale
+            assert err < 50 * TOL, (k, err)
+
+
+def test_scheduler_restart_quirk():
+    """Restart fires only when Tcur/Ti hits an odd integer exactly (scheduler.py:35-38)."""
+    s = O.CosineRestartLR(1e-3, 1e-6, 1, 2, 4.0)      # nbpe integral -> restart at it=4
+    etas = [s.step() for _ in range(6)]
+    assert etas[0] == pytest.approx(1e-3)
+    assert etas[4] == pytest.approx(1e-6)
+    assert s.Ti == 2 and etas[5] == pytest.approx(1e-3)
+    s = O.CosineRestartLR(1e-3, 1e-6, 1, 2, 4.5)      # non-integral nbpe: keeps going past pi
+    etas = [s.step() for _ in range(12)]
+    assert s.Ti == 1 and etas[9] == pytest.approx(1e-3)
+
+
+def test_no_recipe_for_nodrop_nobn():
+    with pytest.raises(UnboundLocalError):
+        O.FusionHead([[0, 0, 0]], 16, 60, {}, batchnorm=False, drpt=0.0)
+
+
+def test_algorithmic_counts_match_survey():
+    c = O.algorithmic_counts([[3, 1, 1], [1, 3, 0], [1, 1, 1], [3, 3, 0]], 128, 60, 64)
+    assert c["F_sel"] == 7680 and c["P"] == 1041468 and c["K"] == [1536, 2432, 1408, 2688]
+    assert abs(c["train_bytes"] - 26.96e6) < 0.01e6 and abs(c["eval_bytes"] - 6.13e6) < 0.01e6
