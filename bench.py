@@ -1,0 +1,313 @@
+#!/usr/bin/env python3
+"""Benchmark of the MFAS candidate-training hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+metric : candidate-epochs/sec -- one candidate-epoch = ceil(N_train/B) Adam steps + ceil(N_dev/B) eval
+         steps of one fusion head (reference: models/search/train_searchable/ntu.py:20-22).
+workload (BASELINE.json configs[1]): found conf 4, inner_repr=128, batchnorm, bs=64, synthetic NTU-shaped
+         cache N_train=10240 / N_dev=5120, `--candidates` heads per GPU trained concurrently for `--epochs`.
+step   : one pass of the hot path = one train_run over all candidates of the rank (E epochs).
+value  : whole-job throughput with inputs resident in HBM (CUDA events, max over ranks).
+e2e    : the same metric through the public API `train_sampled_models` with HOST caches: model
+         construction, H2D of cache / weights / batch orders and the D2H of the accuracies are timed.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CONF4 = [[3, 1, 1], [1, 3, 0], [1, 1, 1], [3, 3, 0]]       # main_found_ntu.py:181-182
+H, B, C = 128, 64, 60
+N_TRAIN, N_DEV = 10240, 5120
+METRIC, UNIT = "candidate-epochs/sec (NTU fusion, bs=64)", "candidate-epochs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--candidates", type=int, default=64, help="candidates per GPU (weak scaling)")
+    ap.add_argument("--epochs", type=int, default=1)
+    ap.add_argument("--cpu-sample-steps", type=int, default=48, help="train steps of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {"workload": "NTU found conf=4 (4-step fusion), inner_repr=128, batchnorm, drpt=0, bs=64, "
+                        f"N_train={N_TRAIN}, N_dev={N_DEV}, {a.candidates} candidates/GPU x {a.epochs} epoch(s) per step",
+            "candidates_per_gpu": a.candidates, "epochs_per_step": a.epochs, "parallelism": f"candidates sharded x{n_gpus}",
+            "l2": "inputs exceed L2 (cache 0.46 GB + per-candidate state 12.5 MB x candidates >> 126 MB)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_sample(train_steps, threads=None):
+    """Time the PyTorch-CPU port of the reference path on a bounded sample of the cfg2 workload:
+    `train_steps` optimiser steps + train_steps/2 eval steps of one candidate (the 2:1 ratio of a
+    candidate-epoch), extrapolated to candidate-epochs/s."""
+    import torch
+    from mfas_b200.cache import synthetic_ntu_cache
+    from oracle.torch_port import FusionHeadTorch, train_candidate
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    dev_steps = max(1, train_steps // 2)
+    train = synthetic_ntu_cache(max(train_steps * B, 2 * B), 1)
+    dev = synthetic_ntu_cache(max(dev_steps * B, B), 2)
+    torch.manual_seed(0)
+    model = FusionHeadTorch(CONF4, H, C, batchnorm=True)
+    tr, dv = (train.ske_cat, train.rgb_cat, train.labels), (dev.ske_cat, dev.rgb_cat, dev.labels)
+    orders = lambda ph, e: torch.randperm(len(train) if ph == "train" else len(dev))
+    train_candidate(model, tr, dv, orders, B, 1, max_train_steps=4, max_dev_steps=2)        # warm-up
+    t0 = time.perf_counter()
+    _, st = train_candidate(model, tr, dv, orders, B, 1, max_train_steps=train_steps, max_dev_steps=dev_steps)
+    dt = time.perf_counter() - t0
+    frac = st[0]["train_steps"] / math.ceil(N_TRAIN / B)        # fraction of a candidate-epoch that was run
+    return {"value": frac / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"oracle/torch_port.py (PyTorch CPU restatement of the reference path), 1 candidate, "
+                      f"{st[0]['train_steps']} train + {st[0]['dev_steps']} eval steps of cfg2 in {dt:.2f} s, "
+                      f"scaled to a {math.ceil(N_TRAIN / B)}+{math.ceil(N_DEV / B)}-step candidate-epoch"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from mfas_b200.cache import synthetic_ntu_cache
+    from oracle.torch_port import FusionHeadTorch, train_candidate
+    threads = os.cpu_count()
+    torch.set_num_threads(threads)
+    # each step: a bounded sample = 1/4 candidate-epoch (40 train + 20 eval steps) of one candidate
+    ts, ds = 40, 20
+    train, dev = synthetic_ntu_cache(ts * B, 1), synthetic_ntu_cache(ds * B, 2)
+    tr, dv = (train.ske_cat, train.rgb_cat, train.labels), (dev.ske_cat, dev.rgb_cat, dev.labels)
+    orders = lambda ph, e: torch.randperm(len(train) if ph == "train" else len(dev))
+    torch.manual_seed(0)
+    model = FusionHeadTorch(CONF4, H, C, batchnorm=True)
+    for _ in range(a.warmup):
+        train_candidate(model, tr, dv, orders, B, 1)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        train_candidate(model, tr, dv, orders, B, 1)
+    dt = (time.perf_counter() - t0) / max(a.steps, 1)
+    value = (ts / math.ceil(N_TRAIN / B)) / dt
+    sample = f"oracle/torch_port.py on {threads} host threads; each step = {ts} train + {ds} eval steps of one cfg2 candidate (1/4 candidate-epoch)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(a, a.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as td
+    from helpers import make_args
+    import mfas_b200.ntu_searchable as ntu
+    from mfas_b200 import dist as mdist
+    from mfas_b200.cache import FeatureCacheLoader, synthetic_ntu_cache
+    from mfas_b200.engine import CandidateGroup, algorithmic_counts
+    from mfas_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=device)
+    n_gpus = world
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+    M, E = a.candidates, a.epochs
+    # ---- inputs: rank 0 builds the cache, NCCL broadcasts it once -------------------------------
+    host_train = synthetic_ntu_cache(N_TRAIN, 1).pin() if rank == 0 else None
+    host_dev = synthetic_ntu_cache(N_DEV, 2).pin() if rank == 0 else None
+    train_dev = mdist.broadcast_cache(host_train, device)
+    dev_dev = mdist.broadcast_cache(host_dev, device)
+    steps_tr, steps_dv = math.ceil(N_TRAIN / B), math.ceil(N_DEV / B)
+
+    # ---- device-resident arm: `value` -------------------------------------------------------
+    args = make_args(H, B, E, bn=True, drpt=0.0, Ti=1)
+    confs = [np.array(CONF4) for _ in range(M)]
+    g = CandidateGroup(confs, H, C, _lib.FLAG_BN, device, batch_max=B, cand_ids=[rank * M + i for i in range(M)])
+    g.set_adam(0.9, 0.999, 1e-8, 1e-4)
+    torch.manual_seed(1234 + rank)
+    for c in range(M):                                    # torch-default Linear init (kaiming-uniform bound 1/sqrt(K))
+        for name in g.names(c):
+            v = g.view(c, name)
+            if name.endswith("0.weight") or name.endswith("0.bias") or name.startswith("central"):
+                K = g.view(c, name.rsplit(".", 1)[0] + ".weight").shape[1]
+                v.uniform_(-1 / math.sqrt(K), 1 / math.sqrt(K))
+            elif name.endswith("2.weight") or name.endswith("running_var"):
+                v.fill_(1.0)
+    gen = torch.Generator().manual_seed(77 + rank)
+    ptr = torch.stack([torch.stack([torch.randperm(N_TRAIN, generator=gen) for _ in range(E)]) for _ in range(M)]).to(device, torch.int32)
+    pdv = torch.stack([torch.stack([torch.randperm(N_DEV, generator=gen) for _ in range(E)]) for _ in range(M)]).to(device, torch.int32)
+    lrs = ntu.cosine_lrs(args, N_TRAIN, E * steps_tr)
+
+    def one_step():
+        return g.train_run(train_dev, dev_dev, ptr, pdv, lrs, E, B)
+
+    for _ in range(a.warmup):
+        one_step()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = g.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(a.steps):
+        stats, best, _ = one_step()
+    ev1.record()
+    barrier()
+    dt = max_over_ranks(ev0.elapsed_time(ev1) / 1e3) / max(a.steps, 1)
+    launches = g.launches - l0
+    clk = clocks.stop() if rank == 0 else None
+    value = M * E * n_gpus / dt
+    finite = bool(torch.isfinite(stats).all().item())
+
+    # ---- roofline of the fused train step (all launches of one optimiser step, all candidates) ----
+    cnt = algorithmic_counts(g.layouts[0], B)
+    rows = ptr[:, 0, :B].contiguous()
+    for _ in range(5):
+        g.train_step(train_dev, rows, 1e-4)
+    n_t = 40
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    r0.record()
+    for i in range(n_t):
+        g.train_step(train_dev, ptr[:, 0, (i % steps_tr) * B:(i % steps_tr + 1) * B], 1e-4)
+    r1.record()
+    torch.cuda.synchronize()
+    t_step = r0.elapsed_time(r1) / 1e3 / n_t
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = M * cnt["train_bytes"] / t_step / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": f"train step = {2 * 4 + 1 + 4} launches (4 x k_fusion_fwd, k_head, 4 x (k_dz + k_fusion_bwd)), {M} candidates",
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
+                "algorithmic_bytes_per_launch": M * cnt["train_bytes"], "ms_per_launch": t_step * 1e3,
+                "tensor_tflops": M * (cnt["fwd_flops"] + cnt["bwd_flops"]) / t_step / 1e12}
+    g.close()
+
+    # ---- e2e: the public API with HOST buffers ---------------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        if rank != 0:       # every rank owns a host copy, as a real multi-process search would
+            host_train = synthetic_ntu_cache(N_TRAIN, 1).pin()
+            host_dev = synthetic_ntu_cache(N_DEV, 2).pin()
+        loaders = {"train": FeatureCacheLoader(host_train, B, True, 100), "dev": FeatureCacheLoader(host_dev, B, True, 200)}
+        all_confs = [np.array(CONF4) for _ in range(M * n_gpus)]
+
+        def e2e_step():
+            host_train.drop_device_copies(); host_dev.drop_device_copies()   # H2D of the cache is inside the step
+            accs = ntu.train_sampled_models(all_confs, ntu.Searchable_Skeleton_Image_Net, loaders, args, device)
+            return accs
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(1, min(a.steps, 2))):
+            accs = e2e_step()
+        barrier()
+        dte = max_over_ranks((time.perf_counter() - t0) / max(1, min(a.steps, 2)))
+        lay = _lib.Layout
+        n_params = 1041484
+        h2d = host_train.nbytes() + host_dev.nbytes() + M * n_params * 4 + M * E * (N_TRAIN + N_DEV) * 4
+        d2h = M * (E * 4 + 1) * 8
+        e2e = {"value": M * E * n_gpus / dte, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": dte * 1e3,
+               "api": "mfas_b200.ntu_searchable.train_sampled_models (host FeatureCache in pinned memory; model construction, "
+                      "cache/weight/order uploads and accuracy read-back inside the timed region)",
+               "accs_head": [float(x) for x in accs[:3]]}
+
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
+        cpu = cpu_reference_sample(a.cpu_sample_steps)
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(a, n_gpus), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "finite": finite,
+            "hbm_ceiling_cand_epochs_per_s_per_gpu": peak * 1e9 / (steps_tr * cnt["train_bytes"] + steps_dv * cnt["eval_bytes"])}))
+    if world > 1:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

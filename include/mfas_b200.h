@@ -1,0 +1,179 @@
+/*
+ * mfas_b200.h -- C ABI of the B200-native MFAS candidate-training hot path.
+ *
+ * The reference (jperezrua/mfas) is pure Python/PyTorch and has no FFI; the seam this library
+ * sits behind is the function-valued plug-in entry of the search driver,
+ *     dataset_searchmethods['train_sampled_fun']      models/searchable.py:57,90,120
+ * i.e. models/search/ntu_searchable.py::train_sampled_models (:23-102), plus the model class
+ * Searchable_Skeleton_Image_Net (:178-301) and models/search/train_searchable/ntu.py
+ * ::train_ntu_track_acc / test_ntu_track_acc (:14-125).  Each entry point below cites the
+ * reference code it replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *  - plain C types only; every pointer named d_* or documented "device" is a DEVICE pointer
+ *    owned by the caller (a torch tensor); the library never frees or retains it beyond the
+ *    lifetime of the handle it was bound to;
+ *  - every launch function takes a cudaStream_t (passed as void*) and is asynchronous on it;
+ *  - return value: 0 = MFAS_OK, negative = error; mfas_last_error() gives the message for the
+ *    calling thread; no C++ exception crosses the ABI;
+ *  - one host thread per handle at a time.
+ */
+#ifndef MFAS_B200_H_
+#define MFAS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFAS_ABI_VERSION 1
+
+#define MFAS_MAX_LAYERS 8     /* fusion steps per candidate (reference max_fusions default 4)   */
+#define MFAS_MAX_BATCH 128    /* rows per batch (BASELINE configs use 8, 64, 128)               */
+#define MFAS_MAX_HIDDEN 256   /* inner_representation_size                                       */
+#define MFAS_MAX_CLASSES 64   /* num_outputs (60 NTU)                                            */
+#define MFAS_NUM_TAPS 4       /* backbone taps per modality, ntu_searchable.py:291-292           */
+
+enum {
+  MFAS_OK = 0,
+  MFAS_ERR_INVALID = -1,      /* bad argument / unsupported shape */
+  MFAS_ERR_CUDA = -2,         /* a CUDA runtime call failed */
+  MFAS_ERR_UNSUPPORTED = -3,  /* recognised but not built (e.g. a layer recipe the reference lacks) */
+  MFAS_ERR_NOMEM = -4,
+  MFAS_ERR_UNBOUND = -5       /* a candidate of the group has no arenas bound */
+};
+
+enum {
+  MFAS_FLAG_BN = 1,        /* args.batchnorm : Linear -> act -> BatchNorm1d     (ntu_searchable.py:274-282) */
+  MFAS_FLAG_DROPOUT = 2,   /* args.drpt>1e-10: ... -> Dropout(p)                (ntu_searchable.py:274-279) */
+  MFAS_FLAG_ALPHAS = 4,    /* args.alphas    : AlphaScalarMultiplication gate   (aux_models.py:94-111)      */
+  MFAS_FLAG_MULTITASK = 8  /* args.multitask : + cached backbone logits         (train_searchable/ntu.py:59-61) */
+};
+
+enum { MFAS_ACT_RELU = 0, MFAS_ACT_SIGMOID = 1, MFAS_ACT_LRELU = 2 };  /* conf[:,2], ntu_searchable.py:267-272 */
+
+/* One split of the feature cache (replaces the backbone forward, ntu_searchable.py:211-225).
+ * Tap t of a modality is a row-major [n_rows, d] fp32 matrix with leading dimension ld (floats). */
+typedef struct mfas_cache_desc {
+  int64_t n_rows;
+  const float* ske[MFAS_NUM_TAPS];
+  const float* rgb[MFAS_NUM_TAPS];
+  int64_t ske_ld[MFAS_NUM_TAPS];
+  int64_t rgb_ld[MFAS_NUM_TAPS];
+  int32_t d_ske[MFAS_NUM_TAPS];
+  int32_t d_rgb[MFAS_NUM_TAPS];
+  const int64_t* labels;     /* [n_rows] */
+  const float* logit_rgb;    /* [n_rows, C] backbone logits (multitask) or NULL */
+  const float* logit_ske;
+} mfas_cache_desc;
+
+/* Where each tensor of one candidate lives inside its flat fp32 arenas.
+ * Parameter arena (same offsets index the Adam m / v arenas and the optional grad arena):
+ *   fusion_layers.l.0.weight [H,K_l] | .0.bias [H] | .2.weight [H] | .2.bias [H]   (l = 0..L-1)
+ *   central_classifier.weight [C,H] | .bias [C] | alphas.l.alpha_x [1] (padded to 4)
+ * Buffer arena: fusion_layers.l.2.running_mean [H] | running_var [H].
+ * Offsets are in floats and 16-byte aligned.  State-dict names: SURVEY.md section 4. */
+typedef struct mfas_layout {
+  int32_t L, H, C, flags;
+  int32_t conf[MFAS_MAX_LAYERS][3];   /* [ske tap, rgb tap, activation] per fusion step */
+  int32_t d_ske[MFAS_MAX_LAYERS];     /* width of the selected taps */
+  int32_t d_rgb[MFAS_MAX_LAYERS];
+  int32_t K[MFAS_MAX_LAYERS];         /* Linear in_features = d_ske + d_rgb + (l>0)*H, ntu_searchable.py:261-264 */
+  int64_t off_W[MFAS_MAX_LAYERS];
+  int64_t off_b[MFAS_MAX_LAYERS];
+  int64_t off_gamma[MFAS_MAX_LAYERS]; /* -1 when no BN */
+  int64_t off_beta[MFAS_MAX_LAYERS];
+  int64_t off_alpha[MFAS_MAX_LAYERS];
+  int64_t off_Wc, off_bc;
+  int64_t n_params;                   /* floats in the parameter arena */
+  int64_t off_rm[MFAS_MAX_LAYERS];    /* -1 when no BN */
+  int64_t off_rv[MFAS_MAX_LAYERS];
+  int64_t n_bufs;                     /* floats in the buffer arena (>= 4) */
+} mfas_layout;
+
+/* Arenas of one candidate; all device pointers, caller-owned (views of torch tensors, so that
+ * state_dict() stays PyTorch-native). grad may be NULL (gradients then never touch HBM). */
+typedef struct mfas_arenas {
+  float* params;      /* [n_params] */
+  float* adam_m;      /* [n_params] exp_avg      */
+  float* adam_v;      /* [n_params] exp_avg_sq   */
+  float* grad;        /* [n_params] or NULL: raw dL/dp of the last train step (parity tests)   */
+  float* bufs;        /* [n_bufs]   BN running stats */
+  int64_t* nbt;       /* [L] num_batches_tracked      */
+} mfas_arenas;
+
+typedef struct mfas_adam_hparams {   /* torch.optim.Adam(params, lr, weight_decay=1e-4), ntu_searchable.py:65 */
+  float beta1, beta2, eps, weight_decay;
+} mfas_adam_hparams;
+
+typedef struct mfas_run_args {       /* one train_ntu_track_acc run for every candidate of a group */
+  int32_t n_epochs;
+  int32_t batch;                     /* args.batchsize; last batch of a pass may be short (drop_last=False) */
+  const int32_t* perm_train;         /* device [n_cand][n_epochs][n_train] row order of each train pass */
+  const int32_t* perm_dev;           /* device [n_cand][n_epochs][n_dev]  or NULL = identity */
+  const float* step_size;            /* HOST [n_epochs*ceil(n_train/batch)]: lr_t / (1-beta1^t), formed in fp64 */
+  const float* bc2_sqrt;             /* HOST, same length: sqrt(1-beta2^t) */
+  int64_t adam_t0;                   /* optimiser steps taken before this run */
+  double* stats;                     /* device [n_cand][n_epochs][4]: train loss sum, train correct, dev loss sum, dev correct */
+  double* best_acc;                  /* device [n_cand] best dev accuracy (strict >, starts at 0) */
+  int32_t* best_epoch;               /* device [n_cand] epoch of best_acc or -1 */
+} mfas_run_args;
+
+typedef struct mfas_group* mfas_group_t;
+
+/* ---- host-only helpers (no GPU needed) ---------------------------------------------------- */
+int mfas_abi_version(void);
+const char* mfas_last_error(void);
+
+/* Layout of one candidate. conf: [L][3] ints. Mirrors _create_fc_layers / _create_alphas
+ * (ntu_searchable.py:258-296). Fails with MFAS_ERR_UNSUPPORTED for drpt<1e-10 && !batchnorm, the
+ * combination for which the reference has no layer recipe (UnboundLocalError). */
+int mfas_plan_layout(int32_t L, const int32_t* conf, int32_t H, int32_t C, int32_t flags,
+                     const int32_t d_ske[MFAS_NUM_TAPS], const int32_t d_rgb[MFAS_NUM_TAPS],
+                     mfas_layout* out);
+
+/* Algorithmic bytes / flops of one step; out[0..3] = train bytes,
+ * eval bytes, fwd flops, bwd flops. */
+int mfas_algorithmic_counts(const mfas_layout* lay, int32_t batch, double out[4]);
+
+/* ---- group of candidates trained together on one device ------------------------------------
+ * Replaces the per-candidate construct/.to(device) of train_sampled_models (ntu_searchable.py:38-72). */
+int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layout* layouts, int32_t batch_max,
+                      float dropout_p, uint32_t dropout_seed, const int32_t* cand_ids /* [n_cand] or NULL */,
+                      mfas_group_t* out);
+int mfas_group_destroy(mfas_group_t g);
+int mfas_group_bind(mfas_group_t g, int32_t cand, const mfas_arenas* arenas);
+int mfas_group_set_adam(mfas_group_t g, const mfas_adam_hparams* hp);
+int mfas_group_num_launches(mfas_group_t g, int64_t* out);   /* kernels launched through g so far */
+
+/* Forward of every candidate over one batch: Searchable_Skeleton_Image_Net.forward
+ * (ntu_searchable.py:206-247) given cached taps. rows: device int32 row ids, candidate c reads
+ * rows + c*rows_stride (stride 0 = shared batch). train!=0: BN batch statistics + running-stat
+ * update (+dropout, keyed by step). d_logits: [n_cand][batch_max][C] or NULL.
+ * d_loss / d_correct: [n_cand] mean CE loss and #correct of the batch, or NULL. */
+int mfas_forward(mfas_group_t g, const mfas_cache_desc* cache, const int32_t* d_rows, int64_t rows_stride,
+                 int32_t n_rows, int32_t train, int64_t step, float* d_logits, float* d_loss,
+                 int32_t* d_correct, void* stream);
+
+/* One optimiser step of every candidate: forward + CE + hand-derived backward + Adam(L2)
+ * (train_searchable/ntu.py:46-69). step_size = lr/(1-beta1^t), bc2_sqrt = sqrt(1-beta2^t). */
+int mfas_train_step(mfas_group_t g, const mfas_cache_desc* cache, const int32_t* d_rows, int64_t rows_stride,
+                    int32_t n_rows, float step_size, float bc2_sqrt, int64_t step, float* d_logits,
+                    float* d_loss, int32_t* d_correct, void* stream);
+
+/* The production path: num_epochs x (train pass + dev pass) for every candidate, best-dev
+ * snapshot and final rollback, nothing returns to the host in between
+ * (train_searchable/ntu.py:14-89). */
+int mfas_train_run(mfas_group_t g, const mfas_cache_desc* train, const mfas_cache_desc* dev,
+                   const mfas_run_args* args, void* stream);
+
+/* Accuracy pass in eval mode (test_ntu_track_acc, train_searchable/ntu.py:92-125).
+ * d_perm: [n_cand][n_rows] or NULL = identity. d_out: [n_cand][2] loss sum, #correct. */
+int mfas_eval_pass(mfas_group_t g, const mfas_cache_desc* cache, const int32_t* d_perm, int32_t batch,
+                   double* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFAS_B200_H_ */

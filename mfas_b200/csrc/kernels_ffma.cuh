@@ -1,0 +1,505 @@
+// Engine "ffma": plain fp32 CUDA-core kernels, one launch per stage, batched over candidates
+// (blockIdx.y = candidate).  Bit-for-bit deterministic (fixed-order reductions, no atomics).
+// This is the first correct CUDA path and the bisecting reference for the tcgen05 engine.
+//
+// Per train step:  L x k_fusion_fwd  ->  k_head  ->  L x (k_dz -> k_fusion_bwd)
+// Reference arithmetic: /root/reference/models/search/ntu_searchable.py:228-242 (forward),
+// models/search/train_searchable/ntu.py:53-69 (loss, backward via autograd, Adam step).
+#pragma once
+#include "common.cuh"
+
+namespace mfas {
+
+constexpr int kThreads = 256;
+constexpr int FWD_HT = 16;            // output columns per CTA
+constexpr int FWD_KC = 32;            // K chunk (floats)
+constexpr int FWD_LD = FWD_KC + 4;    // padded smem row, keeps 16-byte alignment
+constexpr int BWD_KT = 32;            // weight columns per CTA in the backward
+
+// ---------------------------------------------------------------------------------------------
+// K1: fused fusion step forward.
+//   x = concat(ske_tap[rows], rgb_tap[rows], h_{l-1})   (gathered on the fly, never materialised)
+//   z = x W^T + b ; a = phi(z) ; h = BN(a) [; dropout]
+// CTA = all batch rows x 16 output columns, so BatchNorm statistics stay inside the CTA.
+// ---------------------------------------------------------------------------------------------
+template <bool TRAIN>
+__global__ void __launch_bounds__(kThreads)
+k_fusion_fwd(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int layer, int bmax,
+             uint32_t drop_seed, float drop_p, uint32_t step) {
+  const int cand = blockIdx.y;
+  const DCand& cd = cands[cand];
+  if (layer >= cd.L) return;
+  const int H = cd.H;
+  const int col0 = blockIdx.x * FWD_HT;
+  if (col0 >= H) return;
+  const DLayer& ly = cd.layer[layer];
+  const int nrows = batch.n_rows;
+  const int tid = threadIdx.x;
+
+  __shared__ __align__(16) float Xs[MFAS_MAX_BATCH][FWD_LD];
+  __shared__ __align__(16) float Ws[FWD_HT][FWD_LD];
+  __shared__ float red[16][FWD_HT + 1];
+  __shared__ int rowid[MFAS_MAX_BATCH];
+
+  for (int r = tid; r < MFAS_MAX_BATCH; r += kThreads) rowid[r] = r < nrows ? batch_row(batch, cand, r) : 0;
+  __syncthreads();
+
+  // the three concat sources, in the reference's column order [ske | rgb | hidden]
+  const float* seg_ptr[3];
+  long long seg_ld[3];
+  int seg_w[3];
+  bool seg_gather[3];
+  seg_ptr[0] = cache.ske[ly.ske_tap]; seg_ld[0] = cache.ske_ld[ly.ske_tap]; seg_w[0] = ly.d_ske; seg_gather[0] = true;
+  seg_ptr[1] = cache.rgb[ly.rgb_tap]; seg_ld[1] = cache.rgb_ld[ly.rgb_tap]; seg_w[1] = ly.d_rgb; seg_gather[1] = true;
+  seg_ptr[2] = layer > 0 ? cd.hid + (long long)(layer - 1) * bmax * H : nullptr;
+  seg_ld[2] = H; seg_w[2] = ly.d_hid; seg_gather[2] = false;
+  int nch[3];
+  for (int s = 0; s < 3; ++s) nch[s] = (seg_w[s] + FWD_KC - 1) / FWD_KC;
+  const int nchunks = nch[0] + nch[1] + nch[2];
+  const float* Wbase = cd.p + ly.oW;
+  const int K = ly.K;
+
+  // register staging of the next chunk (global loads in flight while the current chunk computes)
+  float4 xr[4];
+  float4 wr;
+  auto load_chunk = [&](int ci) {
+    int s = 0, c = ci;
+    if (c >= nch[0]) { c -= nch[0]; s = 1; if (c >= nch[1]) { c -= nch[1]; s = 2; } }
+    const int k0 = c * FWD_KC;
+    const int kw = min(FWD_KC, seg_w[s] - k0);
+    int kglob = k0;
+    if (s >= 1) kglob += seg_w[0];
+    if (s >= 2) kglob += seg_w[1];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + kThreads * i;
+      const int r = idx >> 3, c4 = (idx & 7) * 4;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nrows && c4 < kw) {
+        const long long row = seg_gather[s] ? (long long)rowid[r] : (long long)r;
+        val = __ldg(reinterpret_cast<const float4*>(seg_ptr[s] + row * seg_ld[s] + k0 + c4));
+      }
+      xr[i] = val;
+    }
+    wr = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < FWD_HT * 8) {
+      const int hr = tid >> 3, c4 = (tid & 7) * 4;
+      if (col0 + hr < H && c4 < kw)
+        wr = *reinterpret_cast<const float4*>(Wbase + (long long)(col0 + hr) * K + kglob + c4);
+    }
+  };
+  auto store_chunk = [&]() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + kThreads * i;
+      *reinterpret_cast<float4*>(&Xs[idx >> 3][(idx & 7) * 4]) = xr[i];
+    }
+    if (tid < FWD_HT * 8) *reinterpret_cast<float4*>(&Ws[tid >> 3][(tid & 7) * 4]) = wr;
+  };
+
+  const int col = tid & (FWD_HT - 1);
+  const int rg = tid >> 4;                       // 16 row groups; thread owns rows rg + 16*i
+  const int nr = (nrows + 15) >> 4;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+  load_chunk(0);
+  for (int ci = 0; ci < nchunks; ++ci) {
+    store_chunk();
+    __syncthreads();
+    if (ci + 1 < nchunks) load_chunk(ci + 1);
+#pragma unroll
+    for (int kk = 0; kk < FWD_KC; kk += 4) {
+      const float4 w = *reinterpret_cast<const float4*>(&Ws[col][kk]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < nr) {
+          const float4 x = *reinterpret_cast<const float4*>(&Xs[rg + 16 * i][kk]);
+          acc[i] = fmaf(x.x, w.x, acc[i]);
+          acc[i] = fmaf(x.y, w.y, acc[i]);
+          acc[i] = fmaf(x.z, w.z, acc[i]);
+          acc[i] = fmaf(x.w, w.w, acc[i]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: bias, activation, BatchNorm over the batch, dropout -------------------------
+  const int c = col0 + col;
+  const bool cvalid = c < H;
+  const float bias = cvalid ? cd.p[ly.ob + c] : 0.f;
+  const bool bn = (cd.flags & MFAS_FLAG_BN) != 0;
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = rg + 16 * i;
+    a[i] = (r < nrows && cvalid) ? act_fwd(acc[i] + bias, ly.act) : 0.f;
+  }
+  float mean = 0.f, var = 1.f, istd = 1.f, gamma = 1.f, beta = 0.f;
+  if (bn) {
+    if (TRAIN) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (rg + 16 * i < nrows) s += a[i];
+      red[rg][col] = s;
+      __syncthreads();
+      float tot = 0.f;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) tot += red[g][col];
+      mean = tot / (float)nrows;
+      __syncthreads();
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (rg + 16 * i < nrows) { const float d = a[i] - mean; q = fmaf(d, d, q); }
+      red[rg][col] = q;
+      __syncthreads();
+      tot = 0.f;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) tot += red[g][col];
+      var = tot / (float)nrows;
+    } else if (cvalid) {
+      mean = cd.bufs[ly.orm + c];
+      var = cd.bufs[ly.orv + c];
+    }
+    istd = 1.f / sqrtf(var + kBnEps);
+    if (cvalid) { gamma = cd.p[ly.og + c]; beta = cd.p[ly.obe + c]; }
+    if (TRAIN && rg == 0 && cvalid) {
+      cd.mu[layer * H + c] = mean;
+      cd.invstd[layer * H + c] = istd;
+      const float n = (float)nrows;
+      float& rm = cd.bufs[ly.orm + c];
+      float& rv = cd.bufs[ly.orv + c];
+      rm = (1.f - kBnMomentum) * rm + kBnMomentum * mean;
+      rv = (1.f - kBnMomentum) * rv + kBnMomentum * (var * (n / (n - 1.f)));
+      if (c == 0) cd.nbt[layer] += 1;
+    }
+  }
+  const bool drop = TRAIN && (cd.flags & MFAS_FLAG_DROPOUT);
+  const uint32_t dkey = drop ? dropout_key(drop_seed, (uint32_t)cd.cand_id, step, (uint32_t)layer) : 0u;
+  const float dscale = drop ? 1.f / (1.f - drop_p) : 1.f;
+  float* actp = cd.act + (long long)layer * bmax * H;
+  float* hidp = cd.hid + (long long)layer * bmax * H;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = rg + 16 * i;
+    if (r < nrows && cvalid) {
+      float h = bn ? (a[i] - mean) * istd * gamma + beta : a[i];
+      if (drop) h = dropout_keep(dkey, (uint32_t)(r * H + c), drop_p) ? h * dscale : 0.f;
+      if (TRAIN) actp[r * H + c] = a[i];
+      hidp[r * H + c] = h;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: classifier + softmax cross-entropy (+ its backward and the classifier's Adam step).
+// One CTA per candidate.  dynamic smem: hs[bmax][H] | wcs[C][H+1] | lg[bmax][C+1] | rowloss[bmax]
+// ---------------------------------------------------------------------------------------------
+struct HeadOut {
+  float* logits;          // [n_cand][bmax][C] or null
+  float* loss;            // [n_cand] or null
+  int* correct;           // [n_cand] or null
+  double* stats;          // accumulators or null: stats[cand*stride + off] += loss*n, [+1] += correct
+  long long stat_stride, stat_off;
+};
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(kThreads)
+k_head(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, AdamH adam, float step_size,
+       float bc2_sqrt, HeadOut out) {
+  extern __shared__ __align__(16) float smem[];
+  const int cand = blockIdx.x;
+  const DCand& cd = cands[cand];
+  const int H = cd.H, C = cd.C, nrows = batch.n_rows, tid = threadIdx.x;
+  float* hs = smem;                         // [bmax][H]
+  float* wcs = hs + bmax * H;               // [C][H+1]
+  float* lg = wcs + C * (H + 1);            // [bmax][C+1]
+  float* rowloss = lg + bmax * (C + 1);     // [bmax]
+  int* rowok = reinterpret_cast<int*>(rowloss + bmax);   // [bmax]
+  int* lab = rowok + bmax;                                // [bmax]
+
+  const float* hl = cd.hid + (long long)(cd.L - 1) * bmax * H;
+  for (int i = tid; i < nrows * H; i += kThreads) hs[i] = hl[i];
+  const float* Wc = cd.p + cd.oWc;
+  for (int i = tid; i < C * H; i += kThreads) wcs[(i / H) * (H + 1) + (i % H)] = Wc[i];
+  for (int r = tid; r < nrows; r += kThreads) lab[r] = (int)cache.labels[batch_row(batch, cand, r)];
+  __syncthreads();
+
+  // logits = h W_c^T + b_c                                    (ntu_searchable.py:242)
+  for (int i = tid; i < nrows * C; i += kThreads) {
+    const int b = i / C, c = i % C;
+    float s = 0.f;
+    const float* hp = hs + b * H;
+    const float* wp = wcs + c * (H + 1);
+    for (int h = 0; h < H; ++h) s = fmaf(hp[h], wp[h], s);
+    s += cd.p[cd.obc + c];
+    lg[b * (C + 1) + c] = s;
+    cd.logits[b * C + c] = s;
+    if (out.logits) out.logits[((long long)cand * bmax + b) * C + c] = s;
+  }
+  __syncthreads();
+
+  // per-row log-softmax, NLL, argmax (first maximum), dlogits = (softmax - onehot)/n
+  if (tid < nrows) {
+    float* row = lg + tid * (C + 1);
+    float mx = row[0];
+    int am = 0;
+    for (int c = 1; c < C; ++c) if (row[c] > mx) { mx = row[c]; am = c; }
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(row[c] - mx);
+    const float lse = logf(se);
+    const int y = lab[tid];
+    rowloss[tid] = -((row[y] - mx) - lse);
+    rowok[tid] = (am == y) ? 1 : 0;
+    if (TRAIN) {
+      const float inv_n = 1.f / (float)nrows;
+      for (int c = 0; c < C; ++c) {
+        float p = expf((row[c] - mx) - lse);
+        if (c == y) p -= 1.f;
+        row[c] = p * inv_n;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float ls = 0.f;
+    int ok = 0;
+    for (int r = 0; r < nrows; ++r) { ls += rowloss[r]; ok += rowok[r]; }
+    const float mean_loss = ls / (float)nrows;                    // CrossEntropyLoss(reduction='mean')
+    if (out.loss) out.loss[cand] = mean_loss;
+    if (out.correct) out.correct[cand] = ok;
+    if (out.stats) {                                              // running_loss += loss.item()*B (ntu.py:72-73)
+      double* st = out.stats + (long long)cand * out.stat_stride + out.stat_off;
+      st[0] += (double)mean_loss * (double)nrows;
+      st[1] += (double)ok;
+    }
+  }
+  if (!TRAIN) return;
+
+  // dh_L = dlogits W_c  (uses the pre-update classifier held in smem)
+  float* dhp = cd.dh + (long long)(cd.L - 1) * bmax * H;
+  for (int i = tid; i < nrows * H; i += kThreads) {
+    const int b = i / H, h = i % H;
+    float s = 0.f;
+    const float* dl = lg + b * (C + 1);
+    for (int c = 0; c < C; ++c) s = fmaf(dl[c], wcs[c * (H + 1) + h], s);
+    dhp[i] = s;
+  }
+  // dW_c = dlogits^T h_L  -> Adam ;  db_c = sum_b dlogits -> Adam
+  for (int i = tid; i < C * H; i += kThreads) {
+    const int c = i / H, h = i % H;
+    float g = 0.f;
+    for (int b = 0; b < nrows; ++b) g = fmaf(lg[b * (C + 1) + c], hs[b * H + h], g);
+    const long long o = cd.oWc + i;
+    if (cd.grad) cd.grad[o] = g;
+    float p = cd.p[o], m = cd.m[o], v = cd.v[o];
+    adam_update(g, p, m, v, adam, step_size, bc2_sqrt);
+    cd.p[o] = p; cd.m[o] = m; cd.v[o] = v;
+  }
+  for (int c = tid; c < C; c += kThreads) {
+    float g = 0.f;
+    for (int b = 0; b < nrows; ++b) g += lg[b * (C + 1) + c];
+    const long long o = cd.obc + c;
+    if (cd.grad) cd.grad[o] = g;
+    float p = cd.p[o], m = cd.m[o], v = cd.v[o];
+    adam_update(g, p, m, v, adam, step_size, bc2_sqrt);
+    cd.p[o] = p; cd.m[o] = m; cd.v[o] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2a: dL/dh_l -> dL/dz_l  (dropout mask, BatchNorm backward, activation backward), plus the
+// gradients and Adam steps of the per-column vectors b_l, gamma_l, beta_l.
+// CTA = 32 columns x 8 row groups.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_dz(const DCand* __restrict__ cands, int layer, int nrows, int bmax, AdamH adam, float step_size, float bc2_sqrt,
+     uint32_t drop_seed, float drop_p, uint32_t step) {
+  const DCand& cd = cands[blockIdx.y];
+  if (layer >= cd.L) return;
+  const int H = cd.H;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  if (blockIdx.x * 32 >= H) return;
+  const bool cvalid = c < H;
+  const int col = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const DLayer& ly = cd.layer[layer];
+  const bool bn = (cd.flags & MFAS_FLAG_BN) != 0;
+  const bool drop = (cd.flags & MFAS_FLAG_DROPOUT) != 0;
+  const uint32_t dkey = drop ? dropout_key(drop_seed, (uint32_t)cd.cand_id, step, (uint32_t)layer) : 0u;
+  const float dscale = drop ? 1.f / (1.f - drop_p) : 1.f;
+  const float* dhp = cd.dh + (long long)layer * bmax * H;
+  const float* actp = cd.act + (long long)layer * bmax * H;
+  __shared__ float red1[8][33], red2[8][33];
+
+  auto dh_at = [&](int r) {
+    float d = dhp[r * H + c];
+    if (drop) d = dropout_keep(dkey, (uint32_t)(r * H + c), drop_p) ? d * dscale : 0.f;
+    return d;
+  };
+  float mu = 0.f, istd = 1.f, gam = 1.f, m1 = 0.f, m2 = 0.f, S1 = 0.f, S2 = 0.f;
+  if (bn) {
+    if (cvalid) { mu = cd.mu[layer * H + c]; istd = cd.invstd[layer * H + c]; gam = cd.p[ly.og + c]; }
+    float s1 = 0.f, s2 = 0.f;
+    if (cvalid)
+      for (int r = rg; r < nrows; r += 8) {
+        const float d = dh_at(r);
+        const float ah = (actp[r * H + c] - mu) * istd;
+        s1 += d;
+        s2 = fmaf(d, ah, s2);
+      }
+    red1[rg][col] = s1; red2[rg][col] = s2;
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < 8; ++g) { S1 += red1[g][col]; S2 += red2[g][col]; }
+    m1 = S1 / (float)nrows; m2 = S2 / (float)nrows;
+    __syncthreads();
+  }
+  float sdz = 0.f;
+  if (cvalid)
+    for (int r = rg; r < nrows; r += 8) {
+      const float d = dh_at(r);
+      const float a = actp[r * H + c];
+      float da = d;
+      if (bn) { const float ah = (a - mu) * istd; da = gam * istd * (d - m1 - ah * m2); }
+      const float dz = da * act_bwd(a, ly.act);
+      cd.dz[r * H + c] = dz;
+      sdz += dz;
+    }
+  red1[rg][col] = sdz;
+  __syncthreads();
+  if (rg == 0 && cvalid) {
+    float db = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) db += red1[g][col];
+    auto upd = [&](long long o, float g) {
+      if (cd.grad) cd.grad[o] = g;
+      float p = cd.p[o], m = cd.m[o], v = cd.v[o];
+      adam_update(g, p, m, v, adam, step_size, bc2_sqrt);
+      cd.p[o] = p; cd.m[o] = m; cd.v[o] = v;
+    };
+    upd(ly.ob + c, db);
+    if (bn) { upd(ly.og + c, S2); upd(ly.obe + c, S1); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2b + K4: dW_l[:, cols] = dz^T x[:, cols] with the Adam(L2) update fused into the epilogue
+// (the gradient never reaches HBM), and for the hidden columns dh_{l-1} = dz W_l[:, cols]
+// computed from the pre-update weights.  Feature columns need no dX.
+// CTA = 32 weight columns x all H rows.  dynamic smem: dzs[bmax][H] | Xs[bmax][32] | Wsm[H][32]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_fusion_bwd(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int layer, int bmax, AdamH adam,
+             float step_size, float bc2_sqrt) {
+  extern __shared__ __align__(16) float smem[];
+  const int cand = blockIdx.y;
+  const DCand& cd = cands[cand];
+  if (layer >= cd.L) return;
+  const DLayer& ly = cd.layer[layer];
+  const int K = ly.K, H = cd.H;
+  const int kc0 = blockIdx.x * BWD_KT;
+  if (kc0 >= K) return;
+  const int kw = min(BWD_KT, K - kc0);
+  const int nrows = batch.n_rows, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* dzs = smem;                   // [bmax][H]
+  float* Xs = dzs + bmax * H;          // [bmax][32]
+  float* Wsm = Xs + bmax * BWD_KT;     // [H][32]
+
+  for (int i = tid * 4; i < nrows * H; i += kThreads * 4)
+    *reinterpret_cast<float4*>(dzs + i) = *reinterpret_cast<const float4*>(cd.dz + i);
+
+  // which concat source do these columns come from?
+  const float* src; long long ld; int k_local; bool gather = true;
+  const int fs = ly.d_ske, fr = ly.d_rgb;
+  if (kc0 < fs) { src = cache.ske[ly.ske_tap]; ld = cache.ske_ld[ly.ske_tap]; k_local = kc0; }
+  else if (kc0 < fs + fr) { src = cache.rgb[ly.rgb_tap]; ld = cache.rgb_ld[ly.rgb_tap]; k_local = kc0 - fs; }
+  else { src = cd.hid + (long long)(layer - 1) * bmax * H; ld = H; k_local = kc0 - fs - fr; gather = false; }
+  const bool hidden = !gather;
+  for (int r = warp; r < nrows; r += 8) {
+    const long long row = gather ? (long long)batch_row(batch, cand, r) : (long long)r;
+    Xs[r * BWD_KT + lane] = lane < kw ? __ldg(src + row * ld + k_local + lane) : 0.f;
+  }
+  float* Wg = cd.p + ly.oW + kc0;
+  if (hidden)
+    for (int h = warp; h < H; h += 8) Wsm[h * BWD_KT + lane] = lane < kw ? Wg[(long long)h * K + lane] : 0.f;
+  __syncthreads();
+
+  if (hidden) {   // dh_{l-1}[b][k_local+lane] = sum_h dz[b][h] * W[h][kc0+lane]   (pre-update W)
+    float* dprev = cd.dh + (long long)(layer - 1) * bmax * H;
+    for (int b = warp; b < nrows; b += 8) {
+      float s = 0.f;
+      const float* dzr = dzs + b * H;
+      for (int h = 0; h < H; ++h) s = fmaf(dzr[h], Wsm[h * BWD_KT + lane], s);
+      if (lane < kw) dprev[b * H + k_local + lane] = s;
+    }
+  }
+
+  float* Mg = cd.m + ly.oW + kc0;
+  float* Vg = cd.v + ly.oW + kc0;
+  float* Gg = cd.grad ? cd.grad + ly.oW + kc0 : nullptr;
+  for (int h0 = warp * 16; h0 < H; h0 += 128) {
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int b = 0; b < nrows; ++b) {
+      const float x = Xs[b * BWD_KT + lane];
+      const float4* dz4 = reinterpret_cast<const float4*>(dzs + b * H + h0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 d = dz4[q];
+        acc[4 * q + 0] = fmaf(d.x, x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(d.y, x, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(d.z, x, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(d.w, x, acc[4 * q + 3]);
+      }
+    }
+    if (lane < kw) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const long long o = (long long)(h0 + i) * K + lane;
+        if (Gg) Gg[o] = acc[i];
+        float p = Wg[o], m = Mg[o], v = Vg[o];
+        adam_update(acc[i], p, m, v, adam, step_size, bc2_sqrt);
+        Wg[o] = p; Mg[o] = m; Vg[o] = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: best-dev bookkeeping (train_searchable/ntu.py:82-86): strict '>' on fp64 accuracy, then a
+// device-side snapshot of parameters + BN buffers; final rollback to the snapshot.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_best_update(int n_cand, const double* stats, long long stat_stride, long long stat_off,
+                              long long n_dev, int epoch, double* best_acc, int* best_epoch, int* improved) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cand) return;
+  const double acc = stats[(long long)c * stat_stride + stat_off + 1] / (double)n_dev;
+  if (acc > best_acc[c]) { best_acc[c] = acc; best_epoch[c] = epoch; improved[c] = 1; }
+  else improved[c] = 0;
+}
+
+// dir = 0: params -> best (when force or improved[c]);  dir = 1: best -> params
+__global__ void __launch_bounds__(kThreads)
+k_snapshot(const DCand* __restrict__ cands, const int* improved, int force, int dir) {
+  const DCand& cd = cands[blockIdx.y];
+  if (!force && !improved[blockIdx.y]) return;
+  float* src_p = dir ? cd.best_p : cd.p;
+  float* dst_p = dir ? cd.p : cd.best_p;
+  float* src_b = dir ? cd.best_bufs : cd.bufs;
+  float* dst_b = dir ? cd.bufs : cd.best_bufs;
+  const long long n4 = cd.n_params >> 2;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (long long)gridDim.x * kThreads)
+    reinterpret_cast<float4*>(dst_p)[i] = reinterpret_cast<const float4*>(src_p)[i];
+  if (blockIdx.x == 0) {
+    for (long long i = threadIdx.x; i < cd.n_bufs; i += kThreads) dst_b[i] = src_b[i];
+    if (threadIdx.x < cd.L) {
+      if (dir) cd.nbt[threadIdx.x] = cd.best_nbt[threadIdx.x];
+      else cd.best_nbt[threadIdx.x] = cd.nbt[threadIdx.x];
+    }
+  }
+}
+
+}  // namespace mfas

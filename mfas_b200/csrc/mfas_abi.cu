@@ -1,0 +1,465 @@
+// C ABI of the B200-native MFAS candidate-training hot path (see include/mfas_b200.h).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "kernels_ffma.cuh"
+
+using namespace mfas;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return fail(MFAS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+extern "C" int mfas_abi_version(void) { return MFAS_ABI_VERSION; }
+extern "C" const char* mfas_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------------
+// layout (host only)
+// ---------------------------------------------------------------------------------------------
+static inline int64_t align4(int64_t x) { return (x + 3) & ~int64_t(3); }
+
+extern "C" int mfas_plan_layout(int32_t L, const int32_t* conf, int32_t H, int32_t C, int32_t flags,
+                                const int32_t d_ske[MFAS_NUM_TAPS], const int32_t d_rgb[MFAS_NUM_TAPS],
+                                mfas_layout* out) {
+  if (!conf || !d_ske || !d_rgb || !out) return fail(MFAS_ERR_INVALID, "null argument");
+  if (L < 1 || L > MFAS_MAX_LAYERS) return fail(MFAS_ERR_INVALID, "L=%d outside [1,%d]", L, MFAS_MAX_LAYERS);
+  if (H < 16 || H > MFAS_MAX_HIDDEN || (H % 16) != 0)
+    return fail(MFAS_ERR_INVALID, "inner_representation_size=%d must be a multiple of 16 in [16,%d]", H, MFAS_MAX_HIDDEN);
+  if (C < 2 || C > MFAS_MAX_CLASSES) return fail(MFAS_ERR_INVALID, "num_outputs=%d outside [2,%d]", C, MFAS_MAX_CLASSES);
+  const bool bn = flags & MFAS_FLAG_BN, drop = flags & MFAS_FLAG_DROPOUT;
+  if (!bn && !drop)   // ntu_searchable.py:274-284: no branch assigns `op` -> UnboundLocalError
+    return fail(MFAS_ERR_UNSUPPORTED, "no layer recipe for drpt<1e-10 and batchnorm=False (reference raises UnboundLocalError)");
+  for (int t = 0; t < MFAS_NUM_TAPS; ++t)
+    if (d_ske[t] <= 0 || d_rgb[t] <= 0 || d_ske[t] % 32 || d_rgb[t] % 32)
+      return fail(MFAS_ERR_INVALID, "tap widths must be positive multiples of 32 (ske[%d]=%d rgb[%d]=%d)", t, d_ske[t], t, d_rgb[t]);
+  memset(out, 0, sizeof(*out));
+  out->L = L; out->H = H; out->C = C; out->flags = flags;
+  int64_t o = 0;
+  for (int l = 0; l < L; ++l) {
+    const int i = conf[3 * l + 0], j = conf[3 * l + 1], a = conf[3 * l + 2];
+    if (i < 0 || i >= MFAS_NUM_TAPS || j < 0 || j >= MFAS_NUM_TAPS)
+      return fail(MFAS_ERR_INVALID, "conf[%d] tap index out of range (%d,%d)", l, i, j);
+    if (a < 0 || a > 2) return fail(MFAS_ERR_INVALID, "conf[%d] activation %d not in {0,1,2}", l, a);
+    out->conf[l][0] = i; out->conf[l][1] = j; out->conf[l][2] = a;
+    out->d_ske[l] = d_ske[i]; out->d_rgb[l] = d_rgb[j];
+    out->K[l] = d_ske[i] + d_rgb[j] + (l > 0 ? H : 0);
+    out->off_W[l] = o; o += align4((int64_t)H * out->K[l]);
+    out->off_b[l] = o; o += align4(H);
+    if (bn) { out->off_gamma[l] = o; o += align4(H); out->off_beta[l] = o; o += align4(H); }
+    else { out->off_gamma[l] = -1; out->off_beta[l] = -1; }
+  }
+  out->off_Wc = o; o += align4((int64_t)C * H);
+  out->off_bc = o; o += align4(C);
+  for (int l = 0; l < L; ++l) { out->off_alpha[l] = o; o += 4; }
+  out->n_params = o;
+  int64_t b = 0;
+  for (int l = 0; l < L; ++l) {
+    if (bn) { out->off_rm[l] = b; b += align4(H); out->off_rv[l] = b; b += align4(H); }
+    else { out->off_rm[l] = -1; out->off_rv[l] = -1; }
+  }
+  out->n_bufs = b > 0 ? b : 4;
+  return MFAS_OK;
+}
+
+extern "C" int mfas_algorithmic_counts(const mfas_layout* lay, int32_t batch, double out[4]) {
+  if (!lay || !out) return fail(MFAS_ERR_INVALID, "null argument");
+  const double B = batch, H = lay->H, C = lay->C, L = lay->L;
+  double F_sel = 0, sumK = 0, P = 0;
+  for (int l = 0; l < lay->L; ++l) {
+    F_sel += lay->d_ske[l] + lay->d_rgb[l];
+    sumK += lay->K[l];
+    P += (double)lay->K[l] * H + H;
+  }
+  if (lay->flags & MFAS_FLAG_BN) P += 2 * H * L;
+  P += C * H + C;
+  out[0] = 4 * (B * F_sel + 6 * P) + 8 * B;      // train step bytes
+  out[1] = 4 * (B * F_sel + P) + 8 * B;          // eval step bytes
+  out[2] = 2 * B * (sumK * H + H * C);           // forward flops
+  out[3] = out[2] + 2 * B * H * H * (L - 1) + 2 * B * H * C;
+  return MFAS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// group
+// ---------------------------------------------------------------------------------------------
+struct mfas_group {
+  int device = 0, n_cand = 0, bmax = 0;
+  int Lmax = 0, Hmax = 0, Cmax = 0;
+  int Kmax[MFAS_MAX_LAYERS] = {0};
+  float drop_p = 0.f;
+  uint32_t drop_seed = 0;
+  AdamH adam;
+  std::vector<mfas_layout> lay;
+  std::vector<DCand> hc;          // host mirror of the device descriptors
+  std::vector<char> bound;
+  DCand* dc = nullptr;            // device descriptors
+  char* ws = nullptr;             // one workspace allocation
+  int* improved = nullptr;        // [n_cand]
+  bool dirty = true;
+  size_t smem_head = 0, smem_bwd = 0;
+  int64_t launches = 0;
+};
+
+static void set_adam(AdamH& a, float b1, float b2, float eps, float wd) {
+  a.beta1 = b1; a.beta2 = b2; a.eps = eps; a.wd = wd;
+  a.one_minus_beta1 = (float)(1.0 - (double)b1);
+  a.one_minus_beta2 = (float)(1.0 - (double)b2);
+}
+
+extern "C" int mfas_group_set_adam(mfas_group_t g, const mfas_adam_hparams* hp) {
+  if (!g || !hp) return fail(MFAS_ERR_INVALID, "null argument");
+  // torch passes python doubles: 1-beta is formed in fp64 and then rounded to fp32
+  set_adam(g->adam, hp->beta1, hp->beta2, hp->eps, hp->weight_decay);
+  return MFAS_OK;
+}
+
+extern "C" int mfas_group_destroy(mfas_group_t g) {
+  if (!g) return MFAS_OK;
+  DeviceGuard dg(g->device);
+  if (g->dc) cudaFree(g->dc);
+  if (g->ws) cudaFree(g->ws);
+  if (g->improved) cudaFree(g->improved);
+  delete g;
+  return MFAS_OK;
+}
+
+extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layout* layouts, int32_t batch_max,
+                                 float dropout_p, uint32_t dropout_seed, const int32_t* cand_ids,
+                                 mfas_group_t* out) {
+  if (!layouts || !out) return fail(MFAS_ERR_INVALID, "null argument");
+  if (n_cand < 1) return fail(MFAS_ERR_INVALID, "n_cand=%d", n_cand);
+  if (batch_max < 1 || batch_max > MFAS_MAX_BATCH)
+    return fail(MFAS_ERR_INVALID, "batch_max=%d outside [1,%d]", batch_max, MFAS_MAX_BATCH);
+  if (dropout_p < 0.f || dropout_p >= 1.f) return fail(MFAS_ERR_INVALID, "dropout p=%f outside [0,1)", dropout_p);
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(MFAS_ERR_INVALID, "device %d of %d", device, ndev);
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(MFAS_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+
+  mfas_group* g = new (std::nothrow) mfas_group();
+  if (!g) return fail(MFAS_ERR_NOMEM, "host allocation failed");
+  g->device = device; g->n_cand = n_cand; g->bmax = batch_max;
+  g->drop_p = dropout_p; g->drop_seed = dropout_seed;
+  set_adam(g->adam, 0.9f, 0.999f, 1e-8f, 1e-4f);
+  g->lay.assign(layouts, layouts + n_cand);
+  g->hc.resize(n_cand);
+  g->bound.assign(n_cand, 0);
+
+  // workspace carve-up
+  auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+  size_t total = 0;
+  std::vector<size_t> base(n_cand);
+  struct Off { size_t act, hid, dh, dz, mu, invstd, logits, best_p, best_bufs, best_nbt; };
+  std::vector<Off> off(n_cand);
+  for (int c = 0; c < n_cand; ++c) {
+    const mfas_layout& l = g->lay[c];
+    if (l.L < 1 || l.L > MFAS_MAX_LAYERS || l.H < 16 || l.H > MFAS_MAX_HIDDEN || l.H % 16 || l.C < 2 ||
+        l.C > MFAS_MAX_CLASSES || l.n_params <= 0) {
+      delete g;
+      return fail(MFAS_ERR_INVALID, "layout %d was not produced by mfas_plan_layout", c);
+    }
+    g->Lmax = l.L > g->Lmax ? l.L : g->Lmax;
+    g->Hmax = l.H > g->Hmax ? l.H : g->Hmax;
+    g->Cmax = l.C > g->Cmax ? l.C : g->Cmax;
+    for (int k = 0; k < l.L; ++k) g->Kmax[k] = l.K[k] > g->Kmax[k] ? l.K[k] : g->Kmax[k];
+    const size_t lbh = (size_t)l.L * batch_max * l.H * sizeof(float);
+    Off& o = off[c];
+    o.act = total; total += up(lbh);
+    o.hid = total; total += up(lbh);
+    o.dh = total; total += up(lbh);
+    o.dz = total; total += up((size_t)batch_max * l.H * sizeof(float));
+    o.mu = total; total += up((size_t)l.L * l.H * sizeof(float));
+    o.invstd = total; total += up((size_t)l.L * l.H * sizeof(float));
+    o.logits = total; total += up((size_t)batch_max * l.C * sizeof(float));
+    o.best_p = total; total += up((size_t)l.n_params * sizeof(float));
+    o.best_bufs = total; total += up((size_t)l.n_bufs * sizeof(float));
+    o.best_nbt = total; total += up((size_t)MFAS_MAX_LAYERS * sizeof(long long));
+  }
+  cudaError_t e = cudaMalloc(&g->ws, total);
+  if (e == cudaSuccess) e = cudaMemset(g->ws, 0, total);
+  if (e == cudaSuccess) e = cudaMalloc(&g->dc, sizeof(DCand) * n_cand);
+  if (e == cudaSuccess) e = cudaMalloc(&g->improved, sizeof(int) * n_cand);
+  if (e == cudaSuccess) e = cudaMemset(g->improved, 0, sizeof(int) * n_cand);
+  if (e != cudaSuccess) {
+    int code = fail(e == cudaErrorMemoryAllocation ? MFAS_ERR_NOMEM : MFAS_ERR_CUDA, "workspace allocation (%zu bytes): %s",
+                    total, cudaGetErrorString(e));
+    mfas_group_destroy(g);
+    return code;
+  }
+  for (int c = 0; c < n_cand; ++c) {
+    const mfas_layout& l = g->lay[c];
+    DCand& d = g->hc[c];
+    memset(&d, 0, sizeof(d));
+    d.L = l.L; d.H = l.H; d.C = l.C; d.flags = l.flags;
+    d.cand_id = cand_ids ? cand_ids[c] : c;
+    for (int k = 0; k < l.L; ++k) {
+      DLayer& y = d.layer[k];
+      y.ske_tap = l.conf[k][0]; y.rgb_tap = l.conf[k][1]; y.act = l.conf[k][2];
+      y.d_ske = l.d_ske[k]; y.d_rgb = l.d_rgb[k]; y.d_hid = k > 0 ? l.H : 0; y.K = l.K[k];
+      y.oW = l.off_W[k]; y.ob = l.off_b[k]; y.og = l.off_gamma[k]; y.obe = l.off_beta[k];
+      y.oalpha = l.off_alpha[k]; y.orm = l.off_rm[k]; y.orv = l.off_rv[k];
+    }
+    d.oWc = l.off_Wc; d.obc = l.off_bc; d.n_params = l.n_params; d.n_bufs = l.n_bufs;
+    const Off& o = off[c];
+    d.act = (float*)(g->ws + o.act); d.hid = (float*)(g->ws + o.hid); d.dh = (float*)(g->ws + o.dh);
+    d.dz = (float*)(g->ws + o.dz); d.mu = (float*)(g->ws + o.mu); d.invstd = (float*)(g->ws + o.invstd);
+    d.logits = (float*)(g->ws + o.logits); d.best_p = (float*)(g->ws + o.best_p);
+    d.best_bufs = (float*)(g->ws + o.best_bufs); d.best_nbt = (long long*)(g->ws + o.best_nbt);
+  }
+  // dynamic shared memory of the two big-smem kernels
+  g->smem_head = sizeof(float) * ((size_t)batch_max * g->Hmax + (size_t)g->Cmax * (g->Hmax + 1) +
+                                  (size_t)batch_max * (g->Cmax + 1) + batch_max) + sizeof(int) * 2 * batch_max;
+  g->smem_bwd = sizeof(float) * ((size_t)batch_max * g->Hmax + (size_t)batch_max * BWD_KT + (size_t)g->Hmax * BWD_KT);
+  const size_t lim = 227 * 1024;
+  if (g->smem_head > lim || g->smem_bwd > lim) {
+    int code = fail(MFAS_ERR_UNSUPPORTED, "shared memory need (%zu / %zu B) exceeds 227 KB", g->smem_head, g->smem_bwd);
+    mfas_group_destroy(g);
+    return code;
+  }
+  e = cudaFuncSetAttribute(k_head<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_head);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_head<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_head);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fusion_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bwd);
+  if (e != cudaSuccess) {
+    int code = fail(MFAS_ERR_CUDA, "cudaFuncSetAttribute: %s (is this an sm_100 device?)", cudaGetErrorString(e));
+    mfas_group_destroy(g);
+    return code;
+  }
+  *out = g;
+  return MFAS_OK;
+}
+
+extern "C" int mfas_group_bind(mfas_group_t g, int32_t cand, const mfas_arenas* a) {
+  if (!g || !a) return fail(MFAS_ERR_INVALID, "null argument");
+  if (cand < 0 || cand >= g->n_cand) return fail(MFAS_ERR_INVALID, "candidate %d of %d", cand, g->n_cand);
+  if (!a->params || !a->adam_m || !a->adam_v || !a->bufs || !a->nbt)
+    return fail(MFAS_ERR_INVALID, "params/adam_m/adam_v/bufs/nbt must be non-null");
+  const uintptr_t bits = (uintptr_t)a->params | (uintptr_t)a->adam_m | (uintptr_t)a->adam_v | (uintptr_t)a->bufs |
+                         (uintptr_t)a->grad;
+  if (bits & 15) return fail(MFAS_ERR_INVALID, "arenas must be 16-byte aligned");
+  DCand& d = g->hc[cand];
+  d.p = a->params; d.m = a->adam_m; d.v = a->adam_v; d.grad = a->grad; d.bufs = a->bufs;
+  d.nbt = (long long*)a->nbt;
+  g->bound[cand] = 1;
+  g->dirty = true;
+  return MFAS_OK;
+}
+
+extern "C" int mfas_group_num_launches(mfas_group_t g, int64_t* out) {
+  if (!g || !out) return fail(MFAS_ERR_INVALID, "null argument");
+  *out = g->launches;
+  return MFAS_OK;
+}
+
+static int sync_descriptors(mfas_group* g, cudaStream_t st) {
+  for (int c = 0; c < g->n_cand; ++c)
+    if (!g->bound[c]) return fail(MFAS_ERR_UNBOUND, "candidate %d has no arenas bound", c);
+  if (g->dirty) {
+    // pageable source: the copy is staged before the call returns, so hc may change afterwards
+    CUDA_TRY(cudaMemcpyAsync(g->dc, g->hc.data(), sizeof(DCand) * g->n_cand, cudaMemcpyHostToDevice, st));
+    g->dirty = false;
+  }
+  return MFAS_OK;
+}
+
+static int to_dcache(const mfas_group* g, const mfas_cache_desc* c, DCache* out) {
+  if (!c) return fail(MFAS_ERR_INVALID, "null cache");
+  if (c->n_rows <= 0 || !c->labels) return fail(MFAS_ERR_INVALID, "cache needs n_rows>0 and labels");
+  out->n_rows = c->n_rows;
+  for (int t = 0; t < MFAS_NUM_TAPS; ++t) {
+    if (!c->ske[t] || !c->rgb[t]) return fail(MFAS_ERR_INVALID, "cache tap %d is null", t);
+    if (((uintptr_t)c->ske[t] | (uintptr_t)c->rgb[t]) & 15 || c->ske_ld[t] % 4 || c->rgb_ld[t] % 4)
+      return fail(MFAS_ERR_INVALID, "cache taps must be 16-byte aligned with ld %% 4 == 0");
+    out->ske[t] = c->ske[t]; out->rgb[t] = c->rgb[t];
+    out->ske_ld[t] = c->ske_ld[t]; out->rgb_ld[t] = c->rgb_ld[t];
+  }
+  for (int k = 0; k < g->n_cand; ++k)
+    for (int l = 0; l < g->lay[k].L; ++l)
+      if (c->d_ske[g->lay[k].conf[l][0]] != g->lay[k].d_ske[l] || c->d_rgb[g->lay[k].conf[l][1]] != g->lay[k].d_rgb[l])
+        return fail(MFAS_ERR_INVALID, "cache tap widths differ from the layout of candidate %d step %d", k, l);
+  out->labels = (const long long*)c->labels;
+  out->logit_rgb = c->logit_rgb; out->logit_ske = c->logit_ske;
+  return MFAS_OK;
+}
+
+#define LAUNCH_CHECK(g)                                                                       \
+  do {                                                                                        \
+    ++(g)->launches;                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                                     \
+    if (e__ != cudaSuccess) return fail(MFAS_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+// one forward (+ optional backward/Adam) of every candidate over one batch
+static int launch_step(mfas_group* g, const DCache& cache, const BatchRef& batch, bool train, bool bn_train,
+                       float step_size, float bc2_sqrt, uint32_t step, const HeadOut& ho, cudaStream_t st) {
+  const dim3 fgrid((g->Hmax + FWD_HT - 1) / FWD_HT, g->n_cand);
+  for (int l = 0; l < g->Lmax; ++l) {
+    if (bn_train)
+      k_fusion_fwd<true><<<fgrid, kThreads, 0, st>>>(g->dc, cache, batch, l, g->bmax, g->drop_seed, g->drop_p, step);
+    else
+      k_fusion_fwd<false><<<fgrid, kThreads, 0, st>>>(g->dc, cache, batch, l, g->bmax, g->drop_seed, g->drop_p, step);
+    LAUNCH_CHECK(g);
+  }
+  if (train)
+    k_head<true><<<g->n_cand, kThreads, g->smem_head, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, ho);
+  else
+    k_head<false><<<g->n_cand, kThreads, g->smem_head, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, ho);
+  LAUNCH_CHECK(g);
+  if (!train) return MFAS_OK;
+  for (int l = g->Lmax - 1; l >= 0; --l) {
+    k_dz<<<dim3((g->Hmax + 31) / 32, g->n_cand), kThreads, 0, st>>>(g->dc, l, batch.n_rows, g->bmax, g->adam, step_size,
+                                                                  bc2_sqrt, g->drop_seed, g->drop_p, step);
+    LAUNCH_CHECK(g);
+    k_fusion_bwd<<<dim3((g->Kmax[l] + BWD_KT - 1) / BWD_KT, g->n_cand), kThreads, g->smem_bwd, st>>>(
+        g->dc, cache, batch, l, g->bmax, g->adam, step_size, bc2_sqrt);
+    LAUNCH_CHECK(g);
+  }
+  return MFAS_OK;
+}
+
+static int check_batch(const mfas_group* g, int n_rows, bool train) {
+  if (n_rows < 1 || n_rows > g->bmax) return fail(MFAS_ERR_INVALID, "n_rows=%d outside [1,%d]", n_rows, g->bmax);
+  if (train && n_rows < 2)
+    for (int c = 0; c < g->n_cand; ++c)
+      if (g->lay[c].flags & MFAS_FLAG_BN)   // torch: "Expected more than 1 value per channel when training"
+        return fail(MFAS_ERR_INVALID, "Expected more than 1 value per channel when training (batch of %d row)", n_rows);
+  return MFAS_OK;
+}
+
+extern "C" int mfas_forward(mfas_group_t g, const mfas_cache_desc* cache, const int32_t* d_rows, int64_t rows_stride,
+                            int32_t n_rows, int32_t train, int64_t step, float* d_logits, float* d_loss,
+                            int32_t* d_correct, void* stream) {
+  if (!g) return fail(MFAS_ERR_INVALID, "null group");
+  DeviceGuard dg(g->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = check_batch(g, n_rows, train != 0);
+  if (rc) return rc;
+  DCache dc;
+  if ((rc = to_dcache(g, cache, &dc))) return rc;
+  if ((rc = sync_descriptors(g, st))) return rc;
+  BatchRef b{d_rows, rows_stride, 0, n_rows};
+  HeadOut ho{d_logits, d_loss, d_correct, nullptr, 0, 0};
+  return launch_step(g, dc, b, false, train != 0, 0.f, 1.f, (uint32_t)step, ho, st);
+}
+
+extern "C" int mfas_train_step(mfas_group_t g, const mfas_cache_desc* cache, const int32_t* d_rows, int64_t rows_stride,
+                               int32_t n_rows, float step_size, float bc2_sqrt, int64_t step, float* d_logits,
+                               float* d_loss, int32_t* d_correct, void* stream) {
+  if (!g) return fail(MFAS_ERR_INVALID, "null group");
+  DeviceGuard dg(g->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = check_batch(g, n_rows, true);
+  if (rc) return rc;
+  DCache dc;
+  if ((rc = to_dcache(g, cache, &dc))) return rc;
+  if ((rc = sync_descriptors(g, st))) return rc;
+  BatchRef b{d_rows, rows_stride, 0, n_rows};
+  HeadOut ho{d_logits, d_loss, d_correct, nullptr, 0, 0};
+  return launch_step(g, dc, b, true, true, step_size, bc2_sqrt, (uint32_t)step, ho, st);
+}
+
+static int snapshot(mfas_group* g, int force, int dir, cudaStream_t st) {
+  k_snapshot<<<dim3(32, g->n_cand), kThreads, 0, st>>>(g->dc, g->improved, force, dir);
+  LAUNCH_CHECK(g);
+  return MFAS_OK;
+}
+
+extern "C" int mfas_train_run(mfas_group_t g, const mfas_cache_desc* train, const mfas_cache_desc* dev,
+                              const mfas_run_args* a, void* stream) {
+  if (!g || !a) return fail(MFAS_ERR_INVALID, "null argument");
+  DeviceGuard dg(g->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->n_epochs < 0 || a->batch < 1 || a->batch > g->bmax)
+    return fail(MFAS_ERR_INVALID, "n_epochs=%d batch=%d (group batch_max=%d)", a->n_epochs, a->batch, g->bmax);
+  if (!a->perm_train || !a->step_size || !a->bc2_sqrt || !a->stats || !a->best_acc || !a->best_epoch)
+    return fail(MFAS_ERR_INVALID, "perm_train/step_size/bc2_sqrt/stats/best_acc/best_epoch must be non-null");
+  DCache dtr, ddv;
+  int rc;
+  if ((rc = to_dcache(g, train, &dtr))) return rc;
+  if ((rc = to_dcache(g, dev, &ddv))) return rc;
+  const long long ntr = dtr.n_rows, ndv = ddv.n_rows;
+  const int B = a->batch;
+  const long long steps_tr = (ntr + B - 1) / B, steps_dv = (ndv + B - 1) / B;
+  const int last_tr = (int)(ntr - (steps_tr - 1) * B);
+  if ((rc = check_batch(g, last_tr, true))) return rc;
+  if ((rc = sync_descriptors(g, st))) return rc;
+
+  const int E = a->n_epochs;
+  CUDA_TRY(cudaMemsetAsync(a->stats, 0, sizeof(double) * 4 * (size_t)E * g->n_cand, st));
+  CUDA_TRY(cudaMemsetAsync(a->best_acc, 0, sizeof(double) * g->n_cand, st));
+  CUDA_TRY(cudaMemsetAsync(a->best_epoch, 0xFF, sizeof(int32_t) * g->n_cand, st));
+  if ((rc = snapshot(g, 1, 0, st))) return rc;            // best_model_sd = deepcopy(state_dict)  (ntu.py:17)
+  const long long stat_stride = 4LL * E;
+  long long t = 0;
+  for (int e = 0; e < E; ++e) {
+    for (long long s = 0; s < steps_tr; ++s, ++t) {        // phase 'train'
+      const int n = (int)((s == steps_tr - 1) ? last_tr : B);
+      BatchRef b{a->perm_train, (long long)E * ntr, (long long)e * ntr + s * B, n};
+      HeadOut ho{nullptr, nullptr, nullptr, a->stats, stat_stride, 4LL * e};
+      if ((rc = launch_step(g, dtr, b, true, true, a->step_size[t], a->bc2_sqrt[t], (uint32_t)(a->adam_t0 + t), ho, st)))
+        return rc;
+    }
+    for (long long s = 0; s < steps_dv; ++s) {             // phase 'dev'
+      const int n = (int)((s == steps_dv - 1) ? ndv - (steps_dv - 1) * B : B);
+      BatchRef b{a->perm_dev, (long long)E * ndv, (a->perm_dev ? (long long)e * ndv : 0) + s * B, n};
+      HeadOut ho{nullptr, nullptr, nullptr, a->stats, stat_stride, 4LL * e + 2};
+      if ((rc = launch_step(g, ddv, b, false, false, 0.f, 1.f, 0u, ho, st))) return rc;
+    }
+    k_best_update<<<(g->n_cand + 127) / 128, 128, 0, st>>>(g->n_cand, a->stats, stat_stride, 4LL * e + 2, ndv, e,
+                                                           a->best_acc, a->best_epoch, g->improved);
+    LAUNCH_CHECK(g);
+    if ((rc = snapshot(g, 0, 0, st))) return rc;           // deepcopy on improvement (ntu.py:82-84)
+  }
+  return snapshot(g, 1, 1, st);                            // model.load_state_dict(best_model_sd) (ntu.py:86)
+}
+
+extern "C" int mfas_eval_pass(mfas_group_t g, const mfas_cache_desc* cache, const int32_t* d_perm, int32_t batch,
+                              double* d_out, void* stream) {
+  if (!g || !d_out) return fail(MFAS_ERR_INVALID, "null argument");
+  DeviceGuard dg(g->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (batch < 1 || batch > g->bmax) return fail(MFAS_ERR_INVALID, "batch=%d (group batch_max=%d)", batch, g->bmax);
+  DCache dc;
+  int rc;
+  if ((rc = to_dcache(g, cache, &dc))) return rc;
+  if ((rc = sync_descriptors(g, st))) return rc;
+  CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * g->n_cand, st));
+  const long long n = dc.n_rows, steps = (n + batch - 1) / batch;
+  for (long long s = 0; s < steps; ++s) {
+    const int nr = (int)((s == steps - 1) ? n - (steps - 1) * batch : batch);
+    BatchRef b{d_perm, n, s * batch, nr};
+    HeadOut ho{nullptr, nullptr, nullptr, d_out, 2, 0};
+    if ((rc = launch_step(g, dc, b, false, false, 0.f, 1.f, 0u, ho, st))) return rc;
+  }
+  return MFAS_OK;
+}

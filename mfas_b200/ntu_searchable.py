@@ -1,0 +1,376 @@
+"""Drop-in for /root/reference/models/search/ntu_searchable.py on cached backbone taps.
+
+Same module attributes the search driver uses (models/searchable.py:23,256-260):
+``train_sampled_models``, ``get_possible_layer_configurations``, ``get_central_states``,
+``set_central_states``, ``Searchable_Skeleton_Image_Net`` -- same signatures, same state_dict key
+names, same return types -- but candidates are trained by the CUDA library (mfas_b200/csrc), many
+at a time, with nothing returning to the host between the first batch and the last epoch.
+
+What is deliberately different from the reference:
+  * the frozen backbones are replaced by a FeatureCache (D5): ``rgbnet`` / ``skenet`` are
+    parameter-free tap splitters kept only so ``.load_state_dict`` calls keep working;
+  * accuracies come back as 0-dim float64 *CPU* tensors (D10) so ``np.array(accs)`` in
+    models/search/tools.py:47-49 works;
+  * there is no CPU execution path: a non-CUDA ``device`` raises.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .cache import D_RGB, FeatureCache, ske_widths
+from .engine import CandidateGroup, flags_from_args
+from .scheduler import LRCosineAnnealingScheduler
+
+
+# ----------------------------------------------------------------------------------------------
+# small modules of the reference's model tree
+# ----------------------------------------------------------------------------------------------
+class GlobalPooling2D(nn.Module):
+    """Mean over every dim but (batch, channel) (/root/reference/models/auxiliary/aux_models.py:54-64).
+    Cached taps are already pooled, so on the hot path this is the identity."""
+
+    def forward(self, x):
+        return x.reshape(x.size(0), x.size(1), -1).mean(2)
+
+
+class AlphaScalarMultiplication(nn.Module):
+    """Scalar modality gate x*sigmoid(a), y*(1-sigmoid(a)) (aux_models.py:94-111)."""
+
+    def __init__(self, size_alpha_x, size_alpha_y):
+        super().__init__()
+        self.size_alpha_x = size_alpha_x
+        self.size_alpha_y = size_alpha_y
+        self.alpha_x = nn.Parameter(torch.zeros(1, dtype=torch.float32))
+
+    def forward(self, x, y):
+        s = torch.sigmoid(self.alpha_x)
+        return x * s, y * (1.0 - s)
+
+
+class CachedTaps(nn.Module):
+    """Stands where a frozen backbone stood (models/central/ntu.py:17-183): parameter-free, splits a
+    row of concatenated cached taps back into the backbone's output structure.  Accepts (and
+    ignores) any backbone checkpoint so ``rmode.skenet.load_state_dict(torch.load(...))``
+    (ntu_searchable.py:46-49) keeps working."""
+
+    def __init__(self, widths, kind):
+        super().__init__()
+        self.widths, self.kind = tuple(widths), kind
+
+    def forward(self, x):
+        taps = torch.split(x, self.widths, 1)
+        if self.kind == "rgb":                       # Visual.forward 6-tuple, central/ntu.py:50
+            return (None, *taps, None)
+        return [None] * 4 + list(taps), None         # Skeleton.forward, central/ntu.py:183
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        return nn.modules.module._IncompatibleKeys([], [])
+
+
+def _activation(kind):
+    kind = int(kind)
+    if kind == 0:
+        return nn.ReLU()
+    if kind == 1:
+        return nn.Sigmoid()
+    if kind == 2:
+        return nn.LeakyReLU()
+    raise ValueError(f"activation id {kind} not in {{0,1,2}}")
+
+
+# ----------------------------------------------------------------------------------------------
+# the searchable fusion network
+# ----------------------------------------------------------------------------------------------
+class Searchable_Skeleton_Image_Net(nn.Module):
+    """Searchable fusion head (/root/reference/models/search/ntu_searchable.py:178-301).
+
+    conf: int array [L, 3], one row per fusion step: [ske tap, rgb tap, nonlinearity].
+    forward(tensor_tuple): tensor_tuple = (rgb, ske) with rgb [B, 5632] / ske [B, 1920] the
+    concatenated cached taps (what FeatureCacheLoader yields); returns [B, num_outputs] logits
+    computed by the CUDA library.  The sub-modules are ordinary nn.Linear / BatchNorm1d objects so
+    ``state_dict()`` has the reference's keys; once on a CUDA device their storage is the flat
+    arenas the kernels update in place.
+    """
+
+    def __init__(self, args, conf):
+        super().__init__()
+        self.conf = conf
+        self.args = args
+        ds = ske_widths(args.vid_len[1])
+        self.rgbnet = CachedTaps(D_RGB, "rgb")
+        self.skenet = CachedTaps(ds, "ske")
+        cf = np.asarray(conf).reshape(-1, 3)
+        # construction order == reference order, so a given torch seed gives the same init
+        self.alphas = nn.ModuleList([AlphaScalarMultiplication(ds[int(c[0])], D_RGB[int(c[1])]) for c in cf])
+        self.gp_v = nn.ModuleList([GlobalPooling2D() for _ in cf])
+        self.gp_s = nn.ModuleList([GlobalPooling2D() for _ in cf])
+        self.fusion_layers = self._create_fc_layers(cf)
+        self.central_classifier = nn.Linear(args.inner_representation_size, args.num_outputs)
+        for m in self.modules():
+            if isinstance(m, AlphaScalarMultiplication):
+                nn.init.normal_(m.alpha_x, 0.0, 0.1)
+        self._group = None          # CandidateGroup whose arenas back this module
+        self._slot = 0
+        self._fwd_steps = 0
+
+    def _create_fc_layers(self, cf):
+        H, drpt, bn = self.args.inner_representation_size, self.args.drpt, self.args.batchnorm
+        layers = []
+        for i, c in enumerate(cf):
+            in_size = self.alphas[i].size_alpha_x + self.alphas[i].size_alpha_y + (H if i > 0 else 0)
+            nl = _activation(c[2])
+            if drpt > 1e-10 and bn:
+                op = nn.Sequential(nn.Linear(in_size, H), nl, nn.BatchNorm1d(H), nn.Dropout(drpt))
+            elif drpt > 1e-10:
+                op = nn.Sequential(nn.Linear(in_size, H), nl, nn.Dropout(drpt))
+            elif bn:
+                op = nn.Sequential(nn.Linear(in_size, H), nl, nn.BatchNorm1d(H))
+            else:   # the reference falls through every branch here (ntu_searchable.py:274-284)
+                raise UnboundLocalError("local variable 'op' referenced before assignment "
+                                        "(no layer recipe for drpt<1e-10 and batchnorm=False)")
+            layers.append(op)
+        return nn.ModuleList(layers)
+
+    def central_params(self):
+        return [{'params': self.alphas.parameters()},
+                {'params': self.fusion_layers.parameters()},
+                {'params': self.central_classifier.parameters()}]
+
+    # ---- arena plumbing ---------------------------------------------------------------------
+    def _named_state(self):
+        d = dict(self.named_parameters())
+        d.update(dict(self.named_buffers()))
+        return d
+
+    def attach(self, group: CandidateGroup, slot: int, copy_in: bool = True):
+        """Make candidate ``slot`` of ``group`` the storage of this module's tensors."""
+        with torch.no_grad():
+            for name, t in self._named_state().items():
+                if name not in group.slots[slot]:
+                    continue
+                v = group.view(slot, name)
+                if copy_in:
+                    v.copy_(t.detach().to(v.device).reshape(v.shape))
+                t.data = v
+        self._group, self._slot = group, slot
+        return self
+
+    def native(self, device=None) -> CandidateGroup:
+        """The 1-candidate group backing this module (created on first use / after .to())."""
+        w = self.fusion_layers[0][0].weight
+        if device is None:
+            device = w.device
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("mfas_b200 computes on CUDA devices only; move the model with .to('cuda') "
+                               "(there is no CPU fallback)")
+        g = self._group
+        if g is not None and w.device == device and w.data_ptr() == g.view(self._slot, "fusion_layers.0.0.weight").data_ptr():
+            return g
+        a = self.args
+        cf = np.asarray(self.conf).reshape(-1, 3)
+        g = CandidateGroup([cf], a.inner_representation_size, a.num_outputs, flags_from_args(a), device,
+                           batch_max=_lib.MAX_BATCH, drop_p=float(a.drpt) if a.drpt > 1e-10 else 0.0,
+                           drop_seed=int(getattr(a, "dropout_seed", 0)), vid_len_ske=a.vid_len[1])
+        self.attach(g, 0, copy_in=True)
+        return g
+
+    # ---- forward ----------------------------------------------------------------------------
+    def forward(self, tensor_tuple):
+        rgb, ske = tensor_tuple[0], tensor_tuple[1]          # caller passes (rgb, ske), ntu_searchable.py:208
+        if getattr(self.args, "alphas", False) or getattr(self.args, "multitask", False):
+            raise NotImplementedError("alphas / multitask are not built yet (SURVEY.md section 8(f) rows 3-4)")
+        if rgb.dim() != 2 or ske.dim() != 2:
+            raise ValueError("expected cached taps: rgb [B, %d], ske [B, %d]" % (sum(D_RGB), sum(self.skenet.widths)))
+        g = self.native(rgb.device)
+        B = rgb.shape[0]
+        if B > g.batch_max:
+            raise ValueError(f"batch of {B} rows exceeds MFAS_MAX_BATCH={g.batch_max}")
+        cache = FeatureCache(ske.contiguous(), rgb.contiguous(),
+                             torch.zeros(B, dtype=torch.int64, device=rgb.device), self.args.vid_len[1])
+        rows = torch.arange(B, dtype=torch.int32, device=rgb.device)
+        logits, _, _ = g.forward(cache, rows, train=self.training, step=self._fwd_steps)
+        if self.training:
+            self._fwd_steps += 1
+        return logits[self._slot].clone()
+
+
+# ----------------------------------------------------------------------------------------------
+# search space / weight sharing
+# ----------------------------------------------------------------------------------------------
+def get_possible_layer_configurations(progression_index):
+    """All [ske tap, rgb tap, activation] rows of one fusion step: 4 x 4 x 2 = 32
+    (/root/reference/models/search/ntu_searchable.py:105-119)."""
+    return [[t, v, n] for t in range(4) for v in range(4) for n in range(2)]
+
+
+_ACT_TAG = {0: '.A_relu', 1: '.A_sigmoid', 2: '.A_lrelu'}
+
+
+def _shared_key(idx_layer, layer, conf_row):
+    return str(idx_layer) + '.L_' + str(layer[0].in_features) + '_' + str(layer[0].out_features) + \
+        _ACT_TAG.get(int(conf_row[2]), '')
+
+
+def get_central_states(model, state_dict, using_dataparallel=False):
+    """Store every fusion layer under '<l>.L_<in>_<out>.A_<act>' (ntu_searchable.py:123-149)."""
+    net = model.module if using_dataparallel else model
+    for idx_layer, layer in enumerate(net.fusion_layers):
+        name = _shared_key(idx_layer, layer, net.conf[idx_layer])
+        print(('Updating' if name in state_dict else 'Creating') + ' shared weight with ID: {}'.format(name))
+        state_dict[name] = {k: v.detach().clone() for k, v in layer.state_dict().items()}
+    return state_dict
+
+
+def set_central_states(model, state_dict, using_dataparallel=False):
+    """Load shared fusion layers whose key matches (ntu_searchable.py:152-174)."""
+    net = model.module if using_dataparallel else model
+    for idx_layer, layer in enumerate(net.fusion_layers):
+        name = _shared_key(idx_layer, layer, net.conf[idx_layer])
+        if name in state_dict:
+            with torch.no_grad():
+                own = layer.state_dict()
+                for k, v in state_dict[name].items():
+                    own[k].copy_(v)          # in place: the tensors are views of the CUDA arenas
+            print('Loaded shared weight with ID: {}'.format(name))
+
+
+# ----------------------------------------------------------------------------------------------
+# candidate trainer
+# ----------------------------------------------------------------------------------------------
+def _feature_cache_of(loader, what):
+    ds = getattr(loader, "dataset", None)
+    if not isinstance(ds, FeatureCache):
+        raise TypeError(f"dataloaders['{what}'].dataset must be a mfas_b200.FeatureCache (pre-extracted backbone "
+                        f"taps); got {type(ds).__name__}. Build one with mfas_b200.cache (DESIGN.md, 'Feature cache').")
+    return ds
+
+
+def pass_orders(loader, first_pass, count, n_rows):
+    """Row orders of ``count`` consecutive passes over ``loader`` as an int32 [count, n_rows] tensor."""
+    if hasattr(loader, "order_for_pass"):
+        return torch.stack([loader.order_for_pass(first_pass + k) for k in range(count)]).to(torch.int32)
+    shuffle = not isinstance(getattr(loader, "sampler", None), torch.utils.data.SequentialSampler)
+    if shuffle:
+        return torch.stack([torch.randperm(n_rows) for _ in range(count)]).to(torch.int32)
+    return torch.arange(n_rows, dtype=torch.int32).repeat(count, 1)
+
+
+def _reserve_passes(loader, count):
+    return loader.take_passes(count) if hasattr(loader, "take_passes") else 0
+
+
+def cosine_lrs(args, n_train, n_steps):
+    """LR of every optimiser step of one candidate (LRCosineAnnealingScheduler, per batch)."""
+    sched = LRCosineAnnealingScheduler(args.eta_max, args.eta_min, args.Ti, args.Tm, n_train / args.batchsize)
+    return [sched.step() for _ in range(n_steps)]
+
+
+def _print_epoch_logs(stats, n_train, n_dev):
+    for e in range(stats.shape[0]):           # same lines as train_searchable/ntu.py:78-79
+        print('{} Loss: {:.4f} Acc: {:.4f}'.format('train', stats[e, 0] / n_train, stats[e, 1] / n_train))
+        print('{} Loss: {:.4f} Acc: {:.4f}'.format('dev', stats[e, 2] / n_dev, stats[e, 3] / n_dev))
+
+
+def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
+                         args, device,
+                         return_model=[], premodels=[], preaccuracies=[],
+                         train_only_central_params=True,
+                         state_dict=dict()):
+    """Train every sampled configuration and return its best dev accuracy, in input order.
+
+    Signature and semantics of /root/reference/models/search/ntu_searchable.py:23-102: Adam(lr=eta_max,
+    weight_decay=1e-4) with the per-batch cosine LR, ``args.epochs`` x (train pass, dev pass), strict-'>'
+    best-dev tracking and rollback to the best weights.  All candidates of the call are trained
+    concurrently by the CUDA library (sequentially only when ``args.weightsharing`` chains them
+    through ``state_dict``); with torch.distributed initialised they are sharded over ranks.
+    """
+    from . import dist as mdist
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("mfas_b200.train_sampled_models needs a CUDA device (no CPU fallback)")
+    if preaccuracies:   # the reference passes init_f1=..., which train_ntu_track_acc does not accept (:85-89)
+        raise TypeError("train_ntu_track_acc() got an unexpected keyword argument 'init_f1'")
+    train_host = _feature_cache_of(dataloaders['train'], 'train')
+    dev_host = _feature_cache_of(dataloaders['dev'], 'dev')
+    n_train, n_dev = len(train_host), len(dev_host)
+    E, B = int(args.epochs), int(args.batchsize)
+    steps = math.ceil(n_train / B)
+
+    todo = [i for i in range(len(sampled_configurations)) if not return_model or i in return_model]
+    # every candidate is constructed here, in order, exactly like the reference does (RNG parity)
+    models = {}
+    for idx in todo:
+        rmode = searchable_type(args, sampled_configurations[idx])
+        if not premodels:
+            for net, cp in ((rmode.skenet, args.ske_cp), (rmode.rgbnet, args.rgb_cp)):
+                fn = os.path.join(args.checkpointdir, cp)
+                if os.path.isfile(fn):          # backbone weights are irrelevant once taps are cached
+                    net.load_state_dict(torch.load(fn))
+        else:
+            src = premodels[idx].module if args.use_dataparallel else premodels[idx]
+            rmode.load_state_dict(src.state_dict())
+        models[idx] = rmode
+
+    first_tr = _reserve_passes(dataloaders['train'], len(todo) * E)
+    first_dv = _reserve_passes(dataloaders['dev'], len(todo) * E)
+    lrs = cosine_lrs(args, n_train, E * steps)
+    flags = flags_from_args(args)
+    if flags & (_lib.FLAG_ALPHAS | _lib.FLAG_MULTITASK):
+        raise NotImplementedError("alphas / multitask are not built yet (SURVEY.md section 8(f) rows 3-4)")
+    drop_p = float(args.drpt) if args.drpt > 1e-10 else 0.0
+
+    mine = mdist.my_share(len(todo)) if not args.weightsharing else list(range(len(todo)))
+    train_dev = train_host.to(device)
+    dev_dev = dev_host.to(device)
+    accs = torch.zeros(len(todo), dtype=torch.float64)
+    all_stats = torch.zeros(len(todo), max(E, 1), 4, dtype=torch.float64)
+
+    def run(js):
+        """train the candidates todo[j], j in js, as one group"""
+        confs = [np.asarray(sampled_configurations[todo[j]]).reshape(-1, 3) for j in js]
+        g = CandidateGroup(confs, args.inner_representation_size, args.num_outputs, flags, device, batch_max=B,
+                           drop_p=drop_p, drop_seed=int(getattr(args, "dropout_seed", 0)),
+                           cand_ids=[todo[j] for j in js], vid_len_ske=args.vid_len[1])
+        g.set_adam(0.9, 0.999, 1e-8, 1e-4)                                   # op.Adam(..., weight_decay=1e-4), :65
+        for k, j in enumerate(js):
+            models[todo[j]].attach(g, k, copy_in=True)                       # rmode.to(device), :72
+            if args.weightsharing:
+                set_central_states(models[todo[j]], state_dict, args.use_dataparallel)
+        ptr = torch.stack([pass_orders(dataloaders['train'], first_tr + j * E, E, n_train) for j in js]) if E else \
+            torch.zeros(len(js), 0, n_train, dtype=torch.int32)
+        pdv = torch.stack([pass_orders(dataloaders['dev'], first_dv + j * E, E, n_dev) for j in js]) if E else \
+            torch.zeros(len(js), 0, n_dev, dtype=torch.int32)
+        stats, best, _ = g.train_run(train_dev, dev_dev, ptr, pdv, lrs, E, B)
+        stats, best = stats.cpu(), best.cpu()                               # the one D2H of the call
+        for k, j in enumerate(js):
+            accs[j] = best[k]
+            all_stats[j] = stats[k]
+            m = models[todo[j]]
+            m.train(False)                                                   # train_searchable/ntu.py:87
+            if args.verbose:
+                print('Now training: ')
+                print(sampled_configurations[todo[j]])
+                _print_epoch_logs(stats[k].numpy(), n_train, n_dev)
+            if args.weightsharing:
+                get_central_states(m, state_dict, args.use_dataparallel)
+        return g
+
+    if args.weightsharing:                 # candidates are chained through state_dict: one at a time
+        for j in mine:
+            run([j])
+    elif mine:
+        run(mine)
+
+    accs = mdist.gather_results(accs, len(todo))
+    real_accuracies = [accs[j].clone() for j in range(len(todo))]
+    train_sampled_models.last_stats = all_stats
+    if return_model:
+        return real_accuracies, [models[i] for i in todo]
+    return real_accuracies

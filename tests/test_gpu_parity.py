@@ -1,0 +1,304 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the reference fixtures.
+
+Tolerance: north_star asks for 1e-4 relative on logits / loss / trained weights / val-acc.  Single
+steps are held to that directly.  Over a trajectory Adam's first steps divide m by sqrt(v) ~ |g|,
+which amplifies rounding noise of tiny gradients, so multi-epoch quantities are compared with the
+same looser factors the oracle-vs-reference test uses (tests/test_oracle_golden.py).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import FOUND_CONFS, GOLDEN_CASES, GOLDEN_DIR, init_states, make_args, rel_err, sample_tensor, split_np
+from mfas_b200.cache import FeatureCacheLoader, synthetic_ntu_cache
+from oracle import mfas_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DEV = "cuda:0"
+
+
+def _group(confs, H, B, bn=True, drpt=0.0, keep_grads=False, seed=0, ids=None):
+    from mfas_b200 import _lib
+    from mfas_b200.engine import CandidateGroup
+    flags = (_lib.FLAG_BN if bn else 0) | (_lib.FLAG_DROPOUT if drpt > 1e-10 else 0)
+    g = CandidateGroup(confs, H, 60, flags, DEV, batch_max=B, drop_p=drpt, drop_seed=seed, keep_grads=keep_grads,
+                       cand_ids=ids)
+    g.set_adam(0.9, 0.999, 1e-8, 1e-4)
+    return g
+
+
+def _close(a, b, tol, what, scale=None):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    s = scale if scale is not None else max(np.abs(b).max(), 1e-30)
+    err = np.abs(a - b).max() / s
+    assert err < tol, f"{what}: rel err {err:.3e} >= {tol:.1e}"
+    return err
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_single_step_vs_oracle_and_fixture(name):
+    """One optimiser step: logits, loss, every gradient, updated params, Adam moments, BN buffers."""
+    cs = GOLDEN_CASES[name]
+    gold = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    train = synthetic_ntu_cache(cs["n_train"], cs["data_seed"])
+    trs = split_np(train)
+    loader = FeatureCacheLoader(train, cs["B"], True, int(gold["meta/loader_seed"]))
+    inits = init_states(cs["confs"], cs["H"], 60, cs["bn"], cs["drpt"], cs["model_seed"])
+    E, B = cs["epochs"], cs["B"]
+    g = _group(cs["confs"], cs["H"], B, cs["bn"], keep_grads=True)
+    tc = train.to(DEV)
+    rows = torch.stack([loader.order_for_pass(ci * E)[:B] for ci in range(len(cs["confs"]))])
+    for ci in range(g.n):
+        g.load_state(ci, inits[ci])
+    logits, loss, correct = g.train_step(tc, rows, lr=1e-3)
+    torch.cuda.synchronize()
+    logits, loss = logits.cpu().numpy(), loss.cpu().numpy()
+    for ci, conf in enumerate(cs["confs"]):
+        head = O.FusionHead(conf, cs["H"], 60, inits[ci], batchnorm=cs["bn"])
+        sk, rg, y = O._taps_of(trs, rows[ci].numpy())
+        ol, oloss, ograds = head.train_step(sk, rg, y, 1e-3)
+        _close(logits[ci], ol, TOL, f"{name} c{ci} logits vs oracle")
+        _close(logits[ci], gold[f"c{ci}/step0_logits"], TOL, f"{name} c{ci} logits vs reference fixture")
+        assert abs(loss[ci] - float(gold[f"c{ci}/step0_loss"])) < TOL * float(gold[f"c{ci}/step0_loss"])
+        assert int(correct[ci]) == int((ol.argmax(1) == y).sum())
+        got_g = g.state(ci, "g")
+        got_p, got_m, got_v = g.state(ci), g.state(ci, "m"), g.state(ci, "v")
+        for k, ref in ograds.items():
+            _close(got_g[k], ref, TOL, f"{name} c{ci} grad {k} vs oracle", scale=max(np.abs(ref).max(), 1e-12))
+            fx = gold[f"c{ci}/grad/{k}/sample"]
+            _close(sample_tensor(got_g[k])["sample"], fx, TOL, f"{name} c{ci} grad {k} vs fixture",
+                   scale=max(float(gold[f"c{ci}/grad/{k}/amax"]), 1e-12))
+            _close(got_m[k], head.adam[k][0], 2 * TOL, f"{name} c{ci} exp_avg {k}", scale=max(np.abs(head.adam[k][0]).max(), 1e-12))
+            _close(got_v[k], head.adam[k][1], 4 * TOL, f"{name} c{ci} exp_avg_sq {k}", scale=max(np.abs(head.adam[k][1]).max(), 1e-20))
+        for k, ref in head.state.items():
+            if k.startswith("alphas"):
+                continue
+            if k.endswith("num_batches_tracked"):
+                assert int(got_p[k]) == int(ref) == 1
+                continue
+            # first Adam step moves every weight by ~lr*sign(g); compare the *update* too
+            _close(got_p[k], ref, TOL, f"{name} c{ci} param {k}")
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_train_sampled_models_vs_reference_fixture(name):
+    """The drop-in entry point against what the unmodified reference produced on the same inputs."""
+    import mfas_b200.ntu_searchable as ntu
+    cs = GOLDEN_CASES[name]
+    gold = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    args = make_args(cs["H"], cs["B"], cs["epochs"], bn=cs["bn"], drpt=cs["drpt"], Ti=cs["Ti"], checkpointdir="/nonexistent")
+    train = synthetic_ntu_cache(cs["n_train"], cs["data_seed"])
+    dev = synthetic_ntu_cache(cs["n_dev"], cs["data_seed"] + 1)
+    seed = int(gold["meta/loader_seed"])
+    loaders = {"train": FeatureCacheLoader(train, cs["B"], True, seed),
+               "dev": FeatureCacheLoader(dev, cs["B"], True, seed + 50000)}
+    confs = [np.array(c) for c in cs["confs"]]
+    torch.manual_seed(cs["model_seed"])
+    accs, models = ntu.train_sampled_models(confs, ntu.Searchable_Skeleton_Image_Net, loaders, args,
+                                            torch.device(DEV), return_model=list(range(len(confs))))
+    stats = ntu.train_sampled_models.last_stats.numpy()
+    B, E = cs["B"], cs["epochs"]
+    n_tb = -(-cs["n_train"] // B)
+    n_db = -(-cs["n_dev"] // B)
+    wtr = np.minimum(B, cs["n_train"] - B * np.arange(n_tb))
+    wdv = np.minimum(B, cs["n_dev"] - B * np.arange(n_db))
+    for ci in range(len(confs)):
+        assert accs[ci].dtype == torch.float64 and accs[ci].dim() == 0 and accs[ci].device.type == "cpu"
+        exp_tr = (gold[f"c{ci}/train_loss"] * wtr).sum(1)
+        exp_dv = (gold[f"c{ci}/dev_loss"] * wdv).sum(1)
+        _close(stats[ci, :, 0], exp_tr, 20 * TOL, f"{name} c{ci} epoch train loss")
+        _close(stats[ci, :, 2], exp_dv, 20 * TOL, f"{name} c{ci} epoch dev loss")
+        assert np.abs(stats[ci, :, 3] - gold[f"c{ci}/dev_correct"].sum(1)).max() <= 1, "dev correct counts"
+        assert np.abs(stats[ci, :, 1] - gold[f"c{ci}/train_correct"].sum(1)).max() <= 2, "train correct counts"
+        assert abs(float(accs[ci]) - float(gold[f"c{ci}/best_acc"])) <= 1.0 / cs["n_dev"] + 1e-12
+        sd = models[ci].state_dict()
+        assert not models[ci].training
+        for k, v in sd.items():
+            if k.startswith("alphas"):
+                continue
+            if k.endswith("num_batches_tracked"):
+                continue
+            fx = gold[f"c{ci}/final/{k}/sample"]
+            _close(sample_tensor(v.cpu().numpy())["sample"], fx, 50 * TOL, f"{name} c{ci} final {k}",
+                   scale=max(float(gold[f"c{ci}/final/{k}/amax"]), 1e-12))
+        # num_batches_tracked follows the rollback too
+        if float(gold[f"c{ci}/best_acc"]) > 0:
+            k = "fusion_layers.0.2.num_batches_tracked"
+            assert int(sd[k]) % n_tb == 0 and int(sd[k]) > 0
+
+
+def test_run_vs_oracle_trajectory_cfg2_shapes():
+    """Several epochs at cfg2 shapes (conf 4, H=128, B=64) against the oracle: epoch losses, dev accuracy
+    per epoch, best-epoch choice, rolled-back weights and the (not rolled back) Adam moments."""
+    conf = FOUND_CONFS[4]
+    H, B, E, ntr, ndv = 128, 64, 3, 448, 192
+    train, dev = synthetic_ntu_cache(ntr, 5), synthetic_ntu_cache(ndv, 6)
+    ltr, ldv = FeatureCacheLoader(train, B, True, 7), FeatureCacheLoader(dev, B, True, 8)
+    init = init_states([conf], H, 60, True, 0.0, 1)[0]
+    g = _group([conf], H, B)
+    g.load_state(0, init)
+    lrs = []
+    sch = O.CosineRestartLR(1e-3, 1e-6, 1, 2, ntr / B)
+    lrs = [sch.step() for _ in range(E * math.ceil(ntr / B))]
+    ptr = torch.stack([ltr.order_for_pass(e) for e in range(E)])[None]
+    pdv = torch.stack([ldv.order_for_pass(e) for e in range(E)])[None]
+    stats, best, best_epoch = g.train_run(train.to(DEV), dev.to(DEV), ptr, pdv, lrs, E, B)
+    stats, best, best_epoch = stats.cpu().numpy()[0], float(best.cpu()[0]), int(best_epoch.cpu()[0])
+
+    head = O.FusionHead(conf, H, 60, init)
+    sched = O.CosineRestartLR(1e-3, 1e-6, 1, 2, ntr / B)
+    obest, ostats = O.train_track_acc(head, sched, split_np(train), split_np(dev), B,
+                                      lambda ph, e: (ltr if ph == "train" else ldv).order_for_pass(e).numpy(), E)
+    _close(stats[:, 0] / ntr, [s["train_loss"] for s in ostats], 20 * TOL, "epoch train loss")
+    _close(stats[:, 2] / ndv, [s["dev_loss"] for s in ostats], 20 * TOL, "epoch dev loss")
+    assert np.abs(stats[:, 3] / ndv - np.array([s["dev_acc"] for s in ostats])).max() <= 1.0 / ndv + 1e-12
+    assert abs(best - float(obest)) <= 1.0 / ndv + 1e-12
+    oe = int(np.argmax([s["dev_acc"] for s in ostats])) if obest > 0 else -1
+    assert best_epoch == oe
+    got = g.state(0)
+    for k, ref in head.state.items():
+        if k.startswith("alphas") or k.endswith("num_batches_tracked"):
+            continue
+        _close(got[k], ref, 50 * TOL, f"rolled-back {k}")
+    gm = g.state(0, "m")
+    for k, (m, v) in head.adam.items():
+        _close(gm[k], m, 100 * TOL, f"exp_avg {k}", scale=max(np.abs(m).max(), 1e-12))
+
+
+def test_batched_candidates_equal_solo_runs_bitwise():
+    """Training M candidates in one group must give exactly what each gives alone (no cross-talk),
+    and two identical runs must be bit-identical (fixed-order reductions, no atomics)."""
+    confs = [[[0, 0, 0]], FOUND_CONFS[4], [[3, 1, 1], [2, 2, 2]], FOUND_CONFS[0][:3]]
+    H, B, E, ntr, ndv = 32, 16, 2, 80, 40
+    train, dev = synthetic_ntu_cache(ntr, 15).to(DEV), synthetic_ntu_cache(ndv, 16).to(DEV)
+    inits = init_states(confs, H, 60, True, 0.0, 2)
+    lrs = [1e-3 * (0.9 ** i) for i in range(E * math.ceil(ntr / B))]
+    gen = torch.Generator().manual_seed(3)
+    ptr = torch.stack([torch.stack([torch.randperm(ntr, generator=gen) for _ in range(E)]) for _ in confs])
+    pdv = torch.stack([torch.stack([torch.randperm(ndv, generator=gen) for _ in range(E)]) for _ in confs])
+
+    def run(idx):
+        g = _group([confs[i] for i in idx], H, B, ids=idx)
+        for k, i in enumerate(idx):
+            g.load_state(k, inits[i])
+        st, best, be = g.train_run(train, dev, ptr[idx], pdv[idx], lrs, E, B)
+        torch.cuda.synchronize()
+        return g, st.cpu(), best.cpu(), be.cpu()
+
+    gall, st, best, be = run([0, 1, 2, 3])
+    g2, st2, best2, _ = run([0, 1, 2, 3])
+    assert torch.equal(st, st2) and torch.equal(best, best2) and torch.equal(gall.params, g2.params)
+    for i in range(4):
+        gi, sti, besti, bei = run([i])
+        assert torch.equal(sti[0], st[i]) and torch.equal(besti[0], best[i]) and int(bei[0]) == int(be[i])
+        for name in gall.names(i):
+            assert torch.equal(gall.view(i, name), gi.view(0, name)), name
+
+
+def test_dropout_path_vs_oracle():
+    """drpt>0 with and without BatchNorm: the counter-based mask is shared with the oracle, so a
+    train step matches exactly like the deterministic path; eval ignores dropout."""
+    for bn in (True, False):
+        conf = [[3, 1, 1], [1, 3, 0]]
+        H, B = 32, 24
+        train = synthetic_ntu_cache(64, 41)
+        init = init_states([conf], H, 60, bn, 0.5, 4)[0]
+        g = _group([conf], H, B, bn=bn, drpt=0.5, keep_grads=True, seed=1234, ids=[7])
+        g.load_state(0, init)
+        rows = torch.arange(B)
+        head = O.FusionHead(conf, H, 60, init, batchnorm=bn, drpt=0.5, dropout_seed=1234, cand_index=7)
+        sk, rg, y = O._taps_of(split_np(train), rows.numpy())
+        for step in range(2):
+            logits, loss, _ = g.train_step(train.to(DEV), rows, lr=1e-3)
+            ol, oloss, ograds = head.train_step(sk, rg, y, 1e-3)
+            _close(logits[0].cpu().numpy(), ol, TOL, f"dropout bn={bn} step {step} logits")
+            gg = g.state(0, "g")
+            for k, ref in ograds.items():
+                _close(gg[k], ref, 2 * TOL, f"dropout bn={bn} step {step} grad {k}", scale=max(np.abs(ref).max(), 1e-12))
+        lg, _, _ = g.forward(train.to(DEV), rows, train=False)
+        ol, _ = head.forward(sk, rg, train=False)
+        _close(lg[0].cpu().numpy(), ol, 5 * TOL, f"dropout bn={bn} eval logits")
+
+
+def test_model_forward_and_found_flow():
+    """Searchable_Skeleton_Image_Net.forward + train_ntu_track_acc + test_ntu_track_acc, driven the way
+    main_found_ntu.py drives them (construct, Adam over central_params, scheduler, .to(device))."""
+    import mfas_b200.ntu_searchable as ntu
+    import mfas_b200.train_ntu as tr
+    from mfas_b200.scheduler import LRCosineAnnealingScheduler
+    conf = np.array(FOUND_CONFS[0])
+    H, B, ntr, ndv = 32, 8, 60, 28
+    args = make_args(H, B, 2, bn=True, drpt=0.0, Ti=5)
+    train, dev = synthetic_ntu_cache(ntr, 11), synthetic_ntu_cache(ndv, 12)
+    loaders = {"train": FeatureCacheLoader(train, B, True, 100), "dev": FeatureCacheLoader(dev, B, True, 50100),
+               "test": FeatureCacheLoader(dev, B, False, 0)}
+    torch.manual_seed(0)
+    model = ntu.Searchable_Skeleton_Image_Net(args, conf)
+    init = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+    ref_init = init_states([FOUND_CONFS[0]], H, 60, True, 0.0, 0)[0]
+    for k in ref_init:
+        assert np.array_equal(init[k], ref_init[k]), k          # same RNG consumption as the reference ctor
+    opt = torch.optim.Adam(model.central_params(), lr=1e-3 / 10, weight_decay=1e-4)
+    sch = LRCosineAnnealingScheduler(1e-3, 1e-6, 5, 2, ntr / B)
+    model.to(DEV)
+    # eval-mode forward through the module == oracle
+    head = O.FusionHead(conf, H, 60, init)
+    rows = np.arange(B)
+    sk, rg, y = O._taps_of(split_np(train), rows)
+    model.train(False)
+    out = model((train.rgb_cat[:B].to(DEV), train.ske_cat[:B].to(DEV)))
+    ol, _ = head.forward(sk, rg, train=False)
+    _close(out.cpu().numpy(), ol, TOL, "module eval forward")
+    best = tr.train_ntu_track_acc(model, [torch.nn.CrossEntropyLoss()] * 3, opt, sch, loaders,
+                                  {"train": ntr, "dev": ndv, "test": ndv}, device=torch.device(DEV), num_epochs=2)
+    sched = O.CosineRestartLR(1e-3, 1e-6, 5, 2, ntr / B)
+    obest, ostats = O.train_track_acc(head, sched, split_np(train), split_np(dev), B,
+                                      lambda ph, e: loaders[ph].order_for_pass(e).numpy(), 2)
+    assert abs(float(best) - float(obest)) <= 1.0 / ndv + 1e-12
+    sd = model.state_dict()
+    for k, ref in head.state.items():
+        if k.startswith("alphas") or k.endswith("num_batches_tracked"):
+            continue
+        _close(sd[k].cpu().numpy(), ref, 50 * TOL, f"found-flow final {k}")
+    assert opt.state[model.central_classifier.weight]["exp_avg"].shape == model.central_classifier.weight.shape
+    acc = tr.test_ntu_track_acc(model, loaders, {"test": ndv}, device=torch.device(DEV))
+    oacc = O.test_track_acc(head, split_np(dev), B, np.arange(ndv))
+    assert abs(float(acc) - float(oacc)) <= 1.0 / ndv + 1e-12
+
+
+def test_errors_are_loud():
+    import mfas_b200.ntu_searchable as ntu
+    from mfas_b200._lib import MfasError
+    args = make_args(16, 8, 1, bn=False, drpt=0.0)
+    with pytest.raises(UnboundLocalError):
+        ntu.Searchable_Skeleton_Image_Net(args, np.array([[0, 0, 0]]))
+    # a 1-row last batch in train mode is an error, like torch's BatchNorm1d
+    g = _group([[[0, 0, 0]]], 16, 8)
+    c = synthetic_ntu_cache(9, 1).to(DEV)
+    with pytest.raises(MfasError):
+        g.train_run(c, c, torch.arange(9)[None, None], None, [1e-3, 1e-3], 1, 8)
+    with pytest.raises(RuntimeError):
+        ntu.train_sampled_models([np.array([[0, 0, 0]])], ntu.Searchable_Skeleton_Image_Net, {}, make_args(16, 8, 1),
+                                 torch.device("cpu"))
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE config 2 at full size (N_train=10240, N_dev=5120): properties that need no oracle pass --
+    loss falls, the learnable signal is found, stats are self-consistent, LR warm restart is applied."""
+    import mfas_b200.ntu_searchable as ntu
+    args = make_args(128, 64, 2, bn=True, Ti=1)
+    train, dev = synthetic_ntu_cache(10240, 1), synthetic_ntu_cache(5120, 2)
+    loaders = {"train": FeatureCacheLoader(train, 64, True, 100), "dev": FeatureCacheLoader(dev, 64, True, 200)}
+    torch.manual_seed(0)
+    confs = [np.array(FOUND_CONFS[4]), np.array(FOUND_CONFS[1])]
+    accs = ntu.train_sampled_models(confs, ntu.Searchable_Skeleton_Image_Net, loaders, args, torch.device(DEV))
+    st = ntu.train_sampled_models.last_stats.numpy()
+    assert st.shape == (2, 2, 4)
+    assert (st[:, 1, 0] < st[:, 0, 0]).all(), "train loss must fall from epoch 0 to 1"
+    assert (st[:, :, 1] <= 10240).all() and (st[:, :, 3] <= 5120).all()
+    assert all(float(a) > 0.5 for a in accs), [float(a) for a in accs]
+    assert np.allclose([float(a) for a in accs], st[:, :, 3].max(1) / 5120)

@@ -97,3 +97,30 @@ def test_algorithmic_counts_match_survey():
     c = O.algorithmic_counts([[3, 1, 1], [1, 3, 0], [1, 1, 1], [3, 3, 0]], 128, 60, 64)
     assert c["F_sel"] == 7680 and c["P"] == 1041468 and c["K"] == [1536, 2432, 1408, 2688]
     assert abs(c["train_bytes"] - 26.96e6) < 0.01e6 and abs(c["eval_bytes"] - 6.13e6) < 0.01e6
+
+
+@pytest.mark.parametrize("name", ["cfg1", "mixL"])
+def test_torch_port_matches_reference_fixture(name):
+    """oracle/torch_port.py (the CPU baseline timed by bench.py) reproduces the reference run."""
+    import torch
+    from oracle.torch_port import FusionHeadTorch, train_candidate
+    torch.set_num_threads(1)
+    cs = GOLDEN_CASES[name]
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    train, dev = _setup(cs)
+    seed = int(g["meta/loader_seed"])
+    ltr = FeatureCacheLoader(train, cs["B"], True, seed)
+    ldv = FeatureCacheLoader(dev, cs["B"], True, seed + 50000)
+    inits = init_states(cs["confs"], cs["H"], 60, cs["bn"], cs["drpt"], cs["model_seed"])
+    E, B = cs["epochs"], cs["B"]
+    for ci, conf in enumerate(cs["confs"]):
+        m = FusionHeadTorch(conf, cs["H"], 60, cs["bn"], cs["drpt"])
+        m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in inits[ci].items() if not k.startswith("alphas")})
+        best, stats = train_candidate(
+            m, (train.ske_cat, train.rgb_cat, train.labels), (dev.ske_cat, dev.rgb_cat, dev.labels),
+            lambda ph, e, ci=ci: (ltr if ph == "train" else ldv).order_for_pass(ci * E + e), B, E, Ti=cs["Ti"])
+        assert abs(best - float(g[f"c{ci}/best_acc"])) < 1e-12
+        for k, v in m.state_dict().items():
+            ref = g[f"c{ci}/final/{k}/sample"]
+            got = sample_tensor(v.numpy())["sample"]
+            assert np.abs(got - ref).max() <= 1e-6 * max(float(g[f"c{ci}/final/{k}/amax"]), 1e-12), k
