@@ -104,7 +104,7 @@ typedef struct mfas_arenas {
 } mfas_arenas;
 
 typedef struct mfas_adam_hparams {   /* torch.optim.Adam(params, lr, weight_decay=1e-4), ntu_searchable.py:65 */
-  float beta1, beta2, eps, weight_decay;
+  double beta1, beta2, eps, weight_decay;   /* python floats: torch forms 1-beta in fp64 before rounding to fp32 */
 } mfas_adam_hparams;
 
 typedef struct mfas_run_args {       /* one train_ntu_track_acc run for every candidate of a group */

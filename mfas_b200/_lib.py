@@ -57,7 +57,7 @@ class Arenas(C.Structure):
 
 
 class AdamHParams(C.Structure):
-    _fields_ = [("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float)]
+    _fields_ = [("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double)]
 
 
 class RunArgs(C.Structure):

@@ -130,10 +130,10 @@ struct mfas_group {
   int64_t launches = 0;
 };
 
-static void set_adam(AdamH& a, float b1, float b2, float eps, float wd) {
-  a.beta1 = b1; a.beta2 = b2; a.eps = eps; a.wd = wd;
-  a.one_minus_beta1 = (float)(1.0 - (double)b1);
-  a.one_minus_beta2 = (float)(1.0 - (double)b2);
+static void set_adam(AdamH& a, double b1, double b2, double eps, double wd) {
+  a.beta1 = (float)b1; a.beta2 = (float)b2; a.eps = (float)eps; a.wd = (float)wd;
+  a.one_minus_beta1 = (float)(1.0 - b1);
+  a.one_minus_beta2 = (float)(1.0 - b2);
 }
 
 extern "C" int mfas_group_set_adam(mfas_group_t g, const mfas_adam_hparams* hp) {
@@ -171,7 +171,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
   if (!g) return fail(MFAS_ERR_NOMEM, "host allocation failed");
   g->device = device; g->n_cand = n_cand; g->bmax = batch_max;
   g->drop_p = dropout_p; g->drop_seed = dropout_seed;
-  set_adam(g->adam, 0.9f, 0.999f, 1e-8f, 1e-4f);
+  set_adam(g->adam, 0.9, 0.999, 1e-8, 1e-4);
   g->lay.assign(layouts, layouts + n_cand);
   g->hc.resize(n_cand);
   g->bound.assign(n_cand, 0);
