@@ -146,6 +146,13 @@ int mfas_group_destroy(mfas_group_t g);
 int mfas_group_bind(mfas_group_t g, int32_t cand, const mfas_arenas* arenas);
 int mfas_group_set_adam(mfas_group_t g, const mfas_adam_hparams* hp);
 int mfas_group_num_launches(mfas_group_t g, int64_t* out);   /* kernels launched through g so far */
+/* Which kernels serve this group: 1 = "tc" (tcgen05 tensor cores, 3xTF32; inner_representation_size a
+ * multiple of 64), 0 = "ffma" (fp32 CUDA cores; any multiple of 16). Both are sm_100a CUDA in this
+ * library; MFAS_ENGINE=ffma|tc in the environment forces one (bisecting / tests). */
+int mfas_group_engine(mfas_group_t g, int32_t* out);
+/* Synchronises the device and returns MFAS_ERR_CUDA if a kernel reported a failure (a bounded
+ * tensor-core barrier wait that expired) since the group was created. */
+int mfas_group_status(mfas_group_t g);
 
 /* Forward of every candidate over one batch: Searchable_Skeleton_Image_Net.forward
  * (ntu_searchable.py:206-247) given cached taps. rows: device int32 row ids, candidate c reads

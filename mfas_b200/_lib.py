@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "_mfas_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "mfas_abi.cu")]
-HEADERS = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "kernels_ffma.cuh")] + [
+HEADERS = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "kernels_ffma.cuh", "kernels_tc.cuh", "umma.cuh")] + [
     os.path.join(ROOT, "include", "mfas_b200.h")]
 
 MAX_LAYERS, MAX_BATCH, MAX_HIDDEN, MAX_CLASSES, NUM_TAPS = 8, 128, 256, 64, 4
@@ -81,6 +81,8 @@ SYMBOLS = {
     "mfas_group_bind": (C.c_int, [_P, C.c_int32, C.POINTER(Arenas)]),
     "mfas_group_set_adam": (C.c_int, [_P, C.POINTER(AdamHParams)]),
     "mfas_group_num_launches": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "mfas_group_engine": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "mfas_group_status": (C.c_int, [_P]),
     "mfas_forward": (C.c_int, [_P, C.POINTER(CacheDesc), _P, C.c_int64, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P]),
     "mfas_train_step": (C.c_int, [_P, C.POINTER(CacheDesc), _P, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_int64,
                                   _P, _P, _P, _P]),

@@ -4,11 +4,13 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
 
 #include "kernels_ffma.cuh"
+#include "kernels_tc.cuh"
 
 using namespace mfas;
 
@@ -128,6 +130,14 @@ struct mfas_group {
   bool dirty = true;
   size_t smem_head = 0, smem_bwd = 0;
   int64_t launches = 0;
+  // engine "tc" (tcgen05 tensor cores); engine 0 = "ffma"
+  int engine = 0;
+  int npad = 64;                  // batch rows padded to the MMA tile (64 or 128)
+  int fwd_splits[MFAS_MAX_LAYERS] = {0};
+  float* part = nullptr;          // split-K partial sums [n_cand][S_cap][Hp][npad]
+  long long part_stride = 0;
+  int* tc_err = nullptr;          // device flag set by a timed-out barrier wait
+  size_t smem_tc_fwd = 0, smem_tc_bwd = 0;
 };
 
 static void set_adam(AdamH& a, double b1, double b2, double eps, double wd) {
@@ -149,6 +159,8 @@ extern "C" int mfas_group_destroy(mfas_group_t g) {
   if (g->dc) cudaFree(g->dc);
   if (g->ws) cudaFree(g->ws);
   if (g->improved) cudaFree(g->improved);
+  if (g->part) cudaFree(g->part);
+  if (g->tc_err) cudaFree(g->tc_err);
   delete g;
   return MFAS_OK;
 }
@@ -255,7 +267,61 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     mfas_group_destroy(g);
     return code;
   }
+  // ---- engine selection: tensor cores whenever the shapes fit the MMA tile ------------------------
+  bool tc_ok = true;
+  for (int c = 0; c < n_cand; ++c) tc_ok = tc_ok && (g->lay[c].H % 64 == 0);
+  const char* env = getenv("MFAS_ENGINE");
+  if (env && !strcmp(env, "ffma")) tc_ok = false;
+  if (env && !strcmp(env, "tc") && !tc_ok) {
+    int code = fail(MFAS_ERR_UNSUPPORTED, "MFAS_ENGINE=tc needs inner_representation_size in {64,128,192,256}");
+    mfas_group_destroy(g);
+    return code;
+  }
+  if (tc_ok) {
+    g->engine = 1;
+    g->npad = batch_max <= 64 ? 64 : 128;
+    int s_cap = 1;
+    for (int l = 0; l < g->Lmax; ++l) {
+      g->fwd_splits[l] = ((g->Kmax[l] >> 5) + TC_KB_PER_CTA - 1) / TC_KB_PER_CTA;
+      s_cap = g->fwd_splits[l] > s_cap ? g->fwd_splits[l] : s_cap;
+    }
+    const int Hp = ((g->Hmax + 127) / 128) * 128;
+    g->part_stride = (long long)s_cap * Hp * g->npad;
+    g->smem_tc_fwd = 1024 + 32768 + 2 * (size_t)g->npad * 128;
+    g->smem_tc_bwd = 1024 + 2 * (size_t)(4 * g->npad * 128) + 1024 + 2 * (size_t)(2 * g->npad * 128);
+    e = cudaMalloc(&g->part, sizeof(float) * g->part_stride * n_cand);
+    if (e == cudaSuccess) e = cudaMalloc(&g->tc_err, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(g->tc_err, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_fwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + 32768 + 2 * 64 * 128));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_fwd<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + 32768 + 2 * 128 * 128));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_bwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + 2 * 32768 + 1024 + 2 * 16384));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_bwd<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + 2 * 65536 + 1024 + 2 * 32768));
+    if (e != cudaSuccess) {
+      int code = fail(MFAS_ERR_CUDA, "tc engine setup: %s", cudaGetErrorString(e));
+      mfas_group_destroy(g);
+      return code;
+    }
+  }
   *out = g;
+  return MFAS_OK;
+}
+
+extern "C" int mfas_group_engine(mfas_group_t g, int32_t* out) {
+  if (!g || !out) return fail(MFAS_ERR_INVALID, "null argument");
+  *out = g->engine;
+  return MFAS_OK;
+}
+
+// Synchronises the device and reports sticky kernel-side failures (a tcgen05 barrier that timed out).
+extern "C" int mfas_group_status(mfas_group_t g) {
+  if (!g) return fail(MFAS_ERR_INVALID, "null group");
+  DeviceGuard dg(g->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (g->tc_err) {
+    int flag = 0;
+    CUDA_TRY(cudaMemcpy(&flag, g->tc_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) return fail(MFAS_ERR_CUDA, "tensor-core pipeline barrier timed out in kernel %s", flag == 1 ? "k_tc_fwd" : "k_tc_bwd");
+  }
   return MFAS_OK;
 }
 
@@ -323,7 +389,24 @@ static int to_dcache(const mfas_group* g, const mfas_cache_desc* c, DCache* out)
 static int launch_step(mfas_group* g, const DCache& cache, const BatchRef& batch, bool train, bool bn_train,
                        float step_size, float bc2_sqrt, uint32_t step, const HeadOut& ho, cudaStream_t st) {
   const dim3 fgrid((g->Hmax + FWD_HT - 1) / FWD_HT, g->n_cand);
+  const TcErr terr{g->tc_err};
   for (int l = 0; l < g->Lmax; ++l) {
+    if (g->engine == 1) {
+      const dim3 gg(g->fwd_splits[l], (g->Hmax + 127) / 128, g->n_cand), ge((g->Hmax + 31) / 32, g->n_cand);
+      if (g->npad == 64) {
+        k_tc_fwd<64><<<gg, TC_THREADS, g->smem_tc_fwd, st>>>(g->dc, cache, batch, l, g->bmax, g->part, g->part_stride, terr);
+        LAUNCH_CHECK(g);
+        if (bn_train) k_tc_fwd_epi<true, 64><<<ge, TC_THREADS, 0, st>>>(g->dc, l, batch.n_rows, g->bmax, g->part, g->part_stride, g->drop_seed, g->drop_p, step);
+        else k_tc_fwd_epi<false, 64><<<ge, TC_THREADS, 0, st>>>(g->dc, l, batch.n_rows, g->bmax, g->part, g->part_stride, g->drop_seed, g->drop_p, step);
+      } else {
+        k_tc_fwd<128><<<gg, TC_THREADS, g->smem_tc_fwd, st>>>(g->dc, cache, batch, l, g->bmax, g->part, g->part_stride, terr);
+        LAUNCH_CHECK(g);
+        if (bn_train) k_tc_fwd_epi<true, 128><<<ge, TC_THREADS, 0, st>>>(g->dc, l, batch.n_rows, g->bmax, g->part, g->part_stride, g->drop_seed, g->drop_p, step);
+        else k_tc_fwd_epi<false, 128><<<ge, TC_THREADS, 0, st>>>(g->dc, l, batch.n_rows, g->bmax, g->part, g->part_stride, g->drop_seed, g->drop_p, step);
+      }
+      LAUNCH_CHECK(g);
+      continue;
+    }
     if (bn_train)
       k_fusion_fwd<true><<<fgrid, kThreads, 0, st>>>(g->dc, cache, batch, l, g->bmax, g->drop_seed, g->drop_p, step);
     else
@@ -340,6 +423,13 @@ static int launch_step(mfas_group* g, const DCache& cache, const BatchRef& batch
     k_dz<<<dim3((g->Hmax + 31) / 32, g->n_cand), kThreads, 0, st>>>(g->dc, l, batch.n_rows, g->bmax, g->adam, step_size,
                                                                   bc2_sqrt, g->drop_seed, g->drop_p, step);
     LAUNCH_CHECK(g);
+    if (g->engine == 1) {
+      const dim3 gb((g->Kmax[l] + TC_BWD_KT - 1) / TC_BWD_KT, g->n_cand);
+      if (g->npad == 64) k_tc_bwd<64><<<gb, TC_THREADS, g->smem_tc_bwd, st>>>(g->dc, cache, batch, l, g->bmax, g->adam, step_size, bc2_sqrt, terr);
+      else k_tc_bwd<128><<<gb, TC_THREADS, g->smem_tc_bwd, st>>>(g->dc, cache, batch, l, g->bmax, g->adam, step_size, bc2_sqrt, terr);
+      LAUNCH_CHECK(g);
+      continue;
+    }
     k_fusion_bwd<<<dim3((g->Kmax[l] + BWD_KT - 1) / BWD_KT, g->n_cand), kThreads, g->smem_bwd, st>>>(
         g->dc, cache, batch, l, g->bmax, g->adam, step_size, bc2_sqrt);
     LAUNCH_CHECK(g);

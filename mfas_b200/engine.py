@@ -188,6 +188,16 @@ class CandidateGroup:
         _lib.check(_lib.lib().mfas_group_set_adam(self._h, C.byref(hp)))
 
     @property
+    def engine(self):
+        e = C.c_int32()
+        _lib.check(_lib.lib().mfas_group_engine(self._h, C.byref(e)))
+        return {0: "ffma", 1: "tc"}[e.value]
+
+    def check(self):
+        """Synchronise and raise if a kernel reported a failure."""
+        _lib.check(_lib.lib().mfas_group_status(self._h))
+
+    @property
     def launches(self):
         n = C.c_int64()
         _lib.check(_lib.lib().mfas_group_num_launches(self._h, C.byref(n)))

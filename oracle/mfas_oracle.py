@@ -197,7 +197,7 @@ class FusionHead:
             W, b = s[f"fusion_layers.{l}.0.weight"], s[f"fusion_layers.{l}.0.bias"]
             z = (x @ W.T + b).astype(F32)
             a = _act(z, act)
-            rec = dict(x=x, a=a, xs=xs, xr=xr, gate=gate)
+            rec = dict(x=x, z=z, a=a, xs=xs, xr=xr, gate=gate)
             out = a
             if self.bn:
                 g_, be = s[f"fusion_layers.{l}.2.weight"], s[f"fusion_layers.{l}.2.bias"]
@@ -308,8 +308,20 @@ class FusionHead:
             self.state[name] = (p - step_size * (m / denom)).astype(F32)     # addcdiv_
             self.adam[name] = (m, v)
 
+    def kink_margin(self):
+        """Smallest |z| / max|z| over the piecewise-linear activations of the last train_step: when this
+        is ~1e-6 a different (equally valid) fp32 summation order flips a ReLU derivative, so gradients
+        of two correct implementations legitimately differ in that unit's row."""
+        m = 1.0
+        for l, rec in enumerate(self.last_tape["layers"]):
+            if int(self.conf[l][2]) != ACT_SIGMOID:
+                z = np.abs(rec["z"])
+                m = min(m, float(z.min() / max(z.max(), 1e-30)))
+        return m
+
     def train_step(self, ske_taps, rgb_taps, labels, lr):
         logits, tape = self.forward(ske_taps, rgb_taps, train=True)
+        self.last_tape = tape
         loss, _ = self.ce_loss(logits, labels)
         grads = self.backward(logits, labels, tape)
         self.adam_step(grads, lr)
