@@ -36,7 +36,8 @@ struct DCand {
   float* act;      // a_l  = phi(z_l)
   float* hid;      // h_l  = layer output (after BN / dropout)
   float* dh;       // dL/dh_l
-  float* dz;       // [Bmax][H] dL/dz of the layer being back-propagated
+  float* dz;       // [Bmax][H] dL/dz of the layer being back-propagated (ffma engine)
+  float* dzs;      // [L][Bmax][H] dL/dz of every layer (tc engine: all layers stream in one launch)
   float* mu;       // [L][H] batch (or running) mean used by the last forward
   float* invstd;   // [L][H]
   float* logits;   // [Bmax][C]
@@ -111,6 +112,22 @@ __device__ __forceinline__ void adam_update(float g, float& p, float& m, float& 
   v = v * a.beta2 + a.one_minus_beta2 * g * g;
   float denom = sqrtf(v) / bc2_sqrt + a.eps;
   p = p - step_size * (m / denom);
+}
+
+// Same update with the two IEEE divisions and the IEEE sqrt replaced by sqrt.approx / rcp.approx and a
+// host-side reciprocal of sqrt(1-beta2^t): ~12 instructions per element instead of ~50, which is what
+// keeps the fused weight-streaming kernel HBM-bound rather than issue-bound.  Differs from
+// adam_update by <= 3 ulp of the update term (tests hold it to 1e-6 of |p|).
+__device__ __forceinline__ void adam_update_fast(float g, float& p, float& m, float& v, const AdamH& a,
+                                                 float step_size, float inv_bc2_sqrt) {
+  g = fmaf(a.wd, p, g);
+  m = fmaf(a.one_minus_beta1, g - m, m);
+  v = fmaf(a.one_minus_beta2 * g, g, v * a.beta2);
+  float s, r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(s) : "f"(v));
+  const float denom = fmaf(s, inv_bc2_sqrt, a.eps);
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(denom));
+  p = fmaf(-step_size * m, r, p);
 }
 
 __device__ __forceinline__ float warp_sum(float x) {

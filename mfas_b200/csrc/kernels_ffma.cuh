@@ -195,8 +195,12 @@ k_fusion_fwd(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int 
 
 // ---------------------------------------------------------------------------------------------
 // K3: classifier + softmax cross-entropy (+ its backward and the classifier's Adam step).
-// One CTA per candidate.  dynamic smem: hs[bmax][H] | wcs[C][H+1] | lg[bmax][C+1] | rowloss[bmax]
+// One CTA of 512 threads per candidate; every inner product runs on float4 shared-memory reads laid
+// out so that a warp either broadcasts an address or walks consecutive 16-byte words.
+// dynamic smem: hs[bmax][hs_ld] | wcs[C][hs_ld] | lg[bmax][lg_ld]      (hs_ld = H+4 when it fits)
 // ---------------------------------------------------------------------------------------------
+constexpr int kHeadThreads = 512;
+
 struct HeadOut {
   float* logits;          // [n_cand][bmax][C] or null
   float* loss;            // [n_cand] or null
@@ -206,60 +210,89 @@ struct HeadOut {
 };
 
 template <bool TRAIN>
-__global__ void __launch_bounds__(kThreads)
-k_head(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, AdamH adam, float step_size,
-       float bc2_sqrt, HeadOut out) {
+__global__ void __launch_bounds__(kHeadThreads)
+k_head(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, int hs_ld, int lg_ld, AdamH adam,
+       float step_size, float bc2_sqrt, HeadOut out) {
   extern __shared__ __align__(16) float smem[];
   const int cand = blockIdx.x;
   const DCand& cd = cands[cand];
-  const int H = cd.H, C = cd.C, nrows = batch.n_rows, tid = threadIdx.x;
-  float* hs = smem;                         // [bmax][H]
-  float* wcs = hs + bmax * H;               // [C][H+1]
-  float* lg = wcs + C * (H + 1);            // [bmax][C+1]
-  float* rowloss = lg + bmax * (C + 1);     // [bmax]
-  int* rowok = reinterpret_cast<int*>(rowloss + bmax);   // [bmax]
-  int* lab = rowok + bmax;                                // [bmax]
+  const int H = cd.H, C = cd.C, nrows = batch.n_rows, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H4 = H >> 2;
+  float* hs = smem;                         // [bmax][hs_ld]
+  float* wcs = hs + (size_t)bmax * hs_ld;   // [C][hs_ld]
+  float* lg = wcs + (size_t)C * hs_ld;      // [bmax][lg_ld]
+  __shared__ float rowloss[MFAS_MAX_BATCH];
+  __shared__ int rowok[MFAS_MAX_BATCH], lab[MFAS_MAX_BATCH];
 
   const float* hl = cd.hid + (long long)(cd.L - 1) * bmax * H;
-  for (int i = tid; i < nrows * H; i += kThreads) hs[i] = hl[i];
   const float* Wc = cd.p + cd.oWc;
-  for (int i = tid; i < C * H; i += kThreads) wcs[(i / H) * (H + 1) + (i % H)] = Wc[i];
-  for (int r = tid; r < nrows; r += kThreads) lab[r] = (int)cache.labels[batch_row(batch, cand, r)];
+  for (int i = tid; i < nrows * H4; i += kHeadThreads) {
+    const int r = i / H4, c4 = i % H4;
+    *reinterpret_cast<float4*>(hs + r * hs_ld + c4 * 4) = *reinterpret_cast<const float4*>(hl + r * H + c4 * 4);
+  }
+  for (int i = tid; i < C * H4; i += kHeadThreads) {
+    const int r = i / H4, c4 = i % H4;
+    *reinterpret_cast<float4*>(wcs + r * hs_ld + c4 * 4) = *reinterpret_cast<const float4*>(Wc + r * H + c4 * 4);
+  }
+  for (int r = tid; r < nrows; r += kHeadThreads) lab[r] = (int)cache.labels[batch_row(batch, cand, r)];
   __syncthreads();
 
-  // logits = h W_c^T + b_c                                    (ntu_searchable.py:242)
-  for (int i = tid; i < nrows * C; i += kThreads) {
-    const int b = i / C, c = i % C;
-    float s = 0.f;
-    const float* hp = hs + b * H;
-    const float* wp = wcs + c * (H + 1);
-    for (int h = 0; h < H; ++h) s = fmaf(hp[h], wp[h], s);
-    s += cd.p[cd.obc + c];
-    lg[b * (C + 1) + c] = s;
-    cd.logits[b * C + c] = s;
-    if (out.logits) out.logits[((long long)cand * bmax + b) * C + c] = s;
+  // logits = h W_c^T + b_c (ntu_searchable.py:242): item = (class quad, batch row), rows run over lanes
+  const int CQ = (C + 3) >> 2, bpad = (nrows + 31) & ~31;
+  for (int it = tid; it < CQ * bpad; it += kHeadThreads) {
+    const int cq = it / bpad, b = it % bpad;
+    if (b >= nrows) continue;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4* hp = reinterpret_cast<const float4*>(hs + b * hs_ld);
+    const float4* wp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wp[i] = reinterpret_cast<const float4*>(wcs + min(cq * 4 + i, C - 1) * hs_ld);
+    for (int h = 0; h < H4; ++h) {
+      const float4 x = hp[h];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 w = wp[i][h];
+        acc[i] = fmaf(x.x, w.x, acc[i]); acc[i] = fmaf(x.y, w.y, acc[i]);
+        acc[i] = fmaf(x.z, w.z, acc[i]); acc[i] = fmaf(x.w, w.w, acc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = cq * 4 + i;
+      if (c < C) {
+        const float s = acc[i] + cd.p[cd.obc + c];
+        lg[b * lg_ld + c] = s;
+        cd.logits[b * C + c] = s;
+        if (out.logits) out.logits[((long long)cand * bmax + b) * C + c] = s;
+      }
+    }
   }
   __syncthreads();
 
-  // per-row log-softmax, NLL, argmax (first maximum), dlogits = (softmax - onehot)/n
-  if (tid < nrows) {
-    float* row = lg + tid * (C + 1);
-    float mx = row[0];
-    int am = 0;
-    for (int c = 1; c < C; ++c) if (row[c] > mx) { mx = row[c]; am = c; }
-    float se = 0.f;
-    for (int c = 0; c < C; ++c) se += expf(row[c] - mx);
-    const float lse = logf(se);
-    const int y = lab[tid];
-    rowloss[tid] = -((row[y] - mx) - lse);
-    rowok[tid] = (am == y) ? 1 : 0;
+  // per-row log-softmax, NLL, argmax (first maximum), dlogits = (softmax - onehot)/n : one warp per row
+  for (int r = warp; r < nrows; r += kHeadThreads / 32) {
+    float* row = lg + r * lg_ld;
+    float v0 = lane < C ? row[lane] : -INFINITY, v1 = lane + 32 < C ? row[lane + 32] : -INFINITY;
+    float mx = fmaxf(v0, v1);
+    int am = (v1 > v0) ? lane + 32 : lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+      if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
+    }
+    const float e0 = lane < C ? expf(v0 - mx) : 0.f, e1 = lane + 32 < C ? expf(v1 - mx) : 0.f;
+    const float lse = logf(warp_sum(e0 + e1));
+    const int y = lab[r];
+    if (lane == 0) {
+      rowloss[r] = -((row[y] - mx) - lse);
+      rowok[r] = (am == y) ? 1 : 0;
+    }
+    __syncwarp();
     if (TRAIN) {
       const float inv_n = 1.f / (float)nrows;
-      for (int c = 0; c < C; ++c) {
-        float p = expf((row[c] - mx) - lse);
-        if (c == y) p -= 1.f;
-        row[c] = p * inv_n;
-      }
+      if (lane < C) row[lane] = (expf((v0 - mx) - lse) - (lane == y ? 1.f : 0.f)) * inv_n;
+      if (lane + 32 < C) row[lane + 32] = (expf((v1 - mx) - lse) - (lane + 32 == y ? 1.f : 0.f)) * inv_n;
     }
   }
   __syncthreads();
@@ -278,29 +311,40 @@ k_head(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, 
   }
   if (!TRAIN) return;
 
-  // dh_L = dlogits W_c  (uses the pre-update classifier held in smem)
+  // dh_L = dlogits W_c (pre-update classifier in smem): item = (row, 4 columns), columns run over lanes
   float* dhp = cd.dh + (long long)(cd.L - 1) * bmax * H;
-  for (int i = tid; i < nrows * H; i += kThreads) {
-    const int b = i / H, h = i % H;
-    float s = 0.f;
-    const float* dl = lg + b * (C + 1);
-    for (int c = 0; c < C; ++c) s = fmaf(dl[c], wcs[c * (H + 1) + h], s);
-    dhp[i] = s;
+  for (int it = tid; it < nrows * H4; it += kHeadThreads) {
+    const int b = it / H4, h4 = it % H4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* dl = lg + b * lg_ld;
+    for (int c = 0; c < C; ++c) {
+      const float d = dl[c];
+      const float4 w = *reinterpret_cast<const float4*>(wcs + c * hs_ld + h4 * 4);
+      s.x = fmaf(d, w.x, s.x); s.y = fmaf(d, w.y, s.y); s.z = fmaf(d, w.z, s.z); s.w = fmaf(d, w.w, s.w);
+    }
+    *reinterpret_cast<float4*>(dhp + b * H + h4 * 4) = s;
   }
-  // dW_c = dlogits^T h_L  -> Adam ;  db_c = sum_b dlogits -> Adam
-  for (int i = tid; i < C * H; i += kThreads) {
-    const int c = i / H, h = i % H;
-    float g = 0.f;
-    for (int b = 0; b < nrows; ++b) g = fmaf(lg[b * (C + 1) + c], hs[b * H + h], g);
-    const long long o = cd.oWc + i;
-    if (cd.grad) cd.grad[o] = g;
-    float p = cd.p[o], m = cd.m[o], v = cd.v[o];
-    adam_update(g, p, m, v, adam, step_size, bc2_sqrt);
-    cd.p[o] = p; cd.m[o] = m; cd.v[o] = v;
+  // dW_c = dlogits^T h_L -> Adam : item = (class, 4 columns)
+  for (int it = tid; it < C * H4; it += kHeadThreads) {
+    const int c = it / H4, h4 = it % H4;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < nrows; ++b) {
+      const float d = lg[b * lg_ld + c];
+      const float4 x = *reinterpret_cast<const float4*>(hs + b * hs_ld + h4 * 4);
+      g.x = fmaf(d, x.x, g.x); g.y = fmaf(d, x.y, g.y); g.z = fmaf(d, x.z, g.z); g.w = fmaf(d, x.w, g.w);
+    }
+    const long long o = cd.oWc + (long long)c * H + h4 * 4;
+    if (cd.grad) *reinterpret_cast<float4*>(cd.grad + o) = g;
+    float4 p = *reinterpret_cast<float4*>(cd.p + o), m = *reinterpret_cast<float4*>(cd.m + o), v = *reinterpret_cast<float4*>(cd.v + o);
+    adam_update(g.x, p.x, m.x, v.x, adam, step_size, bc2_sqrt);
+    adam_update(g.y, p.y, m.y, v.y, adam, step_size, bc2_sqrt);
+    adam_update(g.z, p.z, m.z, v.z, adam, step_size, bc2_sqrt);
+    adam_update(g.w, p.w, m.w, v.w, adam, step_size, bc2_sqrt);
+    *reinterpret_cast<float4*>(cd.p + o) = p; *reinterpret_cast<float4*>(cd.m + o) = m; *reinterpret_cast<float4*>(cd.v + o) = v;
   }
-  for (int c = tid; c < C; c += kThreads) {
+  for (int c = tid; c < C; c += kHeadThreads) {                   // db_c = sum_b dlogits
     float g = 0.f;
-    for (int b = 0; b < nrows; ++b) g += lg[b * (C + 1) + c];
+    for (int b = 0; b < nrows; ++b) g += lg[b * lg_ld + c];
     const long long o = cd.obc + c;
     if (cd.grad) cd.grad[o] = g;
     float p = cd.p[o], m = cd.m[o], v = cd.v[o];

@@ -1,16 +1,23 @@
-// Engine "tc": the two GEMM-shaped stages of a fusion step on the 5th-gen tensor cores
-// (tcgen05.mma kind::tf32, accumulators in TMEM), fp32-accurate through a 3xTF32 split
-// (x = hi + lo; D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, fp32 accumulate).  The problem is HBM-bound
-// (10 FLOP/B), so operands are staged by coalesced vectorised loads through registers -- the gather of
-// the batch rows, the concat bookkeeping and the hi/lo split all happen on that pass -- and stored into
-// the canonical 128B-swizzled shared-memory tiles the tensor core reads.
+// Engine "tc": the GEMM-shaped stages of a training step on the 5th-gen tensor cores
+// (tcgen05.mma kind::tf32, accumulators in TMEM), fp32-accurate through a TF32 split
+// (x = hi + lo, both rounded to tf32; D = [A_lo*B_lo +] A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, fp32
+// accumulate; the small chain GEMMs take all four products, the two streaming GEMMs three).
 //
-//   forward :  zT[h, b] = sum_k W[h, k] * x[b, k]            A = W tile   (K-major), B = x tile (K-major)
-//              split over K across CTAs; partial sums reduced, then bias/act/BN by k_tc_fwd_epi
-//   backward:  dW[h, k] = sum_b dz[b, h] * x[b, k]           A = dz tile (MN-major), B = x tile (MN-major)
-//              fused Adam(L2) epilogue: the gradient never reaches HBM; hidden columns also give dh_{l-1}
+// The step is HBM-bound (10 FLOP/B): 95 % of its bytes are the feature columns of the L weight
+// matrices (forward: read once; backward: p/m/v read + written by Adam).  Those columns do not
+// depend on the chain h_0 -> h_1 -> ... so they are processed for ALL layers in one launch each way:
 //
-// Shapes: H in {64,128,256} (M tile 128, rows >= H are zero), batch <= 128.
+//   k_tc_fwd_all   zT_l[h,b] partials over the feature columns of every layer (split-K work items)
+//   k_fwd_layer    per layer: + h_{l-1} W_l[:,hid]^T (small), + bias, activation, BatchNorm, dropout
+//   k_head         classifier + softmax-CE (+ backward + Adam of the classifier)      [kernels_ffma.cuh]
+//   k_dzx          per layer, reverse: dh_l = dz_{l+1} W_{l+1}[:,hid] (small), BN/act backward -> dz_l
+//   k_tc_bwd_all   dW_l^T[k,h] = x^T dz for every layer, every 128-column chunk, Adam(L2) fused in the
+//                  epilogue straight out of TMEM: the gradient never reaches HBM
+//
+// Operands are staged by coalesced float4 loads through registers -- the gather of the batch rows, the
+// concat bookkeeping and the hi/lo split all happen on that pass -- into the canonical 128B-swizzled
+// shared-memory tiles the tensor core reads (umma.cuh).
+// Shapes: H multiple of 64 (<= 256), tap widths multiples of 128, batch <= 128.
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
@@ -18,11 +25,16 @@
 namespace mfas {
 
 constexpr int TC_THREADS = 256;
-constexpr int TC_KB_PER_CTA = 16;     // forward: k-blocks (of 32 columns) per CTA = 512 columns of K
-constexpr int TC_BWD_KT = 64;         // backward: weight columns per CTA
-constexpr int TC_G_LD = 65;           // epilogue staging tile leading dimension (conflict-free transpose)
+constexpr int TC_KB_PER_ITEM = 16;    // forward: k-blocks (32 columns each) per work item = 512 columns of K
+constexpr int TC_BWD_KT = 128;        // backward: weight columns (TMEM lanes) per work item
+constexpr int TC_BWD_HT = 64;         // backward: output rows h (TMEM columns) per work item
 
 struct TcErr { int* flag; };          // set when a bounded barrier wait expires (never hangs the GPU)
+
+__host__ __device__ __forceinline__ int tc_fwd_items(int d_ske, int d_rgb) {
+  return (((d_ske + d_rgb) >> 5) + TC_KB_PER_ITEM - 1) / TC_KB_PER_ITEM;
+}
+__host__ __device__ __forceinline__ int tc_bwd_items(int K) { return (K + TC_BWD_KT - 1) / TC_BWD_KT; }
 
 __device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, float4 x) {
   float4 h, l;
@@ -33,27 +45,34 @@ __device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward GEMM: partial zT over a K slice.  grid = (splits, H/128 m-tiles, candidates)
-// NPAD = batch rows padded to the MMA N (64 or 128).
+// forward, all layers: partial zT over a slice of FEATURE columns of one layer.
+// grid = (max items per candidate, ceil(H/128), candidates);  NPAD = batch padded to the MMA N.
+// part[cand][item][Hp][NPAD]
 // dynamic smem (1024-aligned): A_hi 16K | A_lo 16K | B_hi NPAD*128 | B_lo NPAD*128
 // ---------------------------------------------------------------------------------------------
 template <int NPAD>
-__global__ void __launch_bounds__(TC_THREADS)
-k_tc_fwd(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int layer, int bmax, float* part_base,
-         long long part_stride_cand, TcErr err) {
+__global__ void __launch_bounds__(TC_THREADS, NPAD == 64 ? 3 : 2)
+k_tc_fwd_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, float* part_base,
+             long long part_stride_cand, TcErr err) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int cand = blockIdx.z;
   const DCand& cd = cands[cand];
-  if (layer >= cd.L) return;
   const int H = cd.H;
   const int m0 = blockIdx.y * 128;
   if (m0 >= H) return;
+  // decode the work item -> (layer, split)
+  int layer = 0, split = blockIdx.x;
+  for (; layer < cd.L; ++layer) {
+    const int n = tc_fwd_items(cd.layer[layer].d_ske, cd.layer[layer].d_rgb);
+    if (split < n) break;
+    split -= n;
+  }
+  if (layer >= cd.L) return;
   const DLayer& ly = cd.layer[layer];
-  const int K = ly.K, nkb = K >> 5;
-  const int kb0 = blockIdx.x * TC_KB_PER_CTA;
-  if (kb0 >= nkb) return;
-  const int kb1 = min(nkb, kb0 + TC_KB_PER_CTA);
+  const int K = ly.K, fs = ly.d_ske, fr = ly.d_rgb;
+  const int nkb = (fs + fr) >> 5;
+  const int kb0 = split * TC_KB_PER_ITEM, kb1 = min(nkb, kb0 + TC_KB_PER_ITEM);
   const int nrows = batch.n_rows, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   uint8_t* a_hi = smem;
@@ -62,6 +81,7 @@ k_tc_fwd(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int laye
   uint8_t* b_lo = b_hi + NPAD * 128;
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ int ok_flag;
   __shared__ int rowid[MFAS_MAX_BATCH];
 
   if (warp == 0) umma::tmem_alloc(&tmem_slot, NPAD);
@@ -71,65 +91,58 @@ k_tc_fwd(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int laye
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tm = tmem_slot;
-
-  const int fs = ly.d_ske, fr = ly.d_rgb;
   const float* Wbase = cd.p + ly.oW;
-  const float* hid_prev = layer > 0 ? cd.hid + (long long)(layer - 1) * bmax * H : nullptr;
 
-  // register staging of one k-block: A = 128 rows x 8 float4, B = NPAD rows x 8 float4
-  constexpr int A_IT = 128 * 8 / TC_THREADS;     // 4
-  constexpr int B_IT = NPAD * 8 / TC_THREADS;    // 2 or 4
-  float4 ar[A_IT], br[B_IT];
-  auto load_kb = [&](int kb) {
-    const int kg = kb << 5;                      // first concat column of this k-block
-    // which concat source? (segment widths are multiples of 32, so a k-block never straddles)
-    const float* src; long long ld; int kl; bool gather = true;
+  constexpr int A_IT = 128 * 8 / TC_THREADS;     // 4 float4 of W per thread per k-block
+  constexpr int B_IT = NPAD * 8 / TC_THREADS;    // 2 or 4 float4 of x
+  struct Regs { float4 a[A_IT], b[B_IT]; };
+  auto load_kb = [&](Regs& rg, int kb) {
+    const int kg = kb << 5;                      // concat column; tap widths are multiples of 32
+    const float* src; long long ld; int kl;
     if (kg < fs) { src = cache.ske[ly.ske_tap]; ld = cache.ske_ld[ly.ske_tap]; kl = kg; }
-    else if (kg < fs + fr) { src = cache.rgb[ly.rgb_tap]; ld = cache.rgb_ld[ly.rgb_tap]; kl = kg - fs; }
-    else { src = hid_prev; ld = H; kl = kg - fs - fr; gather = false; }
+    else { src = cache.rgb[ly.rgb_tap]; ld = cache.rgb_ld[ly.rgb_tap]; kl = kg - fs; }
 #pragma unroll
     for (int i = 0; i < A_IT; ++i) {
       const int idx = tid + TC_THREADS * i, r = idx >> 3, c4 = idx & 7;
-      ar[i] = (m0 + r < H) ? *reinterpret_cast<const float4*>(Wbase + (long long)(m0 + r) * K + kg + c4 * 4)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      rg.a[i] = (m0 + r < H) ? *reinterpret_cast<const float4*>(Wbase + (long long)(m0 + r) * K + kg + c4 * 4)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int i = 0; i < B_IT; ++i) {
       const int idx = tid + TC_THREADS * i, r = idx >> 3, c4 = idx & 7;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < nrows) {
-        const long long row = gather ? (long long)rowid[r] : (long long)r;
-        v = __ldg(reinterpret_cast<const float4*>(src + row * ld + kl + c4 * 4));
-      }
-      br[i] = v;
+      rg.b[i] = (r < nrows) ? __ldg(reinterpret_cast<const float4*>(src + (long long)rowid[r] * ld + kl + c4 * 4))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  auto store_kb = [&]() {
+  auto store_kb = [&](const Regs& rg) {
 #pragma unroll
     for (int i = 0; i < A_IT; ++i) {
       const int idx = tid + TC_THREADS * i;
-      store_split(a_hi, a_lo, umma::sw128(idx >> 3, (idx & 7) * 16), ar[i]);
+      store_split(a_hi, a_lo, umma::sw128(idx >> 3, (idx & 7) * 16), rg.a[i]);
     }
 #pragma unroll
     for (int i = 0; i < B_IT; ++i) {
       const int idx = tid + TC_THREADS * i;
-      store_split(b_hi, b_lo, umma::sw128(idx >> 3, (idx & 7) * 16), br[i]);
+      store_split(b_hi, b_lo, umma::sw128(idx >> 3, (idx & 7) * 16), rg.b[i]);
     }
   };
 
   constexpr uint32_t idesc = umma::idesc_tf32(128, NPAD, false, false);
   uint32_t phase = 0;
   bool ok = true;
-  load_kb(kb0);
-  for (int kb = kb0; kb < kb1; ++kb) {
-    if (kb > kb0) {                                  // the tensor core must be done reading the tiles
-      ok = umma::mbar_wait(&bar, phase);
+  // one k-block: (wait for the tensor core to release the tiles) -> store this block's registers ->
+  // refill the same registers with the block two steps ahead -> issue this block's MMAs.
+  // Two register sets alternate, so every thread always has two k-blocks of global loads in flight.
+  auto stage = [&](Regs& rg, int kb) {
+    if (kb > kb0) {
+      ok = umma::cta_wait(&bar, phase, &ok_flag);
       phase ^= 1;
-      if (!ok) break;
+      if (!ok) return;
     }
-    store_kb();
+    store_kb(rg);
     umma::fence_async_smem();
     __syncthreads();
+    if (kb + 2 < kb1) load_kb(rg, kb + 2);
     if (tid == 0) {
       umma::tc_fence_after();
 #pragma unroll
@@ -145,18 +158,25 @@ k_tc_fwd(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int laye
       }
       umma::mma_commit(&bar);
     }
-    if (kb + 1 < kb1) load_kb(kb + 1);               // global loads fly while the MMAs run
+  };
+  Regs r0, r1;
+  load_kb(r0, kb0);
+  if (kb0 + 1 < kb1) load_kb(r1, kb0 + 1);
+  for (int kb = kb0; kb < kb1 && ok; kb += 2) {
+    stage(r0, kb);
+    if (kb + 1 < kb1 && ok) stage(r1, kb + 1);
   }
-  if (ok) ok = umma::mbar_wait(&bar, phase);
+  if (ok) ok = umma::cta_wait(&bar, phase, &ok_flag);
   if (!ok && tid == 0) atomicExch(err.flag, 1);
   umma::tc_fence_after();
 
   // epilogue: thread = one output column h (TMEM lane), 32 consecutive batch rows per tcgen05.ld
-  float* part = part_base + (long long)cand * part_stride_cand +
-                ((long long)blockIdx.x * (((H + 127) >> 7) << 7) + m0) * NPAD;
+  const int Hp = ((H + 127) >> 7) << 7;
+  float* part = part_base + (long long)cand * part_stride_cand + ((long long)blockIdx.x * Hp + m0) * NPAD;
   const int h_loc = (warp & 3) * 32 + lane;
 #pragma unroll
-  for (int c0 = (warp >> 2) * (NPAD / 2); c0 < (warp >> 2) * (NPAD / 2) + NPAD / 2; c0 += 32) {
+  for (int cc = 0; cc < NPAD / 64; ++cc) {
+    const int c0 = (warp >> 2) * (NPAD / 2) + cc * 32;
     float v[32];
     umma::tmem_ld32(tm + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
     float4* dst = reinterpret_cast<float4*>(part + (long long)h_loc * NPAD + c0);
@@ -169,255 +189,784 @@ k_tc_fwd(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int laye
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward epilogue: z = sum of the split-K partials (fixed order), + bias, activation, BatchNorm over
-// the batch (train: batch statistics + running-stat update; eval: running statistics), dropout.
-// grid = (H/32, candidates); a warp owns one output column at a time, lanes run over batch rows.
+// forward, one layer: z = (sum of this layer's feature partials, fixed order) + h_{l-1} W[:,hid]^T + b,
+// activation, BatchNorm over the batch (train: batch statistics + running-stat update; eval: running
+// statistics), dropout.  These kernels sit on the serial chain h_0 -> h_1 -> ..., so they are cut fine
+// for latency: grid = (H/8, candidates), one warp per output column, lanes run over batch rows.
+// dynamic smem: hp[bmax][H+1] | wh[8][H]
 // ---------------------------------------------------------------------------------------------
+constexpr int TC_CB = 16;             // output columns per CTA in the per-layer chain kernels (one warp each)
+constexpr int TC_CHAIN_THREADS = TC_CB * 32;
+
 template <bool TRAIN, int NPAD>
-__global__ void __launch_bounds__(TC_THREADS)
-k_tc_fwd_epi(const DCand* __restrict__ cands, int layer, int nrows, int bmax, const float* part_base,
-             long long part_stride_cand, uint32_t drop_seed, float drop_p, uint32_t step) {
+__global__ void __launch_bounds__(TC_CHAIN_THREADS)
+k_fwd_layer(const DCand* __restrict__ cands, int layer, int nrows, int bmax, const float* part_base,
+            long long part_stride_cand, uint32_t drop_seed, float drop_p, uint32_t step) {
+  extern __shared__ __align__(16) float fsm[];
   const DCand& cd = cands[blockIdx.y];
   if (layer >= cd.L) return;
   const int H = cd.H;
-  const int col0 = blockIdx.x * 32;
+  const int col0 = blockIdx.x * TC_CB;
   if (col0 >= H) return;
   const DLayer& ly = cd.layer[layer];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nsplit = ((ly.K >> 5) + TC_KB_PER_CTA - 1) / TC_KB_PER_CTA;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int item0 = 0;
+  for (int l = 0; l < layer; ++l) item0 += tc_fwd_items(cd.layer[l].d_ske, cd.layer[l].d_rgb);
+  const int nsplit = tc_fwd_items(ly.d_ske, ly.d_rgb);
   const int Hp = ((H + 127) >> 7) << 7;
-  const float* part = part_base + (long long)blockIdx.y * part_stride_cand;
+  const float* part = part_base + (long long)blockIdx.y * part_stride_cand + (long long)item0 * Hp * NPAD;
   const bool bn = (cd.flags & MFAS_FLAG_BN) != 0;
   const bool drop = TRAIN && (cd.flags & MFAS_FLAG_DROPOUT);
   const uint32_t dkey = drop ? dropout_key(drop_seed, (uint32_t)cd.cand_id, step, (uint32_t)layer) : 0u;
   const float dscale = drop ? 1.f / (1.f - drop_p) : 1.f;
   constexpr int NJ = NPAD / 32;
-  __shared__ float sa[MFAS_MAX_BATCH][33], sh[MFAS_MAX_BATCH][33];
+  __shared__ float sa[MFAS_MAX_BATCH][TC_CB + 1], sh[MFAS_MAX_BATCH][TC_CB + 1];
+  float* hp = fsm;                               // [nrows][H+1]
+  float* wh = fsm + (size_t)bmax * (H + 1);      // [TC_CB][H]
+  const bool has_hid = layer > 0;
+  const int c = col0 + warp;                     // this warp's output column (H % 8 == 0)
 
-  for (int cc = warp; cc < 32; cc += 8) {
-    const int c = col0 + cc;
-    if (c >= H) break;
-    float z[NJ];
+  // split-K partials first: their loads overlap the staging of h_{l-1} below
+  float z[NJ];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) z[j] = 0.f;
-    for (int s = 0; s < nsplit; ++s) {
-      const float* p = part + ((long long)s * Hp + c) * NPAD;
+  for (int j = 0; j < NJ; ++j) z[j] = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const float* p = part + ((long long)s * Hp + c) * NPAD;
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) z[j] += p[lane + 32 * j];
-    }
-    const float bias = cd.p[ly.ob + c];
-    float a[NJ];
+    for (int j = 0; j < NJ; ++j) z[j] += p[lane + 32 * j];
+  }
+  if (has_hid) {
+    const float* hprev = cd.hid + (long long)(layer - 1) * bmax * H;
+    {   // h_{l-1} -> smem, 8 independent loads in flight per thread
+      const int total = nrows * H;
+#pragma unroll 1
+      for (int i0 = tid; i0 < total; i0 += TC_CHAIN_THREADS * 8) {
+        float t[8];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) a[j] = (lane + 32 * j < nrows) ? act_fwd(z[j] + bias, ly.act) : 0.f;
-    float mean = 0.f, var = 1.f, istd = 1.f, gamma = 1.f, beta = 0.f;
-    if (bn) {
-      if (TRAIN) {
-        float s1 = 0.f;
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * TC_CHAIN_THREADS; t[u] = i < total ? hprev[i] : 0.f; }
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) s1 += a[j];
-        mean = warp_sum(s1) / (float)nrows;
-        float q = 0.f;
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) if (lane + 32 * j < nrows) { const float d = a[j] - mean; q = fmaf(d, d, q); }
-        var = warp_sum(q) / (float)nrows;
-      } else {
-        mean = cd.bufs[ly.orm + c];
-        var = cd.bufs[ly.orv + c];
-      }
-      istd = 1.f / sqrtf(var + kBnEps);
-      gamma = cd.p[ly.og + c]; beta = cd.p[ly.obe + c];
-      if (TRAIN && lane == 0) {
-        cd.mu[layer * H + c] = mean;
-        cd.invstd[layer * H + c] = istd;
-        const float n = (float)nrows;
-        float& rm = cd.bufs[ly.orm + c];
-        float& rv = cd.bufs[ly.orv + c];
-        rm = (1.f - kBnMomentum) * rm + kBnMomentum * mean;
-        rv = (1.f - kBnMomentum) * rv + kBnMomentum * (var * (n / (n - 1.f)));
-        if (c == 0) cd.nbt[layer] += 1;
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * TC_CHAIN_THREADS; if (i < total) hp[(i / H) * (H + 1) + (i % H)] = t[u]; }
       }
     }
+    const float* Wh = cd.p + ly.oW + ly.d_ske + ly.d_rgb + (long long)c * ly.K;
+    for (int j = lane; j < H; j += 32) wh[warp * H + j] = Wh[j];
+    __syncthreads();
+    const float* w = wh + warp * H;
+    float zh[NJ];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int r = lane + 32 * j;
-      if (r < nrows) {
-        float h = bn ? (a[j] - mean) * istd * gamma + beta : a[j];
-        if (drop) h = dropout_keep(dkey, (uint32_t)(r * H + c), drop_p) ? h * dscale : 0.f;
-        sa[r][cc] = a[j];
-        sh[r][cc] = h;
-      }
+    for (int j = 0; j < NJ; ++j) zh[j] = 0.f;
+    for (int jj = 0; jj < H; ++jj) {
+      const float wv = w[jj];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        if (lane + 32 * j < nrows) zh[j] = fmaf(hp[(lane + 32 * j) * (H + 1) + jj], wv, zh[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) z[j] += zh[j];
+  }
+  const float bias = cd.p[ly.ob + c];
+  float a[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) a[j] = (lane + 32 * j < nrows) ? act_fwd(z[j] + bias, ly.act) : 0.f;
+  float mean = 0.f, var = 1.f, istd = 1.f, gamma = 1.f, beta = 0.f;
+  if (bn) {
+    if (TRAIN) {
+      float s1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) s1 += a[j];
+      mean = warp_sum(s1) / (float)nrows;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) if (lane + 32 * j < nrows) { const float d = a[j] - mean; q = fmaf(d, d, q); }
+      var = warp_sum(q) / (float)nrows;
+    } else {
+      mean = cd.bufs[ly.orm + c];
+      var = cd.bufs[ly.orv + c];
+    }
+    istd = 1.f / sqrtf(var + kBnEps);
+    gamma = cd.p[ly.og + c]; beta = cd.p[ly.obe + c];
+    if (TRAIN && lane == 0) {
+      cd.mu[layer * H + c] = mean;
+      cd.invstd[layer * H + c] = istd;
+      const float n = (float)nrows;
+      float& rm = cd.bufs[ly.orm + c];
+      float& rv = cd.bufs[ly.orv + c];
+      rm = (1.f - kBnMomentum) * rm + kBnMomentum * mean;
+      rv = (1.f - kBnMomentum) * rv + kBnMomentum * (var * (n / (n - 1.f)));
+      if (c == 0) cd.nbt[layer] += 1;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int r = lane + 32 * j;
+    if (r < nrows) {
+      float h = bn ? (a[j] - mean) * istd * gamma + beta : a[j];
+      if (drop) h = dropout_keep(dkey, (uint32_t)(r * H + c), drop_p) ? h * dscale : 0.f;
+      sa[r][warp] = a[j];
+      sh[r][warp] = h;
     }
   }
   __syncthreads();
-  // coalesced write-out: a row of 32 columns = 128 bytes
-  float* actp = cd.act + (long long)layer * bmax * H;
+  float* actp = cd.act + (long long)layer * bmax * H;       // write-out: 16 columns = two 32-byte sectors per row
   float* hidp = cd.hid + (long long)layer * bmax * H;
-  for (int r = warp; r < nrows; r += 8) {
-    if (col0 + lane < H) {
-      if (TRAIN) actp[r * H + col0 + lane] = sa[r][lane];
-      hidp[r * H + col0 + lane] = sh[r][lane];
-    }
+  for (int r = tid / TC_CB; r < nrows; r += TC_CHAIN_THREADS / TC_CB) {
+    const int cc = tid % TC_CB;
+    if (TRAIN) actp[r * H + col0 + cc] = sa[r][cc];
+    hidp[r * H + col0 + cc] = sh[r][cc];
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward: dW[:, kc0:kc0+64] = dz^T x[:, kc0:kc0+64] on the tensor core, then, straight from TMEM:
-// Adam(L2) on p/m/v (coalesced through a transposed staging tile), and for hidden columns
-// dh_{l-1} = dz W[:, cols] from the pre-update weights.   grid = (ceil(Kmax/64), candidates)
-// BP = batch rows padded to the tile (64 or 128); MMA K runs over the batch.
-// dynamic smem (1024-aligned): A_hi | A_lo (4 blocks x BP x 128 B each) | 1 KB | B_hi | B_lo (2 blocks x BP x 128 B)
-//                              after the MMAs the A region (+1 KB) is reused: G[128][65] staging, Wsm[128][64]
+// backward chain, one layer: dh_l = dz_{l+1} W_{l+1}[:, hidden columns] (pre-update weights; for the
+// last layer dh comes from k_head), then dropout mask, BatchNorm backward, activation backward ->
+// dz_l (kept per layer for k_tc_bwd_all), plus gradients + Adam of the per-column vectors b, gamma, beta.
+// grid = (H/8, candidates); CTA = 8 columns x 32 row groups.  dynamic smem: dzn[bmax][H] | wt[H][9]
 // ---------------------------------------------------------------------------------------------
-template <int BP>
-__global__ void __launch_bounds__(TC_THREADS)
-k_tc_bwd(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int layer, int bmax, AdamH adam,
-         float step_size, float bc2_sqrt, TcErr err) {
+__global__ void __launch_bounds__(kThreads)
+k_dzx(const DCand* __restrict__ cands, int layer, int nrows, int bmax, AdamH adam, float step_size, float bc2_sqrt,
+      uint32_t drop_seed, float drop_p, uint32_t step) {
+  extern __shared__ __align__(16) float dsm[];
+  const DCand& cd = cands[blockIdx.y];
+  if (layer >= cd.L) return;
+  const int H = cd.H;
+  if (blockIdx.x * TC_CB >= H) return;
+  const int tid = threadIdx.x, col = tid % TC_CB, rg = tid / TC_CB;   // NRG row groups: rows rg, rg+NRG, ...
+  constexpr int NRG = kThreads / TC_CB, NI = MFAS_MAX_BATCH / NRG;
+  const int c = blockIdx.x * TC_CB + col;
+  const DLayer& ly = cd.layer[layer];
+  const bool bn = (cd.flags & MFAS_FLAG_BN) != 0;
+  const bool drop = (cd.flags & MFAS_FLAG_DROPOUT) != 0;
+  const uint32_t dkey = drop ? dropout_key(drop_seed, (uint32_t)cd.cand_id, step, (uint32_t)layer) : 0u;
+  const float dscale = drop ? 1.f / (1.f - drop_p) : 1.f;
+  const float* actp = cd.act + (long long)layer * bmax * H;
+  float* dzl = cd.dzs + (long long)layer * bmax * H;
+  __shared__ float red1[NRG][TC_CB + 1], red2[NRG][TC_CB + 1];
+  float dhv[NI];                                                  // dh of rows rg + NRG*i
+#pragma unroll
+  for (int i = 0; i < NI; ++i) dhv[i] = 0.f;
+
+  if (layer + 1 < cd.L) {
+    // dh_l[b][c] = sum_h dz_{l+1}[b][h] * W_{l+1}[h][fs+fr+c]
+    const DLayer& up = cd.layer[layer + 1];
+    float* dzn = dsm;                          // [nrows][H]
+    float* wt = dsm + (size_t)bmax * H;        // [H][9]
+    const float* dzg = cd.dzs + (long long)(layer + 1) * bmax * H;
+    {   // dz_{l+1} and the hidden columns of W_{l+1} -> smem, loads batched (latency is paid once)
+      const int total = nrows * H;
+#pragma unroll 1
+      for (int i0 = tid * 4; i0 < total; i0 += kThreads * 4 * 4) {
+        float4 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int i = i0 + u * kThreads * 4; t[u] = i < total ? *reinterpret_cast<const float4*>(dzg + i) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int i = i0 + u * kThreads * 4; if (i < total) *reinterpret_cast<float4*>(dzn + i) = t[u]; }
+      }
+      const float* Wg = cd.p + up.oW + up.d_ske + up.d_rgb + blockIdx.x * TC_CB;
+      float wv[MFAS_MAX_HIDDEN / NRG];
+#pragma unroll
+      for (int u = 0; u < MFAS_MAX_HIDDEN / NRG; ++u) { const int h = rg + NRG * u; wv[u] = h < H ? Wg[(long long)h * up.K + col] : 0.f; }
+#pragma unroll
+      for (int u = 0; u < MFAS_MAX_HIDDEN / NRG; ++u) { const int h = rg + NRG * u; if (h < H) wt[h * (TC_CB + 1) + col] = wv[u]; }
+    }
+    __syncthreads();
+    for (int h = 0; h < H; h += 4) {
+      const float w0 = wt[h * (TC_CB + 1) + col], w1 = wt[(h + 1) * (TC_CB + 1) + col], w2 = wt[(h + 2) * (TC_CB + 1) + col], w3 = wt[(h + 3) * (TC_CB + 1) + col];
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int r = rg + NRG * i;
+        if (r < nrows) {
+          const float4 d = *reinterpret_cast<const float4*>(dzn + (size_t)r * H + h);
+          dhv[i] = fmaf(d.x, w0, dhv[i]); dhv[i] = fmaf(d.y, w1, dhv[i]);
+          dhv[i] = fmaf(d.z, w2, dhv[i]); dhv[i] = fmaf(d.w, w3, dhv[i]);
+        }
+      }
+    }
+  } else {
+    const float* dhp = cd.dh + (long long)layer * bmax * H;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) if (rg + NRG * i < nrows) dhv[i] = dhp[(rg + NRG * i) * H + c];
+  }
+  if (drop) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int r = rg + NRG * i;
+      if (r < nrows) dhv[i] = dropout_keep(dkey, (uint32_t)(r * H + c), drop_p) ? dhv[i] * dscale : 0.f;
+    }
+  }
+  float av[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) av[i] = (rg + NRG * i < nrows) ? actp[(rg + NRG * i) * H + c] : 0.f;
+
+  float mu = 0.f, istd = 1.f, gam = 1.f, m1 = 0.f, m2 = 0.f, S1 = 0.f, S2 = 0.f;
+  if (bn) {
+    mu = cd.mu[layer * H + c]; istd = cd.invstd[layer * H + c]; gam = cd.p[ly.og + c];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+      if (rg + NRG * i < nrows) { s1 += dhv[i]; s2 = fmaf(dhv[i], (av[i] - mu) * istd, s2); }
+    red1[rg][col] = s1; red2[rg][col] = s2;
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < NRG; ++g) { S1 += red1[g][col]; S2 += red2[g][col]; }
+    m1 = S1 / (float)nrows; m2 = S2 / (float)nrows;
+    __syncthreads();
+  }
+  float sdz = 0.f;
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int r = rg + NRG * i;
+    if (r < nrows) {
+      float da = dhv[i];
+      if (bn) { const float ah = (av[i] - mu) * istd; da = gam * istd * (dhv[i] - m1 - ah * m2); }
+      const float dz = da * act_bwd(av[i], ly.act);
+      dzl[r * H + c] = dz;
+      sdz += dz;
+    }
+  }
+  red1[rg][col] = sdz;
+  __syncthreads();
+  if (rg == 0) {
+    float db = 0.f;
+#pragma unroll
+    for (int g = 0; g < NRG; ++g) db += red1[g][col];
+    auto upd = [&](long long o, float g) {
+      if (cd.grad) cd.grad[o] = g;
+      float p = cd.p[o], m = cd.m[o], v = cd.v[o];
+      adam_update(g, p, m, v, adam, step_size, bc2_sqrt);
+      cd.p[o] = p; cd.m[o] = m; cd.v[o] = v;
+    };
+    upd(ly.ob + c, db);
+    if (bn) { upd(ly.og + c, S2); upd(ly.obe + c, S1); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chain kernels on the tensor core.  The per-layer steps of the serial chain (hidden-state GEMM +
+// BatchNorm forward, and its mirror image backward) are tiny, so what matters is latency: one CTA per
+// (candidate, 128 output columns) does the whole thing.  The MMA is oriented so that a TMEM lane is an
+// output column: each epilogue thread then owns ALL batch rows of its column in registers, and the
+// BatchNorm reductions over the batch are plain sequential sums inside a thread (deterministic, no
+// shuffles, no shared memory), while global reads/writes stay coalesced across the 32 lanes of a warp.
+//
+// k_chain_fwd:  zT[c,b] = sum_j W_l[c, hid j] h_{l-1}[b, j]  (+ feature partials + bias) -> act -> BN
+//               A = W_l hidden columns (K-major), B = h_{l-1} (K-major); K = H in passes of 128
+// dynamic smem (1024-aligned), per pass of <= 4 k-blocks: A_hi | A_lo (4 x 16 KB) | B_hi | B_lo (4 x NPAD*128 B)
+// ---------------------------------------------------------------------------------------------
+template <int NPAD> struct ChainCfg {
+  static constexpr int THREADS = 512;                     // 16 warps: 4 per TMEM lane quarter
+  static constexpr int NB = NPAD / 4;                     // batch rows per epilogue thread
+  static constexpr int PASS = NPAD == 64 ? 128 : 64;      // K columns staged per pass (smem budget)
+  static constexpr int NKB = PASS / 32;
+  static constexpr size_t SMEM = 1024 + 2 * (size_t)NKB * 16384 + 2 * (size_t)NKB * NPAD * 128;
+};
+
+template <bool TRAIN, int NPAD>
+__global__ void __launch_bounds__(ChainCfg<NPAD>::THREADS)
+k_chain_fwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, const float* part_base,
+            long long part_stride_cand, uint32_t drop_seed, float drop_p, uint32_t step, TcErr err) {
+  constexpr int THREADS = ChainCfg<NPAD>::THREADS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int cand = blockIdx.y;
-  const DCand& cd = cands[cand];
+  const DCand& cd = cands[blockIdx.y];
   if (layer >= cd.L) return;
+  const int H = cd.H;
+  const int m0 = blockIdx.x * 128;
+  if (m0 >= H) return;
   const DLayer& ly = cd.layer[layer];
-  const int K = ly.K, H = cd.H;
-  const int kc0 = blockIdx.x * TC_BWD_KT;
-  if (kc0 >= K) return;
-  const int kw = min(TC_BWD_KT, K - kc0);
-  const int nrows = batch.n_rows, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  constexpr uint32_t A_BLK = BP * 128, A_TILE = 4 * A_BLK, B_TILE = 2 * A_BLK;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool has_hid = layer > 0;
+  constexpr uint32_t A_KB = 16384, B_KB = NPAD * 128;
+  constexpr int PASS = ChainCfg<NPAD>::PASS, NKB = ChainCfg<NPAD>::NKB;
   uint8_t* a_hi = smem;
-  uint8_t* a_lo = a_hi + A_TILE;
-  uint8_t* b_hi = a_lo + A_TILE + 1024;
-  uint8_t* b_lo = b_hi + B_TILE;
-  float* G = reinterpret_cast<float*>(smem);                        // [128][65]  aliases the A tiles (dead after the MMAs)
-  float* Wsm = reinterpret_cast<float*>(smem + 128 * TC_G_LD * 4);  // [128][64]  aliases A_lo + the 1 KB gap; never the B tiles
-  static_assert(128 * TC_G_LD * 4 + 128 * 64 * 4 <= 2 * A_TILE + 1024, "staging tiles must fit in the A region");
+  uint8_t* a_lo = a_hi + NKB * A_KB;
+  uint8_t* b_hi = a_lo + NKB * A_KB;
+  uint8_t* b_lo = b_hi + NKB * B_KB;
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
-
-  if (warp == 0) umma::tmem_alloc(&tmem_slot, 64);
+  __shared__ int ok_flag;
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, NPAD);
   if (tid == 0) { umma::mbar_init(&bar, 1); umma::fence_mbar_init(); }
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tm = tmem_slot;
 
-  // ---- B tile: x[:, kc0:kc0+64] (MN-major: one row per batch row, 2 blocks of 32 columns) ----------
+  uint32_t phase = 0;
+  bool ok = true;
+  if (has_hid) {
+    const float* Wh = cd.p + ly.oW + ly.d_ske + ly.d_rgb;              // hidden columns of W_l
+    const float* hprev = cd.hid + (long long)(layer - 1) * bmax * H;
+    constexpr uint32_t idesc = umma::idesc_tf32(128, NPAD, false, false);
+    for (int j0 = 0; j0 < H; j0 += PASS) {                              // passes of <= NKB k-blocks
+      const int jw = min(PASS, H - j0), f4 = jw >> 2;                   // float4 per row in this pass
+      if (j0 > 0) { ok = umma::cta_wait(&bar, phase, &ok_flag); phase ^= 1; if (!ok) break; }
+      for (int i0 = tid; i0 < 128 * f4; i0 += THREADS * 4) {            // A: 128 rows of W
+        float4 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * THREADS, r = i / f4, c4 = i % f4;
+          t[u] = (i < 128 * f4 && m0 + r < H) ? *reinterpret_cast<const float4*>(Wh + (long long)(m0 + r) * ly.K + j0 + c4 * 4)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * THREADS, r = i / f4, c4 = i % f4;
+          if (i < 128 * f4) store_split(a_hi, a_lo, (uint32_t)(c4 >> 3) * A_KB + umma::sw128(r, (c4 & 7) * 16), t[u]);
+        }
+      }
+      for (int i0 = tid; i0 < NPAD * f4; i0 += THREADS * 4) {           // B: batch rows of h_{l-1}
+        float4 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * THREADS, r = i / f4, c4 = i % f4;
+          t[u] = (i < NPAD * f4 && r < nrows) ? *reinterpret_cast<const float4*>(hprev + (long long)r * H + j0 + c4 * 4)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * THREADS, r = i / f4, c4 = i % f4;
+          if (i < NPAD * f4) store_split(b_hi, b_lo, (uint32_t)(c4 >> 3) * B_KB + umma::sw128(r, (c4 & 7) * 16), t[u]);
+        }
+      }
+      umma::fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        umma::tc_fence_after();
+        for (int ks = 0; ks < (jw >> 3); ++ks) {
+          const uint32_t oa = (uint32_t)(ks >> 2) * A_KB + (ks & 3) * 32u, ob = (uint32_t)(ks >> 2) * B_KB + (ks & 3) * 32u;
+          const uint64_t dah = umma::smem_desc(umma::smem_u32(a_hi) + oa, 16, 1024), dal = umma::smem_desc(umma::smem_u32(a_lo) + oa, 16, 1024);
+          const uint64_t dbh = umma::smem_desc(umma::smem_u32(b_hi) + ob, 16, 1024), dbl = umma::smem_desc(umma::smem_u32(b_lo) + ob, 16, 1024);
+          umma::mma_tf32(tm, dal, dbl, idesc, (j0 > 0 || ks > 0) ? 1u : 0u);
+          umma::mma_tf32(tm, dal, dbh, idesc, 1u);
+          umma::mma_tf32(tm, dah, dbl, idesc, 1u);
+          umma::mma_tf32(tm, dah, dbh, idesc, 1u);
+        }
+        umma::mma_commit(&bar);
+      }
+    }
+  }
+
+  // ---- epilogue: thread = (output column c = m0 + 32q + lane, batch rows [cg*NB, cg*NB+NB)), q = warp%4 (the
+  //      TMEM lane quarter this warp may read), cg = warp/4.  BatchNorm sums: per-thread partial, then a
+  //      fixed-order combine of the 4 row groups through shared memory (deterministic).
+  constexpr int NB = ChainCfg<NPAD>::NB;
+  const int q = warp & 3, cg = warp >> 2, cl = q * 32 + lane, b0 = cg * NB;
+  const int c = m0 + cl;
+  const bool mine = c < H;
+  __shared__ float red[4][128];
+  float z[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) z[b] = 0.f;
+  if (mine) {      // feature partials of this layer (their loads fly while the MMAs run)
+    int item0 = 0;
+    for (int l = 0; l < layer; ++l) item0 += tc_fwd_items(cd.layer[l].d_ske, cd.layer[l].d_rgb);
+    const int nsplit = tc_fwd_items(ly.d_ske, ly.d_rgb);
+    const int Hp = ((H + 127) >> 7) << 7;
+    const float* part = part_base + (long long)blockIdx.y * part_stride_cand + ((long long)item0 * Hp + c) * NPAD + b0;
+    for (int s = 0; s < nsplit; ++s) {
+      const float4* p4 = reinterpret_cast<const float4*>(part + (long long)s * Hp * NPAD);
+#pragma unroll
+      for (int k = 0; k < NB / 4; ++k) {
+        const float4 v = p4[k];
+        z[4 * k] += v.x; z[4 * k + 1] += v.y; z[4 * k + 2] += v.z; z[4 * k + 3] += v.w;
+      }
+    }
+  }
+  if (has_hid) {
+    if (ok) ok = umma::cta_wait(&bar, phase, &ok_flag);
+    if (!ok && tid == 0) atomicExch(err.flag, 3);
+    umma::tc_fence_after();
+    float v[NB];
+    if (NB == 16) umma::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + b0, v);
+    else umma::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + b0, v);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) z[b] += v[b];
+  }
+  const bool bn = (cd.flags & MFAS_FLAG_BN) != 0;
+  const bool drop = TRAIN && (cd.flags & MFAS_FLAG_DROPOUT);
+  const float bias = mine ? cd.p[ly.ob + c] : 0.f;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) z[b] = (mine && b0 + b < nrows) ? act_fwd(z[b] + bias, ly.act) : 0.f;   // z <- a = phi(z)
+  float mean = 0.f, var = 1.f, istd = 1.f, gamma = 1.f, beta = 0.f;
+  if (bn) {
+    if (TRAIN) {
+      float s1 = 0.f;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) s1 += z[b];
+      red[cg][cl] = s1;
+      __syncthreads();
+      mean = (red[0][cl] + red[1][cl] + red[2][cl] + red[3][cl]) / (float)nrows;
+      __syncthreads();
+      float qq = 0.f;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) if (b0 + b < nrows) { const float d = z[b] - mean; qq = fmaf(d, d, qq); }
+      red[cg][cl] = qq;
+      __syncthreads();
+      var = (red[0][cl] + red[1][cl] + red[2][cl] + red[3][cl]) / (float)nrows;
+    } else if (mine) {
+      mean = cd.bufs[ly.orm + c];
+      var = cd.bufs[ly.orv + c];
+    }
+    istd = 1.f / sqrtf(var + kBnEps);
+    if (mine) { gamma = cd.p[ly.og + c]; beta = cd.p[ly.obe + c]; }
+    if (TRAIN && mine && cg == 0) {
+      cd.mu[layer * H + c] = mean;
+      cd.invstd[layer * H + c] = istd;
+      const float n = (float)nrows;
+      float& rm = cd.bufs[ly.orm + c];
+      float& rv = cd.bufs[ly.orv + c];
+      rm = (1.f - kBnMomentum) * rm + kBnMomentum * mean;
+      rv = (1.f - kBnMomentum) * rv + kBnMomentum * (var * (n / (n - 1.f)));
+      if (c == 0) cd.nbt[layer] += 1;
+    }
+  }
+  if (mine) {
+    const uint32_t dkey = drop ? dropout_key(drop_seed, (uint32_t)cd.cand_id, step, (uint32_t)layer) : 0u;
+    const float dscale = drop ? 1.f / (1.f - drop_p) : 1.f;
+    float* actp = cd.act + ((long long)layer * bmax + b0) * H + c;     // lanes = consecutive columns: coalesced rows
+    float* hidp = cd.hid + ((long long)layer * bmax + b0) * H + c;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      if (b0 + b < nrows) {
+        float h = bn ? (z[b] - mean) * istd * gamma + beta : z[b];
+        if (drop) h = dropout_keep(dkey, (uint32_t)((b0 + b) * H + c), drop_p) ? h * dscale : 0.f;
+        if (TRAIN) *actp = z[b];
+        *hidp = h;
+      }
+      actp += H; hidp += H;
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_free(tm, NPAD);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_chain_bwd: dhT_l[c,b] = sum_h W_{l+1}[h, hid c] dz_{l+1}[b,h]  (pre-update weights; the last layer
+//              takes dh from k_head) -> dropout mask -> BatchNorm backward -> activation backward -> dz_l,
+//              plus gradients and Adam of the per-column vectors b_l, gamma_l, beta_l.
+//              A = hidden columns of W_{l+1} (MN-major: one smem row per h), B = dz_{l+1} (K-major)
+// dynamic smem (1024-aligned), per pass of PASS h: A_hi | A_lo (4 blocks x PASS rows x 128 B) | B_hi | B_lo (NKB x NPAD*128 B)
+// ---------------------------------------------------------------------------------------------
+template <int NPAD>
+__global__ void __launch_bounds__(ChainCfg<NPAD>::THREADS)
+k_chain_bwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, AdamH adam, float step_size,
+            float bc2_sqrt, uint32_t drop_seed, float drop_p, uint32_t step, TcErr err) {
+  constexpr int THREADS = ChainCfg<NPAD>::THREADS;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const DCand& cd = cands[blockIdx.y];
+  if (layer >= cd.L) return;
+  const int H = cd.H;
+  const int m0 = blockIdx.x * 128;
+  if (m0 >= H) return;
+  const DLayer& ly = cd.layer[layer];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool has_up = layer + 1 < cd.L;
+  constexpr int PASS = ChainCfg<NPAD>::PASS, NKB = ChainCfg<NPAD>::NKB;
+  constexpr uint32_t A_BLK = PASS * 128, B_KB = NPAD * 128;      // A block = 32 columns x PASS h rows
+  uint8_t* a_hi = smem;
+  uint8_t* a_lo = a_hi + 4 * A_BLK;
+  uint8_t* b_hi = a_lo + 4 * A_BLK;
+  uint8_t* b_lo = b_hi + NKB * B_KB;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int ok_flag;
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, NPAD);
+  if (tid == 0) { umma::mbar_init(&bar, 1); umma::fence_mbar_init(); }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tm = tmem_slot;
+
+  uint32_t phase = 0;
+  bool ok = true;
+  if (has_up) {
+    const DLayer& up = cd.layer[layer + 1];
+    const float* Wu = cd.p + up.oW + up.d_ske + up.d_rgb + m0;       // W_{l+1}[h][hid m0 + .]
+    const float* dzu = cd.dzs + (long long)(layer + 1) * bmax * H;
+    const int mw = min(128, H - m0);                                   // valid output columns of this tile
+    constexpr uint32_t idesc = umma::idesc_tf32(128, NPAD, true, false);
+    for (int h0 = 0; h0 < H; h0 += PASS) {                             // passes of PASS rows of W_{l+1}
+      const int hw = min(PASS, H - h0);
+      if (h0 > 0) { ok = umma::cta_wait(&bar, phase, &ok_flag); phase ^= 1; if (!ok) break; }
+      for (int i0 = tid; i0 < hw * 32; i0 += THREADS * 4) {            // A: hw rows (h) x 32 float4 (128 columns)
+        float4 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * THREADS, r = i >> 5, c4 = i & 31;
+          t[u] = (i < hw * 32 && c4 * 4 < mw) ? *reinterpret_cast<const float4*>(Wu + (long long)(h0 + r) * up.K + c4 * 4)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * THREADS, r = i >> 5, c4 = i & 31;
+          if (i < hw * 32) store_split(a_hi, a_lo, (uint32_t)(c4 >> 3) * A_BLK + umma::sw128_b32(r, (c4 & 7) * 16), t[u]);
+        }
+      }
+      const int f4 = hw >> 2;
+      for (int i0 = tid; i0 < NPAD * f4; i0 += THREADS * 4) {          // B: batch rows of dz_{l+1}[:, h0:h0+hw]
+        float4 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * THREADS, r = i / f4, c4 = i % f4;
+          t[u] = (i < NPAD * f4 && r < nrows) ? *reinterpret_cast<const float4*>(dzu + (long long)r * H + h0 + c4 * 4)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * THREADS, r = i / f4, c4 = i % f4;
+          if (i < NPAD * f4) store_split(b_hi, b_lo, (uint32_t)(c4 >> 3) * B_KB + umma::sw128(r, (c4 & 7) * 16), t[u]);
+        }
+      }
+      umma::fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        umma::tc_fence_after();
+        for (int ks = 0; ks < (hw >> 3); ++ks) {
+          const uint32_t oa = ks * 1024u, ob = (uint32_t)(ks >> 2) * B_KB + (ks & 3) * 32u;
+          const uint64_t dah = umma::smem_desc(umma::smem_u32(a_hi) + oa, A_BLK, 512, umma::kLayoutSw128Base32);
+          const uint64_t dal = umma::smem_desc(umma::smem_u32(a_lo) + oa, A_BLK, 512, umma::kLayoutSw128Base32);
+          const uint64_t dbh = umma::smem_desc(umma::smem_u32(b_hi) + ob, 16, 1024), dbl = umma::smem_desc(umma::smem_u32(b_lo) + ob, 16, 1024);
+          umma::mma_tf32(tm, dal, dbl, idesc, (h0 > 0 || ks > 0) ? 1u : 0u);
+          umma::mma_tf32(tm, dal, dbh, idesc, 1u);
+          umma::mma_tf32(tm, dah, dbl, idesc, 1u);
+          umma::mma_tf32(tm, dah, dbh, idesc, 1u);
+        }
+        umma::mma_commit(&bar);
+      }
+    }
+  }
+
+  // ---- epilogue: thread = (column c = m0 + 32q + lane of layer l, batch rows [cg*NB, cg*NB+NB)) ----------
+  constexpr int NB = ChainCfg<NPAD>::NB;
+  const int q = warp & 3, cg = warp >> 2, cl = q * 32 + lane, b0 = cg * NB;
+  const int c = m0 + cl;
+  const bool mine = c < H;
+  const bool bn = (cd.flags & MFAS_FLAG_BN) != 0;
+  const bool drop = (cd.flags & MFAS_FLAG_DROPOUT) != 0;
+  __shared__ float red1[4][128], red2[4][128];
+  float av[NB], dh[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) { av[b] = 0.f; dh[b] = 0.f; }
+  if (mine) {                                   // activations of this column (loads fly during the MMAs)
+    const float* actp = cd.act + ((long long)layer * bmax + b0) * H + c;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) if (b0 + b < nrows) av[b] = actp[(long long)b * H];
+    if (!has_up) {
+      const float* dhp = cd.dh + ((long long)layer * bmax + b0) * H + c;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) if (b0 + b < nrows) dh[b] = dhp[(long long)b * H];
+    }
+  }
+  if (has_up) {
+    if (ok) ok = umma::cta_wait(&bar, phase, &ok_flag);
+    if (!ok && tid == 0) atomicExch(err.flag, 4);
+    umma::tc_fence_after();
+    if (NB == 16) umma::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + b0, dh);
+    else umma::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + b0, dh);
+  }
+  if (drop && mine) {
+    const uint32_t dkey = dropout_key(drop_seed, (uint32_t)cd.cand_id, step, (uint32_t)layer);
+    const float dscale = 1.f / (1.f - drop_p);
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+      if (b0 + b < nrows) dh[b] = dropout_keep(dkey, (uint32_t)((b0 + b) * H + c), drop_p) ? dh[b] * dscale : 0.f;
+  }
+  float mu = 0.f, istd = 1.f, gam = 1.f, S1 = 0.f, S2 = 0.f;
+  if (bn) {
+    if (mine) { mu = cd.mu[layer * H + c]; istd = cd.invstd[layer * H + c]; gam = cd.p[ly.og + c]; }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) if (b0 + b < nrows) { s1 += dh[b]; s2 = fmaf(dh[b], (av[b] - mu) * istd, s2); }
+    red1[cg][cl] = s1; red2[cg][cl] = s2;
+    __syncthreads();
+    S1 = red1[0][cl] + red1[1][cl] + red1[2][cl] + red1[3][cl];
+    S2 = red2[0][cl] + red2[1][cl] + red2[2][cl] + red2[3][cl];
+    __syncthreads();
+  }
+  const float m1 = S1 / (float)nrows, m2 = S2 / (float)nrows;
+  float db = 0.f;
+  if (mine) {
+    float* dzl = cd.dzs + ((long long)layer * bmax + b0) * H + c;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      if (b0 + b < nrows) {
+        float da = dh[b];
+        if (bn) { const float ah = (av[b] - mu) * istd; da = gam * istd * (dh[b] - m1 - ah * m2); }
+        const float dz = da * act_bwd(av[b], ly.act);
+        *dzl = dz;
+        db += dz;
+      }
+      dzl += H;
+    }
+  }
+  red1[cg][cl] = db;
+  __syncthreads();
+  if (mine && cg == 0) {
+    db = red1[0][cl] + red1[1][cl] + red1[2][cl] + red1[3][cl];
+    auto upd = [&](long long o, float g) {
+      if (cd.grad) cd.grad[o] = g;
+      float p = cd.p[o], m = cd.m[o], v = cd.v[o];
+      adam_update(g, p, m, v, adam, step_size, bc2_sqrt);
+      cd.p[o] = p; cd.m[o] = m; cd.v[o] = v;
+    };
+    upd(ly.ob + c, db);
+    if (bn) { upd(ly.og + c, S2); upd(ly.obe + c, S1); }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_free(tm, NPAD);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, all layers: one work item = 128 weight columns (k) x 64 output rows (h) of one layer.
+//   dW^T[k,h] = sum_b x[b,k] dz[b,h]      A = x chunk (MN-major, M = k), B = dz slice (MN-major, N = h)
+// TMEM lane = weight column k, so for a fixed h the 32 lanes of a warp touch 32 consecutive floats of
+// W[h,:], m[h,:], v[h,:]: every Adam access is a coalesced 128-byte line with no transpose.
+// 512 threads: 4 warps per TMEM lane quarter, each owning 16 of the 64 rows; every thread keeps
+// 2 x 12 independent loads in flight (two register sets, software-pipelined; the first two sets are
+// requested before the MMAs are waited for).  2 CTAs/SM -> 32 warps/SM hide the HBM latency.
+// (Measured alternatives, kept out: draining TMEM to a shared-memory tile and running Adam on float4s
+//  halves the instruction count but is 11 % slower; looping several chunks per CTA is 25 % slower.)
+// grid = (max items per candidate, H/64, candidates);  BP = batch rows padded (64 or 128) = MMA K extent
+// dynamic smem (1024-aligned): A_hi | A_lo (4 blocks x BP x 128 B) | B_hi | B_lo (2 blocks x BP x 128 B)
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_BWD_THREADS = 512;
+
+template <int BP, bool KEEP_GRAD>
+__global__ void __launch_bounds__(TC_BWD_THREADS, BP == 64 ? 2 : 1)
+k_tc_bwd_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, AdamH adam, float step_size,
+             float bc2_sqrt, TcErr err, int dbg) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int cand = blockIdx.z;
+  const DCand& cd = cands[cand];
+  const int H = cd.H;
+  const int h0 = blockIdx.y * TC_BWD_HT;
+  if (h0 >= H) return;
+  int layer = 0, chunk = blockIdx.x;
+  for (; layer < cd.L; ++layer) {
+    const int n = tc_bwd_items(cd.layer[layer].K);
+    if (chunk < n) break;
+    chunk -= n;
+  }
+  if (layer >= cd.L) return;
+  const DLayer& ly = cd.layer[layer];
+  const int K = ly.K;
+  const int kc0 = chunk * TC_BWD_KT;
+  const int kw = min(TC_BWD_KT, K - kc0);
+  const int nrows = batch.n_rows, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  constexpr uint32_t BLK = BP * 128, A_TILE = 4 * BLK, B_TILE = 2 * BLK;
+  uint8_t* a_hi = smem;
+  uint8_t* a_lo = a_hi + A_TILE;
+  uint8_t* b_hi = a_lo + A_TILE;
+  uint8_t* b_lo = b_hi + B_TILE;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int ok_flag;
+
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 64);
+  if (tid == 0) { umma::mbar_init(&bar, 1); umma::fence_mbar_init(); }
+
+  // ---- A tile: x[:, kc0:kc0+128] (one smem row per batch row, 4 blocks of 32 columns) and
+  //      B tile: dz_l[:, h0:h0+64] (2 blocks); all loads of a thread are issued before the first store
   const int fs = ly.d_ske, fr = ly.d_rgb;
   const float* src; long long ld; int kl; bool gather = true;
   if (kc0 < fs) { src = cache.ske[ly.ske_tap]; ld = cache.ske_ld[ly.ske_tap]; kl = kc0; }
   else if (kc0 < fs + fr) { src = cache.rgb[ly.rgb_tap]; ld = cache.rgb_ld[ly.rgb_tap]; kl = kc0 - fs; }
   else { src = cd.hid + (long long)(layer - 1) * bmax * H; ld = H; kl = kc0 - fs - fr; gather = false; }
-  const bool hidden = !gather;
+  {
+    constexpr int XIT = BP * 32 / TC_BWD_THREADS, DIT = BP * 16 / TC_BWD_THREADS;
+    const float* dzl = cd.dzs + (long long)layer * bmax * H + h0;
+    float4 xv[XIT], dv[DIT];
 #pragma unroll
-  for (int i = 0; i < BP * 16 / TC_THREADS; ++i) {
-    const int idx = tid + TC_THREADS * i, r = idx >> 4, c4 = idx & 15;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < nrows && c4 * 4 < kw) {
-      const long long row = gather ? (long long)batch_row(batch, cand, r) : (long long)r;
-      v = __ldg(reinterpret_cast<const float4*>(src + row * ld + kl + c4 * 4));
+    for (int i = 0; i < XIT; ++i) {
+      const int idx = tid + TC_BWD_THREADS * i, r = idx >> 5, c4 = idx & 31;
+      xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nrows && c4 * 4 < kw) {
+        const long long row = gather ? (long long)batch_row(batch, cand, r) : (long long)r;
+        xv[i] = __ldg(reinterpret_cast<const float4*>(src + row * ld + kl + c4 * 4));
+      }
     }
-    store_split(b_hi, b_lo, (uint32_t)(c4 >> 3) * A_BLK + umma::sw128_b32(r, (c4 & 7) * 16), v);
+#pragma unroll
+    for (int i = 0; i < DIT; ++i) {
+      const int idx = tid + TC_BWD_THREADS * i, r = idx >> 4, c4 = idx & 15;
+      dv[i] = (r < nrows) ? *reinterpret_cast<const float4*>(dzl + (long long)r * H + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < XIT; ++i) {
+      const int idx = tid + TC_BWD_THREADS * i, r = idx >> 5, c4 = idx & 31;
+      store_split(a_hi, a_lo, (uint32_t)(c4 >> 3) * BLK + umma::sw128_b32(r, (c4 & 7) * 16), xv[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < DIT; ++i) {
+      const int idx = tid + TC_BWD_THREADS * i, r = idx >> 4, c4 = idx & 15;
+      store_split(b_hi, b_lo, (uint32_t)(c4 >> 3) * BLK + umma::sw128_b32(r, (c4 & 7) * 16), dv[i]);
+    }
+  }
+  umma::fence_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tm = tmem_slot;
+
+  if (tid == 0) {
+    constexpr uint32_t idesc = umma::idesc_tf32(128, TC_BWD_HT, true, true);
+    const int ksteps = (nrows + 7) >> 3;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const uint32_t adv = ks * 1024u;               // 8 batch rows = two 512-byte swizzle atoms
+      const uint64_t dah = umma::smem_desc(umma::smem_u32(a_hi) + adv, BLK, 512, umma::kLayoutSw128Base32);
+      const uint64_t dal = umma::smem_desc(umma::smem_u32(a_lo) + adv, BLK, 512, umma::kLayoutSw128Base32);
+      const uint64_t dbh = umma::smem_desc(umma::smem_u32(b_hi) + adv, BLK, 512, umma::kLayoutSw128Base32);
+      const uint64_t dbl = umma::smem_desc(umma::smem_u32(b_lo) + adv, BLK, 512, umma::kLayoutSw128Base32);
+      umma::mma_tf32(tm, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+      umma::mma_tf32(tm, dah, dbl, idesc, 1u);
+      umma::mma_tf32(tm, dah, dbh, idesc, 1u);
+    }
+    umma::mma_commit(&bar);
   }
 
-  constexpr uint32_t idesc = umma::idesc_tf32(128, 64, true, true);
-  const int ksteps = (nrows + 7) >> 3;
-  uint32_t phase = 0;
-  bool ok = true;
-  float* Wg = cd.p + ly.oW + kc0;
-  float* Mg = cd.m + ly.oW + kc0;
-  float* Vg = cd.v + ly.oW + kc0;
-  float* Gg = cd.grad ? cd.grad + ly.oW + kc0 : nullptr;
-
-  for (int m0 = 0; m0 < H; m0 += 128) {
-    // ---- A tile: dz[:, m0:m0+128] (MN-major: one row per batch row, 4 blocks of 32 columns) -------
+  // ---- epilogue: thread = weight column kc0 + 32q + lane (q = warp%4), rows h0 + 16*(warp/4) + [0,16) --
+  const int q = warp & 3, cg = warp >> 2;
+  const int kcol = q * 32 + lane;
+  const bool kvalid = q * 32 < kw && !(dbg & 1);      // kw is a multiple of 32: uniform per warp
+  const int hb = h0 + cg * 16;
+  float* Wg = cd.p + ly.oW + (long long)hb * K + kc0 + kcol;
+  const long long moff = (long long)(cd.m - cd.p), voff = (long long)(cd.v - cd.p), goff = KEEP_GRAD ? (long long)(cd.grad - cd.p) : 0;
+  const float inv_bc2 = 1.f / bc2_sqrt;
+  struct Set { float p[4], m[4], v[4]; };
+  Set sa, sb;
+  auto prefetch = [&](Set& st, int j0) {
+    const float* w = Wg + (long long)j0 * K;
 #pragma unroll
-    for (int i = 0; i < BP * 32 / TC_THREADS; ++i) {
-      const int idx = tid + TC_THREADS * i, r = idx >> 5, c4 = idx & 31;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < nrows && m0 + c4 * 4 < H) v = *reinterpret_cast<const float4*>(cd.dz + (long long)r * H + m0 + c4 * 4);
-      store_split(a_hi, a_lo, (uint32_t)(c4 >> 3) * A_BLK + umma::sw128_b32(r, (c4 & 7) * 16), v);
-    }
-    umma::fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      umma::tc_fence_after();
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint32_t adv = ks * 1024u;             // 8 batch rows = two 512-byte atoms
-        const uint64_t dah = umma::smem_desc(umma::smem_u32(a_hi) + adv, A_BLK, 512, umma::kLayoutSw128Base32);
-        const uint64_t dal = umma::smem_desc(umma::smem_u32(a_lo) + adv, A_BLK, 512, umma::kLayoutSw128Base32);
-        const uint64_t dbh = umma::smem_desc(umma::smem_u32(b_hi) + adv, A_BLK, 512, umma::kLayoutSw128Base32);
-        const uint64_t dbl = umma::smem_desc(umma::smem_u32(b_lo) + adv, A_BLK, 512, umma::kLayoutSw128Base32);
-        umma::mma_tf32(tm, dal, dbh, idesc, ks > 0 ? 1u : 0u);
-        umma::mma_tf32(tm, dah, dbl, idesc, 1u);
-        umma::mma_tf32(tm, dah, dbh, idesc, 1u);
-      }
-      umma::mma_commit(&bar);
-    }
-    ok = umma::mbar_wait(&bar, phase);
-    phase ^= 1;
-    if (!ok) break;
-    umma::tc_fence_after();
-
-    // ---- TMEM -> registers -> transposed staging tile G[h][col] ------------------------------------
-    {
-      float v[32];
-      const int c0 = (warp >> 2) * 32, hl = (warp & 3) * 32 + lane;
-      umma::tmem_ld32(tm + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
+    for (int j = 0; j < 4; ++j) { st.p[j] = w[0]; st.m[j] = w[moff]; st.v[j] = w[voff]; w += K; }
+  };
+  auto update = [&](Set& st, int j0) {
+    float g[4];
+    umma::tmem_ld4(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 16 + j0), g);
+    if (kvalid) {
+      float* w = Wg + (long long)j0 * K;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) G[hl * TC_G_LD + c0 + j] = v[j];
-    }
-    umma::tc_fence_before();
-    // hidden columns: dh_{l-1}[b][kl+j] += sum_h dz[b][m0+h] * W[m0+h][kc0+j]   (pre-update weights)
-    const int hrows = min(128, H - m0);
-    if (hidden) {
-      for (int i = tid; i < hrows * 16; i += TC_THREADS) {
-        const int h = i >> 4, c4 = i & 15;
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c4 * 4 < kw) w = *reinterpret_cast<const float4*>(Wg + (long long)(m0 + h) * K + c4 * 4);
-        *reinterpret_cast<float4*>(Wsm + h * 64 + c4 * 4) = w;
+      for (int j = 0; j < 4; ++j) {
+        if (KEEP_GRAD) w[goff] = g[j];
+        adam_update_fast(g[j], st.p[j], st.m[j], st.v[j], adam, step_size, inv_bc2);
+        w[0] = st.p[j]; w[moff] = st.m[j]; w[voff] = st.v[j];
+        w += K;
       }
     }
-    __syncthreads();
-    if (hidden) {
-      float* dprev = cd.dh + (long long)(layer - 1) * bmax * H;
-      const int j = tid & 63, bg = tid >> 6;
-      for (int b = bg; b < nrows; b += 4) {
-        const float* dzr = cd.dz + (long long)b * H + m0;
-        float s = 0.f;
-        for (int h = 0; h < hrows; ++h) s = fmaf(dzr[h], Wsm[h * 64 + j], s);
-        if (j < kw) {
-          float* o = dprev + b * H + kl + j;
-          *o = (m0 == 0) ? s : *o + s;
-        }
-      }
-      __syncthreads();      // Wsm reads done before the weights below are overwritten in place
-    }
-    // ---- Adam(L2) straight from the staging tile; every p/m/v access is a coalesced 128-byte row ----
-    for (int it = 0; it < hrows * 64 / TC_THREADS; it += 4) {
-      float pp[4], mm[4], vv[4];
-      long long off[4];
-      bool act4[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int idx = (it + u) * TC_THREADS + tid, r = idx >> 6, c = idx & 63;
-        act4[u] = c < kw;
-        off[u] = (long long)(m0 + r) * K + c;
-        if (act4[u]) { pp[u] = Wg[off[u]]; mm[u] = Mg[off[u]]; vv[u] = Vg[off[u]]; }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (!act4[u]) continue;
-        const int idx = (it + u) * TC_THREADS + tid, r = idx >> 6, c = idx & 63;
-        const float g = G[r * TC_G_LD + c];
-        if (Gg) Gg[off[u]] = g;
-        adam_update(g, pp[u], mm[u], vv[u], adam, step_size, bc2_sqrt);
-        Wg[off[u]] = pp[u]; Mg[off[u]] = mm[u]; Vg[off[u]] = vv[u];
-      }
-    }
-    __syncthreads();        // G / Wsm (aliasing the A tiles) free before the next m-tile is staged
-  }
+  };
+  if (kvalid) { prefetch(sa, 0); prefetch(sb, 4); }   // p/m/v loads fly while the tensor core works
+  const bool ok = umma::cta_wait(&bar, 0, &ok_flag);
   if (!ok && tid == 0) atomicExch(err.flag, 2);
+  umma::tc_fence_after();
+  update(sa, 0);
+  if (kvalid) prefetch(sa, 8);
+  update(sb, 4);
+  if (kvalid) prefetch(sb, 12);
+  update(sa, 8);
+  update(sb, 12);
   umma::tc_fence_before();
   __syncthreads();
   if (warp == 0) umma::tmem_free(tm, 64);

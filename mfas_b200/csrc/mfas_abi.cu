@@ -129,15 +129,18 @@ struct mfas_group {
   int* improved = nullptr;        // [n_cand]
   bool dirty = true;
   size_t smem_head = 0, smem_bwd = 0;
+  int hs_ld = 0, lg_ld = 0;       // leading dimensions of the head kernel's smem tiles
   int64_t launches = 0;
   // engine "tc" (tcgen05 tensor cores); engine 0 = "ffma"
   int engine = 0;
   int npad = 64;                  // batch rows padded to the MMA tile (64 or 128)
-  int fwd_splits[MFAS_MAX_LAYERS] = {0};
-  float* part = nullptr;          // split-K partial sums [n_cand][S_cap][Hp][npad]
+  int items_fwd = 0, items_bwd = 0;   // work items per candidate (max over the group)
+  float* part = nullptr;          // forward partial sums [n_cand][items_fwd][Hp][npad]
   long long part_stride = 0;
   int* tc_err = nullptr;          // device flag set by a timed-out barrier wait
-  size_t smem_tc_fwd = 0, smem_tc_bwd = 0;
+  size_t smem_tc_fwd = 0, smem_tc_bwd = 0, smem_fl = 0, smem_dzx = 0, smem_chain = 0;
+  int dbg = 0;                    // MFAS_TC_DEBUG bit 0: skip the Adam epilogue, bit 1: skip operand staging (timing experiments only)
+  int chain = 1;                  // 1: tensor-core chain kernels, 0: CUDA-core chain kernels (MFAS_CHAIN=ffma)
 };
 
 static void set_adam(AdamH& a, double b1, double b2, double eps, double wd) {
@@ -192,7 +195,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
   auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
   size_t total = 0;
   std::vector<size_t> base(n_cand);
-  struct Off { size_t act, hid, dh, dz, mu, invstd, logits, best_p, best_bufs, best_nbt; };
+  struct Off { size_t act, hid, dh, dz, dzs, mu, invstd, logits, best_p, best_bufs, best_nbt; };
   std::vector<Off> off(n_cand);
   for (int c = 0; c < n_cand; ++c) {
     const mfas_layout& l = g->lay[c];
@@ -211,6 +214,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     o.hid = total; total += up(lbh);
     o.dh = total; total += up(lbh);
     o.dz = total; total += up((size_t)batch_max * l.H * sizeof(float));
+    o.dzs = total; total += up(lbh);
     o.mu = total; total += up((size_t)l.L * l.H * sizeof(float));
     o.invstd = total; total += up((size_t)l.L * l.H * sizeof(float));
     o.logits = total; total += up((size_t)batch_max * l.C * sizeof(float));
@@ -245,13 +249,18 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     d.oWc = l.off_Wc; d.obc = l.off_bc; d.n_params = l.n_params; d.n_bufs = l.n_bufs;
     const Off& o = off[c];
     d.act = (float*)(g->ws + o.act); d.hid = (float*)(g->ws + o.hid); d.dh = (float*)(g->ws + o.dh);
-    d.dz = (float*)(g->ws + o.dz); d.mu = (float*)(g->ws + o.mu); d.invstd = (float*)(g->ws + o.invstd);
+    d.dz = (float*)(g->ws + o.dz); d.dzs = (float*)(g->ws + o.dzs); d.mu = (float*)(g->ws + o.mu); d.invstd = (float*)(g->ws + o.invstd);
     d.logits = (float*)(g->ws + o.logits); d.best_p = (float*)(g->ws + o.best_p);
     d.best_bufs = (float*)(g->ws + o.best_bufs); d.best_nbt = (long long*)(g->ws + o.best_nbt);
   }
   // dynamic shared memory of the two big-smem kernels
-  g->smem_head = sizeof(float) * ((size_t)batch_max * g->Hmax + (size_t)g->Cmax * (g->Hmax + 1) +
-                                  (size_t)batch_max * (g->Cmax + 1) + batch_max) + sizeof(int) * 2 * batch_max;
+  // head kernel tiles: rows padded by 4 floats (conflict-free float4 walks) when that still fits
+  auto head_bytes = [&](int hs_ld, int lg_ld) {
+    return sizeof(float) * ((size_t)batch_max * hs_ld + (size_t)g->Cmax * hs_ld + (size_t)batch_max * lg_ld);
+  };
+  g->hs_ld = g->Hmax + 4; g->lg_ld = g->Cmax + 1;
+  if (head_bytes(g->hs_ld, g->lg_ld) > 220 * 1024) { g->hs_ld = g->Hmax; g->lg_ld = g->Cmax; }
+  g->smem_head = head_bytes(g->hs_ld, g->lg_ld);
   g->smem_bwd = sizeof(float) * ((size_t)batch_max * g->Hmax + (size_t)batch_max * BWD_KT + (size_t)g->Hmax * BWD_KT);
   const size_t lim = 227 * 1024;
   if (g->smem_head > lim || g->smem_bwd > lim) {
@@ -267,35 +276,63 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     mfas_group_destroy(g);
     return code;
   }
-  // ---- engine selection: tensor cores whenever the shapes fit the MMA tile ------------------------
+  // ---- engine selection: tensor cores whenever the shapes fit the MMA tiles -----------------------
   bool tc_ok = true;
-  for (int c = 0; c < n_cand; ++c) tc_ok = tc_ok && (g->lay[c].H % 64 == 0);
+  for (int c = 0; c < n_cand; ++c) {
+    tc_ok = tc_ok && (g->lay[c].H % 64 == 0);
+    for (int l = 0; l < g->lay[c].L; ++l) tc_ok = tc_ok && g->lay[c].d_ske[l] % 128 == 0 && g->lay[c].d_rgb[l] % 128 == 0;
+  }
   const char* env = getenv("MFAS_ENGINE");
   if (env && !strcmp(env, "ffma")) tc_ok = false;
   if (env && !strcmp(env, "tc") && !tc_ok) {
-    int code = fail(MFAS_ERR_UNSUPPORTED, "MFAS_ENGINE=tc needs inner_representation_size in {64,128,192,256}");
+    int code = fail(MFAS_ERR_UNSUPPORTED, "MFAS_ENGINE=tc needs inner_representation_size %% 64 == 0 and tap widths %% 128 == 0");
     mfas_group_destroy(g);
     return code;
   }
   if (tc_ok) {
     g->engine = 1;
     g->npad = batch_max <= 64 ? 64 : 128;
-    int s_cap = 1;
-    for (int l = 0; l < g->Lmax; ++l) {
-      g->fwd_splits[l] = ((g->Kmax[l] >> 5) + TC_KB_PER_CTA - 1) / TC_KB_PER_CTA;
-      s_cap = g->fwd_splits[l] > s_cap ? g->fwd_splits[l] : s_cap;
+    for (int c = 0; c < n_cand; ++c) {
+      int nf = 0, nb = 0;
+      for (int l = 0; l < g->lay[c].L; ++l) {
+        nf += tc_fwd_items(g->lay[c].d_ske[l], g->lay[c].d_rgb[l]);
+        nb += tc_bwd_items(g->lay[c].K[l]);
+      }
+      g->items_fwd = nf > g->items_fwd ? nf : g->items_fwd;
+      g->items_bwd = nb > g->items_bwd ? nb : g->items_bwd;
     }
     const int Hp = ((g->Hmax + 127) / 128) * 128;
-    g->part_stride = (long long)s_cap * Hp * g->npad;
+    g->part_stride = (long long)g->items_fwd * Hp * g->npad;
     g->smem_tc_fwd = 1024 + 32768 + 2 * (size_t)g->npad * 128;
-    g->smem_tc_bwd = 1024 + 2 * (size_t)(4 * g->npad * 128) + 1024 + 2 * (size_t)(2 * g->npad * 128);
+    g->smem_tc_bwd = 1024 + 2 * (size_t)(4 * g->npad * 128) + 2 * (size_t)(2 * g->npad * 128);
+    g->smem_fl = sizeof(float) * ((size_t)batch_max * (g->Hmax + 1) + TC_CB * (size_t)g->Hmax);
+    g->smem_dzx = sizeof(float) * ((size_t)batch_max * g->Hmax + (TC_CB + 1) * (size_t)g->Hmax);
     e = cudaMalloc(&g->part, sizeof(float) * g->part_stride * n_cand);
     if (e == cudaSuccess) e = cudaMalloc(&g->tc_err, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(g->tc_err, 0, sizeof(int));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_fwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + 32768 + 2 * 64 * 128));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_fwd<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + 32768 + 2 * 128 * 128));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_bwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + 2 * 32768 + 1024 + 2 * 16384));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_bwd<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + 2 * 65536 + 1024 + 2 * 32768));
+    auto attr = [&](const void* f, size_t bytes) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    };
+    attr((const void*)k_tc_fwd_all<64>, 1024 + 32768 + 2 * 64 * 128);
+    attr((const void*)k_tc_fwd_all<128>, 1024 + 32768 + 2 * 128 * 128);
+    attr((const void*)k_tc_bwd_all<64, false>, 1024 + 6 * 64 * 128 * 2);
+    attr((const void*)k_tc_bwd_all<64, true>, 1024 + 6 * 64 * 128 * 2);
+    attr((const void*)k_tc_bwd_all<128, false>, 1024 + 6 * 128 * 128 * 2);
+    attr((const void*)k_tc_bwd_all<128, true>, 1024 + 6 * 128 * 128 * 2);
+    attr((const void*)k_fwd_layer<true, 64>, g->smem_fl);
+    attr((const void*)k_fwd_layer<false, 64>, g->smem_fl);
+    attr((const void*)k_fwd_layer<true, 128>, g->smem_fl);
+    attr((const void*)k_fwd_layer<false, 128>, g->smem_fl);
+    attr((const void*)k_dzx, g->smem_dzx);
+    g->smem_chain = g->npad == 64 ? ChainCfg<64>::SMEM : ChainCfg<128>::SMEM;
+    attr((const void*)k_chain_fwd<true, 64>, ChainCfg<64>::SMEM);
+    attr((const void*)k_chain_fwd<false, 64>, ChainCfg<64>::SMEM);
+    attr((const void*)k_chain_fwd<true, 128>, ChainCfg<128>::SMEM);
+    attr((const void*)k_chain_fwd<false, 128>, ChainCfg<128>::SMEM);
+    attr((const void*)k_chain_bwd<64>, ChainCfg<64>::SMEM);
+    attr((const void*)k_chain_bwd<128>, ChainCfg<128>::SMEM);
+    { const char* ce = getenv("MFAS_CHAIN"); if (ce && !strcmp(ce, "ffma")) g->chain = 0; }
+    { const char* de = getenv("MFAS_TC_DEBUG"); if (de) g->dbg = atoi(de); }
     if (e != cudaSuccess) {
       int code = fail(MFAS_ERR_CUDA, "tc engine setup: %s", cudaGetErrorString(e));
       mfas_group_destroy(g);
@@ -320,7 +357,7 @@ extern "C" int mfas_group_status(mfas_group_t g) {
   if (g->tc_err) {
     int flag = 0;
     CUDA_TRY(cudaMemcpy(&flag, g->tc_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flag) return fail(MFAS_ERR_CUDA, "tensor-core pipeline barrier timed out in kernel %s", flag == 1 ? "k_tc_fwd" : "k_tc_bwd");
+    if (flag) return fail(MFAS_ERR_CUDA, "tensor-core pipeline barrier timed out in kernel %s", flag == 1 ? "k_tc_fwd_all" : flag == 2 ? "k_tc_bwd_all" : flag == 3 ? "k_chain_fwd" : "k_chain_bwd");
   }
   return MFAS_OK;
 }
@@ -385,28 +422,62 @@ static int to_dcache(const mfas_group* g, const mfas_cache_desc* c, DCache* out)
     if (e__ != cudaSuccess) return fail(MFAS_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// tc engine: one launch covers the feature columns of every layer, small per-layer kernels carry the chain
+static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& batch, bool train, bool bn_train,
+                          float step_size, float bc2_sqrt, uint32_t step, const HeadOut& ho, cudaStream_t st) {
+  const TcErr terr{g->tc_err};
+  const dim3 gf(g->items_fwd, (g->Hmax + 127) / 128, g->n_cand), gl((g->Hmax + TC_CB - 1) / TC_CB, g->n_cand);
+  if (g->npad == 64) k_tc_fwd_all<64><<<gf, TC_THREADS, g->smem_tc_fwd, st>>>(g->dc, cache, batch, g->part, g->part_stride, terr);
+  else k_tc_fwd_all<128><<<gf, TC_THREADS, g->smem_tc_fwd, st>>>(g->dc, cache, batch, g->part, g->part_stride, terr);
+  LAUNCH_CHECK(g);
+  const dim3 gc((g->Hmax + 127) / 128, g->n_cand);
+  for (int l = 0; l < g->Lmax; ++l) {
+#define FL(T, N) k_fwd_layer<T, N><<<gl, TC_CHAIN_THREADS, g->smem_fl, st>>>(g->dc, l, batch.n_rows, g->bmax, g->part, g->part_stride, g->drop_seed, g->drop_p, step)
+#define CF(T, N) k_chain_fwd<T, N><<<gc, ChainCfg<N>::THREADS, g->smem_chain, st>>>(g->dc, l, batch.n_rows, g->bmax, g->part, g->part_stride, g->drop_seed, g->drop_p, step, terr)
+    if (g->chain) {
+      if (g->npad == 64) { if (bn_train) CF(true, 64); else CF(false, 64); }
+      else { if (bn_train) CF(true, 128); else CF(false, 128); }
+    } else {
+      if (g->npad == 64) { if (bn_train) FL(true, 64); else FL(false, 64); }
+      else { if (bn_train) FL(true, 128); else FL(false, 128); }
+    }
+#undef FL
+#undef CF
+    LAUNCH_CHECK(g);
+  }
+  if (train)
+    k_head<true><<<g->n_cand, kHeadThreads, g->smem_head, st>>>(g->dc, cache, batch, g->bmax, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, ho);
+  else
+    k_head<false><<<g->n_cand, kHeadThreads, g->smem_head, st>>>(g->dc, cache, batch, g->bmax, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, ho);
+  LAUNCH_CHECK(g);
+  if (!train) return MFAS_OK;
+  for (int l = g->Lmax - 1; l >= 0; --l) {
+    if (g->chain) {
+      if (g->npad == 64) k_chain_bwd<64><<<gc, ChainCfg<64>::THREADS, g->smem_chain, st>>>(g->dc, l, batch.n_rows, g->bmax, g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, terr);
+      else k_chain_bwd<128><<<gc, ChainCfg<128>::THREADS, g->smem_chain, st>>>(g->dc, l, batch.n_rows, g->bmax, g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, terr);
+    } else {
+      k_dzx<<<gl, kThreads, g->smem_dzx, st>>>(g->dc, l, batch.n_rows, g->bmax, g->adam, step_size, bc2_sqrt, g->drop_seed,
+                                               g->drop_p, step);
+    }
+    LAUNCH_CHECK(g);
+  }
+  const dim3 gb(g->items_bwd, (g->Hmax + TC_BWD_HT - 1) / TC_BWD_HT, g->n_cand);
+  bool keep = false;                                  // the grad arena is a test facility: all candidates or none
+  for (int c = 0; c < g->n_cand; ++c) keep = keep || g->hc[c].grad != nullptr;
+#define BW(BPV, KG) k_tc_bwd_all<BPV, KG><<<gb, TC_BWD_THREADS, g->smem_tc_bwd, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, terr, g->dbg)
+  if (g->npad == 64) { if (keep) BW(64, true); else BW(64, false); }
+  else { if (keep) BW(128, true); else BW(128, false); }
+#undef BW
+  LAUNCH_CHECK(g);
+  return MFAS_OK;
+}
+
 // one forward (+ optional backward/Adam) of every candidate over one batch
 static int launch_step(mfas_group* g, const DCache& cache, const BatchRef& batch, bool train, bool bn_train,
                        float step_size, float bc2_sqrt, uint32_t step, const HeadOut& ho, cudaStream_t st) {
+  if (g->engine == 1) return launch_step_tc(g, cache, batch, train, bn_train, step_size, bc2_sqrt, step, ho, st);
   const dim3 fgrid((g->Hmax + FWD_HT - 1) / FWD_HT, g->n_cand);
-  const TcErr terr{g->tc_err};
   for (int l = 0; l < g->Lmax; ++l) {
-    if (g->engine == 1) {
-      const dim3 gg(g->fwd_splits[l], (g->Hmax + 127) / 128, g->n_cand), ge((g->Hmax + 31) / 32, g->n_cand);
-      if (g->npad == 64) {
-        k_tc_fwd<64><<<gg, TC_THREADS, g->smem_tc_fwd, st>>>(g->dc, cache, batch, l, g->bmax, g->part, g->part_stride, terr);
-        LAUNCH_CHECK(g);
-        if (bn_train) k_tc_fwd_epi<true, 64><<<ge, TC_THREADS, 0, st>>>(g->dc, l, batch.n_rows, g->bmax, g->part, g->part_stride, g->drop_seed, g->drop_p, step);
-        else k_tc_fwd_epi<false, 64><<<ge, TC_THREADS, 0, st>>>(g->dc, l, batch.n_rows, g->bmax, g->part, g->part_stride, g->drop_seed, g->drop_p, step);
-      } else {
-        k_tc_fwd<128><<<gg, TC_THREADS, g->smem_tc_fwd, st>>>(g->dc, cache, batch, l, g->bmax, g->part, g->part_stride, terr);
-        LAUNCH_CHECK(g);
-        if (bn_train) k_tc_fwd_epi<true, 128><<<ge, TC_THREADS, 0, st>>>(g->dc, l, batch.n_rows, g->bmax, g->part, g->part_stride, g->drop_seed, g->drop_p, step);
-        else k_tc_fwd_epi<false, 128><<<ge, TC_THREADS, 0, st>>>(g->dc, l, batch.n_rows, g->bmax, g->part, g->part_stride, g->drop_seed, g->drop_p, step);
-      }
-      LAUNCH_CHECK(g);
-      continue;
-    }
     if (bn_train)
       k_fusion_fwd<true><<<fgrid, kThreads, 0, st>>>(g->dc, cache, batch, l, g->bmax, g->drop_seed, g->drop_p, step);
     else
@@ -414,22 +485,15 @@ static int launch_step(mfas_group* g, const DCache& cache, const BatchRef& batch
     LAUNCH_CHECK(g);
   }
   if (train)
-    k_head<true><<<g->n_cand, kThreads, g->smem_head, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, ho);
+    k_head<true><<<g->n_cand, kHeadThreads, g->smem_head, st>>>(g->dc, cache, batch, g->bmax, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, ho);
   else
-    k_head<false><<<g->n_cand, kThreads, g->smem_head, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, ho);
+    k_head<false><<<g->n_cand, kHeadThreads, g->smem_head, st>>>(g->dc, cache, batch, g->bmax, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, ho);
   LAUNCH_CHECK(g);
   if (!train) return MFAS_OK;
   for (int l = g->Lmax - 1; l >= 0; --l) {
     k_dz<<<dim3((g->Hmax + 31) / 32, g->n_cand), kThreads, 0, st>>>(g->dc, l, batch.n_rows, g->bmax, g->adam, step_size,
                                                                   bc2_sqrt, g->drop_seed, g->drop_p, step);
     LAUNCH_CHECK(g);
-    if (g->engine == 1) {
-      const dim3 gb((g->Kmax[l] + TC_BWD_KT - 1) / TC_BWD_KT, g->n_cand);
-      if (g->npad == 64) k_tc_bwd<64><<<gb, TC_THREADS, g->smem_tc_bwd, st>>>(g->dc, cache, batch, l, g->bmax, g->adam, step_size, bc2_sqrt, terr);
-      else k_tc_bwd<128><<<gb, TC_THREADS, g->smem_tc_bwd, st>>>(g->dc, cache, batch, l, g->bmax, g->adam, step_size, bc2_sqrt, terr);
-      LAUNCH_CHECK(g);
-      continue;
-    }
     k_fusion_bwd<<<dim3((g->Kmax[l] + BWD_KT - 1) / BWD_KT, g->n_cand), kThreads, g->smem_bwd, st>>>(
         g->dc, cache, batch, l, g->bmax, g->adam, step_size, bc2_sqrt);
     LAUNCH_CHECK(g);

@@ -123,11 +123,66 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// 3xTF32 split: x = hi + lo with hi exactly representable in tf32 (low 13 mantissa bits zero).
-// lo is kept in full fp32; the tensor core truncates it to tf32 itself, which costs ~2^-21 relative.
+// warp-collective: 32 lanes x 16 consecutive columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// warp-collective: 32 lanes x 4 consecutive columns
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// warp-collective: 32 lanes x 8 consecutive columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 3xTF32 split: x = hi + lo (+ O(2^-22 |x|)), hi and lo both rounded to nearest tf32 (ties away from
+// zero, i.e. cvt.rna.tf32.f32) so the error of the three-product scheme is unbiased -- the tensor core
+// itself would truncate the low 13 bits.  Done with two integer ops per rounding (add half an ulp of
+// tf32 to the magnitude, clear the low 13 bits): the conversion pipe (cvt) runs at quarter rate and
+// would otherwise cost as many issue slots as the loads it decorates.
+__device__ __forceinline__ float round_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  lo = x - hi;
+  hi = round_tf32(x);
+  lo = round_tf32(x - hi);
+}
+
+// warp 0 polls the mbarrier, everybody else sleeps on the CTA barrier (no issue slots burnt spinning)
+__device__ __forceinline__ bool cta_wait(uint64_t* bar, uint32_t parity, int* ok_flag) {
+  if (threadIdx.x < 32) {
+    const bool ok = mbar_wait(bar, parity);
+    if (threadIdx.x == 0) *ok_flag = ok ? 1 : 0;
+  }
+  __syncthreads();
+  return *ok_flag != 0;
 }
 
 }  // namespace umma

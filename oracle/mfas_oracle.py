@@ -28,12 +28,26 @@ CUDA kernels implement, so the oracle validates the derivation as well as the ar
 """
 from __future__ import annotations
 
+import contextlib
 import copy
 import math
 
 import numpy as np
 
-F32 = np.float32
+F32 = np.float32            # working precision of the restatement (see precision() below)
+
+
+@contextlib.contextmanager
+def precision(dtype):
+    """Run the restatement in another working precision (tests use float64 as ground truth to measure
+    how much of a gradient is fp32 rounding noise: BatchNorm over a nearly constant unit multiplies
+    rounding errors by 1/sqrt(var+eps), up to 316x, twice, whatever the implementation)."""
+    global F32
+    old, F32 = F32, dtype
+    try:
+        yield
+    finally:
+        F32 = old
 D_RGB = (512, 1024, 2048, 2048)            # ntu_searchable.py:292
 BN_EPS = 1e-5                              # torch.nn.BatchNorm1d default
 BN_MOMENTUM = 0.1

