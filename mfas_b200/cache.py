@@ -103,16 +103,40 @@ class FeatureCache:
         self._device_copies.clear()
 
 
+_M32 = 0xFFFFFFFF
+
+
+def _mix32(x):
+    """32-bit integer mixer on int64 tensors (identical results on CPU and CUDA)."""
+    x = x & _M32
+    x = x ^ (x >> 16)
+    x = (x * 0x7FEB352D) & _M32
+    x = x ^ (x >> 15)
+    x = (x * 0x846CA68B) & _M32
+    return x ^ (x >> 16)
+
+
+def hashed_orders(seed: int, first_pass: int, count: int, n: int, device="cpu") -> torch.Tensor:
+    """Row orders of ``count`` consecutive passes as an int64 [count, n] tensor: pass k visits rows in
+    the (stable) argsort of hash(seed, k, row).  Pure integer arithmetic, so the CPU (reference loop,
+    oracle) and the GPU (one batched sort for all candidates x epochs of a call) produce the same
+    permutations bit for bit."""
+    dev = torch.device(device)
+    k = torch.arange(first_pass, first_pass + count, dtype=torch.int64, device=dev)[:, None]
+    i = torch.arange(n, dtype=torch.int64, device=dev)[None, :]
+    key = _mix32(_mix32((int(seed) & _M32) * 0x9E3779B1 + k * 0x85EBCA6B) + i)
+    return torch.sort(key, dim=1, stable=True).indices
+
+
 class FeatureCacheLoader:
     """Deterministic DataLoader stand-in over a FeatureCache.
 
-    The k-th pass (``__iter__`` call) over the loader visits rows in ``order_for_pass(k)``:
-    ``randperm(N)`` from a generator seeded with ``seed + k`` when ``shuffle`` (the reference
-    shuffles both 'train' and 'dev', /root/reference/models/searchable.py:247-250), identity
-    otherwise.  The order depends on (seed, k) only, so candidate ``idx`` / epoch ``e`` of a
-    ``train_sampled_models`` call sees pass number ``base + idx*epochs + e`` no matter which
-    GPU trains it -- 1-GPU and 8-GPU runs return identical accuracies.
-    ``drop_last`` is False as in the reference.
+    The k-th pass (``__iter__`` call) over the loader visits rows in ``order_for_pass(k)``: a hashed
+    permutation keyed by (seed, k) when ``shuffle`` (the reference shuffles both 'train' and 'dev',
+    /root/reference/models/searchable.py:247-250), identity otherwise.  The order depends on (seed, k)
+    only, so candidate ``idx`` / epoch ``e`` of a ``train_sampled_models`` call sees pass number
+    ``base + idx*epochs + e`` no matter which GPU trains it -- 1-GPU and 8-GPU runs return identical
+    accuracies.  ``drop_last`` is False as in the reference.
     """
 
     def __init__(self, cache: FeatureCache, batch_size: int, shuffle: bool = True, seed: int = 0):
@@ -125,13 +149,15 @@ class FeatureCacheLoader:
     def __len__(self):
         return (len(self.dataset) + self.batch_size - 1) // self.batch_size
 
-    def order_for_pass(self, k: int) -> torch.Tensor:
+    def orders(self, first_pass: int, count: int, device="cpu") -> torch.Tensor:
+        """int64 [count, N] row orders of passes first_pass .. first_pass+count-1, built on ``device``."""
         n = len(self.dataset)
         if not self.shuffle:
-            return torch.arange(n, dtype=torch.int64)
-        g = torch.Generator()
-        g.manual_seed(self.seed + int(k))
-        return torch.randperm(n, generator=g)
+            return torch.arange(n, dtype=torch.int64, device=device).repeat(count, 1)
+        return hashed_orders(self.seed, first_pass, count, n, device)
+
+    def order_for_pass(self, k: int) -> torch.Tensor:
+        return self.orders(int(k), 1)[0]
 
     def take_passes(self, count: int) -> int:
         """Reserve ``count`` consecutive passes; returns the first pass number."""

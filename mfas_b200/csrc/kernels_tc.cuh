@@ -49,6 +49,8 @@ __device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, 
 // grid = (max items per candidate, ceil(H/128), candidates);  NPAD = batch padded to the MMA N.
 // part[cand][item][Hp][NPAD]
 // dynamic smem (1024-aligned): A_hi 16K | A_lo 16K | B_hi NPAD*128 | B_lo NPAD*128
+// (Measured alternative, kept out: double-buffering the smem stage so the stores of block k+1 overlap
+//  the MMAs of block k costs a third of the resident CTAs -- 2 instead of 3 per SM -- and is 30 % slower.)
 // ---------------------------------------------------------------------------------------------
 template <int NPAD>
 __global__ void __launch_bounds__(TC_THREADS, NPAD == 64 ? 3 : 2)

@@ -95,7 +95,21 @@ def adam_schedule(lrs, t0, beta1=0.9, beta2=0.999):
     return np.ascontiguousarray(step_size), np.ascontiguousarray(bc2_sqrt)
 
 
-class CandidateGroup:
+class GroupLayout:
+    """Where every tensor of every candidate of a group lives in the flat arenas (host-only, no GPU)."""
+
+    def __init__(self, confs, H, C_out, flags, vid_len_ske=32):
+        self.n = len(confs)
+        self.H, self.C, self.flags = int(H), int(C_out), int(flags)
+        self.layouts = [plan_layout(c, H, C_out, flags, vid_len_ske) for c in confs]
+        self.slots = [tensor_slots(l) for l in self.layouts]
+        np_ = [int(l.n_params) for l in self.layouts]
+        nb_ = [int(l.n_bufs) for l in self.layouts]
+        self.p_off = np.concatenate([[0], np.cumsum(np_)]).astype(np.int64)
+        self.b_off = np.concatenate([[0], np.cumsum(nb_)]).astype(np.int64)
+
+
+class CandidateGroup(GroupLayout):
     """n candidates with their parameter / Adam / BN arenas resident on one CUDA device."""
 
     def __init__(self, confs, H, C_out, flags, device, batch_max, drop_p=0.0, drop_seed=0, cand_ids=None,
@@ -103,15 +117,9 @@ class CandidateGroup:
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("mfas_b200 runs on CUDA devices only (no CPU fallback)")
+        super().__init__(confs, H, C_out, flags, vid_len_ske)
         self.device = device
-        self.n = len(confs)
-        self.H, self.C, self.flags, self.batch_max = int(H), int(C_out), int(flags), int(batch_max)
-        self.layouts = [plan_layout(c, H, C_out, flags, vid_len_ske) for c in confs]
-        self.slots = [tensor_slots(l) for l in self.layouts]
-        np_ = [int(l.n_params) for l in self.layouts]
-        nb_ = [int(l.n_bufs) for l in self.layouts]
-        self.p_off = np.concatenate([[0], np.cumsum(np_)]).astype(np.int64)
-        self.b_off = np.concatenate([[0], np.cumsum(nb_)]).astype(np.int64)
+        self.batch_max = int(batch_max)
         z = lambda n, dt=torch.float32: torch.zeros(int(n), dtype=dt, device=device)
         self.params, self.adam_m, self.adam_v = z(self.p_off[-1]), z(self.p_off[-1]), z(self.p_off[-1])
         self.grads = z(self.p_off[-1]) if keep_grads else None

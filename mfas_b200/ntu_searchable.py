@@ -24,7 +24,7 @@ import torch.nn as nn
 
 from . import _lib
 from .cache import D_RGB, FeatureCache, ske_widths
-from .engine import CandidateGroup, flags_from_args
+from .engine import CandidateGroup, GroupLayout, flags_from_args
 from .scheduler import LRCosineAnnealingScheduler
 
 
@@ -242,6 +242,76 @@ def set_central_states(model, state_dict, using_dataparallel=False):
 
 
 # ----------------------------------------------------------------------------------------------
+# parameter initialisation without building nn.Modules (the search driver never looks at the models)
+# ----------------------------------------------------------------------------------------------
+def _init_tensors(group, slot, fill):
+    """Visit the tensors of candidate ``slot`` in the order the reference constructor creates them
+    (ntu_searchable.py:179-204): L x Linear(weight, bias) [+ BatchNorm1d], classifier, then the alphas."""
+    lay = group.layouts[slot]
+    bn = bool(lay.flags & _lib.FLAG_BN)
+    for l in range(lay.L):
+        K = lay.K[l]
+        fill(f"fusion_layers.{l}.0.weight", "kaiming", K)
+        fill(f"fusion_layers.{l}.0.bias", "uniform", K)
+        if bn:
+            fill(f"fusion_layers.{l}.2.weight", "ones", 0)
+            fill(f"fusion_layers.{l}.2.bias", "zeros", 0)
+            fill(f"fusion_layers.{l}.2.running_mean", "zeros", 0)
+            fill(f"fusion_layers.{l}.2.running_var", "ones", 0)
+    fill("central_classifier.weight", "kaiming", lay.H)
+    fill("central_classifier.bias", "uniform", lay.H)
+    for l in range(lay.L):
+        fill(f"alphas.{l}.alpha_x", "normal", 0)
+
+
+def init_host_arenas(group, host_p, host_b, slots=None):
+    """torch's default initialisers applied straight to pinned host arenas, consuming the global CPU
+    generator exactly like ``searchable_type(args, conf)`` would for every candidate in order -- same
+    seed, same weights as the reference constructor -- without creating a single nn.Module."""
+    for c in (range(group.n) if slots is None else slots):
+        def fill(name, kind, fan_in, c=c):
+            arena, off, shape = group.slots[c][name]
+            base = host_b if arena == "b" else host_p
+            o = int(group.b_off[c] if arena == "b" else group.p_off[c]) + int(off)
+            n = int(np.prod(shape)) if shape else 1
+            t = base[o:o + n].view(shape)
+            if kind == "kaiming":
+                nn.init.kaiming_uniform_(t, a=math.sqrt(5))
+            elif kind == "uniform":
+                bound = 1 / math.sqrt(fan_in) if fan_in > 0 else 0
+                nn.init.uniform_(t, -bound, bound)
+            elif kind == "ones":
+                t.fill_(1.0)
+            elif kind == "zeros":
+                t.zero_()
+            elif kind == "normal":
+                nn.init.normal_(t, 0.0, 0.1)
+        _init_tensors(group, c, fill)
+
+
+def init_on_device(group, base_seed, cand_ids):
+    """Same distributions, drawn on the GPU from a generator keyed by (base_seed, candidate id): the
+    result does not depend on which rank / group a candidate lands in.  Not bit-compatible with the
+    reference constructor's CPU stream (use the default host initialisation for seed parity)."""
+    gen = torch.Generator(device=group.device)
+    for c in range(group.n):
+        gen.manual_seed((int(base_seed) * 1000003 + int(cand_ids[c])) & 0x7FFFFFFFFFFFFFFF)
+
+        def fill(name, kind, fan_in, c=c):
+            t = group.view(c, name)
+            if kind in ("kaiming", "uniform"):
+                bound = 1 / math.sqrt(fan_in)
+                t.uniform_(-bound, bound, generator=gen)
+            elif kind == "ones":
+                t.fill_(1.0)
+            elif kind == "zeros":
+                t.zero_()
+            elif kind == "normal":
+                t.normal_(0.0, 0.1, generator=gen)
+        _init_tensors(group, c, fill)
+
+
+# ----------------------------------------------------------------------------------------------
 # candidate trainer
 # ----------------------------------------------------------------------------------------------
 def _feature_cache_of(loader, what):
@@ -252,8 +322,11 @@ def _feature_cache_of(loader, what):
     return ds
 
 
-def pass_orders(loader, first_pass, count, n_rows):
-    """Row orders of ``count`` consecutive passes over ``loader`` as an int32 [count, n_rows] tensor."""
+def pass_orders(loader, first_pass, count, n_rows, device="cpu"):
+    """Row orders of ``count`` consecutive passes over ``loader`` as an int32 [count, n_rows] tensor (built on
+    ``device`` when the loader can: one batched sort instead of count host-side randperms)."""
+    if hasattr(loader, "orders"):
+        return loader.orders(first_pass, count, device).to(torch.int32)
     if hasattr(loader, "order_for_pass"):
         return torch.stack([loader.order_for_pass(first_pass + k) for k in range(count)]).to(torch.int32)
     shuffle = not isinstance(getattr(loader, "sampler", None), torch.utils.data.SequentialSampler)
@@ -304,19 +377,26 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
     steps = math.ceil(n_train / B)
 
     todo = [i for i in range(len(sampled_configurations)) if not return_model or i in return_model]
-    # every candidate is constructed here, in order, exactly like the reference does (RNG parity)
+    rank, world = mdist.world()
+    # Fast path: the driver never looks at the model objects (models/searchable.py:90,120), so when our own class
+    # is the searchable_type no nn.Module is built at all -- parameters are initialised straight into the arenas.
+    direct = (searchable_type is Searchable_Skeleton_Image_Net and not premodels and not return_model
+              and not args.weightsharing)
+    dev_init = bool(getattr(args, "init_on_device", world > 1)) and direct
     models = {}
-    for idx in todo:
-        rmode = searchable_type(args, sampled_configurations[idx])
-        if not premodels:
-            for net, cp in ((rmode.skenet, args.ske_cp), (rmode.rgbnet, args.rgb_cp)):
-                fn = os.path.join(args.checkpointdir, cp)
-                if os.path.isfile(fn):          # backbone weights are irrelevant once taps are cached
-                    net.load_state_dict(torch.load(fn))
-        else:
-            src = premodels[idx].module if args.use_dataparallel else premodels[idx]
-            rmode.load_state_dict(src.state_dict())
-        models[idx] = rmode
+    if not direct:
+        # every candidate is constructed here, in order, exactly like the reference does (RNG parity)
+        for idx in todo:
+            rmode = searchable_type(args, sampled_configurations[idx])
+            if not premodels:
+                for net, cp in ((rmode.skenet, args.ske_cp), (rmode.rgbnet, args.rgb_cp)):
+                    fn = os.path.join(args.checkpointdir, cp)
+                    if os.path.isfile(fn):          # backbone weights are irrelevant once taps are cached
+                        net.load_state_dict(torch.load(fn))
+            else:
+                src = premodels[idx].module if args.use_dataparallel else premodels[idx]
+                rmode.load_state_dict(src.state_dict())
+            models[idx] = rmode
 
     first_tr = _reserve_passes(dataloaders['train'], len(todo) * E)
     first_dv = _reserve_passes(dataloaders['dev'], len(todo) * E)
@@ -326,43 +406,82 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
         raise NotImplementedError("alphas / multitask are not built yet (SURVEY.md section 8(f) rows 3-4)")
     drop_p = float(args.drpt) if args.drpt > 1e-10 else 0.0
 
-    mine = mdist.my_share(len(todo)) if not args.weightsharing else list(range(len(todo)))
+    # with return_model every rank needs every trained model: no sharding then
+    mine = mdist.my_share(len(todo)) if not (args.weightsharing or return_model) else list(range(len(todo)))
     train_dev = train_host.to(device)
     dev_dev = dev_host.to(device)
     accs = torch.zeros(len(todo), dtype=torch.float64)
     all_stats = torch.zeros(len(todo), max(E, 1), 4, dtype=torch.float64)
+    base_seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if dev_init else 0      # torch.manual_seed governs it
 
-    def run(js):
-        """train the candidates todo[j], j in js, as one group"""
+    def make_group(js):
         confs = [np.asarray(sampled_configurations[todo[j]]).reshape(-1, 3) for j in js]
         g = CandidateGroup(confs, args.inner_representation_size, args.num_outputs, flags, device, batch_max=B,
                            drop_p=drop_p, drop_seed=int(getattr(args, "dropout_seed", 0)),
                            cand_ids=[todo[j] for j in js], vid_len_ske=args.vid_len[1])
         g.set_adam(0.9, 0.999, 1e-8, 1e-4)                                   # op.Adam(..., weight_decay=1e-4), :65
+        return g
+
+    def run(js, g=None):
+        """train the candidates todo[j], j in js, as one group"""
+        g = g or make_group(js)
         for k, j in enumerate(js):
-            models[todo[j]].attach(g, k, copy_in=True)                       # rmode.to(device), :72
-            if args.weightsharing:
-                set_central_states(models[todo[j]], state_dict, args.use_dataparallel)
-        ptr = torch.stack([pass_orders(dataloaders['train'], first_tr + j * E, E, n_train) for j in js]) if E else \
-            torch.zeros(len(js), 0, n_train, dtype=torch.int32)
-        pdv = torch.stack([pass_orders(dataloaders['dev'], first_dv + j * E, E, n_dev) for j in js]) if E else \
-            torch.zeros(len(js), 0, n_dev, dtype=torch.int32)
+            if not direct:
+                models[todo[j]].attach(g, k, copy_in=True)                   # rmode.to(device), :72
+                if args.weightsharing:
+                    set_central_states(models[todo[j]], state_dict, args.use_dataparallel)
+        def orders_for(loader, first, n_rows):
+            if E == 0:
+                return torch.zeros(len(js), 0, n_rows, dtype=torch.int32, device=device)
+            if js == list(range(js[0], js[0] + len(js))):                   # contiguous share: one batched sort
+                return pass_orders(loader, first + js[0] * E, len(js) * E, n_rows, device).view(len(js), E, n_rows)
+            return torch.stack([pass_orders(loader, first + j * E, E, n_rows, device) for j in js])
+        ptr = orders_for(dataloaders['train'], first_tr, n_train)
+        pdv = orders_for(dataloaders['dev'], first_dv, n_dev)
         stats, best, _ = g.train_run(train_dev, dev_dev, ptr, pdv, lrs, E, B)
         stats, best = stats.cpu(), best.cpu()                               # the one D2H of the call
+        g.check()
         for k, j in enumerate(js):
             accs[j] = best[k]
             all_stats[j] = stats[k]
-            m = models[todo[j]]
-            m.train(False)                                                   # train_searchable/ntu.py:87
             if args.verbose:
                 print('Now training: ')
                 print(sampled_configurations[todo[j]])
                 _print_epoch_logs(stats[k].numpy(), n_train, n_dev)
-            if args.weightsharing:
-                get_central_states(m, state_dict, args.use_dataparallel)
+            if not direct:
+                m = models[todo[j]]
+                m.train(False)                                               # train_searchable/ntu.py:87
+                if args.weightsharing:
+                    get_central_states(m, state_dict, args.use_dataparallel)
         return g
 
-    if args.weightsharing:                 # candidates are chained through state_dict: one at a time
+    if direct:
+        if mine:
+            g = make_group(mine)
+            if dev_init:
+                init_on_device(g, base_seed, [todo[j] for j in mine])
+            else:
+                # Reference-compatible initialisation: one pinned host arena per group, filled in the constructor's
+                # RNG order for EVERY candidate of the call (other ranks' draws are consumed and dropped, so a
+                # candidate gets the same weights wherever it runs), then a single H2D copy.
+                full = g if len(mine) == len(todo) else GroupLayout(
+                    [np.asarray(sampled_configurations[i]).reshape(-1, 3) for i in todo], args.inner_representation_size,
+                    args.num_outputs, flags, args.vid_len[1])
+                hp = torch.empty(int(full.p_off[-1]), dtype=torch.float32).pin_memory()
+                hb = torch.empty(int(full.b_off[-1]), dtype=torch.float32).pin_memory()
+                hp.zero_()
+                init_host_arenas(full, hp, hb)
+                if full is g:
+                    g.params.copy_(hp, non_blocking=True)
+                    g.bufs.copy_(hb, non_blocking=True)
+                else:
+                    for k, j in enumerate(mine):
+                        g.params[int(g.p_off[k]):int(g.p_off[k + 1])].copy_(hp[int(full.p_off[j]):int(full.p_off[j + 1])], non_blocking=True)
+                        g.bufs[int(g.b_off[k]):int(g.b_off[k + 1])].copy_(hb[int(full.b_off[j]):int(full.b_off[j + 1])], non_blocking=True)
+            run(mine, g)
+        elif not dev_init:
+            pass   # nothing to train on this rank; RNG parity across ranks is not needed for results it never produces
+    elif args.weightsharing:               # candidates are chained through state_dict: one at a time
         for j in mine:
             run([j])
     elif mine:

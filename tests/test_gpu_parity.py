@@ -154,7 +154,7 @@ def test_teacher_forced_steps_along_a_trajectory():
     of a cfg2-shaped trajectory into the GPU group and compare ONE step from there: this is parity of
     the step function on warmed-up states, free of trajectory amplification."""
     conf = FOUND_CONFS[4]
-    H, B, ntr = 128, 64, 640
+    H, B, ntr = 128, 64, 1024
     train = synthetic_ntu_cache(ntr, 5)
     trs = split_np(train)
     order = FeatureCacheLoader(train, B, True, 7).order_for_pass(0).numpy()
@@ -164,7 +164,7 @@ def test_teacher_forced_steps_along_a_trajectory():
     g = _group([conf], H, B, keep_grads=True)
     tc = train.to(DEV)
     checked = 0
-    for step in range(10):
+    for step in range(16):
         rows = order[step * B:(step + 1) * B]
         lr = sch.step()
         before = dict(state={k: v.copy() for k, v in head.state.items()},
@@ -172,9 +172,9 @@ def test_teacher_forced_steps_along_a_trajectory():
         t_before = head.t
         sk, rg, y = O._taps_of(trs, rows)
         ol, oloss, ograds = head.train_step(sk, rg, y, lr)
-        if step not in (0, 2, 3, 6, 9):
+        if step % 2 == 1 and step != 15:
             continue
-        if head.kink_margin() < 4e-6:
+        if head.kink_margin() < 2e-5:
             continue      # a pre-activation sits on the ReLU kink: the derivative is decided by rounding
         g.load_state(0, before["state"])
         for k, (m, v) in before["adam"].items():
@@ -481,3 +481,29 @@ def test_tc_engine_matches_ffma_engine_and_is_deterministic(monkeypatch):
     assert torch.equal(st1[0], stt[1])
     for name in gt.names(1):
         assert torch.equal(gt.view(1, name), g1.view(0, name)), name
+
+
+def test_hashed_orders_same_on_cpu_and_gpu():
+    from mfas_b200.cache import hashed_orders
+    a = hashed_orders(100, 3, 5, 1000, "cpu")
+    b = hashed_orders(100, 3, 5, 1000, DEV).cpu()
+    assert torch.equal(a, b)
+    assert sorted(a[2].tolist()) == list(range(1000))
+
+
+def test_device_init_is_placement_independent():
+    """args.init_on_device: a candidate gets the same initial weights and result whatever group / rank it lands in."""
+    import mfas_b200.ntu_searchable as ntu
+    args = make_args(64, 32, 1, bn=True)
+    args.init_on_device = True
+    train, dev = synthetic_ntu_cache(128, 5), synthetic_ntu_cache(64, 6)
+    confs = [np.array(FOUND_CONFS[4]), np.array([[0, 0, 0]]), np.array(FOUND_CONFS[1][:2])]
+
+    def run(sel):
+        loaders = {"train": FeatureCacheLoader(train, 32, True, 1), "dev": FeatureCacheLoader(dev, 32, True, 2)}
+        torch.manual_seed(11)
+        return ntu.train_sampled_models([confs[i] for i in sel], ntu.Searchable_Skeleton_Image_Net, loaders, args, torch.device(DEV))
+
+    full = run([0, 1, 2])
+    again = run([0, 1, 2])
+    assert [float(a) for a in full] == [float(a) for a in again]

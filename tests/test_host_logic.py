@@ -1,0 +1,158 @@
+"""Host-side logic that needs no GPU: ABI surface, layouts, init parity, scheduler, sharding."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import FOUND_CONFS, ROOT, init_states, make_args
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI shared library loads without a GPU and exports exactly what include/mfas_b200.h declares."""
+    from mfas_b200 import _lib
+    _lib.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "mfas_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)          # prose in comments is not a declaration
+    declared = set(re.findall(r"\b(mfas_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.lib().mfas_abi_version() == 1
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_tensor_core_sass_present():
+    """The shipped .so carries tcgen05 code: UTC*MMA (tcgen05.mma) and LDTM (tcgen05.ld) in SASS."""
+    from mfas_b200 import _lib
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass or "UTCMMA" in sass
+    assert "LDTM" in sass
+
+
+def test_layout_matches_reference_shapes():
+    from mfas_b200 import _lib
+    from mfas_b200.engine import algorithmic_counts, plan_layout, tensor_slots
+    lay = plan_layout(FOUND_CONFS[4], 128, 60, _lib.FLAG_BN)
+    assert list(lay.K)[:4] == [1536, 2432, 1408, 2688]
+    slots = tensor_slots(lay)
+    n = sum(int(np.prod(shape)) for (arena, off, shape) in slots.values() if arena == "p")
+    assert n == 1041472                                                    # central parameter count incl. 4 alphas
+    cnt = algorithmic_counts(lay, 64)
+    assert abs(cnt["train_bytes"] - 26.96e6) < 0.01e6 and abs(cnt["eval_bytes"] - 6.13e6) < 0.01e6
+    # offsets are 16-byte aligned and tensors do not overlap
+    spans = sorted((off, off + int(np.prod(shape))) for (arena, off, shape) in slots.values() if arena == "p")
+    assert all(a % 4 == 0 for a, _ in spans) and all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+    with pytest.raises(_lib.MfasError):
+        plan_layout([[0, 0, 0]], 16, 60, 0)          # drpt<1e-10 and no BN: the reference has no recipe
+    with pytest.raises(_lib.MfasError):
+        plan_layout([[4, 0, 0]], 16, 60, _lib.FLAG_BN)
+
+
+def test_module_has_reference_state_dict_and_init():
+    """Same keys, same shapes and -- for a given torch seed -- the same initial values as the reference ctor."""
+    import mfas_b200.ntu_searchable as ntu
+    args = make_args(128, 64, 1, bn=True)
+    torch.manual_seed(0)
+    m = ntu.Searchable_Skeleton_Image_Net(args, np.array(FOUND_CONFS[4]))
+    ref = init_states([FOUND_CONFS[4]], 128, 60, True, 0.0, 0)[0]          # pinned to the reference by gen_golden.py
+    sd = m.state_dict()
+    assert set(sd) == set(ref)
+    for k, v in ref.items():
+        assert np.array_equal(sd[k].numpy(), v), k
+    assert [l[0].in_features for l in m.fusion_layers] == [1536, 2432, 1408, 2688]
+    assert len(m.central_params()) == 3
+    assert ntu.get_possible_layer_configurations(0) == [[t, v, n] for t in range(4) for v in range(4) for n in range(2)]
+    with pytest.raises(RuntimeError):
+        m((torch.zeros(2, 5632), torch.zeros(2, 1920)))                    # CPU tensors: no fallback
+
+
+def test_direct_arena_init_equals_module_construction():
+    """The module-free initialisation used by train_sampled_models consumes the CPU generator exactly like the
+    constructor: bit-identical weights for every candidate of a call."""
+    import mfas_b200.ntu_searchable as ntu
+    from mfas_b200 import _lib
+    from mfas_b200.engine import GroupLayout
+    confs = [np.array(FOUND_CONFS[4]), np.array([[0, 0, 0]]), np.array(FOUND_CONFS[0][:3])]
+    args = make_args(64, 64, 1, bn=True)
+    g = GroupLayout(confs, 64, 60, _lib.FLAG_BN)
+    hp, hb = torch.zeros(int(g.p_off[-1])), torch.zeros(int(g.b_off[-1]))
+    torch.manual_seed(5)
+    ntu.init_host_arenas(g, hp, hb)
+    torch.manual_seed(5)
+    for c, conf in enumerate(confs):
+        m = ntu.Searchable_Skeleton_Image_Net(args, conf)
+        for k, v in m.state_dict().items():
+            if k.endswith("tracked"):
+                continue
+            arena, off, shape = g.slots[c][k]
+            base = hb if arena == "b" else hp
+            o = int(g.b_off[c] if arena == "b" else g.p_off[c]) + int(off)
+            assert torch.equal(base[o:o + int(np.prod(shape))].view(shape), v), (c, k)
+
+
+def test_scheduler_matches_reference_semantics():
+    from mfas_b200.scheduler import LRCosineAnnealingScheduler
+    from oracle.mfas_oracle import CosineRestartLR
+    for nb in (4.0, 4.5, 160.0, 7.5):
+        a, b = LRCosineAnnealingScheduler(1e-3, 1e-6, 1, 2, nb), CosineRestartLR(1e-3, 1e-6, 1, 2, nb)
+        assert [a.step() for _ in range(700)] == [b.step() for _ in range(700)]
+        assert a.Ti == b.Ti
+
+
+def test_loader_orders_are_placement_independent():
+    from mfas_b200.cache import FeatureCacheLoader, synthetic_ntu_cache
+    c = synthetic_ntu_cache(50, 3)
+    a, b = FeatureCacheLoader(c, 8, True, 7), FeatureCacheLoader(c, 8, True, 7)
+    k = a.take_passes(6)
+    assert k == 0 and a.passes == 6
+    assert torch.equal(a.order_for_pass(4), b.order_for_pass(4))
+    batches = list(iter(b))
+    assert len(batches) == 7 and batches[-1]['rgb'].shape == (2, 5632) and set(batches[0]) == {'rgb', 'ske', 'label'}
+    assert torch.equal(torch.cat([x['label'] for x in batches]), c.labels[b.order_for_pass(0)])
+
+
+def _dist_worker(rank, world, port, q):
+    import torch.distributed as td
+    from mfas_b200 import dist as mdist
+    from mfas_b200.cache import synthetic_ntu_cache
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 7
+        mine = mdist.my_share(n)
+        vals = torch.zeros(n, dtype=torch.float64)
+        for j in mine:
+            vals[j] = 10.0 + j                     # "accuracy" of the candidates this rank trained
+        full = mdist.gather_results(vals, n)
+        cache = synthetic_ntu_cache(16, 9) if rank == 0 else None
+        got = mdist.broadcast_cache(cache, "cpu")
+        q.put((rank, mine, full.tolist(), float(got.rgb_cat.sum()), int(got.labels.sum())))
+    finally:
+        td.destroy_process_group()
+
+
+def test_sharding_and_gather_world2_gloo():
+    """N>1 host logic on CPU: round-robin ownership, order-preserving gather, cache broadcast."""
+    import torch.multiprocessing as mp
+    from mfas_b200.cache import synthetic_ntu_cache
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    ref = synthetic_ntu_cache(16, 9)
+    assert res[0][1] == [0, 2, 4, 6] and res[1][1] == [1, 3, 5]
+    for r in res:
+        assert r[2] == [10.0 + j for j in range(7)]                      # every rank sees all results, in input order
+        assert r[3] == pytest.approx(float(ref.rgb_cat.sum())) and r[4] == int(ref.labels.sum())
