@@ -1,0 +1,45 @@
+"""Plug the B200 path into the *unmodified* reference tree.
+
+The reference driver binds the hot path by module attribute
+(`import models.search.ntu_searchable as ntu`, /root/reference/models/searchable.py:23, used at :256-260)
+and `main_found_ntu.py` by `import models.search.train_searchable.ntu as tr` (:19).  `install()` makes those
+imports resolve to this package; nothing in the reference is edited.
+"""
+from __future__ import annotations
+
+import sys
+import types
+
+
+def install(shim_broken_imports: bool = True):
+    """Call once, after the reference root is on sys.path and before `import models.searchable`."""
+    from . import ntu_searchable, scheduler, train_ntu
+    if shim_broken_imports:
+        # the reference as shipped does not import: matplotlib is an unused import of
+        # models/utils.py:61, `models.aux` / `models.train` are dangling names in loops we never call
+        for n in ("matplotlib", "matplotlib.pyplot"):
+            sys.modules.setdefault(n, types.ModuleType(n))
+        for n in ("models.aux", "models.train"):
+            pkg = types.ModuleType(n)
+            pkg.scheduler = scheduler
+            sys.modules.setdefault(n, pkg)
+            sys.modules.setdefault(n + ".scheduler", scheduler)
+    sys.modules["models.search.ntu_searchable"] = ntu_searchable
+    sys.modules["models.search.train_searchable.ntu"] = train_ntu
+    sys.modules["models.auxiliary.scheduler"] = scheduler
+    return ntu_searchable
+
+
+def cached_ntu_searcher(S, args, device, train_cache, dev_cache, seed=0):
+    """An `NTUSearcher` (models/searchable.py:233-260) whose dataloaders walk a feature cache instead of decoding
+    NTU videos; `.search()` is the reference's own `_epnas` loop.  `S` is the imported `models.searchable`."""
+    from .cache import FeatureCacheLoader
+
+    class CachedNTUSearcher(S.NTUSearcher):
+        def __init__(self):
+            S.ModelSearcher.__init__(self, args)
+            self.device = device
+            self.dataloaders = {"train": FeatureCacheLoader(train_cache, args.batchsize, True, seed),
+                                "dev": FeatureCacheLoader(dev_cache, args.batchsize, True, seed + 50000)}
+
+    return CachedNTUSearcher()
