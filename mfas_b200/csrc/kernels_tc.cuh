@@ -974,4 +974,192 @@ k_tc_bwd_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int 
   if (warp == 0) umma::tmem_free(tm, 64);
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward, all layers, persistent + warp-specialised (BP = 64): one CTA per SM walks a static list of
+// tiles (the same 128 weight columns x 64 rows tile as k_tc_bwd_all) with three decoupled roles, so
+// the x/dz operand traffic, the tensor-core work and the Adam p/m/v stream of different tiles overlap
+// all the time instead of taking turns inside a CTA:
+//   warps 0-7   stagers : gather x rows + dz slice -> hi/lo split -> smem stage s      (full[s]  -> MMA)
+//   warp  8     MMA     : 3 x tcgen05.mma per 8 batch rows into TMEM buffer t          (empty[s] -> stagers,
+//                                                                                       tfull[t] -> Adam)
+//   warps 9-16  Adam    : p/m/v prefetched two row-batches ahead (across tile boundaries), gradient read
+//                         straight out of TMEM, update, store                          (tempty[t] -> MMA)
+// smem: 2 stages x 96 KB; TMEM: 2 x 64 columns.  Tile list: int4 {candidate, layer, first column, first row}.
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_WS_THREADS = 17 * 32;
+
+template <bool KEEP_GRAD>
+__global__ void __launch_bounds__(TC_WS_THREADS, 1)
+k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, AdamH adam, float step_size,
+            float bc2_sqrt, const int4* __restrict__ tiles, int n_tiles, TcErr err) {
+  constexpr int BP = 64;
+  constexpr uint32_t BLK = BP * 128, A_TILE = 4 * BLK, B_TILE = 2 * BLK, STAGE = 2 * A_TILE + 2 * B_TILE;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full[2], empty[2], tfull[2], tempty[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nrows = batch.n_rows;
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
+  if (tid == 32) {
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(&full[i], 8); umma::mbar_init(&empty[i], 1);
+      umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 8);
+    }
+    umma::fence_mbar_init();
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tm = tmem_slot;
+  const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  bool ok = true;
+
+  if (warp < 8) {
+    // ================================ stagers =====================================================
+    float4 xv[8], dv[4];
+    auto issue_loads = [&](int i) {
+      const int4 t = tiles[blockIdx.x + i * gridDim.x];
+      const DCand& cd = cands[t.x];
+      const DLayer& ly = cd.layer[t.y];
+      const int H = cd.H, K = ly.K, kc0 = t.z, kw = min(TC_BWD_KT, K - kc0);
+      const int fs = ly.d_ske, fr = ly.d_rgb;
+      const float* src; long long ld; int kl; bool gather = true;
+      if (kc0 < fs) { src = cache.ske[ly.ske_tap]; ld = cache.ske_ld[ly.ske_tap]; kl = kc0; }
+      else if (kc0 < fs + fr) { src = cache.rgb[ly.rgb_tap]; ld = cache.rgb_ld[ly.rgb_tap]; kl = kc0 - fs; }
+      else { src = cd.hid + (long long)(t.y - 1) * bmax * H; ld = H; kl = kc0 - fs - fr; gather = false; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int idx = tid + 256 * j, r = idx >> 5, c4 = idx & 31;
+        xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nrows && c4 * 4 < kw) {
+          const long long row = gather ? (long long)batch_row(batch, t.x, r) : (long long)r;
+          xv[j] = __ldg(reinterpret_cast<const float4*>(src + row * ld + kl + c4 * 4));
+        }
+      }
+      const float* dzl = cd.dzs + (long long)t.y * bmax * H + t.w;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = tid + 256 * j, r = idx >> 4, c4 = idx & 15;
+        dv[j] = (r < nrows) ? *reinterpret_cast<const float4*>(dzl + (long long)r * H + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (n_my > 0) issue_loads(0);
+    for (int i = 0; i < n_my; ++i) {
+      const int sg = i & 1;
+      uint8_t* st = smem + sg * STAGE;
+      if (!umma::mbar_wait(&empty[sg], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int idx = tid + 256 * j, r = idx >> 5, c4 = idx & 31;
+        store_split(st, st + A_TILE, (uint32_t)(c4 >> 3) * BLK + umma::sw128_b32(r, (c4 & 7) * 16), xv[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = tid + 256 * j, r = idx >> 4, c4 = idx & 15;
+        store_split(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, (uint32_t)(c4 >> 3) * BLK + umma::sw128_b32(r, (c4 & 7) * 16), dv[j]);
+      }
+      umma::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&full[sg]);
+      if (i + 1 < n_my) issue_loads(i + 1);            // in flight while the next stage is still being consumed
+    }
+  } else if (warp == 8) {
+    // ================================ MMA issuer ==================================================
+    constexpr uint32_t idesc = umma::idesc_tf32(128, TC_BWD_HT, true, true);
+    const int ksteps = (nrows + 7) >> 3;
+    for (int i = 0; i < n_my; ++i) {
+      const int sg = i & 1;
+      if (!umma::mbar_wait(&full[sg], (i >> 1) & 1)) { ok = false; break; }
+      if (!umma::mbar_wait(&tempty[sg], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
+      umma::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_hi = umma::smem_u32(smem + sg * STAGE), a_lo = a_hi + A_TILE, b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
+        const uint32_t d = tm + sg * 64;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t adv = ks * 1024u;
+          const uint64_t dah = umma::smem_desc(a_hi + adv, BLK, 512, umma::kLayoutSw128Base32);
+          const uint64_t dal = umma::smem_desc(a_lo + adv, BLK, 512, umma::kLayoutSw128Base32);
+          const uint64_t dbh = umma::smem_desc(b_hi + adv, BLK, 512, umma::kLayoutSw128Base32);
+          const uint64_t dbl = umma::smem_desc(b_lo + adv, BLK, 512, umma::kLayoutSw128Base32);
+          umma::mma_tf32(d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+          umma::mma_tf32(d, dah, dbl, idesc, 1u);
+          umma::mma_tf32(d, dah, dbh, idesc, 1u);
+        }
+        umma::mma_commit(&empty[sg]);                  // smem stage free once these MMAs have read it
+        umma::mma_commit(&tfull[sg]);                  // accumulator ready for the Adam warps
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================ Adam warps ==================================================
+    const int aw = warp - 9;                           // 0..7
+    const int q = warp & 3, cg = aw >> 2;              // TMEM lane quarter this warp may read; row half
+    const int kcol = q * 32 + lane;
+    const float inv_bc2 = 1.f / bc2_sqrt;
+    struct Set { float p[8], m[8], v[8]; };
+    struct Tile { float* W; long long K, moff, voff, goff; bool valid; };
+    Set sa, sb;
+    auto open_tile = [&](int i) {
+      const int4 t = tiles[blockIdx.x + i * gridDim.x];
+      const DCand& cd = cands[t.x];
+      const DLayer& ly = cd.layer[t.y];
+      Tile o;
+      o.K = ly.K;
+      o.valid = q * 32 < min(TC_BWD_KT, ly.K - t.z);
+      o.W = cd.p + ly.oW + (long long)(t.w + cg * 32) * ly.K + t.z + kcol;
+      o.moff = (long long)(cd.m - cd.p); o.voff = (long long)(cd.v - cd.p);
+      o.goff = KEEP_GRAD ? (long long)(cd.grad - cd.p) : 0;
+      return o;
+    };
+    auto prefetch = [&](Set& st, const Tile& t, int j0) {
+      if (!t.valid) return;
+      const float* w = t.W + (long long)j0 * t.K;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { st.p[j] = w[0]; st.m[j] = w[t.moff]; st.v[j] = w[t.voff]; w += t.K; }
+    };
+    auto update = [&](Set& st, const Tile& t, uint32_t tcol, int j0) {
+      float g[8];
+      umma::tmem_ld8(tm + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)(cg * 32 + j0), g);
+      if (t.valid) {
+        float* w = t.W + (long long)j0 * t.K;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (KEEP_GRAD) w[t.goff] = g[j];
+          adam_update_fast(g[j], st.p[j], st.m[j], st.v[j], adam, step_size, inv_bc2);
+          w[0] = st.p[j]; w[t.moff] = st.m[j]; w[t.voff] = st.v[j];
+          w += t.K;
+        }
+      }
+    };
+    Tile cur{}, nxt{};
+    if (n_my > 0) {
+      cur = open_tile(0);
+      prefetch(sa, cur, 0);
+      prefetch(sb, cur, 8);
+    }
+    for (int i = 0; i < n_my; ++i) {
+      const int sg = i & 1;
+      if (!umma::mbar_wait(&tfull[sg], (i >> 1) & 1)) { ok = false; break; }
+      umma::tc_fence_after();
+      const uint32_t tcol = sg * 64;
+      update(sa, cur, tcol, 0);
+      prefetch(sa, cur, 16);
+      update(sb, cur, tcol, 8);
+      prefetch(sb, cur, 24);
+      update(sa, cur, tcol, 16);
+      if (i + 1 < n_my) { nxt = open_tile(i + 1); prefetch(sa, nxt, 0); }     // the stream never drains between tiles
+      update(sb, cur, tcol, 24);
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&tempty[sg]);   // this warp has drained its part of the accumulator
+      if (i + 1 < n_my) { prefetch(sb, nxt, 8); cur = nxt; }
+    }
+  }
+  if (!ok) atomicExch(err.flag, 5);
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_free(tm, 128);
+}
+
 }  // namespace mfas

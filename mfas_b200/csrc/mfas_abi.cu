@@ -139,6 +139,8 @@ struct mfas_group {
   long long part_stride = 0;
   int* tc_err = nullptr;          // device flag set by a timed-out barrier wait
   size_t smem_tc_fwd = 0, smem_tc_bwd = 0, smem_fl = 0, smem_dzx = 0, smem_chain = 0;
+  int4* bwd_tiles = nullptr;      // tile list of the persistent backward kernel {cand, layer, first column, first row}
+  int n_bwd_tiles = 0, n_sms = 148, bwd_ws = 1;
   int dbg = 0;                    // MFAS_TC_DEBUG bit 0: skip the Adam epilogue, bit 1: skip operand staging (timing experiments only)
   int chain = 1;                  // 1: tensor-core chain kernels, 0: CUDA-core chain kernels (MFAS_CHAIN=ffma)
 };
@@ -163,6 +165,7 @@ extern "C" int mfas_group_destroy(mfas_group_t g) {
   if (g->ws) cudaFree(g->ws);
   if (g->improved) cudaFree(g->improved);
   if (g->part) cudaFree(g->part);
+  if (g->bwd_tiles) cudaFree(g->bwd_tiles);
   if (g->tc_err) cudaFree(g->tc_err);
   delete g;
   return MFAS_OK;
@@ -332,6 +335,23 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     attr((const void*)k_chain_bwd<64>, ChainCfg<64>::SMEM);
     attr((const void*)k_chain_bwd<128>, ChainCfg<128>::SMEM);
     { const char* ce = getenv("MFAS_CHAIN"); if (ce && !strcmp(ce, "ffma")) g->chain = 0; }
+    { const char* be = getenv("MFAS_BWD"); if (be && !strcmp(be, "cta")) g->bwd_ws = 0; }
+    if (g->npad != 64) g->bwd_ws = 0;                   // the persistent kernel double-buffers 96 KB stages: batch <= 64
+    if (g->bwd_ws) {
+      std::vector<int4> tl;
+      for (int c = 0; c < n_cand; ++c)
+        for (int l = 0; l < g->lay[c].L; ++l)
+          for (int kc0 = 0; kc0 < g->lay[c].K[l]; kc0 += TC_BWD_KT)
+            for (int h0 = 0; h0 < g->lay[c].H; h0 += TC_BWD_HT) tl.push_back(make_int4(c, l, kc0, h0));
+      g->n_bwd_tiles = (int)tl.size();
+      cudaDeviceProp prop;
+      if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+      if (e == cudaSuccess) g->n_sms = prop.multiProcessorCount;
+      if (e == cudaSuccess) e = cudaMalloc(&g->bwd_tiles, sizeof(int4) * tl.size());
+      if (e == cudaSuccess) e = cudaMemcpy(g->bwd_tiles, tl.data(), sizeof(int4) * tl.size(), cudaMemcpyHostToDevice);
+      attr((const void*)k_tc_bwd_ws<false>, 1024 + 2 * 98304);
+      attr((const void*)k_tc_bwd_ws<true>, 1024 + 2 * 98304);
+    }
     { const char* de = getenv("MFAS_TC_DEBUG"); if (de) g->dbg = atoi(de); }
     if (e != cudaSuccess) {
       int code = fail(MFAS_ERR_CUDA, "tc engine setup: %s", cudaGetErrorString(e));
@@ -357,7 +377,7 @@ extern "C" int mfas_group_status(mfas_group_t g) {
   if (g->tc_err) {
     int flag = 0;
     CUDA_TRY(cudaMemcpy(&flag, g->tc_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flag) return fail(MFAS_ERR_CUDA, "tensor-core pipeline barrier timed out in kernel %s", flag == 1 ? "k_tc_fwd_all" : flag == 2 ? "k_tc_bwd_all" : flag == 3 ? "k_chain_fwd" : "k_chain_bwd");
+    if (flag) return fail(MFAS_ERR_CUDA, "tensor-core pipeline barrier timed out in kernel %s", flag == 1 ? "k_tc_fwd_all" : flag == 2 ? "k_tc_bwd_all" : flag == 3 ? "k_chain_fwd" : flag == 4 ? "k_chain_bwd" : "k_tc_bwd_ws");
   }
   return MFAS_OK;
 }
@@ -464,6 +484,13 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
   const dim3 gb(g->items_bwd, (g->Hmax + TC_BWD_HT - 1) / TC_BWD_HT, g->n_cand);
   bool keep = false;                                  // the grad arena is a test facility: all candidates or none
   for (int c = 0; c < g->n_cand; ++c) keep = keep || g->hc[c].grad != nullptr;
+  if (g->bwd_ws) {
+    const int grid = g->n_bwd_tiles < g->n_sms ? g->n_bwd_tiles : g->n_sms;
+    if (keep) k_tc_bwd_ws<true><<<grid, TC_WS_THREADS, 1024 + 2 * 98304, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, g->bwd_tiles, g->n_bwd_tiles, terr);
+    else k_tc_bwd_ws<false><<<grid, TC_WS_THREADS, 1024 + 2 * 98304, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, g->bwd_tiles, g->n_bwd_tiles, terr);
+    LAUNCH_CHECK(g);
+    return MFAS_OK;
+  }
 #define BW(BPV, KG) k_tc_bwd_all<BPV, KG><<<gb, TC_BWD_THREADS, g->smem_tc_bwd, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, terr, g->dbg)
   if (g->npad == 64) { if (keep) BW(64, true); else BW(64, false); }
   else { if (keep) BW(128, true); else BW(128, false); }

@@ -71,10 +71,16 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// bounded wait; returns false if the phase never completed
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// bounded wait (~2 s of SM clock at most); returns false if the phase never completed
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t max_spins = 1u << 24) {
   const uint32_t a = smem_u32(bar);
+  const long long t0 = clock64();
   for (uint32_t i = 0; i < max_spins; ++i) {
+    if ((i & 1023u) == 1023u && clock64() - t0 > 4000000000LL) return false;
     uint32_t done;
     asm volatile(
         "{\n\t"

@@ -13,20 +13,30 @@ import types
 
 def install(shim_broken_imports: bool = True):
     """Call once, after the reference root is on sys.path and before `import models.searchable`."""
+    import importlib
     from . import ntu_searchable, scheduler, train_ntu
     if shim_broken_imports:
         # the reference as shipped does not import (SURVEY.md D7): matplotlib is an unused import of
         # models/utils.py:61, `models.aux` / `models.train` are dangling names in loops we never call
         for n in ("matplotlib", "matplotlib.pyplot"):
             sys.modules.setdefault(n, types.ModuleType(n))
+        try:
+            ref_sched = importlib.import_module("models.auxiliary.scheduler")   # the reference's own class is fine:
+        except ImportError:                                                       # train_ntu duck-types it
+            ref_sched = scheduler
         for n in ("models.aux", "models.train"):
             pkg = types.ModuleType(n)
-            pkg.scheduler = scheduler
+            pkg.scheduler = ref_sched
             sys.modules.setdefault(n, pkg)
-            sys.modules.setdefault(n + ".scheduler", scheduler)
-    sys.modules["models.search.ntu_searchable"] = ntu_searchable
-    sys.modules["models.search.train_searchable.ntu"] = train_ntu
-    sys.modules["models.auxiliary.scheduler"] = scheduler
+            sys.modules.setdefault(n + ".scheduler", ref_sched)
+    for name, mod in (("models.search.ntu_searchable", ntu_searchable),
+                      ("models.search.train_searchable.ntu", train_ntu)):
+        sys.modules[name] = mod
+        parent, _, leaf = name.rpartition(".")
+        try:
+            setattr(importlib.import_module(parent), leaf, mod)
+        except ImportError:
+            pass
     return ntu_searchable
 
 
