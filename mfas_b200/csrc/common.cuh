@@ -124,9 +124,9 @@ __device__ __forceinline__ void adam_update_fast(float g, float& p, float& m, fl
   m = fmaf(a.one_minus_beta1, g - m, m);
   v = fmaf(a.one_minus_beta2 * g, g, v * a.beta2);
   float s, r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(s) : "f"(v));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(v));
   const float denom = fmaf(s, inv_bc2_sqrt, a.eps);
-  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(denom));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(denom));
   p = fmaf(-step_size * m, r, p);
 }
 

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(TC_THREADS, NPAD == 64 ? 3 : 2)
 k_tc_fwd_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, float* part_base,
              long long part_stride_cand, TcErr err) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = umma::align1024(smem_raw);
   const int cand = blockIdx.z;
   const DCand& cd = cands[cand];
   const int H = cd.H;
@@ -468,7 +468,7 @@ k_chain_fwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, con
             long long part_stride_cand, uint32_t drop_seed, float drop_p, uint32_t step, TcErr err) {
   constexpr int THREADS = ChainCfg<NPAD>::THREADS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = umma::align1024(smem_raw);
   const DCand& cd = cands[blockIdx.y];
   if (layer >= cd.L) return;
   const int H = cd.H;
@@ -656,7 +656,7 @@ k_chain_bwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, Ada
             float bc2_sqrt, uint32_t drop_seed, float drop_p, uint32_t step, TcErr err) {
   constexpr int THREADS = ChainCfg<NPAD>::THREADS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = umma::align1024(smem_raw);
   const DCand& cd = cands[blockIdx.y];
   if (layer >= cd.L) return;
   const int H = cd.H;
@@ -841,7 +841,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, BP == 64 ? 2 : 1)
 k_tc_bwd_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, AdamH adam, float step_size,
              float bc2_sqrt, TcErr err, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = umma::align1024(smem_raw);
   const int cand = blockIdx.z;
   const DCand& cd = cands[cand];
   const int H = cd.H;
@@ -979,33 +979,53 @@ k_tc_bwd_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int 
 // tiles (the same 128 weight columns x 64 rows tile as k_tc_bwd_all) with three decoupled roles, so
 // the x/dz operand traffic, the tensor-core work and the Adam p/m/v stream of different tiles overlap
 // all the time instead of taking turns inside a CTA:
-//   warps 0-7   stagers : gather x rows + dz slice -> hi/lo split -> smem stage s      (full[s]  -> MMA)
-//   warp  8     MMA     : 3 x tcgen05.mma per 8 batch rows into TMEM buffer t          (empty[s] -> stagers,
-//                                                                                       tfull[t] -> Adam)
-//   warps 9-16  Adam    : p/m/v prefetched two row-batches ahead (across tile boundaries), gradient read
-//                         straight out of TMEM, update, store                          (tempty[t] -> MMA)
-// smem: 2 stages x 96 KB; TMEM: 2 x 64 columns.  Tile list: int4 {candidate, layer, first column, first row}.
+//   warps 0-7   stagers : gather x rows + dz slice -> hi/lo split -> smem operand stage   (full  -> MMA)
+//   warp  8     MMA     : 3 x tcgen05.mma per 8 batch rows into TMEM buffer t             (empty -> stagers,
+//                                                                                          tfull[t] -> Adam)
+//   warps 9-16  Adam    : p/m/v arrive through a per-warp cp.async ring in shared memory (WS_RING batches of
+//                         8 rows x 3 arrays x 128 B, requested one whole tile ahead, so the bytes in flight
+//                         are bounded by shared memory instead of registers); gradient straight out of
+//                         TMEM, update, coalesced 128-byte stores                         (tempty[t] -> MMA)
+// (r01 ncu of the register-prefetch version: 3.8 TB/s, long-scoreboard bound with 25 KB of p/m/v in flight
+//  per SM; the ring keeps 72-96 KB in flight.)
+// smem: 1 operand stage of 96 KB + 8 rings x WS_RING x 3 KB; TMEM: 2 x 64 columns.
+// Tile list: int4 {candidate, layer, first column, first row}.
 // ---------------------------------------------------------------------------------------------
+// Self-contained tile record (built on the host whenever arenas are (re)bound): the Adam warps need no
+// dependent descriptor loads, one 64-byte record fetched two tiles ahead is all they read.
+struct __align__(16) BwdTile {
+  float* W;                       // &params[oW + h0 * K + kc0]
+  long long moff, voff, goff;     // adam_m - params, adam_v - params, grad - params (floats; goff 0 when no grad arena)
+  int K, kw, pad0, pad1;
+  int cand, layer, kc0, h0;       // 16-byte aligned: the stagers read these four as one int4
+};
 constexpr int TC_WS_THREADS = 17 * 32;
+constexpr int WS_RING = 4;                              // ring slots per Adam warp (= batches per tile)
+constexpr int WS_SLOT = 3 * 8 * 128;                    // bytes: 3 arrays x 8 rows x 32 floats
+constexpr size_t TC_WS_SMEM = 1024 + 98304 + 8 * (size_t)WS_RING * WS_SLOT;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <bool KEEP_GRAD>
 __global__ void __launch_bounds__(TC_WS_THREADS, 1)
 k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, AdamH adam, float step_size,
-            float bc2_sqrt, const int4* __restrict__ tiles, int n_tiles, TcErr err) {
+            float bc2_sqrt, const BwdTile* __restrict__ tiles, int n_tiles, TcErr err) {
   constexpr int BP = 64;
   constexpr uint32_t BLK = BP * 128, A_TILE = 4 * BLK, B_TILE = 2 * BLK, STAGE = 2 * A_TILE + 2 * B_TILE;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full[2], empty[2], tfull[2], tempty[2];
+  uint8_t* smem = umma::align1024(smem_raw);
+  __shared__ uint64_t full, empty, tfull[2], tempty[2];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nrows = batch.n_rows;
   if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
   if (tid == 32) {
-    for (int i = 0; i < 2; ++i) {
-      umma::mbar_init(&full[i], 8); umma::mbar_init(&empty[i], 1);
-      umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 8);
-    }
+    umma::mbar_init(&full, 8); umma::mbar_init(&empty, 1);
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 8); }
     umma::fence_mbar_init();
   }
   umma::tc_fence_before();
@@ -1017,65 +1037,76 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
 
   if (warp < 8) {
     // ================================ stagers =====================================================
+    // Two-deep software pipeline so that no wait sits on a chain of dependent loads: the tile descriptor
+    // and the 8 gather indices of tile i+2 are fetched while the x / dz loads of tile i+1 are in flight
+    // (r01 ncu: with index -> x load pairs issued one after the other the stagers, not HBM, set the pace).
+    struct Desc { const float* src; const float* dz; long long ld; int H, kw; int row[8]; };
     float4 xv[8], dv[4];
-    auto issue_loads = [&](int i) {
-      const int4 t = tiles[blockIdx.x + i * gridDim.x];
+    auto fetch_desc = [&](int i, Desc& d) {
+      const int4 t = *reinterpret_cast<const int4*>(&tiles[blockIdx.x + i * gridDim.x].cand);   // {cand, layer, kc0, h0}
       const DCand& cd = cands[t.x];
       const DLayer& ly = cd.layer[t.y];
-      const int H = cd.H, K = ly.K, kc0 = t.z, kw = min(TC_BWD_KT, K - kc0);
+      const int H = cd.H, kc0 = t.z;
       const int fs = ly.d_ske, fr = ly.d_rgb;
-      const float* src; long long ld; int kl; bool gather = true;
-      if (kc0 < fs) { src = cache.ske[ly.ske_tap]; ld = cache.ske_ld[ly.ske_tap]; kl = kc0; }
-      else if (kc0 < fs + fr) { src = cache.rgb[ly.rgb_tap]; ld = cache.rgb_ld[ly.rgb_tap]; kl = kc0 - fs; }
-      else { src = cd.hid + (long long)(t.y - 1) * bmax * H; ld = H; kl = kc0 - fs - fr; gather = false; }
+      bool gather = true;
+      if (kc0 < fs) { d.src = cache.ske[ly.ske_tap] + kc0; d.ld = cache.ske_ld[ly.ske_tap]; }
+      else if (kc0 < fs + fr) { d.src = cache.rgb[ly.rgb_tap] + (kc0 - fs); d.ld = cache.rgb_ld[ly.rgb_tap]; }
+      else { d.src = cd.hid + (long long)(t.y - 1) * bmax * H + (kc0 - fs - fr); d.ld = H; gather = false; }
+      d.H = H; d.kw = min(TC_BWD_KT, ly.K - kc0);
+      d.dz = cd.dzs + (long long)t.y * bmax * H + t.w;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int idx = tid + 256 * j, r = idx >> 5, c4 = idx & 31;
-        xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < nrows && c4 * 4 < kw) {
-          const long long row = gather ? (long long)batch_row(batch, t.x, r) : (long long)r;
-          xv[j] = __ldg(reinterpret_cast<const float4*>(src + row * ld + kl + c4 * 4));
-        }
-      }
-      const float* dzl = cd.dzs + (long long)t.y * bmax * H + t.w;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int idx = tid + 256 * j, r = idx >> 4, c4 = idx & 15;
-        dv[j] = (r < nrows) ? *reinterpret_cast<const float4*>(dzl + (long long)r * H + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < 8; ++j) {                     // rows warp, warp+8, ...: one index per warp and j
+        const int r = min(warp + 8 * j, nrows - 1);
+        d.row[j] = gather ? batch_row(batch, t.x, r) : r;
       }
     };
-    if (n_my > 0) issue_loads(0);
+    auto issue_loads = [&](const Desc& d) {             // unconditional loads from clamped addresses, then select
+      const int c4 = tid & 31, cc = min(c4 * 4, d.kw - 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(d.src + (long long)d.row[j] * d.ld + cc));
+        xv[j] = (warp + 8 * j < nrows && c4 * 4 < d.kw) ? x : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = tid + 256 * j, r = idx >> 4, cd4 = idx & 15;
+        const float4 x = *reinterpret_cast<const float4*>(d.dz + (long long)min(r, nrows - 1) * d.H + cd4 * 4);
+        dv[j] = (r < nrows) ? x : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    Desc d1{};
+    if (n_my > 0) { fetch_desc(0, d1); issue_loads(d1); }
+    if (n_my > 1) fetch_desc(1, d1);
     for (int i = 0; i < n_my; ++i) {
-      const int sg = i & 1;
-      uint8_t* st = smem + sg * STAGE;
-      if (!umma::mbar_wait(&empty[sg], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
+      if (!umma::mbar_wait(&empty, (i & 1) ^ 1)) { ok = false; break; }   // MMAs of tile i-1 have read the stage
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int idx = tid + 256 * j, r = idx >> 5, c4 = idx & 31;
-        store_split(st, st + A_TILE, (uint32_t)(c4 >> 3) * BLK + umma::sw128_b32(r, (c4 & 7) * 16), xv[j]);
+        store_split(smem, smem + A_TILE, (uint32_t)(c4 >> 3) * BLK + umma::sw128_b32(r, (c4 & 7) * 16), xv[j]);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int idx = tid + 256 * j, r = idx >> 4, c4 = idx & 15;
-        store_split(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, (uint32_t)(c4 >> 3) * BLK + umma::sw128_b32(r, (c4 & 7) * 16), dv[j]);
+        store_split(smem + 2 * A_TILE, smem + 2 * A_TILE + B_TILE, (uint32_t)(c4 >> 3) * BLK + umma::sw128_b32(r, (c4 & 7) * 16), dv[j]);
       }
       umma::fence_async_smem();
       __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&full[sg]);
-      if (i + 1 < n_my) issue_loads(i + 1);            // in flight while the next stage is still being consumed
+      if (lane == 0) umma::mbar_arrive(&full);
+      if (i + 1 < n_my) issue_loads(d1);               // in flight while this tile's MMAs and Adam pass run
+      if (i + 2 < n_my) fetch_desc(i + 2, d1);
     }
   } else if (warp == 8) {
     // ================================ MMA issuer ==================================================
     constexpr uint32_t idesc = umma::idesc_tf32(128, TC_BWD_HT, true, true);
     const int ksteps = (nrows + 7) >> 3;
     for (int i = 0; i < n_my; ++i) {
-      const int sg = i & 1;
-      if (!umma::mbar_wait(&full[sg], (i >> 1) & 1)) { ok = false; break; }
-      if (!umma::mbar_wait(&tempty[sg], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
+      const int tb = i & 1;
+      if (!umma::mbar_wait(&full, i & 1)) { ok = false; break; }
+      if (!umma::mbar_wait(&tempty[tb], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
       umma::tc_fence_after();
       if (lane == 0) {
-        const uint32_t a_hi = umma::smem_u32(smem + sg * STAGE), a_lo = a_hi + A_TILE, b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
-        const uint32_t d = tm + sg * 64;
+        const uint32_t a_hi = umma::smem_u32(smem), a_lo = a_hi + A_TILE, b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
+        const uint32_t d = tm + tb * 64;
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint32_t adv = ks * 1024u;
           const uint64_t dah = umma::smem_desc(a_hi + adv, BLK, 512, umma::kLayoutSw128Base32);
@@ -1086,8 +1117,8 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
           umma::mma_tf32(d, dah, dbl, idesc, 1u);
           umma::mma_tf32(d, dah, dbh, idesc, 1u);
         }
-        umma::mma_commit(&empty[sg]);                  // smem stage free once these MMAs have read it
-        umma::mma_commit(&tfull[sg]);                  // accumulator ready for the Adam warps
+        umma::mma_commit(&empty);                      // operand stage free once these MMAs have read it
+        umma::mma_commit(&tfull[tb]);                  // accumulator ready for the Adam warps
       }
       __syncwarp();
     }
@@ -1095,66 +1126,88 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
     // ================================ Adam warps ==================================================
     const int aw = warp - 9;                           // 0..7
     const int q = warp & 3, cg = aw >> 2;              // TMEM lane quarter this warp may read; row half
-    const int kcol = q * 32 + lane;
     const float inv_bc2 = 1.f / bc2_sqrt;
-    struct Set { float p[8], m[8], v[8]; };
+    uint8_t* ring = smem + STAGE + (size_t)aw * WS_RING * WS_SLOT;
+    const uint32_t ring_u32 = umma::smem_u32(ring);
+    const int srow = lane >> 3, schunk = lane & 7;     // cp.async: a lane moves 16 B of row (4*u + srow)
     struct Tile { float* W; long long K, moff, voff, goff; bool valid; };
-    Set sa, sb;
-    auto open_tile = [&](int i) {
-      const int4 t = tiles[blockIdx.x + i * gridDim.x];
-      const DCand& cd = cands[t.x];
-      const DLayer& ly = cd.layer[t.y];
-      Tile o;
-      o.K = ly.K;
-      o.valid = q * 32 < min(TC_BWD_KT, ly.K - t.z);
-      o.W = cd.p + ly.oW + (long long)(t.w + cg * 32) * ly.K + t.z + kcol;
-      o.moff = (long long)(cd.m - cd.p); o.voff = (long long)(cd.v - cd.p);
-      o.goff = KEEP_GRAD ? (long long)(cd.grad - cd.p) : 0;
+    struct Raw { int4 a, b, c; };                      // first 48 bytes of a BwdTile
+    auto fetch_raw = [&](int i) {
+      const int4* r = reinterpret_cast<const int4*>(&tiles[blockIdx.x + i * gridDim.x]);
+      Raw o; o.a = __ldg(r); o.b = __ldg(r + 1); o.c = __ldg(r + 2);
       return o;
     };
-    auto prefetch = [&](Set& st, const Tile& t, int j0) {
-      if (!t.valid) return;
-      const float* w = t.W + (long long)j0 * t.K;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { st.p[j] = w[0]; st.m[j] = w[t.moff]; st.v[j] = w[t.voff]; w += t.K; }
+    auto open_tile = [&](const Raw& r) {
+      Tile o;
+      const long long Wbits = ((long long)(uint32_t)r.a.y << 32) | (uint32_t)r.a.x;
+      o.moff = ((long long)(uint32_t)r.a.w << 32) | (uint32_t)r.a.z;
+      o.voff = ((long long)(uint32_t)r.b.y << 32) | (uint32_t)r.b.x;
+      o.goff = KEEP_GRAD ? (((long long)(uint32_t)r.b.w << 32) | (uint32_t)r.b.z) : 0;
+      o.K = r.c.x;
+      o.valid = q * 32 < r.c.y;
+      o.W = reinterpret_cast<float*>(Wbits) + (long long)(cg * 32) * o.K + q * 32;   // first row / column of this warp
+      return o;
     };
-    auto update = [&](Set& st, const Tile& t, uint32_t tcol, int j0) {
-      float g[8];
-      umma::tmem_ld8(tm + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)(cg * 32 + j0), g);
+    // request batch j (rows 8j .. 8j+7 of this warp's 32) of tile t into ring slot j; always commits a group
+    auto request = [&](const Tile& t, int j) {
       if (t.valid) {
-        float* w = t.W + (long long)j0 * t.K;
+        const uint32_t dst = ring_u32 + j * WS_SLOT + srow * 128 + schunk * 16;
+        const float* w = t.W + (long long)(8 * j + srow) * t.K + schunk * 4;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (KEEP_GRAD) w[t.goff] = g[j];
-          adam_update_fast(g[j], st.p[j], st.m[j], st.v[j], adam, step_size, inv_bc2);
-          w[0] = st.p[j]; w[t.moff] = st.m[j]; w[t.voff] = st.v[j];
-          w += t.K;
+        for (int u = 0; u < 2; ++u) {
+          const float* wu = w + (long long)(4 * u) * t.K;
+          cp_async16(dst + u * 512, wu);
+          cp_async16(dst + 1024 + u * 512, wu + t.moff);
+          cp_async16(dst + 2048 + u * 512, wu + t.voff);
         }
       }
+      cp_async_commit();
     };
     Tile cur{}, nxt{};
+    Raw ahead{};                                       // record of tile i+2, in flight during iteration i
     if (n_my > 0) {
-      cur = open_tile(0);
-      prefetch(sa, cur, 0);
-      prefetch(sb, cur, 8);
+      cur = open_tile(fetch_raw(0));
+#pragma unroll
+      for (int j = 0; j < WS_RING; ++j) request(cur, j);
     }
+    if (n_my > 1) ahead = fetch_raw(1);
     for (int i = 0; i < n_my; ++i) {
-      const int sg = i & 1;
-      if (!umma::mbar_wait(&tfull[sg], (i >> 1) & 1)) { ok = false; break; }
+      const int tb = i & 1;
+      const bool more = i + 1 < n_my;
+      if (more) nxt = open_tile(ahead);
+      if (i + 2 < n_my) ahead = fetch_raw(i + 2);
+      if (!umma::mbar_wait(&tfull[tb], (i >> 1) & 1)) { ok = false; break; }
       umma::tc_fence_after();
-      const uint32_t tcol = sg * 64;
-      update(sa, cur, tcol, 0);
-      prefetch(sa, cur, 16);
-      update(sb, cur, tcol, 8);
-      prefetch(sb, cur, 24);
-      update(sa, cur, tcol, 16);
-      if (i + 1 < n_my) { nxt = open_tile(i + 1); prefetch(sa, nxt, 0); }     // the stream never drains between tiles
-      update(sb, cur, tcol, 24);
+#pragma unroll
+      for (int j = 0; j < WS_RING; ++j) {
+        cp_async_wait<WS_RING - 1>();                  // the oldest outstanding batch (this one) has landed
+        __syncwarp();
+        float g[8];
+        umma::tmem_ld8(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 64 + cg * 32 + 8 * j), g);
+        if (cur.valid) {
+          const float* sp = reinterpret_cast<const float*>(ring + j * WS_SLOT) + lane;
+          float* w = cur.W + (long long)(8 * j) * cur.K + lane;
+          float p[8], m[8], v[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) { p[r] = sp[r * 32]; m[r] = sp[256 + r * 32]; v[r] = sp[512 + r * 32]; }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) adam_update_fast(g[r], p[r], m[r], v[r], adam, step_size, inv_bc2);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            if (KEEP_GRAD) w[cur.goff] = g[r];
+            w[0] = p[r]; w[cur.moff] = m[r]; w[cur.voff] = v[r];
+            w += cur.K;
+          }
+        }
+        __syncwarp();                                  // every lane has read slot j before it is refilled
+        if (more) request(nxt, j); else cp_async_commit();
+      }
       umma::tc_fence_before();
       __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&tempty[sg]);   // this warp has drained its part of the accumulator
-      if (i + 1 < n_my) { prefetch(sb, nxt, 8); cur = nxt; }
+      if (lane == 0) umma::mbar_arrive(&tempty[tb]);   // this warp has drained its part of the accumulator
+      cur = nxt;
     }
+    cp_async_wait<0>();
   }
   if (!ok) atomicExch(err.flag, 5);
   umma::tc_fence_before();

@@ -139,7 +139,8 @@ struct mfas_group {
   long long part_stride = 0;
   int* tc_err = nullptr;          // device flag set by a timed-out barrier wait
   size_t smem_tc_fwd = 0, smem_tc_bwd = 0, smem_fl = 0, smem_dzx = 0, smem_chain = 0;
-  int4* bwd_tiles = nullptr;      // tile list of the persistent backward kernel {cand, layer, first column, first row}
+  BwdTile* bwd_tiles = nullptr;   // tile list of the persistent backward kernel (device), rebuilt when arenas are rebound
+  std::vector<int4> bwd_tl;       // host: {cand, layer, first column, first row}
   int n_bwd_tiles = 0, n_sms = 148, bwd_ws = 1;
   int dbg = 0;                    // MFAS_TC_DEBUG bit 0: skip the Adam epilogue, bit 1: skip operand staging (timing experiments only)
   int chain = 1;                  // 1: tensor-core chain kernels, 0: CUDA-core chain kernels (MFAS_CHAIN=ffma)
@@ -336,7 +337,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     attr((const void*)k_chain_bwd<128>, ChainCfg<128>::SMEM);
     { const char* ce = getenv("MFAS_CHAIN"); if (ce && !strcmp(ce, "ffma")) g->chain = 0; }
     { const char* be = getenv("MFAS_BWD"); if (be && !strcmp(be, "cta")) g->bwd_ws = 0; }
-    if (g->npad != 64) g->bwd_ws = 0;                   // the persistent kernel double-buffers 96 KB stages: batch <= 64
+    if (g->npad != 64) g->bwd_ws = 0;                   // the persistent kernel is sized for batch <= 64 (96 KB operand stage + p/m/v rings)
     if (g->bwd_ws) {
       std::vector<int4> tl;
       for (int c = 0; c < n_cand; ++c)
@@ -347,10 +348,10 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       cudaDeviceProp prop;
       if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
       if (e == cudaSuccess) g->n_sms = prop.multiProcessorCount;
-      if (e == cudaSuccess) e = cudaMalloc(&g->bwd_tiles, sizeof(int4) * tl.size());
-      if (e == cudaSuccess) e = cudaMemcpy(g->bwd_tiles, tl.data(), sizeof(int4) * tl.size(), cudaMemcpyHostToDevice);
-      attr((const void*)k_tc_bwd_ws<false>, 1024 + 2 * 98304);
-      attr((const void*)k_tc_bwd_ws<true>, 1024 + 2 * 98304);
+      if (e == cudaSuccess) e = cudaMalloc(&g->bwd_tiles, sizeof(BwdTile) * tl.size());
+      g->bwd_tl = std::move(tl);
+      attr((const void*)k_tc_bwd_ws<false>, TC_WS_SMEM);
+      attr((const void*)k_tc_bwd_ws<true>, TC_WS_SMEM);
     }
     { const char* de = getenv("MFAS_TC_DEBUG"); if (de) g->dbg = atoi(de); }
     if (e != cudaSuccess) {
@@ -410,6 +411,22 @@ static int sync_descriptors(mfas_group* g, cudaStream_t st) {
   if (g->dirty) {
     // pageable source: the copy is staged before the call returns, so hc may change afterwards
     CUDA_TRY(cudaMemcpyAsync(g->dc, g->hc.data(), sizeof(DCand) * g->n_cand, cudaMemcpyHostToDevice, st));
+    if (g->bwd_tiles) {
+      std::vector<BwdTile> recs(g->bwd_tl.size());
+      for (size_t i = 0; i < recs.size(); ++i) {
+        const int4 t = g->bwd_tl[i];
+        const DCand& d = g->hc[t.x];
+        const DLayer& ly = d.layer[t.y];
+        BwdTile& r = recs[i];
+        r.W = d.p + ly.oW + (long long)t.w * ly.K + t.z;
+        r.moff = (long long)(d.m - d.p); r.voff = (long long)(d.v - d.p);
+        r.goff = d.grad ? (long long)(d.grad - d.p) : 0;
+        r.K = ly.K; r.kw = ly.K - t.z < TC_BWD_KT ? ly.K - t.z : TC_BWD_KT;
+        r.cand = t.x; r.layer = t.y; r.kc0 = t.z; r.h0 = t.w; r.pad0 = r.pad1 = 0;
+      }
+      // pageable source: staged before the call returns
+      CUDA_TRY(cudaMemcpyAsync(g->bwd_tiles, recs.data(), sizeof(BwdTile) * recs.size(), cudaMemcpyHostToDevice, st));
+    }
     g->dirty = false;
   }
   return MFAS_OK;
@@ -486,8 +503,8 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
   for (int c = 0; c < g->n_cand; ++c) keep = keep || g->hc[c].grad != nullptr;
   if (g->bwd_ws) {
     const int grid = g->n_bwd_tiles < g->n_sms ? g->n_bwd_tiles : g->n_sms;
-    if (keep) k_tc_bwd_ws<true><<<grid, TC_WS_THREADS, 1024 + 2 * 98304, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, g->bwd_tiles, g->n_bwd_tiles, terr);
-    else k_tc_bwd_ws<false><<<grid, TC_WS_THREADS, 1024 + 2 * 98304, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, g->bwd_tiles, g->n_bwd_tiles, terr);
+    if (keep) k_tc_bwd_ws<true><<<grid, TC_WS_THREADS, TC_WS_SMEM, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, g->bwd_tiles, g->n_bwd_tiles, terr);
+    else k_tc_bwd_ws<false><<<grid, TC_WS_THREADS, TC_WS_SMEM, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, g->bwd_tiles, g->n_bwd_tiles, terr);
     LAUNCH_CHECK(g);
     return MFAS_OK;
   }

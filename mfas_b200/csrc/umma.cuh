@@ -14,6 +14,10 @@ namespace umma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// first 1024-byte aligned address at or after p; written as pointer + offset (not integer arithmetic on the
+// pointer) so the compiler keeps the shared address space and emits LDS/STS instead of generic LD/ST
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) { return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u); }
+
 // byte offset of (row, byte_in_row) inside a SWIZZLE_128B tile whose base is 1024-byte aligned
 __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t byte_in_row) {
   return row * 128u + ((((byte_in_row >> 4) ^ (row & 7u)) << 4) | (byte_in_row & 15u));
