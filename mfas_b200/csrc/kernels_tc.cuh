@@ -25,7 +25,7 @@
 namespace mfas {
 
 constexpr int TC_THREADS = 256;
-constexpr int TC_KB_PER_ITEM = 16;    // forward: k-blocks (32 columns each) per work item = 512 columns of K
+constexpr int TC_KB_PER_ITEM = 32;    // forward: at most this many k-blocks (32 columns each) per work item
 constexpr int TC_BWD_KT = 128;        // backward: weight columns (TMEM lanes) per work item
 constexpr int TC_BWD_HT = 64;         // backward: output rows h (TMEM columns) per work item
 
@@ -33,6 +33,12 @@ struct TcErr { int* flag; };          // set when a bounded barrier wait expires
 
 __host__ __device__ __forceinline__ int tc_fwd_items(int d_ske, int d_rgb) {
   return (((d_ske + d_rgb) >> 5) + TC_KB_PER_ITEM - 1) / TC_KB_PER_ITEM;
+}
+// k-block range of split `split` of a layer with nkb feature k-blocks (even split over tc_fwd_items pieces)
+__host__ __device__ __forceinline__ void tc_fwd_range(int nkb, int split, int& kb0, int& kb1) {
+  const int n = (nkb + TC_KB_PER_ITEM - 1) / TC_KB_PER_ITEM, per = (nkb + n - 1) / n;
+  kb0 = split * per;
+  kb1 = kb0 + per < nkb ? kb0 + per : nkb;
 }
 __host__ __device__ __forceinline__ int tc_bwd_items(int K) { return (K + TC_BWD_KT - 1) / TC_BWD_KT; }
 
@@ -74,7 +80,8 @@ k_tc_fwd_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, floa
   const DLayer& ly = cd.layer[layer];
   const int K = ly.K, fs = ly.d_ske, fr = ly.d_rgb;
   const int nkb = (fs + fr) >> 5;
-  const int kb0 = split * TC_KB_PER_ITEM, kb1 = min(nkb, kb0 + TC_KB_PER_ITEM);
+  int kb0, kb1;
+  tc_fwd_range(nkb, split, kb0, kb1);
   const int nrows = batch.n_rows, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   uint8_t* a_hi = smem;
@@ -188,6 +195,200 @@ k_tc_fwd_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, floa
   umma::tc_fence_before();
   __syncthreads();
   if (warp == 0) umma::tmem_free(tm, NPAD);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward, all layers, persistent + warp-specialised.  Same work items and partial-sum layout as
+// k_tc_fwd_all, but one CTA per SM walks a static list of items, the bytes in flight are bounded by
+// shared memory instead of registers, and no role ever waits for another inside a k-block:
+//   warps 0-3   loaders    : cp.async (16 B per lane, swizzle applied to the destination) of the raw fp32 W
+//                            and gathered x tiles straight into canonical SW128 K-major tiles, a ring of
+//                            RAW stages.  The raw tiles ARE the "hi" operands: kind::tf32 reads the top 19
+//                            bits of each 32-bit container, i.e. hi = trunc_tf32(x) for free.
+//                            (rawfree[s] <- MMA; landed[s] -> converters, signalled by cp.async itself)
+//   warps 4-11  converters : lo = rna_tf32(x - trunc_tf32(x)) (the subtraction is exact in fp32) into a
+//                            shorter ring of LO stages                     (lofree[s] <- MMA; lofull[s] -> MMA)
+//   warp  12    MMA        : per k-block 4 x {A_hi*B_hi -> main accumulator; A_lo*B_hi, A_hi*B_lo -> a second,
+//                            correction accumulator}.  The tensor core truncates when it adds into the fp32
+//                            accumulator, so the long chain of adds is the dominant error (measured 5e-6..1e-5
+//                            of max|logit| against 1e-6 for the fp32 reference); keeping the small cross terms
+//                            out of the main chain cuts its length by three            (tfull[t] -> epilogue)
+//   warps 13-16 epilogue   : main + correction -> partial sums in global memory                      (tempty[t] -> MMA)
+// The stream of k-blocks runs across item boundaries, so the pipeline never drains inside a launch.
+// (r01 ncu of k_tc_fwd_all: 3.4 TB/s, stalled on the CTA barrier + MMA round trip of every 24 KB k-block.)
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) FwdItem {
+  const float* W;                 // &params[oW + m0 * K]
+  long long part_off;             // float offset of this item's [128][NPAD] tile in the partial-sum buffer
+  int K, kb0, kb1, fs_kb;         // row stride of W; k-block range [kb0, kb1); first k-block of the rgb tap
+  int ske_tap, rgb_tap, cand, rows_valid;   // rows_valid = min(128, H - m0)
+};
+
+template <int NPAD> struct FwdWs {
+  static constexpr int RAW = NPAD == 64 ? 5 : 4, LO = NPAD == 64 ? 3 : 2;
+  static constexpr uint32_t A_BYTES = 16384, B_BYTES = NPAD * 128, TILE = A_BYTES + B_BYTES;
+  static constexpr size_t SMEM = 1024 + (size_t)(RAW + LO) * TILE;
+  static constexpr int LOADERS = 128, CONVERTERS = 256, THREADS = 17 * 32;
+};
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;    // src-size 0: the 16 destination bytes are zero-filled, src is not read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all of its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+
+template <int NPAD>
+__global__ void __launch_bounds__(FwdWs<NPAD>::THREADS, 1)
+k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchRef batch, float* part_base, TcErr err) {
+  using Cfg = FwdWs<NPAD>;
+  constexpr int R = Cfg::RAW, LQ = Cfg::LO;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = umma::align1024(smem_raw);
+  uint8_t* lo_base = smem + R * Cfg::TILE;
+  __shared__ uint64_t landed[R], rawfree[R], lofull[LQ], lofree[LQ], tfull[2], tempty[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nrows = batch.n_rows;
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 4 * NPAD);
+  if (tid == 32) {
+    for (int i = 0; i < R; ++i) { umma::mbar_init(&landed[i], Cfg::LOADERS); umma::mbar_init(&rawfree[i], 1); }
+    for (int i = 0; i < LQ; ++i) { umma::mbar_init(&lofull[i], Cfg::CONVERTERS / 32); umma::mbar_init(&lofree[i], 1); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 4); }
+    umma::fence_mbar_init();
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tm = tmem_slot;
+  const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  bool ok = true;
+
+  if (warp < 4) {
+    // ================================ loaders =====================================================
+    constexpr int WJ = 8, XJ = NPAD / 16;                          // rows r + 16 j of the W / x tile
+    const int r = tid >> 3, c = tid & 7;                           // 16-byte chunk c of the 128-byte row
+    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);   // sw128(r + 16 j, 16 c) = off + 2048 j
+    const uint32_t s0 = umma::smem_u32(smem);
+    int n = 0;
+    for (int i = 0; i < n_my && ok; ++i) {
+      const FwdItem it = items[blockIdx.x + i * gridDim.x];
+      const long long wstride = 16LL * it.K;
+      const float* wp = it.W + (long long)r * it.K + c * 4;        // &W[m0 + r][4 c]
+      const float* xs[XJ]; const float* xr[XJ];                    // gathered rows of the two taps, indexed by concat column
+#pragma unroll
+      for (int j = 0; j < XJ; ++j) {
+        const int row = r + 16 * j;
+        const long long gr = batch_row(batch, it.cand, row < nrows ? row : 0);
+        xs[j] = cache.ske[it.ske_tap] + gr * cache.ske_ld[it.ske_tap] + c * 4;
+        xr[j] = cache.rgb[it.rgb_tap] + gr * cache.rgb_ld[it.rgb_tap] + c * 4 - 32LL * it.fs_kb;
+      }
+#pragma unroll 1
+      for (int kb = it.kb0; kb < it.kb1; ++kb, ++n) {
+        const int sg = n % R;
+        if (n >= R && !umma::mbar_wait(&rawfree[sg], ((n / R) & 1) ^ 1)) { ok = false; break; }
+        const uint32_t a = s0 + sg * Cfg::TILE + off, b = a + Cfg::A_BYTES;
+        const float* w = wp + 32LL * kb;
+#pragma unroll
+        for (int j = 0; j < WJ; ++j) cp_async16_zfill(a + j * 2048, w + j * wstride, r + 16 * j < it.rows_valid);
+        const bool ske = kb < it.fs_kb;
+#pragma unroll
+        for (int j = 0; j < XJ; ++j) cp_async16_zfill(b + j * 2048, (ske ? xs[j] : xr[j]) + 32LL * kb, r + 16 * j < nrows);
+        cp_async_arrive_noinc(&landed[sg]);
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp < 12) {
+    // ================================ converters ==================================================
+    const int ct = tid - 128;
+    constexpr int CJ = (int)(Cfg::TILE / 16) / Cfg::CONVERTERS;    // 16-byte chunks per thread (elementwise: linear order)
+    int total = 0;
+    for (int i = 0; i < n_my; ++i) { const FwdItem& it = items[blockIdx.x + i * gridDim.x]; total += it.kb1 - it.kb0; }
+#pragma unroll 1
+    for (int n = 0; n < total; ++n) {
+      const int sg = n % R, sl = n % LQ;
+      if (!umma::mbar_wait(&landed[sg], (n / R) & 1)) { ok = false; break; }
+      if (n >= LQ && !umma::mbar_wait(&lofree[sl], ((n / LQ) & 1) ^ 1)) { ok = false; break; }
+      const float4* src = reinterpret_cast<const float4*>(smem + sg * Cfg::TILE) + ct;
+      float4* dst = reinterpret_cast<float4*>(lo_base + sl * Cfg::TILE) + ct;
+      float4 x[CJ];
+#pragma unroll
+      for (int j = 0; j < CJ; ++j) x[j] = src[j * Cfg::CONVERTERS];
+#pragma unroll
+      for (int j = 0; j < CJ; ++j) {
+        float4 l;
+        l.x = umma::round_tf32(x[j].x - __uint_as_float(__float_as_uint(x[j].x) & 0xFFFFE000u));
+        l.y = umma::round_tf32(x[j].y - __uint_as_float(__float_as_uint(x[j].y) & 0xFFFFE000u));
+        l.z = umma::round_tf32(x[j].z - __uint_as_float(__float_as_uint(x[j].z) & 0xFFFFE000u));
+        l.w = umma::round_tf32(x[j].w - __uint_as_float(__float_as_uint(x[j].w) & 0xFFFFE000u));
+        dst[j * Cfg::CONVERTERS] = l;
+      }
+      umma::fence_async_smem();                                    // lo (generic proxy) and the landed raw tile -> tensor core
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&lofull[sl]);
+    }
+  } else if (warp == 12) {
+    // ================================ MMA issuer ==================================================
+    constexpr uint32_t idesc = umma::idesc_tf32(128, NPAD, false, false);
+    int n = 0;
+    for (int i = 0; i < n_my && ok; ++i) {
+      const FwdItem& it = items[blockIdx.x + i * gridDim.x];
+      const int nkb = it.kb1 - it.kb0, tb = i & 1;
+      if (!umma::mbar_wait(&tempty[tb], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
+      for (int k = 0; k < nkb; ++k, ++n) {
+        const int sg = n % R, sl = n % LQ;
+        if (!umma::mbar_wait(&lofull[sl], (n / LQ) & 1)) { ok = false; break; }
+        umma::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = umma::smem_u32(smem) + sg * Cfg::TILE, b_hi = a_hi + Cfg::A_BYTES;
+          const uint32_t a_lo = umma::smem_u32(lo_base) + sl * Cfg::TILE, b_lo = a_lo + Cfg::A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t adv = ks * 32u;
+            const uint64_t dah = umma::smem_desc(a_hi + adv, 16, 1024), dal = umma::smem_desc(a_lo + adv, 16, 1024);
+            const uint64_t dbh = umma::smem_desc(b_hi + adv, 16, 1024), dbl = umma::smem_desc(b_lo + adv, 16, 1024);
+            const uint32_t acc = (k > 0 || ks > 0) ? 1u : 0u;
+            umma::mma_tf32(tm + tb * 2 * NPAD, dah, dbh, idesc, acc);             // main accumulator: hi*hi only
+            umma::mma_tf32(tm + tb * 2 * NPAD + NPAD, dal, dbh, idesc, acc);      // correction accumulator
+            umma::mma_tf32(tm + tb * 2 * NPAD + NPAD, dah, dbl, idesc, 1u);
+          }
+          umma::mma_commit(&rawfree[sg]);
+          umma::mma_commit(&lofree[sl]);
+          if (k == nkb - 1) umma::mma_commit(&tfull[tb]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================ epilogue ====================================================
+    const int q = warp & 3;                                        // TMEM lane quarter this warp may read
+    for (int i = 0; i < n_my; ++i) {
+      const FwdItem& it = items[blockIdx.x + i * gridDim.x];
+      const int tb = i & 1;
+      float* dst = part_base + it.part_off + (long long)(q * 32 + lane) * NPAD;
+      if (!umma::mbar_wait(&tfull[tb], (i >> 1) & 1)) { ok = false; break; }
+      umma::tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < NPAD / 32; ++cc) {
+        float v[32], w[32];
+        umma::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 2 * NPAD + cc * 32), v);
+        umma::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 2 * NPAD + NPAD + cc * 32), w);
+        float4* d4 = reinterpret_cast<float4*>(dst + cc * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          d4[j] = make_float4(v[4 * j] + w[4 * j], v[4 * j + 1] + w[4 * j + 1], v[4 * j + 2] + w[4 * j + 2], v[4 * j + 3] + w[4 * j + 3]);
+      }
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&tempty[tb]);
+    }
+  }
+  if (!ok) atomicExch(err.flag, 6);
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_free(tm, 4 * NPAD);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,6 +1,7 @@
 // C ABI of the B200-native MFAS candidate-training hot path (see include/mfas_b200.h).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -142,6 +143,8 @@ struct mfas_group {
   BwdTile* bwd_tiles = nullptr;   // tile list of the persistent backward kernel (device), rebuilt when arenas are rebound
   std::vector<int4> bwd_tl;       // host: {cand, layer, first column, first row}
   int n_bwd_tiles = 0, n_sms = 148, bwd_ws = 1;
+  FwdItem* fwd_items = nullptr;   // item list of the persistent forward kernel (device), rebuilt when arenas are rebound
+  int n_fwd_items = 0, fwd_ws = 1;
   int dbg = 0;                    // MFAS_TC_DEBUG bit 0: skip the Adam epilogue, bit 1: skip operand staging (timing experiments only)
   int chain = 1;                  // 1: tensor-core chain kernels, 0: CUDA-core chain kernels (MFAS_CHAIN=ffma)
 };
@@ -167,6 +170,7 @@ extern "C" int mfas_group_destroy(mfas_group_t g) {
   if (g->improved) cudaFree(g->improved);
   if (g->part) cudaFree(g->part);
   if (g->bwd_tiles) cudaFree(g->bwd_tiles);
+  if (g->fwd_items) cudaFree(g->fwd_items);
   if (g->tc_err) cudaFree(g->tc_err);
   delete g;
   return MFAS_OK;
@@ -335,6 +339,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     attr((const void*)k_chain_fwd<false, 128>, ChainCfg<128>::SMEM);
     attr((const void*)k_chain_bwd<64>, ChainCfg<64>::SMEM);
     attr((const void*)k_chain_bwd<128>, ChainCfg<128>::SMEM);
+    { int nsm = 0; if (e == cudaSuccess) e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device); if (nsm > 0) g->n_sms = nsm; }
     { const char* ce = getenv("MFAS_CHAIN"); if (ce && !strcmp(ce, "ffma")) g->chain = 0; }
     { const char* be = getenv("MFAS_BWD"); if (be && !strcmp(be, "cta")) g->bwd_ws = 0; }
     if (g->npad != 64) g->bwd_ws = 0;                   // the persistent kernel is sized for batch <= 64 (96 KB operand stage + p/m/v rings)
@@ -345,13 +350,21 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
           for (int kc0 = 0; kc0 < g->lay[c].K[l]; kc0 += TC_BWD_KT)
             for (int h0 = 0; h0 < g->lay[c].H; h0 += TC_BWD_HT) tl.push_back(make_int4(c, l, kc0, h0));
       g->n_bwd_tiles = (int)tl.size();
-      cudaDeviceProp prop;
-      if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
-      if (e == cudaSuccess) g->n_sms = prop.multiProcessorCount;
       if (e == cudaSuccess) e = cudaMalloc(&g->bwd_tiles, sizeof(BwdTile) * tl.size());
       g->bwd_tl = std::move(tl);
       attr((const void*)k_tc_bwd_ws<false>, TC_WS_SMEM);
       attr((const void*)k_tc_bwd_ws<true>, TC_WS_SMEM);
+    }
+    { const char* fe = getenv("MFAS_FWD"); if (fe && !strcmp(fe, "cta")) g->fwd_ws = 0; }
+    if (g->fwd_ws) {
+      int n = 0;
+      for (int c = 0; c < n_cand; ++c)
+        for (int l = 0; l < g->lay[c].L; ++l)
+          n += tc_fwd_items(g->lay[c].d_ske[l], g->lay[c].d_rgb[l]) * ((g->lay[c].H + 127) / 128);
+      g->n_fwd_items = n;
+      if (e == cudaSuccess) e = cudaMalloc(&g->fwd_items, sizeof(FwdItem) * n);
+      attr((const void*)k_tc_fwd_ws<64>, FwdWs<64>::SMEM);
+      attr((const void*)k_tc_fwd_ws<128>, FwdWs<128>::SMEM);
     }
     { const char* de = getenv("MFAS_TC_DEBUG"); if (de) g->dbg = atoi(de); }
     if (e != cudaSuccess) {
@@ -378,7 +391,7 @@ extern "C" int mfas_group_status(mfas_group_t g) {
   if (g->tc_err) {
     int flag = 0;
     CUDA_TRY(cudaMemcpy(&flag, g->tc_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flag) return fail(MFAS_ERR_CUDA, "tensor-core pipeline barrier timed out in kernel %s", flag == 1 ? "k_tc_fwd_all" : flag == 2 ? "k_tc_bwd_all" : flag == 3 ? "k_chain_fwd" : flag == 4 ? "k_chain_bwd" : "k_tc_bwd_ws");
+    if (flag) return fail(MFAS_ERR_CUDA, "tensor-core pipeline barrier timed out in kernel %s", flag == 1 ? "k_tc_fwd_all" : flag == 2 ? "k_tc_bwd_all" : flag == 3 ? "k_chain_fwd" : flag == 4 ? "k_chain_bwd" : flag == 5 ? "k_tc_bwd_ws" : "k_tc_fwd_ws");
   }
   return MFAS_OK;
 }
@@ -427,6 +440,35 @@ static int sync_descriptors(mfas_group* g, cudaStream_t st) {
       // pageable source: staged before the call returns
       CUDA_TRY(cudaMemcpyAsync(g->bwd_tiles, recs.data(), sizeof(BwdTile) * recs.size(), cudaMemcpyHostToDevice, st));
     }
+    if (g->fwd_items) {
+      // one item per (candidate, layer, 128-row tile, k-range); biggest first, so that the static round-robin
+      // over the persistent CTAs ends level
+      std::vector<FwdItem> its;
+      const int Hp = ((g->Hmax + 127) / 128) * 128;
+      for (int c = 0; c < g->n_cand; ++c) {
+        const DCand& d = g->hc[c];
+        int item0 = 0;
+        for (int l = 0; l < d.L; ++l) {
+          const DLayer& ly = d.layer[l];
+          const int nkb = (ly.d_ske + ly.d_rgb) >> 5, ns = tc_fwd_items(ly.d_ske, ly.d_rgb);
+          for (int sp = 0; sp < ns; ++sp)
+            for (int m0 = 0; m0 < d.H; m0 += 128) {
+              FwdItem it;
+              tc_fwd_range(nkb, sp, it.kb0, it.kb1);
+              it.W = d.p + ly.oW + (long long)m0 * ly.K;
+              it.part_off = (long long)c * g->part_stride + ((long long)(item0 + sp) * Hp + m0) * g->npad;
+              it.K = ly.K; it.fs_kb = ly.d_ske >> 5;
+              it.ske_tap = ly.ske_tap; it.rgb_tap = ly.rgb_tap; it.cand = c;
+              it.rows_valid = d.H - m0 < 128 ? d.H - m0 : 128;
+              its.push_back(it);
+            }
+          item0 += ns;
+        }
+      }
+      std::stable_sort(its.begin(), its.end(), [](const FwdItem& a, const FwdItem& b) { return a.kb1 - a.kb0 > b.kb1 - b.kb0; });
+      if ((int)its.size() != g->n_fwd_items) return fail(MFAS_ERR_INVALID, "internal: forward item count changed");
+      CUDA_TRY(cudaMemcpyAsync(g->fwd_items, its.data(), sizeof(FwdItem) * its.size(), cudaMemcpyHostToDevice, st));
+    }
     g->dirty = false;
   }
   return MFAS_OK;
@@ -464,7 +506,11 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
                           float step_size, float bc2_sqrt, uint32_t step, const HeadOut& ho, cudaStream_t st) {
   const TcErr terr{g->tc_err};
   const dim3 gf(g->items_fwd, (g->Hmax + 127) / 128, g->n_cand), gl((g->Hmax + TC_CB - 1) / TC_CB, g->n_cand);
-  if (g->npad == 64) k_tc_fwd_all<64><<<gf, TC_THREADS, g->smem_tc_fwd, st>>>(g->dc, cache, batch, g->part, g->part_stride, terr);
+  if (g->fwd_ws) {
+    const int grid = g->n_fwd_items < g->n_sms ? g->n_fwd_items : g->n_sms;
+    if (g->npad == 64) k_tc_fwd_ws<64><<<grid, FwdWs<64>::THREADS, FwdWs<64>::SMEM, st>>>(g->fwd_items, g->n_fwd_items, cache, batch, g->part, terr);
+    else k_tc_fwd_ws<128><<<grid, FwdWs<128>::THREADS, FwdWs<128>::SMEM, st>>>(g->fwd_items, g->n_fwd_items, cache, batch, g->part, terr);
+  } else if (g->npad == 64) k_tc_fwd_all<64><<<gf, TC_THREADS, g->smem_tc_fwd, st>>>(g->dc, cache, batch, g->part, g->part_stride, terr);
   else k_tc_fwd_all<128><<<gf, TC_THREADS, g->smem_tc_fwd, st>>>(g->dc, cache, batch, g->part, g->part_stride, terr);
   LAUNCH_CHECK(g);
   const dim3 gc((g->Hmax + 127) / 128, g->n_cand);
