@@ -180,6 +180,15 @@ int mfas_train_run(mfas_group_t g, const mfas_cache_desc* train, const mfas_cach
 int mfas_eval_pass(mfas_group_t g, const mfas_cache_desc* cache, const int32_t* d_perm, int32_t batch,
                    double* d_out, void* stream);
 
+/* Host-side helper (no GPU): fills n_ops float arrays with U(from, to) draws taken from torch's global CPU generator
+ * stream, bit-identical to torch.nn.init.uniform_/kaiming_uniform_ applied in the same order -- what the reference
+ * constructor does for every candidate (models/search/ntu_searchable.py:200, :274-282 via nn.Linear.reset_parameters).
+ * torch_rng_state is the byte buffer of torch.get_rng_state() (legacy 5056-byte mt19937 layout), advanced in place.
+ * use_fma selects x*(to-from)+from as one fused multiply-add (what an FMA-contracting ATen build computes) or as two
+ * roundings.  Returns MFAS_ERR_UNSUPPORTED if the buffer does not look like a seeded mt19937 state. */
+int mfas_host_uniform_fill(uint8_t* torch_rng_state, int64_t state_bytes, int32_t n_ops, float* const* dst,
+                           const int64_t* count, const float* from, const float* to, int32_t use_fma);
+
 #ifdef __cplusplus
 }
 #endif

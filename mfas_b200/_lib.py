@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "_mfas_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", "mfas_abi.cu")]
+SOURCES = [os.path.join(HERE, "csrc", "mfas_abi.cu"), os.path.join(HERE, "csrc", "host_init.cpp")]
 HEADERS = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "kernels_ffma.cuh", "kernels_tc.cuh", "umma.cuh")] + [
     os.path.join(ROOT, "include", "mfas_b200.h")]
 
@@ -88,6 +88,7 @@ SYMBOLS = {
                                   _P, _P, _P, _P]),
     "mfas_train_run": (C.c_int, [_P, C.POINTER(CacheDesc), C.POINTER(CacheDesc), C.POINTER(RunArgs), _P]),
     "mfas_eval_pass": (C.c_int, [_P, C.POINTER(CacheDesc), _P, C.c_int32, _P, _P]),
+    "mfas_host_uniform_fill": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P, C.c_int32]),
 }
 
 

@@ -268,6 +268,9 @@ def init_host_arenas(group, host_p, host_b, slots=None):
     """torch's default initialisers applied straight to pinned host arenas, consuming the global CPU
     generator exactly like ``searchable_type(args, conf)`` would for every candidate in order -- same
     seed, same weights as the reference constructor -- without creating a single nn.Module."""
+    from .host_init import init_host_arenas_fast
+    if os.environ.get("MFAS_HOST_INIT") != "torch" and init_host_arenas_fast(group, host_p, host_b, _init_tensors, slots):
+        return
     for c in (range(group.n) if slots is None else slots):
         def fill(name, kind, fan_in, c=c):
             arena, off, shape = group.slots[c][name]
@@ -287,6 +290,20 @@ def init_host_arenas(group, host_p, host_b, slots=None):
             elif kind == "normal":
                 nn.init.normal_(t, 0.0, 0.1)
         _init_tensors(group, c, fill)
+
+
+_STAGING = {}
+
+
+def _staging(n_p, n_b):
+    """Pinned host staging arenas, kept across calls (pinning 0.5 GB costs more than filling it).  Zeroed once: the
+    initialisers overwrite every parameter on every call, the alignment gaps between tensors stay zero."""
+    hp, hb = _STAGING.get("p"), _STAGING.get("b")
+    if hp is None or hp.numel() < n_p:
+        hp = _STAGING["p"] = torch.zeros(n_p, dtype=torch.float32).pin_memory()
+    if hb is None or hb.numel() < n_b:
+        hb = _STAGING["b"] = torch.zeros(n_b, dtype=torch.float32).pin_memory()
+    return hp[:n_p], hb[:n_b]
 
 
 def init_on_device(group, base_seed, cand_ids):
@@ -368,6 +385,17 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("mfas_b200.train_sampled_models needs a CUDA device (no CPU fallback)")
+    import time
+    timing = os.environ.get("MFAS_TIMING") == "1"       # phase timings of the host path on stderr (synchronising!)
+    t_last = [time.perf_counter()]
+
+    def lap(what):
+        if timing:
+            torch.cuda.synchronize(device)
+            now = time.perf_counter()
+            import sys
+            sys.stderr.write(f"[mfas timing] {what}: {(now - t_last[0]) * 1e3:.1f} ms\n")
+            t_last[0] = now
     if preaccuracies:   # the reference passes init_f1=..., which train_ntu_track_acc does not accept (:85-89)
         raise TypeError("train_ntu_track_acc() got an unexpected keyword argument 'init_f1'")
     train_host = _feature_cache_of(dataloaders['train'], 'train')
@@ -408,8 +436,10 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
 
     # with return_model every rank needs every trained model: no sharding then
     mine = mdist.my_share(len(todo)) if not (args.weightsharing or return_model) else list(range(len(todo)))
+    lap("setup")
     train_dev = train_host.to(device)
     dev_dev = dev_host.to(device)
+    lap("feature cache H2D")
     accs = torch.zeros(len(todo), dtype=torch.float64)
     all_stats = torch.zeros(len(todo), max(E, 1), 4, dtype=torch.float64)
     base_seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if dev_init else 0      # torch.manual_seed governs it
@@ -438,9 +468,12 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
             return torch.stack([pass_orders(loader, first + j * E, E, n_rows, device) for j in js])
         ptr = orders_for(dataloaders['train'], first_tr, n_train)
         pdv = orders_for(dataloaders['dev'], first_dv, n_dev)
+        lap("batch orders")
         stats, best, _ = g.train_run(train_dev, dev_dev, ptr, pdv, lrs, E, B)
+        lap("train_run (enqueue + GPU)")
         stats, best = stats.cpu(), best.cpu()                               # the one D2H of the call
         g.check()
+        lap("D2H of the results")
         for k, j in enumerate(js):
             accs[j] = best[k]
             all_stats[j] = stats[k]
@@ -458,6 +491,7 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
     if direct:
         if mine:
             g = make_group(mine)
+            lap("group creation")
             if dev_init:
                 init_on_device(g, base_seed, [todo[j] for j in mine])
             else:
@@ -467,9 +501,7 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
                 full = g if len(mine) == len(todo) else GroupLayout(
                     [np.asarray(sampled_configurations[i]).reshape(-1, 3) for i in todo], args.inner_representation_size,
                     args.num_outputs, flags, args.vid_len[1])
-                hp = torch.empty(int(full.p_off[-1]), dtype=torch.float32).pin_memory()
-                hb = torch.empty(int(full.b_off[-1]), dtype=torch.float32).pin_memory()
-                hp.zero_()
+                hp, hb = _staging(int(full.p_off[-1]), int(full.b_off[-1]))
                 init_host_arenas(full, hp, hb)
                 if full is g:
                     g.params.copy_(hp, non_blocking=True)
@@ -478,6 +510,7 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
                     for k, j in enumerate(mine):
                         g.params[int(g.p_off[k]):int(g.p_off[k + 1])].copy_(hp[int(full.p_off[j]):int(full.p_off[j + 1])], non_blocking=True)
                         g.bufs[int(g.b_off[k]):int(g.b_off[k + 1])].copy_(hb[int(full.b_off[j]):int(full.b_off[j + 1])], non_blocking=True)
+            lap("parameter initialisation + H2D")
             run(mine, g)
         elif not dev_init:
             pass   # nothing to train on this rank; RNG parity across ranks is not needed for results it never produces
@@ -488,6 +521,7 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
         run(mine)
 
     accs = mdist.gather_results(accs, len(todo))
+    lap("gather")
     real_accuracies = [accs[j].clone() for j in range(len(todo))]
     train_sampled_models.last_stats = all_stats
     if return_model:

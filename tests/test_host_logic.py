@@ -97,6 +97,38 @@ def test_direct_arena_init_equals_module_construction():
             assert torch.equal(base[o:o + int(np.prod(shape))].view(shape), v), (c, k)
 
 
+@pytest.mark.parametrize("mode", ["torch", "fast"])
+def test_bulk_mt19937_initialiser_is_torch_bit_for_bit(mode, monkeypatch):
+    """csrc/host_init.cpp restates torch's CPU mt19937 + uniform_ stream in bulk: same weights as module
+    construction (which is what the reference does per candidate) AND the same generator state afterwards."""
+    import mfas_b200.ntu_searchable as ntu
+    from mfas_b200 import _lib, host_init
+    from mfas_b200.engine import GroupLayout
+    monkeypatch.setenv("MFAS_HOST_INIT", mode)
+    if mode == "fast":
+        assert host_init._self_check() >= 0, "bulk helper does not reproduce torch's uniform_ on this CPU"
+    confs = [np.array(FOUND_CONFS[4]), np.array([[2, 3, 1]]), np.array(FOUND_CONFS[1])]
+    args = make_args(128, 64, 1, bn=True)
+    g = GroupLayout(confs, 128, 60, _lib.FLAG_BN)
+    hp, hb = torch.zeros(int(g.p_off[-1])), torch.zeros(int(g.b_off[-1]))
+    torch.manual_seed(11)
+    torch.rand(1000)                                   # start in the middle of a 624-word block
+    ntu.init_host_arenas(g, hp, hb)
+    after_fast = torch.rand(5)
+    torch.manual_seed(11)
+    torch.rand(1000)
+    for c, conf in enumerate(confs):
+        m = ntu.Searchable_Skeleton_Image_Net(args, conf)
+        for k, v in m.state_dict().items():
+            if k.endswith("tracked"):
+                continue
+            arena, off, shape = g.slots[c][k]
+            base = hb if arena == "b" else hp
+            o = int(g.b_off[c] if arena == "b" else g.p_off[c]) + int(off)
+            assert torch.equal(base[o:o + int(np.prod(shape))].view(shape), v), (c, k)
+    assert torch.equal(after_fast, torch.rand(5)), "generator state diverged after the initialisation"
+
+
 def test_scheduler_matches_reference_semantics():
     from mfas_b200.scheduler import LRCosineAnnealingScheduler
     from oracle.mfas_oracle import CosineRestartLR
