@@ -76,12 +76,17 @@ class FeatureCache:
 
     def __getitem__(self, i):
         """Sample dict with the reference's keys (/root/reference/datasets/ntu.py:84-87)."""
+        if self.logit_rgb is not None:
+            return {'rgb': torch.cat((self.rgb_cat[i], self.logit_rgb[i])), 'ske': torch.cat((self.ske_cat[i], self.logit_ske[i])),
+                    'label': self.labels[i]}
         return {'rgb': self.rgb_cat[i], 'ske': self.ske_cat[i], 'label': self.labels[i]}
 
     def pin(self):
         if self.device.type == 'cpu' and torch.cuda.is_available() and not self.ske_cat.is_pinned():
             self.ske_cat, self.rgb_cat, self.labels = (self.ske_cat.pin_memory(), self.rgb_cat.pin_memory(),
                                                        self.labels.pin_memory())
+            if self.logit_rgb is not None:
+                self.logit_rgb, self.logit_ske = self.logit_rgb.pin_memory(), self.logit_ske.pin_memory()
         return self
 
     def to(self, device, non_blocking=True, memoize=True):
@@ -171,8 +176,11 @@ class FeatureCacheLoader:
         dev = c.device
         for s in range(0, len(order), self.batch_size):
             rows = order[s:s + self.batch_size].to(dev)
-            yield {'rgb': c.rgb_cat.index_select(0, rows), 'ske': c.ske_cat.index_select(0, rows),
-                   'label': c.labels.index_select(0, rows)}
+            rgb, ske = c.rgb_cat.index_select(0, rows), c.ske_cat.index_select(0, rows)
+            if c.logit_rgb is not None:      # multitask: the cached backbone logits ride behind the taps of their modality
+                rgb = torch.cat((rgb, c.logit_rgb.index_select(0, rows)), 1)
+                ske = torch.cat((ske, c.logit_ske.index_select(0, rows)), 1)
+            yield {'rgb': rgb, 'ske': ske, 'label': c.labels.index_select(0, rows)}
 
 
 def synthetic_ntu_cache(n_rows: int, seed: int, num_outputs: int = 60, vid_len_ske: int = 32,

@@ -41,7 +41,10 @@ struct DCand {
   float* mu;       // [L][H] batch (or running) mean used by the last forward
   float* invstd;   // [L][H]
   float* logits;   // [Bmax][C]
+  float* dsp;      // [L][MFAS_DSP_SLOTS] per-CTA partials of d(loss)/d(sigmoid(alpha_l)) (alpha gates, ffma engine)
 };
+
+constexpr int MFAS_DSP_SLOTS = 128;    // >= (widest ske tap + widest rgb tap) / 32
 
 struct DCache {
   long long n_rows;
@@ -71,6 +74,9 @@ __device__ __forceinline__ int batch_row(const BatchRef& b, int cand, int r) {
   if (b.rows == nullptr) return (int)(b.base + r);
   return b.rows[(long long)cand * b.stride + b.base + r];
 }
+
+// sigmoid(alpha) of the modality gate, the arithmetic of torch.sigmoid on fp32
+__device__ __forceinline__ float gate_of(float alpha) { return 1.f / (1.f + expf(-alpha)); }
 
 __device__ __forceinline__ float act_fwd(float z, int kind) {
   if (kind == MFAS_ACT_RELU) return fmaxf(z, 0.f);

@@ -58,6 +58,12 @@ k_fusion_fwd(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int 
   const int nchunks = nch[0] + nch[1] + nch[2];
   const float* Wbase = cd.p + ly.oW;
   const int K = ly.K;
+  // AlphaScalarMultiplication (aux_models.py:103-111): ske * sigmoid(alpha), rgb * (1 - sigmoid(alpha))
+  float seg_gate[3] = {1.f, 1.f, 1.f};
+  if (cd.flags & MFAS_FLAG_ALPHAS) {
+    const float sg = gate_of(cd.p[ly.oalpha]);
+    seg_gate[0] = sg; seg_gate[1] = 1.0f - sg;
+  }
 
   // register staging of the next chunk (global loads in flight while the current chunk computes)
   float4 xr[4];
@@ -78,6 +84,8 @@ k_fusion_fwd(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int 
       if (r < nrows && c4 < kw) {
         const long long row = seg_gather[s] ? (long long)rowid[r] : (long long)r;
         val = __ldg(reinterpret_cast<const float4*>(seg_ptr[s] + row * seg_ld[s] + k0 + c4));
+        const float gt = seg_gate[s];
+        val.x *= gt; val.y *= gt; val.z *= gt; val.w *= gt;      // exact no-op when the gate is off (1.0f)
       }
       xr[i] = val;
     }
@@ -209,20 +217,21 @@ struct HeadOut {
   long long stat_stride, stat_off;
 };
 
+// body shared by k_head and the fused chain kernel (kernels_tc.cuh: k_chain_all); blockDim.x == kHeadThreads
 template <bool TRAIN>
-__global__ void __launch_bounds__(kHeadThreads)
-k_head(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, int hs_ld, int lg_ld, AdamH adam,
-       float step_size, float bc2_sqrt, HeadOut out) {
-  extern __shared__ __align__(16) float smem[];
-  const int cand = blockIdx.x;
-  const DCand& cd = cands[cand];
+__device__ __forceinline__ void head_body(const DCand& cd, int cand, const DCache& cache, const BatchRef& batch, int bmax,
+                                          int hs_ld, int lg_ld, const AdamH& adam, float step_size, float bc2_sqrt,
+                                          const HeadOut& out, float* smem) {
   const int H = cd.H, C = cd.C, nrows = batch.n_rows, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H4 = H >> 2;
   float* hs = smem;                         // [bmax][hs_ld]
   float* wcs = hs + (size_t)bmax * hs_ld;   // [C][hs_ld]
   float* lg = wcs + (size_t)C * hs_ld;      // [bmax][lg_ld]
   __shared__ float rowloss[MFAS_MAX_BATCH];
-  __shared__ int rowok[MFAS_MAX_BATCH], lab[MFAS_MAX_BATCH];
+  __shared__ int rowok[MFAS_MAX_BATCH], lab[MFAS_MAX_BATCH], grow[MFAS_MAX_BATCH];
+  // multitask (train_searchable/ntu.py:59-61): loss = CE(fusion) + CE(rgb backbone) + CE(ske backbone), preds from
+  // the sum of the three logit vectors.  The backbone logits are cached constants, so gradients are unchanged.
+  const bool multitask = (cd.flags & MFAS_FLAG_MULTITASK) && cache.logit_rgb && cache.logit_ske;
 
   const float* hl = cd.hid + (long long)(cd.L - 1) * bmax * H;
   const float* Wc = cd.p + cd.oWc;
@@ -234,7 +243,11 @@ k_head(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, 
     const int r = i / H4, c4 = i % H4;
     *reinterpret_cast<float4*>(wcs + r * hs_ld + c4 * 4) = *reinterpret_cast<const float4*>(Wc + r * H + c4 * 4);
   }
-  for (int r = tid; r < nrows; r += kHeadThreads) lab[r] = (int)cache.labels[batch_row(batch, cand, r)];
+  for (int r = tid; r < nrows; r += kHeadThreads) {
+    const int gr = batch_row(batch, cand, r);
+    grow[r] = gr;
+    lab[r] = (int)cache.labels[gr];
+  }
   __syncthreads();
 
   // logits = h W_c^T + b_c (ntu_searchable.py:242): item = (class quad, batch row), rows run over lanes
@@ -284,8 +297,35 @@ k_head(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, 
     const float e0 = lane < C ? expf(v0 - mx) : 0.f, e1 = lane + 32 < C ? expf(v1 - mx) : 0.f;
     const float lse = logf(warp_sum(e0 + e1));
     const int y = lab[r];
+    float extra = 0.f;
+    if (multitask) {
+      const float* lr_ = cache.logit_rgb + (long long)grow[r] * C;
+      const float* ls_ = cache.logit_ske + (long long)grow[r] * C;
+      const float r0 = lane < C ? lr_[lane] : -INFINITY, r1 = lane + 32 < C ? lr_[lane + 32] : -INFINITY;
+      const float s0 = lane < C ? ls_[lane] : -INFINITY, s1 = lane + 32 < C ? ls_[lane + 32] : -INFINITY;
+      auto ce_of = [&](float a0, float a1) {                       // -log_softmax(a)[y], warp-wide
+        float m = fmaxf(a0, a1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float e = (lane < C ? expf(a0 - m) : 0.f) + (lane + 32 < C ? expf(a1 - m) : 0.f);
+        const float l2 = logf(warp_sum(e));
+        const float ay = __shfl_sync(0xffffffffu, y < 32 ? a0 : a1, y & 31);
+        return -((ay - m) - l2);
+      };
+      extra = ce_of(r0, r1) + ce_of(s0, s1);
+      // preds = argmax(out + visual + skeleton), first maximum (torch.max(sum(output), 1))
+      const float t0 = lane < C ? (v0 + r0) + s0 : -INFINITY, t1 = lane + 32 < C ? (v1 + r1) + s1 : -INFINITY;
+      float tm = fmaxf(t0, t1);
+      am = (t1 > t0) ? lane + 32 : lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, tm, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+        if (om > tm || (om == tm && oa < am)) { tm = om; am = oa; }
+      }
+    }
     if (lane == 0) {
-      rowloss[r] = -((row[y] - mx) - lse);
+      rowloss[r] = -((row[y] - mx) - lse) + extra;
       rowok[r] = (am == y) ? 1 : 0;
     }
     __syncwarp();
@@ -351,6 +391,14 @@ k_head(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, 
     adam_update(g, p, m, v, adam, step_size, bc2_sqrt);
     cd.p[o] = p; cd.m[o] = m; cd.v[o] = v;
   }
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(kHeadThreads)
+k_head(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, int hs_ld, int lg_ld, AdamH adam,
+       float step_size, float bc2_sqrt, HeadOut out) {
+  extern __shared__ __align__(16) float smem[];
+  head_body<TRAIN>(cands[blockIdx.x], blockIdx.x, cache, batch, bmax, hs_ld, lg_ld, adam, step_size, bc2_sqrt, out, smem);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -461,6 +509,15 @@ k_fusion_bwd(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int 
   else if (kc0 < fs + fr) { src = cache.rgb[ly.rgb_tap]; ld = cache.rgb_ld[ly.rgb_tap]; k_local = kc0 - fs; }
   else { src = cd.hid + (long long)(layer - 1) * bmax * H; ld = H; k_local = kc0 - fs - fr; gather = false; }
   const bool hidden = !gather;
+  // alpha gate: the columns of this CTA belong to one segment; x is kept unscaled in smem, so acc below is the
+  // unscaled G = dz^T x: dW = gate * G, and d(loss)/d(sigmoid) = +-sum(W o G) over the gated columns
+  const bool gated = (cd.flags & MFAS_FLAG_ALPHAS) && !hidden;
+  float gsc = 1.f, gsign = 0.f;
+  if (gated) {
+    const float sg = gate_of(cd.p[ly.oalpha]);
+    if (kc0 < fs) { gsc = sg; gsign = 1.f; } else { gsc = 1.0f - sg; gsign = -1.f; }
+  }
+  float dsum = 0.f;
   for (int r = warp; r < nrows; r += 8) {
     const long long row = gather ? (long long)batch_row(batch, cand, r) : (long long)r;
     Xs[r * BWD_KT + lane] = lane < kw ? __ldg(src + row * ld + k_local + lane) : 0.f;
@@ -503,13 +560,47 @@ k_fusion_bwd(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int 
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const long long o = (long long)(h0 + i) * K + lane;
-        if (Gg) Gg[o] = acc[i];
         float p = Wg[o], m = Mg[o], v = Vg[o];
-        adam_update(acc[i], p, m, v, adam, step_size, bc2_sqrt);
+        dsum = fmaf(p, acc[i], dsum);
+        const float gw = gated ? acc[i] * gsc : acc[i];
+        if (Gg) Gg[o] = gw;
+        adam_update(gw, p, m, v, adam, step_size, bc2_sqrt);
         Wg[o] = p; Mg[o] = m; Vg[o] = v;
       }
     }
   }
+  if (cd.flags & MFAS_FLAG_ALPHAS) {     // fixed-order reduction -> one partial per CTA; k_alpha_step finishes the sum
+    __shared__ float dsw[8];
+    dsum = warp_sum(dsum);
+    if (lane == 0) dsw[warp] = dsum;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += dsw[w];
+      cd.dsp[layer * MFAS_DSP_SLOTS + blockIdx.x] = gsign * t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// alpha gates: d(alpha_l) = (sum of the per-CTA partials of k_fusion_bwd, fixed order) * s (1 - s), then Adam.
+// One thread per (candidate, layer); launched once per train step after every k_fusion_bwd.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_alpha_step(const DCand* __restrict__ cands, int n_cand, AdamH adam, float step_size, float bc2_sqrt) {
+  const int cand = blockIdx.x * (blockDim.x / MFAS_MAX_LAYERS) + threadIdx.x / MFAS_MAX_LAYERS, l = threadIdx.x % MFAS_MAX_LAYERS;
+  if (cand >= n_cand) return;
+  const DCand& cd = cands[cand];
+  if (l >= cd.L || !(cd.flags & MFAS_FLAG_ALPHAS)) return;
+  const DLayer& ly = cd.layer[l];
+  const int nt = (ly.d_ske + ly.d_rgb + BWD_KT - 1) / BWD_KT;      // feature-column CTAs of k_fusion_bwd
+  float ds = 0.f;
+  for (int i = 0; i < nt; ++i) ds += cd.dsp[l * MFAS_DSP_SLOTS + i];
+  float p = cd.p[ly.oalpha], m = cd.m[ly.oalpha], v = cd.v[ly.oalpha];
+  const float sg = gate_of(p);
+  const float g = ds * sg * (1.0f - sg);
+  if (cd.grad) cd.grad[ly.oalpha] = g;
+  adam_update(g, p, m, v, adam, step_size, bc2_sqrt);
+  cd.p[ly.oalpha] = p; cd.m[ly.oalpha] = m; cd.v[ly.oalpha] = v;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -663,18 +663,48 @@ template <int NPAD> struct ChainCfg {
   static constexpr size_t SMEM = 1024 + 2 * (size_t)NKB * 16384 + 2 * (size_t)NKB * NPAD * 128;
 };
 
+// Shared state of the chain kernels: operand tiles, the MMA-completion mbarrier and its running phase, the TMEM
+// accumulator.  One layer step is a device function so that the per-layer kernels and the fused k_chain_all
+// (every layer forward, the head, every layer backward in ONE launch per step) run the same code.
+struct ChainCtx {
+  uint8_t* smem;          // 1024-aligned dynamic shared memory
+  uint64_t* bar;
+  int* ok_flag;
+  uint32_t tm;            // TMEM accumulator (NPAD columns)
+  uint32_t phase;
+  bool ok;
+};
+
+template <int NPAD>
+__device__ __forceinline__ void chain_ctx_open(ChainCtx& cx, uint8_t* smem_raw, uint64_t* bar, uint32_t* tmem_slot, int* ok_flag) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  cx.smem = umma::align1024(smem_raw);
+  cx.bar = bar; cx.ok_flag = ok_flag; cx.phase = 0; cx.ok = true;
+  if (warp == 0) umma::tmem_alloc(tmem_slot, NPAD);
+  if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_mbar_init(); }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  cx.tm = *tmem_slot;
+}
+template <int NPAD>
+__device__ __forceinline__ void chain_ctx_close(ChainCtx& cx) {
+  umma::tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) umma::tmem_free(cx.tm, NPAD);
+}
+__device__ __forceinline__ void chain_wait(ChainCtx& cx) {      // wait for the MMAs committed last; flips the phase
+  if (cx.ok) cx.ok = umma::cta_wait(cx.bar, cx.phase, cx.ok_flag);
+  cx.phase ^= 1;
+}
+
 template <bool TRAIN, int NPAD>
-__global__ void __launch_bounds__(ChainCfg<NPAD>::THREADS)
-k_chain_fwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, const float* part_base,
-            long long part_stride_cand, uint32_t drop_seed, float drop_p, uint32_t step, TcErr err) {
+__device__ __forceinline__ void chain_fwd_layer(ChainCtx& cx, const DCand& cd, int cand, int layer, int m0, int nrows, int bmax,
+                                                const float* part_base, long long part_stride_cand, uint32_t drop_seed,
+                                                float drop_p, uint32_t step) {
   constexpr int THREADS = ChainCfg<NPAD>::THREADS;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = umma::align1024(smem_raw);
-  const DCand& cd = cands[blockIdx.y];
-  if (layer >= cd.L) return;
+  uint8_t* smem = cx.smem;
   const int H = cd.H;
-  const int m0 = blockIdx.x * 128;
-  if (m0 >= H) return;
   const DLayer& ly = cd.layer[layer];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool has_hid = layer > 0;
@@ -684,25 +714,15 @@ k_chain_fwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, con
   uint8_t* a_lo = a_hi + NKB * A_KB;
   uint8_t* b_hi = a_lo + NKB * A_KB;
   uint8_t* b_lo = b_hi + NKB * B_KB;
-  __shared__ uint64_t bar;
-  __shared__ uint32_t tmem_slot;
-  __shared__ int ok_flag;
-  if (warp == 0) umma::tmem_alloc(&tmem_slot, NPAD);
-  if (tid == 0) { umma::mbar_init(&bar, 1); umma::fence_mbar_init(); }
-  umma::tc_fence_before();
-  __syncthreads();
-  umma::tc_fence_after();
-  const uint32_t tm = tmem_slot;
+  const uint32_t tm = cx.tm;
 
-  uint32_t phase = 0;
-  bool ok = true;
   if (has_hid) {
     const float* Wh = cd.p + ly.oW + ly.d_ske + ly.d_rgb;              // hidden columns of W_l
     const float* hprev = cd.hid + (long long)(layer - 1) * bmax * H;
     constexpr uint32_t idesc = umma::idesc_tf32(128, NPAD, false, false);
     for (int j0 = 0; j0 < H; j0 += PASS) {                              // passes of <= NKB k-blocks
       const int jw = min(PASS, H - j0), f4 = jw >> 2;                   // float4 per row in this pass
-      if (j0 > 0) { ok = umma::cta_wait(&bar, phase, &ok_flag); phase ^= 1; if (!ok) break; }
+      if (j0 > 0) { chain_wait(cx); if (!cx.ok) break; }
       for (int i0 = tid; i0 < 128 * f4; i0 += THREADS * 4) {            // A: 128 rows of W
         float4 t[4];
 #pragma unroll
@@ -744,7 +764,7 @@ k_chain_fwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, con
           umma::mma_tf32(tm, dah, dbl, idesc, 1u);
           umma::mma_tf32(tm, dah, dbh, idesc, 1u);
         }
-        umma::mma_commit(&bar);
+        umma::mma_commit(cx.bar);
       }
     }
   }
@@ -765,7 +785,7 @@ k_chain_fwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, con
     for (int l = 0; l < layer; ++l) item0 += tc_fwd_items(cd.layer[l].d_ske, cd.layer[l].d_rgb);
     const int nsplit = tc_fwd_items(ly.d_ske, ly.d_rgb);
     const int Hp = ((H + 127) >> 7) << 7;
-    const float* part = part_base + (long long)blockIdx.y * part_stride_cand + ((long long)item0 * Hp + c) * NPAD + b0;
+    const float* part = part_base + (long long)cand * part_stride_cand + ((long long)item0 * Hp + c) * NPAD + b0;
     for (int s = 0; s < nsplit; ++s) {
       const float4* p4 = reinterpret_cast<const float4*>(part + (long long)s * Hp * NPAD);
 #pragma unroll
@@ -776,8 +796,7 @@ k_chain_fwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, con
     }
   }
   if (has_hid) {
-    if (ok) ok = umma::cta_wait(&bar, phase, &ok_flag);
-    if (!ok && tid == 0) atomicExch(err.flag, 3);
+    chain_wait(cx);
     umma::tc_fence_after();
     float v[NB];
     if (NB == 16) umma::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + b0, v);
@@ -839,10 +858,25 @@ k_chain_fwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, con
       actp += H; hidp += H;
     }
   }
-  umma::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) umma::tmem_free(tm, NPAD);
 }
+
+template <bool TRAIN, int NPAD>
+__global__ void __launch_bounds__(ChainCfg<NPAD>::THREADS)
+k_chain_fwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, const float* part_base,
+            long long part_stride_cand, uint32_t drop_seed, float drop_p, uint32_t step, TcErr err) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int ok_flag;
+  const DCand& cd = cands[blockIdx.y];
+  if (layer >= cd.L || (int)blockIdx.x * 128 >= cd.H) return;
+  ChainCtx cx;
+  chain_ctx_open<NPAD>(cx, smem_raw, &bar, &tmem_slot, &ok_flag);
+  chain_fwd_layer<TRAIN, NPAD>(cx, cd, blockIdx.y, layer, blockIdx.x * 128, nrows, bmax, part_base, part_stride_cand, drop_seed, drop_p, step);
+  if (!cx.ok && threadIdx.x == 0) atomicExch(err.flag, 3);
+  chain_ctx_close<NPAD>(cx);
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // k_chain_bwd: dhT_l[c,b] = sum_h W_{l+1}[h, hid c] dz_{l+1}[b,h]  (pre-update weights; the last layer
@@ -852,17 +886,11 @@ k_chain_fwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, con
 // dynamic smem (1024-aligned), per pass of PASS h: A_hi | A_lo (4 blocks x PASS rows x 128 B) | B_hi | B_lo (NKB x NPAD*128 B)
 // ---------------------------------------------------------------------------------------------
 template <int NPAD>
-__global__ void __launch_bounds__(ChainCfg<NPAD>::THREADS)
-k_chain_bwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, AdamH adam, float step_size,
-            float bc2_sqrt, uint32_t drop_seed, float drop_p, uint32_t step, TcErr err) {
+__device__ __forceinline__ void chain_bwd_layer(ChainCtx& cx, const DCand& cd, int layer, int m0, int nrows, int bmax, AdamH adam,
+                                                float step_size, float bc2_sqrt, uint32_t drop_seed, float drop_p, uint32_t step) {
   constexpr int THREADS = ChainCfg<NPAD>::THREADS;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = umma::align1024(smem_raw);
-  const DCand& cd = cands[blockIdx.y];
-  if (layer >= cd.L) return;
+  uint8_t* smem = cx.smem;
   const int H = cd.H;
-  const int m0 = blockIdx.x * 128;
-  if (m0 >= H) return;
   const DLayer& ly = cd.layer[layer];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool has_up = layer + 1 < cd.L;
@@ -872,18 +900,8 @@ k_chain_bwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, Ada
   uint8_t* a_lo = a_hi + 4 * A_BLK;
   uint8_t* b_hi = a_lo + 4 * A_BLK;
   uint8_t* b_lo = b_hi + NKB * B_KB;
-  __shared__ uint64_t bar;
-  __shared__ uint32_t tmem_slot;
-  __shared__ int ok_flag;
-  if (warp == 0) umma::tmem_alloc(&tmem_slot, NPAD);
-  if (tid == 0) { umma::mbar_init(&bar, 1); umma::fence_mbar_init(); }
-  umma::tc_fence_before();
-  __syncthreads();
-  umma::tc_fence_after();
-  const uint32_t tm = tmem_slot;
+  const uint32_t tm = cx.tm;
 
-  uint32_t phase = 0;
-  bool ok = true;
   if (has_up) {
     const DLayer& up = cd.layer[layer + 1];
     const float* Wu = cd.p + up.oW + up.d_ske + up.d_rgb + m0;       // W_{l+1}[h][hid m0 + .]
@@ -892,7 +910,7 @@ k_chain_bwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, Ada
     constexpr uint32_t idesc = umma::idesc_tf32(128, NPAD, true, false);
     for (int h0 = 0; h0 < H; h0 += PASS) {                             // passes of PASS rows of W_{l+1}
       const int hw = min(PASS, H - h0);
-      if (h0 > 0) { ok = umma::cta_wait(&bar, phase, &ok_flag); phase ^= 1; if (!ok) break; }
+      if (h0 > 0) { chain_wait(cx); if (!cx.ok) break; }
       for (int i0 = tid; i0 < hw * 32; i0 += THREADS * 4) {            // A: hw rows (h) x 32 float4 (128 columns)
         float4 t[4];
 #pragma unroll
@@ -936,7 +954,7 @@ k_chain_bwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, Ada
           umma::mma_tf32(tm, dah, dbl, idesc, 1u);
           umma::mma_tf32(tm, dah, dbh, idesc, 1u);
         }
-        umma::mma_commit(&bar);
+        umma::mma_commit(cx.bar);
       }
     }
   }
@@ -963,8 +981,7 @@ k_chain_bwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, Ada
     }
   }
   if (has_up) {
-    if (ok) ok = umma::cta_wait(&bar, phase, &ok_flag);
-    if (!ok && tid == 0) atomicExch(err.flag, 4);
+    chain_wait(cx);
     umma::tc_fence_after();
     if (NB == 16) umma::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + b0, dh);
     else umma::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + b0, dh);
@@ -1017,9 +1034,79 @@ k_chain_bwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, Ada
     upd(ly.ob + c, db);
     if (bn) { upd(ly.og + c, S2); upd(ly.obe + c, S1); }
   }
-  umma::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) umma::tmem_free(tm, NPAD);
+}
+
+template <int NPAD>
+__global__ void __launch_bounds__(ChainCfg<NPAD>::THREADS)
+k_chain_bwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, AdamH adam, float step_size,
+            float bc2_sqrt, uint32_t drop_seed, float drop_p, uint32_t step, TcErr err) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int ok_flag;
+  const DCand& cd = cands[blockIdx.y];
+  if (layer >= cd.L || (int)blockIdx.x * 128 >= cd.H) return;
+  ChainCtx cx;
+  chain_ctx_open<NPAD>(cx, smem_raw, &bar, &tmem_slot, &ok_flag);
+  chain_bwd_layer<NPAD>(cx, cd, layer, blockIdx.x * 128, nrows, bmax, adam, step_size, bc2_sqrt, drop_seed, drop_p, step);
+  if (!cx.ok && threadIdx.x == 0) atomicExch(err.flag, 4);
+  chain_ctx_close<NPAD>(cx);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// k_chain_all: the whole serial chain of one step in ONE launch -- for every candidate (one CTA each, H <= 128)
+// layer 0..L-1 forward, the classifier head (loss, dlogits, classifier Adam), layer L-1..0 backward.
+// The chain is latency-bound (a dozen dependent phases of a few microseconds); fusing it removes eight launch
+// boundaries per step and lets the weights the later phases need (hidden columns of W_1.., the classifier)
+// be pulled into L2 while the first phases run.  Intermediate activations go through global memory (L2) exactly
+// as between the separate kernels.
+// dynamic smem: max(chain operand tiles, head tiles)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <bool TRAIN, int NPAD>
+__global__ void __launch_bounds__(ChainCfg<NPAD>::THREADS)
+k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, const float* part_base,
+            long long part_stride_cand, int hs_ld, int lg_ld, AdamH adam, float step_size, float bc2_sqrt,
+            uint32_t drop_seed, float drop_p, uint32_t step, HeadOut ho, TcErr err) {
+  static_assert(ChainCfg<NPAD>::THREADS == kHeadThreads, "the head body is written for the chain CTA size");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int ok_flag;
+  const int cand = blockIdx.x, tid = threadIdx.x;
+  const DCand& cd = cands[cand];
+  const int nrows = batch.n_rows, L = cd.L, H = cd.H;
+  ChainCtx cx;
+  chain_ctx_open<NPAD>(cx, smem_raw, &bar, &tmem_slot, &ok_flag);
+  // L2 prefetch of what the later phases read from HBM: hidden columns of W_1.. (H rows x H floats each) and W_c
+  for (int l = 1; l < L; ++l) {
+    const DLayer& ly = cd.layer[l];
+    const float* Wh = cd.p + ly.oW + ly.d_ske + ly.d_rgb;
+    const int lines = H >> 5;                                    // 128-byte lines per row
+    for (int i = tid; i < H * lines; i += ChainCfg<NPAD>::THREADS) prefetch_l2(Wh + (long long)(i / lines) * ly.K + (i % lines) * 32);
+  }
+  for (int i = tid; i < (cd.C * H) >> 5; i += ChainCfg<NPAD>::THREADS) prefetch_l2(cd.p + cd.oWc + i * 32);
+
+  for (int l = 0; l < L; ++l) {
+    chain_fwd_layer<TRAIN, NPAD>(cx, cd, cand, l, 0, nrows, bmax, part_base, part_stride_cand, drop_seed, drop_p, step);
+    umma::tc_fence_before();
+    __syncthreads();                                             // h_l (global) and the TMEM reads are done
+    umma::tc_fence_after();
+  }
+  head_body<TRAIN>(cd, cand, cache, batch, bmax, hs_ld, lg_ld, adam, step_size, bc2_sqrt, ho, reinterpret_cast<float*>(cx.smem));
+  if (TRAIN) {
+    for (int l = L - 1; l >= 0; --l) {
+      __syncthreads();                                           // dh_L / dz_{l+1} (global) visible, smem tiles free
+      chain_bwd_layer<NPAD>(cx, cd, l, 0, nrows, bmax, adam, step_size, bc2_sqrt, drop_seed, drop_p, step);
+      umma::tc_fence_before();
+      __syncthreads();
+      umma::tc_fence_after();
+    }
+  }
+  if (!cx.ok && tid == 0) atomicExch(err.flag, 7);
+  chain_ctx_close<NPAD>(cx);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -145,8 +145,11 @@ struct mfas_group {
   int n_bwd_tiles = 0, n_sms = 148, bwd_ws = 1;
   FwdItem* fwd_items = nullptr;   // item list of the persistent forward kernel (device), rebuilt when arenas are rebound
   int n_fwd_items = 0, fwd_ws = 1;
+  bool any_alphas = false;
   int dbg = 0;                    // MFAS_TC_DEBUG bit 0: skip the Adam epilogue, bit 1: skip operand staging (timing experiments only)
-  int chain = 1;                  // 1: tensor-core chain kernels, 0: CUDA-core chain kernels (MFAS_CHAIN=ffma)
+  int chain = 2;                  // 2: fused chain kernel (H <= 128), 1: per-layer tensor-core chain kernels (MFAS_CHAIN=layers),
+                                  // 0: per-layer CUDA-core chain kernels (MFAS_CHAIN=ffma)
+  size_t smem_chain_all = 0;
 };
 
 static void set_adam(AdamH& a, double b1, double b2, double eps, double wd) {
@@ -203,7 +206,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
   auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
   size_t total = 0;
   std::vector<size_t> base(n_cand);
-  struct Off { size_t act, hid, dh, dz, dzs, mu, invstd, logits, best_p, best_bufs, best_nbt; };
+  struct Off { size_t act, hid, dh, dz, dzs, mu, invstd, logits, dsp, best_p, best_bufs, best_nbt; };
   std::vector<Off> off(n_cand);
   for (int c = 0; c < n_cand; ++c) {
     const mfas_layout& l = g->lay[c];
@@ -226,6 +229,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     o.mu = total; total += up((size_t)l.L * l.H * sizeof(float));
     o.invstd = total; total += up((size_t)l.L * l.H * sizeof(float));
     o.logits = total; total += up((size_t)batch_max * l.C * sizeof(float));
+    o.dsp = total; total += up((size_t)MFAS_MAX_LAYERS * MFAS_DSP_SLOTS * sizeof(float));
     o.best_p = total; total += up((size_t)l.n_params * sizeof(float));
     o.best_bufs = total; total += up((size_t)l.n_bufs * sizeof(float));
     o.best_nbt = total; total += up((size_t)MFAS_MAX_LAYERS * sizeof(long long));
@@ -258,7 +262,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     const Off& o = off[c];
     d.act = (float*)(g->ws + o.act); d.hid = (float*)(g->ws + o.hid); d.dh = (float*)(g->ws + o.dh);
     d.dz = (float*)(g->ws + o.dz); d.dzs = (float*)(g->ws + o.dzs); d.mu = (float*)(g->ws + o.mu); d.invstd = (float*)(g->ws + o.invstd);
-    d.logits = (float*)(g->ws + o.logits); d.best_p = (float*)(g->ws + o.best_p);
+    d.logits = (float*)(g->ws + o.logits); d.dsp = (float*)(g->ws + o.dsp); d.best_p = (float*)(g->ws + o.best_p);
     d.best_bufs = (float*)(g->ws + o.best_bufs); d.best_nbt = (long long*)(g->ws + o.best_nbt);
   }
   // dynamic shared memory of the two big-smem kernels
@@ -288,12 +292,14 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
   bool tc_ok = true;
   for (int c = 0; c < n_cand; ++c) {
     tc_ok = tc_ok && (g->lay[c].H % 64 == 0);
+    tc_ok = tc_ok && !(g->lay[c].flags & MFAS_FLAG_ALPHAS);      // the modality gates are built in the CUDA-core engine only
+    g->any_alphas = g->any_alphas || (g->lay[c].flags & MFAS_FLAG_ALPHAS);
     for (int l = 0; l < g->lay[c].L; ++l) tc_ok = tc_ok && g->lay[c].d_ske[l] % 128 == 0 && g->lay[c].d_rgb[l] % 128 == 0;
   }
   const char* env = getenv("MFAS_ENGINE");
   if (env && !strcmp(env, "ffma")) tc_ok = false;
   if (env && !strcmp(env, "tc") && !tc_ok) {
-    int code = fail(MFAS_ERR_UNSUPPORTED, "MFAS_ENGINE=tc needs inner_representation_size %% 64 == 0 and tap widths %% 128 == 0");
+    int code = fail(MFAS_ERR_UNSUPPORTED, "MFAS_ENGINE=tc needs inner_representation_size %% 64 == 0, tap widths %% 128 == 0 and alphas off");
     mfas_group_destroy(g);
     return code;
   }
@@ -340,7 +346,16 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     attr((const void*)k_chain_bwd<64>, ChainCfg<64>::SMEM);
     attr((const void*)k_chain_bwd<128>, ChainCfg<128>::SMEM);
     { int nsm = 0; if (e == cudaSuccess) e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device); if (nsm > 0) g->n_sms = nsm; }
-    { const char* ce = getenv("MFAS_CHAIN"); if (ce && !strcmp(ce, "ffma")) g->chain = 0; }
+    { const char* ce = getenv("MFAS_CHAIN"); if (ce && !strcmp(ce, "ffma")) g->chain = 0; if (ce && !strcmp(ce, "layers")) g->chain = 1; }
+    if (g->Hmax > 128 && g->chain == 2) g->chain = 1;                  // the fused kernel owns one 128-column tile per candidate
+    g->smem_chain_all = g->smem_chain > 1024 + g->smem_head ? g->smem_chain : 1024 + g->smem_head;
+    if (g->smem_chain_all > 227 * 1024 && g->chain == 2) g->chain = 1;
+    if (g->chain == 2) {
+      attr((const void*)k_chain_all<true, 64>, g->smem_chain_all);
+      attr((const void*)k_chain_all<false, 64>, g->smem_chain_all);
+      attr((const void*)k_chain_all<true, 128>, g->smem_chain_all);
+      attr((const void*)k_chain_all<false, 128>, g->smem_chain_all);
+    }
     { const char* be = getenv("MFAS_BWD"); if (be && !strcmp(be, "cta")) g->bwd_ws = 0; }
     if (g->npad != 64) g->bwd_ws = 0;                   // the persistent kernel is sized for batch <= 64 (96 KB operand stage + p/m/v rings)
     if (g->bwd_ws) {
@@ -391,7 +406,7 @@ extern "C" int mfas_group_status(mfas_group_t g) {
   if (g->tc_err) {
     int flag = 0;
     CUDA_TRY(cudaMemcpy(&flag, g->tc_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flag) return fail(MFAS_ERR_CUDA, "tensor-core pipeline barrier timed out in kernel %s", flag == 1 ? "k_tc_fwd_all" : flag == 2 ? "k_tc_bwd_all" : flag == 3 ? "k_chain_fwd" : flag == 4 ? "k_chain_bwd" : flag == 5 ? "k_tc_bwd_ws" : "k_tc_fwd_ws");
+    if (flag) return fail(MFAS_ERR_CUDA, "tensor-core pipeline barrier timed out in kernel %s", flag == 1 ? "k_tc_fwd_all" : flag == 2 ? "k_tc_bwd_all" : flag == 3 ? "k_chain_fwd" : flag == 4 ? "k_chain_bwd" : flag == 5 ? "k_tc_bwd_ws" : flag == 6 ? "k_tc_fwd_ws" : "k_chain_all");
   }
   return MFAS_OK;
 }
@@ -491,6 +506,9 @@ static int to_dcache(const mfas_group* g, const mfas_cache_desc* c, DCache* out)
         return fail(MFAS_ERR_INVALID, "cache tap widths differ from the layout of candidate %d step %d", k, l);
   out->labels = (const long long*)c->labels;
   out->logit_rgb = c->logit_rgb; out->logit_ske = c->logit_ske;
+  for (int k = 0; k < g->n_cand; ++k)
+    if ((g->lay[k].flags & MFAS_FLAG_MULTITASK) && (!c->logit_rgb || !c->logit_ske))
+      return fail(MFAS_ERR_INVALID, "multitask candidates need the cached backbone logits (cache.logit_rgb / logit_ske)");
   return MFAS_OK;
 }
 
@@ -500,6 +518,9 @@ static int to_dcache(const mfas_group* g, const mfas_cache_desc* c, DCache* out)
     cudaError_t e__ = cudaGetLastError();                                                     \
     if (e__ != cudaSuccess) return fail(MFAS_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
+
+static int launch_bwd_stream(mfas_group* g, const DCache& cache, const BatchRef& batch, float step_size, float bc2_sqrt,
+                             bool keep, cudaStream_t st);
 
 // tc engine: one launch covers the feature columns of every layer, small per-layer kernels carry the chain
 static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& batch, bool train, bool bn_train,
@@ -514,6 +535,17 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
   else k_tc_fwd_all<128><<<gf, TC_THREADS, g->smem_tc_fwd, st>>>(g->dc, cache, batch, g->part, g->part_stride, terr);
   LAUNCH_CHECK(g);
   const dim3 gc((g->Hmax + 127) / 128, g->n_cand);
+  bool keep = false;                                  // the grad arena is a test facility: all candidates or none
+  for (int c = 0; c < g->n_cand; ++c) keep = keep || g->hc[c].grad != nullptr;
+  if (g->chain == 2 && train == bn_train) {           // the whole serial chain in one launch
+#define CA(T, N) k_chain_all<T, N><<<g->n_cand, ChainCfg<N>::THREADS, g->smem_chain_all, st>>>(g->dc, cache, batch, g->bmax, g->part, g->part_stride, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, ho, terr)
+    if (g->npad == 64) { if (train) CA(true, 64); else CA(false, 64); }
+    else { if (train) CA(true, 128); else CA(false, 128); }
+#undef CA
+    LAUNCH_CHECK(g);
+    if (!train) return MFAS_OK;
+    return launch_bwd_stream(g, cache, batch, step_size, bc2_sqrt, keep, st);
+  }
   for (int l = 0; l < g->Lmax; ++l) {
 #define FL(T, N) k_fwd_layer<T, N><<<gl, TC_CHAIN_THREADS, g->smem_fl, st>>>(g->dc, l, batch.n_rows, g->bmax, g->part, g->part_stride, g->drop_seed, g->drop_p, step)
 #define CF(T, N) k_chain_fwd<T, N><<<gc, ChainCfg<N>::THREADS, g->smem_chain, st>>>(g->dc, l, batch.n_rows, g->bmax, g->part, g->part_stride, g->drop_seed, g->drop_p, step, terr)
@@ -544,9 +576,14 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
     }
     LAUNCH_CHECK(g);
   }
+  return launch_bwd_stream(g, cache, batch, step_size, bc2_sqrt, keep, st);
+}
+
+// the weight-gradient + Adam streaming kernel of a train step (all layers, all candidates)
+static int launch_bwd_stream(mfas_group* g, const DCache& cache, const BatchRef& batch, float step_size, float bc2_sqrt,
+                             bool keep, cudaStream_t st) {
+  const TcErr terr{g->tc_err};
   const dim3 gb(g->items_bwd, (g->Hmax + TC_BWD_HT - 1) / TC_BWD_HT, g->n_cand);
-  bool keep = false;                                  // the grad arena is a test facility: all candidates or none
-  for (int c = 0; c < g->n_cand; ++c) keep = keep || g->hc[c].grad != nullptr;
   if (g->bwd_ws) {
     const int grid = g->n_bwd_tiles < g->n_sms ? g->n_bwd_tiles : g->n_sms;
     if (keep) k_tc_bwd_ws<true><<<grid, TC_WS_THREADS, TC_WS_SMEM, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, g->bwd_tiles, g->n_bwd_tiles, terr);
@@ -586,6 +623,11 @@ static int launch_step(mfas_group* g, const DCache& cache, const BatchRef& batch
     LAUNCH_CHECK(g);
     k_fusion_bwd<<<dim3((g->Kmax[l] + BWD_KT - 1) / BWD_KT, g->n_cand), kThreads, g->smem_bwd, st>>>(
         g->dc, cache, batch, l, g->bmax, g->adam, step_size, bc2_sqrt);
+    LAUNCH_CHECK(g);
+  }
+  if (g->any_alphas) {
+    const int per = 256 / MFAS_MAX_LAYERS;
+    k_alpha_step<<<(g->n_cand + per - 1) / per, 256, 0, st>>>(g->dc, g->n_cand, g->adam, step_size, bc2_sqrt);
     LAUNCH_CHECK(g);
   }
   return MFAS_OK;

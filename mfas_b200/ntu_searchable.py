@@ -64,10 +64,12 @@ class CachedTaps(nn.Module):
         self.widths, self.kind = tuple(widths), kind
 
     def forward(self, x):
-        taps = torch.split(x, self.widths, 1)
+        n = sum(self.widths)
+        logits = x[:, n:] if x.shape[1] > n else None         # cached backbone logits ride behind the taps (multitask)
+        taps = torch.split(x[:, :n], self.widths, 1)
         if self.kind == "rgb":                       # Visual.forward 6-tuple, central/ntu.py:50
-            return (None, *taps, None)
-        return [None] * 4 + list(taps), None         # Skeleton.forward, central/ntu.py:183
+            return (None, *taps, logits)
+        return [None] * 4 + list(taps), logits       # Skeleton.forward, central/ntu.py:183
 
     def load_state_dict(self, state_dict, strict=True, assign=False):
         return nn.modules.module._IncompatibleKeys([], [])
@@ -184,21 +186,30 @@ class Searchable_Skeleton_Image_Net(nn.Module):
     # ---- forward ----------------------------------------------------------------------------
     def forward(self, tensor_tuple):
         rgb, ske = tensor_tuple[0], tensor_tuple[1]          # caller passes (rgb, ske), ntu_searchable.py:208
-        if getattr(self.args, "alphas", False) or getattr(self.args, "multitask", False):
-            raise NotImplementedError("alphas / multitask are not built yet (SURVEY.md section 8(f) rows 3-4)")
         if rgb.dim() != 2 or ske.dim() != 2:
             raise ValueError("expected cached taps: rgb [B, %d], ske [B, %d]" % (sum(D_RGB), sum(self.skenet.widths)))
+        nr, ns = sum(D_RGB), sum(self.skenet.widths)
+        multitask = bool(getattr(self.args, "multitask", False))
+        vis_logits = rgb[:, nr:] if rgb.shape[1] > nr else None      # visual_classifier / skel_classifier, :213,:217
+        ske_logits = ske[:, ns:] if ske.shape[1] > ns else None
+        if multitask and (vis_logits is None or ske_logits is None):
+            raise ValueError("args.multitask needs the cached backbone logits behind the taps (FeatureCache(logit_rgb=, "
+                             "logit_ske=); FeatureCacheLoader appends them)")
         g = self.native(rgb.device)
         B = rgb.shape[0]
         if B > g.batch_max:
             raise ValueError(f"batch of {B} rows exceeds MFAS_MAX_BATCH={g.batch_max}")
-        cache = FeatureCache(ske.contiguous(), rgb.contiguous(),
-                             torch.zeros(B, dtype=torch.int64, device=rgb.device), self.args.vid_len[1])
+        cache = FeatureCache(ske[:, :ns].contiguous(), rgb[:, :nr].contiguous(),
+                             torch.zeros(B, dtype=torch.int64, device=rgb.device), self.args.vid_len[1],
+                             vis_logits.contiguous() if multitask else None, ske_logits.contiguous() if multitask else None)
         rows = torch.arange(B, dtype=torch.int32, device=rgb.device)
         logits, _, _ = g.forward(cache, rows, train=self.training, step=self._fwd_steps)
         if self.training:
             self._fwd_steps += 1
-        return logits[self._slot].clone()
+        out = logits[self._slot].clone()
+        if not multitask:
+            return out
+        return out, vis_logits, ske_logits                       # ntu_searchable.py:244-247
 
 
 # ----------------------------------------------------------------------------------------------
@@ -430,8 +441,11 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
     first_dv = _reserve_passes(dataloaders['dev'], len(todo) * E)
     lrs = cosine_lrs(args, n_train, E * steps)
     flags = flags_from_args(args)
-    if flags & (_lib.FLAG_ALPHAS | _lib.FLAG_MULTITASK):
-        raise NotImplementedError("alphas / multitask are not built yet (SURVEY.md section 8(f) rows 3-4)")
+    if flags & _lib.FLAG_MULTITASK:
+        # the reference calls train_ntu_track_acc WITHOUT multitask= (ntu_searchable.py:81-83) while the model returns a
+        # 3-tuple (:244-247), so torch.max(output, 1) raises there; multitask training goes through train_ntu_track_acc
+        raise TypeError("max() received an invalid combination of arguments - got (tuple, int): train_sampled_models "
+                        "does not pass multitask to the training loop (use train_ntu_track_acc(..., multitask=True))")
     drop_p = float(args.drpt) if args.drpt > 1e-10 else 0.0
 
     # with return_model every rank needs every trained model: no sharding then

@@ -21,15 +21,27 @@ def _adam_hparams(optimizer):
     return g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], g["lr"]
 
 
+def _check_multitask(net, multitask, dataloaders, splits):
+    """The model returns the 3-tuple iff args.multitask (ntu_searchable.py:244-247) and the loop indexes it iff
+    ``multitask`` (train_searchable/ntu.py:53-61): a mismatch fails in the reference too."""
+    if bool(getattr(net.args, "multitask", False)) != bool(multitask):
+        raise TypeError(f"multitask={bool(multitask)} but the model was built with args.multitask="
+                        f"{bool(getattr(net.args, 'multitask', False))} (the reference loop would index / reduce the wrong type)")
+    if multitask:
+        for sp in splits:
+            if _feature_cache_of(dataloaders[sp], sp).logit_rgb is None:
+                raise ValueError(f"multitask needs cached backbone logits in dataloaders['{sp}'].dataset "
+                                 "(FeatureCache(logit_rgb=, logit_ske=))")
+
+
 def train_ntu_track_acc(model, criteria, optimizer, scheduler, dataloaders, dataset_sizes,
                         device=None, num_epochs=200, verbose=False, multitask=False):
     """num_epochs x (train pass, dev pass) with best-dev rollback; returns the best dev accuracy
     (/root/reference/models/search/train_searchable/ntu.py:14-89).  ``criteria`` must be cross-entropy
     (what every caller passes); the LR of every batch comes from ``scheduler`` exactly as in the
     reference (per-batch for LRCosineAnnealingScheduler, otherwise stepped once per epoch)."""
-    if multitask:
-        raise NotImplementedError("multitask is not built yet (SURVEY.md section 8(f) row 3)")
     net = model.module if isinstance(model, torch.nn.DataParallel) else model
+    _check_multitask(net, multitask, dataloaders, ('train', 'dev'))
     g = net.native(device)
     b1, b2, eps, wd, lr0 = _adam_hparams(optimizer)
     g.set_adam(b1, b2, eps, wd)
@@ -44,11 +56,16 @@ def train_ntu_track_acc(model, criteria, optimizer, scheduler, dataloaders, data
     slot = net._slot
     t0 = 0
     for name, p in named.items():
+        if name not in g.slots[slot]:
+            continue
         st = optimizer.state.get(p, None)
-        if st and name in g.slots[slot]:
+        if st:
             g.view(slot, name, "m").copy_(st["exp_avg"].reshape(g.view(slot, name, "m").shape))
             g.view(slot, name, "v").copy_(st["exp_avg_sq"].reshape(g.view(slot, name, "v").shape))
             t0 = int(st["step"])
+        else:                                                 # a fresh optimiser starts from zero moments, whatever an
+            g.view(slot, name, "m").zero_()                   # earlier stage left in the arenas (main_found_ntu.py:133)
+            g.view(slot, name, "v").zero_()
     g.adam_t = t0
 
     lrs = []
@@ -87,9 +104,8 @@ def train_ntu_track_acc(model, criteria, optimizer, scheduler, dataloaders, data
 
 def test_ntu_track_acc(model, dataloaders, dataset_sizes, device=None, multitask=False):
     """Eval-mode accuracy over dataloaders['test'] (train_searchable/ntu.py:92-125)."""
-    if multitask:
-        raise NotImplementedError("multitask is not built yet (SURVEY.md section 8(f) row 3)")
     net = model.module if isinstance(model, torch.nn.DataParallel) else model
+    _check_multitask(net, multitask, dataloaders, ('test',))
     model.train(False)
     g = net.native(device)
     test_c = _feature_cache_of(dataloaders['test'], 'test').to(g.device)

@@ -349,7 +349,22 @@ def _taps_of(split, rows):
     return [t[rows] for t in split["ske"]], [t[rows] for t in split["rgb"]], split["labels"][rows]
 
 
-def train_track_acc(head, sched, train_split, dev_split, batch, orders, num_epochs, log=None):
+def multitask_loss_preds(logits, labels, aux):
+    """train_searchable/ntu.py:59-61: loss = CE(out) + CE(visual) + CE(skeleton), preds = argmax of the sum.
+    ``aux`` = (rgb backbone logits, ske backbone logits) of the batch rows, or None (single task, :53-58)."""
+    loss, _ = FusionHead.ce_loss(logits, labels)
+    if aux is None:
+        return loss, logits.argmax(axis=1)
+    lr, ls = (a.astype(F32) for a in aux)
+    loss = F32(F32(loss + FusionHead.ce_loss(lr, labels)[0]) + FusionHead.ce_loss(ls, labels)[0])
+    return loss, ((logits + lr).astype(F32) + ls).astype(F32).argmax(axis=1)
+
+
+def _aux_of(split, rows, multitask):
+    return (split["logit_rgb"][rows], split["logit_ske"][rows]) if multitask else None
+
+
+def train_track_acc(head, sched, train_split, dev_split, batch, orders, num_epochs, log=None, multitask=False):
     """orders: callable (phase, epoch) -> row-index array for that pass.
 
     Returns (best_acc float64, per-epoch stats list).  Rolls ``head.state`` back to the best
@@ -369,12 +384,12 @@ def train_track_acc(head, sched, train_split, dev_split, batch, orders, num_epoc
                 sk, rg, y = _taps_of(split, rows)
                 if phase == "train":
                     lr = sched.step()
-                    logits, loss, _ = head.train_step(sk, rg, y, lr)
+                    logits, loss, _ = head.train_step(sk, rg, y, lr)      # backbone logits are constants: same gradients
                 else:
                     logits, _ = head.forward(sk, rg, train=False)
-                    loss, _ = head.ce_loss(logits, y)
+                loss, preds = multitask_loss_preds(logits, y, _aux_of(split, rows, multitask))
                 run_loss += float(loss) * len(rows)
-                run_correct += int((logits.argmax(axis=1) == y).sum())
+                run_correct += int((preds == y).sum())
             row[phase + "_loss"] = run_loss / n
             row[phase + "_acc"] = run_correct / n
             if log:
@@ -387,13 +402,15 @@ def train_track_acc(head, sched, train_split, dev_split, batch, orders, num_epoc
     return np.float64(best_acc), stats
 
 
-def test_track_acc(head, split, batch, order):
+def test_track_acc(head, split, batch, order, multitask=False):
     order = np.asarray(order)
     correct = 0
     for s0 in range(0, len(order), batch):
-        sk, rg, y = _taps_of(split, order[s0:s0 + batch])
+        rows = order[s0:s0 + batch]
+        sk, rg, y = _taps_of(split, rows)
         logits, _ = head.forward(sk, rg, train=False)
-        correct += int((logits.argmax(axis=1) == y).sum())
+        _, preds = multitask_loss_preds(logits, y, _aux_of(split, rows, multitask))
+        correct += int((preds == y).sum())
     return np.float64(correct / len(order))
 
 

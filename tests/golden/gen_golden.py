@@ -84,7 +84,7 @@ def run_case(name, cs):
     tmp = tempfile.mkdtemp()
     torch.save({}, os.path.join(tmp, "ske"))
     torch.save({}, os.path.join(tmp, "rgb"))
-    args = make_args(H, B, E, bn=cs["bn"], drpt=cs["drpt"], Ti=cs["Ti"], checkpointdir=tmp)
+    args = make_args(H, B, E, bn=cs["bn"], drpt=cs["drpt"], Ti=cs["Ti"], checkpointdir=tmp, alphas=cs.get("alphas", False))
     train = synthetic_ntu_cache(cs["n_train"], cs["data_seed"])
     dev = synthetic_ntu_cache(cs["n_dev"], cs["data_seed"] + 1)
     loaders = {"train": FeatureCacheLoader(train, B, True, LOADER_SEED),

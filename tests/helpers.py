@@ -34,7 +34,15 @@ GOLDEN_CASES = {
     "mixL": dict(confs=[[[0, 0, 0]], [[3, 1, 1], [2, 2, 2]], [[1, 3, 2], [0, 0, 1], [2, 1, 0]]],
                  H=16, B=32, n_train=128, n_dev=64, epochs=2, bn=True, drpt=0.0, Ti=1, model_seed=3,
                  data_seed=31),
+    # modality gates (AlphaScalarMultiplication, aux_models.py:94-111): args.alphas=True, mixed depths
+    "alph": dict(confs=[[[3, 1, 1], [1, 3, 0]], [[0, 2, 1]], [[2, 0, 0], [1, 1, 1], [3, 2, 2]]], H=32, B=16, n_train=80,
+                 n_dev=40, epochs=2, bn=True, drpt=0.0, Ti=1, model_seed=5, data_seed=41, alphas=True),
 }
+
+
+# main_found_ntu.py flow (multitask + alphas, two training stages, test pass): tests/golden/gen_golden_found.py
+FOUND_MT_CASE = dict(conf=FOUND_CONFS[3][:3], H=32, B=16, n_train=96, n_dev=48, n_test=40, epochs=2, Ti=1, alphas=True,
+                     model_seed=9, data_seed=51, loader_seed=300)
 
 
 def make_args(H, B, epochs, bn=True, drpt=0.0, Ti=1, Tm=2, eta_max=1e-3, eta_min=1e-6, C=60,
@@ -100,5 +108,8 @@ def rel_err(a, b):
 
 def split_np(cache):
     """FeatureCache -> dict of numpy tap arrays for the oracle."""
-    return dict(ske=[t.numpy() for t in cache.ske_taps()], rgb=[t.numpy() for t in cache.rgb_taps()],
-                labels=cache.labels.numpy())
+    d = dict(ske=[t.numpy() for t in cache.ske_taps()], rgb=[t.numpy() for t in cache.rgb_taps()],
+             labels=cache.labels.numpy())
+    if cache.logit_rgb is not None:
+        d.update(logit_rgb=cache.logit_rgb.numpy(), logit_ske=cache.logit_ske.numpy())
+    return d

@@ -28,10 +28,11 @@ TRAJ_W = 0.25         # trained weights, relative L2 (fp32-vs-fp64 band of the r
 DEV = "cuda:0"
 
 
-def _group(confs, H, B, bn=True, drpt=0.0, keep_grads=False, seed=0, ids=None):
+def _group(confs, H, B, bn=True, drpt=0.0, keep_grads=False, seed=0, ids=None, alphas=False, multitask=False):
     from mfas_b200 import _lib
     from mfas_b200.engine import CandidateGroup
-    flags = (_lib.FLAG_BN if bn else 0) | (_lib.FLAG_DROPOUT if drpt > 1e-10 else 0)
+    flags = (_lib.FLAG_BN if bn else 0) | (_lib.FLAG_DROPOUT if drpt > 1e-10 else 0) | (_lib.FLAG_ALPHAS if alphas else 0) | \
+        (_lib.FLAG_MULTITASK if multitask else 0)
     g = CandidateGroup(confs, H, 60, flags, DEV, batch_max=B, drop_p=drpt, drop_seed=seed, keep_grads=keep_grads,
                        cand_ids=ids)
     g.set_adam(0.9, 0.999, 1e-8, 1e-4)
@@ -75,7 +76,8 @@ def _fp32_noise(head_after, head_before, batch):
     sk, rg, y = batch
     with O.precision(np.float64):
         h64 = O.FusionHead(head_after.conf, head_after.H, head_after.C, head_before["state"], batchnorm=head_after.bn,
-                           drpt=head_after.drpt, dropout_seed=head_after.dropout_seed, cand_index=head_after.cand_index)
+                           drpt=head_after.drpt, dropout_seed=head_after.dropout_seed, cand_index=head_after.cand_index,
+                           alphas=head_after.use_alphas)
         h64.t = head_after.t - 1
         logits, tape = h64.forward(sk, rg, train=True)
         g64 = h64.backward(logits, y, tape)
@@ -97,8 +99,10 @@ def _check_step(g, ci, head_before, head_after, ograds, logits, ol, lr, t, what,
             # tensor-level (L2) relative error at 1e-4; no single element further than 3e-4 of the tensor's max
             assert _rel_l2(got_g[k], g64[k]) < tol, f"{what} grad {k}: rel L2 {_rel_l2(got_g[k], g64[k]):.2e} vs float64 ground truth"
             _close(got_g[k], g64[k], 3 * tol, f"{what} grad {k} vs float64 ground truth", scale=gmax)
-        assert _rel_l2(got_g[k], ref) < tol, f"{what} grad {k}: rel L2 {_rel_l2(got_g[k], ref):.2e}"
-        _close(got_g[k], ref, 3 * tol, f"{what} grad {k}", scale=gmax)
+        # against the fp32 oracle: its own distance from the float64 truth adds to ours (triangle inequality)
+        own = _rel_l2(ref, g64[k]) if g64 is not None else 0.0
+        assert _rel_l2(got_g[k], ref) < tol + own, f"{what} grad {k}: rel L2 {_rel_l2(got_g[k], ref):.2e}"
+        _close(got_g[k], ref, 3 * tol + (noise if g64 is not None else 0.0), f"{what} grad {k}", scale=gmax)
         p0 = head_before["state"][k]
         m0, v0 = head_before["adam"].get(k, (np.zeros_like(p0), np.zeros_like(p0)))
         ep, em, ev = _adam_ref(p0, m0, v0, got_g[k].reshape(p0.shape), lr, t)
@@ -124,7 +128,7 @@ def test_single_step_vs_oracle_and_fixture(name):
     loader = FeatureCacheLoader(train, cs["B"], True, int(gold["meta/loader_seed"]))
     inits = init_states(cs["confs"], cs["H"], 60, cs["bn"], cs["drpt"], cs["model_seed"])
     E, B = cs["epochs"], cs["B"]
-    g = _group(cs["confs"], cs["H"], B, cs["bn"], keep_grads=True)
+    g = _group(cs["confs"], cs["H"], B, cs["bn"], keep_grads=True, alphas=cs.get("alphas", False))
     tc = train.to(DEV)
     rows = torch.stack([loader.order_for_pass(ci * E)[:B] for ci in range(len(cs["confs"]))])
     for ci in range(g.n):
@@ -133,7 +137,7 @@ def test_single_step_vs_oracle_and_fixture(name):
     torch.cuda.synchronize()
     logits, loss = logits.cpu().numpy(), loss.cpu().numpy()
     for ci, conf in enumerate(cs["confs"]):
-        head = O.FusionHead(conf, cs["H"], 60, inits[ci], batchnorm=cs["bn"])
+        head = O.FusionHead(conf, cs["H"], 60, inits[ci], batchnorm=cs["bn"], alphas=cs.get("alphas", False))
         before = dict(state={k: v.copy() for k, v in head.state.items()}, adam={})
         sk, rg, y = O._taps_of(trs, rows[ci].numpy())
         ol, oloss, ograds = head.train_step(sk, rg, y, 1e-3)
@@ -195,7 +199,8 @@ def test_train_sampled_models_vs_reference_fixture(name):
     import mfas_b200.ntu_searchable as ntu
     cs = GOLDEN_CASES[name]
     gold = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
-    args = make_args(cs["H"], cs["B"], cs["epochs"], bn=cs["bn"], drpt=cs["drpt"], Ti=cs["Ti"], checkpointdir="/nonexistent")
+    args = make_args(cs["H"], cs["B"], cs["epochs"], bn=cs["bn"], drpt=cs["drpt"], Ti=cs["Ti"], checkpointdir="/nonexistent",
+                     alphas=cs.get("alphas", False))
     train = synthetic_ntu_cache(cs["n_train"], cs["data_seed"])
     dev = synthetic_ntu_cache(cs["n_dev"], cs["data_seed"] + 1)
     seed = int(gold["meta/loader_seed"])
@@ -225,6 +230,8 @@ def test_train_sampled_models_vs_reference_fixture(name):
         assert not models[ci].training
         for k, v in sd.items():
             if k.startswith("alphas"):
+                if cs.get("alphas", False):       # scalar gates: absolute agreement along the trajectory
+                    assert abs(float(v) - float(gold[f"c{ci}/final/{k}/sample"][0])) < 2e-3, f"{name} c{ci} final {k}"
                 continue
             if k.endswith("num_batches_tracked"):
                 continue
@@ -507,3 +514,74 @@ def test_device_init_is_placement_independent():
     full = run([0, 1, 2])
     again = run([0, 1, 2])
     assert [float(a) for a in full] == [float(a) for a in again]
+
+
+def test_found_flow_multitask_alphas_vs_reference_fixture(capsys):
+    """main_found_ntu.py:94-157 through the drop-in API -- multitask 3-head loss + alpha gates, stage 1 on
+    central_params() then stage 2 on model.parameters() with a fresh Adam, test pass -- against what the unmodified
+    reference printed / returned (tests/golden/gen_golden_found.py) and against the oracle's final weights."""
+    import re
+    import mfas_b200.ntu_searchable as ntu
+    import mfas_b200.train_ntu as tr
+    from mfas_b200.scheduler import LRCosineAnnealingScheduler
+    from helpers import FOUND_MT_CASE as cs
+    gold = np.load(os.path.join(GOLDEN_DIR, "found_mt.npz"))
+    args = make_args(cs["H"], cs["B"], cs["epochs"], bn=True, drpt=0.0, Ti=cs["Ti"], alphas=cs["alphas"], multitask=True)
+    splits = {k: synthetic_ntu_cache(n, cs["data_seed"] + i, with_backbone_logits=True)
+              for i, (k, n) in enumerate((("train", cs["n_train"]), ("dev", cs["n_dev"]), ("test", cs["n_test"])))}
+    loaders = {k: FeatureCacheLoader(v, cs["B"], True, cs["loader_seed"] + 1000 * i) for i, (k, v) in enumerate(splits.items())}
+    sizes = {k: len(v) for k, v in splits.items()}
+    torch.manual_seed(cs["model_seed"])
+    conf = np.array(cs["conf"])
+    rmode = ntu.Searchable_Skeleton_Image_Net(args, conf)
+    criteria = [torch.nn.CrossEntropyLoss()] * 3
+    nbpe = sizes["train"] / args.batchsize
+    dev = torch.device(DEV)
+    opt = torch.optim.Adam(rmode.central_params(), lr=args.eta_max / 10, weight_decay=1e-4)
+    sch = LRCosineAnnealingScheduler(args.eta_max, args.eta_min, args.Ti, args.Tm, nbpe)
+    rmode.to(dev)
+    interm = tr.train_ntu_track_acc(rmode, criteria, opt, sch, loaders, sizes, device=dev, num_epochs=1, multitask=True)
+    opt = torch.optim.Adam(rmode.parameters(), lr=args.eta_max, weight_decay=1e-4)
+    sch = LRCosineAnnealingScheduler(args.eta_max, args.eta_min, args.Ti, args.Tm, nbpe)
+    final = tr.train_ntu_track_acc(rmode, criteria, opt, sch, loaders, sizes, device=dev, num_epochs=args.epochs, multitask=True)
+    test_acc = tr.test_ntu_track_acc(rmode, loaders, sizes, device=dev, multitask=True)
+    rows = re.findall(r"(train|dev) Loss: ([0-9.]+) Acc: ([0-9.]+)", capsys.readouterr().out)
+    assert [r[0] for r in rows] == list(gold["epoch_phase"])
+    assert np.abs(np.array([float(r[1]) for r in rows]) - gold["epoch_loss"]).max() < 5e-3
+    assert np.abs(np.array([float(r[2]) for r in rows]) - gold["epoch_acc"]).max() <= 2.0 / cs["n_dev"]
+    assert abs(float(interm) - float(gold["interm_acc"])) <= 2.0 / cs["n_dev"]
+    assert abs(float(final) - float(gold["final_acc"])) <= 2.0 / cs["n_dev"]
+    assert abs(float(test_acc) - float(gold["test_acc"])) <= 2.0 / cs["n_test"]
+    assert test_acc.dtype == torch.float64
+    for k, v in rmode.state_dict().items():
+        if k.endswith("num_batches_tracked") or k.endswith(".bias") or "running" in k:
+            continue
+        assert _rel_l2(sample_tensor(v.cpu().numpy())["sample"], gold[f"final/{k}/sample"]) < TRAJ_W, k
+    # forward() returns the 3-tuple of the reference (ntu_searchable.py:244-247)
+    b = next(iter(loaders["test"]))
+    out = rmode((b["rgb"].to(dev), b["ske"].to(dev)))
+    assert isinstance(out, tuple) and len(out) == 3 and out[0].shape == (cs["B"], 60) and out[1].shape == (cs["B"], 60)
+    with pytest.raises(TypeError):          # loop / model disagreement about multitask fails, as in the reference
+        tr.test_ntu_track_acc(rmode, loaders, sizes, device=dev, multitask=False)
+
+
+def test_multitask_head_on_tensor_core_engine():
+    """The multitask loss / preds live in the shared head: same numbers from the tc engine (H=128) as from the oracle."""
+    conf = FOUND_CONFS[4]
+    H, B = 128, 64
+    train = synthetic_ntu_cache(128, 8, with_backbone_logits=True)
+    trs = split_np(train)
+    init = init_states([conf], H, 60, True, 0.0, 2)[0]
+    g = _group([conf], H, B, multitask=True)
+    assert g.engine == "tc"
+    g.load_state(0, init)
+    rows = torch.arange(B) + 17
+    head = O.FusionHead(conf, H, 60, init)
+    sk, rg, y = O._taps_of(trs, rows.numpy())
+    ol, _ = head.forward(sk, rg, train=True)
+    oloss, opreds = O.multitask_loss_preds(ol, y, (trs["logit_rgb"][rows.numpy()], trs["logit_ske"][rows.numpy()]))
+    logits, loss, correct = g.train_step(train.to(DEV), rows, lr=1e-3)
+    torch.cuda.synchronize()
+    _close(logits[0].cpu().numpy(), ol, TOL, "multitask fusion logits")
+    assert abs(float(loss[0]) - float(oloss)) < TOL * float(oloss)
+    assert int(correct[0]) == int((opreds == y).sum())

@@ -31,7 +31,7 @@ def test_oracle_matches_reference_fixture(name):
     E, B = cs["epochs"], cs["B"]
     for ci, conf in enumerate(cs["confs"]):
         # --- one step: logits, loss, gradients (autograd vs hand-derived)
-        head = O.FusionHead(conf, cs["H"], 60, inits[ci], batchnorm=cs["bn"], drpt=cs["drpt"])
+        head = O.FusionHead(conf, cs["H"], 60, inits[ci], batchnorm=cs["bn"], drpt=cs["drpt"], alphas=cs.get("alphas", False))
         rows = ltr.order_for_pass(ci * E)[:B].numpy()
         sk, rg, y = O._taps_of(trs, rows)
         logits, tape = head.forward(sk, rg, train=True)
@@ -39,17 +39,24 @@ def test_oracle_matches_reference_fixture(name):
         assert rel_err(logits, g[f"c{ci}/step0_logits"]) < TOL
         assert abs(float(loss) - float(g[f"c{ci}/step0_loss"])) < TOL * abs(float(g[f"c{ci}/step0_loss"]))
         grads = head.backward(logits, y, tape)
+        with O.precision(np.float64):       # fp32 noise of the reference arithmetic itself (cancelling sums such as d(beta))
+            h64 = O.FusionHead(conf, cs["H"], 60, inits[ci], batchnorm=cs["bn"], drpt=cs["drpt"], alphas=cs.get("alphas", False))
+            l64, t64 = h64.forward(sk, rg, train=True)
+            g64 = h64.backward(l64, y, t64)
         for k, v in grads.items():
-            if k.startswith("alphas"):
+            if k.startswith("alphas") and not cs.get("alphas", False):
                 continue
             s = sample_tensor(v)
             ref = g[f"c{ci}/grad/{k}/sample"]
             scale = max(float(g[f"c{ci}/grad/{k}/amax"]), 1e-12)
-            assert np.abs(s["sample"] - ref).max() / scale < TOL, k
+            noise = float(np.abs(np.asarray(v, np.float64) - g64[k]).max() / scale)
+            tol = max(TOL, 4 * noise)
+            assert tol < 10 * TOL, (k, noise)
+            assert np.abs(s["sample"] - ref).max() / scale < tol, k
             assert abs(s["s2"] - float(g[f"c{ci}/grad/{k}/s2"])) <= 2 * TOL * float(g[f"c{ci}/grad/{k}/s2"]) + 1e-20
 
         # --- full run: per-batch losses, dev accuracy, best-epoch rollback, final weights
-        head = O.FusionHead(conf, cs["H"], 60, inits[ci], batchnorm=cs["bn"], drpt=cs["drpt"])
+        head = O.FusionHead(conf, cs["H"], 60, inits[ci], batchnorm=cs["bn"], drpt=cs["drpt"], alphas=cs.get("alphas", False))
         sched = O.CosineRestartLR(1e-3, 1e-6, cs["Ti"], 2, cs["n_train"] / B)
         per_batch = {"train": [], "dev": []}
 
@@ -124,3 +131,39 @@ def test_torch_port_matches_reference_fixture(name):
             ref = g[f"c{ci}/final/{k}/sample"]
             got = sample_tensor(v.numpy())["sample"]
             assert np.abs(got - ref).max() <= 1e-6 * max(float(g[f"c{ci}/final/{k}/amax"]), 1e-12), k
+
+
+def test_oracle_matches_reference_found_flow_multitask():
+    """main_found_ntu.py flow executed by the unmodified reference (tests/golden/gen_golden_found.py): multitask
+    3-head loss + alpha gates, stage 1 (1 epoch) and stage 2 (fresh Adam), rollback, test pass."""
+    from helpers import FOUND_MT_CASE as cs
+    g = np.load(os.path.join(GOLDEN_DIR, "found_mt.npz"))
+    splits = {k: synthetic_ntu_cache(n, cs["data_seed"] + i, with_backbone_logits=True)
+              for i, (k, n) in enumerate((("train", cs["n_train"]), ("dev", cs["n_dev"]), ("test", cs["n_test"])))}
+    loaders = {k: FeatureCacheLoader(v, cs["B"], True, cs["loader_seed"] + 1000 * i) for i, (k, v) in enumerate(splits.items())}
+    sp = {k: split_np(v) for k, v in splits.items()}
+    init = init_states([cs["conf"]], cs["H"], 60, True, 0.0, cs["model_seed"])[0]
+    head = O.FusionHead(cs["conf"], cs["H"], 60, init, alphas=cs["alphas"])
+    rows = []
+    first = 0
+    for stage, epochs in ((1, 1), (2, cs["epochs"])):
+        head.adam, head.t = {}, 0                                   # a fresh torch.optim.Adam per stage (main_found_ntu.py:109,133)
+        sched = O.CosineRestartLR(1e-3, 1e-6, cs["Ti"], 2, cs["n_train"] / cs["B"])
+        orders = lambda ph, e, first=first: loaders["train" if ph == "train" else "dev"].order_for_pass(first + e).numpy()
+        best, stats = O.train_track_acc(head, sched, sp["train"], sp["dev"], cs["B"], orders, epochs, multitask=True)
+        first += epochs
+        for s in stats:
+            rows += [("train", s["train_loss"], s["train_acc"]), ("dev", s["dev_loss"], s["dev_acc"])]
+        assert abs(float(best) - float(g["interm_acc" if stage == 1 else "final_acc"])) < 1e-4 + 1.0 / cs["n_dev"]
+    assert [r[0] for r in rows] == list(g["epoch_phase"])
+    # the reference prints 4 decimals
+    assert np.abs(np.array([r[1] for r in rows]) - g["epoch_loss"]).max() < 2e-3
+    assert np.abs(np.array([r[2] for r in rows]) - g["epoch_acc"]).max() <= 1.0 / cs["n_dev"] + 1e-4
+    acc = O.test_track_acc(head, sp["test"], cs["B"], loaders["test"].order_for_pass(0).numpy(), multitask=True)
+    assert abs(float(acc) - float(g["test_acc"])) <= 1.0 / cs["n_test"] + 1e-12
+    for k, v in head.state.items():
+        if k.endswith("num_batches_tracked") or k.endswith(".bias") or "running" in k:
+            continue
+        ref = g[f"final/{k}/sample"]
+        got = sample_tensor(v)["sample"]
+        assert np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30) < 0.05, k
