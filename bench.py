@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--candidates", type=int, default=128, help="candidates per GPU (weak scaling)")
+    ap.add_argument("--candidates", type=int, default=148, help="candidates per GPU (weak scaling); 148 = one fused-chain CTA per SM")
     ap.add_argument("--epochs", type=int, default=3, help="epochs per candidate per step (search driver default: --epochs 3)")
     ap.add_argument("--cpu-sample-steps", type=int, default=48, help="train steps of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -254,12 +254,52 @@ def run_ours(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = M * cnt["train_bytes"] / t_step / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": f"fused train step of {M} candidates ({engine} engine: k_tc_fwd_all + 4 x k_chain_fwd + k_head + 4 x k_chain_bwd + "
-                          f"k_tc_bwd_all = 11 launches; the two *_all kernels carry 95 % of the bytes)",
+    # ncu --set full capture of the same step (dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/)
+    traffic, per_kernel_traffic = None, {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        if tj.get("workload") == "cfg2":
+            per_kernel_traffic = {k: v * M for k, v in tj["dram_bytes_per_launch_per_candidate"].items()}
+            traffic = float(sum(per_kernel_traffic.values()))
+    except Exception:
+        pass
+    # the three kernels of the step, each timed with CUDA events on the launching stream (C ABI: mfas_group_last_step_ms)
+    kernels = []
+    if engine == "tc":
+        lay = g.layouts[0]
+        L, Hh = lay.L, lay.H
+        k_feat = sum(lay.d_ske[l] + lay.d_rgb[l] for l in range(L))
+        k_all = sum(lay.K[l] for l in range(L))
+        alg = {"k_tc_fwd_ws": 4 * (Hh * k_feat + B * k_feat),                                   # W feature columns + gathered x
+               "k_chain_all": 4 * (2 * Hh * Hh * (L - 1) + 6 * (3 * Hh * L + C * Hh + C) + 4 * B * Hh * L),
+               "k_tc_bwd_ws": 4 * (6 * Hh * k_all + B * k_all + B * Hh * L)}                    # p/m/v read+write, x, dz
+        try:
+            g.set_profiling(True)
+            acc = [0.0, 0.0, 0.0]
+            n_p = 20
+            for i in range(n_p):
+                g.train_step(train_dev, ptr[:, 0, (i % steps_tr) * B:(i % steps_tr + 1) * B], 1e-4)
+                ms = g.last_step_ms()
+                acc = [a_ + m_ for a_, m_ in zip(acc, ms)]
+            g.set_profiling(False)
+            for name, tms in zip(("k_tc_fwd_ws", "k_chain_all", "k_tc_bwd_ws"), acc):
+                tms /= n_p
+                gbs = M * alg[name] / (tms * 1e-3) / 1e9
+                kernels.append({"kernel": name, "ms_per_launch": tms, "share_of_step": None, "algorithmic_bytes_per_launch": M * alg[name],
+                                "achieved": gbs, "frac": gbs / peak,
+                                "traffic": per_kernel_traffic.get(name)})
+            tot = sum(k["ms_per_launch"] for k in kernels)
+            for k in kernels:
+                k["share_of_step"] = k["ms_per_launch"] / tot
+        except Exception as ex:                      # profiling is an aid, never the measurement itself
+            kernels = [{"error": str(ex)}]
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": f"fused train step of {M} candidates ({engine} engine: k_tc_fwd_ws -> k_chain_all -> k_tc_bwd_ws, 3 launches; "
+                          f"achieved = SURVEY 8(d) algorithmic bytes of the whole step / CUDA-event time of the whole step)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": M * cnt["train_bytes"], "ms_per_launch": t_step * 1e3,
-                "tensor_tflops": M * (cnt["fwd_flops"] + cnt["bwd_flops"]) / t_step / 1e12}
+                "tensor_tflops": M * (cnt["fwd_flops"] + cnt["bwd_flops"]) / t_step / 1e12,
+                "kernels": kernels}
     g.close()
 
     # ---- e2e: the public API with HOST buffers ---------------------------------------------------

@@ -180,6 +180,16 @@ int mfas_train_run(mfas_group_t g, const mfas_cache_desc* train, const mfas_cach
 int mfas_eval_pass(mfas_group_t g, const mfas_cache_desc* cache, const int32_t* d_perm, int32_t batch,
                    double* d_out, void* stream);
 
+/* Measurement aid (bench.py): with profiling on, every train step of the tensor-core engine records CUDA events on the
+ * launching stream around its three kernels; mfas_group_last_step_ms returns the device time in milliseconds of
+ * {forward streaming kernel, fused chain kernel, backward streaming kernel} of the most recent train step. */
+int mfas_group_set_profiling(mfas_group_t g, int32_t on);
+int mfas_group_last_step_ms(mfas_group_t g, float* ms3);
+/* Debug aid: groups created with MFAS_CHAIN_TIMELINE=1 in the environment record clock64() stamps at the phase
+ * boundaries of the fused chain kernel (start, after each forward layer, head, after each backward layer);
+ * copies out[n_cand][16] (synchronises the device). */
+int mfas_group_chain_timeline(mfas_group_t g, int64_t* out, int32_t n_cand);
+
 /* Host-side helper (no GPU): fills n_ops float arrays with U(from, to) draws taken from torch's global CPU generator
  * stream, bit-identical to torch.nn.init.uniform_/kaiming_uniform_ applied in the same order -- what the reference
  * constructor does for every candidate (models/search/ntu_searchable.py:200, :274-282 via nn.Linear.reset_parameters).

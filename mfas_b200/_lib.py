@@ -88,6 +88,9 @@ SYMBOLS = {
                                   _P, _P, _P, _P]),
     "mfas_train_run": (C.c_int, [_P, C.POINTER(CacheDesc), C.POINTER(CacheDesc), C.POINTER(RunArgs), _P]),
     "mfas_eval_pass": (C.c_int, [_P, C.POINTER(CacheDesc), _P, C.c_int32, _P, _P]),
+    "mfas_group_set_profiling": (C.c_int, [_P, C.c_int32]),
+    "mfas_group_last_step_ms": (C.c_int, [_P, _P]),
+    "mfas_group_chain_timeline": (C.c_int, [_P, _P, C.c_int32]),
     "mfas_host_uniform_fill": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P, C.c_int32]),
 }
 

@@ -29,7 +29,10 @@ constexpr int TC_KB_PER_ITEM = 32;    // forward: at most this many k-blocks (32
 constexpr int TC_BWD_KT = 128;        // backward: weight columns (TMEM lanes) per work item
 constexpr int TC_BWD_HT = 64;         // backward: output rows h (TMEM columns) per work item
 
-struct TcErr { int* flag; };          // set when a bounded barrier wait expires (never hangs the GPU)
+struct TcErr {
+  int* flag;                          // set when a bounded barrier wait expires (never hangs the GPU)
+  long long* timeline;                // optional [n_cand][16] clock64 stamps of k_chain_all's phases (MFAS_CHAIN_TIMELINE=1)
+};
 
 __host__ __device__ __forceinline__ int tc_fwd_items(int d_ske, int d_rgb) {
   return (((d_ske + d_rgb) >> 5) + TC_KB_PER_ITEM - 1) / TC_KB_PER_ITEM;
@@ -53,7 +56,9 @@ __device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, 
 // ---------------------------------------------------------------------------------------------
 // forward, all layers: partial zT over a slice of FEATURE columns of one layer.
 // grid = (max items per candidate, ceil(H/128), candidates);  NPAD = batch padded to the MMA N.
-// part[cand][item][Hp][NPAD]
+// part[cand][item][NPAD/4][Hp][4]: four consecutive batch rows of one output column are one float4, and for a fixed
+// group of four rows consecutive columns are consecutive float4s -- the producer (TMEM lane = column) and the consumers
+// (lane = column) both move 512 contiguous bytes per warp instruction
 // dynamic smem (1024-aligned): A_hi 16K | A_lo 16K | B_hi NPAD*128 | B_lo NPAD*128
 // (Measured alternative, kept out: double-buffering the smem stage so the stores of block k+1 overlap
 //  the MMAs of block k costs a third of the resident CTAs -- 2 instead of 3 per SM -- and is 30 % slower.)
@@ -181,16 +186,16 @@ k_tc_fwd_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, floa
 
   // epilogue: thread = one output column h (TMEM lane), 32 consecutive batch rows per tcgen05.ld
   const int Hp = ((H + 127) >> 7) << 7;
-  float* part = part_base + (long long)cand * part_stride_cand + ((long long)blockIdx.x * Hp + m0) * NPAD;
+  float* part = part_base + (long long)cand * part_stride_cand + (long long)blockIdx.x * Hp * NPAD;
   const int h_loc = (warp & 3) * 32 + lane;
 #pragma unroll
   for (int cc = 0; cc < NPAD / 64; ++cc) {
     const int c0 = (warp >> 2) * (NPAD / 2) + cc * 32;
     float v[32];
     umma::tmem_ld32(tm + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
-    float4* dst = reinterpret_cast<float4*>(part + (long long)h_loc * NPAD + c0);
+    float4* dst = reinterpret_cast<float4*>(part) + (long long)(c0 >> 2) * Hp + m0 + h_loc;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    for (int j = 0; j < 8; ++j) dst[(long long)j * Hp] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   }
   umma::tc_fence_before();
   __syncthreads();
@@ -219,9 +224,10 @@ k_tc_fwd_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, floa
 // ---------------------------------------------------------------------------------------------
 struct __align__(16) FwdItem {
   const float* W;                 // &params[oW + m0 * K]
-  long long part_off;             // float offset of this item's [128][NPAD] tile in the partial-sum buffer
+  long long part_off;             // float offset of this item's tile (+ 4 * m0: first row of this CTA's 128) in the partial-sum buffer
   int K, kb0, kb1, fs_kb;         // row stride of W; k-block range [kb0, kb1); first k-block of the rgb tap
   int ske_tap, rgb_tap, cand, rows_valid;   // rows_valid = min(128, H - m0)
+  int Hp, pad0, pad1, pad2;       // H rounded up to 128: rows of the partial-sum tile
 };
 
 template <int NPAD> struct FwdWs {
@@ -367,7 +373,7 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
     for (int i = 0; i < n_my; ++i) {
       const FwdItem& it = items[blockIdx.x + i * gridDim.x];
       const int tb = i & 1;
-      float* dst = part_base + it.part_off + (long long)(q * 32 + lane) * NPAD;
+      float4* dst = reinterpret_cast<float4*>(part_base + it.part_off) + (q * 32 + lane);   // part_off includes the row tile
       if (!umma::mbar_wait(&tfull[tb], (i >> 1) & 1)) { ok = false; break; }
       umma::tc_fence_after();
 #pragma unroll
@@ -375,10 +381,10 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
         float v[32], w[32];
         umma::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 2 * NPAD + cc * 32), v);
         umma::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 2 * NPAD + NPAD + cc * 32), w);
-        float4* d4 = reinterpret_cast<float4*>(dst + cc * 32);
+        float4* d4 = dst + (long long)(cc * 8) * it.Hp;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          d4[j] = make_float4(v[4 * j] + w[4 * j], v[4 * j + 1] + w[4 * j + 1], v[4 * j + 2] + w[4 * j + 2], v[4 * j + 3] + w[4 * j + 3]);
+          d4[(long long)j * it.Hp] = make_float4(v[4 * j] + w[4 * j], v[4 * j + 1] + w[4 * j + 1], v[4 * j + 2] + w[4 * j + 2], v[4 * j + 3] + w[4 * j + 3]);
       }
       umma::tc_fence_before();
       __syncwarp();
@@ -434,9 +440,9 @@ k_fwd_layer(const DCand* __restrict__ cands, int layer, int nrows, int bmax, con
 #pragma unroll
   for (int j = 0; j < NJ; ++j) z[j] = 0.f;
   for (int s = 0; s < nsplit; ++s) {
-    const float* p = part + ((long long)s * Hp + c) * NPAD;
+    const float* p = part + (long long)s * Hp * NPAD + (long long)c * 4;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) z[j] += p[lane + 32 * j];
+    for (int j = 0; j < NJ; ++j) { const int b = lane + 32 * j; z[j] += p[(long long)(b >> 2) * Hp * 4 + (b & 3)]; }
   }
   if (has_hid) {
     const float* hprev = cd.hid + (long long)(layer - 1) * bmax * H;
@@ -673,13 +679,18 @@ struct ChainCtx {
   uint32_t tm;            // TMEM accumulator (NPAD columns)
   uint32_t phase;
   bool ok;
+  long long* tl;          // debug timeline slots 10.. of this candidate (or null)
+  int tli;
 };
+__device__ __forceinline__ void chain_stamp(ChainCtx& cx, int layer) {
+  if (cx.tl && layer == 0 && threadIdx.x == 0 && cx.tli < 16) cx.tl[cx.tli++] = clock64();
+}
 
 template <int NPAD>
 __device__ __forceinline__ void chain_ctx_open(ChainCtx& cx, uint8_t* smem_raw, uint64_t* bar, uint32_t* tmem_slot, int* ok_flag) {
   const int tid = threadIdx.x, warp = tid >> 5;
   cx.smem = umma::align1024(smem_raw);
-  cx.bar = bar; cx.ok_flag = ok_flag; cx.phase = 0; cx.ok = true;
+  cx.bar = bar; cx.ok_flag = ok_flag; cx.phase = 0; cx.ok = true; cx.tl = nullptr; cx.tli = 10;
   if (warp == 0) umma::tmem_alloc(tmem_slot, NPAD);
   if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_mbar_init(); }
   umma::tc_fence_before();
@@ -722,18 +733,19 @@ __device__ __forceinline__ void chain_fwd_layer(ChainCtx& cx, const DCand& cd, i
     constexpr uint32_t idesc = umma::idesc_tf32(128, NPAD, false, false);
     for (int j0 = 0; j0 < H; j0 += PASS) {                              // passes of <= NKB k-blocks
       const int jw = min(PASS, H - j0), f4 = jw >> 2;                   // float4 per row in this pass
+      const int fsh = 31 - __clz(f4);                                   // H % 64 == 0 and PASS in {64, 128}: f4 is 16 or 32 -- no integer divisions in the staging loops
       if (j0 > 0) { chain_wait(cx); if (!cx.ok) break; }
       for (int i0 = tid; i0 < 128 * f4; i0 += THREADS * 4) {            // A: 128 rows of W
         float4 t[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * THREADS, r = i / f4, c4 = i % f4;
+          const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
           t[u] = (i < 128 * f4 && m0 + r < H) ? *reinterpret_cast<const float4*>(Wh + (long long)(m0 + r) * ly.K + j0 + c4 * 4)
                                               : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * THREADS, r = i / f4, c4 = i % f4;
+          const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
           if (i < 128 * f4) store_split(a_hi, a_lo, (uint32_t)(c4 >> 3) * A_KB + umma::sw128(r, (c4 & 7) * 16), t[u]);
         }
       }
@@ -741,13 +753,13 @@ __device__ __forceinline__ void chain_fwd_layer(ChainCtx& cx, const DCand& cd, i
         float4 t[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * THREADS, r = i / f4, c4 = i % f4;
+          const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
           t[u] = (i < NPAD * f4 && r < nrows) ? *reinterpret_cast<const float4*>(hprev + (long long)r * H + j0 + c4 * 4)
                                               : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * THREADS, r = i / f4, c4 = i % f4;
+          const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
           if (i < NPAD * f4) store_split(b_hi, b_lo, (uint32_t)(c4 >> 3) * B_KB + umma::sw128(r, (c4 & 7) * 16), t[u]);
         }
       }
@@ -785,16 +797,18 @@ __device__ __forceinline__ void chain_fwd_layer(ChainCtx& cx, const DCand& cd, i
     for (int l = 0; l < layer; ++l) item0 += tc_fwd_items(cd.layer[l].d_ske, cd.layer[l].d_rgb);
     const int nsplit = tc_fwd_items(ly.d_ske, ly.d_rgb);
     const int Hp = ((H + 127) >> 7) << 7;
-    const float* part = part_base + (long long)cand * part_stride_cand + ((long long)item0 * Hp + c) * NPAD + b0;
+    const float4* part = reinterpret_cast<const float4*>(part_base + (long long)cand * part_stride_cand + (long long)item0 * Hp * NPAD) +
+                         (long long)(b0 >> 2) * Hp + c;
     for (int s = 0; s < nsplit; ++s) {
-      const float4* p4 = reinterpret_cast<const float4*>(part + (long long)s * Hp * NPAD);
+      const float4* p4 = part + (long long)s * Hp * (NPAD / 4);
 #pragma unroll
       for (int k = 0; k < NB / 4; ++k) {
-        const float4 v = p4[k];
+        const float4 v = p4[(long long)k * Hp];
         z[4 * k] += v.x; z[4 * k + 1] += v.y; z[4 * k + 2] += v.z; z[4 * k + 3] += v.w;
       }
     }
   }
+  chain_stamp(cx, layer);          // 10: partial sums in registers
   if (has_hid) {
     chain_wait(cx);
     umma::tc_fence_after();
@@ -809,6 +823,7 @@ __device__ __forceinline__ void chain_fwd_layer(ChainCtx& cx, const DCand& cd, i
   const float bias = mine ? cd.p[ly.ob + c] : 0.f;
 #pragma unroll
   for (int b = 0; b < NB; ++b) z[b] = (mine && b0 + b < nrows) ? act_fwd(z[b] + bias, ly.act) : 0.f;   // z <- a = phi(z)
+  chain_stamp(cx, layer);          // 11: bias + activation
   float mean = 0.f, var = 1.f, istd = 1.f, gamma = 1.f, beta = 0.f;
   if (bn) {
     if (TRAIN) {
@@ -842,6 +857,7 @@ __device__ __forceinline__ void chain_fwd_layer(ChainCtx& cx, const DCand& cd, i
       if (c == 0) cd.nbt[layer] += 1;
     }
   }
+  chain_stamp(cx, layer);          // 12: BatchNorm statistics
   if (mine) {
     const uint32_t dkey = drop ? dropout_key(drop_seed, (uint32_t)cd.cand_id, step, (uint32_t)layer) : 0u;
     const float dscale = drop ? 1.f / (1.f - drop_p) : 1.f;
@@ -925,18 +941,18 @@ __device__ __forceinline__ void chain_bwd_layer(ChainCtx& cx, const DCand& cd, i
           if (i < hw * 32) store_split(a_hi, a_lo, (uint32_t)(c4 >> 3) * A_BLK + umma::sw128_b32(r, (c4 & 7) * 16), t[u]);
         }
       }
-      const int f4 = hw >> 2;
+      const int f4 = hw >> 2, fsh = 31 - __clz(f4);
       for (int i0 = tid; i0 < NPAD * f4; i0 += THREADS * 4) {          // B: batch rows of dz_{l+1}[:, h0:h0+hw]
         float4 t[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * THREADS, r = i / f4, c4 = i % f4;
+          const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
           t[u] = (i < NPAD * f4 && r < nrows) ? *reinterpret_cast<const float4*>(dzu + (long long)r * H + h0 + c4 * 4)
                                               : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * THREADS, r = i / f4, c4 = i % f4;
+          const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
           if (i < NPAD * f4) store_split(b_hi, b_lo, (uint32_t)(c4 >> 3) * B_KB + umma::sw128(r, (c4 & 7) * 16), t[u]);
         }
       }
@@ -1079,23 +1095,35 @@ k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
   const DCand& cd = cands[cand];
   const int nrows = batch.n_rows, L = cd.L, H = cd.H;
   ChainCtx cx;
+  int stamp_i = 0;
+  auto stamp = [&]() { if (err.timeline && tid == 0 && stamp_i < 16) err.timeline[cand * 16 + stamp_i] = clock64(); ++stamp_i; };
+  stamp();
   chain_ctx_open<NPAD>(cx, smem_raw, &bar, &tmem_slot, &ok_flag);
-  // L2 prefetch of what the later phases read from HBM: hidden columns of W_1.. (H rows x H floats each) and W_c
-  for (int l = 1; l < L; ++l) {
-    const DLayer& ly = cd.layer[l];
-    const float* Wh = cd.p + ly.oW + ly.d_ske + ly.d_rgb;
-    const int lines = H >> 5;                                    // 128-byte lines per row
-    for (int i = tid; i < H * lines; i += ChainCfg<NPAD>::THREADS) prefetch_l2(Wh + (long long)(i / lines) * ly.K + (i % lines) * 32);
-  }
-  for (int i = tid; i < (cd.C * H) >> 5; i += ChainCfg<NPAD>::THREADS) prefetch_l2(cd.p + cd.oWc + i * 32);
+  if (err.timeline) cx.tl = err.timeline + cand * 16;
+  chain_stamp(cx, 0);              // 10 -> (shifted: first inner stamp is "context open")
+  // L2 prefetch, one phase ahead, of what the next phase reads from HBM: the hidden columns of W_{l+1} (H rows x H
+  // floats), then W_c.  (Issued all at once at kernel start the 29 MB burst of 128 CTAs delayed the first layer by 3 us.)
+  auto prefetch_next = [&](int l) {
+    if (l < L) {
+      const DLayer& ly = cd.layer[l];
+      const float* Wh = cd.p + ly.oW + ly.d_ske + ly.d_rgb;
+      const int lsh = 31 - __clz(H >> 5) , lines = H >> 5;       // 128-byte lines per row (H in {64, 128}: 2 or 4)
+      for (int i = tid; i < H * lines; i += ChainCfg<NPAD>::THREADS) prefetch_l2(Wh + (long long)(i >> lsh) * ly.K + (i & (lines - 1)) * 32);
+    } else {
+      for (int i = tid; i < (cd.C * H) >> 5; i += ChainCfg<NPAD>::THREADS) prefetch_l2(cd.p + cd.oWc + i * 32);
+    }
+  };
 
   for (int l = 0; l < L; ++l) {
+    prefetch_next(l + 1);
     chain_fwd_layer<TRAIN, NPAD>(cx, cd, cand, l, 0, nrows, bmax, part_base, part_stride_cand, drop_seed, drop_p, step);
     umma::tc_fence_before();
     __syncthreads();                                             // h_l (global) and the TMEM reads are done
     umma::tc_fence_after();
+    stamp();
   }
   head_body<TRAIN>(cd, cand, cache, batch, bmax, hs_ld, lg_ld, adam, step_size, bc2_sqrt, ho, reinterpret_cast<float*>(cx.smem));
+  stamp();
   if (TRAIN) {
     for (int l = L - 1; l >= 0; --l) {
       __syncthreads();                                           // dh_L / dz_{l+1} (global) visible, smem tiles free
@@ -1103,6 +1131,7 @@ k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
       umma::tc_fence_before();
       __syncthreads();
       umma::tc_fence_after();
+      stamp();
     }
   }
   if (!cx.ok && tid == 0) atomicExch(err.flag, 7);

@@ -139,6 +139,7 @@ struct mfas_group {
   float* part = nullptr;          // forward partial sums [n_cand][items_fwd][Hp][npad]
   long long part_stride = 0;
   int* tc_err = nullptr;          // device flag set by a timed-out barrier wait
+  long long* timeline = nullptr;  // [n_cand][16] phase stamps of k_chain_all (debug: MFAS_CHAIN_TIMELINE=1)
   size_t smem_tc_fwd = 0, smem_tc_bwd = 0, smem_fl = 0, smem_dzx = 0, smem_chain = 0;
   BwdTile* bwd_tiles = nullptr;   // tile list of the persistent backward kernel (device), rebuilt when arenas are rebound
   std::vector<int4> bwd_tl;       // host: {cand, layer, first column, first row}
@@ -146,6 +147,8 @@ struct mfas_group {
   FwdItem* fwd_items = nullptr;   // item list of the persistent forward kernel (device), rebuilt when arenas are rebound
   int n_fwd_items = 0, fwd_ws = 1;
   bool any_alphas = false;
+  cudaEvent_t prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // mfas_group_set_profiling: around fwd / chain / bwd of a step
+  bool prof = false, prof_valid = false;
   int dbg = 0;                    // MFAS_TC_DEBUG bit 0: skip the Adam epilogue, bit 1: skip operand staging (timing experiments only)
   int chain = 2;                  // 2: fused chain kernel (H <= 128), 1: per-layer tensor-core chain kernels (MFAS_CHAIN=layers),
                                   // 0: per-layer CUDA-core chain kernels (MFAS_CHAIN=ffma)
@@ -174,7 +177,9 @@ extern "C" int mfas_group_destroy(mfas_group_t g) {
   if (g->part) cudaFree(g->part);
   if (g->bwd_tiles) cudaFree(g->bwd_tiles);
   if (g->fwd_items) cudaFree(g->fwd_items);
+  for (auto& ev : g->prof_ev) if (ev) cudaEventDestroy(ev);
   if (g->tc_err) cudaFree(g->tc_err);
+  if (g->timeline) cudaFree(g->timeline);
   delete g;
   return MFAS_OK;
 }
@@ -370,6 +375,10 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       attr((const void*)k_tc_bwd_ws<false>, TC_WS_SMEM);
       attr((const void*)k_tc_bwd_ws<true>, TC_WS_SMEM);
     }
+    if (getenv("MFAS_CHAIN_TIMELINE") && e == cudaSuccess) {
+      e = cudaMalloc(&g->timeline, sizeof(long long) * 16 * n_cand);
+      if (e == cudaSuccess) e = cudaMemset(g->timeline, 0, sizeof(long long) * 16 * n_cand);
+    }
     { const char* fe = getenv("MFAS_FWD"); if (fe && !strcmp(fe, "cta")) g->fwd_ws = 0; }
     if (g->fwd_ws) {
       int n = 0;
@@ -433,6 +442,35 @@ extern "C" int mfas_group_num_launches(mfas_group_t g, int64_t* out) {
   return MFAS_OK;
 }
 
+extern "C" int mfas_group_chain_timeline(mfas_group_t g, int64_t* out, int32_t n_cand) {
+  if (!g || !out) return fail(MFAS_ERR_INVALID, "null argument");
+  if (!g->timeline) return fail(MFAS_ERR_INVALID, "create the group with MFAS_CHAIN_TIMELINE=1");
+  DeviceGuard dg(g->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out, g->timeline, sizeof(long long) * 16 * (n_cand < g->n_cand ? n_cand : g->n_cand), cudaMemcpyDeviceToHost));
+  return MFAS_OK;
+}
+
+extern "C" int mfas_group_set_profiling(mfas_group_t g, int32_t on) {
+  if (!g) return fail(MFAS_ERR_INVALID, "null group");
+  DeviceGuard dg(g->device);
+  if (on)
+    for (auto& ev : g->prof_ev)
+      if (!ev) CUDA_TRY(cudaEventCreate(&ev));
+  g->prof = on != 0;
+  g->prof_valid = false;
+  return MFAS_OK;
+}
+
+extern "C" int mfas_group_last_step_ms(mfas_group_t g, float* ms3) {
+  if (!g || !ms3) return fail(MFAS_ERR_INVALID, "null argument");
+  if (!g->prof || !g->prof_valid) return fail(MFAS_ERR_INVALID, "no profiled train step (tensor-core engine with the fused chain, after mfas_group_set_profiling(g, 1))");
+  DeviceGuard dg(g->device);
+  CUDA_TRY(cudaEventSynchronize(g->prof_ev[3]));
+  for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventElapsedTime(&ms3[i], g->prof_ev[i], g->prof_ev[i + 1]));
+  return MFAS_OK;
+}
+
 static int sync_descriptors(mfas_group* g, cudaStream_t st) {
   for (int c = 0; c < g->n_cand; ++c)
     if (!g->bound[c]) return fail(MFAS_ERR_UNBOUND, "candidate %d has no arenas bound", c);
@@ -471,7 +509,8 @@ static int sync_descriptors(mfas_group* g, cudaStream_t st) {
               FwdItem it;
               tc_fwd_range(nkb, sp, it.kb0, it.kb1);
               it.W = d.p + ly.oW + (long long)m0 * ly.K;
-              it.part_off = (long long)c * g->part_stride + ((long long)(item0 + sp) * Hp + m0) * g->npad;
+              it.part_off = (long long)c * g->part_stride + (long long)(item0 + sp) * Hp * g->npad + 4LL * m0;
+              it.Hp = Hp; it.pad0 = it.pad1 = it.pad2 = 0;
               it.K = ly.K; it.fs_kb = ly.d_ske >> 5;
               it.ske_tap = ly.ske_tap; it.rgb_tap = ly.rgb_tap; it.cand = c;
               it.rows_valid = d.H - m0 < 128 ? d.H - m0 : 128;
@@ -525,8 +564,10 @@ static int launch_bwd_stream(mfas_group* g, const DCache& cache, const BatchRef&
 // tc engine: one launch covers the feature columns of every layer, small per-layer kernels carry the chain
 static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& batch, bool train, bool bn_train,
                           float step_size, float bc2_sqrt, uint32_t step, const HeadOut& ho, cudaStream_t st) {
-  const TcErr terr{g->tc_err};
+  const TcErr terr{g->tc_err, g->timeline};
   const dim3 gf(g->items_fwd, (g->Hmax + 127) / 128, g->n_cand), gl((g->Hmax + TC_CB - 1) / TC_CB, g->n_cand);
+  const bool prof = g->prof && train && g->chain == 2;
+  if (prof) { g->prof_valid = false; cudaEventRecord(g->prof_ev[0], st); }
   if (g->fwd_ws) {
     const int grid = g->n_fwd_items < g->n_sms ? g->n_fwd_items : g->n_sms;
     if (g->npad == 64) k_tc_fwd_ws<64><<<grid, FwdWs<64>::THREADS, FwdWs<64>::SMEM, st>>>(g->fwd_items, g->n_fwd_items, cache, batch, g->part, terr);
@@ -537,6 +578,7 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
   const dim3 gc((g->Hmax + 127) / 128, g->n_cand);
   bool keep = false;                                  // the grad arena is a test facility: all candidates or none
   for (int c = 0; c < g->n_cand; ++c) keep = keep || g->hc[c].grad != nullptr;
+  if (prof) cudaEventRecord(g->prof_ev[1], st);
   if (g->chain == 2 && train == bn_train) {           // the whole serial chain in one launch
 #define CA(T, N) k_chain_all<T, N><<<g->n_cand, ChainCfg<N>::THREADS, g->smem_chain_all, st>>>(g->dc, cache, batch, g->bmax, g->part, g->part_stride, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, ho, terr)
     if (g->npad == 64) { if (train) CA(true, 64); else CA(false, 64); }
@@ -544,7 +586,10 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
 #undef CA
     LAUNCH_CHECK(g);
     if (!train) return MFAS_OK;
-    return launch_bwd_stream(g, cache, batch, step_size, bc2_sqrt, keep, st);
+    if (prof) cudaEventRecord(g->prof_ev[2], st);
+    const int rc = launch_bwd_stream(g, cache, batch, step_size, bc2_sqrt, keep, st);
+    if (prof) { cudaEventRecord(g->prof_ev[3], st); g->prof_valid = true; }
+    return rc;
   }
   for (int l = 0; l < g->Lmax; ++l) {
 #define FL(T, N) k_fwd_layer<T, N><<<gl, TC_CHAIN_THREADS, g->smem_fl, st>>>(g->dc, l, batch.n_rows, g->bmax, g->part, g->part_stride, g->drop_seed, g->drop_p, step)
@@ -582,7 +627,7 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
 // the weight-gradient + Adam streaming kernel of a train step (all layers, all candidates)
 static int launch_bwd_stream(mfas_group* g, const DCache& cache, const BatchRef& batch, float step_size, float bc2_sqrt,
                              bool keep, cudaStream_t st) {
-  const TcErr terr{g->tc_err};
+  const TcErr terr{g->tc_err, g->timeline};
   const dim3 gb(g->items_bwd, (g->Hmax + TC_BWD_HT - 1) / TC_BWD_HT, g->n_cand);
   if (g->bwd_ws) {
     const int grid = g->n_bwd_tiles < g->n_sms ? g->n_bwd_tiles : g->n_sms;

@@ -201,6 +201,15 @@ class CandidateGroup(GroupLayout):
         _lib.check(_lib.lib().mfas_group_engine(self._h, C.byref(e)))
         return {0: "ffma", 1: "tc"}[e.value]
 
+    def set_profiling(self, on=True):
+        _lib.check(_lib.lib().mfas_group_set_profiling(self._h, 1 if on else 0))
+
+    def last_step_ms(self):
+        """Device time (ms) of the forward streaming / fused chain / backward streaming kernel of the last train step."""
+        ms = (C.c_float * 3)()
+        _lib.check(_lib.lib().mfas_group_last_step_ms(self._h, ms))
+        return [float(x) for x in ms]
+
     def check(self):
         """Synchronise and raise if a kernel reported a failure."""
         _lib.check(_lib.lib().mfas_group_status(self._h))

@@ -1,0 +1,36 @@
+"""Diagnostic (GPU box): phase timeline of the fused chain kernel, 128 cfg2 candidates, in SM clocks."""
+import os, sys, ctypes as C
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ["MFAS_CHAIN_TIMELINE"] = "1"
+import numpy as np, torch
+from mfas_b200 import _lib
+from mfas_b200.cache import synthetic_ntu_cache
+from mfas_b200.engine import CandidateGroup
+conf = [[3, 1, 1], [1, 3, 0], [1, 1, 1], [3, 3, 0]]
+M, H, B = 128, 128, 64
+train = synthetic_ntu_cache(4096, 3).to("cuda:0")
+g = CandidateGroup([conf] * M, H, 60, _lib.FLAG_BN, "cuda:0", batch_max=B)
+g.set_adam(0.9, 0.999, 1e-8, 1e-4)
+for c in range(M):
+    for name in g.names(c):
+        v = g.view(c, name)
+        if name.endswith("0.weight") or name.startswith("central"):
+            v.uniform_(-0.02, 0.02)
+        elif name.endswith("2.weight") or name.endswith("running_var"):
+            v.fill_(1.0)
+rows = torch.stack([torch.randperm(4096)[:B] for _ in range(M)]).to("cuda:0", torch.int32)
+for it in range(6):
+    g.train_step(train, rows, 1e-4)
+out = np.zeros((M, 16), np.int64)
+_lib.check(_lib.lib().mfas_group_chain_timeline(g._h, out.ctypes.data, M))
+d = np.diff(out[:, :10], axis=1)
+names = ["open+fwd0", "fwd1", "fwd2", "fwd3", "head", "bwd3", "bwd2", "bwd1", "bwd0"]
+print("phase: median / max cycles over candidates (1 us ~ 1900 cycles)")
+for i, n in enumerate(names):
+    print(f"  {n:10s} {np.median(d[:, i]):9.0f} {d[:, i].max():9.0f}")
+print("  total      %9.0f %9.0f" % (np.median(out[:, 9] - out[:, 0]), (out[:, 9] - out[:, 0]).max()))
+inner = out[:, 10:15]
+print("inside forward layer 0 (cycles since kernel start, median): ctx open %d | partials %d | activation %d | BN stats %d | (layer end %d)" % (
+    np.median(inner[:, 0] - out[:, 0]), np.median(inner[:, 1] - out[:, 0]), np.median(inner[:, 2] - out[:, 0]),
+    np.median(inner[:, 3] - out[:, 0]), np.median(out[:, 1] - out[:, 0])))
