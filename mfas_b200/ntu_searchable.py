@@ -530,6 +530,9 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
                         g.bufs[int(g.b_off[k]):int(g.b_off[k + 1])].copy_(hb[int(full.b_off[j]):int(full.b_off[j + 1])], non_blocking=True)
             lap("parameter initialisation + H2D")
             run(mine, g)
+            g.close()                       # the driver never sees the models of the direct path: free the workspace now
+            del g
+            lap("group teardown")
         elif not dev_init:
             pass   # nothing to train on this rank; RNG parity across ranks is not needed for results it never produces
     elif args.weightsharing:               # candidates are chained through state_dict: one at a time

@@ -10,7 +10,7 @@ ht, hd = synthetic_ntu_cache(10240, 1).pin(), synthetic_ntu_cache(5120, 2).pin()
 loaders = {"train": FeatureCacheLoader(ht, 64, True, 100), "dev": FeatureCacheLoader(hd, 64, True, 200)}
 args = make_args(128, 64, 3, bn=True, drpt=0.0, Ti=1)
 args.init_on_device = os.environ.get("PROBE_DEVICE_INIT") == "1"
-confs = [np.array(CONF4) for _ in range(128)]
+confs = [np.array(CONF4) for _ in range(int(os.environ.get("PROBE_M", "148")))]
 for it in range(3):
     ht.drop_device_copies(); hd.drop_device_copies()
     t0 = time.perf_counter()
