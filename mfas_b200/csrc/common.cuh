@@ -42,6 +42,7 @@ struct DCand {
   float* invstd;   // [L][H]
   float* logits;   // [Bmax][C]
   float* dsp;      // [L][MFAS_DSP_SLOTS] per-CTA partials of d(loss)/d(sigmoid(alpha_l)) (alpha gates, ffma engine)
+  float* dlog;     // [Bmax][64] dL/dlogits, zero-padded (tc engine, tensor-core head: read by the last layer's backward and by the classifier tile of k_tc_bwd_ws)
 };
 
 constexpr int MFAS_DSP_SLOTS = 128;    // >= (widest ske tap + widest rgb tap) / 32

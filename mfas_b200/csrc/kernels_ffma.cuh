@@ -217,6 +217,71 @@ struct HeadOut {
   long long stat_stride, stat_off;
 };
 
+// per-row log-softmax, NLL, argmax (first maximum), dlogits = (softmax - onehot)/n : one warp per row.
+// lg[nrows][lg_ld] (shared) holds the logits and, when TRAIN, receives dlogits in place; dlog (global, [.][64], or null)
+// receives a zero-padded copy for the tensor-core consumers.  blockDim.x == kHeadThreads, C <= 64.
+template <bool TRAIN>
+__device__ __forceinline__ void head_rows(const DCand& cd, const DCache& cache, int nrows, float* lg, int lg_ld,
+                                          float* rowloss, int* rowok, const int* lab, const int* grow, float* dlog) {
+  const int C = cd.C, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool multitask = (cd.flags & MFAS_FLAG_MULTITASK) && cache.logit_rgb && cache.logit_ske;
+  for (int r = warp; r < nrows; r += kHeadThreads / 32) {
+    float* row = lg + r * lg_ld;
+    float v0 = lane < C ? row[lane] : -INFINITY, v1 = lane + 32 < C ? row[lane + 32] : -INFINITY;
+    float mx = fmaxf(v0, v1);
+    int am = (v1 > v0) ? lane + 32 : lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+      if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
+    }
+    const float e0 = lane < C ? expf(v0 - mx) : 0.f, e1 = lane + 32 < C ? expf(v1 - mx) : 0.f;
+    const float lse = logf(warp_sum(e0 + e1));
+    const int y = lab[r];
+    float extra = 0.f;
+    if (multitask) {
+      const float* lr_ = cache.logit_rgb + (long long)grow[r] * C;
+      const float* ls_ = cache.logit_ske + (long long)grow[r] * C;
+      const float r0 = lane < C ? lr_[lane] : -INFINITY, r1 = lane + 32 < C ? lr_[lane + 32] : -INFINITY;
+      const float s0 = lane < C ? ls_[lane] : -INFINITY, s1 = lane + 32 < C ? ls_[lane + 32] : -INFINITY;
+      auto ce_of = [&](float a0, float a1) {                       // -log_softmax(a)[y], warp-wide
+        float m = fmaxf(a0, a1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float e = (lane < C ? expf(a0 - m) : 0.f) + (lane + 32 < C ? expf(a1 - m) : 0.f);
+        const float l2 = logf(warp_sum(e));
+        const float ay = __shfl_sync(0xffffffffu, y < 32 ? a0 : a1, y & 31);
+        return -((ay - m) - l2);
+      };
+      extra = ce_of(r0, r1) + ce_of(s0, s1);
+      // preds = argmax(out + visual + skeleton), first maximum (torch.max(sum(output), 1))
+      const float t0 = lane < C ? (v0 + r0) + s0 : -INFINITY, t1 = lane + 32 < C ? (v1 + r1) + s1 : -INFINITY;
+      float tm = fmaxf(t0, t1);
+      am = (t1 > t0) ? lane + 32 : lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, tm, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+        if (om > tm || (om == tm && oa < am)) { tm = om; am = oa; }
+      }
+    }
+    if (lane == 0) {
+      rowloss[r] = -((row[y] - mx) - lse) + extra;
+      rowok[r] = (am == y) ? 1 : 0;
+    }
+    __syncwarp();
+    if (TRAIN) {
+      const float inv_n = 1.f / (float)nrows;
+      const float d0 = lane < C ? (expf((v0 - mx) - lse) - (lane == y ? 1.f : 0.f)) * inv_n : 0.f;
+      const float d1 = lane + 32 < C ? (expf((v1 - mx) - lse) - (lane + 32 == y ? 1.f : 0.f)) * inv_n : 0.f;
+      if (lane < C) row[lane] = d0;
+      if (lane + 32 < C) row[lane + 32] = d1;
+      if (dlog) { dlog[r * 64 + lane] = d0; dlog[r * 64 + 32 + lane] = d1; }     // zero-padded to 64 columns
+    }
+  }
+}
+
 // body shared by k_head and the fused chain kernel (kernels_tc.cuh: k_chain_all); blockDim.x == kHeadThreads
 template <bool TRAIN>
 __device__ __forceinline__ void head_body(const DCand& cd, int cand, const DCache& cache, const BatchRef& batch, int bmax,
@@ -230,8 +295,7 @@ __device__ __forceinline__ void head_body(const DCand& cd, int cand, const DCach
   __shared__ float rowloss[MFAS_MAX_BATCH];
   __shared__ int rowok[MFAS_MAX_BATCH], lab[MFAS_MAX_BATCH], grow[MFAS_MAX_BATCH];
   // multitask (train_searchable/ntu.py:59-61): loss = CE(fusion) + CE(rgb backbone) + CE(ske backbone), preds from
-  // the sum of the three logit vectors.  The backbone logits are cached constants, so gradients are unchanged.
-  const bool multitask = (cd.flags & MFAS_FLAG_MULTITASK) && cache.logit_rgb && cache.logit_ske;
+  // the sum of the three logit vectors.  The backbone logits are cached constants, so gradients are unchanged (head_rows).
 
   const float* hl = cd.hid + (long long)(cd.L - 1) * bmax * H;
   const float* Wc = cd.p + cd.oWc;
@@ -282,59 +346,7 @@ __device__ __forceinline__ void head_body(const DCand& cd, int cand, const DCach
   }
   __syncthreads();
 
-  // per-row log-softmax, NLL, argmax (first maximum), dlogits = (softmax - onehot)/n : one warp per row
-  for (int r = warp; r < nrows; r += kHeadThreads / 32) {
-    float* row = lg + r * lg_ld;
-    float v0 = lane < C ? row[lane] : -INFINITY, v1 = lane + 32 < C ? row[lane + 32] : -INFINITY;
-    float mx = fmaxf(v0, v1);
-    int am = (v1 > v0) ? lane + 32 : lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
-      const int oa = __shfl_xor_sync(0xffffffffu, am, o);
-      if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
-    }
-    const float e0 = lane < C ? expf(v0 - mx) : 0.f, e1 = lane + 32 < C ? expf(v1 - mx) : 0.f;
-    const float lse = logf(warp_sum(e0 + e1));
-    const int y = lab[r];
-    float extra = 0.f;
-    if (multitask) {
-      const float* lr_ = cache.logit_rgb + (long long)grow[r] * C;
-      const float* ls_ = cache.logit_ske + (long long)grow[r] * C;
-      const float r0 = lane < C ? lr_[lane] : -INFINITY, r1 = lane + 32 < C ? lr_[lane + 32] : -INFINITY;
-      const float s0 = lane < C ? ls_[lane] : -INFINITY, s1 = lane + 32 < C ? ls_[lane + 32] : -INFINITY;
-      auto ce_of = [&](float a0, float a1) {                       // -log_softmax(a)[y], warp-wide
-        float m = fmaxf(a0, a1);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        const float e = (lane < C ? expf(a0 - m) : 0.f) + (lane + 32 < C ? expf(a1 - m) : 0.f);
-        const float l2 = logf(warp_sum(e));
-        const float ay = __shfl_sync(0xffffffffu, y < 32 ? a0 : a1, y & 31);
-        return -((ay - m) - l2);
-      };
-      extra = ce_of(r0, r1) + ce_of(s0, s1);
-      // preds = argmax(out + visual + skeleton), first maximum (torch.max(sum(output), 1))
-      const float t0 = lane < C ? (v0 + r0) + s0 : -INFINITY, t1 = lane + 32 < C ? (v1 + r1) + s1 : -INFINITY;
-      float tm = fmaxf(t0, t1);
-      am = (t1 > t0) ? lane + 32 : lane;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float om = __shfl_xor_sync(0xffffffffu, tm, o);
-        const int oa = __shfl_xor_sync(0xffffffffu, am, o);
-        if (om > tm || (om == tm && oa < am)) { tm = om; am = oa; }
-      }
-    }
-    if (lane == 0) {
-      rowloss[r] = -((row[y] - mx) - lse) + extra;
-      rowok[r] = (am == y) ? 1 : 0;
-    }
-    __syncwarp();
-    if (TRAIN) {
-      const float inv_n = 1.f / (float)nrows;
-      if (lane < C) row[lane] = (expf((v0 - mx) - lse) - (lane == y ? 1.f : 0.f)) * inv_n;
-      if (lane + 32 < C) row[lane + 32] = (expf((v1 - mx) - lse) - (lane + 32 == y ? 1.f : 0.f)) * inv_n;
-    }
-  }
+  head_rows<TRAIN>(cd, cache, nrows, lg, lg_ld, rowloss, rowok, lab, grow, nullptr);
   __syncthreads();
   if (tid == 0) {
     float ls = 0.f;

@@ -32,6 +32,7 @@ constexpr int TC_BWD_HT = 64;         // backward: output rows h (TMEM columns) 
 struct TcErr {
   int* flag;                          // set when a bounded barrier wait expires (never hangs the GPU)
   long long* timeline;                // optional [n_cand][16] clock64 stamps of k_chain_all's phases (MFAS_CHAIN_TIMELINE=1)
+  int l2_hints;                       // 1: the once-per-launch streams are loaded with L2 evict-first priority (MFAS_L2_HINTS=0 turns it off)
 };
 
 __host__ __device__ __forceinline__ int tc_fwd_items(int d_ske, int d_rgb) {
@@ -230,26 +231,35 @@ struct __align__(16) FwdItem {
   int Hp, pad0, pad1, pad2;       // H rounded up to 128: rows of the partial-sum tile
 };
 
-template <int NPAD> struct FwdWs {
-  static constexpr int RAW = NPAD == 64 ? 5 : 4, LO = NPAD == 64 ? 3 : 2;
+template <int NPAD, int XR = 0> struct FwdWs {     // XR: extra raw stages (XR = 1 fills the 227 KB of an SM)
+  static constexpr int RAW = (NPAD == 64 ? 5 : 4) + XR, LO = NPAD == 64 ? 3 : 2;
   static constexpr uint32_t A_BYTES = 16384, B_BYTES = NPAD * 128, TILE = A_BYTES + B_BYTES;
   static constexpr size_t SMEM = 1024 + (size_t)(RAW + LO) * TILE;
   static constexpr int LOADERS = 128, CONVERTERS = 256, THREADS = 17 * 32;
 };
 
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, bool valid) {
+// L2 eviction priority for the streams that are read exactly once per launch (weights, Adam moments, gathered feature
+// rows: >> L2 in total).  Marked evict-first they stop flushing what IS re-read out of the 126 MB L2 -- the split-K
+// partial sums between k_tc_fwd_ws and the chain, the activations / dz between the chain and k_tc_bwd_ws.
+__device__ __forceinline__ uint64_t l2_stream_policy(bool evict_first) {
+  uint64_t p;
+  if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, bool valid, uint64_t policy) {
   const int n = valid ? 16 : 0;    // src-size 0: the 16 destination bytes are zero-filled, src is not read
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst_smem), "l"(src), "r"(n), "l"(policy) : "memory");
 }
 // the mbarrier receives one arrival from this thread once all of its earlier cp.async have landed
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
 }
 
-template <int NPAD>
-__global__ void __launch_bounds__(FwdWs<NPAD>::THREADS, 1)
+template <int NPAD, int XR>
+__global__ void __launch_bounds__((FwdWs<NPAD, XR>::THREADS), 1)
 k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchRef batch, float* part_base, TcErr err) {
-  using Cfg = FwdWs<NPAD>;
+  using Cfg = FwdWs<NPAD, XR>;
   constexpr int R = Cfg::RAW, LQ = Cfg::LO;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = umma::align1024(smem_raw);
@@ -278,6 +288,7 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
     const int r = tid >> 3, c = tid & 7;                           // 16-byte chunk c of the 128-byte row
     const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);   // sw128(r + 16 j, 16 c) = off + 2048 j
     const uint32_t s0 = umma::smem_u32(smem);
+    const uint64_t stream_policy = l2_stream_policy(err.l2_hints != 0);
     int n = 0;
     for (int i = 0; i < n_my && ok; ++i) {
       const FwdItem it = items[blockIdx.x + i * gridDim.x];
@@ -298,10 +309,10 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
         const uint32_t a = s0 + sg * Cfg::TILE + off, b = a + Cfg::A_BYTES;
         const float* w = wp + 32LL * kb;
 #pragma unroll
-        for (int j = 0; j < WJ; ++j) cp_async16_zfill(a + j * 2048, w + j * wstride, r + 16 * j < it.rows_valid);
+        for (int j = 0; j < WJ; ++j) cp_async16_zfill(a + j * 2048, w + j * wstride, r + 16 * j < it.rows_valid, stream_policy);
         const bool ske = kb < it.fs_kb;
 #pragma unroll
-        for (int j = 0; j < XJ; ++j) cp_async16_zfill(b + j * 2048, (ske ? xs[j] : xr[j]) + 32LL * kb, r + 16 * j < nrows);
+        for (int j = 0; j < XJ; ++j) cp_async16_zfill(b + j * 2048, (ske ? xs[j] : xr[j]) + 32LL * kb, r + 16 * j < nrows, stream_policy);
         cp_async_arrive_noinc(&landed[sg]);
       }
     }
@@ -680,17 +691,17 @@ struct ChainCtx {
   uint32_t phase;
   bool ok;
   long long* tl;          // debug timeline slots 10.. of this candidate (or null)
-  int tli;
+  int tli, tl_layer;      // next slot; the forward layer whose inner phases are stamped
 };
 __device__ __forceinline__ void chain_stamp(ChainCtx& cx, int layer) {
-  if (cx.tl && layer == 0 && threadIdx.x == 0 && cx.tli < 16) cx.tl[cx.tli++] = clock64();
+  if (cx.tl && layer == cx.tl_layer && threadIdx.x == 0 && cx.tli < 16) cx.tl[cx.tli++] = clock64();
 }
 
 template <int NPAD>
 __device__ __forceinline__ void chain_ctx_open(ChainCtx& cx, uint8_t* smem_raw, uint64_t* bar, uint32_t* tmem_slot, int* ok_flag) {
   const int tid = threadIdx.x, warp = tid >> 5;
   cx.smem = umma::align1024(smem_raw);
-  cx.bar = bar; cx.ok_flag = ok_flag; cx.phase = 0; cx.ok = true; cx.tl = nullptr; cx.tli = 10;
+  cx.bar = bar; cx.ok_flag = ok_flag; cx.phase = 0; cx.ok = true; cx.tl = nullptr; cx.tli = 10; cx.tl_layer = 0;
   if (warp == 0) umma::tmem_alloc(tmem_slot, NPAD);
   if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_mbar_init(); }
   umma::tc_fence_before();
@@ -709,6 +720,75 @@ __device__ __forceinline__ void chain_wait(ChainCtx& cx) {      // wait for the 
   cx.phase ^= 1;
 }
 
+// accT[m, b] = sum_{j < Kd} A[m, j] X[b, j]: stage (hi/lo split) and issue, in passes of PASS columns of j.
+//   A: rows m < rows_valid of a row-major matrix with row stride ldA (rows beyond are zero), X: batch rows b < nrows, stride ldX
+// Both operands K-major SW128; the caller waits for the last commit with chain_wait().  Kd % 64 == 0.
+template <int NPAD>
+__device__ __forceinline__ void chain_mma_kmajor(ChainCtx& cx, const float* A, long long ldA, int rows_valid,
+                                                 const float* X, int ldX, int Kd, int nrows, int stamp_layer = -1) {
+  constexpr int THREADS = ChainCfg<NPAD>::THREADS;
+  constexpr uint32_t A_KB = 16384, B_KB = NPAD * 128;
+  constexpr int PASS = ChainCfg<NPAD>::PASS, NKB = ChainCfg<NPAD>::NKB;
+  const int tid = threadIdx.x;
+  uint8_t* a_hi = cx.smem;
+  uint8_t* a_lo = a_hi + NKB * A_KB;
+  uint8_t* b_hi = a_lo + NKB * A_KB;
+  uint8_t* b_lo = b_hi + NKB * B_KB;
+  const uint32_t tm = cx.tm;
+  constexpr uint32_t idesc = umma::idesc_tf32(128, NPAD, false, false);
+  for (int j0 = 0; j0 < Kd; j0 += PASS) {                             // passes of <= NKB k-blocks
+    const int jw = min(PASS, Kd - j0), f4 = jw >> 2;                  // float4 per row in this pass
+    const int fsh = 31 - __clz(f4);                                   // Kd % 64 == 0 and PASS in {64, 128}: f4 is 16 or 32 -- no integer divisions in the staging loops
+    if (j0 > 0) { chain_wait(cx); if (!cx.ok) break; }
+    for (int i0 = tid; i0 < 128 * f4; i0 += THREADS * 4) {            // A: 128 rows
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
+        t[u] = (i < 128 * f4 && r < rows_valid) ? *reinterpret_cast<const float4*>(A + (long long)r * ldA + j0 + c4 * 4)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
+        if (i < 128 * f4) store_split(a_hi, a_lo, (uint32_t)(c4 >> 3) * A_KB + umma::sw128(r, (c4 & 7) * 16), t[u]);
+      }
+    }
+    chain_stamp(cx, stamp_layer);    // 11: A staged
+    for (int i0 = tid; i0 < NPAD * f4; i0 += THREADS * 4) {           // B: batch rows
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
+        t[u] = (i < NPAD * f4 && r < nrows) ? *reinterpret_cast<const float4*>(X + (long long)r * ldX + j0 + c4 * 4)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
+        if (i < NPAD * f4) store_split(b_hi, b_lo, (uint32_t)(c4 >> 3) * B_KB + umma::sw128(r, (c4 & 7) * 16), t[u]);
+      }
+    }
+    chain_stamp(cx, stamp_layer);    // 12: B staged
+    umma::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      umma::tc_fence_after();
+      for (int ks = 0; ks < (jw >> 3); ++ks) {
+        const uint32_t oa = (uint32_t)(ks >> 2) * A_KB + (ks & 3) * 32u, ob = (uint32_t)(ks >> 2) * B_KB + (ks & 3) * 32u;
+        const uint64_t dah = umma::smem_desc(umma::smem_u32(a_hi) + oa, 16, 1024), dal = umma::smem_desc(umma::smem_u32(a_lo) + oa, 16, 1024);
+        const uint64_t dbh = umma::smem_desc(umma::smem_u32(b_hi) + ob, 16, 1024), dbl = umma::smem_desc(umma::smem_u32(b_lo) + ob, 16, 1024);
+        umma::mma_tf32(tm, dal, dbl, idesc, (j0 > 0 || ks > 0) ? 1u : 0u);
+        umma::mma_tf32(tm, dal, dbh, idesc, 1u);
+        umma::mma_tf32(tm, dah, dbl, idesc, 1u);
+        umma::mma_tf32(tm, dah, dbh, idesc, 1u);
+      }
+      umma::mma_commit(cx.bar);
+    }
+    chain_stamp(cx, stamp_layer);    // 13: MMAs issued
+  }
+}
+
 template <bool TRAIN, int NPAD>
 __device__ __forceinline__ void chain_fwd_layer(ChainCtx& cx, const DCand& cd, int cand, int layer, int m0, int nrows, int bmax,
                                                 const float* part_base, long long part_stride_cand, uint32_t drop_seed,
@@ -719,96 +799,66 @@ __device__ __forceinline__ void chain_fwd_layer(ChainCtx& cx, const DCand& cd, i
   const DLayer& ly = cd.layer[layer];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool has_hid = layer > 0;
-  constexpr uint32_t A_KB = 16384, B_KB = NPAD * 128;
-  constexpr int PASS = ChainCfg<NPAD>::PASS, NKB = ChainCfg<NPAD>::NKB;
-  uint8_t* a_hi = smem;
-  uint8_t* a_lo = a_hi + NKB * A_KB;
-  uint8_t* b_hi = a_lo + NKB * A_KB;
-  uint8_t* b_lo = b_hi + NKB * B_KB;
   const uint32_t tm = cx.tm;
-
-  if (has_hid) {
-    const float* Wh = cd.p + ly.oW + ly.d_ske + ly.d_rgb;              // hidden columns of W_l
-    const float* hprev = cd.hid + (long long)(layer - 1) * bmax * H;
-    constexpr uint32_t idesc = umma::idesc_tf32(128, NPAD, false, false);
-    for (int j0 = 0; j0 < H; j0 += PASS) {                              // passes of <= NKB k-blocks
-      const int jw = min(PASS, H - j0), f4 = jw >> 2;                   // float4 per row in this pass
-      const int fsh = 31 - __clz(f4);                                   // H % 64 == 0 and PASS in {64, 128}: f4 is 16 or 32 -- no integer divisions in the staging loops
-      if (j0 > 0) { chain_wait(cx); if (!cx.ok) break; }
-      for (int i0 = tid; i0 < 128 * f4; i0 += THREADS * 4) {            // A: 128 rows of W
-        float4 t[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
-          t[u] = (i < 128 * f4 && m0 + r < H) ? *reinterpret_cast<const float4*>(Wh + (long long)(m0 + r) * ly.K + j0 + c4 * 4)
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
-          if (i < 128 * f4) store_split(a_hi, a_lo, (uint32_t)(c4 >> 3) * A_KB + umma::sw128(r, (c4 & 7) * 16), t[u]);
-        }
-      }
-      for (int i0 = tid; i0 < NPAD * f4; i0 += THREADS * 4) {           // B: batch rows of h_{l-1}
-        float4 t[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
-          t[u] = (i < NPAD * f4 && r < nrows) ? *reinterpret_cast<const float4*>(hprev + (long long)r * H + j0 + c4 * 4)
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
-          if (i < NPAD * f4) store_split(b_hi, b_lo, (uint32_t)(c4 >> 3) * B_KB + umma::sw128(r, (c4 & 7) * 16), t[u]);
-        }
-      }
-      umma::fence_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        umma::tc_fence_after();
-        for (int ks = 0; ks < (jw >> 3); ++ks) {
-          const uint32_t oa = (uint32_t)(ks >> 2) * A_KB + (ks & 3) * 32u, ob = (uint32_t)(ks >> 2) * B_KB + (ks & 3) * 32u;
-          const uint64_t dah = umma::smem_desc(umma::smem_u32(a_hi) + oa, 16, 1024), dal = umma::smem_desc(umma::smem_u32(a_lo) + oa, 16, 1024);
-          const uint64_t dbh = umma::smem_desc(umma::smem_u32(b_hi) + ob, 16, 1024), dbl = umma::smem_desc(umma::smem_u32(b_lo) + ob, 16, 1024);
-          umma::mma_tf32(tm, dal, dbl, idesc, (j0 > 0 || ks > 0) ? 1u : 0u);
-          umma::mma_tf32(tm, dal, dbh, idesc, 1u);
-          umma::mma_tf32(tm, dah, dbl, idesc, 1u);
-          umma::mma_tf32(tm, dah, dbh, idesc, 1u);
-        }
-        umma::mma_commit(cx.bar);
-      }
-    }
-  }
-
-  // ---- epilogue: thread = (output column c = m0 + 32q + lane, batch rows [cg*NB, cg*NB+NB)), q = warp%4 (the
-  //      TMEM lane quarter this warp may read), cg = warp/4.  BatchNorm sums: per-thread partial, then a
-  //      fixed-order combine of the 4 row groups through shared memory (deterministic).
+  chain_stamp(cx, layer);          // 10: layer entered
+  // epilogue mapping: thread = (output column c = m0 + 32q + lane, batch rows [cg*NB, cg*NB+NB)), q = warp%4 (the TMEM
+  // lane quarter this warp may read), cg = warp/4.  The per-column vectors are requested first: the chain is a string of
+  // dependent HBM/L2 round trips (r01 timeline: 2-3 k cycles each), so every load that does not depend on the chain is
+  // issued at the top of its phase and lands while the operands are staged and the MMAs run.
   constexpr int NB = ChainCfg<NPAD>::NB;
   const int q = warp & 3, cg = warp >> 2, cl = q * 32 + lane, b0 = cg * NB;
   const int c = m0 + cl;
   const bool mine = c < H;
+  const bool bn = (cd.flags & MFAS_FLAG_BN) != 0;
+  const bool drop = TRAIN && (cd.flags & MFAS_FLAG_DROPOUT);
+  float bias = 0.f, gamma = 1.f, beta = 0.f, rm0 = 0.f, rv0 = 1.f;
+  long long nbt0 = 0;
+  if (TRAIN && bn && c == 0 && cg == 0) nbt0 = cd.nbt[layer];
+  if (mine) {
+    bias = cd.p[ly.ob + c];
+    if (bn) {
+      gamma = cd.p[ly.og + c]; beta = cd.p[ly.obe + c];
+      if (!TRAIN || cg == 0) { rm0 = cd.bufs[ly.orm + c]; rv0 = cd.bufs[ly.orv + c]; }
+    }
+  }
+
+  if (has_hid) {
+    const float* Wh = cd.p + ly.oW + ly.d_ske + ly.d_rgb;              // hidden columns of W_l
+    const float* hprev = cd.hid + (long long)(layer - 1) * bmax * H;
+    chain_mma_kmajor<NPAD>(cx, Wh + (long long)m0 * ly.K, ly.K, H - m0, hprev, H, H, nrows, layer);
+  }
+
+  // ---- epilogue.  BatchNorm sums: per-thread partial, then a fixed-order combine of the 4 row groups through
+  //      shared memory (deterministic).
   __shared__ float red[4][128];
   float z[NB];
 #pragma unroll
   for (int b = 0; b < NB; ++b) z[b] = 0.f;
-  if (mine) {      // feature partials of this layer (their loads fly while the MMAs run)
+  if (mine) {      // feature partials of this layer: all requested at once (they fly while the MMAs run), summed in split order
     int item0 = 0;
     for (int l = 0; l < layer; ++l) item0 += tc_fwd_items(cd.layer[l].d_ske, cd.layer[l].d_rgb);
     const int nsplit = tc_fwd_items(ly.d_ske, ly.d_rgb);
     const int Hp = ((H + 127) >> 7) << 7;
     const float4* part = reinterpret_cast<const float4*>(part_base + (long long)cand * part_stride_cand + (long long)item0 * Hp * NPAD) +
                          (long long)(b0 >> 2) * Hp + c;
-    for (int s = 0; s < nsplit; ++s) {
-      const float4* p4 = part + (long long)s * Hp * (NPAD / 4);
+    constexpr int SU = NB == 16 ? 3 : 1;           // splits in flight per round (K_feat <= 3072 -> nsplit <= 3)
+    for (int s0 = 0; s0 < nsplit; s0 += SU) {
+      float4 v[SU][NB / 4];
 #pragma unroll
-      for (int k = 0; k < NB / 4; ++k) {
-        const float4 v = p4[(long long)k * Hp];
-        z[4 * k] += v.x; z[4 * k + 1] += v.y; z[4 * k + 2] += v.z; z[4 * k + 3] += v.w;
+      for (int u = 0; u < SU; ++u) {
+        const float4* p4 = part + (long long)min(s0 + u, nsplit - 1) * Hp * (NPAD / 4);
+#pragma unroll
+        for (int k = 0; k < NB / 4; ++k) v[u][k] = p4[(long long)k * Hp];
+      }
+#pragma unroll
+      for (int u = 0; u < SU; ++u) {
+        if (s0 + u < nsplit) {
+#pragma unroll
+          for (int k = 0; k < NB / 4; ++k) { z[4 * k] += v[u][k].x; z[4 * k + 1] += v[u][k].y; z[4 * k + 2] += v[u][k].z; z[4 * k + 3] += v[u][k].w; }
+        }
       }
     }
   }
-  chain_stamp(cx, layer);          // 10: partial sums in registers
   if (has_hid) {
     chain_wait(cx);
     umma::tc_fence_after();
@@ -818,13 +868,10 @@ __device__ __forceinline__ void chain_fwd_layer(ChainCtx& cx, const DCand& cd, i
 #pragma unroll
     for (int b = 0; b < NB; ++b) z[b] += v[b];
   }
-  const bool bn = (cd.flags & MFAS_FLAG_BN) != 0;
-  const bool drop = TRAIN && (cd.flags & MFAS_FLAG_DROPOUT);
-  const float bias = mine ? cd.p[ly.ob + c] : 0.f;
 #pragma unroll
   for (int b = 0; b < NB; ++b) z[b] = (mine && b0 + b < nrows) ? act_fwd(z[b] + bias, ly.act) : 0.f;   // z <- a = phi(z)
-  chain_stamp(cx, layer);          // 11: bias + activation
-  float mean = 0.f, var = 1.f, istd = 1.f, gamma = 1.f, beta = 0.f;
+  chain_stamp(cx, layer);          // 14: partials + MMA result + bias + activation
+  float mean = 0.f, var = 1.f, istd = 1.f;
   if (bn) {
     if (TRAIN) {
       float s1 = 0.f;
@@ -841,23 +888,20 @@ __device__ __forceinline__ void chain_fwd_layer(ChainCtx& cx, const DCand& cd, i
       __syncthreads();
       var = (red[0][cl] + red[1][cl] + red[2][cl] + red[3][cl]) / (float)nrows;
     } else if (mine) {
-      mean = cd.bufs[ly.orm + c];
-      var = cd.bufs[ly.orv + c];
+      mean = rm0;
+      var = rv0;
     }
     istd = 1.f / sqrtf(var + kBnEps);
-    if (mine) { gamma = cd.p[ly.og + c]; beta = cd.p[ly.obe + c]; }
     if (TRAIN && mine && cg == 0) {
       cd.mu[layer * H + c] = mean;
       cd.invstd[layer * H + c] = istd;
       const float n = (float)nrows;
-      float& rm = cd.bufs[ly.orm + c];
-      float& rv = cd.bufs[ly.orv + c];
-      rm = (1.f - kBnMomentum) * rm + kBnMomentum * mean;
-      rv = (1.f - kBnMomentum) * rv + kBnMomentum * (var * (n / (n - 1.f)));
-      if (c == 0) cd.nbt[layer] += 1;
+      cd.bufs[ly.orm + c] = (1.f - kBnMomentum) * rm0 + kBnMomentum * mean;
+      cd.bufs[ly.orv + c] = (1.f - kBnMomentum) * rv0 + kBnMomentum * (var * (n / (n - 1.f)));
+      if (c == 0) cd.nbt[layer] = nbt0 + 1;
     }
   }
-  chain_stamp(cx, layer);          // 12: BatchNorm statistics
+  chain_stamp(cx, layer);          // 15: BatchNorm statistics
   if (mine) {
     const uint32_t dkey = drop ? dropout_key(drop_seed, (uint32_t)cd.cand_id, step, (uint32_t)layer) : 0u;
     const float dscale = drop ? 1.f / (1.f - drop_p) : 1.f;
@@ -901,87 +945,120 @@ k_chain_fwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, con
 //              A = hidden columns of W_{l+1} (MN-major: one smem row per h), B = dz_{l+1} (K-major)
 // dynamic smem (1024-aligned), per pass of PASS h: A_hi | A_lo (4 blocks x PASS rows x 128 B) | B_hi | B_lo (NKB x NPAD*128 B)
 // ---------------------------------------------------------------------------------------------
+// accT[c, b] = sum_{h < Kd} U[h, c] G[b, h]: stage (hi/lo split) and issue, in passes of PASS rows h.
+//   U: rows h < k_valid (zero beyond) of a row-major matrix with row stride ldU, columns c < mw (zero beyond);
+//   G: batch rows b < nrows with row stride ldG, readable (and zero) up to column Kd.   Kd % 64 == 0.
+// A = U as an MN-major tile (one smem row per h), B = G K-major; the caller waits for the last commit with chain_wait().
 template <int NPAD>
-__device__ __forceinline__ void chain_bwd_layer(ChainCtx& cx, const DCand& cd, int layer, int m0, int nrows, int bmax, AdamH adam,
-                                                float step_size, float bc2_sqrt, uint32_t drop_seed, float drop_p, uint32_t step) {
+__device__ __forceinline__ void chain_mma_mnmajor(ChainCtx& cx, const float* U, long long ldU, int k_valid, int Kd, int mw,
+                                                  const float* G, int ldG, int nrows) {
   constexpr int THREADS = ChainCfg<NPAD>::THREADS;
-  uint8_t* smem = cx.smem;
-  const int H = cd.H;
-  const DLayer& ly = cd.layer[layer];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool has_up = layer + 1 < cd.L;
   constexpr int PASS = ChainCfg<NPAD>::PASS, NKB = ChainCfg<NPAD>::NKB;
   constexpr uint32_t A_BLK = PASS * 128, B_KB = NPAD * 128;      // A block = 32 columns x PASS h rows
-  uint8_t* a_hi = smem;
+  const int tid = threadIdx.x;
+  uint8_t* a_hi = cx.smem;
   uint8_t* a_lo = a_hi + 4 * A_BLK;
   uint8_t* b_hi = a_lo + 4 * A_BLK;
   uint8_t* b_lo = b_hi + NKB * B_KB;
   const uint32_t tm = cx.tm;
-
-  if (has_up) {
-    const DLayer& up = cd.layer[layer + 1];
-    const float* Wu = cd.p + up.oW + up.d_ske + up.d_rgb + m0;       // W_{l+1}[h][hid m0 + .]
-    const float* dzu = cd.dzs + (long long)(layer + 1) * bmax * H;
-    const int mw = min(128, H - m0);                                   // valid output columns of this tile
-    constexpr uint32_t idesc = umma::idesc_tf32(128, NPAD, true, false);
-    for (int h0 = 0; h0 < H; h0 += PASS) {                             // passes of PASS rows of W_{l+1}
-      const int hw = min(PASS, H - h0);
-      if (h0 > 0) { chain_wait(cx); if (!cx.ok) break; }
-      for (int i0 = tid; i0 < hw * 32; i0 += THREADS * 4) {            // A: hw rows (h) x 32 float4 (128 columns)
-        float4 t[4];
+  constexpr uint32_t idesc = umma::idesc_tf32(128, NPAD, true, false);
+  for (int h0 = 0; h0 < Kd; h0 += PASS) {                            // passes of PASS rows of U
+    const int hw = min(PASS, Kd - h0);
+    if (h0 > 0) { chain_wait(cx); if (!cx.ok) break; }
+    for (int i0 = tid; i0 < hw * 32; i0 += THREADS * 4) {            // A: hw rows (h) x 32 float4 (128 columns)
+      float4 t[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * THREADS, r = i >> 5, c4 = i & 31;
-          t[u] = (i < hw * 32 && c4 * 4 < mw) ? *reinterpret_cast<const float4*>(Wu + (long long)(h0 + r) * up.K + c4 * 4)
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * THREADS, r = i >> 5, c4 = i & 31;
-          if (i < hw * 32) store_split(a_hi, a_lo, (uint32_t)(c4 >> 3) * A_BLK + umma::sw128_b32(r, (c4 & 7) * 16), t[u]);
-        }
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * THREADS, r = i >> 5, c4 = i & 31;
+        t[u] = (i < hw * 32 && c4 * 4 < mw && h0 + r < k_valid) ? *reinterpret_cast<const float4*>(U + (long long)(h0 + r) * ldU + c4 * 4)
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const int f4 = hw >> 2, fsh = 31 - __clz(f4);
-      for (int i0 = tid; i0 < NPAD * f4; i0 += THREADS * 4) {          // B: batch rows of dz_{l+1}[:, h0:h0+hw]
-        float4 t[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
-          t[u] = (i < NPAD * f4 && r < nrows) ? *reinterpret_cast<const float4*>(dzu + (long long)r * H + h0 + c4 * 4)
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
-          if (i < NPAD * f4) store_split(b_hi, b_lo, (uint32_t)(c4 >> 3) * B_KB + umma::sw128(r, (c4 & 7) * 16), t[u]);
-        }
-      }
-      umma::fence_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        umma::tc_fence_after();
-        for (int ks = 0; ks < (hw >> 3); ++ks) {
-          const uint32_t oa = ks * 1024u, ob = (uint32_t)(ks >> 2) * B_KB + (ks & 3) * 32u;
-          const uint64_t dah = umma::smem_desc(umma::smem_u32(a_hi) + oa, A_BLK, 512, umma::kLayoutSw128Base32);
-          const uint64_t dal = umma::smem_desc(umma::smem_u32(a_lo) + oa, A_BLK, 512, umma::kLayoutSw128Base32);
-          const uint64_t dbh = umma::smem_desc(umma::smem_u32(b_hi) + ob, 16, 1024), dbl = umma::smem_desc(umma::smem_u32(b_lo) + ob, 16, 1024);
-          umma::mma_tf32(tm, dal, dbl, idesc, (h0 > 0 || ks > 0) ? 1u : 0u);
-          umma::mma_tf32(tm, dal, dbh, idesc, 1u);
-          umma::mma_tf32(tm, dah, dbl, idesc, 1u);
-          umma::mma_tf32(tm, dah, dbh, idesc, 1u);
-        }
-        umma::mma_commit(cx.bar);
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * THREADS, r = i >> 5, c4 = i & 31;
+        if (i < hw * 32) store_split(a_hi, a_lo, (uint32_t)(c4 >> 3) * A_BLK + umma::sw128_b32(r, (c4 & 7) * 16), t[u]);
       }
     }
+    const int f4 = hw >> 2, fsh = 31 - __clz(f4);
+    for (int i0 = tid; i0 < NPAD * f4; i0 += THREADS * 4) {          // B: batch rows of G[:, h0:h0+hw]
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
+        t[u] = (i < NPAD * f4 && r < nrows) ? *reinterpret_cast<const float4*>(G + (long long)r * ldG + h0 + c4 * 4)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
+        if (i < NPAD * f4) store_split(b_hi, b_lo, (uint32_t)(c4 >> 3) * B_KB + umma::sw128(r, (c4 & 7) * 16), t[u]);
+      }
+    }
+    umma::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      umma::tc_fence_after();
+      for (int ks = 0; ks < (hw >> 3); ++ks) {
+        const uint32_t oa = ks * 1024u, ob = (uint32_t)(ks >> 2) * B_KB + (ks & 3) * 32u;
+        const uint64_t dah = umma::smem_desc(umma::smem_u32(a_hi) + oa, A_BLK, 512, umma::kLayoutSw128Base32);
+        const uint64_t dal = umma::smem_desc(umma::smem_u32(a_lo) + oa, A_BLK, 512, umma::kLayoutSw128Base32);
+        const uint64_t dbh = umma::smem_desc(umma::smem_u32(b_hi) + ob, 16, 1024), dbl = umma::smem_desc(umma::smem_u32(b_lo) + ob, 16, 1024);
+        umma::mma_tf32(tm, dal, dbl, idesc, (h0 > 0 || ks > 0) ? 1u : 0u);
+        umma::mma_tf32(tm, dal, dbh, idesc, 1u);
+        umma::mma_tf32(tm, dah, dbl, idesc, 1u);
+        umma::mma_tf32(tm, dah, dbh, idesc, 1u);
+      }
+      umma::mma_commit(cx.bar);
+    }
   }
+}
 
-  // ---- epilogue: thread = (column c = m0 + 32q + lane of layer l, batch rows [cg*NB, cg*NB+NB)) ----------
+constexpr int TC_DLOG_LD = 64;        // row stride of DCand::dlog (dL/dlogits, zero-padded): the K extent of the classifier "layer"
+
+// head_up: the classifier is the "upper layer" of the last fusion step (dh_L = dlogits W_c on the tensor core, with
+// dlogits in cd.dlog as k_chain_all's head leaves it); otherwise the last layer takes dh from k_head.
+template <int NPAD>
+__device__ __forceinline__ void chain_bwd_layer(ChainCtx& cx, const DCand& cd, int layer, int m0, int nrows, int bmax, AdamH adam,
+                                                float step_size, float bc2_sqrt, uint32_t drop_seed, float drop_p, uint32_t step,
+                                                bool head_up = false) {
+  const int H = cd.H;
+  const DLayer& ly = cd.layer[layer];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool inner = layer + 1 < cd.L;
+  const bool has_up = inner || head_up;
+  const uint32_t tm = cx.tm;
+  // epilogue mapping and early requests (see chain_fwd_layer): thread = (column c = m0 + 32q + lane of layer l, batch
+  // rows [cg*NB, cg*NB+NB)); the statistics of the forward pass and, for the row group that applies them, the Adam
+  // state of b / gamma / beta are on their way while the operands are staged
   constexpr int NB = ChainCfg<NPAD>::NB;
   const int q = warp & 3, cg = warp >> 2, cl = q * 32 + lane, b0 = cg * NB;
   const int c = m0 + cl;
   const bool mine = c < H;
   const bool bn = (cd.flags & MFAS_FLAG_BN) != 0;
   const bool drop = (cd.flags & MFAS_FLAG_DROPOUT) != 0;
+  float mu = 0.f, istd = 1.f, gam = 1.f;
+  float pb = 0.f, mb = 0.f, vb = 0.f, mg = 0.f, vg = 0.f, pe = 0.f, me = 0.f, ve = 0.f;
+  if (mine) {
+    if (bn) { mu = cd.mu[layer * H + c]; istd = cd.invstd[layer * H + c]; gam = cd.p[ly.og + c]; }
+    if (cg == 0) {
+      pb = cd.p[ly.ob + c]; mb = cd.m[ly.ob + c]; vb = cd.v[ly.ob + c];
+      if (bn) { mg = cd.m[ly.og + c]; vg = cd.v[ly.og + c]; pe = cd.p[ly.obe + c]; me = cd.m[ly.obe + c]; ve = cd.v[ly.obe + c]; }
+    }
+  }
+
+  if (has_up) {
+    const int mw = min(128, H - m0);                                   // valid output columns of this tile
+    if (inner) {
+      const DLayer& up = cd.layer[layer + 1];
+      const float* Wu = cd.p + up.oW + up.d_ske + up.d_rgb + m0;       // W_{l+1}[h][hid m0 + .]
+      const float* dzu = cd.dzs + (long long)(layer + 1) * bmax * H;
+      chain_mma_mnmajor<NPAD>(cx, Wu, up.K, H, H, mw, dzu, H, nrows);
+    } else {
+      chain_mma_mnmajor<NPAD>(cx, cd.p + cd.oWc + m0, H, cd.C, TC_DLOG_LD, mw, cd.dlog, TC_DLOG_LD, nrows);
+    }
+  }
+
+  // ---- epilogue: thread = (column c = m0 + 32q + lane of layer l, batch rows [cg*NB, cg*NB+NB)) ----------
   __shared__ float red1[4][128], red2[4][128];
   float av[NB], dh[NB];
 #pragma unroll
@@ -1009,9 +1086,8 @@ __device__ __forceinline__ void chain_bwd_layer(ChainCtx& cx, const DCand& cd, i
     for (int b = 0; b < NB; ++b)
       if (b0 + b < nrows) dh[b] = dropout_keep(dkey, (uint32_t)((b0 + b) * H + c), drop_p) ? dh[b] * dscale : 0.f;
   }
-  float mu = 0.f, istd = 1.f, gam = 1.f, S1 = 0.f, S2 = 0.f;
+  float S1 = 0.f, S2 = 0.f;
   if (bn) {
-    if (mine) { mu = cd.mu[layer * H + c]; istd = cd.invstd[layer * H + c]; gam = cd.p[ly.og + c]; }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int b = 0; b < NB; ++b) if (b0 + b < nrows) { s1 += dh[b]; s2 = fmaf(dh[b], (av[b] - mu) * istd, s2); }
@@ -1041,14 +1117,13 @@ __device__ __forceinline__ void chain_bwd_layer(ChainCtx& cx, const DCand& cd, i
   __syncthreads();
   if (mine && cg == 0) {
     db = red1[0][cl] + red1[1][cl] + red1[2][cl] + red1[3][cl];
-    auto upd = [&](long long o, float g) {
+    auto upd = [&](long long o, float g, float p, float m, float v) {
       if (cd.grad) cd.grad[o] = g;
-      float p = cd.p[o], m = cd.m[o], v = cd.v[o];
       adam_update(g, p, m, v, adam, step_size, bc2_sqrt);
       cd.p[o] = p; cd.m[o] = m; cd.v[o] = v;
     };
-    upd(ly.ob + c, db);
-    if (bn) { upd(ly.og + c, S2); upd(ly.obe + c, S1); }
+    upd(ly.ob + c, db, pb, mb, vb);
+    if (bn) { upd(ly.og + c, S2, gam, mg, vg); upd(ly.obe + c, S1, pe, me, ve); }
   }
 }
 
@@ -1081,7 +1156,87 @@ k_chain_bwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, Ada
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// Row-wise state of the head shared between its phases (static shared memory of k_chain_all)
+struct HeadRows {
+  float rowloss[MFAS_MAX_BATCH];
+  int rowok[MFAS_MAX_BATCH], lab[MFAS_MAX_BATCH], grow[MFAS_MAX_BATCH];
+};
+
+// The classifier head on the tensor core (C <= 64, H <= 128, one CTA per candidate):
+//   logitsT[c, b] = sum_h W_c[c, h] h_L[b, h]   -- the forward-chain MMA with W_c as a 128-row tile (rows >= C zero)
+//   -> + b_c -> shared lg[b][c] -> head_rows (softmax-CE, argmax, dlogits) -> dlogits to cd.dlog (zero-padded)
+//   -> loss / accuracy statistics, gradient + Adam of b_c.
+// What the CUDA-core head did after that is not on the chain any more: dh_L = dlogits W_c is the "upper layer" MMA of
+// the last fusion step's backward (chain_bwd_layer, head_up), and dW_c = dlogits^T h_L with its Adam step is one more
+// tile of the weight-streaming kernel (k_tc_bwd_ws, layer index L).  (r01 timeline: the CUDA-core head was 86 k of the
+// chain's 280 k cycles -- shared-memory bandwidth on dh/dW_c and the p/m/v round trip of W_c.)
 template <bool TRAIN, int NPAD>
+__device__ __forceinline__ void chain_head_tc(ChainCtx& cx, const DCand& cd, int cand, const DCache& cache, const BatchRef& batch,
+                                              int bmax, const AdamH& adam, float step_size, float bc2_sqrt, const HeadOut& out,
+                                              HeadRows& hr) {
+  constexpr int NB = ChainCfg<NPAD>::NB, LG_LD = TC_DLOG_LD;
+  const int H = cd.H, C = cd.C, nrows = batch.n_rows, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, cg = warp >> 2, c = q * 32 + lane, b0 = cg * NB;
+  const bool mine = c < C;
+  const float bias = mine ? cd.p[cd.obc + c] : 0.f;
+  // classifier-bias Adam state for the threads that will apply it (warps 2-3), requested now
+  const int cb = tid - 64;
+  const bool bias_thread = TRAIN && cb >= 0 && cb < C;
+  float pbc = 0.f, mbc = 0.f, vbc = 0.f;
+  if (bias_thread) { pbc = cd.p[cd.obc + cb]; mbc = cd.m[cd.obc + cb]; vbc = cd.v[cd.obc + cb]; }
+
+  const float* hl = cd.hid + (long long)(cd.L - 1) * bmax * H;
+  chain_mma_kmajor<NPAD>(cx, cd.p + cd.oWc, H, C, hl, H, H, nrows);
+  chain_wait(cx);
+  umma::tc_fence_after();
+  float v[NB];
+  if (NB == 16) umma::tmem_ld16(cx.tm + ((uint32_t)(q * 32) << 16) + b0, v);
+  else umma::tmem_ld32(cx.tm + ((uint32_t)(q * 32) << 16) + b0, v);
+  float* lg = reinterpret_cast<float*>(cx.smem);          // [nrows][LG_LD]; the operand tiles are free (MMAs complete)
+  if (mine) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      if (b0 + b < nrows) {
+        const float s = v[b] + bias;
+        lg[(b0 + b) * LG_LD + c] = s;
+        cd.logits[(b0 + b) * C + c] = s;
+        if (out.logits) out.logits[((long long)cand * bmax + b0 + b) * C + c] = s;
+      }
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  head_rows<TRAIN>(cd, cache, nrows, lg, LG_LD, hr.rowloss, hr.rowok, hr.lab, hr.grow, TRAIN ? cd.dlog : nullptr);
+  __syncthreads();
+  if (warp == 0) {                                         // batch statistics: fixed-order tree (deterministic)
+    float ls = 0.f;
+    int ok = 0;
+    for (int r = lane; r < nrows; r += 32) { ls += hr.rowloss[r]; ok += hr.rowok[r]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ls += __shfl_xor_sync(0xffffffffu, ls, o); ok += __shfl_xor_sync(0xffffffffu, ok, o); }
+    if (lane == 0) {
+      const float mean_loss = ls / (float)nrows;                    // CrossEntropyLoss(reduction='mean')
+      if (out.loss) out.loss[cand] = mean_loss;
+      if (out.correct) out.correct[cand] = ok;
+      if (out.stats) {                                              // running_loss += loss.item()*B (ntu.py:72-73)
+        double* st = out.stats + (long long)cand * out.stat_stride + out.stat_off;
+        st[0] += (double)mean_loss * (double)nrows;
+        st[1] += (double)ok;
+      }
+    }
+  }
+  if (bias_thread) {                                       // db_c = sum_b dlogits, in row order
+    float g = 0.f;
+    for (int b = 0; b < nrows; ++b) g += lg[b * LG_LD + cb];
+    const long long o = cd.obc + cb;
+    if (cd.grad) cd.grad[o] = g;
+    adam_update(g, pbc, mbc, vbc, adam, step_size, bc2_sqrt);
+    cd.p[o] = pbc; cd.m[o] = mbc; cd.v[o] = vbc;
+  }
+}
+
+template <bool TRAIN, int NPAD, bool TCHEAD>
 __global__ void __launch_bounds__(ChainCfg<NPAD>::THREADS)
 k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, const float* part_base,
             long long part_stride_cand, int hs_ld, int lg_ld, AdamH adam, float step_size, float bc2_sqrt,
@@ -1091,16 +1246,31 @@ k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   __shared__ int ok_flag;
+  __shared__ DCand scd;            // this candidate's descriptor: every field access below is an LDS, not a dependent global load
+  __shared__ HeadRows hr;
   const int cand = blockIdx.x, tid = threadIdx.x;
-  const DCand& cd = cands[cand];
-  const int nrows = batch.n_rows, L = cd.L, H = cd.H;
+  {
+    static_assert(sizeof(DCand) % 4 == 0, "DCand is copied as words");
+    const int* src = reinterpret_cast<const int*>(cands + cand);
+    int* dst = reinterpret_cast<int*>(&scd);
+    for (int i = tid; i < (int)(sizeof(DCand) / 4); i += ChainCfg<NPAD>::THREADS) dst[i] = src[i];
+  }
+  const int nrows = batch.n_rows;
+  if (TCHEAD) {                    // labels of this batch: two dependent loads that nothing on the chain has to wait for
+    for (int r = tid; r < nrows; r += ChainCfg<NPAD>::THREADS) {
+      const int gr = batch_row(batch, cand, r);
+      hr.grow[r] = gr;
+      hr.lab[r] = (int)cache.labels[gr];
+    }
+  }
   ChainCtx cx;
   int stamp_i = 0;
   auto stamp = [&]() { if (err.timeline && tid == 0 && stamp_i < 16) err.timeline[cand * 16 + stamp_i] = clock64(); ++stamp_i; };
   stamp();
-  chain_ctx_open<NPAD>(cx, smem_raw, &bar, &tmem_slot, &ok_flag);
-  if (err.timeline) cx.tl = err.timeline + cand * 16;
-  chain_stamp(cx, 0);              // 10 -> (shifted: first inner stamp is "context open")
+  chain_ctx_open<NPAD>(cx, smem_raw, &bar, &tmem_slot, &ok_flag);      // (__syncthreads inside: scd is visible)
+  const DCand& cd = scd;
+  const int L = cd.L, H = cd.H;
+  if (err.timeline) { cx.tl = err.timeline + cand * 16; cx.tl_layer = L > 1 ? 1 : 0; }
   // L2 prefetch, one phase ahead, of what the next phase reads from HBM: the hidden columns of W_{l+1} (H rows x H
   // floats), then W_c.  (Issued all at once at kernel start the 29 MB burst of 128 CTAs delayed the first layer by 3 us.)
   auto prefetch_next = [&](int l) {
@@ -1122,12 +1292,13 @@ k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
     umma::tc_fence_after();
     stamp();
   }
-  head_body<TRAIN>(cd, cand, cache, batch, bmax, hs_ld, lg_ld, adam, step_size, bc2_sqrt, ho, reinterpret_cast<float*>(cx.smem));
+  if (TCHEAD) chain_head_tc<TRAIN, NPAD>(cx, cd, cand, cache, batch, bmax, adam, step_size, bc2_sqrt, ho, hr);
+  else head_body<TRAIN>(cd, cand, cache, batch, bmax, hs_ld, lg_ld, adam, step_size, bc2_sqrt, ho, reinterpret_cast<float*>(cx.smem));
   stamp();
   if (TRAIN) {
     for (int l = L - 1; l >= 0; --l) {
-      __syncthreads();                                           // dh_L / dz_{l+1} (global) visible, smem tiles free
-      chain_bwd_layer<NPAD>(cx, cd, l, 0, nrows, bmax, adam, step_size, bc2_sqrt, drop_seed, drop_p, step);
+      __syncthreads();                                           // dlogits / dh_L / dz_{l+1} (global) visible, smem tiles free
+      chain_bwd_layer<NPAD>(cx, cd, l, 0, nrows, bmax, adam, step_size, bc2_sqrt, drop_seed, drop_p, step, TCHEAD);
       umma::tc_fence_before();
       __syncthreads();
       umma::tc_fence_after();
@@ -1313,16 +1484,16 @@ k_tc_bwd_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int 
 struct __align__(16) BwdTile {
   float* W;                       // &params[oW + h0 * K + kc0]
   long long moff, voff, goff;     // adam_m - params, adam_v - params, grad - params (floats; goff 0 when no grad arena)
-  int K, kw, pad0, pad1;
-  int cand, layer, kc0, h0;       // 16-byte aligned: the stagers read these four as one int4
+  int K, kw, rows, pad1;          // rows: valid rows of the 64 (64 for a fusion layer, C for the classifier tile)
+  int cand, layer, kc0, h0;       // 16-byte aligned: the stagers read these four as one int4 (layer == L: the classifier)
 };
 constexpr int TC_WS_THREADS = 17 * 32;
 constexpr int WS_RING = 4;                              // ring slots per Adam warp (= batches per tile)
 constexpr int WS_SLOT = 3 * 8 * 128;                    // bytes: 3 arrays x 8 rows x 32 floats
 constexpr size_t TC_WS_SMEM = 1024 + 98304 + 8 * (size_t)WS_RING * WS_SLOT;
 
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -1362,15 +1533,21 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
     auto fetch_desc = [&](int i, Desc& d) {
       const int4 t = *reinterpret_cast<const int4*>(&tiles[blockIdx.x + i * gridDim.x].cand);   // {cand, layer, kc0, h0}
       const DCand& cd = cands[t.x];
-      const DLayer& ly = cd.layer[t.y];
       const int H = cd.H, kc0 = t.z;
-      const int fs = ly.d_ske, fr = ly.d_rgb;
       bool gather = true;
-      if (kc0 < fs) { d.src = cache.ske[ly.ske_tap] + kc0; d.ld = cache.ske_ld[ly.ske_tap]; }
-      else if (kc0 < fs + fr) { d.src = cache.rgb[ly.rgb_tap] + (kc0 - fs); d.ld = cache.rgb_ld[ly.rgb_tap]; }
-      else { d.src = cd.hid + (long long)(t.y - 1) * bmax * H + (kc0 - fs - fr); d.ld = H; gather = false; }
-      d.H = H; d.kw = min(TC_BWD_KT, ly.K - kc0);
-      d.dz = cd.dzs + (long long)t.y * bmax * H + t.w;
+      if (t.y >= cd.L) {                                // the classifier as one more layer: x = h_L, dz = dlogits (zero-padded to 64 classes)
+        d.src = cd.hid + (long long)(cd.L - 1) * bmax * H + kc0; d.ld = H; gather = false;
+        d.H = TC_DLOG_LD; d.kw = min(TC_BWD_KT, H - kc0);
+        d.dz = cd.dlog;
+      } else {
+        const DLayer& ly = cd.layer[t.y];
+        const int fs = ly.d_ske, fr = ly.d_rgb;
+        if (kc0 < fs) { d.src = cache.ske[ly.ske_tap] + kc0; d.ld = cache.ske_ld[ly.ske_tap]; }
+        else if (kc0 < fs + fr) { d.src = cache.rgb[ly.rgb_tap] + (kc0 - fs); d.ld = cache.rgb_ld[ly.rgb_tap]; }
+        else { d.src = cd.hid + (long long)(t.y - 1) * bmax * H + (kc0 - fs - fr); d.ld = H; gather = false; }
+        d.H = H; d.kw = min(TC_BWD_KT, ly.K - kc0);
+        d.dz = cd.dzs + (long long)t.y * bmax * H + t.w;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {                     // rows warp, warp+8, ...: one index per warp and j
         const int r = min(warp + 8 * j, nrows - 1);
@@ -1447,7 +1624,8 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
     uint8_t* ring = smem + STAGE + (size_t)aw * WS_RING * WS_SLOT;
     const uint32_t ring_u32 = umma::smem_u32(ring);
     const int srow = lane >> 3, schunk = lane & 7;     // cp.async: a lane moves 16 B of row (4*u + srow)
-    struct Tile { float* W; long long K, moff, voff, goff; bool valid; };
+    const uint64_t stream_policy = l2_stream_policy(err.l2_hints != 0);
+    struct Tile { float* W; long long K, moff, voff, goff; bool valid; int rows; };   // rows: valid rows of this warp's 32 (64-row tiles: 32; the classifier tile: C - 32 cg, clamped)
     struct Raw { int4 a, b, c; };                      // first 48 bytes of a BwdTile
     auto fetch_raw = [&](int i) {
       const int4* r = reinterpret_cast<const int4*>(&tiles[blockIdx.x + i * gridDim.x]);
@@ -1462,6 +1640,7 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
       o.goff = KEEP_GRAD ? (((long long)(uint32_t)r.b.w << 32) | (uint32_t)r.b.z) : 0;
       o.K = r.c.x;
       o.valid = q * 32 < r.c.y;
+      o.rows = min(32, max(0, r.c.z - cg * 32));
       o.W = reinterpret_cast<float*>(Wbits) + (long long)(cg * 32) * o.K + q * 32;   // first row / column of this warp
       return o;
     };
@@ -1472,10 +1651,12 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
         const float* w = t.W + (long long)(8 * j + srow) * t.K + schunk * 4;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const float* wu = w + (long long)(4 * u) * t.K;
-          cp_async16(dst + u * 512, wu);
-          cp_async16(dst + 1024 + u * 512, wu + t.moff);
-          cp_async16(dst + 2048 + u * 512, wu + t.voff);
+          if (8 * j + 4 * u + srow < t.rows) {
+            const float* wu = w + (long long)(4 * u) * t.K;
+            cp_async16(dst + u * 512, wu, stream_policy);
+            cp_async16(dst + 1024 + u * 512, wu + t.moff, stream_policy);
+            cp_async16(dst + 2048 + u * 512, wu + t.voff, stream_policy);
+          }
         }
       }
       cp_async_commit();
@@ -1509,11 +1690,22 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
           for (int r = 0; r < 8; ++r) { p[r] = sp[r * 32]; m[r] = sp[256 + r * 32]; v[r] = sp[512 + r * 32]; }
 #pragma unroll
           for (int r = 0; r < 8; ++r) adam_update_fast(g[r], p[r], m[r], v[r], adam, step_size, inv_bc2);
+          if (8 * j + 8 <= cur.rows) {                 // (always, except in the classifier tile)
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            if (KEEP_GRAD) w[cur.goff] = g[r];
-            w[0] = p[r]; w[cur.moff] = m[r]; w[cur.voff] = v[r];
-            w += cur.K;
+            for (int r = 0; r < 8; ++r) {
+              if (KEEP_GRAD) w[cur.goff] = g[r];
+              w[0] = p[r]; w[cur.moff] = m[r]; w[cur.voff] = v[r];
+              w += cur.K;
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              if (8 * j + r < cur.rows) {
+                if (KEEP_GRAD) w[cur.goff] = g[r];
+                w[0] = p[r]; w[cur.moff] = m[r]; w[cur.voff] = v[r];
+              }
+              w += cur.K;
+            }
           }
         }
         __syncwarp();                                  // every lane has read slot j before it is refilled

@@ -143,10 +143,12 @@ struct mfas_group {
   size_t smem_tc_fwd = 0, smem_tc_bwd = 0, smem_fl = 0, smem_dzx = 0, smem_chain = 0;
   BwdTile* bwd_tiles = nullptr;   // tile list of the persistent backward kernel (device), rebuilt when arenas are rebound
   std::vector<int4> bwd_tl;       // host: {cand, layer, first column, first row}
-  int n_bwd_tiles = 0, n_sms = 148, bwd_ws = 1;
+  int n_bwd_tiles = 0, n_bwd_layer_tiles = 0, n_sms = 148, bwd_ws = 1;
   FwdItem* fwd_items = nullptr;   // item list of the persistent forward kernel (device), rebuilt when arenas are rebound
-  int n_fwd_items = 0, fwd_ws = 1;
+  int n_fwd_items = 0, fwd_ws = 1, fwd_xr = 0;
   bool any_alphas = false;
+  int l2_hints = 1;
+  bool tchead = false;            // classifier head on the tensor core inside k_chain_all (+ its dW as a k_tc_bwd_ws tile)
   cudaEvent_t prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // mfas_group_set_profiling: around fwd / chain / bwd of a step
   bool prof = false, prof_valid = false;
   int dbg = 0;                    // MFAS_TC_DEBUG bit 0: skip the Adam epilogue, bit 1: skip operand staging (timing experiments only)
@@ -211,7 +213,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
   auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
   size_t total = 0;
   std::vector<size_t> base(n_cand);
-  struct Off { size_t act, hid, dh, dz, dzs, mu, invstd, logits, dsp, best_p, best_bufs, best_nbt; };
+  struct Off { size_t act, hid, dh, dz, dzs, mu, invstd, logits, dsp, dlog, best_p, best_bufs, best_nbt; };
   std::vector<Off> off(n_cand);
   for (int c = 0; c < n_cand; ++c) {
     const mfas_layout& l = g->lay[c];
@@ -235,6 +237,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     o.invstd = total; total += up((size_t)l.L * l.H * sizeof(float));
     o.logits = total; total += up((size_t)batch_max * l.C * sizeof(float));
     o.dsp = total; total += up((size_t)MFAS_MAX_LAYERS * MFAS_DSP_SLOTS * sizeof(float));
+    o.dlog = total; total += up((size_t)batch_max * TC_DLOG_LD * sizeof(float));
     o.best_p = total; total += up((size_t)l.n_params * sizeof(float));
     o.best_bufs = total; total += up((size_t)l.n_bufs * sizeof(float));
     o.best_nbt = total; total += up((size_t)MFAS_MAX_LAYERS * sizeof(long long));
@@ -267,7 +270,8 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     const Off& o = off[c];
     d.act = (float*)(g->ws + o.act); d.hid = (float*)(g->ws + o.hid); d.dh = (float*)(g->ws + o.dh);
     d.dz = (float*)(g->ws + o.dz); d.dzs = (float*)(g->ws + o.dzs); d.mu = (float*)(g->ws + o.mu); d.invstd = (float*)(g->ws + o.invstd);
-    d.logits = (float*)(g->ws + o.logits); d.dsp = (float*)(g->ws + o.dsp); d.best_p = (float*)(g->ws + o.best_p);
+    d.logits = (float*)(g->ws + o.logits); d.dsp = (float*)(g->ws + o.dsp); d.dlog = (float*)(g->ws + o.dlog);
+    d.best_p = (float*)(g->ws + o.best_p);
     d.best_bufs = (float*)(g->ws + o.best_bufs); d.best_nbt = (long long*)(g->ws + o.best_nbt);
   }
   // dynamic shared memory of the two big-smem kernels
@@ -356,19 +360,29 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     g->smem_chain_all = g->smem_chain > 1024 + g->smem_head ? g->smem_chain : 1024 + g->smem_head;
     if (g->smem_chain_all > 227 * 1024 && g->chain == 2) g->chain = 1;
     if (g->chain == 2) {
-      attr((const void*)k_chain_all<true, 64>, g->smem_chain_all);
-      attr((const void*)k_chain_all<false, 64>, g->smem_chain_all);
-      attr((const void*)k_chain_all<true, 128>, g->smem_chain_all);
-      attr((const void*)k_chain_all<false, 128>, g->smem_chain_all);
+      attr((const void*)k_chain_all<true, 64, false>, g->smem_chain_all);
+      attr((const void*)k_chain_all<false, 64, false>, g->smem_chain_all);
+      attr((const void*)k_chain_all<true, 128, false>, g->smem_chain_all);
+      attr((const void*)k_chain_all<false, 128, false>, g->smem_chain_all);
+      attr((const void*)k_chain_all<true, 64, true>, g->smem_chain_all);
+      attr((const void*)k_chain_all<false, 64, true>, g->smem_chain_all);
     }
     { const char* be = getenv("MFAS_BWD"); if (be && !strcmp(be, "cta")) g->bwd_ws = 0; }
     if (g->npad != 64) g->bwd_ws = 0;                   // the persistent kernel is sized for batch <= 64 (96 KB operand stage + p/m/v rings)
+    // tensor-core head: needs the fused chain (its tiles and TMEM), the persistent backward (the classifier's dW + Adam
+    // become one of its tiles) and C <= 64 (one 64-row tile; head_rows' two values per lane)
+    g->tchead = g->chain == 2 && g->bwd_ws && g->Cmax <= TC_DLOG_LD;
+    { const char* he = getenv("MFAS_HEAD"); if (he && !strcmp(he, "ffma")) g->tchead = false; }
     if (g->bwd_ws) {
       std::vector<int4> tl;
       for (int c = 0; c < n_cand; ++c)
         for (int l = 0; l < g->lay[c].L; ++l)
           for (int kc0 = 0; kc0 < g->lay[c].K[l]; kc0 += TC_BWD_KT)
             for (int h0 = 0; h0 < g->lay[c].H; h0 += TC_BWD_HT) tl.push_back(make_int4(c, l, kc0, h0));
+      g->n_bwd_layer_tiles = (int)tl.size();
+      if (g->tchead)                                    // classifier tiles last: a step that ran k_head instead simply stops short of them
+        for (int c = 0; c < n_cand; ++c)
+          for (int kc0 = 0; kc0 < g->lay[c].H; kc0 += TC_BWD_KT) tl.push_back(make_int4(c, g->lay[c].L, kc0, 0));
       g->n_bwd_tiles = (int)tl.size();
       if (e == cudaSuccess) e = cudaMalloc(&g->bwd_tiles, sizeof(BwdTile) * tl.size());
       g->bwd_tl = std::move(tl);
@@ -387,10 +401,14 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
           n += tc_fwd_items(g->lay[c].d_ske[l], g->lay[c].d_rgb[l]) * ((g->lay[c].H + 127) / 128);
       g->n_fwd_items = n;
       if (e == cudaSuccess) e = cudaMalloc(&g->fwd_items, sizeof(FwdItem) * n);
-      attr((const void*)k_tc_fwd_ws<64>, FwdWs<64>::SMEM);
-      attr((const void*)k_tc_fwd_ws<128>, FwdWs<128>::SMEM);
+      attr((const void*)k_tc_fwd_ws<64, 0>, FwdWs<64, 0>::SMEM);
+      attr((const void*)k_tc_fwd_ws<128, 0>, FwdWs<128, 0>::SMEM);
+      attr((const void*)k_tc_fwd_ws<64, 1>, FwdWs<64, 1>::SMEM);
+      attr((const void*)k_tc_fwd_ws<128, 1>, FwdWs<128, 1>::SMEM);
+      { const char* xe = getenv("MFAS_FWD_XR"); if (xe) g->fwd_xr = atoi(xe) ? 1 : 0; }
     }
     { const char* de = getenv("MFAS_TC_DEBUG"); if (de) g->dbg = atoi(de); }
+    { const char* le = getenv("MFAS_L2_HINTS"); if (le) g->l2_hints = atoi(le) ? 1 : 0; }
     if (e != cudaSuccess) {
       int code = fail(MFAS_ERR_CUDA, "tc engine setup: %s", cudaGetErrorString(e));
       mfas_group_destroy(g);
@@ -482,13 +500,18 @@ static int sync_descriptors(mfas_group* g, cudaStream_t st) {
       for (size_t i = 0; i < recs.size(); ++i) {
         const int4 t = g->bwd_tl[i];
         const DCand& d = g->hc[t.x];
-        const DLayer& ly = d.layer[t.y];
         BwdTile& r = recs[i];
-        r.W = d.p + ly.oW + (long long)t.w * ly.K + t.z;
         r.moff = (long long)(d.m - d.p); r.voff = (long long)(d.v - d.p);
         r.goff = d.grad ? (long long)(d.grad - d.p) : 0;
-        r.K = ly.K; r.kw = ly.K - t.z < TC_BWD_KT ? ly.K - t.z : TC_BWD_KT;
-        r.cand = t.x; r.layer = t.y; r.kc0 = t.z; r.h0 = t.w; r.pad0 = r.pad1 = 0;
+        if (t.y >= d.L) {                               // classifier tile (tensor-core head): W_c [C][H], columns t.z..
+          r.W = d.p + d.oWc + t.z;
+          r.K = d.H; r.kw = d.H - t.z < TC_BWD_KT ? d.H - t.z : TC_BWD_KT; r.rows = d.C;
+        } else {
+          const DLayer& ly = d.layer[t.y];
+          r.W = d.p + ly.oW + (long long)t.w * ly.K + t.z;
+          r.K = ly.K; r.kw = ly.K - t.z < TC_BWD_KT ? ly.K - t.z : TC_BWD_KT; r.rows = TC_BWD_HT;
+        }
+        r.cand = t.x; r.layer = t.y; r.kc0 = t.z; r.h0 = t.w; r.pad1 = 0;
       }
       // pageable source: staged before the call returns
       CUDA_TRY(cudaMemcpyAsync(g->bwd_tiles, recs.data(), sizeof(BwdTile) * recs.size(), cudaMemcpyHostToDevice, st));
@@ -559,19 +582,21 @@ static int to_dcache(const mfas_group* g, const mfas_cache_desc* c, DCache* out)
   } while (0)
 
 static int launch_bwd_stream(mfas_group* g, const DCache& cache, const BatchRef& batch, float step_size, float bc2_sqrt,
-                             bool keep, cudaStream_t st);
+                             bool keep, bool head_tiles, cudaStream_t st);
 
 // tc engine: one launch covers the feature columns of every layer, small per-layer kernels carry the chain
 static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& batch, bool train, bool bn_train,
                           float step_size, float bc2_sqrt, uint32_t step, const HeadOut& ho, cudaStream_t st) {
-  const TcErr terr{g->tc_err, g->timeline};
+  const TcErr terr{g->tc_err, g->timeline, g->l2_hints};
   const dim3 gf(g->items_fwd, (g->Hmax + 127) / 128, g->n_cand), gl((g->Hmax + TC_CB - 1) / TC_CB, g->n_cand);
   const bool prof = g->prof && train && g->chain == 2;
   if (prof) { g->prof_valid = false; cudaEventRecord(g->prof_ev[0], st); }
   if (g->fwd_ws) {
     const int grid = g->n_fwd_items < g->n_sms ? g->n_fwd_items : g->n_sms;
-    if (g->npad == 64) k_tc_fwd_ws<64><<<grid, FwdWs<64>::THREADS, FwdWs<64>::SMEM, st>>>(g->fwd_items, g->n_fwd_items, cache, batch, g->part, terr);
-    else k_tc_fwd_ws<128><<<grid, FwdWs<128>::THREADS, FwdWs<128>::SMEM, st>>>(g->fwd_items, g->n_fwd_items, cache, batch, g->part, terr);
+#define FW(N, X) k_tc_fwd_ws<N, X><<<grid, FwdWs<N, X>::THREADS, FwdWs<N, X>::SMEM, st>>>(g->fwd_items, g->n_fwd_items, cache, batch, g->part, terr)
+    if (g->npad == 64) { if (g->fwd_xr) FW(64, 1); else FW(64, 0); }
+    else { if (g->fwd_xr) FW(128, 1); else FW(128, 0); }
+#undef FW
   } else if (g->npad == 64) k_tc_fwd_all<64><<<gf, TC_THREADS, g->smem_tc_fwd, st>>>(g->dc, cache, batch, g->part, g->part_stride, terr);
   else k_tc_fwd_all<128><<<gf, TC_THREADS, g->smem_tc_fwd, st>>>(g->dc, cache, batch, g->part, g->part_stride, terr);
   LAUNCH_CHECK(g);
@@ -580,14 +605,15 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
   for (int c = 0; c < g->n_cand; ++c) keep = keep || g->hc[c].grad != nullptr;
   if (prof) cudaEventRecord(g->prof_ev[1], st);
   if (g->chain == 2 && train == bn_train) {           // the whole serial chain in one launch
-#define CA(T, N) k_chain_all<T, N><<<g->n_cand, ChainCfg<N>::THREADS, g->smem_chain_all, st>>>(g->dc, cache, batch, g->bmax, g->part, g->part_stride, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, ho, terr)
-    if (g->npad == 64) { if (train) CA(true, 64); else CA(false, 64); }
-    else { if (train) CA(true, 128); else CA(false, 128); }
+#define CA(T, N, TH) k_chain_all<T, N, TH><<<g->n_cand, ChainCfg<N>::THREADS, g->smem_chain_all, st>>>(g->dc, cache, batch, g->bmax, g->part, g->part_stride, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, ho, terr)
+    if (g->tchead) { if (train) CA(true, 64, true); else CA(false, 64, true); }
+    else if (g->npad == 64) { if (train) CA(true, 64, false); else CA(false, 64, false); }
+    else { if (train) CA(true, 128, false); else CA(false, 128, false); }
 #undef CA
     LAUNCH_CHECK(g);
     if (!train) return MFAS_OK;
     if (prof) cudaEventRecord(g->prof_ev[2], st);
-    const int rc = launch_bwd_stream(g, cache, batch, step_size, bc2_sqrt, keep, st);
+    const int rc = launch_bwd_stream(g, cache, batch, step_size, bc2_sqrt, keep, g->tchead, st);
     if (prof) { cudaEventRecord(g->prof_ev[3], st); g->prof_valid = true; }
     return rc;
   }
@@ -621,18 +647,19 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
     }
     LAUNCH_CHECK(g);
   }
-  return launch_bwd_stream(g, cache, batch, step_size, bc2_sqrt, keep, st);
+  return launch_bwd_stream(g, cache, batch, step_size, bc2_sqrt, keep, false, st);
 }
 
 // the weight-gradient + Adam streaming kernel of a train step (all layers, all candidates)
 static int launch_bwd_stream(mfas_group* g, const DCache& cache, const BatchRef& batch, float step_size, float bc2_sqrt,
-                             bool keep, cudaStream_t st) {
-  const TcErr terr{g->tc_err, g->timeline};
+                             bool keep, bool head_tiles, cudaStream_t st) {
+  const TcErr terr{g->tc_err, g->timeline, g->l2_hints};
   const dim3 gb(g->items_bwd, (g->Hmax + TC_BWD_HT - 1) / TC_BWD_HT, g->n_cand);
   if (g->bwd_ws) {
-    const int grid = g->n_bwd_tiles < g->n_sms ? g->n_bwd_tiles : g->n_sms;
-    if (keep) k_tc_bwd_ws<true><<<grid, TC_WS_THREADS, TC_WS_SMEM, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, g->bwd_tiles, g->n_bwd_tiles, terr);
-    else k_tc_bwd_ws<false><<<grid, TC_WS_THREADS, TC_WS_SMEM, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, g->bwd_tiles, g->n_bwd_tiles, terr);
+    const int nt = head_tiles ? g->n_bwd_tiles : g->n_bwd_layer_tiles;
+    const int grid = nt < g->n_sms ? nt : g->n_sms;
+    if (keep) k_tc_bwd_ws<true><<<grid, TC_WS_THREADS, TC_WS_SMEM, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, g->bwd_tiles, nt, terr);
+    else k_tc_bwd_ws<false><<<grid, TC_WS_THREADS, TC_WS_SMEM, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, g->bwd_tiles, nt, terr);
     LAUNCH_CHECK(g);
     return MFAS_OK;
   }

@@ -30,7 +30,8 @@ print("phase: median / max cycles over candidates (1 us ~ 1900 cycles)")
 for i, n in enumerate(names):
     print(f"  {n:10s} {np.median(d[:, i]):9.0f} {d[:, i].max():9.0f}")
 print("  total      %9.0f %9.0f" % (np.median(out[:, 9] - out[:, 0]), (out[:, 9] - out[:, 0]).max()))
-inner = out[:, 10:15]
-print("inside forward layer 0 (cycles since kernel start, median): ctx open %d | partials %d | activation %d | BN stats %d | (layer end %d)" % (
-    np.median(inner[:, 0] - out[:, 0]), np.median(inner[:, 1] - out[:, 0]), np.median(inner[:, 2] - out[:, 0]),
-    np.median(inner[:, 3] - out[:, 0]), np.median(out[:, 1] - out[:, 0])))
+inner = out[:, 10:16]
+t0 = inner[:, 0]
+print("inside forward layer 1 (cycles since the layer was entered, median): A staged %d | B staged %d | MMAs issued %d | z complete (partials, MMA, bias, act) %d | BN stats %d | (layer end %d)" % (
+    np.median(inner[:, 1] - t0), np.median(inner[:, 2] - t0), np.median(inner[:, 3] - t0), np.median(inner[:, 4] - t0),
+    np.median(inner[:, 5] - t0), np.median(out[:, 2] - t0)))
