@@ -117,6 +117,34 @@ def cpu_reference_sample(train_steps, threads=None):
                       f"scaled to a {math.ceil(N_TRAIN / B)}+{math.ceil(N_DEV / B)}-step candidate-epoch"}
 
 
+def gpu_eager_reference_sample(device, train_steps=80):
+    """The reference's arithmetic stack as eager PyTorch ON THE GPU (the favourable case: cached
+    features already resident on the device, no DataLoader): the same port as the CPU baseline moved to `device`,
+    one candidate, a bounded sample.  north_star's ">= 10x the reference 1-GPU PyTorch" is read against this."""
+    import torch
+    from mfas_b200.cache import synthetic_ntu_cache
+    from oracle.torch_port import FusionHeadTorch, train_candidate
+    dev_steps = max(1, train_steps // 2)
+    train = synthetic_ntu_cache(train_steps * B, 1)
+    dev = synthetic_ntu_cache(dev_steps * B, 2)
+    torch.manual_seed(0)
+    model = FusionHeadTorch(CONF4, H, C, batchnorm=True).to(device)
+    tr = tuple(t.to(device) for t in (train.ske_cat, train.rgb_cat, train.labels))
+    dv = tuple(t.to(device) for t in (dev.ske_cat, dev.rgb_cat, dev.labels))
+    orders = lambda ph, e: torch.randperm(len(train) if ph == "train" else len(dev)).to(device)
+    train_candidate(model, tr, dv, orders, B, 1, max_train_steps=10, max_dev_steps=5)        # warm-up (cuBLAS handles, allocator)
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    _, st = train_candidate(model, tr, dv, orders, B, 1, max_train_steps=train_steps, max_dev_steps=dev_steps)
+    torch.cuda.synchronize(device)
+    dt = time.perf_counter() - t0
+    frac = st[0]["train_steps"] / math.ceil(N_TRAIN / B)
+    return {"value": frac / dt, "unit": UNIT, "kind": "port",
+            "sample": f"oracle/torch_port.py as eager PyTorch on cuda (fp32, TF32 off), 1 candidate at a time as the reference trains them, "
+                      f"features resident on the device, {st[0]['train_steps']} train + {st[0]['dev_steps']} eval steps of cfg2 in {dt:.2f} s, "
+                      f"scaled to a {math.ceil(N_TRAIN / B)}+{math.ceil(N_DEV / B)}-step candidate-epoch"}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -351,15 +379,20 @@ def run_ours(a):
             e2e_dev = measure(True)         # opt-in args.init_on_device=True (default when sharded over ranks)
 
     cpu = None
+    gpu_eager = None
     if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
         cpu = cpu_reference_sample(a.cpu_sample_steps)
+        try:
+            gpu_eager = gpu_eager_reference_sample(device)
+        except Exception as ex:                      # a reported baseline, never the measurement itself
+            gpu_eager = {"error": str(ex)}
 
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(a, n_gpus), "clocks": clk, "e2e": e2e, "e2e_device_init": e2e_dev, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "finite": finite,
+            "roofline": roofline, "cpu_baseline": cpu, "reference_gpu_eager": gpu_eager, "finite": finite,
             "hbm_ceiling_cand_epochs_per_s_per_gpu": peak * 1e9 / (steps_tr * cnt["train_bytes"] + steps_dv * cnt["eval_bytes"])}))
     if world > 1:
         td.destroy_process_group()

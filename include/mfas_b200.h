@@ -143,6 +143,10 @@ int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layout* layouts
                       float dropout_p, uint32_t dropout_seed, const int32_t* cand_ids /* [n_cand] or NULL */,
                       mfas_group_t* out);
 int mfas_group_destroy(mfas_group_t g);
+/* The workspace and partial-sum blocks of a destroyed group are parked for the next mfas_group_create on the same
+ * device (the reference builds and drops a model per candidate, ntu_searchable.py:38-99; here the unit is a group per
+ * train_sampled_models call).  This returns everything parked to the CUDA driver.  MFAS_POOL_MB caps it (default 4096). */
+int mfas_release_cached_memory(void);
 int mfas_group_bind(mfas_group_t g, int32_t cand, const mfas_arenas* arenas);
 int mfas_group_set_adam(mfas_group_t g, const mfas_adam_hparams* hp);
 int mfas_group_num_launches(mfas_group_t g, int64_t* out);   /* kernels launched through g so far */

@@ -78,6 +78,7 @@ SYMBOLS = {
     "mfas_group_create": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(Layout), C.c_int32, C.c_float, C.c_uint32,
                                     C.POINTER(C.c_int32), C.POINTER(_P)]),
     "mfas_group_destroy": (C.c_int, [_P]),
+    "mfas_release_cached_memory": (C.c_int, []),
     "mfas_group_bind": (C.c_int, [_P, C.c_int32, C.POINTER(Arenas)]),
     "mfas_group_set_adam": (C.c_int, [_P, C.POINTER(AdamHParams)]),
     "mfas_group_num_launches": (C.c_int, [_P, C.POINTER(C.c_int64)]),

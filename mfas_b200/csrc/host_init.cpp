@@ -9,7 +9,12 @@
 // weights as the reference constructor would.  mfas_b200/host_init.py cross-checks the first draws against
 // torch itself and falls back to torch's initialisers on any mismatch.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <atomic>
+#include <thread>
+#include <vector>
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -103,6 +108,99 @@ void emit(const uint32_t* s, float* out, int k, float from, float range, int fma
 }
 }  // namespace
 
+// ---- pipelined variant for large fills -------------------------------------------------------------------
+// The twist is a serial recurrence (one thread, ~0.3 ns/word); tempering, the float conversion and above all the
+// stores into the pinned arena are not.  One producer thread regenerates state blocks into a ring of chunks,
+// kConsumers threads temper/scale/store disjoint chunks of the word stream.  The word stream is cut into blocks:
+// block 0 = what is left of the current state (rem0 words), block b >= 1 = one full regeneration (624 words);
+// a chunk is kChunkBlocks consecutive blocks.  Result and final generator state are identical to the serial loop.
+namespace {
+constexpr int kChunkBlocks = 64, kRing = 24;
+
+struct Stream {
+  int n_ops;
+  float* const* dst;
+  const int64_t* count;
+  const float* from;
+  const float* to;
+  std::vector<int64_t> start;      // first word of op i; start[n_ops] = total
+  int fma;
+};
+
+// words [w0, w0 + k) of the stream come from src[0..k)
+void emit_range(const Stream& S, int64_t w0, const uint32_t* src, int64_t k) {
+  int lo = 0, hi = S.n_ops - 1;                      // op containing w0 (ops with count 0 are skipped by the search)
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (S.start[mid] <= w0) lo = mid; else hi = mid - 1; }
+  int op = lo;
+  while (k > 0) {
+    while (S.start[op + 1] <= w0) ++op;
+    const int64_t in_op = w0 - S.start[op], take = (S.start[op + 1] - w0 < k) ? S.start[op + 1] - w0 : k;
+    emit(src, S.dst[op] + in_op, (int)take, S.from[op], S.to[op] - S.from[op], S.fma);
+    src += take; w0 += take; k -= take;
+  }
+}
+
+void fill_pipelined(Engine& e, const Stream& S, int n_consumers) {
+  const int64_t total = S.start[S.n_ops];
+  const int rem0 = e.rem;
+  const int64_t n_blocks = 1 + (total > rem0 ? (total - rem0 + N - 1) / N : 0);       // block 0 + regenerated blocks
+  const int64_t n_chunks = (n_blocks + kChunkBlocks - 1) / kChunkBlocks;
+  std::vector<uint32_t> ring((size_t)kRing * kChunkBlocks * N);
+  std::vector<std::atomic<int64_t>> ready(kRing);    // chunk index + 1 held by the slot (0: never filled); consumer stores -(chunk+1) when done
+  for (auto& r : ready) r.store(0, std::memory_order_relaxed);
+  auto block_words = [&](int64_t b, int64_t& w0) {   // words of block b that belong to the stream, and its first word
+    if (b == 0) { w0 = 0; return (int64_t)(total < rem0 ? total : rem0); }
+    w0 = rem0 + (b - 1) * N;
+    const int64_t left = total - w0;
+    return left < N ? (left < 0 ? 0 : left) : (int64_t)N;
+  };
+  std::vector<std::thread> consumers;
+  for (int c = 0; c < n_consumers; ++c)
+    consumers.emplace_back([&, c] {
+      for (int64_t ch = c; ch < n_chunks; ch += n_consumers) {
+        std::atomic<int64_t>& slot = ready[ch % kRing];
+        while (slot.load(std::memory_order_acquire) != ch + 1) {
+#if defined(__x86_64__)
+          _mm_pause();
+#endif
+        }
+        const uint32_t* base = ring.data() + (size_t)(ch % kRing) * kChunkBlocks * N;
+        const int64_t b0 = ch * kChunkBlocks, b1 = b0 + kChunkBlocks < n_blocks ? b0 + kChunkBlocks : n_blocks;
+        for (int64_t b = b0; b < b1; ++b) {
+          int64_t w0;
+          const int64_t k = block_words(b, w0);
+          if (k > 0) emit_range(S, w0, base + (size_t)(b - b0) * N, k);
+        }
+        slot.store(-(ch + 1), std::memory_order_release);
+      }
+    });
+  // producer (this thread)
+  int64_t last_used = 0;                             // words of the stream taken from the last generated block
+  for (int64_t ch = 0; ch < n_chunks; ++ch) {
+    std::atomic<int64_t>& slot = ready[ch % kRing];
+    if (ch >= kRing)
+      while (slot.load(std::memory_order_acquire) != -(ch - kRing + 1)) {
+#if defined(__x86_64__)
+        _mm_pause();
+#endif
+      }
+    uint32_t* base = ring.data() + (size_t)(ch % kRing) * kChunkBlocks * N;
+    const int64_t b0 = ch * kChunkBlocks, b1 = b0 + kChunkBlocks < n_blocks ? b0 + kChunkBlocks : n_blocks;
+    for (int64_t b = b0; b < b1; ++b) {
+      uint32_t* o = base + (size_t)(b - b0) * N;
+      if (b == 0) memcpy(o, e.st + e.pos, sizeof(uint32_t) * rem0);
+      else { regen(e.st); memcpy(o, e.st, sizeof(uint32_t) * N); }
+      int64_t w0;
+      last_used = block_words(b, w0);
+    }
+    slot.store(ch + 1, std::memory_order_release);
+  }
+  for (auto& t : consumers) t.join();
+  if (n_blocks == 1) { e.pos += (int)last_used; e.rem -= (int)last_used; }
+  else { e.pos = (int)last_used; e.rem = N - (int)last_used; }
+}
+}  // namespace
+
 // torch.get_rng_state() legacy layout: u64 seed | i32 left | i32 seeded | u64 next | u64 state[624] | ...
 extern "C" int mfas_host_uniform_fill(uint8_t* torch_rng_state, int64_t state_bytes, int32_t n_ops,
                                       float* const* dst, const int64_t* count, const float* from, const float* to,
@@ -117,15 +215,30 @@ extern "C" int mfas_host_uniform_fill(uint8_t* torch_rng_state, int64_t state_by
   Engine e;
   for (int i = 0; i < N; ++i) { uint64_t w; memcpy(&w, torch_rng_state + 24 + 8 * i, 8); e.st[i] = (uint32_t)w; }
   e.pos = (int)next; e.rem = left - 1;
-  for (int op = 0; op < n_ops; ++op) {
-    float* o = dst[op];
-    int64_t n = count[op];
-    const float range = to[op] - from[op];
-    while (n > 0) {
-      if (e.rem == 0) { regen(e.st); e.pos = 0; e.rem = N; }
-      const int k = (int)(n < e.rem ? n : e.rem);
-      emit(e.st + e.pos, o, k, from[op], range, use_fma);
-      o += k; n -= k; e.pos += k; e.rem -= k;
+  int64_t total = 0;
+  for (int op = 0; op < n_ops; ++op) { if (count[op] < 0) return MFAS_ERR_INVALID; total += count[op]; }
+  int n_consumers = 0;
+  if (total >= (4 << 20)) {                          // MFAS_HOST_INIT_THREADS: consumer threads (0 = the serial loop)
+    const char* te = getenv("MFAS_HOST_INIT_THREADS");
+    const unsigned hw = std::thread::hardware_concurrency();
+    n_consumers = te ? atoi(te) : (hw >= 8 ? 4 : hw >= 4 ? 2 : 0);
+    if (n_consumers > 16) n_consumers = 16;
+  }
+  if (n_consumers > 0) {
+    Stream S{n_ops, dst, count, from, to, std::vector<int64_t>((size_t)n_ops + 1, 0), use_fma};
+    for (int op = 0; op < n_ops; ++op) S.start[op + 1] = S.start[op] + count[op];
+    fill_pipelined(e, S, n_consumers);
+  } else {
+    for (int op = 0; op < n_ops; ++op) {
+      float* o = dst[op];
+      int64_t n = count[op];
+      const float range = to[op] - from[op];
+      while (n > 0) {
+        if (e.rem == 0) { regen(e.st); e.pos = 0; e.rem = N; }
+        const int k = (int)(n < e.rem ? n : e.rem);
+        emit(e.st + e.pos, o, k, from[op], range, use_fma);
+        o += k; n -= k; e.pos += k; e.rem -= k;
+      }
     }
   }
   left = e.rem + 1; next = (uint64_t)e.pos;

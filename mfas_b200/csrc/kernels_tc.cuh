@@ -32,7 +32,8 @@ constexpr int TC_BWD_HT = 64;         // backward: output rows h (TMEM columns) 
 struct TcErr {
   int* flag;                          // set when a bounded barrier wait expires (never hangs the GPU)
   long long* timeline;                // optional [n_cand][16] clock64 stamps of k_chain_all's phases (MFAS_CHAIN_TIMELINE=1)
-  int l2_hints;                       // 1: the once-per-launch streams are loaded with L2 evict-first priority (MFAS_L2_HINTS=0 turns it off)
+  int l2_hints;                       // bit 0: k_tc_fwd_ws loads its once-per-launch streams with L2 evict-first priority; bit 1: k_tc_bwd_ws too
+                                      // (MFAS_L2_HINTS; default 1 -- on the backward's read-modify-write stream the hint costs 55 %, r01n)
 };
 
 __host__ __device__ __forceinline__ int tc_fwd_items(int d_ske, int d_rgb) {
@@ -288,7 +289,7 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
     const int r = tid >> 3, c = tid & 7;                           // 16-byte chunk c of the 128-byte row
     const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);   // sw128(r + 16 j, 16 c) = off + 2048 j
     const uint32_t s0 = umma::smem_u32(smem);
-    const uint64_t stream_policy = l2_stream_policy(err.l2_hints != 0);
+    const uint64_t stream_policy = l2_stream_policy((err.l2_hints & 1) != 0);
     int n = 0;
     for (int i = 0; i < n_my && ok; ++i) {
       const FwdItem it = items[blockIdx.x + i * gridDim.x];
@@ -773,15 +774,21 @@ __device__ __forceinline__ void chain_mma_kmajor(ChainCtx& cx, const float* A, l
     umma::fence_async_smem();
     __syncthreads();
     if (tid == 0) {
+      // One thread issues on behalf of the CTA, so its instruction stream IS the critical path here (r01 timeline:
+      // 4.9 k cycles for 64 MMAs with the descriptors rebuilt per k-step): base descriptors once, compile-time
+      // offsets in a fully unrolled loop, and three products (lo x lo is 2^-22 of the result, as in the streaming kernels).
       umma::tc_fence_after();
-      for (int ks = 0; ks < (jw >> 3); ++ks) {
-        const uint32_t oa = (uint32_t)(ks >> 2) * A_KB + (ks & 3) * 32u, ob = (uint32_t)(ks >> 2) * B_KB + (ks & 3) * 32u;
-        const uint64_t dah = umma::smem_desc(umma::smem_u32(a_hi) + oa, 16, 1024), dal = umma::smem_desc(umma::smem_u32(a_lo) + oa, 16, 1024);
-        const uint64_t dbh = umma::smem_desc(umma::smem_u32(b_hi) + ob, 16, 1024), dbl = umma::smem_desc(umma::smem_u32(b_lo) + ob, 16, 1024);
-        umma::mma_tf32(tm, dal, dbl, idesc, (j0 > 0 || ks > 0) ? 1u : 0u);
-        umma::mma_tf32(tm, dal, dbh, idesc, 1u);
-        umma::mma_tf32(tm, dah, dbl, idesc, 1u);
-        umma::mma_tf32(tm, dah, dbh, idesc, 1u);
+      const uint64_t dah0 = umma::smem_desc(umma::smem_u32(a_hi), 16, 1024), dal0 = umma::smem_desc(umma::smem_u32(a_lo), 16, 1024);
+      const uint64_t dbh0 = umma::smem_desc(umma::smem_u32(b_hi), 16, 1024), dbl0 = umma::smem_desc(umma::smem_u32(b_lo), 16, 1024);
+      const int nks = jw >> 3;
+#pragma unroll
+      for (int ks = 0; ks < PASS / 8; ++ks) {
+        if (ks < nks) {
+          const uint64_t oa = ((uint32_t)(ks >> 2) * A_KB + (ks & 3) * 32u) >> 4, ob = ((uint32_t)(ks >> 2) * B_KB + (ks & 3) * 32u) >> 4;
+          umma::mma_tf32(tm, dal0 + oa, dbh0 + ob, idesc, (j0 > 0 || ks > 0) ? 1u : 0u);
+          umma::mma_tf32(tm, dah0 + oa, dbl0 + ob, idesc, 1u);
+          umma::mma_tf32(tm, dah0 + oa, dbh0 + ob, idesc, 1u);
+        }
       }
       umma::mma_commit(cx.bar);
     }
@@ -996,17 +1003,20 @@ __device__ __forceinline__ void chain_mma_mnmajor(ChainCtx& cx, const float* U, 
     }
     umma::fence_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0) {                                                   // (see chain_mma_kmajor)
       umma::tc_fence_after();
-      for (int ks = 0; ks < (hw >> 3); ++ks) {
-        const uint32_t oa = ks * 1024u, ob = (uint32_t)(ks >> 2) * B_KB + (ks & 3) * 32u;
-        const uint64_t dah = umma::smem_desc(umma::smem_u32(a_hi) + oa, A_BLK, 512, umma::kLayoutSw128Base32);
-        const uint64_t dal = umma::smem_desc(umma::smem_u32(a_lo) + oa, A_BLK, 512, umma::kLayoutSw128Base32);
-        const uint64_t dbh = umma::smem_desc(umma::smem_u32(b_hi) + ob, 16, 1024), dbl = umma::smem_desc(umma::smem_u32(b_lo) + ob, 16, 1024);
-        umma::mma_tf32(tm, dal, dbl, idesc, (h0 > 0 || ks > 0) ? 1u : 0u);
-        umma::mma_tf32(tm, dal, dbh, idesc, 1u);
-        umma::mma_tf32(tm, dah, dbl, idesc, 1u);
-        umma::mma_tf32(tm, dah, dbh, idesc, 1u);
+      const uint64_t dah0 = umma::smem_desc(umma::smem_u32(a_hi), A_BLK, 512, umma::kLayoutSw128Base32);
+      const uint64_t dal0 = umma::smem_desc(umma::smem_u32(a_lo), A_BLK, 512, umma::kLayoutSw128Base32);
+      const uint64_t dbh0 = umma::smem_desc(umma::smem_u32(b_hi), 16, 1024), dbl0 = umma::smem_desc(umma::smem_u32(b_lo), 16, 1024);
+      const int nks = hw >> 3;
+#pragma unroll
+      for (int ks = 0; ks < PASS / 8; ++ks) {
+        if (ks < nks) {
+          const uint64_t oa = (ks * 1024u) >> 4, ob = ((uint32_t)(ks >> 2) * B_KB + (ks & 3) * 32u) >> 4;
+          umma::mma_tf32(tm, dal0 + oa, dbh0 + ob, idesc, (h0 > 0 || ks > 0) ? 1u : 0u);
+          umma::mma_tf32(tm, dah0 + oa, dbl0 + ob, idesc, 1u);
+          umma::mma_tf32(tm, dah0 + oa, dbh0 + ob, idesc, 1u);
+        }
       }
       umma::mma_commit(cx.bar);
     }
@@ -1624,7 +1634,7 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
     uint8_t* ring = smem + STAGE + (size_t)aw * WS_RING * WS_SLOT;
     const uint32_t ring_u32 = umma::smem_u32(ring);
     const int srow = lane >> 3, schunk = lane & 7;     // cp.async: a lane moves 16 B of row (4*u + srow)
-    const uint64_t stream_policy = l2_stream_policy(err.l2_hints != 0);
+    const uint64_t stream_policy = l2_stream_policy((err.l2_hints & 2) != 0);
     struct Tile { float* W; long long K, moff, voff, goff; bool valid; int rows; };   // rows: valid rows of this warp's 32 (64-row tiles: 32; the classifier tile: C - 32 cg, clamped)
     struct Raw { int4 a, b, c; };                      // first 48 bytes of a BwdTile
     auto fetch_raw = [&](int i) {

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <mutex>
 #include <vector>
 
 #include "kernels_ffma.cuh"
@@ -113,6 +114,68 @@ extern "C" int mfas_algorithmic_counts(const mfas_layout* lay, int32_t batch, do
 }
 
 // ---------------------------------------------------------------------------------------------
+// Device-memory cache for the two large per-group allocations (workspace + partial sums, ~0.8 GB for a 148-candidate
+// cfg2 group).  A search driver creates and destroys a group per train_sampled_models call; cudaFree / cudaMalloc
+// of blocks this size cost 10-400 ms each on the B200 box (r01 e2e timings), several times the per-call host work
+// that remains.  Freed blocks are parked here and handed to the next group that fits; mfas_release_cached_memory()
+// returns them to the driver.  MFAS_POOL_MB caps what is parked (default 4096, 0 disables).
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct PoolBlock { int device; void* p; size_t bytes; };
+std::mutex g_pool_mu;
+std::vector<PoolBlock> g_pool;
+size_t pool_cap_bytes() {
+  static const size_t cap = [] { const char* e = getenv("MFAS_POOL_MB"); return (size_t)(e ? atoll(e) : 4096) << 20; }();
+  return cap;
+}
+cudaError_t pool_alloc(int device, size_t bytes, void** out, size_t* got) {
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_pool.size(); ++i)
+      if (g_pool[i].device == device && g_pool[i].bytes >= bytes && g_pool[i].bytes <= bytes + bytes / 4 &&
+          (best < 0 || g_pool[i].bytes < g_pool[best].bytes)) best = i;
+    if (best >= 0) {
+      *out = g_pool[best].p; *got = g_pool[best].bytes;
+      g_pool.erase(g_pool.begin() + best);
+      return cudaSuccess;
+    }
+  }
+  *got = bytes;
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e == cudaErrorMemoryAllocation) {               // make room: drop everything parked on this device and retry
+    cudaGetLastError();
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (int i = (int)g_pool.size() - 1; i >= 0; --i)
+      if (g_pool[i].device == device) { cudaFree(g_pool[i].p); g_pool.erase(g_pool.begin() + i); }
+    e = cudaMalloc(out, bytes);
+  }
+  return e;
+}
+// caller guarantees no work that touches the block is in flight (mfas_group_destroy synchronises the device first)
+void pool_free(int device, void* p, size_t bytes) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    size_t parked = 0;
+    for (const PoolBlock& b : g_pool) parked += b.bytes;
+    if (bytes >= (1u << 20) && parked + bytes <= pool_cap_bytes()) { g_pool.push_back({device, p, bytes}); return; }
+  }
+  cudaFree(p);
+}
+}  // namespace
+
+extern "C" int mfas_release_cached_memory(void) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (const PoolBlock& b : g_pool) { cudaSetDevice(b.device); cudaFree(b.p); }
+  g_pool.clear();
+  cudaSetDevice(cur);
+  return MFAS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // group
 // ---------------------------------------------------------------------------------------------
 struct mfas_group {
@@ -127,6 +190,7 @@ struct mfas_group {
   std::vector<char> bound;
   DCand* dc = nullptr;            // device descriptors
   char* ws = nullptr;             // one workspace allocation
+  size_t ws_bytes = 0, part_bytes = 0;   // block sizes as the pool handed them out
   int* improved = nullptr;        // [n_cand]
   bool dirty = true;
   size_t smem_head = 0, smem_bwd = 0;
@@ -173,10 +237,11 @@ extern "C" int mfas_group_set_adam(mfas_group_t g, const mfas_adam_hparams* hp) 
 extern "C" int mfas_group_destroy(mfas_group_t g) {
   if (!g) return MFAS_OK;
   DeviceGuard dg(g->device);
+  cudaDeviceSynchronize();                            // what cudaFree did implicitly: nothing of this group is in flight any more
   if (g->dc) cudaFree(g->dc);
-  if (g->ws) cudaFree(g->ws);
+  pool_free(g->device, g->ws, g->ws_bytes);
   if (g->improved) cudaFree(g->improved);
-  if (g->part) cudaFree(g->part);
+  pool_free(g->device, g->part, g->part_bytes);
   if (g->bwd_tiles) cudaFree(g->bwd_tiles);
   if (g->fwd_items) cudaFree(g->fwd_items);
   for (auto& ev : g->prof_ev) if (ev) cudaEventDestroy(ev);
@@ -242,7 +307,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     o.best_bufs = total; total += up((size_t)l.n_bufs * sizeof(float));
     o.best_nbt = total; total += up((size_t)MFAS_MAX_LAYERS * sizeof(long long));
   }
-  cudaError_t e = cudaMalloc(&g->ws, total);
+  cudaError_t e = pool_alloc(device, total, (void**)&g->ws, &g->ws_bytes);
   if (e == cudaSuccess) e = cudaMemset(g->ws, 0, total);
   if (e == cudaSuccess) e = cudaMalloc(&g->dc, sizeof(DCand) * n_cand);
   if (e == cudaSuccess) e = cudaMalloc(&g->improved, sizeof(int) * n_cand);
@@ -330,7 +395,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     g->smem_tc_bwd = 1024 + 2 * (size_t)(4 * g->npad * 128) + 2 * (size_t)(2 * g->npad * 128);
     g->smem_fl = sizeof(float) * ((size_t)batch_max * (g->Hmax + 1) + TC_CB * (size_t)g->Hmax);
     g->smem_dzx = sizeof(float) * ((size_t)batch_max * g->Hmax + (TC_CB + 1) * (size_t)g->Hmax);
-    e = cudaMalloc(&g->part, sizeof(float) * g->part_stride * n_cand);
+    e = pool_alloc(device, sizeof(float) * g->part_stride * n_cand, (void**)&g->part, &g->part_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&g->tc_err, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(g->tc_err, 0, sizeof(int));
     auto attr = [&](const void* f, size_t bytes) {
@@ -408,7 +473,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       { const char* xe = getenv("MFAS_FWD_XR"); if (xe) g->fwd_xr = atoi(xe) ? 1 : 0; }
     }
     { const char* de = getenv("MFAS_TC_DEBUG"); if (de) g->dbg = atoi(de); }
-    { const char* le = getenv("MFAS_L2_HINTS"); if (le) g->l2_hints = atoi(le) ? 1 : 0; }
+    { const char* le = getenv("MFAS_L2_HINTS"); if (le) g->l2_hints = atoi(le) & 3; }
     if (e != cudaSuccess) {
       int code = fail(MFAS_ERR_CUDA, "tc engine setup: %s", cudaGetErrorString(e));
       mfas_group_destroy(g);

@@ -520,11 +520,18 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
                     [np.asarray(sampled_configurations[i]).reshape(-1, 3) for i in todo], args.inner_representation_size,
                     args.num_outputs, flags, args.vid_len[1])
                 hp, hb = _staging(int(full.p_off[-1]), int(full.b_off[-1]))
-                init_host_arenas(full, hp, hb)
                 if full is g:
-                    g.params.copy_(hp, non_blocking=True)
-                    g.bufs.copy_(hb, non_blocking=True)
+                    # a quarter of the candidates at a time: the H2D copy of one slice overlaps the fill of the next
+                    step_c = max(1, (g.n + 3) // 4)
+                    for c0 in range(0, g.n, step_c):
+                        c1 = min(g.n, c0 + step_c)
+                        init_host_arenas(full, hp, hb, slots=range(c0, c1))
+                        pa, pb = int(g.p_off[c0]), int(g.p_off[c1])
+                        ba, bb = int(g.b_off[c0]), int(g.b_off[c1])
+                        g.params[pa:pb].copy_(hp[pa:pb], non_blocking=True)
+                        g.bufs[ba:bb].copy_(hb[ba:bb], non_blocking=True)
                 else:
+                    init_host_arenas(full, hp, hb)
                     for k, j in enumerate(mine):
                         g.params[int(g.p_off[k]):int(g.p_off[k + 1])].copy_(hp[int(full.p_off[j]):int(full.p_off[j + 1])], non_blocking=True)
                         g.bufs[int(g.b_off[k]):int(g.b_off[k + 1])].copy_(hb[int(full.b_off[j]):int(full.b_off[j + 1])], non_blocking=True)
