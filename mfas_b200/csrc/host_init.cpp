@@ -92,6 +92,11 @@ __attribute__((target("avx2,fma"))) void emit_avx2(const uint32_t* s, float* out
 }
 #endif
 
+// tempered words as they are (count < 0 ops: the caller derives non-uniform draws from them, e.g. Box-Muller normals)
+void emit_raw(const uint32_t* s, uint32_t* out, int k) {
+  for (int i = 0; i < k; ++i) out[i] = temper(s[i]);
+}
+
 void regen(uint32_t* p) {
 #if defined(__x86_64__)
   static const bool fast = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma");
@@ -135,7 +140,8 @@ void emit_range(const Stream& S, int64_t w0, const uint32_t* src, int64_t k) {
   while (k > 0) {
     while (S.start[op + 1] <= w0) ++op;
     const int64_t in_op = w0 - S.start[op], take = (S.start[op + 1] - w0 < k) ? S.start[op + 1] - w0 : k;
-    emit(src, S.dst[op] + in_op, (int)take, S.from[op], S.to[op] - S.from[op], S.fma);
+    if (S.count[op] < 0) emit_raw(src, reinterpret_cast<uint32_t*>(S.dst[op]) + in_op, (int)take);
+    else emit(src, S.dst[op] + in_op, (int)take, S.from[op], S.to[op] - S.from[op], S.fma);
     src += take; w0 += take; k -= take;
   }
 }
@@ -146,8 +152,9 @@ void fill_pipelined(Engine& e, const Stream& S, int n_consumers) {
   const int64_t n_blocks = 1 + (total > rem0 ? (total - rem0 + N - 1) / N : 0);       // block 0 + regenerated blocks
   const int64_t n_chunks = (n_blocks + kChunkBlocks - 1) / kChunkBlocks;
   std::vector<uint32_t> ring((size_t)kRing * kChunkBlocks * N);
-  std::vector<std::atomic<int64_t>> ready(kRing);    // chunk index + 1 held by the slot (0: never filled); consumer stores -(chunk+1) when done
-  for (auto& r : ready) r.store(0, std::memory_order_relaxed);
+  struct alignas(128) Flag { std::atomic<int64_t> v; };   // own cache line each: the spinning readers must not slow the writers next door
+  std::vector<Flag> ready(kRing);                    // chunk index + 1 held by the slot (0: never filled); consumer stores -(chunk+1) when done
+  for (auto& r : ready) r.v.store(0, std::memory_order_relaxed);
   auto block_words = [&](int64_t b, int64_t& w0) {   // words of block b that belong to the stream, and its first word
     if (b == 0) { w0 = 0; return (int64_t)(total < rem0 ? total : rem0); }
     w0 = rem0 + (b - 1) * N;
@@ -158,7 +165,7 @@ void fill_pipelined(Engine& e, const Stream& S, int n_consumers) {
   for (int c = 0; c < n_consumers; ++c)
     consumers.emplace_back([&, c] {
       for (int64_t ch = c; ch < n_chunks; ch += n_consumers) {
-        std::atomic<int64_t>& slot = ready[ch % kRing];
+        std::atomic<int64_t>& slot = ready[ch % kRing].v;
         while (slot.load(std::memory_order_acquire) != ch + 1) {
 #if defined(__x86_64__)
           _mm_pause();
@@ -177,7 +184,7 @@ void fill_pipelined(Engine& e, const Stream& S, int n_consumers) {
   // producer (this thread)
   int64_t last_used = 0;                             // words of the stream taken from the last generated block
   for (int64_t ch = 0; ch < n_chunks; ++ch) {
-    std::atomic<int64_t>& slot = ready[ch % kRing];
+    std::atomic<int64_t>& slot = ready[ch % kRing].v;
     if (ch >= kRing)
       while (slot.load(std::memory_order_acquire) != -(ch - kRing + 1)) {
 #if defined(__x86_64__)
@@ -216,27 +223,29 @@ extern "C" int mfas_host_uniform_fill(uint8_t* torch_rng_state, int64_t state_by
   for (int i = 0; i < N; ++i) { uint64_t w; memcpy(&w, torch_rng_state + 24 + 8 * i, 8); e.st[i] = (uint32_t)w; }
   e.pos = (int)next; e.rem = left - 1;
   int64_t total = 0;
-  for (int op = 0; op < n_ops; ++op) { if (count[op] < 0) return MFAS_ERR_INVALID; total += count[op]; }
+  for (int op = 0; op < n_ops; ++op) total += count[op] < 0 ? -count[op] : count[op];     // count < 0: -count raw tempered words
   int n_consumers = 0;
   if (total >= (4 << 20)) {                          // MFAS_HOST_INIT_THREADS: consumer threads (0 = the serial loop)
     const char* te = getenv("MFAS_HOST_INIT_THREADS");
     const unsigned hw = std::thread::hardware_concurrency();
-    n_consumers = te ? atoi(te) : (hw >= 8 ? 4 : hw >= 4 ? 2 : 0);
+    n_consumers = te ? atoi(te) : (hw >= 8 ? 3 : hw >= 4 ? 2 : 0);
     if (n_consumers > 16) n_consumers = 16;
   }
   if (n_consumers > 0) {
     Stream S{n_ops, dst, count, from, to, std::vector<int64_t>((size_t)n_ops + 1, 0), use_fma};
-    for (int op = 0; op < n_ops; ++op) S.start[op + 1] = S.start[op] + count[op];
+    for (int op = 0; op < n_ops; ++op) S.start[op + 1] = S.start[op] + (count[op] < 0 ? -count[op] : count[op]);
     fill_pipelined(e, S, n_consumers);
   } else {
     for (int op = 0; op < n_ops; ++op) {
       float* o = dst[op];
-      int64_t n = count[op];
+      const bool raw = count[op] < 0;
+      int64_t n = raw ? -count[op] : count[op];
       const float range = to[op] - from[op];
       while (n > 0) {
         if (e.rem == 0) { regen(e.st); e.pos = 0; e.rem = N; }
         const int k = (int)(n < e.rem ? n : e.rem);
-        emit(e.st + e.pos, o, k, from[op], range, use_fma);
+        if (raw) emit_raw(e.st + e.pos, reinterpret_cast<uint32_t*>(o), k);
+        else emit(e.st + e.pos, o, k, from[op], range, use_fma);
         o += k; n -= k; e.pos += k; e.rem -= k;
       }
     }

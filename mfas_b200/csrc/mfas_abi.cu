@@ -114,11 +114,12 @@ extern "C" int mfas_algorithmic_counts(const mfas_layout* lay, int32_t batch, do
 }
 
 // ---------------------------------------------------------------------------------------------
-// Device-memory cache for the two large per-group allocations (workspace + partial sums, ~0.8 GB for a 148-candidate
-// cfg2 group).  A search driver creates and destroys a group per train_sampled_models call; cudaFree / cudaMalloc
-// of blocks this size cost 10-400 ms each on the B200 box (r01 e2e timings), several times the per-call host work
-// that remains.  Freed blocks are parked here and handed to the next group that fits; mfas_release_cached_memory()
-// returns them to the driver.  MFAS_POOL_MB caps what is parked (default 4096, 0 disables).
+// Device-memory cache for the per-group allocations: workspace + partial sums (~0.8 GB for a 148-candidate cfg2 group)
+// and the small descriptor / tile-list blocks.  A search driver creates and destroys a group per train_sampled_models
+// call; cudaMalloc / cudaFree of these blocks cost 10-400 ms on the B200 box and single cudaFree calls up to 1.3 s
+// (r01 e2e timings) -- more than all the per-call host work that remains.  Freed blocks are parked here and handed to
+// the next group that fits; mfas_release_cached_memory() returns them to the driver.  MFAS_POOL_MB caps what is
+// parked (default 4096, 0 disables).
 // ---------------------------------------------------------------------------------------------
 namespace {
 struct PoolBlock { int device; void* p; size_t bytes; };
@@ -133,7 +134,7 @@ cudaError_t pool_alloc(int device, size_t bytes, void** out, size_t* got) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     int best = -1;
     for (int i = 0; i < (int)g_pool.size(); ++i)
-      if (g_pool[i].device == device && g_pool[i].bytes >= bytes && g_pool[i].bytes <= bytes + bytes / 4 &&
+      if (g_pool[i].device == device && g_pool[i].bytes >= bytes && g_pool[i].bytes <= bytes + bytes / 4 + 65536 &&
           (best < 0 || g_pool[i].bytes < g_pool[best].bytes)) best = i;
     if (best >= 0) {
       *out = g_pool[best].p; *got = g_pool[best].bytes;
@@ -159,9 +160,15 @@ void pool_free(int device, void* p, size_t bytes) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     size_t parked = 0;
     for (const PoolBlock& b : g_pool) parked += b.bytes;
-    if (bytes >= (1u << 20) && parked + bytes <= pool_cap_bytes()) { g_pool.push_back({device, p, bytes}); return; }
+    if (parked + bytes <= pool_cap_bytes() && g_pool.size() < 256) { g_pool.push_back({device, p, bytes}); return; }
   }
   cudaFree(p);
+}
+template <class T> cudaError_t pool_alloc_t(int device, size_t bytes, T** out, size_t* got) {
+  void* p = nullptr;
+  const cudaError_t e = pool_alloc(device, bytes, &p, got);
+  *out = (T*)p;
+  return e;
 }
 }  // namespace
 
@@ -190,7 +197,7 @@ struct mfas_group {
   std::vector<char> bound;
   DCand* dc = nullptr;            // device descriptors
   char* ws = nullptr;             // one workspace allocation
-  size_t ws_bytes = 0, part_bytes = 0;   // block sizes as the pool handed them out
+  size_t ws_bytes = 0, part_bytes = 0, dc_bytes = 0, improved_bytes = 0, tiles_bytes = 0, items_bytes = 0, err_bytes = 0, tl_bytes = 0;   // block sizes as the pool handed them out
   int* improved = nullptr;        // [n_cand]
   bool dirty = true;
   size_t smem_head = 0, smem_bwd = 0;
@@ -238,15 +245,15 @@ extern "C" int mfas_group_destroy(mfas_group_t g) {
   if (!g) return MFAS_OK;
   DeviceGuard dg(g->device);
   cudaDeviceSynchronize();                            // what cudaFree did implicitly: nothing of this group is in flight any more
-  if (g->dc) cudaFree(g->dc);
+  pool_free(g->device, g->dc, g->dc_bytes);
   pool_free(g->device, g->ws, g->ws_bytes);
-  if (g->improved) cudaFree(g->improved);
+  pool_free(g->device, g->improved, g->improved_bytes);
   pool_free(g->device, g->part, g->part_bytes);
-  if (g->bwd_tiles) cudaFree(g->bwd_tiles);
-  if (g->fwd_items) cudaFree(g->fwd_items);
+  pool_free(g->device, g->bwd_tiles, g->tiles_bytes);
+  pool_free(g->device, g->fwd_items, g->items_bytes);
   for (auto& ev : g->prof_ev) if (ev) cudaEventDestroy(ev);
-  if (g->tc_err) cudaFree(g->tc_err);
-  if (g->timeline) cudaFree(g->timeline);
+  pool_free(g->device, g->tc_err, g->err_bytes);
+  pool_free(g->device, g->timeline, g->tl_bytes);
   delete g;
   return MFAS_OK;
 }
@@ -309,8 +316,8 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
   }
   cudaError_t e = pool_alloc(device, total, (void**)&g->ws, &g->ws_bytes);
   if (e == cudaSuccess) e = cudaMemset(g->ws, 0, total);
-  if (e == cudaSuccess) e = cudaMalloc(&g->dc, sizeof(DCand) * n_cand);
-  if (e == cudaSuccess) e = cudaMalloc(&g->improved, sizeof(int) * n_cand);
+  if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(DCand) * n_cand, &g->dc, &g->dc_bytes);
+  if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(int) * n_cand, &g->improved, &g->improved_bytes);
   if (e == cudaSuccess) e = cudaMemset(g->improved, 0, sizeof(int) * n_cand);
   if (e != cudaSuccess) {
     int code = fail(e == cudaErrorMemoryAllocation ? MFAS_ERR_NOMEM : MFAS_ERR_CUDA, "workspace allocation (%zu bytes): %s",
@@ -396,7 +403,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     g->smem_fl = sizeof(float) * ((size_t)batch_max * (g->Hmax + 1) + TC_CB * (size_t)g->Hmax);
     g->smem_dzx = sizeof(float) * ((size_t)batch_max * g->Hmax + (TC_CB + 1) * (size_t)g->Hmax);
     e = pool_alloc(device, sizeof(float) * g->part_stride * n_cand, (void**)&g->part, &g->part_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&g->tc_err, sizeof(int));
+    if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(int), &g->tc_err, &g->err_bytes);
     if (e == cudaSuccess) e = cudaMemset(g->tc_err, 0, sizeof(int));
     auto attr = [&](const void* f, size_t bytes) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -449,13 +456,13 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
         for (int c = 0; c < n_cand; ++c)
           for (int kc0 = 0; kc0 < g->lay[c].H; kc0 += TC_BWD_KT) tl.push_back(make_int4(c, g->lay[c].L, kc0, 0));
       g->n_bwd_tiles = (int)tl.size();
-      if (e == cudaSuccess) e = cudaMalloc(&g->bwd_tiles, sizeof(BwdTile) * tl.size());
+      if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(BwdTile) * tl.size(), &g->bwd_tiles, &g->tiles_bytes);
       g->bwd_tl = std::move(tl);
       attr((const void*)k_tc_bwd_ws<false>, TC_WS_SMEM);
       attr((const void*)k_tc_bwd_ws<true>, TC_WS_SMEM);
     }
     if (getenv("MFAS_CHAIN_TIMELINE") && e == cudaSuccess) {
-      e = cudaMalloc(&g->timeline, sizeof(long long) * 16 * n_cand);
+      e = pool_alloc_t(device, sizeof(long long) * 16 * n_cand, &g->timeline, &g->tl_bytes);
       if (e == cudaSuccess) e = cudaMemset(g->timeline, 0, sizeof(long long) * 16 * n_cand);
     }
     { const char* fe = getenv("MFAS_FWD"); if (fe && !strcmp(fe, "cta")) g->fwd_ws = 0; }
@@ -465,7 +472,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
         for (int l = 0; l < g->lay[c].L; ++l)
           n += tc_fwd_items(g->lay[c].d_ske[l], g->lay[c].d_rgb[l]) * ((g->lay[c].H + 127) / 128);
       g->n_fwd_items = n;
-      if (e == cudaSuccess) e = cudaMalloc(&g->fwd_items, sizeof(FwdItem) * n);
+      if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(FwdItem) * n, &g->fwd_items, &g->items_bytes);
       attr((const void*)k_tc_fwd_ws<64, 0>, FwdWs<64, 0>::SMEM);
       attr((const void*)k_tc_fwd_ws<128, 0>, FwdWs<128, 0>::SMEM);
       attr((const void*)k_tc_fwd_ws<64, 1>, FwdWs<64, 1>::SMEM);

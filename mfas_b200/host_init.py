@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import struct
 
 import numpy as np
 import torch
@@ -69,6 +70,17 @@ def init_host_arenas_fast(group, host_p, host_b, visit, slots=None) -> bool:
         return False
     state = torch.get_rng_state()
     pend = ([], [], [], [])
+    slot_list = list(range(group.n) if slots is None else slots)
+    # N(0, 0.1) of the scalar alphas (at::normal_distribution<double> through cpu_serial_kernel): Box-Muller on two
+    # 53-bit uniforms = 4 generator words, the sine branch cached in the generator for the next draw.  The words are
+    # fetched raw inside the same bulk fill and turned into samples afterwards, so one C call (and its thread pipeline)
+    # covers every candidate of the slice.
+    sbuf = state.numpy()
+    cache_valid = bool(struct.unpack_from("i", sbuf, 5040)[0])
+    cached = struct.unpack_from("d", sbuf, 5024)[0]
+    raw = np.zeros(4 * max(1, sum(int(group.layouts[c].L) for c in slot_list)), dtype=np.uint32)
+    n_raw = 0
+    normals = []                      # (tensor view, offset into raw or None when the cached sample serves it)
 
     def flush():
         if pend[0]:
@@ -77,10 +89,26 @@ def init_host_arenas_fast(group, host_p, host_b, visit, slots=None) -> bool:
             for p in pend:
                 p.clear()
 
+    def finish_normals():
+        nonlocal cached
+        for t, off in normals:
+            if off is None:
+                z = cached
+            else:
+                r1, r2, r3, r4 = (int(x) for x in raw[off:off + 4])
+                u1 = (((r1 << 32) | r2) & ((1 << 53) - 1)) * (1.0 / (1 << 53))
+                u2 = (((r3 << 32) | r4) & ((1 << 53) - 1)) * (1.0 / (1 << 53))
+                r = math.sqrt(-2.0 * math.log1p(-u2))
+                theta = 2.0 * math.pi * u1
+                cached = r * math.sin(theta)
+                z = r * math.cos(theta)
+            t.fill_(z * 0.1 + 0.0)
+        normals.clear()
+
     base_p, base_b = host_p.data_ptr(), host_b.data_ptr()
-    for c in (range(group.n) if slots is None else slots):
+    for c in slot_list:
         def fill(name, kind, fan_in, c=c):
-            nonlocal state
+            nonlocal state, cache_valid, n_raw, sbuf
             arena, off, shape = group.slots[c][name]
             o = int(group.b_off[c] if arena == "b" else group.p_off[c]) + int(off)
             n = int(np.prod(shape)) if shape else 1
@@ -94,12 +122,31 @@ def init_host_arenas_fast(group, host_p, host_b, visit, slots=None) -> bool:
                 t.fill_(1.0)
             elif kind == "zeros":
                 t.zero_()
-            elif kind == "normal":            # N(0, 0.1) of the alphas: Box-Muller with a cached sample -- left to torch
+            elif kind == "normal" and n == 1:
+                if cache_valid:
+                    normals.append((t, None))
+                    cache_valid = False
+                else:
+                    pend[0].append(raw.ctypes.data + 4 * n_raw)
+                    pend[1].append(-4); pend[2].append(0.0); pend[3].append(0.0)
+                    normals.append((t, n_raw))
+                    n_raw += 4
+                    cache_valid = True
+            elif kind == "normal":            # larger tensors take torch's vectorised normal_fill: left to torch
                 flush()
+                finish_normals()
+                struct.pack_into("d", sbuf, 5024, cached if cache_valid else 0.0)
+                struct.pack_into("i", sbuf, 5040, 1 if cache_valid else 0)
                 torch.set_rng_state(state)
                 nn.init.normal_(t.view(shape), 0.0, 0.1)
                 state = torch.get_rng_state()
+                sbuf = state.numpy()
+                cache_valid = bool(struct.unpack_from("i", sbuf, 5040)[0])
+                cached = struct.unpack_from("d", sbuf, 5024)[0]
         visit(group, c, fill)
     flush()
+    finish_normals()
+    struct.pack_into("d", sbuf, 5024, cached if cache_valid else 0.0)
+    struct.pack_into("i", sbuf, 5040, 1 if cache_valid else 0)
     torch.set_rng_state(state)
     return True
