@@ -31,6 +31,29 @@ N_TRAIN, N_DEV = 10240, 5120
 METRIC, UNIT = "candidate-epochs/sec (NTU fusion, bs=64)", "candidate-epochs/s"
 
 
+def workload_of(a, n_gpus):
+    """BASELINE.json configs: 'cfg2' = configs[1] (the metric's configuration, the default and the only one the driver
+    runs); 'search32' = configs[2] (the 32 one-step configurations [i,j,a], H=16, 5 epochs, sharded over the GPUs);
+    'search256' = north_star's 256-candidate search iteration (8 parents x 32 unfolded rows, L=2, H=16, 1 epoch)."""
+    import numpy as np
+    rows32 = [[i, j, k] for i in range(4) for j in range(4) for k in range(2)]
+    if a.workload == "cfg2":
+        return {"name": "cfg2", "H": H, "E": a.epochs, "per_gpu": a.candidates, "scaling": "weak",
+                "confs": lambda n: [np.array(CONF4) for _ in range(n)],
+                "desc": "NTU found conf=4 (4-step fusion), inner_repr=128, batchnorm, drpt=0, bs=64, "
+                        f"N_train={N_TRAIN}, N_dev={N_DEV}, {a.candidates} candidates/GPU x {a.epochs} epoch(s) per step"}
+    if a.workload == "search32":
+        allc = [np.array([r]) for r in rows32]
+        return {"name": "search32", "H": 16, "E": 5, "per_gpu": 32 // n_gpus, "scaling": "strong", "confs": lambda n: allc[:n],
+                "desc": "main_searchable_ntu.py first SMBO level: the 32 one-step configurations [i,j,a], inner_repr=16, batchnorm, "
+                        f"drpt=0, bs=64, N_train={N_TRAIN}, N_dev={N_DEV}, 5 epochs, {32 // n_gpus} candidates/GPU"}
+    parents = [[3, 1, 1], [1, 3, 0], [1, 1, 1], [3, 3, 0], [2, 2, 0], [0, 0, 1], [3, 2, 0], [2, 3, 1]]
+    allc = [np.array([p_, r]) for p_ in parents for r in rows32]
+    return {"name": "search256", "H": 16, "E": 1, "per_gpu": 256 // n_gpus, "scaling": "strong", "confs": lambda n: allc[:n],
+            "desc": "256-candidate search iteration: 8 parents x 32 unfolded rows, L=2, inner_repr=16, batchnorm, drpt=0, bs=64, "
+                    f"N_train={N_TRAIN}, N_dev={N_DEV}, 1 epoch, {256 // n_gpus} candidates/GPU"}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -42,13 +65,15 @@ def parse():
     ap.add_argument("--cpu-sample-steps", type=int, default=48, help="train steps of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "search32", "search256"],
+                    help="cfg2 = BASELINE.json configs[1] (default, the metric's configuration); the others are reported extras")
     return ap.parse_args()
 
 
 def workload_config(a, n_gpus):
-    return {"workload": "NTU found conf=4 (4-step fusion), inner_repr=128, batchnorm, drpt=0, bs=64, "
-                        f"N_train={N_TRAIN}, N_dev={N_DEV}, {a.candidates} candidates/GPU x {a.epochs} epoch(s) per step",
-            "candidates_per_gpu": a.candidates, "epochs_per_step": a.epochs, "parallelism": f"candidates sharded x{n_gpus}",
+    w = workload_of(a, n_gpus)
+    return {"workload": w["desc"],
+            "candidates_per_gpu": w["per_gpu"], "epochs_per_step": w["E"], "parallelism": f"candidates sharded x{n_gpus}",
             "l2": "inputs exceed L2 (cache 0.46 GB + per-candidate state 12.5 MB x candidates >> 126 MB)"}
 
 
@@ -210,7 +235,8 @@ def run_ours(a):
         td.all_reduce(t, op=td.ReduceOp.MAX)
         return float(t.item())
 
-    M, E = a.candidates, a.epochs
+    wl = workload_of(a, n_gpus)
+    M, E, Hw = wl["per_gpu"], wl["E"], wl["H"]
     # ---- inputs: rank 0 builds the cache, NCCL broadcasts it once -------------------------------
     host_train = synthetic_ntu_cache(N_TRAIN, 1).pin() if rank == 0 else None
     host_dev = synthetic_ntu_cache(N_DEV, 2).pin() if rank == 0 else None
@@ -219,9 +245,10 @@ def run_ours(a):
     steps_tr, steps_dv = math.ceil(N_TRAIN / B), math.ceil(N_DEV / B)
 
     # ---- device-resident arm: `value` -------------------------------------------------------
-    args = make_args(H, B, E, bn=True, drpt=0.0, Ti=1)
-    confs = [np.array(CONF4) for _ in range(M)]
-    g = CandidateGroup(confs, H, C, _lib.FLAG_BN, device, batch_max=B, cand_ids=[rank * M + i for i in range(M)])
+    args = make_args(Hw, B, E, bn=True, drpt=0.0, Ti=1)
+    all_confs = wl["confs"](M * n_gpus)
+    confs = all_confs[rank * M:(rank + 1) * M]
+    g = CandidateGroup(confs, Hw, C, _lib.FLAG_BN, device, batch_max=B, cand_ids=[rank * M + i for i in range(M)])
     g.set_adam(0.9, 0.999, 1e-8, 1e-4)
     torch.manual_seed(1234 + rank)
     for c in range(M):                                    # torch-default Linear init (kaiming-uniform bound 1/sqrt(K))
@@ -260,9 +287,10 @@ def run_ours(a):
     finite = bool(torch.isfinite(stats).all().item())
 
     # ---- roofline of the fused train step (all launches of one optimiser step, all candidates) ----
-    cnt = algorithmic_counts(g.layouts[0], B)
+    cnts = [algorithmic_counts(l_, B) for l_ in g.layouts]
+    cnt = {k: sum(c_[k] for c_ in cnts) / M for k in cnts[0]}          # per-candidate mean (the candidates of cfg2 are identical)
     engine = g.engine
-    g_n_params = g.layouts[0].n_params
+    g_n_params = sum(int(l_.n_params) for l_ in g.layouts) / M
     rows = ptr[:, 0, :B].contiguous()
     for _ in range(5):
         g.train_step(train_dev, rows, 1e-4)
@@ -286,14 +314,14 @@ def run_ours(a):
     traffic, per_kernel_traffic = None, {}
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
-        if tj.get("workload") == "cfg2":
+        if tj.get("workload") == "cfg2" and wl["name"] == "cfg2":
             per_kernel_traffic = {k: v * M for k, v in tj["dram_bytes_per_launch_per_candidate"].items()}
             traffic = float(sum(per_kernel_traffic.values()))
     except Exception:
         pass
     # the three kernels of the step, each timed with CUDA events on the launching stream (C ABI: mfas_group_last_step_ms)
     kernels = []
-    if engine == "tc":
+    if engine == "tc" and wl["name"] == "cfg2":
         lay = g.layouts[0]
         L, Hh = lay.L, lay.H
         k_feat = sum(lay.d_ske[l] + lay.d_rgb[l] for l in range(L))
@@ -322,8 +350,9 @@ def run_ours(a):
         except Exception as ex:                      # profiling is an aid, never the measurement itself
             kernels = [{"error": str(ex)}]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": f"fused train step of {M} candidates ({engine} engine: k_tc_fwd_ws -> k_chain_all -> k_tc_bwd_ws, 3 launches; "
-                          f"achieved = SURVEY 8(d) algorithmic bytes of the whole step / CUDA-event time of the whole step)",
+                "kernel": f"fused train step of {M} candidates (" + ("tc engine: k_tc_fwd_ws -> k_chain_all -> k_tc_bwd_ws, 3 launches; " if engine == "tc" else
+                                                                       "ffma engine (inner_repr below the MMA tiles): per-layer CUDA-core kernels; ") +
+                          "achieved = SURVEY 8(d) algorithmic bytes of the whole step / CUDA-event time of the whole step)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": M * cnt["train_bytes"], "ms_per_launch": t_step * 1e3,
                 "tensor_tflops": M * (cnt["fwd_flops"] + cnt["bwd_flops"]) / t_step / 1e12,
@@ -338,7 +367,6 @@ def run_ours(a):
             host_train = synthetic_ntu_cache(N_TRAIN, 1).pin()
             host_dev = synthetic_ntu_cache(N_DEV, 2).pin()
         loaders = {"train": FeatureCacheLoader(host_train, B, True, 100), "dev": FeatureCacheLoader(host_dev, B, True, 200)}
-        all_confs = [np.array(CONF4) for _ in range(M * n_gpus)]
         n_params = int(g_n_params)
 
         def measure(init_on_device):
@@ -380,7 +408,7 @@ def run_ours(a):
 
     cpu = None
     gpu_eager = None
-    if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
+    if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline and wl["name"] == "cfg2":
         cpu = cpu_reference_sample(a.cpu_sample_steps)
         try:
             gpu_eager = gpu_eager_reference_sample(device)
@@ -390,7 +418,7 @@ def run_ours(a):
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(a, n_gpus), "clocks": clk, "e2e": e2e, "e2e_device_init": e2e_dev, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "reference_gpu_eager": gpu_eager, "finite": finite,
             "hbm_ceiling_cand_epochs_per_s_per_gpu": peak * 1e9 / (steps_tr * cnt["train_bytes"] + steps_dv * cnt["eval_bytes"])}))
