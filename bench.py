@@ -303,6 +303,16 @@ def run_ours(a):
     r1.record()
     torch.cuda.synchronize()
     t_step = r0.elapsed_time(r1) / 1e3 / n_t
+    # one dev pass (eval steps: forward stream + forward chain + head, running BatchNorm statistics)
+    for _ in range(2):
+        g.eval_pass(dev_dev, B, pdv[:, 0])
+    torch.cuda.synchronize()
+    r0.record()
+    for _ in range(3):
+        g.eval_pass(dev_dev, B, pdv[:, 0])
+    r1.record()
+    torch.cuda.synchronize()
+    t_eval = r0.elapsed_time(r1) / 1e3 / 3 / steps_dv
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -355,6 +365,8 @@ def run_ours(a):
                           "achieved = SURVEY 8(d) algorithmic bytes of the whole step / CUDA-event time of the whole step)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": M * cnt["train_bytes"], "ms_per_launch": t_step * 1e3,
+                "eval_step": {"ms": t_eval * 1e3, "algorithmic_bytes": M * cnt["eval_bytes"], "achieved": M * cnt["eval_bytes"] / t_eval / 1e9,
+                              "frac": M * cnt["eval_bytes"] / t_eval / 1e9 / peak},
                 "tensor_tflops": M * (cnt["fwd_flops"] + cnt["bwd_flops"]) / t_step / 1e12,
                 "kernels": kernels}
     g.close()

@@ -390,6 +390,7 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
       umma::tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < NPAD / 32; ++cc) {
+        if (q * 32 >= it.rows_valid) break;                        // lane quarter beyond H (inner_repr 16 / 32 / 64): rows of zeros nobody reads
         float v[32], w[32];
         umma::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 2 * NPAD + cc * 32), v);
         umma::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 2 * NPAD + NPAD + cc * 32), w);
@@ -723,7 +724,7 @@ __device__ __forceinline__ void chain_wait(ChainCtx& cx) {      // wait for the 
 
 // accT[m, b] = sum_{j < Kd} A[m, j] X[b, j]: stage (hi/lo split) and issue, in passes of PASS columns of j.
 //   A: rows m < rows_valid of a row-major matrix with row stride ldA (rows beyond are zero), X: batch rows b < nrows, stride ldX
-// Both operands K-major SW128; the caller waits for the last commit with chain_wait().  Kd % 64 == 0.
+// Both operands K-major SW128; the caller waits for the last commit with chain_wait().  Kd in {16, 32} or Kd % 64 == 0.
 template <int NPAD>
 __device__ __forceinline__ void chain_mma_kmajor(ChainCtx& cx, const float* A, long long ldA, int rows_valid,
                                                  const float* X, int ldX, int Kd, int nrows, int stamp_layer = -1) {
@@ -739,7 +740,7 @@ __device__ __forceinline__ void chain_mma_kmajor(ChainCtx& cx, const float* A, l
   constexpr uint32_t idesc = umma::idesc_tf32(128, NPAD, false, false);
   for (int j0 = 0; j0 < Kd; j0 += PASS) {                             // passes of <= NKB k-blocks
     const int jw = min(PASS, Kd - j0), f4 = jw >> 2;                  // float4 per row in this pass
-    const int fsh = 31 - __clz(f4);                                   // Kd % 64 == 0 and PASS in {64, 128}: f4 is 16 or 32 -- no integer divisions in the staging loops
+    const int fsh = 31 - __clz(f4);                                   // jw in {16, 32, 64, 128}: f4 is a power of two -- no integer divisions in the staging loops
     if (j0 > 0) { chain_wait(cx); if (!cx.ok) break; }
     for (int i0 = tid; i0 < 128 * f4; i0 += THREADS * 4) {            // A: 128 rows
       float4 t[4];
@@ -954,7 +955,7 @@ k_chain_fwd(const DCand* __restrict__ cands, int layer, int nrows, int bmax, con
 // ---------------------------------------------------------------------------------------------
 // accT[c, b] = sum_{h < Kd} U[h, c] G[b, h]: stage (hi/lo split) and issue, in passes of PASS rows h.
 //   U: rows h < k_valid (zero beyond) of a row-major matrix with row stride ldU, columns c < mw (zero beyond);
-//   G: batch rows b < nrows with row stride ldG, readable (and zero) up to column Kd.   Kd % 64 == 0.
+//   G: batch rows b < nrows with row stride ldG, readable (and zero) up to column Kd.   Kd in {16, 32} or Kd % 64 == 0.
 // A = U as an MN-major tile (one smem row per h), B = G K-major; the caller waits for the last commit with chain_wait().
 template <int NPAD>
 __device__ __forceinline__ void chain_mma_mnmajor(ChainCtx& cx, const float* U, long long ldU, int k_valid, int Kd, int mw,
@@ -1538,7 +1539,7 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
     // Two-deep software pipeline so that no wait sits on a chain of dependent loads: the tile descriptor
     // and the 8 gather indices of tile i+2 are fetched while the x / dz loads of tile i+1 are in flight
     // (r01 ncu: with index -> x load pairs issued one after the other the stagers, not HBM, set the pace).
-    struct Desc { const float* src; const float* dz; long long ld; int H, kw; int row[8]; };
+    struct Desc { const float* src; const float* dz; long long ld; int H, kw; int row[8]; };   // kw = valid x columns | valid dz columns (H < 64) << 16
     float4 xv[8], dv[4];
     auto fetch_desc = [&](int i, Desc& d) {
       const int4 t = *reinterpret_cast<const int4*>(&tiles[blockIdx.x + i * gridDim.x].cand);   // {cand, layer, kc0, h0}
@@ -1547,7 +1548,7 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
       bool gather = true;
       if (t.y >= cd.L) {                                // the classifier as one more layer: x = h_L, dz = dlogits (zero-padded to 64 classes)
         d.src = cd.hid + (long long)(cd.L - 1) * bmax * H + kc0; d.ld = H; gather = false;
-        d.H = TC_DLOG_LD; d.kw = min(TC_BWD_KT, H - kc0);
+        d.H = TC_DLOG_LD; d.kw = min(TC_BWD_KT, H - kc0) | (TC_BWD_HT << 16);
         d.dz = cd.dlog;
       } else {
         const DLayer& ly = cd.layer[t.y];
@@ -1555,7 +1556,7 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
         if (kc0 < fs) { d.src = cache.ske[ly.ske_tap] + kc0; d.ld = cache.ske_ld[ly.ske_tap]; }
         else if (kc0 < fs + fr) { d.src = cache.rgb[ly.rgb_tap] + (kc0 - fs); d.ld = cache.rgb_ld[ly.rgb_tap]; }
         else { d.src = cd.hid + (long long)(t.y - 1) * bmax * H + (kc0 - fs - fr); d.ld = H; gather = false; }
-        d.H = H; d.kw = min(TC_BWD_KT, ly.K - kc0);
+        d.H = H; d.kw = min(TC_BWD_KT, ly.K - kc0) | (min(TC_BWD_HT, H - t.w) << 16);
         d.dz = cd.dzs + (long long)t.y * bmax * H + t.w;
       }
 #pragma unroll
@@ -1565,17 +1566,18 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
       }
     };
     auto issue_loads = [&](const Desc& d) {             // unconditional loads from clamped addresses, then select
-      const int c4 = tid & 31, cc = min(c4 * 4, d.kw - 4);
+      const int kw = d.kw & 0xffff, hw = d.kw >> 16;
+      const int c4 = tid & 31, cc = min(c4 * 4, kw - 4);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 x = __ldg(reinterpret_cast<const float4*>(d.src + (long long)d.row[j] * d.ld + cc));
-        xv[j] = (warp + 8 * j < nrows && c4 * 4 < d.kw) ? x : make_float4(0.f, 0.f, 0.f, 0.f);
+        xv[j] = (warp + 8 * j < nrows && c4 * 4 < kw) ? x : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int idx = tid + 256 * j, r = idx >> 4, cd4 = idx & 15;
-        const float4 x = *reinterpret_cast<const float4*>(d.dz + (long long)min(r, nrows - 1) * d.H + cd4 * 4);
-        dv[j] = (r < nrows) ? x : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 x = *reinterpret_cast<const float4*>(d.dz + (long long)min(r, nrows - 1) * d.H + min(cd4 * 4, hw - 4));
+        dv[j] = (r < nrows && cd4 * 4 < hw) ? x : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     Desc d1{};
@@ -1635,7 +1637,7 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
     const uint32_t ring_u32 = umma::smem_u32(ring);
     const int srow = lane >> 3, schunk = lane & 7;     // cp.async: a lane moves 16 B of row (4*u + srow)
     const uint64_t stream_policy = l2_stream_policy((err.l2_hints & 2) != 0);
-    struct Tile { float* W; long long K, moff, voff, goff; bool valid; int rows; };   // rows: valid rows of this warp's 32 (64-row tiles: 32; the classifier tile: C - 32 cg, clamped)
+    struct Tile { float* W; long long K, moff, voff, goff; int rc; };   // rc = rows | cols << 8: valid rows / columns of this warp's 32 x 32 (0 columns: nothing to do)   // rows: valid rows of this warp's 32 (64-row tiles: 32; the classifier tile: C - 32 cg, clamped)
     struct Raw { int4 a, b, c; };                      // first 48 bytes of a BwdTile
     auto fetch_raw = [&](int i) {
       const int4* r = reinterpret_cast<const int4*>(&tiles[blockIdx.x + i * gridDim.x]);
@@ -1649,19 +1651,21 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
       o.voff = ((long long)(uint32_t)r.b.y << 32) | (uint32_t)r.b.x;
       o.goff = KEEP_GRAD ? (((long long)(uint32_t)r.b.w << 32) | (uint32_t)r.b.z) : 0;
       o.K = r.c.x;
-      o.valid = q * 32 < r.c.y;
-      o.rows = min(32, max(0, r.c.z - cg * 32));
+      // 64-row x 128-column tiles of a fusion layer: 32 | 32 << 8; fewer rows in the classifier tile and for inner_repr < 64,
+      // fewer columns in the last chunk of a layer (the 16 / 32 / 64 hidden columns)
+      o.rc = min(32, max(0, r.c.z - cg * 32)) | (min(32, max(0, r.c.y - q * 32)) << 8);
       o.W = reinterpret_cast<float*>(Wbits) + (long long)(cg * 32) * o.K + q * 32;   // first row / column of this warp
       return o;
     };
     // request batch j (rows 8j .. 8j+7 of this warp's 32) of tile t into ring slot j; always commits a group
     auto request = [&](const Tile& t, int j) {
-      if (t.valid) {
+      if (t.rc >> 8) {
+        const int rows = t.rc & 255, cols = t.rc >> 8;
         const uint32_t dst = ring_u32 + j * WS_SLOT + srow * 128 + schunk * 16;
         const float* w = t.W + (long long)(8 * j + srow) * t.K + schunk * 4;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          if (8 * j + 4 * u + srow < t.rows) {
+          if (8 * j + 4 * u + srow < rows && schunk * 4 < cols) {
             const float* wu = w + (long long)(4 * u) * t.K;
             cp_async16(dst + u * 512, wu, stream_policy);
             cp_async16(dst + 1024 + u * 512, wu + t.moff, stream_policy);
@@ -1692,7 +1696,7 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
         __syncwarp();
         float g[8];
         umma::tmem_ld8(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 64 + cg * 32 + 8 * j), g);
-        if (cur.valid) {
+        if (cur.rc >> 8) {
           const float* sp = reinterpret_cast<const float*>(ring + j * WS_SLOT) + lane;
           float* w = cur.W + (long long)(8 * j) * cur.K + lane;
           float p[8], m[8], v[8];
@@ -1700,7 +1704,7 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
           for (int r = 0; r < 8; ++r) { p[r] = sp[r * 32]; m[r] = sp[256 + r * 32]; v[r] = sp[512 + r * 32]; }
 #pragma unroll
           for (int r = 0; r < 8; ++r) adam_update_fast(g[r], p[r], m[r], v[r], adam, step_size, inv_bc2);
-          if (8 * j + 8 <= cur.rows) {                 // (always, except in the classifier tile)
+          if (cur.rc == (32 | (32 << 8))) {             // full 32 x 32 (always, except in the classifier tile and for inner_repr < 64)
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
               if (KEEP_GRAD) w[cur.goff] = g[r];
@@ -1710,7 +1714,7 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
           } else {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-              if (8 * j + r < cur.rows) {
+              if (8 * j + r < (cur.rc & 255) && lane < (cur.rc >> 8)) {
                 if (KEEP_GRAD) w[cur.goff] = g[r];
                 w[0] = p[r]; w[cur.moff] = m[r]; w[cur.voff] = v[r];
               }

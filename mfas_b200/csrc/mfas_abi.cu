@@ -370,9 +370,14 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     return code;
   }
   // ---- engine selection: tensor cores whenever the shapes fit the MMA tiles -----------------------
+  auto l_small_ok = [](const mfas_layout& l) { return l.C <= TC_DLOG_LD; };     // small inner_repr needs the tensor-core head
   bool tc_ok = true;
   for (int c = 0; c < n_cand; ++c) {
-    tc_ok = tc_ok && (g->lay[c].H % 64 == 0);
+    // inner_repr 16 / 32 (the search default) ride the same tiles with most rows masked; that needs the row / column
+    // masks of the persistent kernels and the fused chain, i.e. batch <= 64 and none of the stage-by-stage overrides
+    const bool small_ok = batch_max <= 64 && !getenv("MFAS_BWD") && !getenv("MFAS_FWD") && !getenv("MFAS_CHAIN") && !getenv("MFAS_HEAD") &&
+                          l_small_ok(g->lay[c]);
+    tc_ok = tc_ok && (g->lay[c].H % 64 == 0 || ((g->lay[c].H == 16 || g->lay[c].H == 32) && small_ok));
     tc_ok = tc_ok && !(g->lay[c].flags & MFAS_FLAG_ALPHAS);      // the modality gates are built in the CUDA-core engine only
     g->any_alphas = g->any_alphas || (g->lay[c].flags & MFAS_FLAG_ALPHAS);
     for (int l = 0; l < g->lay[c].L; ++l) tc_ok = tc_ok && g->lay[c].d_ske[l] % 128 == 0 && g->lay[c].d_rgb[l] % 128 == 0;
@@ -380,7 +385,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
   const char* env = getenv("MFAS_ENGINE");
   if (env && !strcmp(env, "ffma")) tc_ok = false;
   if (env && !strcmp(env, "tc") && !tc_ok) {
-    int code = fail(MFAS_ERR_UNSUPPORTED, "MFAS_ENGINE=tc needs inner_representation_size %% 64 == 0, tap widths %% 128 == 0 and alphas off");
+    int code = fail(MFAS_ERR_UNSUPPORTED, "MFAS_ENGINE=tc needs inner_representation_size 16, 32 or a multiple of 64, tap widths %% 128 == 0 and alphas off");
     mfas_group_destroy(g);
     return code;
   }
@@ -581,7 +586,8 @@ static int sync_descriptors(mfas_group* g, cudaStream_t st) {
         } else {
           const DLayer& ly = d.layer[t.y];
           r.W = d.p + ly.oW + (long long)t.w * ly.K + t.z;
-          r.K = ly.K; r.kw = ly.K - t.z < TC_BWD_KT ? ly.K - t.z : TC_BWD_KT; r.rows = TC_BWD_HT;
+          r.K = ly.K; r.kw = ly.K - t.z < TC_BWD_KT ? ly.K - t.z : TC_BWD_KT;
+          r.rows = d.H - t.w < TC_BWD_HT ? d.H - t.w : TC_BWD_HT;
         }
         r.cand = t.x; r.layer = t.y; r.kc0 = t.z; r.h0 = t.w; r.pad1 = 0;
       }

@@ -421,6 +421,9 @@ def test_full_size_properties_cfg2():
     (256, 128, 128, [[1, 3, 0], [3, 0, 1]]),
     (192, 128, 100, [[0, 1, 2], [2, 2, 0]]),
     (128, 32, 24, [[2, 0, 1]]),
+    (16, 64, 64, [[3, 1, 1], [1, 3, 0]]),                       # the search default inner_repr: masked rows / columns of the same tiles
+    (16, 64, 37, [[0, 0, 2]]),
+    (32, 8, 8, FOUND_CONFS[0]),                                 # cfg1 shapes
 ])
 def test_tc_engine_step_vs_oracle(H, B, nrows, conf):
     """The tcgen05 (3xTF32) engine on every tile shape it serves: one optimiser step, gradients at 1e-4."""
