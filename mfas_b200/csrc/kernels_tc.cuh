@@ -290,16 +290,34 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
     const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);   // sw128(r + 16 j, 16 c) = off + 2048 j
     const uint32_t s0 = umma::smem_u32(smem);
     const uint64_t stream_policy = l2_stream_policy((err.l2_hints & 1) != 0);
+    // Two-deep software pipeline over the item list, so that no item starts on a chain of dependent loads (descriptor ->
+    // gather indices -> first cp.async): the descriptor of item i+2 and the row indices of item i+1 are requested while
+    // the k-blocks of item i are issued (r01t ncu: long-scoreboard was this kernel's top stall; an item is only ~24 k-blocks).
+    auto load_rows = [&](const FwdItem& it, int* rows) {
+#pragma unroll
+      for (int j = 0; j < XJ; ++j) {
+        const int row = r + 16 * j;
+        rows[j] = batch_row(batch, it.cand, row < nrows ? row : 0);
+      }
+    };
+    FwdItem cur{}, nxt{};
+    int rows_cur[XJ], rows_nxt[XJ];
+#pragma unroll
+    for (int j = 0; j < XJ; ++j) rows_cur[j] = rows_nxt[j] = 0;
+    if (n_my > 0) { cur = items[blockIdx.x]; load_rows(cur, rows_cur); }
+    if (n_my > 1) nxt = items[blockIdx.x + gridDim.x];
     int n = 0;
     for (int i = 0; i < n_my && ok; ++i) {
-      const FwdItem it = items[blockIdx.x + i * gridDim.x];
+      if (i + 1 < n_my) load_rows(nxt, rows_nxt);
+      FwdItem nx2{};
+      if (i + 2 < n_my) nx2 = items[blockIdx.x + (i + 2) * gridDim.x];
+      const FwdItem& it = cur;
       const long long wstride = 16LL * it.K;
       const float* wp = it.W + (long long)r * it.K + c * 4;        // &W[m0 + r][4 c]
       const float* xs[XJ]; const float* xr[XJ];                    // gathered rows of the two taps, indexed by concat column
 #pragma unroll
       for (int j = 0; j < XJ; ++j) {
-        const int row = r + 16 * j;
-        const long long gr = batch_row(batch, it.cand, row < nrows ? row : 0);
+        const long long gr = rows_cur[j];
         xs[j] = cache.ske[it.ske_tap] + gr * cache.ske_ld[it.ske_tap] + c * 4;
         xr[j] = cache.rgb[it.rgb_tap] + gr * cache.rgb_ld[it.rgb_tap] + c * 4 - 32LL * it.fs_kb;
       }
@@ -316,6 +334,9 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
         for (int j = 0; j < XJ; ++j) cp_async16_zfill(b + j * 2048, (ske ? xs[j] : xr[j]) + 32LL * kb, r + 16 * j < nrows, stream_policy);
         cp_async_arrive_noinc(&landed[sg]);
       }
+      cur = nxt; nxt = nx2;
+#pragma unroll
+      for (int j = 0; j < XJ; ++j) rows_cur[j] = rows_nxt[j];
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp < 12) {
@@ -351,15 +372,17 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
     // ================================ MMA issuer ==================================================
     constexpr uint32_t idesc = umma::idesc_tf32(128, NPAD, false, false);
     int n = 0;
+    auto nkb_of = [&](int i) { const FwdItem& it = items[blockIdx.x + i * gridDim.x]; return it.kb1 - it.kb0; };
+    int nkb_next = n_my > 0 ? nkb_of(0) : 0;                       // one item ahead: the issue loop never waits for a descriptor
     for (int i = 0; i < n_my && ok; ++i) {
-      const FwdItem& it = items[blockIdx.x + i * gridDim.x];
-      const int nkb = it.kb1 - it.kb0, tb = i & 1;
+      const int nkb = nkb_next, tb = i & 1;
+      if (i + 1 < n_my) nkb_next = nkb_of(i + 1);
       if (!umma::mbar_wait(&tempty[tb], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
       for (int k = 0; k < nkb; ++k, ++n) {
         const int sg = n % R, sl = n % LQ;
         if (!umma::mbar_wait(&lofull[sl], (n / LQ) & 1)) { ok = false; break; }
         umma::tc_fence_after();
-        if (lane == 0) {
+        if (umma::elect_one()) {
           const uint32_t a_hi = umma::smem_u32(smem) + sg * Cfg::TILE, b_hi = a_hi + Cfg::A_BYTES;
           const uint32_t a_lo = umma::smem_u32(lo_base) + sl * Cfg::TILE, b_lo = a_lo + Cfg::A_BYTES;
 #pragma unroll
@@ -382,8 +405,12 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
   } else {
     // ================================ epilogue ====================================================
     const int q = warp & 3;                                        // TMEM lane quarter this warp may read
+    struct Ep { long long part_off; int rows_valid, Hp; };
+    auto ep_of = [&](int i) { const FwdItem& f = items[blockIdx.x + i * gridDim.x]; return Ep{f.part_off, f.rows_valid, f.Hp}; };
+    Ep ep_next = n_my > 0 ? ep_of(0) : Ep{0, 0, 0};
     for (int i = 0; i < n_my; ++i) {
-      const FwdItem& it = items[blockIdx.x + i * gridDim.x];
+      const Ep it = ep_next;
+      if (i + 1 < n_my) ep_next = ep_of(i + 1);
       const int tb = i & 1;
       float4* dst = reinterpret_cast<float4*>(part_base + it.part_off) + (q * 32 + lane);   // part_off includes the row tile
       if (!umma::mbar_wait(&tfull[tb], (i >> 1) & 1)) { ok = false; break; }
@@ -774,10 +801,10 @@ __device__ __forceinline__ void chain_mma_kmajor(ChainCtx& cx, const float* A, l
     chain_stamp(cx, stamp_layer);    // 12: B staged
     umma::fence_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32 && umma::elect_one()) {
       // One thread issues on behalf of the CTA, so its instruction stream IS the critical path here (r01 timeline:
-      // 4.9 k cycles for 64 MMAs with the descriptors rebuilt per k-step): base descriptors once, compile-time
-      // offsets in a fully unrolled loop, and three products (lo x lo is 2^-22 of the result, as in the streaming kernels).
+      // 4.9 k cycles for 64 MMAs behind `tid == 0`, i.e. an ELECT / R2UR / BRA.U.ANY loop around every MMA): elect.sync
+      // leader, compile-time offsets in a fully unrolled loop, and three products (lo x lo is 2^-22 of the result).
       umma::tc_fence_after();
       const uint64_t dah0 = umma::smem_desc(umma::smem_u32(a_hi), 16, 1024), dal0 = umma::smem_desc(umma::smem_u32(a_lo), 16, 1024);
       const uint64_t dbh0 = umma::smem_desc(umma::smem_u32(b_hi), 16, 1024), dbl0 = umma::smem_desc(umma::smem_u32(b_lo), 16, 1024);
@@ -1004,7 +1031,7 @@ __device__ __forceinline__ void chain_mma_mnmajor(ChainCtx& cx, const float* U, 
     }
     umma::fence_async_smem();
     __syncthreads();
-    if (tid == 0) {                                                   // (see chain_mma_kmajor)
+    if (tid < 32 && umma::elect_one()) {                              // (see chain_mma_kmajor)
       umma::tc_fence_after();
       const uint64_t dah0 = umma::smem_desc(umma::smem_u32(a_hi), A_BLK, 512, umma::kLayoutSw128Base32);
       const uint64_t dal0 = umma::smem_desc(umma::smem_u32(a_lo), A_BLK, 512, umma::kLayoutSw128Base32);
@@ -1610,7 +1637,7 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
       if (!umma::mbar_wait(&full, i & 1)) { ok = false; break; }
       if (!umma::mbar_wait(&tempty[tb], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
       umma::tc_fence_after();
-      if (lane == 0) {
+      if (umma::elect_one()) {
         const uint32_t a_hi = umma::smem_u32(smem), a_lo = a_hi + A_TILE, b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
         const uint32_t d = tm + tb * 64;
         for (int ks = 0; ks < ksteps; ++ks) {

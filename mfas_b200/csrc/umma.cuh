@@ -64,6 +64,25 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       : "memory");
 }
 
+// One lane of a converged warp (CUTLASS's elect_one_sync).  Branching on this instead of `lane == 0` tells the compiler that
+// exactly one thread issues the tcgen05 instructions that follow: it then keeps the descriptors in uniform registers and
+// emits straight UTCHMMAs, where a `lane == 0` branch gets an ELECT / R2UR.BROADCAST / BRA.U.ANY loop around every MMA
+// (12-20 instructions, ~90 cycles per MMA against the tensor pipe's 32: r01 SASS of k_tc_fwd_ws).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 %%rx;\n\t"
+      ".reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t"
+      "}\n"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+
 // arrive on an mbarrier once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
