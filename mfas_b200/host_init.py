@@ -59,6 +59,32 @@ def kaiming_bound(fan_in: int) -> float:
     return math.sqrt(3.0) * (gain / math.sqrt(fan_in))
 
 
+_TEMPLATES = {}
+
+
+def _template(group, c, visit):
+    """The tensors of candidate ``c`` in constructor order as (kind, in buffer arena, offset, numel, bound, shape), cached
+    per layout: a search iteration initialises hundreds of candidates that share a handful of layouts."""
+    key = bytes(group.layouts[c])
+    tpl = _TEMPLATES.get(key)
+    if tpl is None:
+        tpl = []
+
+        def rec(name, kind, fan_in):
+            arena, off, shape = group.slots[c][name]
+            n = int(np.prod(shape)) if shape else 1
+            if kind in ("kaiming", "uniform"):
+                bound = kaiming_bound(fan_in) if kind == "kaiming" else (1 / math.sqrt(fan_in) if fan_in > 0 else 0)
+                tpl.append((0, arena == "b", int(off), n, bound, shape))
+            else:
+                tpl.append(({"ones": 1, "zeros": 2, "normal": 3}[kind], arena == "b", int(off), n, 0.0, shape))
+        visit(group, c, rec)
+        if len(_TEMPLATES) > 4096:
+            _TEMPLATES.clear()
+        _TEMPLATES[key] = tpl
+    return tpl
+
+
 def init_host_arenas_fast(group, host_p, host_b, visit, slots=None) -> bool:
     """Same result as ntu_searchable.init_host_arenas (torch initialisers in constructor order), through the bulk
     helper.  ``visit(group, slot, fill)`` enumerates the tensors.  Returns False (nothing touched) if the helper is
@@ -106,23 +132,21 @@ def init_host_arenas_fast(group, host_p, host_b, visit, slots=None) -> bool:
         normals.clear()
 
     base_p, base_b = host_p.data_ptr(), host_b.data_ptr()
+    np_p, np_b = host_p.numpy(), host_b.numpy()        # views of the same (pinned) memory
+    p_off, b_off = group.p_off.tolist(), group.b_off.tolist()
     for c in slot_list:
-        def fill(name, kind, fan_in, c=c):
-            nonlocal state, cache_valid, n_raw, sbuf
-            arena, off, shape = group.slots[c][name]
-            o = int(group.b_off[c] if arena == "b" else group.p_off[c]) + int(off)
-            n = int(np.prod(shape)) if shape else 1
-            if kind in ("kaiming", "uniform"):
-                bound = kaiming_bound(fan_in) if kind == "kaiming" else (1 / math.sqrt(fan_in) if fan_in > 0 else 0)
-                pend[0].append((base_b if arena == "b" else base_p) + 4 * o)
+        pb, bb = int(p_off[c]), int(b_off[c])
+        for kind, is_b, off, n, bound, shape in _template(group, c, visit):
+            o = (bb if is_b else pb) + off
+            if kind == 0:                                  # kaiming / uniform
+                pend[0].append((base_b if is_b else base_p) + 4 * o)
                 pend[1].append(n); pend[2].append(-bound); pend[3].append(bound)
-                return
-            t = (host_b if arena == "b" else host_p)[o:o + n]
-            if kind == "ones":
-                t.fill_(1.0)
-            elif kind == "zeros":
-                t.zero_()
-            elif kind == "normal" and n == 1:
+            elif kind == 1:
+                (np_b if is_b else np_p)[o:o + n] = 1.0
+            elif kind == 2:
+                (np_b if is_b else np_p)[o:o + n] = 0.0
+            elif n == 1:                                   # scalar normal
+                t = (host_b if is_b else host_p)[o:o + 1]
                 if cache_valid:
                     normals.append((t, None))
                     cache_valid = False
@@ -132,7 +156,8 @@ def init_host_arenas_fast(group, host_p, host_b, visit, slots=None) -> bool:
                     normals.append((t, n_raw))
                     n_raw += 4
                     cache_valid = True
-            elif kind == "normal":            # larger tensors take torch's vectorised normal_fill: left to torch
+            else:                                          # larger tensors take torch's vectorised normal_fill: left to torch
+                t = (host_b if is_b else host_p)[o:o + n]
                 flush()
                 finish_normals()
                 struct.pack_into("d", sbuf, 5024, cached if cache_valid else 0.0)
@@ -143,7 +168,6 @@ def init_host_arenas_fast(group, host_p, host_b, visit, slots=None) -> bool:
                 sbuf = state.numpy()
                 cache_valid = bool(struct.unpack_from("i", sbuf, 5040)[0])
                 cached = struct.unpack_from("d", sbuf, 5024)[0]
-        visit(group, c, fill)
     flush()
     finish_normals()
     struct.pack_into("d", sbuf, 5024, cached if cache_valid else 0.0)
