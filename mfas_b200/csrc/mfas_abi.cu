@@ -217,6 +217,10 @@ struct mfas_group {
   int n_bwd_tiles = 0, n_bwd_layer_tiles = 0, n_sms = 148, bwd_ws = 1;
   FwdItem* fwd_items = nullptr;   // item list of the persistent forward kernel (device), rebuilt when arenas are rebound
   int n_fwd_items = 0, fwd_ws = 1, fwd_xr = 0;
+  FwdItem* fwd_items_ev = nullptr; // the same items with the partial-sum offsets of the 128-row eval layout
+  size_t items_ev_bytes = 0;
+  bool ev128 = false;             // dev / test passes run 128 rows per step (tc engine, batch <= 64): W is read half as often
+  long long part_stride_ev = 0;
   bool any_alphas = false;
   int l2_hints = 1;
   bool tchead = false;            // classifier head on the tensor core inside k_chain_all (+ its dW as a k_tc_bwd_ws tile)
@@ -251,6 +255,7 @@ extern "C" int mfas_group_destroy(mfas_group_t g) {
   pool_free(g->device, g->part, g->part_bytes);
   pool_free(g->device, g->bwd_tiles, g->tiles_bytes);
   pool_free(g->device, g->fwd_items, g->items_bytes);
+  pool_free(g->device, g->fwd_items_ev, g->items_ev_bytes);
   for (auto& ev : g->prof_ev) if (ev) cudaEventDestroy(ev);
   pool_free(g->device, g->tc_err, g->err_bytes);
   pool_free(g->device, g->timeline, g->tl_bytes);
@@ -299,15 +304,16 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     g->Cmax = l.C > g->Cmax ? l.C : g->Cmax;
     for (int k = 0; k < l.L; ++k) g->Kmax[k] = l.K[k] > g->Kmax[k] ? l.K[k] : g->Kmax[k];
     const size_t lbh = (size_t)l.L * batch_max * l.H * sizeof(float);
+    const int rows_ev = batch_max <= 64 ? 128 : batch_max;       // dev passes may run 128 rows per step (eval rows are independent)
     Off& o = off[c];
     o.act = total; total += up(lbh);
-    o.hid = total; total += up(lbh);
+    o.hid = total; total += up((size_t)l.L * rows_ev * l.H * sizeof(float));
     o.dh = total; total += up(lbh);
     o.dz = total; total += up((size_t)batch_max * l.H * sizeof(float));
     o.dzs = total; total += up(lbh);
     o.mu = total; total += up((size_t)l.L * l.H * sizeof(float));
     o.invstd = total; total += up((size_t)l.L * l.H * sizeof(float));
-    o.logits = total; total += up((size_t)batch_max * l.C * sizeof(float));
+    o.logits = total; total += up((size_t)rows_ev * l.C * sizeof(float));
     o.dsp = total; total += up((size_t)MFAS_MAX_LAYERS * MFAS_DSP_SLOTS * sizeof(float));
     o.dlog = total; total += up((size_t)batch_max * TC_DLOG_LD * sizeof(float));
     o.best_p = total; total += up((size_t)l.n_params * sizeof(float));
@@ -407,8 +413,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     g->smem_tc_bwd = 1024 + 2 * (size_t)(4 * g->npad * 128) + 2 * (size_t)(2 * g->npad * 128);
     g->smem_fl = sizeof(float) * ((size_t)batch_max * (g->Hmax + 1) + TC_CB * (size_t)g->Hmax);
     g->smem_dzx = sizeof(float) * ((size_t)batch_max * g->Hmax + (TC_CB + 1) * (size_t)g->Hmax);
-    e = pool_alloc(device, sizeof(float) * g->part_stride * n_cand, (void**)&g->part, &g->part_bytes);
-    if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(int), &g->tc_err, &g->err_bytes);
+    e = pool_alloc_t(device, sizeof(int), &g->tc_err, &g->err_bytes);
     if (e == cudaSuccess) e = cudaMemset(g->tc_err, 0, sizeof(int));
     auto attr = [&](const void* f, size_t bytes) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -483,6 +488,16 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       attr((const void*)k_tc_fwd_ws<64, 1>, FwdWs<64, 1>::SMEM);
       attr((const void*)k_tc_fwd_ws<128, 1>, FwdWs<128, 1>::SMEM);
       { const char* xe = getenv("MFAS_FWD_XR"); if (xe) g->fwd_xr = atoi(xe) ? 1 : 0; }
+    }
+    // wide eval: needs the persistent forward (its item list carries the partial-sum offsets) and the tensor-core head
+    g->ev128 = g->fwd_ws && g->tchead && g->npad == 64;
+    { const char* ee = getenv("MFAS_EVAL128"); if (ee && !atoi(ee)) g->ev128 = false; }
+    g->part_stride_ev = (long long)g->items_fwd * Hp * 128;
+    if (e == cudaSuccess)
+      e = pool_alloc(device, sizeof(float) * (g->ev128 ? g->part_stride_ev : g->part_stride) * n_cand, (void**)&g->part, &g->part_bytes);
+    if (g->ev128) {
+      if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(FwdItem) * g->n_fwd_items, &g->fwd_items_ev, &g->items_ev_bytes);
+      attr((const void*)k_chain_all<false, 128, true>, g->smem_chain_all);
     }
     { const char* de = getenv("MFAS_TC_DEBUG"); if (de) g->dbg = atoi(de); }
     { const char* le = getenv("MFAS_L2_HINTS"); if (le) g->l2_hints = atoi(le) & 3; }
@@ -623,6 +638,14 @@ static int sync_descriptors(mfas_group* g, cudaStream_t st) {
       std::stable_sort(its.begin(), its.end(), [](const FwdItem& a, const FwdItem& b) { return a.kb1 - a.kb0 > b.kb1 - b.kb0; });
       if ((int)its.size() != g->n_fwd_items) return fail(MFAS_ERR_INVALID, "internal: forward item count changed");
       CUDA_TRY(cudaMemcpyAsync(g->fwd_items, its.data(), sizeof(FwdItem) * its.size(), cudaMemcpyHostToDevice, st));
+      if (g->fwd_items_ev) {                            // same items, partial sums laid out for 128 batch rows
+        for (FwdItem& it : its) {
+          const long long rel = it.part_off - (long long)it.cand * g->part_stride;     // (item index) * Hp * npad + 4 m0
+          const long long idx = rel / ((long long)Hp * g->npad), m4 = rel % ((long long)Hp * g->npad);
+          it.part_off = (long long)it.cand * g->part_stride_ev + idx * Hp * 128 + m4;
+        }
+        CUDA_TRY(cudaMemcpyAsync(g->fwd_items_ev, its.data(), sizeof(FwdItem) * its.size(), cudaMemcpyHostToDevice, st));
+      }
     }
     g->dirty = false;
   }
@@ -669,10 +692,12 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
   const dim3 gf(g->items_fwd, (g->Hmax + 127) / 128, g->n_cand), gl((g->Hmax + TC_CB - 1) / TC_CB, g->n_cand);
   const bool prof = g->prof && train && g->chain == 2;
   if (prof) { g->prof_valid = false; cudaEventRecord(g->prof_ev[0], st); }
+  const bool wide = g->ev128 && !train && !bn_train && batch.n_rows > 64;      // a 128-row dev / test step
   if (g->fwd_ws) {
     const int grid = g->n_fwd_items < g->n_sms ? g->n_fwd_items : g->n_sms;
-#define FW(N, X) k_tc_fwd_ws<N, X><<<grid, FwdWs<N, X>::THREADS, FwdWs<N, X>::SMEM, st>>>(g->fwd_items, g->n_fwd_items, cache, batch, g->part, terr)
-    if (g->npad == 64) { if (g->fwd_xr) FW(64, 1); else FW(64, 0); }
+    const FwdItem* items = wide ? g->fwd_items_ev : g->fwd_items;
+#define FW(N, X) k_tc_fwd_ws<N, X><<<grid, FwdWs<N, X>::THREADS, FwdWs<N, X>::SMEM, st>>>(items, g->n_fwd_items, cache, batch, g->part, terr)
+    if (g->npad == 64 && !wide) { if (g->fwd_xr) FW(64, 1); else FW(64, 0); }
     else { if (g->fwd_xr) FW(128, 1); else FW(128, 0); }
 #undef FW
   } else if (g->npad == 64) k_tc_fwd_all<64><<<gf, TC_THREADS, g->smem_tc_fwd, st>>>(g->dc, cache, batch, g->part, g->part_stride, terr);
@@ -684,7 +709,9 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
   if (prof) cudaEventRecord(g->prof_ev[1], st);
   if (g->chain == 2 && train == bn_train) {           // the whole serial chain in one launch
 #define CA(T, N, TH) k_chain_all<T, N, TH><<<g->n_cand, ChainCfg<N>::THREADS, g->smem_chain_all, st>>>(g->dc, cache, batch, g->bmax, g->part, g->part_stride, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, ho, terr)
-    if (g->tchead) { if (train) CA(true, 64, true); else CA(false, 64, true); }
+    if (wide)
+      k_chain_all<false, 128, true><<<g->n_cand, ChainCfg<128>::THREADS, g->smem_chain_all, st>>>(g->dc, cache, batch, 128, g->part, g->part_stride_ev, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, ho, terr);
+    else if (g->tchead) { if (train) CA(true, 64, true); else CA(false, 64, true); }
     else if (g->npad == 64) { if (train) CA(true, 64, false); else CA(false, 64, false); }
     else { if (train) CA(true, 128, false); else CA(false, 128, false); }
 #undef CA
@@ -845,7 +872,7 @@ extern "C" int mfas_train_run(mfas_group_t g, const mfas_cache_desc* train, cons
   if ((rc = to_dcache(g, dev, &ddv))) return rc;
   const long long ntr = dtr.n_rows, ndv = ddv.n_rows;
   const int B = a->batch;
-  const long long steps_tr = (ntr + B - 1) / B, steps_dv = (ndv + B - 1) / B;
+  const long long steps_tr = (ntr + B - 1) / B;
   const int last_tr = (int)(ntr - (steps_tr - 1) * B);
   if ((rc = check_batch(g, last_tr, true))) return rc;
   if ((rc = sync_descriptors(g, st))) return rc;
@@ -865,9 +892,14 @@ extern "C" int mfas_train_run(mfas_group_t g, const mfas_cache_desc* train, cons
       if ((rc = launch_step(g, dtr, b, true, true, a->step_size[t], a->bc2_sqrt[t], (uint32_t)(a->adam_t0 + t), ho, st)))
         return rc;
     }
-    for (long long s = 0; s < steps_dv; ++s) {             // phase 'dev'
-      const int n = (int)((s == steps_dv - 1) ? ndv - (steps_dv - 1) * B : B);
-      BatchRef b{a->perm_dev, (long long)E * ndv, (a->perm_dev ? (long long)e * ndv : 0) + s * B, n};
+    // phase 'dev': rows are independent in eval mode (running BatchNorm statistics, no dropout), so the pass may use
+    // its own step width -- 128 rows when the wide eval path is on: the weights are streamed half as often.  Accuracy
+    // counts are unchanged; the size-weighted loss sum differs by fp32 summation order only.
+    const int Bd = g->ev128 ? 128 : B;
+    const long long steps_dv_w = (ndv + Bd - 1) / Bd;
+    for (long long s = 0; s < steps_dv_w; ++s) {
+      const int n = (int)((s == steps_dv_w - 1) ? ndv - (steps_dv_w - 1) * Bd : Bd);
+      BatchRef b{a->perm_dev, (long long)E * ndv, (a->perm_dev ? (long long)e * ndv : 0) + s * Bd, n};
       HeadOut ho{nullptr, nullptr, nullptr, a->stats, stat_stride, 4LL * e + 2};
       if ((rc = launch_step(g, ddv, b, false, false, 0.f, 1.f, 0u, ho, st))) return rc;
     }
@@ -890,6 +922,7 @@ extern "C" int mfas_eval_pass(mfas_group_t g, const mfas_cache_desc* cache, cons
   if ((rc = to_dcache(g, cache, &dc))) return rc;
   if ((rc = sync_descriptors(g, st))) return rc;
   CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * g->n_cand, st));
+  if (g->ev128) batch = 128;                               // (see mfas_train_run, phase 'dev')
   const long long n = dc.n_rows, steps = (n + batch - 1) / batch;
   for (long long s = 0; s < steps; ++s) {
     const int nr = (int)((s == steps - 1) ? n - (steps - 1) * batch : batch);
