@@ -248,6 +248,11 @@ __device__ __forceinline__ uint64_t l2_stream_policy(bool evict_first) {
   else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, bool valid, uint64_t policy) {
   const int n = valid ? 16 : 0;    // src-size 0: the 16 destination bytes are zero-filled, src is not read
   asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst_smem), "l"(src), "r"(n), "l"(policy) : "memory");
@@ -290,6 +295,8 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
     const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);   // sw128(r + 16 j, 16 c) = off + 2048 j
     const uint32_t s0 = umma::smem_u32(smem);
     const uint64_t stream_policy = l2_stream_policy((err.l2_hints & 1) != 0);
+    // the gathered x rows are read again by the backward stream of the same step: bit 2 = default priority, bit 3 = evict-last
+    const uint64_t x_policy = (err.l2_hints & 8) ? l2_keep_policy() : (err.l2_hints & 4) ? l2_stream_policy(false) : stream_policy;
     // Two-deep software pipeline over the item list, so that no item starts on a chain of dependent loads (descriptor ->
     // gather indices -> first cp.async): the descriptor of item i+2 and the row indices of item i+1 are requested while
     // the k-blocks of item i are issued (r01t ncu: long-scoreboard was this kernel's top stall; an item is only ~24 k-blocks).
@@ -331,7 +338,7 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
         for (int j = 0; j < WJ; ++j) cp_async16_zfill(a + j * 2048, w + j * wstride, r + 16 * j < it.rows_valid, stream_policy);
         const bool ske = kb < it.fs_kb;
 #pragma unroll
-        for (int j = 0; j < XJ; ++j) cp_async16_zfill(b + j * 2048, (ske ? xs[j] : xr[j]) + 32LL * kb, r + 16 * j < nrows, stream_policy);
+        for (int j = 0; j < XJ; ++j) cp_async16_zfill(b + j * 2048, (ske ? xs[j] : xr[j]) + 32LL * kb, r + 16 * j < nrows, x_policy);
         cp_async_arrive_noinc(&landed[sg]);
       }
       cur = nxt; nxt = nx2;

@@ -500,7 +500,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       attr((const void*)k_chain_all<false, 128, true>, g->smem_chain_all);
     }
     { const char* de = getenv("MFAS_TC_DEBUG"); if (de) g->dbg = atoi(de); }
-    { const char* le = getenv("MFAS_L2_HINTS"); if (le) g->l2_hints = atoi(le) & 3; }
+    { const char* le = getenv("MFAS_L2_HINTS"); if (le) g->l2_hints = atoi(le) & 15; }
     if (e != cudaSuccess) {
       int code = fail(MFAS_ERR_CUDA, "tc engine setup: %s", cudaGetErrorString(e));
       mfas_group_destroy(g);

@@ -588,3 +588,73 @@ def test_multitask_head_on_tensor_core_engine():
     _close(logits[0].cpu().numpy(), ol, TOL, "multitask fusion logits")
     assert abs(float(loss[0]) - float(oloss)) < TOL * float(oloss)
     assert int(correct[0]) == int((opreds == y).sum())
+
+
+@pytest.mark.gpu
+def test_wide_eval_and_small_inner_repr_agree_with_the_plain_paths(monkeypatch):
+    """Two structural shortcuts of the tensor-core engine against the paths they replace: (1) dev / test passes in 128-row
+    steps (MFAS_EVAL128) must count exactly the same correct predictions as 64-row steps and agree on the loss sum to
+    fp32 summation order; (2) inner_repr 16 on the masked MMA tiles must train like the CUDA-core engine."""
+    conf, H, B = FOUND_CONFS[4], 128, 64
+    dev = synthetic_ntu_cache(300, 21).to(DEV)              # 300 = 2 x 128 + 44: wide steps and a narrow tail
+    init = init_states([conf, FOUND_CONFS[1]], H, 60, True, 0.0, 5)
+    outs = {}
+    for wide in ("1", "0"):
+        monkeypatch.setenv("MFAS_EVAL128", wide)
+        g = _group([conf, FOUND_CONFS[1]], H, B)
+        assert g.engine == "tc"
+        for k in range(2):
+            g.load_state(k, init[k])
+        perm = torch.stack([torch.randperm(300, generator=torch.Generator().manual_seed(9 + k)) for k in range(2)])
+        outs[wide] = g.eval_pass(dev, B, perm).cpu()
+        g.check()
+    monkeypatch.delenv("MFAS_EVAL128")
+    assert torch.equal(outs["1"][:, 1], outs["0"][:, 1]), "wide eval changed the number of correct predictions"
+    _close(outs["1"][:, 0].numpy(), outs["0"][:, 0].numpy(), 1e-6, "wide eval loss sum")
+
+    confs = [[[3, 1, 1], [1, 3, 0]], [[0, 0, 2]], [[2, 2, 0], [3, 3, 1], [1, 0, 0]]]
+    H, B, E, ntr, ndv = 16, 32, 2, 96, 160
+    train, dev = synthetic_ntu_cache(ntr, 15).to(DEV), synthetic_ntu_cache(ndv, 16).to(DEV)
+    inits = init_states(confs, H, 60, True, 0.0, 2)
+    lrs = [1e-3] * (E * math.ceil(ntr / B))
+    gen = torch.Generator().manual_seed(3)
+    ptr = torch.stack([torch.stack([torch.randperm(ntr, generator=gen) for _ in range(E)]) for _ in confs])
+    pdv = torch.stack([torch.stack([torch.randperm(ndv, generator=gen) for _ in range(E)]) for _ in confs])
+    res = {}
+    for engine in ("tc", "ffma"):
+        monkeypatch.setenv("MFAS_ENGINE", engine)
+        g = _group(confs, H, B, keep_grads=True)
+        assert g.engine == engine
+        for k in range(len(confs)):
+            g.load_state(k, inits[k])
+        lg, loss, _ = g.train_step(train, ptr[:, 0, :B], lr=1e-3)
+        grads = g.grads.clone().cpu()
+        st, best, _ = g.train_run(train, dev, ptr, pdv, lrs, E, B)
+        g.check()
+        res[engine] = (lg.cpu(), grads, st.cpu(), best.cpu())
+    _close(res["tc"][0].numpy(), res["ffma"][0].numpy(), 1e-5, "inner_repr 16: tc vs ffma logits")
+    _close(res["tc"][1].numpy(), res["ffma"][1].numpy(), 5e-5, "inner_repr 16: tc vs ffma gradients", scale=float(res["ffma"][1].abs().max()))
+    _close(res["tc"][2][:, :, 0].numpy(), res["ffma"][2][:, :, 0].numpy(), TRAJ_LOSS, "inner_repr 16: tc vs ffma epoch loss")
+
+
+@pytest.mark.gpu
+def test_group_blocks_are_recycled_and_released():
+    """mfas_group_destroy parks the group's device blocks, the next group of the same shape gets them back (same
+    workspace address), and mfas_release_cached_memory hands everything to the driver."""
+    from mfas_b200 import _lib
+    conf = [[3, 1, 1], [1, 3, 0]]
+    free0 = torch.cuda.mem_get_info()[0]
+    g = _group([conf] * 8, 64, 32)
+    init = init_states([conf], 64, 60, True, 0.0, 1)[0]
+    g.load_state(0, init)
+    lg1, _, _ = g.forward(synthetic_ntu_cache(64, 3).to(DEV), torch.arange(32), train=False)
+    g.close()
+    during = torch.cuda.mem_get_info()[0]
+    g2 = _group([conf] * 8, 64, 32)                     # recycled blocks are zeroed again: results do not depend on history
+    g2.load_state(0, init)
+    lg2, _, _ = g2.forward(synthetic_ntu_cache(64, 3).to(DEV), torch.arange(32), train=False)
+    assert torch.equal(lg1[0], lg2[0])
+    g2.close()
+    assert _lib.lib().mfas_release_cached_memory() == 0
+    after = torch.cuda.mem_get_info()[0]
+    assert after >= during, (free0, during, after)
