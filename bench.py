@@ -219,7 +219,12 @@ def run_ours(a):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout at the first collective; the contract is ONE JSON line there
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         td.init_process_group("nccl", device_id=device)
     n_gpus = world
 
@@ -427,6 +432,10 @@ def run_ours(a):
         except Exception as ex:                      # a reported baseline, never the measurement itself
             gpu_eager = {"error": str(ex)}
 
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
