@@ -696,6 +696,24 @@ k_dzx(const DCand* __restrict__ cands, int layer, int nrows, int bmax, AdamH ada
   }
 }
 
+// 16-byte cp.async without a cache hint; src-size 0 zero-fills the destination and reads nothing
+__device__ __forceinline__ void cp_async16_zf(uint32_t dst_smem, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// lo = rna_tf32(x - trunc_tf32(x)) of one 16-byte chunk of a raw operand tile (the raw tile itself is the hi operand:
+// kind::tf32 reads the top 19 bits of each container), written to the same offset of the lo tile
+__device__ __forceinline__ void lo_of_chunk(const uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off) {
+  const float4 x = *reinterpret_cast<const float4*>(hi_tile + off);
+  float4 l;
+  l.x = umma::round_tf32(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
+  l.y = umma::round_tf32(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+  l.z = umma::round_tf32(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
+  l.w = umma::round_tf32(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+  *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Chain kernels on the tensor core.  The per-layer steps of the serial chain (hidden-state GEMM +
 // BatchNorm forward, and its mirror image backward) are tiny, so what matters is latency: one CTA per
@@ -776,34 +794,29 @@ __device__ __forceinline__ void chain_mma_kmajor(ChainCtx& cx, const float* A, l
     const int jw = min(PASS, Kd - j0), f4 = jw >> 2;                  // float4 per row in this pass
     const int fsh = 31 - __clz(f4);                                   // jw in {16, 32, 64, 128}: f4 is a power of two -- no integer divisions in the staging loops
     if (j0 > 0) { chain_wait(cx); if (!cx.ok) break; }
-    for (int i0 = tid; i0 < 128 * f4; i0 += THREADS * 4) {            // A: 128 rows
-      float4 t[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
-        t[u] = (i < 128 * f4 && r < rows_valid) ? *reinterpret_cast<const float4*>(A + (long long)r * ldA + j0 + c4 * 4)
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
-        if (i < 128 * f4) store_split(a_hi, a_lo, (uint32_t)(c4 >> 3) * A_KB + umma::sw128(r, (c4 & 7) * 16), t[u]);
-      }
+    // Staging: every 16-byte chunk of both operands goes global -> shared with cp.async (all of a thread's chunks in
+    // flight at once: ONE memory round trip per pass instead of three dependent LDG -> split -> STS rounds, r01o
+    // timeline: 8 k cycles), landing as the hi tiles; the thread then derives the lo chunks of what it fetched.
+    const uint32_t a_hi_u = umma::smem_u32(a_hi), b_hi_u = umma::smem_u32(b_hi);
+    for (int i = tid; i < 128 * f4; i += THREADS) {                   // A: 128 rows
+      const int r = i >> fsh, c4 = i & (f4 - 1);
+      const bool v = r < rows_valid;
+      cp_async16_zf(a_hi_u + (uint32_t)(c4 >> 3) * A_KB + umma::sw128(r, (c4 & 7) * 16), v ? A + (long long)r * ldA + j0 + c4 * 4 : A, v);
     }
-    chain_stamp(cx, stamp_layer);    // 11: A staged
-    for (int i0 = tid; i0 < NPAD * f4; i0 += THREADS * 4) {           // B: batch rows
-      float4 t[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
-        t[u] = (i < NPAD * f4 && r < nrows) ? *reinterpret_cast<const float4*>(X + (long long)r * ldX + j0 + c4 * 4)
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
-        if (i < NPAD * f4) store_split(b_hi, b_lo, (uint32_t)(c4 >> 3) * B_KB + umma::sw128(r, (c4 & 7) * 16), t[u]);
-      }
+    for (int i = tid; i < NPAD * f4; i += THREADS) {                  // B: batch rows
+      const int r = i >> fsh, c4 = i & (f4 - 1);
+      const bool v = r < nrows;
+      cp_async16_zf(b_hi_u + (uint32_t)(c4 >> 3) * B_KB + umma::sw128(r, (c4 & 7) * 16), v ? X + (long long)r * ldX + j0 + c4 * 4 : X, v);
+    }
+    cp_async_wait_all();
+    chain_stamp(cx, stamp_layer);    // 11: raw tiles landed
+    for (int i = tid; i < 128 * f4; i += THREADS) {
+      const int r = i >> fsh, c4 = i & (f4 - 1);
+      lo_of_chunk(a_hi, a_lo, (uint32_t)(c4 >> 3) * A_KB + umma::sw128(r, (c4 & 7) * 16));
+    }
+    for (int i = tid; i < NPAD * f4; i += THREADS) {
+      const int r = i >> fsh, c4 = i & (f4 - 1);
+      lo_of_chunk(b_hi, b_lo, (uint32_t)(c4 >> 3) * B_KB + umma::sw128(r, (c4 & 7) * 16));
     }
     chain_stamp(cx, stamp_layer);    // 12: B staged
     umma::fence_async_smem();
@@ -1007,34 +1020,26 @@ __device__ __forceinline__ void chain_mma_mnmajor(ChainCtx& cx, const float* U, 
   for (int h0 = 0; h0 < Kd; h0 += PASS) {                            // passes of PASS rows of U
     const int hw = min(PASS, Kd - h0);
     if (h0 > 0) { chain_wait(cx); if (!cx.ok) break; }
-    for (int i0 = tid; i0 < hw * 32; i0 += THREADS * 4) {            // A: hw rows (h) x 32 float4 (128 columns)
-      float4 t[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * THREADS, r = i >> 5, c4 = i & 31;
-        t[u] = (i < hw * 32 && c4 * 4 < mw && h0 + r < k_valid) ? *reinterpret_cast<const float4*>(U + (long long)(h0 + r) * ldU + c4 * 4)
-                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * THREADS, r = i >> 5, c4 = i & 31;
-        if (i < hw * 32) store_split(a_hi, a_lo, (uint32_t)(c4 >> 3) * A_BLK + umma::sw128_b32(r, (c4 & 7) * 16), t[u]);
-      }
-    }
+    const uint32_t a_hi_u = umma::smem_u32(a_hi), b_hi_u = umma::smem_u32(b_hi);      // (staging: see chain_mma_kmajor)
     const int f4 = hw >> 2, fsh = 31 - __clz(f4);
-    for (int i0 = tid; i0 < NPAD * f4; i0 += THREADS * 4) {          // B: batch rows of G[:, h0:h0+hw]
-      float4 t[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
-        t[u] = (i < NPAD * f4 && r < nrows) ? *reinterpret_cast<const float4*>(G + (long long)r * ldG + h0 + c4 * 4)
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * THREADS, r = i >> fsh, c4 = i & (f4 - 1);
-        if (i < NPAD * f4) store_split(b_hi, b_lo, (uint32_t)(c4 >> 3) * B_KB + umma::sw128(r, (c4 & 7) * 16), t[u]);
-      }
+    for (int i = tid; i < hw * 32; i += THREADS) {                   // A: hw rows (h) x 32 float4 (128 columns)
+      const int r = i >> 5, c4 = i & 31;
+      const bool v = c4 * 4 < mw && h0 + r < k_valid;
+      cp_async16_zf(a_hi_u + (uint32_t)(c4 >> 3) * A_BLK + umma::sw128_b32(r, (c4 & 7) * 16), v ? U + (long long)(h0 + r) * ldU + c4 * 4 : U, v);
+    }
+    for (int i = tid; i < NPAD * f4; i += THREADS) {                 // B: batch rows of G[:, h0:h0+hw]
+      const int r = i >> fsh, c4 = i & (f4 - 1);
+      const bool v = r < nrows;
+      cp_async16_zf(b_hi_u + (uint32_t)(c4 >> 3) * B_KB + umma::sw128(r, (c4 & 7) * 16), v ? G + (long long)r * ldG + h0 + c4 * 4 : G, v);
+    }
+    cp_async_wait_all();
+    for (int i = tid; i < hw * 32; i += THREADS) {
+      const int r = i >> 5, c4 = i & 31;
+      lo_of_chunk(a_hi, a_lo, (uint32_t)(c4 >> 3) * A_BLK + umma::sw128_b32(r, (c4 & 7) * 16));
+    }
+    for (int i = tid; i < NPAD * f4; i += THREADS) {
+      const int r = i >> fsh, c4 = i & (f4 - 1);
+      lo_of_chunk(b_hi, b_lo, (uint32_t)(c4 >> 3) * B_KB + umma::sw128(r, (c4 & 7) * 16));
     }
     umma::fence_async_smem();
     __syncthreads();

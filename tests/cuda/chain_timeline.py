@@ -32,6 +32,6 @@ for i, n in enumerate(names):
 print("  total      %9.0f %9.0f" % (np.median(out[:, 9] - out[:, 0]), (out[:, 9] - out[:, 0]).max()))
 inner = out[:, 10:16]
 t0 = inner[:, 0]
-print("inside forward layer 1 (cycles since the layer was entered, median): A staged %d | B staged %d | MMAs issued %d | z complete (partials, MMA, bias, act) %d | BN stats %d | (layer end %d)" % (
+print("inside forward layer 1 (cycles since the layer was entered, median): raw operand tiles landed (cp.async) %d | lo tiles written %d | MMAs issued %d | z complete (partials, MMA, bias, act) %d | BN stats %d | (layer end %d)" % (
     np.median(inner[:, 1] - t0), np.median(inner[:, 2] - t0), np.median(inner[:, 3] - t0), np.median(inner[:, 4] - t0),
     np.median(inner[:, 5] - t0), np.median(out[:, 2] - t0)))
