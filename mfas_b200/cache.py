@@ -121,6 +121,15 @@ def _mix32(x):
     return x ^ (x >> 16)
 
 
+def hashed_orders_of(seed: int, pass_ids, n: int, device="cpu") -> torch.Tensor:
+    """``hashed_orders`` for an arbitrary list of pass numbers (a rank's share of a sharded call): int64 [len(ids), n]."""
+    dev = torch.device(device)
+    k = torch.as_tensor(list(pass_ids), dtype=torch.int64, device=dev)[:, None]
+    i = torch.arange(n, dtype=torch.int64, device=dev)[None, :]
+    key = _mix32(_mix32((int(seed) & _M32) * 0x9E3779B1 + k * 0x85EBCA6B) + i)
+    return torch.sort(key, dim=1, stable=True).indices
+
+
 def hashed_orders(seed: int, first_pass: int, count: int, n: int, device="cpu") -> torch.Tensor:
     """Row orders of ``count`` consecutive passes as an int64 [count, n] tensor: pass k visits rows in
     the (stable) argsort of hash(seed, k, row).  Pure integer arithmetic, so the CPU (reference loop,
@@ -160,6 +169,13 @@ class FeatureCacheLoader:
         if not self.shuffle:
             return torch.arange(n, dtype=torch.int64, device=device).repeat(count, 1)
         return hashed_orders(self.seed, first_pass, count, n, device)
+
+    def orders_of(self, pass_ids, device="cpu") -> torch.Tensor:
+        """int64 [len(pass_ids), N] row orders of the given passes (any subset, any order), built on ``device``."""
+        n = len(self.dataset)
+        if not self.shuffle:
+            return torch.arange(n, dtype=torch.int64, device=device).repeat(len(pass_ids), 1)
+        return hashed_orders_of(self.seed, pass_ids, n, device)
 
     def order_for_pass(self, k: int) -> torch.Tensor:
         return self.orders(int(k), 1)[0]

@@ -479,8 +479,11 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
                 return torch.zeros(len(js), 0, n_rows, dtype=torch.int32, device=device)
             if js == list(range(js[0], js[0] + len(js))):                   # contiguous share: one batched sort
                 return pass_orders(loader, first + js[0] * E, len(js) * E, n_rows, device).view(len(js), E, n_rows)
-            if hasattr(loader, "orders"):                                   # round-robin share: sort the covering range once,
-                lo, hi = min(js), max(js)                                   # then pick this rank's candidates
+            if hasattr(loader, "orders_of"):                                # round-robin share: one batched sort of exactly
+                ids = [first + j * E + e for j in js for e in range(E)]     # this rank's passes
+                return loader.orders_of(ids, device).to(torch.int32).view(len(js), E, n_rows)
+            if hasattr(loader, "orders"):                                   # sort the covering range once, then pick
+                lo, hi = min(js), max(js)
                 allp = pass_orders(loader, first + lo * E, (hi - lo + 1) * E, n_rows, device).view(hi - lo + 1, E, n_rows)
                 return allp[torch.tensor([j - lo for j in js], device=allp.device)]
             return torch.stack([pass_orders(loader, first + j * E, E, n_rows, device) for j in js])

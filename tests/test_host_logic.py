@@ -145,6 +145,9 @@ def test_loader_orders_are_placement_independent():
     k = a.take_passes(6)
     assert k == 0 and a.passes == 6
     assert torch.equal(a.order_for_pass(4), b.order_for_pass(4))
+    # a rank's share of a sharded call (any subset of passes, one batched sort) sees the orders of the full range
+    full, share = a.orders(0, 6), a.orders_of([5, 1, 3])
+    assert torch.equal(share[0], full[5]) and torch.equal(share[1], full[1]) and torch.equal(share[2], full[3])
     batches = list(iter(b))
     assert len(batches) == 7 and batches[-1]['rgb'].shape == (2, 5632) and set(batches[0]) == {'rgb', 'ske', 'label'}
     assert torch.equal(torch.cat([x['label'] for x in batches]), c.labels[b.order_for_pass(0)])
