@@ -175,12 +175,15 @@ int mfas_train_step(mfas_group_t g, const mfas_cache_desc* cache, const int32_t*
 
 /* The production path: num_epochs x (train pass + dev pass) for every candidate, best-dev
  * snapshot and final rollback, nothing returns to the host in between
- * (train_searchable/ntu.py:14-89). */
+ * (train_searchable/ntu.py:14-89).  The dev pass is an eval-mode pass (see mfas_eval_pass for its step width). */
 int mfas_train_run(mfas_group_t g, const mfas_cache_desc* train, const mfas_cache_desc* dev,
                    const mfas_run_args* args, void* stream);
 
 /* Accuracy pass in eval mode (test_ntu_track_acc, train_searchable/ntu.py:92-125).
- * d_perm: [n_cand][n_rows] or NULL = identity. d_out: [n_cand][2] loss sum, #correct. */
+ * d_perm: [n_cand][n_rows] or NULL = identity. d_out: [n_cand][2] loss sum, #correct.
+ * Rows are independent in eval mode (running BatchNorm statistics, no dropout), so `batch` only bounds the step width:
+ * on the tensor-core engine with batch_max <= 64 the pass runs 128 rows per step (the weights are streamed half as
+ * often); #correct is unchanged, the loss sum differs by fp32 summation order.  MFAS_EVAL128=0 keeps `batch`. */
 int mfas_eval_pass(mfas_group_t g, const mfas_cache_desc* cache, const int32_t* d_perm, int32_t batch,
                    double* d_out, void* stream);
 
@@ -198,6 +201,9 @@ int mfas_group_chain_timeline(mfas_group_t g, int64_t* out, int32_t n_cand);
  * stream, bit-identical to torch.nn.init.uniform_/kaiming_uniform_ applied in the same order -- what the reference
  * constructor does for every candidate (models/search/ntu_searchable.py:200, :274-282 via nn.Linear.reset_parameters).
  * torch_rng_state is the byte buffer of torch.get_rng_state() (legacy 5056-byte mt19937 layout), advanced in place.
+ * count[op] < 0 asks for -count[op] raw tempered 32-bit words instead (dst is then a uint32_t array): the caller turns
+ * them into draws of other distributions (the Box-Muller normals of the scalar alphas, ntu_searchable.py:202-204).
+ * Fills of 4 M words and more are pipelined over threads (MFAS_HOST_INIT_THREADS consumers, default 2; 0 = serial).
  * use_fma selects x*(to-from)+from as one fused multiply-add (what an FMA-contracting ATen build computes) or as two
  * roundings.  Returns MFAS_ERR_UNSUPPORTED if the buffer does not look like a seeded mt19937 state. */
 int mfas_host_uniform_fill(uint8_t* torch_rng_state, int64_t state_bytes, int32_t n_ops, float* const* dst,
