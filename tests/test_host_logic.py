@@ -191,3 +191,30 @@ def test_sharding_and_gather_world2_gloo():
     for r in res:
         assert r[2] == [10.0 + j for j in range(7)]                      # every rank sees all results, in input order
         assert r[3] == pytest.approx(float(ref.rgb_cat.sum())) and r[4] == int(ref.labels.sum())
+
+
+def test_sliced_threaded_initialisation_equals_one_serial_fill(monkeypatch):
+    """train_sampled_models fills the pinned arena a quarter of the candidates at a time (so the H2D copies overlap) and
+    the C helper pipelines fills of >= 4 M words over threads: same bytes and same generator state as one serial fill."""
+    import mfas_b200.ntu_searchable as ntu
+    from mfas_b200 import _lib, host_init
+    from mfas_b200.engine import GroupLayout
+    if host_init._self_check() < 0:
+        pytest.skip("bulk helper does not reproduce torch's uniform_ on this CPU")
+    confs = [np.array(FOUND_CONFS[4])] * 21 + [np.array([[2, 3, 1]])] * 3      # 22 M words; an odd number of alphas
+    g = GroupLayout(confs, 128, 60, _lib.FLAG_BN)
+    outs = []
+    for threads, sliced in (("0", False), ("2", True), ("3", False)):
+        monkeypatch.setenv("MFAS_HOST_INIT_THREADS", threads)
+        hp, hb = torch.zeros(int(g.p_off[-1])), torch.zeros(int(g.b_off[-1]))
+        torch.manual_seed(123)
+        torch.rand(77)
+        if sliced:
+            for c0 in range(0, g.n, 7):
+                ntu.init_host_arenas(g, hp, hb, slots=range(c0, min(g.n, c0 + 7)))
+        else:
+            ntu.init_host_arenas(g, hp, hb)
+        outs.append((hp, hb, torch.cat([torch.empty(1).normal_(), torch.rand(3)])))
+    for hp, hb, after in outs[1:]:
+        assert torch.equal(hp, outs[0][0]) and torch.equal(hb, outs[0][1])
+        assert torch.equal(after, outs[0][2]), "generator state diverged"
