@@ -167,3 +167,16 @@ def test_oracle_matches_reference_found_flow_multitask():
         ref = g[f"final/{k}/sample"]
         got = sample_tensor(v)["sample"]
         assert np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30) < 0.05, k
+
+
+def test_mmimdb_head_matches_reference():
+    """SURVEY 8(f)-1, first piece: the weighted BCE-with-logits loss, its hand-derived gradient and the F1-samples metric
+    of the MM-IMDB head against the reference class (autograd gradient) and sklearn, executed by gen_golden_mmimdb.py."""
+    from oracle import mmimdb_head as MH
+    fx = np.load(os.path.join(GOLDEN_DIR, "mmimdb_head.npz"))
+    for name in ("a", "b", "c"):
+        loss, dl = MH.weighted_bce_with_logits(fx[f"{name}_logits"], fx[f"{name}_targets"], fx[f"{name}_pos_weight"])
+        assert abs(float(loss) - float(fx[f"{name}_loss"])) < 1e-5 * abs(float(fx[f"{name}_loss"])), name
+        ref = fx[f"{name}_dlogits"]
+        assert np.abs(dl - ref).max() < 1e-4 * np.abs(ref).max(), (name, np.abs(dl - ref).max(), np.abs(ref).max())
+        assert abs(MH.f1_samples(fx[f"{name}_logits"], fx[f"{name}_targets"]) - float(fx[f"{name}_f1"])) < 1e-12, name
