@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MFAS_ABI_VERSION 1
+#define MFAS_ABI_VERSION 2
 
 #define MFAS_MAX_LAYERS 8     /* fusion steps per candidate (reference max_fusions default 4)   */
 #define MFAS_MAX_BATCH 128    /* rows per batch (BASELINE configs use 8, 64, 128)               */
@@ -48,7 +48,11 @@ enum {
   MFAS_FLAG_BN = 1,        /* args.batchnorm : Linear -> act -> BatchNorm1d     (ntu_searchable.py:274-282) */
   MFAS_FLAG_DROPOUT = 2,   /* args.drpt>1e-10: ... -> Dropout(p)                (ntu_searchable.py:274-279) */
   MFAS_FLAG_ALPHAS = 4,    /* args.alphas    : AlphaScalarMultiplication gate   (aux_models.py:94-111)      */
-  MFAS_FLAG_MULTITASK = 8  /* args.multitask : + cached backbone logits         (train_searchable/ntu.py:59-61) */
+  MFAS_FLAG_MULTITASK = 8, /* args.multitask : + cached backbone logits         (train_searchable/ntu.py:59-61) */
+  MFAS_FLAG_MULTILABEL = 16 /* MM-IMDB head: WeightedCrossEntropyWithLogits (aux_models.py:129-147) on multi-hot
+                              * targets instead of softmax-CE; the per-batch statistic is the sum of per-sample F1 of
+                              * sigmoid(logits) > 0.3 (train_searchable/mmimdb.py:84,101) instead of #correct.  All candidates
+                              * of a group share this flag; such groups run on the CUDA-core engine. */
 };
 
 enum { MFAS_ACT_RELU = 0, MFAS_ACT_SIGMOID = 1, MFAS_ACT_LRELU = 2 };  /* conf[:,2], ntu_searchable.py:267-272 */
@@ -63,9 +67,11 @@ typedef struct mfas_cache_desc {
   int64_t rgb_ld[MFAS_NUM_TAPS];
   int32_t d_ske[MFAS_NUM_TAPS];
   int32_t d_rgb[MFAS_NUM_TAPS];
-  const int64_t* labels;     /* [n_rows] */
+  const int64_t* labels;     /* [n_rows] class ids (single-label heads) */
   const float* logit_rgb;    /* [n_rows, C] backbone logits (multitask) or NULL */
   const float* logit_ske;
+  const float* targets;      /* [n_rows, C] multi-hot fp32 targets (MFAS_FLAG_MULTILABEL; labels may then be NULL) or NULL */
+  const float* pos_weight;   /* [C] positive-class weights of the weighted BCE (MFAS_FLAG_MULTILABEL) or NULL */
 } mfas_cache_desc;
 
 /* Where each tensor of one candidate lives inside its flat fp32 arenas.
@@ -115,8 +121,9 @@ typedef struct mfas_run_args {       /* one train_ntu_track_acc run for every ca
   const float* step_size;            /* HOST [n_epochs*ceil(n_train/batch)]: lr_t / (1-beta1^t), formed in fp64 */
   const float* bc2_sqrt;             /* HOST, same length: sqrt(1-beta2^t) */
   int64_t adam_t0;                   /* optimiser steps taken before this run */
-  double* stats;                     /* device [n_cand][n_epochs][4]: train loss sum, train correct, dev loss sum, dev correct */
-  double* best_acc;                  /* device [n_cand] best dev accuracy (strict >, starts at 0) */
+  double* stats;                     /* device [n_cand][n_epochs][4]: train loss sum, train correct, dev loss sum, dev correct
+                                      * (MFAS_FLAG_MULTILABEL: "correct" is the sum of per-sample F1 scores) */
+  double* best_acc;                  /* device [n_cand] best dev accuracy (strict >, starts at 0); MULTILABEL: best dev F1-samples */
   int32_t* best_epoch;               /* device [n_cand] epoch of best_acc or -1 */
 } mfas_run_args;
 
@@ -162,7 +169,8 @@ int mfas_group_status(mfas_group_t g);
  * (ntu_searchable.py:206-247) given cached taps. rows: device int32 row ids, candidate c reads
  * rows + c*rows_stride (stride 0 = shared batch). train!=0: BN batch statistics + running-stat
  * update (+dropout, keyed by step). d_logits: [n_cand][batch_max][C] or NULL.
- * d_loss / d_correct: [n_cand] mean CE loss and #correct of the batch, or NULL. */
+ * d_loss / d_correct: [n_cand] mean CE loss and #correct of the batch, or NULL
+ * (MFAS_FLAG_MULTILABEL: mean weighted BCE and the number of rows whose thresholded label set is exactly right). */
 int mfas_forward(mfas_group_t g, const mfas_cache_desc* cache, const int32_t* d_rows, int64_t rows_stride,
                  int32_t n_rows, int32_t train, int64_t step, float* d_logits, float* d_loss,
                  int32_t* d_correct, void* stream);

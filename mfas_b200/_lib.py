@@ -18,7 +18,7 @@ HEADERS = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "kernels_ffma.c
     os.path.join(ROOT, "include", "mfas_b200.h")]
 
 MAX_LAYERS, MAX_BATCH, MAX_HIDDEN, MAX_CLASSES, NUM_TAPS = 8, 128, 256, 64, 4
-FLAG_BN, FLAG_DROPOUT, FLAG_ALPHAS, FLAG_MULTITASK = 1, 2, 4, 8
+FLAG_BN, FLAG_DROPOUT, FLAG_ALPHAS, FLAG_MULTITASK, FLAG_MULTILABEL = 1, 2, 4, 8, 16
 ERRORS = {0: "MFAS_OK", -1: "MFAS_ERR_INVALID", -2: "MFAS_ERR_CUDA", -3: "MFAS_ERR_UNSUPPORTED",
           -4: "MFAS_ERR_NOMEM", -5: "MFAS_ERR_UNBOUND"}
 
@@ -48,7 +48,8 @@ class CacheDesc(C.Structure):
                 ("ske", C.c_void_p * NUM_TAPS), ("rgb", C.c_void_p * NUM_TAPS),
                 ("ske_ld", C.c_int64 * NUM_TAPS), ("rgb_ld", C.c_int64 * NUM_TAPS),
                 ("d_ske", C.c_int32 * NUM_TAPS), ("d_rgb", C.c_int32 * NUM_TAPS),
-                ("labels", C.c_void_p), ("logit_rgb", C.c_void_p), ("logit_ske", C.c_void_p)]
+                ("labels", C.c_void_p), ("logit_rgb", C.c_void_p), ("logit_ske", C.c_void_p),
+                ("targets", C.c_void_p), ("pos_weight", C.c_void_p)]
 
 
 class Arenas(C.Structure):
@@ -131,7 +132,7 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
-        if l.mfas_abi_version() != 1:
+        if l.mfas_abi_version() != 2:
             raise RuntimeError("ABI version mismatch; rebuild the library")
         _lib = l
     return _lib

@@ -39,16 +39,28 @@ def _offsets(widths):
 class FeatureCache:
     """One split (train / dev / test) of cached backbone taps."""
 
-    def __init__(self, ske_cat, rgb_cat, labels, vid_len_ske=32, logit_rgb=None, logit_ske=None):
-        self.d_ske = ske_widths(vid_len_ske)
-        self.d_rgb = D_RGB
+    def __init__(self, ske_cat, rgb_cat, labels, vid_len_ske=32, logit_rgb=None, logit_ske=None, widths=None,
+                 pos_weight=None):
+        """``widths`` = (first-modality tap widths, second-modality tap widths) for a tap set other than NTU's (the
+        MM-IMDB text / image taps, mfas_b200.mmimdb_searchable); the first modality rides in ``ske_cat``, the second in
+        ``rgb_cat``.  ``labels`` is int64 [N] class ids, or fp32 [N, C] multi-hot targets together with ``pos_weight``
+        [C] for the multi-label head."""
+        self.d_ske, self.d_rgb = (ske_widths(vid_len_ske), D_RGB) if widths is None else (tuple(widths[0]), tuple(widths[1]))
+        self.widths = widths if widths is None else (self.d_ske, self.d_rgb)
         assert ske_cat.dtype == torch.float32 and rgb_cat.dtype == torch.float32
         assert ske_cat.shape[1] == sum(self.d_ske), ske_cat.shape
         assert rgb_cat.shape[1] == sum(self.d_rgb), rgb_cat.shape
-        assert labels.dtype == torch.int64 and labels.shape[0] == ske_cat.shape[0] == rgb_cat.shape[0]
+        assert labels.shape[0] == ske_cat.shape[0] == rgb_cat.shape[0]
+        self.multilabel = labels.dim() == 2
+        if self.multilabel:
+            assert labels.dtype == torch.float32 and pos_weight is not None and pos_weight.dtype == torch.float32
+            assert pos_weight.shape == (labels.shape[1],), (pos_weight.shape, labels.shape)
+        else:
+            assert labels.dtype == torch.int64
         self.ske_cat = ske_cat.contiguous()
         self.rgb_cat = rgb_cat.contiguous()
         self.labels = labels.contiguous()
+        self.pos_weight = None if pos_weight is None else pos_weight.contiguous()
         self.logit_rgb = logit_rgb       # [N, C] backbone logits, only for multitask
         self.logit_ske = logit_ske
         self.vid_len_ske = vid_len_ske
@@ -62,7 +74,7 @@ class FeatureCache:
         return self.ske_cat.device
 
     def nbytes(self):
-        n = self.ske_cat.numel() * 4 + self.rgb_cat.numel() * 4 + self.labels.numel() * 8
+        n = self.ske_cat.numel() * 4 + self.rgb_cat.numel() * 4 + self.labels.numel() * self.labels.element_size()
         for t in (self.logit_rgb, self.logit_ske):
             if t is not None:
                 n += t.numel() * 4
@@ -85,6 +97,8 @@ class FeatureCache:
         if self.device.type == 'cpu' and torch.cuda.is_available() and not self.ske_cat.is_pinned():
             self.ske_cat, self.rgb_cat, self.labels = (self.ske_cat.pin_memory(), self.rgb_cat.pin_memory(),
                                                        self.labels.pin_memory())
+            if self.pos_weight is not None:
+                self.pos_weight = self.pos_weight.pin_memory()
             if self.logit_rgb is not None:
                 self.logit_rgb, self.logit_ske = self.logit_rgb.pin_memory(), self.logit_ske.pin_memory()
         return self
@@ -99,7 +113,7 @@ class FeatureCache:
             return self._device_copies[key]
         mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)
         out = FeatureCache(mv(self.ske_cat), mv(self.rgb_cat), mv(self.labels), self.vid_len_ske,
-                           mv(self.logit_rgb), mv(self.logit_ske))
+                           mv(self.logit_rgb), mv(self.logit_ske), self.widths, mv(self.pos_weight))
         if memoize:
             self._device_copies[key] = out
         return out

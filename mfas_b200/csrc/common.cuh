@@ -56,6 +56,8 @@ struct DCache {
   const long long* labels;
   const float* logit_rgb;
   const float* logit_ske;
+  const float* targets;        // [n_rows][C] multi-hot (MFAS_FLAG_MULTILABEL)
+  const float* pos_weight;     // [C]
 };
 
 struct AdamH {

@@ -282,8 +282,51 @@ __device__ __forceinline__ void head_rows(const DCand& cd, const DCache& cache, 
   }
 }
 
-// body shared by k_head and the fused chain kernel (kernels_tc.cuh: k_chain_all); blockDim.x == kHeadThreads
+// Multi-label head of the MM-IMDB fusion network, one warp per row, C <= 64:
+//   loss   L[b][c] = q_c z (-log s) + (1 - z)(-log(1 - s)), s = sigmoid(x), through the explicit sigmoid and logs of
+//          WeightedCrossEntropyWithLogits.forward (/root/reference/models/auxiliary/aux_models.py:136-146) -- NOT the
+//          stable softplus form, so a saturated logit gives the same inf / nan the reference gives;
+//   dlogits = (-q z (1 - s) + (1 - z) s) / (B C)   (mean over all B*C elements), written in place when TRAIN;
+//   metric  sigmoid(x) > 0.3 against z: true positives and |pred| + |true| of the row, from which the caller forms the
+//          per-sample F1 in fp64 (f1_score(average='samples'), train_searchable/mmimdb.py:84,101).
+// rowloss[r] = sum_c L[r][c]; rowok[r] = 1 when the thresholded set equals the label set; tpden[r] = tp | (den << 8).
 template <bool TRAIN>
+__device__ __forceinline__ void head_rows_ml(const DCand& cd, const DCache& cache, int nrows, float* lg, int lg_ld,
+                                             float* rowloss, int* rowok, int* tpden, const int* grow) {
+  const int C = cd.C, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float inv_bc = 1.f / ((float)nrows * (float)C);
+  for (int r = warp; r < nrows; r += kHeadThreads / 32) {
+    float* row = lg + r * lg_ld;
+    const float* zt = cache.targets + (long long)grow[r] * C;
+    float ls = 0.f;
+    int tp = 0, den = 0, wrong = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int c = lane + 32 * half;
+      const bool ok = c < C;
+      const float x = ok ? row[c] : 0.f, z = ok ? zt[c] : 0.f, q = ok ? cache.pos_weight[c] : 0.f;
+      const float s = 1.f / (1.f + expf(-x));
+      const float L = q * z * -logf(s) + (1.f - z) * -logf(1.f - s);
+      ls += ok ? L : 0.f;
+      const bool pred = ok && s > 0.3f, tru = ok && z > 0.5f;
+      const unsigned pb = __ballot_sync(0xffffffffu, pred), tb = __ballot_sync(0xffffffffu, tru);
+      tp += __popc(pb & tb);
+      den += __popc(pb) + __popc(tb);
+      wrong += __popc(pb ^ tb);
+      if (TRAIN && ok) row[c] = (-q * z * (1.f - s) + (1.f - z) * s) * inv_bc;
+    }
+    ls = warp_sum(ls);
+    if (lane == 0) {
+      rowloss[r] = ls;
+      rowok[r] = wrong == 0 ? 1 : 0;
+      tpden[r] = tp | (den << 8);
+    }
+    __syncwarp();
+  }
+}
+
+// body shared by k_head and the fused chain kernel (kernels_tc.cuh: k_chain_all); blockDim.x == kHeadThreads
+template <bool TRAIN, bool ML = false>
 __device__ __forceinline__ void head_body(const DCand& cd, int cand, const DCache& cache, const BatchRef& batch, int bmax,
                                           int hs_ld, int lg_ld, const AdamH& adam, float step_size, float bc2_sqrt,
                                           const HeadOut& out, float* smem) {
@@ -310,7 +353,7 @@ __device__ __forceinline__ void head_body(const DCand& cd, int cand, const DCach
   for (int r = tid; r < nrows; r += kHeadThreads) {
     const int gr = batch_row(batch, cand, r);
     grow[r] = gr;
-    lab[r] = (int)cache.labels[gr];
+    lab[r] = ML ? 0 : (int)cache.labels[gr];
   }
   __syncthreads();
 
@@ -346,19 +389,25 @@ __device__ __forceinline__ void head_body(const DCand& cd, int cand, const DCach
   }
   __syncthreads();
 
-  head_rows<TRAIN>(cd, cache, nrows, lg, lg_ld, rowloss, rowok, lab, grow, nullptr);
+  if (ML) head_rows_ml<TRAIN>(cd, cache, nrows, lg, lg_ld, rowloss, rowok, lab, grow);
+  else head_rows<TRAIN>(cd, cache, nrows, lg, lg_ld, rowloss, rowok, lab, grow, nullptr);
   __syncthreads();
   if (tid == 0) {
     float ls = 0.f;
     int ok = 0;
-    for (int r = 0; r < nrows; ++r) { ls += rowloss[r]; ok += rowok[r]; }
-    const float mean_loss = ls / (float)nrows;                    // CrossEntropyLoss(reduction='mean')
+    double f1 = 0.0;                                              // ML: sum over rows of 2 tp / (|pred| + |true|), 0 when both are empty
+    for (int r = 0; r < nrows; ++r) {
+      ls += rowloss[r]; ok += rowok[r];
+      if (ML) { const int tp = lab[r] & 255, den = lab[r] >> 8; f1 += den > 0 ? 2.0 * (double)tp / (double)den : 0.0; }
+    }
+    // CrossEntropyLoss(reduction='mean'); ML: torch.mean over all B*C elements (aux_models.py:146)
+    const float mean_loss = ML ? ls / ((float)nrows * (float)C) : ls / (float)nrows;
     if (out.loss) out.loss[cand] = mean_loss;
     if (out.correct) out.correct[cand] = ok;
-    if (out.stats) {                                              // running_loss += loss.item()*B (ntu.py:72-73)
+    if (out.stats) {                                              // running_loss += loss.item()*B (ntu.py:72-73, mmimdb.py:88)
       double* st = out.stats + (long long)cand * out.stat_stride + out.stat_off;
       st[0] += (double)mean_loss * (double)nrows;
-      st[1] += (double)ok;
+      st[1] += ML ? f1 : (double)ok;
     }
   }
   if (!TRAIN) return;
@@ -405,12 +454,12 @@ __device__ __forceinline__ void head_body(const DCand& cd, int cand, const DCach
   }
 }
 
-template <bool TRAIN>
+template <bool TRAIN, bool ML = false>
 __global__ void __launch_bounds__(kHeadThreads)
 k_head(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, int hs_ld, int lg_ld, AdamH adam,
        float step_size, float bc2_sqrt, HeadOut out) {
   extern __shared__ __align__(16) float smem[];
-  head_body<TRAIN>(cands[blockIdx.x], blockIdx.x, cache, batch, bmax, hs_ld, lg_ld, adam, step_size, bc2_sqrt, out, smem);
+  head_body<TRAIN, ML>(cands[blockIdx.x], blockIdx.x, cache, batch, bmax, hs_ld, lg_ld, adam, step_size, bc2_sqrt, out, smem);
 }
 
 // ---------------------------------------------------------------------------------------------

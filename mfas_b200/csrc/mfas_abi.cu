@@ -205,6 +205,7 @@ struct mfas_group {
   int64_t launches = 0;
   // engine "tc" (tcgen05 tensor cores); engine 0 = "ffma"
   int engine = 0;
+  bool multilabel = false;        // every candidate carries MFAS_FLAG_MULTILABEL (the MM-IMDB head)
   int npad = 64;                  // batch rows padded to the MMA tile (64 or 128)
   int items_fwd = 0, items_bwd = 0;   // work items per candidate (max over the group)
   float* part = nullptr;          // forward partial sums [n_cand][items_fwd][Hp][npad]
@@ -369,6 +370,8 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
   }
   e = cudaFuncSetAttribute(k_head<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_head);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_head<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_head);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_head<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_head);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_head<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_head);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fusion_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bwd);
   if (e != cudaSuccess) {
     int code = fail(MFAS_ERR_CUDA, "cudaFuncSetAttribute: %s (is this an sm_100 device?)", cudaGetErrorString(e));
@@ -385,13 +388,21 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
                           l_small_ok(g->lay[c]);
     tc_ok = tc_ok && (g->lay[c].H % 64 == 0 || ((g->lay[c].H == 16 || g->lay[c].H == 32) && small_ok));
     tc_ok = tc_ok && !(g->lay[c].flags & MFAS_FLAG_ALPHAS);      // the modality gates are built in the CUDA-core engine only
+    tc_ok = tc_ok && !(g->lay[c].flags & MFAS_FLAG_MULTILABEL);  // so is the multi-label (MM-IMDB) head
+    g->multilabel = g->multilabel || (g->lay[c].flags & MFAS_FLAG_MULTILABEL);
+    if (((g->lay[c].flags ^ g->lay[0].flags) & MFAS_FLAG_MULTILABEL) ||
+        ((g->lay[c].flags & MFAS_FLAG_MULTILABEL) && (g->lay[c].flags & MFAS_FLAG_MULTITASK))) {
+      int code = fail(MFAS_ERR_INVALID, "MFAS_FLAG_MULTILABEL must be set for all candidates of a group or none, and excludes MFAS_FLAG_MULTITASK");
+      mfas_group_destroy(g);
+      return code;
+    }
     g->any_alphas = g->any_alphas || (g->lay[c].flags & MFAS_FLAG_ALPHAS);
     for (int l = 0; l < g->lay[c].L; ++l) tc_ok = tc_ok && g->lay[c].d_ske[l] % 128 == 0 && g->lay[c].d_rgb[l] % 128 == 0;
   }
   const char* env = getenv("MFAS_ENGINE");
   if (env && !strcmp(env, "ffma")) tc_ok = false;
   if (env && !strcmp(env, "tc") && !tc_ok) {
-    int code = fail(MFAS_ERR_UNSUPPORTED, "MFAS_ENGINE=tc needs inner_representation_size 16, 32 or a multiple of 64, tap widths %% 128 == 0 and alphas off");
+    int code = fail(MFAS_ERR_UNSUPPORTED, "MFAS_ENGINE=tc needs inner_representation_size 16, 32 or a multiple of 64, tap widths %% 128 == 0, alphas off and a single-label head");
     mfas_group_destroy(g);
     return code;
   }
@@ -654,7 +665,10 @@ static int sync_descriptors(mfas_group* g, cudaStream_t st) {
 
 static int to_dcache(const mfas_group* g, const mfas_cache_desc* c, DCache* out) {
   if (!c) return fail(MFAS_ERR_INVALID, "null cache");
-  if (c->n_rows <= 0 || !c->labels) return fail(MFAS_ERR_INVALID, "cache needs n_rows>0 and labels");
+  if (c->n_rows <= 0) return fail(MFAS_ERR_INVALID, "cache needs n_rows>0");
+  if (!g->multilabel && !c->labels) return fail(MFAS_ERR_INVALID, "cache needs labels");
+  if (g->multilabel && (!c->targets || !c->pos_weight))
+    return fail(MFAS_ERR_INVALID, "multi-label candidates need cache.targets [n_rows, C] and cache.pos_weight [C]");
   out->n_rows = c->n_rows;
   for (int t = 0; t < MFAS_NUM_TAPS; ++t) {
     if (!c->ske[t] || !c->rgb[t]) return fail(MFAS_ERR_INVALID, "cache tap %d is null", t);
@@ -669,6 +683,7 @@ static int to_dcache(const mfas_group* g, const mfas_cache_desc* c, DCache* out)
         return fail(MFAS_ERR_INVALID, "cache tap widths differ from the layout of candidate %d step %d", k, l);
   out->labels = (const long long*)c->labels;
   out->logit_rgb = c->logit_rgb; out->logit_ske = c->logit_ske;
+  out->targets = c->targets; out->pos_weight = c->pos_weight;
   for (int k = 0; k < g->n_cand; ++k)
     if ((g->lay[k].flags & MFAS_FLAG_MULTITASK) && (!c->logit_rgb || !c->logit_ske))
       return fail(MFAS_ERR_INVALID, "multitask candidates need the cached backbone logits (cache.logit_rgb / logit_ske)");
@@ -736,7 +751,12 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
 #undef CF
     LAUNCH_CHECK(g);
   }
-  if (train)
+  if (g->multilabel) {
+    if (train)
+      k_head<true, true><<<g->n_cand, kHeadThreads, g->smem_head, st>>>(g->dc, cache, batch, g->bmax, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, ho);
+    else
+      k_head<false, true><<<g->n_cand, kHeadThreads, g->smem_head, st>>>(g->dc, cache, batch, g->bmax, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, ho);
+  } else if (train)
     k_head<true><<<g->n_cand, kHeadThreads, g->smem_head, st>>>(g->dc, cache, batch, g->bmax, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, ho);
   else
     k_head<false><<<g->n_cand, kHeadThreads, g->smem_head, st>>>(g->dc, cache, batch, g->bmax, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, ho);
@@ -788,7 +808,12 @@ static int launch_step(mfas_group* g, const DCache& cache, const BatchRef& batch
       k_fusion_fwd<false><<<fgrid, kThreads, 0, st>>>(g->dc, cache, batch, l, g->bmax, g->drop_seed, g->drop_p, step);
     LAUNCH_CHECK(g);
   }
-  if (train)
+  if (g->multilabel) {
+    if (train)
+      k_head<true, true><<<g->n_cand, kHeadThreads, g->smem_head, st>>>(g->dc, cache, batch, g->bmax, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, ho);
+    else
+      k_head<false, true><<<g->n_cand, kHeadThreads, g->smem_head, st>>>(g->dc, cache, batch, g->bmax, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, ho);
+  } else if (train)
     k_head<true><<<g->n_cand, kHeadThreads, g->smem_head, st>>>(g->dc, cache, batch, g->bmax, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, ho);
   else
     k_head<false><<<g->n_cand, kHeadThreads, g->smem_head, st>>>(g->dc, cache, batch, g->bmax, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, ho);

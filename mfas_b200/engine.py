@@ -28,11 +28,24 @@ def flags_from_args(args) -> int:
     return f
 
 
-def plan_layout(conf, H, C_out, flags, vid_len_ske=32) -> _lib.Layout:
+def _four(widths):
+    """The ABI carries MFAS_NUM_TAPS = 4 taps per modality; a shorter tap set (the 2 MM-IMDB text taps) is repeated to fill
+    the unused slots -- ``plan_layout`` rejects a conf row that points at one of them."""
+    w = [int(x) for x in widths]
+    if not 1 <= len(w) <= _lib.NUM_TAPS:
+        raise ValueError(f"a modality has 1..{_lib.NUM_TAPS} taps, got {len(w)}")
+    return [w[t % len(w)] for t in range(_lib.NUM_TAPS)]
+
+
+def plan_layout(conf, H, C_out, flags, vid_len_ske=32, widths=None) -> _lib.Layout:
+    """``widths`` = (first-modality tap widths, second-modality tap widths); default: the NTU taps."""
     conf = np.ascontiguousarray(np.asarray(conf, dtype=np.int32).reshape(-1, 3))
     lay = _lib.Layout()
-    ds = (C.c_int32 * 4)(*ske_widths(vid_len_ske))
-    dr = (C.c_int32 * 4)(*D_RGB)
+    d0, d1 = (ske_widths(vid_len_ske), D_RGB) if widths is None else widths
+    if conf.shape[0] and (conf[:, 0].max() >= len(d0) or conf[:, 1].max() >= len(d1) or conf[:, :2].min() < 0):
+        raise ValueError(f"conf tap index out of range for a ({len(d0)}, {len(d1)})-tap set: {conf.tolist()}")
+    ds = (C.c_int32 * 4)(*_four(d0))
+    dr = (C.c_int32 * 4)(*_four(d1))
     _lib.check(_lib.lib().mfas_plan_layout(conf.shape[0], conf.ctypes.data_as(C.POINTER(C.c_int32)), int(H),
                                            int(C_out), int(flags), ds, dr, C.byref(lay)))
     return lay
@@ -68,19 +81,20 @@ def cache_desc(cache: FeatureCache) -> _lib.CacheDesc:
         raise RuntimeError("feature cache must be resident on a CUDA device (FeatureCache.to('cuda'))")
     d = _lib.CacheDesc()
     d.n_rows = len(cache)
-    o = 0
-    for t, w in enumerate(cache.d_ske):
-        d.ske[t] = cache.ske_cat.data_ptr() + 4 * o
-        d.ske_ld[t] = cache.ske_cat.stride(0)
-        d.d_ske[t] = w
-        o += w
-    o = 0
-    for t, w in enumerate(cache.d_rgb):
-        d.rgb[t] = cache.rgb_cat.data_ptr() + 4 * o
-        d.rgb_ld[t] = cache.rgb_cat.stride(0)
-        d.d_rgb[t] = w
-        o += w
-    d.labels = cache.labels.data_ptr()
+    for widths, cat, ptr, ld, dw in ((cache.d_ske, cache.ske_cat, d.ske, d.ske_ld, d.d_ske),
+                                     (cache.d_rgb, cache.rgb_cat, d.rgb, d.rgb_ld, d.d_rgb)):
+        offs = np.concatenate([[0], np.cumsum(widths)])
+        for t in range(_lib.NUM_TAPS):             # a shorter tap set repeats (see _four)
+            u = t % len(widths)
+            ptr[t] = cat.data_ptr() + 4 * int(offs[u])
+            ld[t] = cat.stride(0)
+            dw[t] = widths[u]
+    if getattr(cache, "multilabel", False):
+        d.labels = None
+        d.targets = cache.labels.data_ptr()
+        d.pos_weight = cache.pos_weight.data_ptr()
+    else:
+        d.labels = cache.labels.data_ptr()
     d.logit_rgb = cache.logit_rgb.data_ptr() if cache.logit_rgb is not None else None
     d.logit_ske = cache.logit_ske.data_ptr() if cache.logit_ske is not None else None
     return d
@@ -98,10 +112,10 @@ def adam_schedule(lrs, t0, beta1=0.9, beta2=0.999):
 class GroupLayout:
     """Where every tensor of every candidate of a group lives in the flat arenas (host-only, no GPU)."""
 
-    def __init__(self, confs, H, C_out, flags, vid_len_ske=32):
+    def __init__(self, confs, H, C_out, flags, vid_len_ske=32, widths=None):
         self.n = len(confs)
         self.H, self.C, self.flags = int(H), int(C_out), int(flags)
-        self.layouts = [plan_layout(c, H, C_out, flags, vid_len_ske) for c in confs]
+        self.layouts = [plan_layout(c, H, C_out, flags, vid_len_ske, widths) for c in confs]
         self.slots = [tensor_slots(l) for l in self.layouts]
         np_ = [int(l.n_params) for l in self.layouts]
         nb_ = [int(l.n_bufs) for l in self.layouts]
@@ -113,11 +127,11 @@ class CandidateGroup(GroupLayout):
     """n candidates with their parameter / Adam / BN arenas resident on one CUDA device."""
 
     def __init__(self, confs, H, C_out, flags, device, batch_max, drop_p=0.0, drop_seed=0, cand_ids=None,
-                 vid_len_ske=32, keep_grads=False):
+                 vid_len_ske=32, keep_grads=False, widths=None):
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("mfas_b200 runs on CUDA devices only (no CPU fallback)")
-        super().__init__(confs, H, C_out, flags, vid_len_ske)
+        super().__init__(confs, H, C_out, flags, vid_len_ske, widths)
         self.device = device
         self.batch_max = int(batch_max)
         z = lambda n, dt=torch.float32: torch.zeros(int(n), dtype=dt, device=device)

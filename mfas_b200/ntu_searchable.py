@@ -100,16 +100,25 @@ class Searchable_Skeleton_Image_Net(nn.Module):
     arenas the kernels update in place.
     """
 
+    # hooks of the sibling networks over other tap sets (mfas_b200.mmimdb_searchable): None / 0 = the NTU taps, softmax-CE head
+    _widths_kw = None
+    _extra_flags = 0
+
+    @staticmethod
+    def _tap_widths(args):
+        """(first-modality tap widths, second-modality tap widths), ntu_searchable.py:291-292"""
+        return ske_widths(args.vid_len[1]), D_RGB
+
     def __init__(self, args, conf):
         super().__init__()
         self.conf = conf
         self.args = args
-        ds = ske_widths(args.vid_len[1])
-        self.rgbnet = CachedTaps(D_RGB, "rgb")
+        ds, dr = self._tap_widths(args)
+        self.rgbnet = CachedTaps(dr, "rgb")
         self.skenet = CachedTaps(ds, "ske")
         cf = np.asarray(conf).reshape(-1, 3)
         # construction order == reference order, so a given torch seed gives the same init
-        self.alphas = nn.ModuleList([AlphaScalarMultiplication(ds[int(c[0])], D_RGB[int(c[1])]) for c in cf])
+        self.alphas = nn.ModuleList([AlphaScalarMultiplication(ds[int(c[0])], dr[int(c[1])]) for c in cf])
         self.gp_v = nn.ModuleList([GlobalPooling2D() for _ in cf])
         self.gp_s = nn.ModuleList([GlobalPooling2D() for _ in cf])
         self.fusion_layers = self._create_fc_layers(cf)
@@ -177,9 +186,10 @@ class Searchable_Skeleton_Image_Net(nn.Module):
             return g
         a = self.args
         cf = np.asarray(self.conf).reshape(-1, 3)
-        g = CandidateGroup([cf], a.inner_representation_size, a.num_outputs, flags_from_args(a), device,
+        g = CandidateGroup([cf], a.inner_representation_size, a.num_outputs, flags_from_args(a) | self._extra_flags, device,
                            batch_max=_lib.MAX_BATCH, drop_p=float(a.drpt) if a.drpt > 1e-10 else 0.0,
-                           drop_seed=int(getattr(a, "dropout_seed", 0)), vid_len_ske=a.vid_len[1])
+                           drop_seed=int(getattr(a, "dropout_seed", 0)), vid_len_ske=getattr(a, "vid_len", (8, 32))[1],
+                           widths=self._widths_kw)
         self.attach(g, 0, copy_in=True)
         return g
 

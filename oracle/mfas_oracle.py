@@ -167,8 +167,8 @@ class FusionHead:
         self.bn = bool(batchnorm)
         self.drpt = float(drpt)
         self.use_alphas = bool(alphas)
-        self.ds = d_ske(vid_len_ske)
-        self.K = layer_in_features(self.conf, H, vid_len_ske)
+        self.ds, self.dr = d_ske(vid_len_ske), D_RGB          # tap widths of the two modalities (subclasses: other tap sets)
+        self.K = [self.ds[int(c[0])] + self.dr[int(c[1])] + (self.H if l > 0 else 0) for l, c in enumerate(self.conf)]
         self.dropout_seed, self.cand_index = dropout_seed, cand_index
         if self.drpt < 1e-10 and not self.bn:
             # ntu_searchable.py:274-284 has no branch for this combination
@@ -259,13 +259,17 @@ class FusionHead:
         return loss, logp
 
     # -- hand-derived backward -------------------------------
-    def backward(self, logits, labels, tape):
-        s = self.state
+    def loss_and_dlogits(self, logits, labels):
+        """mean cross-entropy and dlogits = (softmax - onehot) / B (a subclass swaps the head: oracle/mmimdb_oracle.py)"""
         B = logits.shape[0]
-        _, logp = self.ce_loss(logits, labels)
+        loss, logp = self.ce_loss(logits, labels)
         dlog = np.exp(logp, dtype=F32)
         dlog[np.arange(B), labels] -= F32(1)
-        dlog = (dlog / F32(B)).astype(F32)
+        return loss, (dlog / F32(B)).astype(F32)
+
+    def backward(self, logits, labels, tape):
+        s = self.state
+        _, dlog = self.loss_and_dlogits(logits, labels)
         g = {}
         h_last = tape["h_last"]
         g["central_classifier.weight"] = (dlog.T @ h_last).astype(F32)
@@ -290,7 +294,7 @@ class FusionHead:
             W = s[f"fusion_layers.{l}.0.weight"]
             g[f"fusion_layers.{l}.0.weight"] = (dz.T @ rec["x"]).astype(F32)
             g[f"fusion_layers.{l}.0.bias"] = dz.sum(axis=0, dtype=F32)
-            Ds, Dr = self.ds[i], D_RGB[j]
+            Ds, Dr = self.ds[i], self.dr[j]
             if self.use_alphas:
                 sg = rec["gate"]
                 dxs = dz @ W[:, :Ds]
@@ -336,7 +340,7 @@ class FusionHead:
     def train_step(self, ske_taps, rgb_taps, labels, lr):
         logits, tape = self.forward(ske_taps, rgb_taps, train=True)
         self.last_tape = tape
-        loss, _ = self.ce_loss(logits, labels)
+        loss, _ = self.loss_and_dlogits(logits, labels)
         grads = self.backward(logits, labels, tape)
         self.adam_step(grads, lr)
         return logits, loss, grads

@@ -59,7 +59,26 @@ D_SKE = (128, 256, 1024, 512)
 D_RGB = (512, 1024, 2048, 2048)
 
 
-def init_states(confs, H, C, bn, drpt, seed):
+# MM-IMDB searchable fusion: the reference loop around a reference-style module, tests/golden/gen_golden_mmimdb_path.py
+MMIMDB_CASE = dict(confs=[[[1, 2, 0], [0, 3, 1], [1, 0, 0]], [[0, 1, 1]]], H=64, B=32, n_train=320, n_dev=72, epochs=4, Ti=1, eta_max=1e-2,
+                   model_seed=7, data_seed=61, loader_seed=400)
+D_TEXT = (64, 128)
+D_IMAGE = (512, 512, 512, 512)
+
+
+def make_mmimdb_args(H, B, epochs, bn=True, drpt=0.0, Ti=1, Tm=2, eta_max=1e-3, eta_min=1e-6, C=23, alphas=False, verbose=False):
+    return argparse.Namespace(inner_representation_size=H, num_outputs=C, drpt=drpt, batchnorm=bn, alphas=alphas,
+                              multitask=False, weightsharing=False, batchsize=B, eta_max=eta_max, eta_min=eta_min, Ti=Ti, Tm=Tm,
+                              use_dataparallel=False, verbose=verbose, epochs=epochs)
+
+
+def split_np_mmimdb(cache):
+    """text/image FeatureCache -> dict of numpy tap arrays for oracle/mmimdb_oracle.py."""
+    return dict(text=[t.numpy() for t in cache.ske_taps()], image=[t.numpy() for t in cache.rgb_taps()],
+                targets=cache.labels.numpy(), pos_weight=cache.pos_weight.numpy())
+
+
+def init_states(confs, H, C, bn, drpt, seed, widths=None):
     """Initial state_dicts of the fusion heads for ``confs`` built back to back from one seed.
 
     Replays the reference constructor's RNG consumption with parameter-free backbones
@@ -68,11 +87,12 @@ def init_states(confs, H, C, bn, drpt, seed):
     ``tests/golden/gen_golden.py`` asserts this equals the reference model's own init.
     """
     torch.manual_seed(seed)
+    d0, d1 = (D_SKE, D_RGB) if widths is None else widths
     out = []
     for conf in confs:
         sd = {}
         for l, c in enumerate(conf):
-            K = D_SKE[c[0]] + D_RGB[c[1]] + (H if l > 0 else 0)
+            K = d0[c[0]] + d1[c[1]] + (H if l > 0 else 0)
             lin = nn.Linear(K, H)
             sd[f"fusion_layers.{l}.0.weight"] = lin.weight.detach().numpy().copy()
             sd[f"fusion_layers.{l}.0.bias"] = lin.bias.detach().numpy().copy()
