@@ -42,8 +42,9 @@ def plan_layout(conf, H, C_out, flags, vid_len_ske=32, widths=None) -> _lib.Layo
     conf = np.ascontiguousarray(np.asarray(conf, dtype=np.int32).reshape(-1, 3))
     lay = _lib.Layout()
     d0, d1 = (ske_widths(vid_len_ske), D_RGB) if widths is None else widths
-    if conf.shape[0] and (conf[:, 0].max() >= len(d0) or conf[:, 1].max() >= len(d1) or conf[:, :2].min() < 0):
-        raise ValueError(f"conf tap index out of range for a ({len(d0)}, {len(d1)})-tap set: {conf.tolist()}")
+    for col, d in ((0, d0), (1, d1)):           # slots a shorter tap set leaves unused (the library checks the range [0, 4))
+        if conf.shape[0] and len(d) <= conf[:, col].max() < _lib.NUM_TAPS:
+            raise ValueError(f"conf tap index out of range for a ({len(d0)}, {len(d1)})-tap set: {conf.tolist()}")
     ds = (C.c_int32 * 4)(*_four(d0))
     dr = (C.c_int32 * 4)(*_four(d1))
     _lib.check(_lib.lib().mfas_plan_layout(conf.shape[0], conf.ctypes.data_as(C.POINTER(C.c_int32)), int(H),
