@@ -54,17 +54,21 @@ def broadcast_cache(cache, device, src: int = 0, vid_len_ske: int = 32) -> Featu
         return cache.to(device)
     cdev = device if td.get_backend() == "nccl" else torch.device("cpu")
     meta = [None]
-    if r == src:
-        meta = [(len(cache), cache.ske_cat.shape[1], cache.rgb_cat.shape[1], cache.vid_len_ske)]
+    if r == src:       # labels: int64 [N] class ids, or fp32 [N, C] multi-hot targets + pos_weight [C] (MM-IMDB)
+        meta = [(len(cache), cache.ske_cat.shape[1], cache.rgb_cat.shape[1], cache.vid_len_ske, tuple(cache.labels.shape),
+                 cache.widths)]
     td.broadcast_object_list(meta, src=src)
-    n, ws, wr, vl = meta[0]
+    n, ws, wr, vl, lshape, widths = meta[0]
+    multilabel = len(lshape) == 2
     if r == src:
         c = cache.to(cdev)
-        ske, rgb, lab = c.ske_cat, c.rgb_cat, c.labels
+        ske, rgb, lab, pw = c.ske_cat, c.rgb_cat, c.labels, c.pos_weight
     else:
         ske = torch.empty(n, ws, dtype=torch.float32, device=cdev)
         rgb = torch.empty(n, wr, dtype=torch.float32, device=cdev)
-        lab = torch.empty(n, dtype=torch.int64, device=cdev)
-    for t in (ske, rgb, lab):
+        lab = torch.empty(lshape, dtype=torch.float32 if multilabel else torch.int64, device=cdev)
+        pw = torch.empty(lshape[1], dtype=torch.float32, device=cdev) if multilabel else None
+    for t in (ske, rgb, lab) + ((pw,) if multilabel else ()):
         td.broadcast(t, src=src)
-    return FeatureCache(ske.to(device), rgb.to(device), lab.to(device), vl)
+    return FeatureCache(ske.to(device), rgb.to(device), lab.to(device), vl, widths=widths,
+                        pos_weight=pw.to(device) if multilabel else None)

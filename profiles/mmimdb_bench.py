@@ -1,0 +1,64 @@
+#!/usr/bin/env python3
+"""BASELINE.json configs[3] as a reported extra (not the driver's bench line): MM-IMDB text+image searchable fusion,
+64 candidates x 3 epochs, inner_repr=256, bs=64, synthetic taps at the dataset's size (15552 train / 2608 dev rows), one
+GPU.  Times `mfas_b200.mmimdb_searchable.train_sampled_models` end to end (host buffers in, F1 list out) after one warm-up
+call and prints one JSON line with candidate-epochs/s and the HBM-roofline fraction of the train steps
+(algorithmic bytes, SURVEY.md 8(d), / wall time).  Usage: python profiles/mmimdb_bench.py [n_candidates] [epochs]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import mfas_b200.mmimdb_searchable as mm  # noqa: E402
+from helpers import make_mmimdb_args  # noqa: E402
+from mfas_b200 import _lib  # noqa: E402
+from mfas_b200.engine import algorithmic_counts, plan_layout  # noqa: E402
+
+
+def main():
+    n_cand = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    dev = torch.device("cuda:0")
+    train, devs = mm.synthetic_mmimdb_cache(15552, 1).pin(), mm.synthetic_mmimdb_cache(2608, 2).pin()
+    rows = mm.get_possible_layer_configurations(0)
+    rng = np.random.default_rng(0)
+    confs = [np.array([rows[i] for i in rng.integers(0, len(rows), size=2)]) for _ in range(n_cand)]      # L=2 candidates
+    args = make_mmimdb_args(256, 64, epochs, Ti=1)
+    mk = lambda: {"train": mm.TextImageCacheLoader(train, 64, True, 100), "dev": mm.TextImageCacheLoader(devs, 64, True, 200)}
+    warm = make_mmimdb_args(256, 64, 1, Ti=1)
+    torch.manual_seed(0)
+    mm.train_sampled_models(confs[:4], mm.Searchable_Text_Image_Net, mk(), warm, dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    f1s = mm.train_sampled_models(confs, mm.Searchable_Text_Image_Net, mk(), args, dev)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    flags = _lib.FLAG_BN | _lib.FLAG_MULTILABEL
+    steps_tr, steps_dv = -(-15552 // 64), -(-2608 // 64)
+    bytes_ce = 0.0
+    for c in confs:
+        cnt = algorithmic_counts(plan_layout(c, 256, 23, flags, widths=mm.WIDTHS), 64)
+        bytes_ce += steps_tr * cnt["train_bytes"] + steps_dv * cnt["eval_bytes"]
+    peak = 6546.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    gbs = bytes_ce * epochs / dt / 1e9
+    print(json.dumps({"metric": "candidate-epochs/sec (MM-IMDB fusion, bs=64)", "value": n_cand * epochs / dt, "unit": "candidate-epochs/s",
+                      "n_gpus": 1, "e2e_seconds": dt, "engine": "ffma (CUDA cores)", "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"BASELINE configs[3]: MM-IMDB text+image searchable fusion, {n_cand} candidates x "
+                                             f"{epochs} epochs, inner_repr=256, L=2, bs=64, 15552/2608 rows"},
+                      "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None},
+                      "dev_f1_samples": {"min": float(min(f1s)), "max": float(max(f1s))}}))
+
+
+if __name__ == "__main__":
+    main()

@@ -168,7 +168,11 @@ def _dist_worker(rank, world, port, q):
         full = mdist.gather_results(vals, n)
         cache = synthetic_ntu_cache(16, 9) if rank == 0 else None
         got = mdist.broadcast_cache(cache, "cpu")
-        q.put((rank, mine, full.tolist(), float(got.rgb_cat.sum()), int(got.labels.sum())))
+        from mfas_b200.mmimdb_searchable import WIDTHS, synthetic_mmimdb_cache     # multi-hot targets + pos_weight ride along
+        ml = mdist.broadcast_cache(synthetic_mmimdb_cache(12, 4) if rank == 0 else None, "cpu")
+        assert ml.multilabel and ml.widths == WIDTHS and ml.labels.shape == (12, 23)
+        q.put((rank, mine, full.tolist(), float(got.rgb_cat.sum()), int(got.labels.sum()),
+               float(ml.labels.sum() + ml.pos_weight.sum() + ml.ske_cat.sum())))
     finally:
         td.destroy_process_group()
 
@@ -191,6 +195,9 @@ def test_sharding_and_gather_world2_gloo():
     for r in res:
         assert r[2] == [10.0 + j for j in range(7)]                      # every rank sees all results, in input order
         assert r[3] == pytest.approx(float(ref.rgb_cat.sum())) and r[4] == int(ref.labels.sum())
+    from mfas_b200.mmimdb_searchable import synthetic_mmimdb_cache
+    ml = synthetic_mmimdb_cache(12, 4)
+    assert res[0][5] == res[1][5] == pytest.approx(float(ml.labels.sum() + ml.pos_weight.sum() + ml.ske_cat.sum()))
 
 
 def test_sliced_threaded_initialisation_equals_one_serial_fill(monkeypatch):

