@@ -17,6 +17,7 @@ SOURCES = [os.path.join(HERE, "csrc", "mfas_abi.cu"), os.path.join(HERE, "csrc",
 HEADERS = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "kernels_ffma.cuh", "kernels_tc.cuh", "umma.cuh")] + [
     os.path.join(ROOT, "include", "mfas_b200.h")]
 
+ABI_VERSION = 2          # MFAS_ABI_VERSION of include/mfas_b200.h
 MAX_LAYERS, MAX_BATCH, MAX_HIDDEN, MAX_CLASSES, NUM_TAPS = 8, 128, 256, 64, 4
 FLAG_BN, FLAG_DROPOUT, FLAG_ALPHAS, FLAG_MULTITASK, FLAG_MULTILABEL = 1, 2, 4, 8, 16
 ERRORS = {0: "MFAS_OK", -1: "MFAS_ERR_INVALID", -2: "MFAS_ERR_CUDA", -3: "MFAS_ERR_UNSUPPORTED",
@@ -132,7 +133,7 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
-        if l.mfas_abi_version() != 2:
+        if l.mfas_abi_version() != ABI_VERSION:
             raise RuntimeError("ABI version mismatch; rebuild the library")
         _lib = l
     return _lib

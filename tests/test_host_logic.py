@@ -23,7 +23,8 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.lib().mfas_abi_version() == 2
+    assert _lib.lib().mfas_abi_version() == _lib.ABI_VERSION
+    assert re.search(r"#define MFAS_ABI_VERSION (\d+)", header).group(1) == str(_lib.ABI_VERSION)
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
 
