@@ -1531,6 +1531,10 @@ k_tc_bwd_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int 
 // ---------------------------------------------------------------------------------------------
 // Self-contained tile record (built on the host whenever arenas are (re)bound): the Adam warps need no
 // dependent descriptor loads, one 64-byte record fetched two tiles ahead is all they read.
+// end of the concat source [ske | rgb | hidden] that weight column kc0 of a layer belongs to
+__host__ __device__ __forceinline__ int tc_bwd_seg_end(int d_ske, int d_rgb, int K, int kc0) {
+  return kc0 < d_ske ? d_ske : (kc0 < d_ske + d_rgb ? d_ske + d_rgb : K);
+}
 struct __align__(16) BwdTile {
   float* W;                       // &params[oW + h0 * K + kc0]
   long long moff, voff, goff;     // adam_m - params, adam_v - params, grad - params (floats; goff 0 when no grad arena)
@@ -1592,10 +1596,13 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
       } else {
         const DLayer& ly = cd.layer[t.y];
         const int fs = ly.d_ske, fr = ly.d_rgb;
-        if (kc0 < fs) { d.src = cache.ske[ly.ske_tap] + kc0; d.ld = cache.ske_ld[ly.ske_tap]; }
-        else if (kc0 < fs + fr) { d.src = cache.rgb[ly.rgb_tap] + (kc0 - fs); d.ld = cache.rgb_ld[ly.rgb_tap]; }
+        // a tile never straddles two concat sources: the host cuts the tile list at the source boundaries (tc_bwd_seg_end),
+        // so taps narrower than / not a multiple of the 128-column tile (the 64-wide MM-IMDB text tap) are short tiles
+        int seg_end = ly.K;
+        if (kc0 < fs) { d.src = cache.ske[ly.ske_tap] + kc0; d.ld = cache.ske_ld[ly.ske_tap]; seg_end = fs; }
+        else if (kc0 < fs + fr) { d.src = cache.rgb[ly.rgb_tap] + (kc0 - fs); d.ld = cache.rgb_ld[ly.rgb_tap]; seg_end = fs + fr; }
         else { d.src = cd.hid + (long long)(t.y - 1) * bmax * H + (kc0 - fs - fr); d.ld = H; gather = false; }
-        d.H = H; d.kw = min(TC_BWD_KT, ly.K - kc0) | (min(TC_BWD_HT, H - t.w) << 16);
+        d.H = H; d.kw = min(TC_BWD_KT, seg_end - kc0) | (min(TC_BWD_HT, H - t.w) << 16);
         d.dz = cd.dzs + (long long)t.y * bmax * H + t.w;
       }
 #pragma unroll

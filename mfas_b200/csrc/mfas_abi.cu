@@ -380,7 +380,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
   }
   // ---- engine selection: tensor cores whenever the shapes fit the MMA tiles -----------------------
   auto l_small_ok = [](const mfas_layout& l) { return l.C <= TC_DLOG_LD; };     // small inner_repr needs the tensor-core head
-  bool tc_ok = true;
+  bool tc_ok = true, ragged = false;
   for (int c = 0; c < n_cand; ++c) {
     // inner_repr 16 / 32 (the search default) ride the same tiles with most rows masked; that needs the row / column
     // masks of the persistent kernels and the fused chain, i.e. batch <= 64 and none of the stage-by-stage overrides
@@ -388,7 +388,6 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
                           l_small_ok(g->lay[c]);
     tc_ok = tc_ok && (g->lay[c].H % 64 == 0 || ((g->lay[c].H == 16 || g->lay[c].H == 32) && small_ok));
     tc_ok = tc_ok && !(g->lay[c].flags & MFAS_FLAG_ALPHAS);      // the modality gates are built in the CUDA-core engine only
-    tc_ok = tc_ok && !(g->lay[c].flags & MFAS_FLAG_MULTILABEL);  // so is the multi-label (MM-IMDB) head
     g->multilabel = g->multilabel || (g->lay[c].flags & MFAS_FLAG_MULTILABEL);
     if (((g->lay[c].flags ^ g->lay[0].flags) & MFAS_FLAG_MULTILABEL) ||
         ((g->lay[c].flags & MFAS_FLAG_MULTILABEL) && (g->lay[c].flags & MFAS_FLAG_MULTITASK))) {
@@ -397,12 +396,18 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       return code;
     }
     g->any_alphas = g->any_alphas || (g->lay[c].flags & MFAS_FLAG_ALPHAS);
-    for (int l = 0; l < g->lay[c].L; ++l) tc_ok = tc_ok && g->lay[c].d_ske[l] % 128 == 0 && g->lay[c].d_rgb[l] % 128 == 0;
+    // the multi-label (MM-IMDB) head lives in k_head: per-layer chain kernels (no fused chain, no tensor-core head), which
+    // have no row / column masks for inner_repr 16 / 32
+    tc_ok = tc_ok && (!(g->lay[c].flags & MFAS_FLAG_MULTILABEL) || g->lay[c].H % 64 == 0);
+    for (int l = 0; l < g->lay[c].L; ++l) ragged = ragged || g->lay[c].d_ske[l] % 128 || g->lay[c].d_rgb[l] % 128;
   }
+  // Tap widths that are not multiples of the 128-column backward tile (the 64-wide MM-IMDB text tap): only the persistent
+  // backward walks a host-built tile list, which is cut at the concat-source boundaries; the grid-indexed backward is not.
+  if (ragged && (batch_max > 64 || getenv("MFAS_BWD") || getenv("MFAS_FWD"))) tc_ok = false;
   const char* env = getenv("MFAS_ENGINE");
   if (env && !strcmp(env, "ffma")) tc_ok = false;
   if (env && !strcmp(env, "tc") && !tc_ok) {
-    int code = fail(MFAS_ERR_UNSUPPORTED, "MFAS_ENGINE=tc needs inner_representation_size 16, 32 or a multiple of 64, tap widths %% 128 == 0, alphas off and a single-label head");
+    int code = fail(MFAS_ERR_UNSUPPORTED, "MFAS_ENGINE=tc needs inner_representation_size 16, 32 or a multiple of 64 (a multiple of 64 with the multi-label head), alphas off, and tap widths %% 128 == 0 unless batch_max <= 64");
     mfas_group_destroy(g);
     return code;
   }
@@ -450,6 +455,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     { int nsm = 0; if (e == cudaSuccess) e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device); if (nsm > 0) g->n_sms = nsm; }
     { const char* ce = getenv("MFAS_CHAIN"); if (ce && !strcmp(ce, "ffma")) g->chain = 0; if (ce && !strcmp(ce, "layers")) g->chain = 1; }
     if (g->Hmax > 128 && g->chain == 2) g->chain = 1;                  // the fused kernel owns one 128-column tile per candidate
+    if (g->multilabel && g->chain == 2) g->chain = 1;                  // the multi-label head is k_head<., true> (see above)
     g->smem_chain_all = g->smem_chain > 1024 + g->smem_head ? g->smem_chain : 1024 + g->smem_head;
     if (g->smem_chain_all > 227 * 1024 && g->chain == 2) g->chain = 1;
     if (g->chain == 2) {
@@ -469,9 +475,10 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     if (g->bwd_ws) {
       std::vector<int4> tl;
       for (int c = 0; c < n_cand; ++c)
-        for (int l = 0; l < g->lay[c].L; ++l)
-          for (int kc0 = 0; kc0 < g->lay[c].K[l]; kc0 += TC_BWD_KT)
-            for (int h0 = 0; h0 < g->lay[c].H; h0 += TC_BWD_HT) tl.push_back(make_int4(c, l, kc0, h0));
+        for (int l = 0; l < g->lay[c].L; ++l)       // 128-column tiles inside each concat source [ske | rgb | hidden]
+          for (int s0 = 0; s0 < g->lay[c].K[l]; s0 = tc_bwd_seg_end(g->lay[c].d_ske[l], g->lay[c].d_rgb[l], g->lay[c].K[l], s0))
+            for (int kc0 = s0; kc0 < tc_bwd_seg_end(g->lay[c].d_ske[l], g->lay[c].d_rgb[l], g->lay[c].K[l], s0); kc0 += TC_BWD_KT)
+              for (int h0 = 0; h0 < g->lay[c].H; h0 += TC_BWD_HT) tl.push_back(make_int4(c, l, kc0, h0));
       g->n_bwd_layer_tiles = (int)tl.size();
       if (g->tchead)                                    // classifier tiles last: a step that ran k_head instead simply stops short of them
         for (int c = 0; c < n_cand; ++c)
@@ -612,7 +619,8 @@ static int sync_descriptors(mfas_group* g, cudaStream_t st) {
         } else {
           const DLayer& ly = d.layer[t.y];
           r.W = d.p + ly.oW + (long long)t.w * ly.K + t.z;
-          r.K = ly.K; r.kw = ly.K - t.z < TC_BWD_KT ? ly.K - t.z : TC_BWD_KT;
+          const int seg_end = tc_bwd_seg_end(ly.d_ske, ly.d_rgb, ly.K, t.z);
+          r.K = ly.K; r.kw = seg_end - t.z < TC_BWD_KT ? seg_end - t.z : TC_BWD_KT;
           r.rows = d.H - t.w < TC_BWD_HT ? d.H - t.w : TC_BWD_HT;
         }
         r.cand = t.x; r.layer = t.y; r.kc0 = t.z; r.h0 = t.w; r.pad1 = 0;

@@ -15,8 +15,10 @@ Taps: text = the two hidden layers of ``MaxOut_MLP`` (central/mm_imdb.py:176-196
 ``GP_VGG`` blocks (central/mm_imdb.py:41-52: 512 wide each).  Concat order ``[text | image | hidden]``.  The fusion steps
 run in the same CUDA kernels as the NTU head (the tap set is a (pointer, width) table); the head is the multi-label one:
 ``WeightedCrossEntropyWithLogits`` and per-sample F1 of ``sigmoid > 0.3`` (MFAS_FLAG_MULTILABEL, kernels_ffma.cuh
-``head_rows_ml``).  Text taps are 64 / 128 wide -- below the 128-column tensor-core tiles -- so these groups run on the
-CUDA-core engine.  No CPU path: a non-CUDA device raises.
+``head_rows_ml``).  With inner_representation_size a multiple of 64 and batches of at most 64 rows the group runs on the
+tensor-core engine (forward / backward streaming kernels + per-layer chain kernels + the CUDA-core head kernel; the backward
+tile list is cut at the concat-source boundaries, so the 64-wide text tap is a short tile); otherwise on the CUDA-core
+engine.  No CPU path: a non-CUDA device raises.
 """
 from __future__ import annotations
 
@@ -119,8 +121,10 @@ class Searchable_Text_Image_Net(Searchable_Skeleton_Image_Net):
             raise ValueError("expected cached taps: text [B, %d], image [B, %d]" % (nt, ni))
         g = self.native(text.device)
         B, Cn = text.shape[0], self.args.num_outputs
-        if B > g.batch_max:
-            raise ValueError(f"batch of {B} rows exceeds MFAS_MAX_BATCH={g.batch_max}")
+        if B > _lib.MAX_BATCH:
+            raise ValueError(f"batch of {B} rows exceeds MFAS_MAX_BATCH={_lib.MAX_BATCH}")
+        if B > g.batch_max:                                # the group was sized by a training loop with a smaller batch
+            g = self.native(text.device, batch_max=_lib.MAX_BATCH)
         cache = FeatureCache(text.contiguous(), image.contiguous(), torch.zeros(B, Cn, device=text.device), widths=WIDTHS,
                              pos_weight=torch.ones(Cn, device=text.device))
         rows = torch.arange(B, dtype=torch.int32, device=text.device)
@@ -238,6 +242,7 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
         stats, best, _ = g.train_run(train_dev, dev_dev, ptr, pdv, lrs, E, B)
         stats, best = stats.cpu(), best.cpu()
         g.check()
+        train_sampled_models.last_engine = g.engine
         for k, j in enumerate(js):
             f1s[j] = _final_f1(stats[k], best[k], init_f1[todo[j]], n_dev)
             all_stats[j] = stats[k]
@@ -278,13 +283,13 @@ def train_mmimdb_track_f1(model, criterion, optimizer, scheduler, dataloaders, d
     if not hasattr(criterion, "w"):
         raise TypeError("criterion must be a WeightedCrossEntropyWithLogits (carrying the pos_weight vector as .w)")
     net = model.module if isinstance(model, torch.nn.DataParallel) else model
-    g = net.native(device)
+    B = int(getattr(dataloaders['train'], 'batch_size', None) or net.args.batchsize)
+    g = net.native(device, batch_max=B)                    # batch <= 64 puts inner_repr % 64 == 0 on the tensor-core engine
     b1, b2, eps, wd, _ = _adam_hparams(optimizer)
     g.set_adam(b1, b2, eps, wd)
     train_c = _with_pos_weight(_multilabel_cache_of(dataloaders['train'], 'train'), criterion.w, g.device)
     dev_c = _with_pos_weight(_multilabel_cache_of(dataloaders['dev'], 'dev'), criterion.w, g.device)
     n_train, n_dev = len(train_c), len(dev_c)
-    B = int(getattr(dataloaders['train'], 'batch_size', None) or net.args.batchsize)
     steps = math.ceil(n_train / B)
     slot = net._slot
     named = dict(net.named_parameters())

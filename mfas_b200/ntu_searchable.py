@@ -172,8 +172,10 @@ class Searchable_Skeleton_Image_Net(nn.Module):
         self._group, self._slot = group, slot
         return self
 
-    def native(self, device=None) -> CandidateGroup:
-        """The 1-candidate group backing this module (created on first use / after .to())."""
+    def native(self, device=None, batch_max=None) -> CandidateGroup:
+        """The 1-candidate group backing this module (created on first use / after .to()).  ``batch_max`` (default: keep
+        the current group, or MFAS_MAX_BATCH for a new one) re-creates the group for another maximum batch -- a training
+        loop asks for its own batch size, which decides the kernels that serve the group (mfas_group_create)."""
         w = self.fusion_layers[0][0].weight
         if device is None:
             device = w.device
@@ -182,12 +184,13 @@ class Searchable_Skeleton_Image_Net(nn.Module):
             raise RuntimeError("mfas_b200 computes on CUDA devices only; move the model with .to('cuda') "
                                "(there is no CPU fallback)")
         g = self._group
-        if g is not None and w.device == device and w.data_ptr() == g.view(self._slot, "fusion_layers.0.0.weight").data_ptr():
+        if g is not None and w.device == device and w.data_ptr() == g.view(self._slot, "fusion_layers.0.0.weight").data_ptr() \
+                and (batch_max is None or g.batch_max == int(batch_max)):
             return g
         a = self.args
         cf = np.asarray(self.conf).reshape(-1, 3)
         g = CandidateGroup([cf], a.inner_representation_size, a.num_outputs, flags_from_args(a) | self._extra_flags, device,
-                           batch_max=_lib.MAX_BATCH, drop_p=float(a.drpt) if a.drpt > 1e-10 else 0.0,
+                           batch_max=int(batch_max or _lib.MAX_BATCH), drop_p=float(a.drpt) if a.drpt > 1e-10 else 0.0,
                            drop_seed=int(getattr(a, "dropout_seed", 0)), vid_len_ske=getattr(a, "vid_len", (8, 32))[1],
                            widths=self._widths_kw)
         self.attach(g, 0, copy_in=True)

@@ -53,7 +53,7 @@ def main():
         pass
     gbs = bytes_ce * epochs / dt / 1e9
     print(json.dumps({"metric": "candidate-epochs/sec (MM-IMDB fusion, bs=64)", "value": n_cand * epochs / dt, "unit": "candidate-epochs/s",
-                      "n_gpus": 1, "e2e_seconds": dt, "engine": "ffma (CUDA cores)", "dtype": "f32", "data": "synthetic",
+                      "n_gpus": 1, "e2e_seconds": dt, "engine": getattr(mm.train_sampled_models, "last_engine", "?"), "dtype": "f32", "data": "synthetic",
                       "config": {"workload": f"BASELINE configs[3]: MM-IMDB text+image searchable fusion, {n_cand} candidates x "
                                              f"{epochs} epochs, inner_repr=256, L=2, bs=64, 15552/2608 rows"},
                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None},

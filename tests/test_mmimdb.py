@@ -157,20 +157,24 @@ def _close(a, b, tol, what, scale=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("H,B,nrows,confs", [
-    (64, 32, 32, MMIMDB_CASE["confs"]),
-    (256, 64, 64, [[[1, 3, 1], [0, 0, 0]], [[1, 1, 0]]]),            # BASELINE configs[3]: inner_repr=256
-    (32, 128, 100, [[[0, 2, 2], [1, 1, 1], [0, 0, 0], [1, 3, 0]]]),
+@pytest.mark.parametrize("H,B,nrows,confs,engine", [
+    (64, 32, 32, MMIMDB_CASE["confs"], "tc"),
+    (256, 64, 64, [[[1, 3, 1], [0, 0, 0]], [[1, 1, 0]]], "tc"),      # BASELINE configs[3]: inner_repr=256
+    (128, 64, 50, [[[0, 1, 0], [0, 2, 1], [1, 3, 2]], [[0, 0, 1]]], "tc"),   # the 64-wide text tap at every depth, a short batch
+    (256, 64, 64, [[[1, 3, 1], [0, 0, 0]], [[1, 1, 0]]], "ffma"),
+    (32, 128, 100, [[[0, 2, 2], [1, 1, 1], [0, 0, 0], [1, 3, 0]]], "ffma"),
 ])
-def test_gpu_single_step_vs_oracle(H, B, nrows, confs):
+def test_gpu_single_step_vs_oracle(H, B, nrows, confs, engine, monkeypatch):
     """One optimiser step per candidate: logits, weighted-BCE loss, every gradient, exact-match count; then the eval-mode
     forward with its F1 statistic."""
     import mfas_b200.mmimdb_searchable as mm
     train = mm.synthetic_mmimdb_cache(160, 71)
     trs = split_np_mmimdb(train)
     inits = init_states(confs, H, 23, True, 0.0, 3, widths=WIDTHS)
+    if engine == "ffma":
+        monkeypatch.setenv("MFAS_ENGINE", "ffma")
     g = _group(confs, H, B, keep_grads=True)
-    assert g.engine == "ffma"
+    assert g.engine == engine            # inner_repr % 64 == 0 and batch <= 64: tensor cores, ragged text taps included
     for ci in range(g.n):
         g.load_state(ci, inits[ci])
     rows = torch.randperm(160, generator=torch.Generator().manual_seed(5))[:nrows]
