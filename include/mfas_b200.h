@@ -217,6 +217,15 @@ int mfas_group_chain_timeline(mfas_group_t g, int64_t* out, int32_t n_cand);
 int mfas_host_uniform_fill(uint8_t* torch_rng_state, int64_t state_bytes, int32_t n_ops, float* const* dst,
                            const int64_t* count, const float* from, const float* to, int32_t use_fma);
 
+/* ---- feature-cache builder (the step before the path) ----------------------------------
+ * Global average pooling of one backbone tap into its column slice of a cache matrix:
+ *   d_out[b * out_ld + c] = mean over s of d_in[(b * C + c) * S + s]
+ * GlobalPooling2D.forward (models/auxiliary/aux_models.py:58-64), which the reference applies to every selected tap on
+ * every batch (models/search/ntu_searchable.py:224-225); here it runs once per sample when the cache is built.
+ * d_in: device fp32 [B, C, S] contiguous (S = product of the trailing dims, 1 for a vector tap); asynchronous on stream. */
+int mfas_global_pool(int32_t device, const float* d_in, int64_t B, int64_t C, int64_t S, float* d_out, int64_t out_ld,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "_mfas_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "mfas_abi.cu"), os.path.join(HERE, "csrc", "host_init.cpp")]
-HEADERS = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "kernels_ffma.cuh", "kernels_tc.cuh", "umma.cuh")] + [
+HEADERS = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "kernels_ffma.cuh", "kernels_tc.cuh", "kernels_pool.cuh", "umma.cuh")] + [
     os.path.join(ROOT, "include", "mfas_b200.h")]
 
 ABI_VERSION = 2          # MFAS_ABI_VERSION of include/mfas_b200.h
@@ -94,6 +94,7 @@ SYMBOLS = {
     "mfas_group_set_profiling": (C.c_int, [_P, C.c_int32]),
     "mfas_group_last_step_ms": (C.c_int, [_P, _P]),
     "mfas_group_chain_timeline": (C.c_int, [_P, _P, C.c_int32]),
+    "mfas_global_pool": (C.c_int, [C.c_int32, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, _P]),
     "mfas_host_uniform_fill": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P, C.c_int32]),
 }
 

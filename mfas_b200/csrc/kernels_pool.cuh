@@ -1,0 +1,46 @@
+// Feature-cache builder: global average pooling of one backbone tap into its column slice of the cache
+// (GlobalPooling2D.forward, /root/reference/models/auxiliary/aux_models.py:58-64; applied to every selected tap at
+// /root/reference/models/search/ntu_searchable.py:224-225 -- here once per sample at cache-build time).
+//
+// in  : [B][C][S] fp32 contiguous (S = product of the trailing dims; S = 1 for a tap that is already a vector)
+// out : out[b * out_ld + c] = (sum_s in[b][c][s]) / S      (a column slice of the [N, sum(D)] cache matrix)
+//
+// HBM-bound streaming reduction: one warp per (b, c) row, lanes walk the row in 16-byte words (4 independent loads in
+// flight per lane, evict-first: every byte is read once), warp-shuffle tree, one 4-byte store per row.  Algorithmic bytes
+// per row: 4 (S + 1).  Deterministic (fixed summation order).
+#pragma once
+#include "common.cuh"
+
+namespace mfas {
+
+constexpr int kPoolThreads = 256;
+
+__global__ void __launch_bounds__(kPoolThreads)
+k_global_pool(const float* __restrict__ in, long long rows, long long C, long long S, float* __restrict__ out, long long out_ld,
+              int vec4) {
+  const int lane = threadIdx.x & 31;
+  const long long nw = (long long)gridDim.x * (kPoolThreads / 32);
+  for (long long r = (long long)blockIdx.x * (kPoolThreads / 32) + (threadIdx.x >> 5); r < rows; r += nw) {
+    const float* p = in + r * S;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (vec4) {                                          // S % 4 == 0 and a 16-byte aligned base: every row is aligned
+      const float4* p4 = reinterpret_cast<const float4*>(p);
+      const long long n4 = S >> 2;
+      long long i = lane;
+      for (; i + 96 < n4; i += 128) {
+        const float4 v0 = __ldcs(p4 + i), v1 = __ldcs(p4 + i + 32), v2 = __ldcs(p4 + i + 64), v3 = __ldcs(p4 + i + 96);
+        a0 += (v0.x + v0.y) + (v0.z + v0.w); a1 += (v1.x + v1.y) + (v1.z + v1.w);
+        a2 += (v2.x + v2.y) + (v2.z + v2.w); a3 += (v3.x + v3.y) + (v3.z + v3.w);
+      }
+      for (; i < n4; i += 32) { const float4 v = __ldcs(p4 + i); a0 += (v.x + v.y) + (v.z + v.w); }
+    } else {
+      long long i = lane;
+      for (; i + 96 < S; i += 128) { a0 += __ldcs(p + i); a1 += __ldcs(p + i + 32); a2 += __ldcs(p + i + 64); a3 += __ldcs(p + i + 96); }
+      for (; i < S; i += 32) a0 += __ldcs(p + i);
+    }
+    const float s = warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) out[(r / C) * out_ld + (r % C)] = s / (float)S;
+  }
+}
+
+}  // namespace mfas

@@ -13,6 +13,7 @@
 
 #include "kernels_ffma.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_pool.cuh"
 
 using namespace mfas;
 
@@ -963,5 +964,30 @@ extern "C" int mfas_eval_pass(mfas_group_t g, const mfas_cache_desc* cache, cons
     HeadOut ho{nullptr, nullptr, nullptr, d_out, 2, 0};
     if ((rc = launch_step(g, dc, b, false, false, 0.f, 1.f, 0u, ho, st))) return rc;
   }
+  return MFAS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// feature-cache builder (the step before the path)
+// ---------------------------------------------------------------------------------------------
+extern "C" int mfas_global_pool(int32_t device, const float* d_in, int64_t B, int64_t C, int64_t S, float* d_out,
+                                int64_t out_ld, void* stream) {
+  if (!d_in || !d_out) return fail(MFAS_ERR_INVALID, "null argument");
+  if (B < 1 || C < 1 || S < 1 || out_ld < C) return fail(MFAS_ERR_INVALID, "B=%lld C=%lld S=%lld out_ld=%lld", (long long)B, (long long)C, (long long)S, (long long)out_ld);
+  if (((uintptr_t)d_in | (uintptr_t)d_out) & 3) return fail(MFAS_ERR_INVALID, "pointers must be 4-byte aligned");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(MFAS_ERR_INVALID, "device %d of %d", device, ndev);
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(MFAS_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+  const long long rows = (long long)B * C, per = kPoolThreads / 32;
+  const long long want = (rows + per - 1) / per, cap = (long long)nsm * 8;      // 8 CTAs of 256 threads per SM: full occupancy
+  const int grid = (int)(want < cap ? want : cap);
+  const int vec4 = (S % 4 == 0) && (((uintptr_t)d_in & 15) == 0);
+  k_global_pool<<<grid, kPoolThreads, 0, (cudaStream_t)stream>>>(d_in, rows, C, S, d_out, out_ld, vec4);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MFAS_ERR_CUDA, "k_global_pool launch failed: %s", cudaGetErrorString(e));
   return MFAS_OK;
 }

@@ -210,8 +210,10 @@ class Searchable_Skeleton_Image_Net(nn.Module):
                              "logit_ske=); FeatureCacheLoader appends them)")
         g = self.native(rgb.device)
         B = rgb.shape[0]
-        if B > g.batch_max:
-            raise ValueError(f"batch of {B} rows exceeds MFAS_MAX_BATCH={g.batch_max}")
+        if B > _lib.MAX_BATCH:
+            raise ValueError(f"batch of {B} rows exceeds MFAS_MAX_BATCH={_lib.MAX_BATCH}")
+        if B > g.batch_max:                                # the group was sized by a training loop with a smaller batch
+            g = self.native(rgb.device, batch_max=_lib.MAX_BATCH)
         cache = FeatureCache(ske[:, :ns].contiguous(), rgb[:, :nr].contiguous(),
                              torch.zeros(B, dtype=torch.int64, device=rgb.device), self.args.vid_len[1],
                              vis_logits.contiguous() if multitask else None, ske_logits.contiguous() if multitask else None)

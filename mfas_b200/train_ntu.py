@@ -42,13 +42,15 @@ def train_ntu_track_acc(model, criteria, optimizer, scheduler, dataloaders, data
     reference (per-batch for LRCosineAnnealingScheduler, otherwise stepped once per epoch)."""
     net = model.module if isinstance(model, torch.nn.DataParallel) else model
     _check_multitask(net, multitask, dataloaders, ('train', 'dev'))
-    g = net.native(device)
+    B = int(getattr(dataloaders['train'], 'batch_size', None) or net.args.batchsize)
+    # size the group by the loop's batch: batches of at most 64 rows get the persistent streaming kernels, the fused chain
+    # and the wide eval pass (a group sized for MFAS_MAX_BATCH rows runs the grid-indexed kernels)
+    g = net.native(device, batch_max=B)
     b1, b2, eps, wd, lr0 = _adam_hparams(optimizer)
     g.set_adam(b1, b2, eps, wd)
     train_c = _feature_cache_of(dataloaders['train'], 'train').to(g.device)
     dev_c = _feature_cache_of(dataloaders['dev'], 'dev').to(g.device)
     n_train, n_dev = len(train_c), len(dev_c)
-    B = int(getattr(dataloaders['train'], 'batch_size', None) or net.args.batchsize)
     steps = math.ceil(n_train / B)
 
     # optimiser state in -> arenas (a fresh Adam has none)
@@ -110,5 +112,7 @@ def test_ntu_track_acc(model, dataloaders, dataset_sizes, device=None, multitask
     g = net.native(device)
     test_c = _feature_cache_of(dataloaders['test'], 'test').to(g.device)
     B = int(getattr(dataloaders['test'], 'batch_size', None) or net.args.batchsize)
+    if B > g.batch_max:                                     # the group was sized by a training loop with a smaller batch
+        g = net.native(device, batch_max=B)
     out = g.eval_pass(test_c, B).cpu()
     return (out[0, 1] / dataset_sizes['test']).clone()
