@@ -15,31 +15,42 @@ namespace mfas {
 
 constexpr int kPoolThreads = 256;
 
+// G lanes share one row (G = 32: a warp per row; G = 8: four rows per warp, for short rows -- a 392-float row is only
+// three 16-byte words per lane of a full warp, too few loads in flight to cover the HBM latency: r01H 0.52 of the roofline).
+template <int G>
 __global__ void __launch_bounds__(kPoolThreads)
 k_global_pool(const float* __restrict__ in, long long rows, long long C, long long S, float* __restrict__ out, long long out_ld,
               int vec4) {
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / G;                            // rows per warp
+  const int lane = threadIdx.x & 31, gl = lane % G, grp = lane / G;
   const long long nw = (long long)gridDim.x * (kPoolThreads / 32);
-  for (long long r = (long long)blockIdx.x * (kPoolThreads / 32) + (threadIdx.x >> 5); r < rows; r += nw) {
-    const float* p = in + r * S;
+  // the row loop is warp-uniform (base), so every lane reaches the shuffles
+  for (long long base = ((long long)blockIdx.x * (kPoolThreads / 32) + (threadIdx.x >> 5)) * RPW; base < rows; base += nw * RPW) {
+    const long long r = base + grp;
+    const bool valid = r < rows;
+    const float* p = in + (valid ? r : 0) * S;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    if (vec4) {                                          // S % 4 == 0 and a 16-byte aligned base: every row is aligned
-      const float4* p4 = reinterpret_cast<const float4*>(p);
-      const long long n4 = S >> 2;
-      long long i = lane;
-      for (; i + 96 < n4; i += 128) {
-        const float4 v0 = __ldcs(p4 + i), v1 = __ldcs(p4 + i + 32), v2 = __ldcs(p4 + i + 64), v3 = __ldcs(p4 + i + 96);
-        a0 += (v0.x + v0.y) + (v0.z + v0.w); a1 += (v1.x + v1.y) + (v1.z + v1.w);
-        a2 += (v2.x + v2.y) + (v2.z + v2.w); a3 += (v3.x + v3.y) + (v3.z + v3.w);
+    if (valid) {
+      if (vec4) {                                        // S % 4 == 0 and a 16-byte aligned base: every row is aligned
+        const float4* p4 = reinterpret_cast<const float4*>(p);
+        const long long n4 = S >> 2;
+        long long i = gl;
+        for (; i + 3 * G < n4; i += 4 * G) {
+          const float4 v0 = __ldcs(p4 + i), v1 = __ldcs(p4 + i + G), v2 = __ldcs(p4 + i + 2 * G), v3 = __ldcs(p4 + i + 3 * G);
+          a0 += (v0.x + v0.y) + (v0.z + v0.w); a1 += (v1.x + v1.y) + (v1.z + v1.w);
+          a2 += (v2.x + v2.y) + (v2.z + v2.w); a3 += (v3.x + v3.y) + (v3.z + v3.w);
+        }
+        for (; i < n4; i += G) { const float4 v = __ldcs(p4 + i); a0 += (v.x + v.y) + (v.z + v.w); }
+      } else {
+        long long i = gl;
+        for (; i + 3 * G < S; i += 4 * G) { a0 += __ldcs(p + i); a1 += __ldcs(p + i + G); a2 += __ldcs(p + i + 2 * G); a3 += __ldcs(p + i + 3 * G); }
+        for (; i < S; i += G) a0 += __ldcs(p + i);
       }
-      for (; i < n4; i += 32) { const float4 v = __ldcs(p4 + i); a0 += (v.x + v.y) + (v.z + v.w); }
-    } else {
-      long long i = lane;
-      for (; i + 96 < S; i += 128) { a0 += __ldcs(p + i); a1 += __ldcs(p + i + 32); a2 += __ldcs(p + i + 64); a3 += __ldcs(p + i + 96); }
-      for (; i < S; i += 32) a0 += __ldcs(p + i);
     }
-    const float s = warp_sum((a0 + a1) + (a2 + a3));
-    if (lane == 0) out[(r / C) * out_ld + (r % C)] = s / (float)S;
+    float s = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);      // o < G: stays inside the row's lanes
+    if (valid && gl == 0) out[(r / C) * out_ld + (r % C)] = s / (float)S;
   }
 }
 

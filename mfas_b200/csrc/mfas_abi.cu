@@ -982,11 +982,13 @@ extern "C" int mfas_global_pool(int32_t device, const float* d_in, int64_t B, in
   if (!dg.ok) return fail(MFAS_ERR_CUDA, "cudaSetDevice(%d) failed", device);
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
-  const long long rows = (long long)B * C, per = kPoolThreads / 32;
+  const bool short_rows = S < 2048;                      // four rows per warp (see kernels_pool.cuh)
+  const long long rows = (long long)B * C, per = (kPoolThreads / 32) * (short_rows ? 4 : 1);
   const long long want = (rows + per - 1) / per, cap = (long long)nsm * 8;      // 8 CTAs of 256 threads per SM: full occupancy
   const int grid = (int)(want < cap ? want : cap);
   const int vec4 = (S % 4 == 0) && (((uintptr_t)d_in & 15) == 0);
-  k_global_pool<<<grid, kPoolThreads, 0, (cudaStream_t)stream>>>(d_in, rows, C, S, d_out, out_ld, vec4);
+  if (short_rows) k_global_pool<8><<<grid, kPoolThreads, 0, (cudaStream_t)stream>>>(d_in, rows, C, S, d_out, out_ld, vec4);
+  else k_global_pool<32><<<grid, kPoolThreads, 0, (cudaStream_t)stream>>>(d_in, rows, C, S, d_out, out_ld, vec4);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MFAS_ERR_CUDA, "k_global_pool launch failed: %s", cudaGetErrorString(e));
   return MFAS_OK;
