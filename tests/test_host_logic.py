@@ -226,3 +226,46 @@ def test_sliced_threaded_initialisation_equals_one_serial_fill(monkeypatch):
     for hp, hb, after in outs[1:]:
         assert torch.equal(hp, outs[0][0]) and torch.equal(hb, outs[0][1])
         assert torch.equal(after, outs[0][2]), "generator state diverged"
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in mfas_b200/_lib.py against the C compiler's view of include/mfas_b200.h: sizes and the
+    offsets of every field (an ABI drift between the header and the binding would otherwise only show on a GPU)."""
+    import ctypes as C
+    import subprocess
+    from mfas_b200 import _lib
+    pairs = {"mfas_layout": _lib.Layout, "mfas_cache_desc": _lib.CacheDesc, "mfas_arenas": _lib.Arenas,
+             "mfas_adam_hparams": _lib.AdamHParams, "mfas_run_args": _lib.RunArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/mfas_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  printf("abi %d flags %d %d\\n", MFAS_ABI_VERSION, MFAS_FLAG_MULTITASK, MFAS_FLAG_MULTILABEL);', '  return 0;', '}']
+    src = tmp_path / "abi_probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi_probe"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src)], check=True)
+    out = dict(l.split(" ", 1) for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines())
+    for cname, cls in pairs.items():
+        assert int(out[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+    assert out["abi"] == f"{_lib.ABI_VERSION} flags {_lib.FLAG_MULTITASK} {_lib.FLAG_MULTILABEL}"
+
+
+def test_argument_errors_need_no_gpu():
+    """Argument validation happens before any CUDA call: bad arguments are MFAS_ERR_INVALID with a message, GPU or not."""
+    import ctypes as C
+    from mfas_b200 import _lib
+    lib = _lib.lib()
+    buf = (C.c_float * 8)()
+    assert lib.mfas_global_pool(0, None, 1, 1, 1, None, 1, None) == -1
+    assert lib.mfas_global_pool(0, C.addressof(buf), 2, 4, 1, C.addressof(buf), 3, None) == -1      # out_ld < C
+    assert b"out_ld" in lib.mfas_last_error()
+    assert lib.mfas_group_create(0, 0, None, 64, 0.0, 0, None, None) == -1
+    lay = _lib.Layout()
+    d = (C.c_int32 * 4)(64, 128, 64, 128)
+    conf = (C.c_int32 * 3)(0, 0, 7)
+    assert lib.mfas_plan_layout(1, conf, 64, 23, _lib.FLAG_BN | _lib.FLAG_MULTILABEL, d, d, C.byref(lay)) == -1      # activation 7
+    assert b"activation" in lib.mfas_last_error()
