@@ -217,6 +217,14 @@ int mfas_group_chain_timeline(mfas_group_t g, int64_t* out, int32_t n_cand);
 int mfas_host_uniform_fill(uint8_t* torch_rng_state, int64_t state_bytes, int32_t n_ops, float* const* dst,
                            const int64_t* count, const float* from, const float* to, int32_t use_fma);
 
+/* Host-only planning aid (no GPU): the tile list the persistent weight-gradient + Adam kernel of the tensor-core engine walks
+ * for these candidates -- out[i] = {candidate, layer, first weight column, first output row} of tile i, 128 columns x 64 rows at
+ * most, never across two concat sources [first-modality tap | second-modality tap | hidden]; with head_tiles the classifier
+ * tiles (layer == L) follow.  out may be NULL to query the counts.  Replaces nothing in the reference (autograd has no tiles);
+ * exported so that the tiling rules are testable without a GPU. */
+int mfas_plan_bwd_tiles(const mfas_layout* layouts, int32_t n_cand, int32_t head_tiles, int32_t* out, int64_t max_tiles,
+                        int64_t* n_tiles, int64_t* n_layer_tiles);
+
 /* ---- feature-cache builder (the step before the path) ----------------------------------
  * Global average pooling of one backbone tap into its column slice of a cache matrix:
  *   d_out[b * out_ld + c] = mean over s of d_in[(b * C + c) * S + s]

@@ -94,6 +94,7 @@ SYMBOLS = {
     "mfas_group_set_profiling": (C.c_int, [_P, C.c_int32]),
     "mfas_group_last_step_ms": (C.c_int, [_P, _P]),
     "mfas_group_chain_timeline": (C.c_int, [_P, _P, C.c_int32]),
+    "mfas_plan_bwd_tiles": (C.c_int, [C.POINTER(Layout), C.c_int32, C.c_int32, _P, C.c_int64, _P, _P]),
     "mfas_global_pool": (C.c_int, [C.c_int32, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, _P]),
     "mfas_host_uniform_fill": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P, C.c_int32]),
 }

@@ -183,6 +183,38 @@ extern "C" int mfas_release_cached_memory(void) {
   return MFAS_OK;
 }
 
+// Tile list of the persistent backward (k_tc_bwd_ws): {candidate, layer, first weight column, first row} of every
+// 128-column x 64-row tile of every fusion layer -- cut at the boundaries of the concat sources [ske | rgb | hidden], so that
+// a tile reads its x columns from ONE source (a tap narrower than / not a multiple of 128 columns is a short tile) --
+// followed, when the classifier head runs on the tensor core, by the classifier tiles (layer == L).  Returns the number
+// of fusion-layer tiles.  Host only.
+static int build_bwd_tiles(const mfas_layout* lay, int n_cand, bool head_tiles, std::vector<int4>& tl) {
+  for (int c = 0; c < n_cand; ++c)
+    for (int l = 0; l < lay[c].L; ++l)
+      for (int s0 = 0; s0 < lay[c].K[l]; s0 = tc_bwd_seg_end(lay[c].d_ske[l], lay[c].d_rgb[l], lay[c].K[l], s0))
+        for (int kc0 = s0; kc0 < tc_bwd_seg_end(lay[c].d_ske[l], lay[c].d_rgb[l], lay[c].K[l], s0); kc0 += TC_BWD_KT)
+          for (int h0 = 0; h0 < lay[c].H; h0 += TC_BWD_HT) tl.push_back(make_int4(c, l, kc0, h0));
+  const int n_layer_tiles = (int)tl.size();
+  if (head_tiles)                                       // classifier tiles last: a step that ran k_head instead simply stops short of them
+    for (int c = 0; c < n_cand; ++c)
+      for (int kc0 = 0; kc0 < lay[c].H; kc0 += TC_BWD_KT) tl.push_back(make_int4(c, lay[c].L, kc0, 0));
+  return n_layer_tiles;
+}
+
+extern "C" int mfas_plan_bwd_tiles(const mfas_layout* layouts, int32_t n_cand, int32_t head_tiles, int32_t* out, int64_t max_tiles,
+                                   int64_t* n_tiles, int64_t* n_layer_tiles) {
+  if (!layouts || n_cand < 1 || !n_tiles) return fail(MFAS_ERR_INVALID, "null argument / n_cand=%d", n_cand);
+  std::vector<int4> tl;
+  const int nl = build_bwd_tiles(layouts, n_cand, head_tiles != 0, tl);
+  *n_tiles = (int64_t)tl.size();
+  if (n_layer_tiles) *n_layer_tiles = nl;
+  if (out) {
+    if ((int64_t)tl.size() > max_tiles) return fail(MFAS_ERR_INVALID, "%zu tiles do not fit max_tiles=%lld", tl.size(), (long long)max_tiles);
+    for (size_t i = 0; i < tl.size(); ++i) { out[4 * i] = tl[i].x; out[4 * i + 1] = tl[i].y; out[4 * i + 2] = tl[i].z; out[4 * i + 3] = tl[i].w; }
+  }
+  return MFAS_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // group
 // ---------------------------------------------------------------------------------------------
@@ -475,15 +507,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     { const char* he = getenv("MFAS_HEAD"); if (he && !strcmp(he, "ffma")) g->tchead = false; }
     if (g->bwd_ws) {
       std::vector<int4> tl;
-      for (int c = 0; c < n_cand; ++c)
-        for (int l = 0; l < g->lay[c].L; ++l)       // 128-column tiles inside each concat source [ske | rgb | hidden]
-          for (int s0 = 0; s0 < g->lay[c].K[l]; s0 = tc_bwd_seg_end(g->lay[c].d_ske[l], g->lay[c].d_rgb[l], g->lay[c].K[l], s0))
-            for (int kc0 = s0; kc0 < tc_bwd_seg_end(g->lay[c].d_ske[l], g->lay[c].d_rgb[l], g->lay[c].K[l], s0); kc0 += TC_BWD_KT)
-              for (int h0 = 0; h0 < g->lay[c].H; h0 += TC_BWD_HT) tl.push_back(make_int4(c, l, kc0, h0));
-      g->n_bwd_layer_tiles = (int)tl.size();
-      if (g->tchead)                                    // classifier tiles last: a step that ran k_head instead simply stops short of them
-        for (int c = 0; c < n_cand; ++c)
-          for (int kc0 = 0; kc0 < g->lay[c].H; kc0 += TC_BWD_KT) tl.push_back(make_int4(c, g->lay[c].L, kc0, 0));
+      g->n_bwd_layer_tiles = build_bwd_tiles(g->lay.data(), n_cand, g->tchead, tl);
       g->n_bwd_tiles = (int)tl.size();
       if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(BwdTile) * tl.size(), &g->bwd_tiles, &g->tiles_bytes);
       g->bwd_tl = std::move(tl);

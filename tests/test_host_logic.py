@@ -269,3 +269,48 @@ def test_argument_errors_need_no_gpu():
     conf = (C.c_int32 * 3)(0, 0, 7)
     assert lib.mfas_plan_layout(1, conf, 64, 23, _lib.FLAG_BN | _lib.FLAG_MULTILABEL, d, d, C.byref(lay)) == -1      # activation 7
     assert b"activation" in lib.mfas_last_error()
+
+
+def test_backward_tile_list_covers_every_weight_once_and_never_straddles_a_source():
+    """Tiling rules of the persistent weight-gradient kernel (host only, mfas_plan_bwd_tiles): for any tap set the tiles of a
+    layer partition its [H, K] weight matrix, no tile reads x columns from two concat sources, the NTU list is the plain
+    128-column walk it always was, classifier tiles come last."""
+    import ctypes as C
+    from mfas_b200 import _lib
+    from mfas_b200.engine import plan_layout
+    lib = _lib.lib()
+
+    def tiles_of(layouts, head):
+        arr = (_lib.Layout * len(layouts))(*layouts)
+        n, nl = C.c_int64(), C.c_int64()
+        assert lib.mfas_plan_bwd_tiles(arr, len(layouts), int(head), None, 0, C.byref(n), C.byref(nl)) == 0
+        out = (C.c_int32 * (4 * n.value))()
+        assert lib.mfas_plan_bwd_tiles(arr, len(layouts), int(head), C.addressof(out), n.value, C.byref(n), C.byref(nl)) == 0
+        return np.array(out, dtype=np.int64).reshape(-1, 4), nl.value
+
+    ntu = plan_layout(FOUND_CONFS[4], 128, 60, _lib.FLAG_BN)
+    t, nl = tiles_of([ntu], head=True)
+    plain = [(0, l, k, h) for l in range(4) for k in range(0, ntu.K[l], 128) for h in range(0, 128, 64)]
+    assert [tuple(r) for r in t[:nl]] == plain
+    assert [tuple(r) for r in t[nl:]] == [(0, 4, 0, 0)]                       # W_c [60, 128]: one classifier tile
+
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        d0 = [int(32 * rng.integers(1, 9)) for _ in range(4)]
+        d1 = [int(32 * rng.integers(1, 20)) for _ in range(4)]
+        L, H = int(rng.integers(1, 5)), int(rng.choice([64, 128, 192, 256]))
+        conf = [[int(rng.integers(0, 4)), int(rng.integers(0, 4)), int(rng.integers(0, 3))] for _ in range(L)]
+        lays = [plan_layout(conf, H, 23, _lib.FLAG_BN | _lib.FLAG_MULTILABEL, widths=(d0, d1)),
+                plan_layout(conf[:1], H, 23, _lib.FLAG_BN | _lib.FLAG_MULTILABEL, widths=(d0, d1))]
+        t, nl = tiles_of(lays, head=False)
+        assert nl == len(t)
+        for c, lay in enumerate(lays):
+            for l in range(lay.L):
+                cover = np.zeros((H, lay.K[l]), dtype=np.int32)
+                bounds = (lay.d_ske[l], lay.d_ske[l] + lay.d_rgb[l], lay.K[l])
+                for _, _, kc0, h0 in t[(t[:, 0] == c) & (t[:, 1] == l)]:
+                    seg_end = next(b for b in bounds if kc0 < b)
+                    kw = min(128, seg_end - kc0)
+                    assert kw > 0 and kw % 16 == 0
+                    cover[h0:h0 + 64, kc0:kc0 + kw] += 1
+                assert (cover == 1).all(), (trial, c, l)
