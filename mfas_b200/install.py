@@ -53,3 +53,28 @@ def cached_ntu_searcher(S, args, device, train_cache, dev_cache, seed=0):
                                 "dev": FeatureCacheLoader(dev_cache, args.batchsize, True, seed + 50000)}
 
     return CachedNTUSearcher()
+
+
+def cached_mmimdb_searcher(S, args, device, train_cache, dev_cache, seed=0):
+    """The searcher the reference lacks for MM-IMDB, by analogy with `NTUSearcher`
+    (models/searchable.py:233-260): a `ModelSearcher` whose `search()` hands
+    `mmimdb_searchable.train_sampled_models` / `get_possible_layer_configurations` / `Searchable_Text_Image_Net` to the
+    reference's own `_epnas` loop.  `train_cache` / `dev_cache`: `mmimdb_searchable.text_image_cache(...)` splits."""
+    from . import mmimdb_searchable as mm
+
+    class CachedMMIMDBSearcher(S.ModelSearcher):
+        def __init__(self):
+            S.ModelSearcher.__init__(self, args)
+            self.device = device
+            self.dataloaders = {"train": mm.TextImageCacheLoader(train_cache, args.batchsize, True, seed),
+                                "dev": mm.TextImageCacheLoader(dev_cache, args.batchsize, True, seed + 50000)}
+
+        def search(self):
+            surrogate = S.surr.SimpleRecurrentSurrogate(100, 3, 100)          # as NTUSearcher.search, :253-260
+            surrogate.to(self.device)
+            surrogate_dict = {'model': surrogate, 'criterion': S.torch.nn.MSELoss()}
+            searchmethods = {'train_sampled_fun': mm.train_sampled_models,
+                             'get_layer_confs': mm.get_possible_layer_configurations}
+            return self._epnas(mm.Searchable_Text_Image_Net, surrogate_dict, self.dataloaders, searchmethods, self.device)
+
+    return CachedMMIMDBSearcher()

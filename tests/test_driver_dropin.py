@@ -1,0 +1,82 @@
+"""Drop-in boundary at the level of the reference's search driver (CPU, build container only): the UNMODIFIED
+`ModelSearcher._epnas` loop (/root/reference/models/searchable.py:48-137) is run over this package's modules -- search-space
+functions, configuration format, return types -- with the candidate trainer stubbed (training itself needs a GPU and is
+covered by the `-m gpu` tests).  Skipped where /root/reference does not exist (the GPU box)."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), reason="the reference tree is not present")
+
+
+def _search_args(**kw):
+    d = dict(lr_surrogate=1e-3, epochs_surrogate=3, search_iterations=2, max_progression_levels=2, num_samples=3,
+             initial_temperature=10.0, final_temperature=0.2, temperature_decay=4.0, verbose=False, batchsize=16, epochs=1,
+             inner_representation_size=64, num_outputs=23, drpt=0.0, batchnorm=True, alphas=False, multitask=False,
+             weightsharing=False, use_dataparallel=False, eta_max=1e-3, eta_min=1e-6, Ti=1, Tm=2, vid_len=(8, 32),
+             checkpointdir="", ske_cp="ske", rgb_cp="rgb")
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+@pytest.fixture()
+def ref_searchable():
+    saved_path, saved_mods = list(sys.path), dict(sys.modules)
+    sys.path.insert(0, REF)
+    import mfas_b200.install as b200
+    b200.install()
+    import models.searchable as S
+    yield S, b200
+    sys.path[:] = saved_path
+    for k in list(sys.modules):
+        if k not in saved_mods and (k == "models" or k.startswith("models.") or k.startswith("matplotlib")):
+            del sys.modules[k]
+
+
+def test_reference_epnas_runs_over_the_mmimdb_module(ref_searchable, monkeypatch):
+    S, b200 = ref_searchable
+    import mfas_b200.mmimdb_searchable as mm
+    train, dev = mm.synthetic_mmimdb_cache(64, 1), mm.synthetic_mmimdb_cache(32, 2)
+    calls = []
+
+    def fake_train(confs, searchable_type, dataloaders, args, device, state_dict=dict(), **kw):
+        assert searchable_type is mm.Searchable_Text_Image_Net and set(dataloaders) == {"train", "dev"}
+        for c in confs:
+            c = np.asarray(c)
+            assert c.ndim == 2 and c.shape[1] == 3 and c[:, 0].max() < 2 and c[:, 1].max() < 4 and c[:, 2].max() < 2
+            searchable_type(args, c)                                  # every sampled configuration is constructible
+        calls.append(len(confs))
+        # what the real trainer returns: 0-dim float64 CPU tensors (np.array(accs) must work)
+        return [torch.tensor(0.3 + 0.01 * (int(np.asarray(c).sum()) % 7), dtype=torch.float64) for c in confs]
+
+    monkeypatch.setattr(mm, "train_sampled_models", fake_train)
+    torch.manual_seed(0); np.random.seed(0)
+    s_data = b200.cached_mmimdb_searcher(S, _search_args(), torch.device("cpu"), train, dev).search()
+    assert calls[0] == 16 and all(c == 3 for c in calls[1:]) and len(calls) == 4      # 16 one-step rows, then K = 3 per step
+    confs, accs = s_data.get_data(to_torch=False)            # grouped by depth: arrays [L, n, 3]; re-sampled confs overwrite
+    assert 16 <= sum(np.asarray(c).shape[1] for c in confs) <= 16 + 3 * 3 and {np.asarray(c).shape[0] for c in confs} == {1, 2}
+
+
+def test_reference_epnas_runs_over_the_ntu_module(ref_searchable, monkeypatch):
+    S, b200 = ref_searchable
+    import mfas_b200.ntu_searchable as ntu
+    from mfas_b200.cache import synthetic_ntu_cache
+    assert sys.modules["models.search.ntu_searchable"] is ntu and S.ntu is ntu           # install() rebinds the driver's import
+    calls = []
+
+    def fake_train(confs, searchable_type, dataloaders, args, device, state_dict=dict(), **kw):
+        assert searchable_type is ntu.Searchable_Skeleton_Image_Net
+        calls.append(len(confs))
+        return [torch.tensor(0.5 + 0.001 * i, dtype=torch.float64) for i, _ in enumerate(confs)]
+
+    monkeypatch.setattr(ntu, "train_sampled_models", fake_train)
+    torch.manual_seed(0); np.random.seed(0)
+    searcher = b200.cached_ntu_searcher(S, _search_args(num_outputs=60), torch.device("cpu"), synthetic_ntu_cache(32, 1),
+                                        synthetic_ntu_cache(16, 2))
+    searcher.search()
+    assert calls[0] == 32 and all(c == 3 for c in calls[1:]) and len(calls) == 4
