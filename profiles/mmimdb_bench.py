@@ -3,7 +3,8 @@
 64 candidates x 3 epochs, inner_repr=256, bs=64, synthetic taps at the dataset's size (15552 train / 2608 dev rows), one
 GPU.  Times `mfas_b200.mmimdb_searchable.train_sampled_models` end to end (host buffers in, F1 list out) after one warm-up
 call (median of 3 calls) and prints one JSON line with candidate-epochs/s and the HBM-roofline fraction of the train steps
-(algorithmic bytes, SURVEY.md 8(d), / wall time).  Usage: python profiles/mmimdb_bench.py [n_candidates] [epochs]
+(algorithmic bytes, SURVEY.md 8(d), / wall time).  Adds `cpu_baseline`: the PyTorch-CPU port of the same step on the host cores (bounded sample).
+Usage: python profiles/mmimdb_bench.py [n_candidates] [epochs] [--cpu-only]
 """
 import json
 import os
@@ -22,9 +23,31 @@ from mfas_b200 import _lib  # noqa: E402
 from mfas_b200.engine import algorithmic_counts, plan_layout  # noqa: E402
 
 
+def cpu_baseline(confs, train, n_sample=4, train_steps=40, eval_steps=10):
+    """The PyTorch-CPU port of the same step (oracle/torch_port_mmimdb.py) on the host cores, a bounded sample: the first
+    ``n_sample`` candidates, ``train_steps`` + ``eval_steps`` timed steps each, scaled to a 243 + 41-step candidate-epoch."""
+    from oracle import torch_port_mmimdb as TP
+    torch.set_num_threads(os.cpu_count() or 1)
+    steps_tr, steps_dv = -(-15552 // 64), -(-2608 // 64)
+    secs = []
+    for c in confs[:n_sample]:
+        tr, ev = TP.timed_sample(c, 256, 23, train.ske_cat, train.rgb_cat, train.labels, train.pos_weight, 64, train_steps, eval_steps)
+        secs.append(steps_tr * tr + steps_dv * ev)
+    return {"value": 1.0 / (sum(secs) / len(secs)), "unit": "candidate-epochs/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle/torch_port_mmimdb.py, {n_sample} candidates x ({train_steps} train + {eval_steps} eval steps), "
+                      f"scaled to {steps_tr} + {steps_dv} steps per candidate-epoch"}
+
+
 def main():
-    n_cand = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-    epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    args_ = [a for a in sys.argv[1:] if not a.startswith("--")]
+    n_cand = int(args_[0]) if len(args_) > 0 else 64
+    epochs = int(args_[1]) if len(args_) > 1 else 3
+    if "--cpu-only" in sys.argv:                                # the baseline leg alone (no GPU needed)
+        rows = mm.get_possible_layer_configurations(0)
+        rng = np.random.default_rng(0)
+        confs = [np.array([rows[i] for i in rng.integers(0, len(rows), size=2)]) for _ in range(n_cand)]
+        print(json.dumps({"cpu_baseline": cpu_baseline(confs, mm.synthetic_mmimdb_cache(15552, 1))}))
+        return
     dev = torch.device("cuda:0")
     train, devs = mm.synthetic_mmimdb_cache(15552, 1).pin(), mm.synthetic_mmimdb_cache(2608, 2).pin()
     rows = mm.get_possible_layer_configurations(0)
@@ -61,7 +84,8 @@ def main():
                       "config": {"workload": f"BASELINE configs[3]: MM-IMDB text+image searchable fusion, {n_cand} candidates x "
                                              f"{epochs} epochs, inner_repr=256, L=2, bs=64, 15552/2608 rows"},
                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None},
-                      "dev_f1_samples": {"min": float(min(f1s)), "max": float(max(f1s))}}))
+                      "dev_f1_samples": {"min": float(min(f1s)), "max": float(max(f1s))},
+                      "cpu_baseline": cpu_baseline(confs, train)}))
 
 
 if __name__ == "__main__":

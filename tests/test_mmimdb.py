@@ -76,6 +76,27 @@ def test_oracle_matches_reference_loop():
             assert _rel_l2(sample_tensor(v)["sample"], gold[f"c{ci}/final/{k}/sample"]) < 0.25, (ci, k)
 
 
+def test_torch_port_matches_reference_fixture():
+    """oracle/torch_port_mmimdb.py (the timed CPU baseline of configs[3]) against the executed reference pieces: one step."""
+    from oracle import torch_port_mmimdb as TP
+    mm, cs, gold, train, dev, inits = _case()
+    for ci, conf in enumerate(cs["confs"]):
+        m = TP.TextImageHeadTorch(conf, cs["H"], 23)
+        m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in inits[ci].items() if not k.startswith("alphas")})
+        m.train(True)
+        rows = _loaders(mm, cs, train, dev, ci)["train"].order_for_pass(0)[:cs["B"]]
+        logits = m(train.ske_cat[rows], train.rgb_cat[rows])
+        loss = TP.weighted_bce_with_logits(logits, train.labels[rows], train.pos_weight)
+        loss.backward()
+        assert np.abs(logits.detach().numpy() - gold[f"c{ci}/step/logits"]).max() < 1e-5 * np.abs(gold[f"c{ci}/step/logits"]).max()
+        assert abs(loss.item() - float(gold[f"c{ci}/step/loss"])) < 1e-5 * float(gold[f"c{ci}/step/loss"])
+        for k, p_ in m.named_parameters():
+            r = gold[f"c{ci}/step/grad/{k}"]
+            assert np.abs(p_.grad.numpy() - r).max() < 1e-4 * max(np.abs(r).max(), 1e-12), (ci, k)
+    tr, ev = TP.timed_sample(cs["confs"][1], 64, 23, train.ske_cat, train.rgb_cat, train.labels, train.pos_weight, 32, 2, 2)
+    assert tr > 0 and ev > 0
+
+
 def test_oracle_nan_loss_escape():
     """A NaN train loss ends the run with the best F1 seen before (train_searchable/mmimdb.py:105-109)."""
     mm, cs, gold, train, dev, inits = _case()
