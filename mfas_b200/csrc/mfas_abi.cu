@@ -107,8 +107,10 @@ extern "C" int mfas_algorithmic_counts(const mfas_layout* lay, int32_t batch, do
   }
   if (lay->flags & MFAS_FLAG_BN) P += 2 * H * L;
   P += C * H + C;
-  out[0] = 4 * (B * F_sel + 6 * P) + 8 * B;      // train step bytes
-  out[1] = 4 * (B * F_sel + P) + 8 * B;          // eval step bytes
+  // labels: B int64 class ids, or (multi-label head) B x C fp32 targets + C positive-class weights
+  const double lab = (lay->flags & MFAS_FLAG_MULTILABEL) ? 4 * (B * C + C) : 8 * B;
+  out[0] = 4 * (B * F_sel + 6 * P) + lab;        // train step bytes
+  out[1] = 4 * (B * F_sel + P) + lab;            // eval step bytes
   out[2] = 2 * B * (sumK * H + H * C);           // forward flops
   out[3] = out[2] + 2 * B * H * H * (L - 1) + 2 * B * H * C;
   return MFAS_OK;

@@ -124,6 +124,13 @@ def test_host_layout_init_and_errors():
     assert lay.flags & _lib.FLAG_MULTILABEL
     with pytest.raises(ValueError):
         plan_layout([[2, 0, 0]], 64, 23, flags, widths=WIDTHS)            # only 2 text taps
+    # algorithmic bytes with the multi-label inputs: features once, p / m / v read + written, B x C targets + C weights
+    from mfas_b200.engine import algorithmic_counts
+    P_ = sum(lay.K[l] * 64 + 64 + 2 * 64 for l in range(3)) + 23 * 64 + 23
+    F_sel = sum(lay.d_ske[l] + lay.d_rgb[l] for l in range(3))
+    cnt = algorithmic_counts(lay, 32)
+    assert cnt["train_bytes"] == 4 * (32 * F_sel + 6 * P_) + 4 * (32 * 23 + 23)
+    assert cnt["eval_bytes"] == 4 * (32 * F_sel + P_) + 4 * (32 * 23 + 23)
     assert len(mm.get_possible_layer_configurations(0)) == 16
     args = make_mmimdb_args(cs["H"], cs["B"], cs["epochs"])
     with pytest.raises(ValueError):
