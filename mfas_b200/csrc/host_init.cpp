@@ -92,6 +92,9 @@ __attribute__((target("avx2,fma"))) void emit_avx2(const uint32_t* s, float* out
 }
 #endif
 
+// (Also measured in the build container and dropped, 154 M-word fill with 2 consumers at 64-69 ms: regenerating out of place straight
+// into the ring instead of regen + memcpy: 64-68 ms, within noise -- the consumers' stores set the pace, not the producer;
+// non-temporal stores in emit_avx2: 80 ms.)
 // (A 16-lane AVX-512F twist was measured and dropped: on the build container's Xeon the 154 M-word fill went from 68 to 120 ms
 // with 2 consumers and from 114 to 133 ms serial -- 512-bit unaligned loads and the licence down-clock cost more than the lanes gain.)
 
