@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.environ.get("MFAS_GOLDEN_OUT", HERE)          # tests regenerate into a scratch directory and compare
 sys.path.insert(0, "/root/reference")
 from models.auxiliary.aux_models import WeightedCrossEntropyWithLogits      # noqa: E402
 from sklearn.metrics import f1_score                                        # noqa: E402
@@ -35,7 +36,7 @@ def main():
             f1 = f1_score(targets.numpy(), (torch.sigmoid(logits.detach()) > 0.3).numpy(), average="samples")
         out.update({f"{name}_logits": logits.detach().numpy(), f"{name}_targets": targets.numpy(), f"{name}_pos_weight": pos_weight,
                     f"{name}_loss": np.float32(loss.item()), f"{name}_dlogits": logits.grad.numpy(), f"{name}_f1": np.float64(f1)})
-    np.savez_compressed(os.path.join(HERE, "mmimdb_head.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "mmimdb_head.npz"), **out)
     print({k: (v.shape if hasattr(v, "shape") and v.shape else float(v)) for k, v in out.items() if k.endswith(("loss", "f1"))})
 
 

@@ -23,6 +23,7 @@ import torch.nn as nn
 import torch.optim as op
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.environ.get("MFAS_GOLDEN_OUT", HERE)          # tests regenerate into a scratch directory and compare
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -111,7 +112,7 @@ def main():
             for kk, vv in sample_tensor(v.numpy()).items():
                 out[f"c{ci}/final/{k}/{kk}"] = np.asarray(vv)
         print(ci, conf, "best F1", best, "per epoch", f1s)
-    np.savez_compressed(os.path.join(HERE, "mmimdb_path.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "mmimdb_path.npz"), **out)
 
 
 if __name__ == "__main__":

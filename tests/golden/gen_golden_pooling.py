@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.environ.get("MFAS_GOLDEN_OUT", HERE)          # tests regenerate into a scratch directory and compare
 sys.path.insert(0, "/root/reference")
 from models.auxiliary.aux_models import GlobalPooling2D  # noqa: E402
 
@@ -26,7 +27,7 @@ def main():
         x = torch.randn(*shape, generator=g).abs()
         out[name + "_x"] = x.numpy()
         out[name + "_y"] = gp(x).numpy()
-    np.savez_compressed(os.path.join(HERE, "pooling.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "pooling.npz"), **out)
     print({k: v.shape for k, v in out.items()})
 
 
