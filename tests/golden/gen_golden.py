@@ -188,7 +188,7 @@ def run_case(name, cs):
             out[f"c{ci}/adam_t"] = np.int64(int(st["step"]))
     out["meta/torch"] = np.array(torch.__version__)
     out["meta/loader_seed"] = np.int64(LOADER_SEED)
-    path = os.path.join(HERE, name + ".npz")
+    path = os.path.join(os.environ.get("MFAS_GOLDEN_OUT", HERE), name + ".npz")
     np.savez_compressed(path, **out)
     print(name, "->", path, os.path.getsize(path) // 1024, "KiB; best accs",
           [float(a) for a in accs])

@@ -98,7 +98,7 @@ def main():
         for kk, vv in sample_tensor(v.numpy()).items():
             out[f"final/{k}/{kk}"] = np.asarray(vv)
     out["meta/torch"] = np.array(torch.__version__)
-    path = os.path.join(HERE, "found_mt.npz")
+    path = os.path.join(os.environ.get("MFAS_GOLDEN_OUT", HERE), "found_mt.npz")
     np.savez_compressed(path, **out)
     print(text[-600:])
     print("->", path, os.path.getsize(path) // 1024, "KiB; test acc", float(test_acc))

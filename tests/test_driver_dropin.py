@@ -82,21 +82,23 @@ def test_reference_epnas_runs_over_the_ntu_module(ref_searchable, monkeypatch):
     assert calls[0] == 32 and all(c == 3 for c in calls[1:]) and len(calls) == 4
 
 
-@pytest.mark.parametrize("script,fixture", [("gen_golden_pooling.py", "pooling.npz"), ("gen_golden_mmimdb.py", "mmimdb_head.npz"),
-                                            ("gen_golden_mmimdb_path.py", "mmimdb_path.npz")])
-def test_committed_fixtures_are_what_executing_the_reference_produces(script, fixture, tmp_path):
+@pytest.mark.parametrize("script,fixtures", [("gen_golden_pooling.py", ["pooling.npz"]), ("gen_golden_mmimdb.py", ["mmimdb_head.npz"]),
+                                             ("gen_golden_mmimdb_path.py", ["mmimdb_path.npz"]), ("gen_golden_found.py", ["found_mt.npz"]),
+                                             ("gen_golden.py", ["cfg1.npz", "cfg2.npz", "mixL.npz", "alph.npz"])])
+def test_committed_fixtures_are_what_executing_the_reference_produces(script, fixtures, tmp_path):
     """Provenance of the golden vectors: re-run the committed generator (it executes the reference's own classes / loop)
     into a scratch directory and compare with the committed .npz, array by array."""
     import subprocess
     here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     env = dict(os.environ, MFAS_GOLDEN_OUT=str(tmp_path))
     subprocess.run([sys.executable, os.path.join(here, script)], check=True, env=env, capture_output=True, timeout=600)
-    new, old = np.load(tmp_path / fixture), np.load(os.path.join(here, fixture))
-    assert sorted(new.files) == sorted(old.files)
-    for k in old.files:
-        a, b = np.asarray(new[k]), np.asarray(old[k])
-        assert a.shape == b.shape and a.dtype == b.dtype, k
-        if a.dtype.kind == "f":          # same machine, same torch: bit-identical in practice; allow the last ulps of a threaded reduction
-            assert np.allclose(a, b, rtol=1e-6, atol=1e-9, equal_nan=True), k
-        else:
-            assert np.array_equal(a, b), k
+    for fixture in fixtures:
+        new, old = np.load(tmp_path / fixture), np.load(os.path.join(here, fixture))
+        assert sorted(new.files) == sorted(old.files), fixture
+        for k in old.files:
+            a, b = np.asarray(new[k]), np.asarray(old[k])
+            assert a.shape == b.shape and a.dtype == b.dtype, (fixture, k)
+            if a.dtype.kind == "f":      # same machine, same torch: bit-identical in practice; allow the last ulps of a threaded reduction
+                assert np.allclose(a, b, rtol=1e-6, atol=1e-9, equal_nan=True), (fixture, k)
+            else:
+                assert np.array_equal(a, b), (fixture, k)
