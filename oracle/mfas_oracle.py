@@ -22,6 +22,7 @@ Reference lines restated (all relative to /root/reference):
                               ``_single_tensor_adam``: lerp for exp_avg, addcmul for exp_avg_sq,
                               denom = sqrt(v)/sqrt(bc2) + eps, step = lr/bc1)
 * candidate loop ............ models/search/ntu_searchable.py:23-102
+* weight sharing ............ models/search/ntu_searchable.py:74-75, :91-92, :123-174
 
 The backward pass is hand derived (the reference uses autograd); it is the derivation the
 CUDA kernels implement, so the oracle validates the derivation as well as the arithmetic.
@@ -416,6 +417,52 @@ def test_track_acc(head, split, batch, order, multitask=False):
         _, preds = multitask_loss_preds(logits, y, _aux_of(split, rows, multitask))
         correct += int((preds == y).sum())
     return np.float64(correct / len(order))
+
+
+# --------------------------------------------------------------------------------------
+# weight sharing between the candidates of one call (args.weightsharing)
+# --------------------------------------------------------------------------------------
+_ACT_TAG = {ACT_RELU: ".A_relu", ACT_SIGMOID: ".A_sigmoid", ACT_LRELU: ".A_lrelu"}
+_LAYER_KEYS = ("0.weight", "0.bias", "2.weight", "2.bias", "2.running_mean", "2.running_var", "2.num_batches_tracked")
+
+
+def shared_key(head, l):
+    """'<step>.L_<in_features>_<out_features>.A_<act>' (ntu_searchable.py:131-140 / :161-170)."""
+    return f"{l}.L_{head.K[l]}_{head.H}" + _ACT_TAG.get(int(head.conf[l][2]), "")
+
+
+def get_central_states(head, shared):
+    """ntu_searchable.py:123-149: every fusion step of the trained candidate is stored under its key (created or overwritten)."""
+    for l in range(head.L):
+        shared[shared_key(head, l)] = {k: np.array(head.state[f"fusion_layers.{l}.{k}"], copy=True)
+                                       for k in _LAYER_KEYS if f"fusion_layers.{l}.{k}" in head.state}
+    return shared
+
+
+def set_central_states(head, shared):
+    """ntu_searchable.py:152-174: a fusion step whose key is in the dict starts from the stored layer (weights AND BatchNorm
+    buffers: ``layer.load_state_dict``); the classifier, the alphas and the optimiser state are never shared."""
+    for l in range(head.L):
+        key = shared_key(head, l)
+        if key in shared:
+            for k, v in shared[key].items():
+                head.state[f"fusion_layers.{l}.{k}"] = np.array(v, copy=True)
+
+
+def train_sampled_heads(heads, scheds, train_split, dev_split, batch, orders, num_epochs, weightsharing=False, shared=None):
+    """The candidate loop of train_sampled_models (ntu_searchable.py:36-97) over already-constructed heads: candidate ``ci``
+    sees passes ``orders(phase, ci, epoch)``; with ``weightsharing`` the candidates are chained through ``shared`` in order."""
+    shared = {} if shared is None else shared
+    accs, all_stats = [], []
+    for ci, (head, sched) in enumerate(zip(heads, scheds)):
+        if weightsharing:
+            set_central_states(head, shared)
+        best, stats = train_track_acc(head, sched, train_split, dev_split, batch, lambda ph, e, ci=ci: orders(ph, ci, e), num_epochs)
+        if weightsharing:
+            get_central_states(head, shared)
+        accs.append(best)
+        all_stats.append(stats)
+    return accs, all_stats
 
 
 # --------------------------------------------------------------------------------------

@@ -66,7 +66,7 @@ class StubSkel(nn.Module):
 central.Visual, central.Skeleton = StubVisual, StubSkel
 import models.search.ntu_searchable as ntu  # noqa: E402
 
-from helpers import GOLDEN_CASES, init_states, make_args, sample_tensor  # noqa: E402
+from helpers import GOLDEN_CASES, WS_CASES, init_states, make_args, sample_tensor  # noqa: E402
 from mfas_b200.cache import FeatureCacheLoader, synthetic_ntu_cache  # noqa: E402
 
 LOADER_SEED = 100
@@ -84,7 +84,8 @@ def run_case(name, cs):
     tmp = tempfile.mkdtemp()
     torch.save({}, os.path.join(tmp, "ske"))
     torch.save({}, os.path.join(tmp, "rgb"))
-    args = make_args(H, B, E, bn=cs["bn"], drpt=cs["drpt"], Ti=cs["Ti"], checkpointdir=tmp, alphas=cs.get("alphas", False))
+    args = make_args(H, B, E, bn=cs["bn"], drpt=cs["drpt"], Ti=cs["Ti"], checkpointdir=tmp, alphas=cs.get("alphas", False),
+                     weightsharing=cs.get("weightsharing", False))
     train = synthetic_ntu_cache(cs["n_train"], cs["data_seed"])
     dev = synthetic_ntu_cache(cs["n_dev"], cs["data_seed"] + 1)
     loaders = {"train": FeatureCacheLoader(train, B, True, LOADER_SEED),
@@ -140,8 +141,9 @@ def run_case(name, cs):
     ntu.op.Adam = RecAdam
     try:
         torch.manual_seed(cs["model_seed"])
+        shared = {}                     # args.weightsharing: the dict the reference chains the candidates through (:27,:74-75,:91-92)
         accs, models = ntu.train_sampled_models(confs, ntu.Searchable_Skeleton_Image_Net, loaders, args,
-                                                torch.device("cpu"), return_model=list(range(len(confs))))
+                                                torch.device("cpu"), return_model=list(range(len(confs))), state_dict=shared)
     finally:
         torch.optim.Adam = real_adam
         ntu.op.Adam = real_adam
@@ -186,6 +188,11 @@ def run_case(name, cs):
             flat(f"c{ci}/adam_m/{named[id(p)]}", sample_tensor(st["exp_avg"].numpy()), out)
             flat(f"c{ci}/adam_v/{named[id(p)]}", sample_tensor(st["exp_avg_sq"].numpy()), out)
             out[f"c{ci}/adam_t"] = np.int64(int(st["step"]))
+    if cs.get("weightsharing", False):
+        out["meta/shared_keys"] = np.array(sorted(shared.keys()))
+        for key, sd in shared.items():                      # what the dict holds after the call (the last writer's layer)
+            for kname, v in sd.items():
+                flat(f"shared/{key}/{kname}", sample_tensor(v.numpy()), out)
     out["meta/torch"] = np.array(torch.__version__)
     out["meta/loader_seed"] = np.int64(LOADER_SEED)
     path = os.path.join(os.environ.get("MFAS_GOLDEN_OUT", HERE), name + ".npz")
@@ -196,6 +203,6 @@ def run_case(name, cs):
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for name, cs in GOLDEN_CASES.items():
+    for name, cs in {**GOLDEN_CASES, **WS_CASES}.items():
         if not only or name in only:
             run_case(name, cs)

@@ -40,6 +40,14 @@ GOLDEN_CASES = {
 }
 
 
+# weight sharing (args.weightsharing, /root/reference/models/search/ntu_searchable.py:74-75,91-92,123-174): candidates are trained one
+# after the other and chained through a dict keyed '<step>.L_<in>_<out>.A_<act>'.  c0 / c1 / c3 share step 0 ('0.L_1536_32.A_sigmoid'),
+# c0 / c2 share step 1 ('1.L_2336_32.A_relu': 256 + 2048 + 32 both ways), c3 also shares its step 1 with c1.
+WS_CASES = {
+    "wsh": dict(confs=[[[3, 1, 1], [1, 3, 0]], [[3, 1, 1], [2, 2, 0]], [[0, 2, 0], [1, 3, 0]], [[3, 1, 1], [2, 2, 0], [0, 0, 1]]],
+                H=32, B=16, n_train=112, n_dev=120, epochs=2, bn=True, drpt=0.0, Ti=1, model_seed=6, data_seed=71, weightsharing=True),
+}
+
 # main_found_ntu.py flow (multitask + alphas, two training stages, test pass): tests/golden/gen_golden_found.py
 FOUND_MT_CASE = dict(conf=FOUND_CONFS[3][:3], H=32, B=16, n_train=96, n_dev=48, n_test=40, epochs=2, Ti=1, alphas=True,
                      model_seed=9, data_seed=51, loader_seed=300)

@@ -4,12 +4,16 @@ Tolerance: north_star asks for 1e-4 relative on logits / loss / trained weights 
  * Every single step is held to 1e-4 directly (logits, loss, every gradient), from the initial state and
    -- teacher-forced -- from states in the middle of a reference trajectory; the Adam arithmetic is held
    to 1e-6 given identical gradients.
- * A *trajectory* of Adam steps is ill-conditioned in fp32 whatever the implementation: the update
-   lr*m/(sqrt(v)+eps) is sign-like, so an element whose gradient is ~0 moves by +-lr depending on
-   rounding.  The reference's own algorithm run in fp32 vs fp64 (torch CPU, 21 steps at cfg2 shapes)
-   differs by 4e-4 in epoch loss and 3-18 % (max-norm) in trained weights ("Parity bar").
-   Multi-epoch quantities are therefore compared at TRAJ_LOSS / TRAJ_W below, and val-acc in samples.
+ * Trajectories (several epochs of Adam steps, the production ``mfas_train_run`` path) are held to
+       trained weights  relative L2 <= TRAJ_W    = 1e-3
+       epoch losses     relative    <= TRAJ_LOSS = 1e-4   (or 4 x the fp32 floor of the reference algorithm itself on that
+                                                           trajectory where the floor is above 2.5e-5: tests/golden/noise_floor.json,
+                                                           measured by tests/golden/noise_floor.py -- one case, cfg2 train loss 2.8e-4)
+       accuracies       <= ACC_SLACK = 1 sample
+   The floor (float32 vs float64 oracle on the same trajectory): weights <= 1.4e-4, losses <= 1.4e-5 (cfg2: 2.8e-4), accuracy 0.
+   Every achieved error is printed (pytest -rP / -s) and appended to gpurun_out/traj_errors.txt when that directory exists.
 """
+import json
 import math
 import os
 
@@ -23,9 +27,27 @@ from oracle import mfas_oracle as O
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
-TRAJ_LOSS = 1e-2      # epoch-level loss, relative
-TRAJ_W = 0.25         # trained weights, relative L2 (fp32-vs-fp64 band of the reference itself: up to 0.18 max-norm)
+TRAJ_LOSS = 1e-4      # epoch-level loss, relative
+TRAJ_W = 1e-3         # trained weights, relative L2
+TRAJ_V = 1e-2         # near-zero vectors along a trajectory (biases, running statistics): relative L2, reported
+ACC_SLACK = 1         # samples
 DEV = "cuda:0"
+_FLOOR = json.load(open(os.path.join(GOLDEN_DIR, "noise_floor.json")))["cases"]
+_LOG = os.path.join(os.path.dirname(GOLDEN_DIR), os.pardir, "gpurun_out")
+
+
+def _loss_tol(case, ci, key):
+    """TRAJ_LOSS, or 4 x the measured fp32 floor of the reference algorithm on this trajectory if that is larger."""
+    return max(TRAJ_LOSS, 4.0 * _FLOOR[case][ci][key])
+
+
+def _report(what, err, tol):
+    line = f"TRAJ {what}: achieved {err:.3e} (bound {tol:.1e})"
+    print(line)
+    if os.path.isdir(_LOG):
+        with open(os.path.join(_LOG, "traj_errors.txt"), "a") as f:
+            f.write(line + "\n")
+    assert err <= tol, line
 
 
 def _group(confs, H, B, bn=True, drpt=0.0, keep_grads=False, seed=0, ids=None, alphas=False, multitask=False):
@@ -51,6 +73,11 @@ def _close(a, b, tol, what, scale=None):
         raise AssertionError(f"{what}: rel err {err:.3e} >= {tol:.1e} at {i}: got {a[i]:.6e} ref {b[i]:.6e}; "
                              f"{nbad}/{d.size} elements over tol; rows {rows}")
     return err
+
+
+def _rel_max(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
 def _rel_l2(a, b):
@@ -220,25 +247,24 @@ def test_train_sampled_models_vs_reference_fixture(name):
         assert accs[ci].dtype == torch.float64 and accs[ci].dim() == 0 and accs[ci].device.type == "cpu"
         exp_tr = (gold[f"c{ci}/train_loss"] * wtr).sum(1)
         exp_dv = (gold[f"c{ci}/dev_loss"] * wdv).sum(1)
-        _close(stats[ci, :, 0], exp_tr, TRAJ_LOSS, f"{name} c{ci} epoch train loss")
-        _close(stats[ci, :, 2], exp_dv, TRAJ_LOSS, f"{name} c{ci} epoch dev loss")
-        slack = lambda n: max(2, 0.02 * n)
-        assert np.abs(stats[ci, :, 3] - gold[f"c{ci}/dev_correct"].sum(1)).max() <= slack(cs["n_dev"]), "dev correct counts"
-        assert np.abs(stats[ci, :, 1] - gold[f"c{ci}/train_correct"].sum(1)).max() <= slack(cs["n_train"]), "train correct counts"
-        assert abs(float(accs[ci]) - float(gold[f"c{ci}/best_acc"])) <= slack(cs["n_dev"]) / cs["n_dev"]
+        _report(f"{name} c{ci} epoch train loss vs reference fixture", _rel_max(stats[ci, :, 0], exp_tr), _loss_tol(name, ci, "train_loss_rel"))
+        _report(f"{name} c{ci} epoch dev loss vs reference fixture", _rel_max(stats[ci, :, 2], exp_dv), _loss_tol(name, ci, "dev_loss_rel"))
+        _report(f"{name} c{ci} dev correct counts", float(np.abs(stats[ci, :, 3] - gold[f"c{ci}/dev_correct"].sum(1)).max()), ACC_SLACK)
+        _report(f"{name} c{ci} train correct counts", float(np.abs(stats[ci, :, 1] - gold[f"c{ci}/train_correct"].sum(1)).max()), ACC_SLACK)
+        _report(f"{name} c{ci} best dev accuracy (samples)", abs(float(accs[ci]) - float(gold[f"c{ci}/best_acc"])) * cs["n_dev"], ACC_SLACK + 1e-9)
         sd = models[ci].state_dict()
         assert not models[ci].training
         for k, v in sd.items():
             if k.startswith("alphas"):
                 if cs.get("alphas", False):       # scalar gates: absolute agreement along the trajectory
-                    assert abs(float(v) - float(gold[f"c{ci}/final/{k}/sample"][0])) < 2e-3, f"{name} c{ci} final {k}"
+                    _report(f"{name} c{ci} final {k} (absolute)", abs(float(v) - float(gold[f"c{ci}/final/{k}/sample"][0])), 1e-4)
                 continue
             if k.endswith("num_batches_tracked"):
+                assert int(v) == int(gold[f"c{ci}/final/{k}/sample"][0]), k
                 continue
-            if k.endswith(".bias") or "running" in k:
-                continue            # near-zero vectors: relative error is meaningless along a trajectory
             fx = gold[f"c{ci}/final/{k}/sample"]
-            assert _rel_l2(sample_tensor(v.cpu().numpy())["sample"], fx) < TRAJ_W, f"{name} c{ci} final {k}"
+            vec = k.endswith(".bias") or "running" in k   # near-zero vectors (biases start at +-1/sqrt(K), BN shifts at 0): looser, reported
+            _report(f"{name} c{ci} final {k}", _rel_l2(sample_tensor(v.cpu().numpy())["sample"], fx), TRAJ_V if vec else TRAJ_W)
         # num_batches_tracked follows the rollback too
         if float(gold[f"c{ci}/best_acc"]) > 0:
             k = "fusion_layers.0.2.num_batches_tracked"
@@ -267,15 +293,24 @@ def test_run_vs_oracle_trajectory_cfg2_shapes():
     sched = O.CosineRestartLR(1e-3, 1e-6, 1, 2, ntr / B)
     obest, ostats = O.train_track_acc(head, sched, split_np(train), split_np(dev), B,
                                       lambda ph, e: (ltr if ph == "train" else ldv).order_for_pass(e).numpy(), E)
-    _close(stats[:, 0] / ntr, [s["train_loss"] for s in ostats], TRAJ_LOSS, "epoch train loss")
-    _close(stats[:, 2] / ndv, [s["dev_loss"] for s in ostats], TRAJ_LOSS, "epoch dev loss")
-    assert np.abs(stats[:, 3] / ndv - np.array([s["dev_acc"] for s in ostats])).max() <= 0.03
-    assert abs(best - float(obest)) <= 0.03
+    _report("traj_cfg2 epoch train loss vs oracle", _rel_max(stats[:, 0] / ntr, [s["train_loss"] for s in ostats]), _loss_tol("traj_cfg2", 0, "train_loss_rel"))
+    _report("traj_cfg2 epoch dev loss vs oracle", _rel_max(stats[:, 2] / ndv, [s["dev_loss"] for s in ostats]), _loss_tol("traj_cfg2", 0, "dev_loss_rel"))
+    _report("traj_cfg2 dev correct counts", float(np.abs(stats[:, 3] - ndv * np.array([s["dev_acc"] for s in ostats])).max()), ACC_SLACK + 1e-9)
+    _report("traj_cfg2 train correct counts", float(np.abs(stats[:, 1] - ntr * np.array([s["train_acc"] for s in ostats])).max()), ACC_SLACK + 1e-9)
+    _report("traj_cfg2 best dev accuracy (samples)", abs(best - float(obest)) * ndv, ACC_SLACK + 1e-9)
     assert best == pytest.approx(stats[:, 3].max() / ndv) and best_epoch == int(np.argmax(stats[:, 3]))   # strict '>' keeps the first maximum
     got = g.state(0)
     for k, ref in head.state.items():
-        if k.endswith("0.weight") or k.endswith("2.weight") or k == "central_classifier.weight":
-            assert _rel_l2(got[k], ref) < TRAJ_W, f"rolled-back {k}"
+        if k.endswith("num_batches_tracked") or k.startswith("alphas"):
+            continue
+        vec = k.endswith(".bias") or "running" in k
+        _report(f"traj_cfg2 rolled-back {k}", _rel_l2(got[k], ref), TRAJ_V if vec else TRAJ_W)
+    # the Adam moments are NOT rolled back: they are the state after the last step
+    gm, gv = g.state(0, "m"), g.state(0, "v")
+    for k, (m, v) in head.adam.items():
+        if k.endswith("0.weight") or k == "central_classifier.weight":
+            _report(f"traj_cfg2 exp_avg {k}", _rel_l2(gm[k], m), 10 * TRAJ_W)
+            _report(f"traj_cfg2 exp_avg_sq {k}", _rel_l2(gv[k], v), TRAJ_W)
     # the snapshot really is the best epoch's weights: BN step counter == steps up to that epoch
     steps_ep = math.ceil(ntr / B)
     assert int(got["fusion_layers.0.2.num_batches_tracked"]) == (best_epoch + 1) * steps_ep
@@ -370,15 +405,15 @@ def test_model_forward_and_found_flow():
     sched = O.CosineRestartLR(1e-3, 1e-6, 5, 2, ntr / B)
     obest, ostats = O.train_track_acc(head, sched, split_np(train), split_np(dev), B,
                                       lambda ph, e: loaders[ph].order_for_pass(e).numpy(), 2)
-    assert abs(float(best) - float(obest)) <= 2.0 / ndv
+    _report("found-flow (cfg1 shapes) best dev accuracy (samples)", abs(float(best) - float(obest)) * ndv, ACC_SLACK + 1e-9)
     sd = model.state_dict()
     for k, ref in head.state.items():
-        if k.endswith("0.weight") or k == "central_classifier.weight":
-            assert _rel_l2(sd[k].cpu().numpy(), ref) < TRAJ_W, f"found-flow final {k}"
+        if k.endswith("0.weight") or k.endswith("2.weight") or k == "central_classifier.weight":
+            _report(f"found-flow (cfg1 shapes) final {k}", _rel_l2(sd[k].cpu().numpy(), ref), TRAJ_W)
     assert opt.state[model.central_classifier.weight]["exp_avg"].shape == model.central_classifier.weight.shape
     acc = tr.test_ntu_track_acc(model, loaders, {"test": ndv}, device=torch.device(DEV))
     oacc = O.test_track_acc(head, split_np(dev), B, np.arange(ndv))
-    assert abs(float(acc) - float(oacc)) <= 2.0 / ndv
+    _report("found-flow (cfg1 shapes) test accuracy (samples)", abs(float(acc) - float(oacc)) * ndv, ACC_SLACK + 1e-9)
 
 
 def test_errors_are_loud():
@@ -484,7 +519,7 @@ def test_tc_engine_matches_ffma_engine_and_is_deterministic(monkeypatch):
     gf, lgf, grf, stf, bf = run([0, 1, 2], "ffma")
     _close(lgt.numpy(), lgf.numpy(), 1e-5, "tc vs ffma logits")
     _close(grt.numpy(), grf.numpy(), 5e-5, "tc vs ffma gradients", scale=float(grf.abs().max()))
-    _close(stt[:, :, 0].numpy(), stf[:, :, 0].numpy(), TRAJ_LOSS, "tc vs ffma epoch loss")
+    _report("tc vs ffma engine epoch loss", _rel_max(stt[:, :, 0].numpy(), stf[:, :, 0].numpy()), TRAJ_LOSS)
     g2, _, _, st2, b2 = run([0, 1, 2], "tc")
     assert torch.equal(stt, st2) and torch.equal(bt, b2) and torch.equal(gt.params, g2.params)
     g1, _, _, st1, b1 = run([1], "tc")
@@ -501,22 +536,198 @@ def test_hashed_orders_same_on_cpu_and_gpu():
     assert sorted(a[2].tolist()) == list(range(1000))
 
 
-def test_device_init_is_placement_independent():
-    """args.init_on_device: a candidate gets the same initial weights and result whatever group / rank it lands in."""
+@pytest.mark.parametrize("init_on_device", [True, False])
+def test_results_do_not_depend_on_placement(monkeypatch, init_on_device):
+    """A candidate's result must not depend on which rank / group trains it: the call is run as one process (world 1), as
+    rank 0 and rank 1 of a 2-rank world and as the three ranks of a 3-rank world (torch.distributed stubbed at the
+    mfas_b200.dist seam: every 'rank' runs the full driver-side code with its own share), and every rank's slots must be
+    BIT-identical to the 1-process run -- accuracies and per-epoch statistics.  Both initialisation modes: the device
+    generator keyed by (seed, candidate) and the reference-compatible host stream (other ranks' draws consumed and dropped)."""
     import mfas_b200.ntu_searchable as ntu
-    args = make_args(64, 32, 1, bn=True)
-    args.init_on_device = True
-    train, dev = synthetic_ntu_cache(128, 5), synthetic_ntu_cache(64, 6)
-    confs = [np.array(FOUND_CONFS[4]), np.array([[0, 0, 0]]), np.array(FOUND_CONFS[1][:2])]
+    from mfas_b200 import dist as mdist
+    args = make_args(64, 32, 2, bn=True)
+    args.init_on_device = init_on_device
+    train, dev = synthetic_ntu_cache(160, 5), synthetic_ntu_cache(96, 6)
+    confs = [np.array(FOUND_CONFS[4]), np.array([[0, 0, 0]]), np.array(FOUND_CONFS[1][:2]), np.array([[2, 3, 1], [1, 1, 0]]),
+             np.array(FOUND_CONFS[2][:3])]
 
-    def run(sel):
+    def run(rank, world):
+        monkeypatch.setattr(mdist, "world", lambda: (rank, world))
+        monkeypatch.setattr(mdist, "gather_results", lambda values, n: values)          # keep this rank's slots only
+        monkeypatch.setattr(mdist, "sync_call_inputs", lambda confs_, seed: (confs_, seed), raising=False)
         loaders = {"train": FeatureCacheLoader(train, 32, True, 1), "dev": FeatureCacheLoader(dev, 32, True, 2)}
         torch.manual_seed(11)
-        return ntu.train_sampled_models([confs[i] for i in sel], ntu.Searchable_Skeleton_Image_Net, loaders, args, torch.device(DEV))
+        accs = ntu.train_sampled_models(confs, ntu.Searchable_Skeleton_Image_Net, loaders, args, torch.device(DEV))
+        return torch.stack(accs), ntu.train_sampled_models.last_stats.clone()
 
-    full = run([0, 1, 2])
-    again = run([0, 1, 2])
-    assert [float(a) for a in full] == [float(a) for a in again]
+    full, full_st = run(0, 1)
+    assert (full > 0).any()
+    again, _ = run(0, 1)
+    assert torch.equal(full, again)
+    for world in (2, 3):
+        seen = torch.zeros(len(confs), dtype=torch.bool)
+        for rank in range(world):
+            part, part_st = run(rank, world)
+            mine = torch.tensor(mdist.shard(len(confs), rank, world))
+            assert torch.equal(part[mine], full[mine]), (world, rank, part, full)
+            assert torch.equal(part_st[mine], full_st[mine]), (world, rank)
+            seen[mine] = True
+        assert seen.all()
+
+
+@pytest.mark.parametrize("H,B,confs,engine", [
+    (128, 64, [FOUND_CONFS[4], FOUND_CONFS[1]], "tc"),           # k_tc_bwd_ws<false> vs <true>, tensor-core head tile included
+    (16, 64, [[[3, 1, 1], [1, 3, 0]], [[0, 0, 1]]], "tc"),      # masked tiles of the search default
+    (256, 128, [[[1, 3, 0], [3, 0, 1]]], "tc"),                 # 128-row batches / inner_repr 256
+    (48, 16, [FOUND_CONFS[0][:2]], "ffma"),
+])
+def test_production_kernels_equal_the_gradient_keeping_instantiation_bitwise(H, B, confs, engine):
+    """The tight step-level checks run with a gradient arena (KEEP_GRAD=true instantiations); production runs without.
+    Both must leave bit-identical parameters, Adam moments and BatchNorm buffers after the same steps."""
+    train = synthetic_ntu_cache(3 * B, 23).to(DEV)
+    inits = init_states(confs, H, 60, True, 0.0, 3)
+    out = []
+    for keep in (True, False):
+        g = _group(confs, H, B, keep_grads=keep)
+        assert g.engine == engine
+        for k in range(len(confs)):
+            g.load_state(k, inits[k])
+        for step in range(3):
+            rows = torch.stack([torch.randperm(3 * B, generator=torch.Generator().manual_seed(10 * step + k))[:B - (step == 2)] for k in range(len(confs))])
+            _, loss, correct = g.train_step(train, rows, lr=1e-3 * (0.5 ** step))
+        g.check()
+        out.append((g.params.clone(), g.adam_m.clone(), g.adam_v.clone(), g.bufs.clone(), g.nbt.clone(), loss.clone(), correct.clone()))
+        assert float(g.adam_m.abs().max()) > 0
+    for a, b, what in zip(out[0], out[1], ("params", "exp_avg", "exp_avg_sq", "BatchNorm buffers", "num_batches_tracked", "loss", "correct")):
+        assert torch.equal(a, b), f"KEEP_GRAD=false differs from KEEP_GRAD=true in {what}"
+
+
+@pytest.mark.parametrize("H,B", [(128, 64), (16, 64), (256, 128)])
+def test_train_run_equals_train_step_driven_with_the_same_scalars_bitwise(H, B):
+    """mfas_train_run (the production epoch loop: per-step step_size[t] / bc2_sqrt[t] arrays, batch offsets into the
+    permutation block, device-side statistics, best-dev snapshot / rollback) against the SAME library driven one
+    mfas_train_step / mfas_eval_pass at a time from Python with the scheduler's scalars, over 4 epochs = two warm restarts
+    of the cosine schedule (Ti=1, Tm=2: after epoch 1 and after epoch 3).  Everything must agree bit for bit: per-epoch
+    statistics, the best epoch, the rolled-back weights and buffers, and the (never rolled back) Adam moments."""
+    import mfas_b200.ntu_searchable as ntu
+    confs = [FOUND_CONFS[4], FOUND_CONFS[2][:2]] if H != 256 else [[[1, 3, 0], [3, 0, 1]], [[0, 1, 1]]]
+    from mfas_b200._lib import MAX_LAYERS as ML
+    E, ntr, ndv = 4, 5 * B, 2 * B + 40            # nbpe integral: the reference's restart test fires only on exact hits (scheduler.py:35-38)
+    steps = math.ceil(ntr / B)
+    train, dev = synthetic_ntu_cache(ntr, 31).to(DEV), synthetic_ntu_cache(ndv, 32).to(DEV)
+    inits = init_states(confs, H, 60, True, 0.0, 4)
+    args = make_args(H, B, E, Ti=1)
+    lrs = ntu.cosine_lrs(args, ntr, E * steps)
+    assert sum(1 for t in range(1, len(lrs)) if lrs[t] > 10 * lrs[t - 1]) == 2, lrs      # two warm restarts inside the run
+    gen = torch.Generator().manual_seed(5)
+    ptr = torch.stack([torch.stack([torch.randperm(ntr, generator=gen) for _ in range(E)]) for _ in confs]).to(DEV, torch.int32)
+    pdv = torch.stack([torch.stack([torch.randperm(ndv, generator=gen) for _ in range(E)]) for _ in confs]).to(DEV, torch.int32)
+
+    g1 = _group(confs, H, B)
+    for k in range(len(confs)):
+        g1.load_state(k, inits[k])
+    stats, best, best_epoch = g1.train_run(train, dev, ptr, pdv, lrs, E, B)
+    g1.check()
+    stats, best, best_epoch = stats.cpu(), best.cpu(), best_epoch.cpu()
+
+    g2 = _group(confs, H, B)
+    for k in range(len(confs)):
+        g2.load_state(k, inits[k])
+    n = len(confs)
+    snap_p, snap_b, snap_n = g2.params.clone(), g2.bufs.clone(), g2.nbt.clone()      # best_model_sd = deepcopy(state_dict), ntu.py:17
+    best2, be2 = torch.zeros(n, dtype=torch.float64), -torch.ones(n, dtype=torch.int32)
+    st2 = torch.zeros(n, E, 4, dtype=torch.float64)
+    t = 0
+    for e in range(E):
+        for s_ in range(steps):
+            rows = ptr[:, e, s_ * B:(s_ + 1) * B]
+            _, loss, correct = g2.train_step(train, rows, lr=lrs[t])
+            t += 1
+            st2[:, e, 0] += loss.cpu().double() * rows.shape[1]                         # running_loss += loss.item() * B, ntu.py:72
+            st2[:, e, 1] += correct.cpu().double()
+        ev = g2.eval_pass(dev, B, pdv[:, e]).cpu()
+        st2[:, e, 2:] = ev
+        acc = ev[:, 1] / ndv
+        for k in range(n):
+            if acc[k] > best2[k]:                                                       # strict '>', ntu.py:82
+                best2[k], be2[k] = acc[k], e
+                sl_p = slice(int(g2.p_off[k]), int(g2.p_off[k + 1]))
+                sl_b = slice(int(g2.b_off[k]), int(g2.b_off[k + 1]))
+                snap_p[sl_p] = g2.params[sl_p]; snap_b[sl_b] = g2.bufs[sl_b]
+                snap_n[k * ML:(k + 1) * ML] = g2.nbt[k * ML:(k + 1) * ML]
+    g2.check()
+    assert torch.equal(stats, st2), (stats - st2).abs().max()
+    assert torch.equal(best, best2) and torch.equal(best_epoch, be2)
+    assert torch.equal(g1.params, snap_p), "rolled-back parameters"
+    assert torch.equal(g1.bufs, snap_b) and torch.equal(g1.nbt, snap_n), "rolled-back BatchNorm buffers"
+    assert torch.equal(g1.adam_m, g2.adam_m) and torch.equal(g1.adam_v, g2.adam_v), "Adam moments after the last step"
+    assert len(set(best_epoch.tolist())) >= 1 and float(best.max()) > 0
+
+
+def test_weightsharing_vs_reference_fixture(capsys):
+    """args.weightsharing=True: candidates chained through the shared dict (get / set_central_states,
+    /root/reference/models/search/ntu_searchable.py:74-75,91-92,123-174) against what the unmodified reference produced
+    (tests/golden/wsh.npz): per-candidate statistics, accuracies, final weights, the dict's keys and contents, the log lines."""
+    import mfas_b200.ntu_searchable as ntu
+    from helpers import WS_CASES
+    name, cs = "wsh", WS_CASES["wsh"]
+    gold = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    args = make_args(cs["H"], cs["B"], cs["epochs"], bn=cs["bn"], drpt=cs["drpt"], Ti=cs["Ti"], checkpointdir="/nonexistent", weightsharing=True)
+    train, dev = synthetic_ntu_cache(cs["n_train"], cs["data_seed"]), synthetic_ntu_cache(cs["n_dev"], cs["data_seed"] + 1)
+    seed = int(gold["meta/loader_seed"])
+    loaders = {"train": FeatureCacheLoader(train, cs["B"], True, seed), "dev": FeatureCacheLoader(dev, cs["B"], True, seed + 50000)}
+    confs = [np.array(c) for c in cs["confs"]]
+    shared = {}
+    torch.manual_seed(cs["model_seed"])
+    accs, models = ntu.train_sampled_models(confs, ntu.Searchable_Skeleton_Image_Net, loaders, args, torch.device(DEV),
+                                            return_model=list(range(len(confs))), state_dict=shared)
+    stats = ntu.train_sampled_models.last_stats.numpy()
+    log = capsys.readouterr().out
+    assert sorted(shared.keys()) == list(gold["meta/shared_keys"])
+    assert log.count("Loaded shared weight with ID: 0.L_1536_32.A_sigmoid") == 2 and "Updating shared weight with ID: 1.L_3104_32.A_relu" in log
+    B = cs["B"]
+    wtr = np.minimum(B, cs["n_train"] - B * np.arange(-(-cs["n_train"] // B)))
+    wdv = np.minimum(B, cs["n_dev"] - B * np.arange(-(-cs["n_dev"] // B)))
+    for ci in range(len(confs)):
+        _report(f"wsh c{ci} epoch train loss vs reference fixture", _rel_max(stats[ci, :, 0], (gold[f"c{ci}/train_loss"] * wtr).sum(1)), _loss_tol(name, ci, "train_loss_rel"))
+        _report(f"wsh c{ci} epoch dev loss vs reference fixture", _rel_max(stats[ci, :, 2], (gold[f"c{ci}/dev_loss"] * wdv).sum(1)), _loss_tol(name, ci, "dev_loss_rel"))
+        _report(f"wsh c{ci} dev correct counts", float(np.abs(stats[ci, :, 3] - gold[f"c{ci}/dev_correct"].sum(1)).max()), ACC_SLACK)
+        _report(f"wsh c{ci} best dev accuracy (samples)", abs(float(accs[ci]) - float(gold[f"c{ci}/best_acc"])) * cs["n_dev"], ACC_SLACK + 1e-9)
+        for k, v in models[ci].state_dict().items():
+            if k.startswith("alphas"):
+                continue
+            if k.endswith("num_batches_tracked"):
+                assert int(v) == int(gold[f"c{ci}/final/{k}/sample"][0]), (ci, k)          # the counter is shared with the layer (BatchNorm buffer)
+                continue
+            vec = k.endswith(".bias") or "running" in k
+            _report(f"wsh c{ci} final {k}", _rel_l2(sample_tensor(v.cpu().numpy())["sample"], gold[f"c{ci}/final/{k}/sample"]), TRAJ_V if vec else TRAJ_W)
+    for key, sd in shared.items():
+        for k, v in sd.items():
+            if k.endswith("num_batches_tracked"):
+                assert int(v) == int(gold[f"shared/{key}/{k}/sample"][0]), (key, k)
+            elif k.endswith("weight"):
+                _report(f"wsh shared['{key}']['{k}']", _rel_l2(sample_tensor(v.cpu().numpy())["sample"], gold[f"shared/{key}/{k}/sample"]), TRAJ_W)
+
+
+@pytest.mark.parametrize("H,B,L", [(64, 128, 5), (128, 128, 6), (256, 128, 6), (128, 64, 5), (16, 64, 6)])
+def test_depth_sweep_shapes_step_vs_oracle(H, B, L):
+    """BASELINE configs[4]: fusion depth 5 and 6 (rows conf4[l mod 4]), inner_repr 64 / 128 / 256, 128-row batches: one
+    optimiser step, every gradient at 1e-4 against the oracle and its float64 ground truth."""
+    conf = [FOUND_CONFS[4][l % 4] for l in range(L)]
+    train = synthetic_ntu_cache(160, 52)
+    init = init_states([conf], H, 60, True, 0.0, 10)[0]
+    g = _group([conf], H, B, keep_grads=True)
+    assert g.engine == "tc"
+    g.load_state(0, init)
+    rows = torch.randperm(160, generator=torch.Generator().manual_seed(2))[:B]
+    head = O.FusionHead(conf, H, 60, init)
+    before = dict(state={k: v.copy() for k, v in head.state.items()}, adam={})
+    sk, rg, y = O._taps_of(split_np(train), rows.numpy())
+    ol, oloss, ograds = head.train_step(sk, rg, y, 1e-3)
+    logits, loss, _ = g.train_step(train.to(DEV), rows, lr=1e-3)
+    g.check()
+    assert abs(float(loss[0]) - float(oloss)) < TOL * float(oloss)
+    _check_step(g, 0, before, head, ograds, logits[0].cpu().numpy(), ol, 1e-3, 1, f"depth L={L} H={H} B={B}", batch=(sk, rg, y))
 
 
 def test_found_flow_multitask_alphas_vs_reference_fixture(capsys):
@@ -550,16 +761,24 @@ def test_found_flow_multitask_alphas_vs_reference_fixture(capsys):
     test_acc = tr.test_ntu_track_acc(rmode, loaders, sizes, device=dev, multitask=True)
     rows = re.findall(r"(train|dev) Loss: ([0-9.]+) Acc: ([0-9.]+)", capsys.readouterr().out)
     assert [r[0] for r in rows] == list(gold["epoch_phase"])
-    assert np.abs(np.array([float(r[1]) for r in rows]) - gold["epoch_loss"]).max() < 5e-3
-    assert np.abs(np.array([float(r[2]) for r in rows]) - gold["epoch_acc"]).max() <= 2.0 / cs["n_dev"]
-    assert abs(float(interm) - float(gold["interm_acc"])) <= 2.0 / cs["n_dev"]
-    assert abs(float(final) - float(gold["final_acc"])) <= 2.0 / cs["n_dev"]
-    assert abs(float(test_acc) - float(gold["test_acc"])) <= 2.0 / cs["n_test"]
+    # the reference prints 4 decimals: half a unit of the last printed digit on both sides + the loss bound itself
+    _report("found_mt printed epoch losses (absolute)", float(np.abs(np.array([float(r[1]) for r in rows]) - gold["epoch_loss"]).max()),
+            1.01e-4 + TRAJ_LOSS * float(gold["epoch_loss"].max()))
+    sizes_of = np.array([cs["n_train"] if r[0] == "train" else cs["n_dev"] for r in rows], np.float64)
+    _report("found_mt printed epoch accuracies (samples; 4 printed decimals)",
+            float((np.abs(np.array([float(r[2]) for r in rows]) - gold["epoch_acc"]) * sizes_of).max()), ACC_SLACK + 1.01e-4 * cs["n_train"])
+    _report("found_mt stage-1 accuracy (samples)", abs(float(interm) - float(gold["interm_acc"])) * cs["n_dev"], ACC_SLACK + 1e-9)
+    _report("found_mt final accuracy (samples)", abs(float(final) - float(gold["final_acc"])) * cs["n_dev"], ACC_SLACK + 1e-9)
+    _report("found_mt test accuracy (samples)", abs(float(test_acc) - float(gold["test_acc"])) * cs["n_test"], ACC_SLACK + 1e-9)
     assert test_acc.dtype == torch.float64
     for k, v in rmode.state_dict().items():
-        if k.endswith("num_batches_tracked") or k.endswith(".bias") or "running" in k:
+        if k.endswith("num_batches_tracked"):
             continue
-        assert _rel_l2(sample_tensor(v.cpu().numpy())["sample"], gold[f"final/{k}/sample"]) < TRAJ_W, k
+        if k.startswith("alphas"):
+            _report(f"found_mt final {k} (absolute)", abs(float(v) - float(gold[f"final/{k}/sample"][0])), 1e-4)
+            continue
+        vec = k.endswith(".bias") or "running" in k
+        _report(f"found_mt final {k}", _rel_l2(sample_tensor(v.cpu().numpy())["sample"], gold[f"final/{k}/sample"]), TRAJ_V if vec else TRAJ_W)
     # forward() returns the 3-tuple of the reference (ntu_searchable.py:244-247)
     b = next(iter(loaders["test"]))
     out = rmode((b["rgb"].to(dev), b["ske"].to(dev)))
@@ -634,7 +853,7 @@ def test_wide_eval_and_small_inner_repr_agree_with_the_plain_paths(monkeypatch):
         res[engine] = (lg.cpu(), grads, st.cpu(), best.cpu())
     _close(res["tc"][0].numpy(), res["ffma"][0].numpy(), 1e-5, "inner_repr 16: tc vs ffma logits")
     _close(res["tc"][1].numpy(), res["ffma"][1].numpy(), 5e-5, "inner_repr 16: tc vs ffma gradients", scale=float(res["ffma"][1].abs().max()))
-    _close(res["tc"][2][:, :, 0].numpy(), res["ffma"][2][:, :, 0].numpy(), TRAJ_LOSS, "inner_repr 16: tc vs ffma epoch loss")
+    _report("inner_repr 16: tc vs ffma engine epoch loss", _rel_max(res["tc"][2][:, :, 0].numpy(), res["ffma"][2][:, :, 0].numpy()), TRAJ_LOSS)
 
 
 @pytest.mark.gpu
