@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MFAS_ABI_VERSION 2
+#define MFAS_ABI_VERSION 3
 
 #define MFAS_MAX_LAYERS 8     /* fusion steps per candidate (reference max_fusions default 4)   */
 #define MFAS_MAX_BATCH 128    /* rows per batch (BASELINE configs use 8, 64, 128)               */
@@ -125,6 +125,9 @@ typedef struct mfas_run_args {       /* one train_ntu_track_acc run for every ca
                                       * (MFAS_FLAG_MULTILABEL: "correct" is the sum of per-sample F1 scores) */
   double* best_acc;                  /* device [n_cand] best dev accuracy (strict >, starts at 0); MULTILABEL: best dev F1-samples */
   int32_t* best_epoch;               /* device [n_cand] epoch of best_acc or -1 */
+  const double* best_acc_init;       /* HOST [n_cand] or NULL (= 0): the value best_acc starts from -- init_f1 of train_mmimdb_track_f1
+                                      * (train_searchable/mmimdb.py:15,21): an epoch is snapshotted only when it beats it (strict >; a NaN
+                                      * is never beaten, so the run ends on the incoming weights) */
 } mfas_run_args;
 
 typedef struct mfas_group* mfas_group_t;

@@ -17,7 +17,7 @@ SOURCES = [os.path.join(HERE, "csrc", "mfas_abi.cu"), os.path.join(HERE, "csrc",
 HEADERS = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "kernels_ffma.cuh", "kernels_tc.cuh", "kernels_pool.cuh", "umma.cuh")] + [
     os.path.join(ROOT, "include", "mfas_b200.h")]
 
-ABI_VERSION = 2          # MFAS_ABI_VERSION of include/mfas_b200.h
+ABI_VERSION = 3          # MFAS_ABI_VERSION of include/mfas_b200.h
 MAX_LAYERS, MAX_BATCH, MAX_HIDDEN, MAX_CLASSES, NUM_TAPS = 8, 128, 256, 64, 4
 FLAG_BN, FLAG_DROPOUT, FLAG_ALPHAS, FLAG_MULTITASK, FLAG_MULTILABEL = 1, 2, 4, 8, 16
 ERRORS = {0: "MFAS_OK", -1: "MFAS_ERR_INVALID", -2: "MFAS_ERR_CUDA", -3: "MFAS_ERR_UNSUPPORTED",
@@ -66,7 +66,8 @@ class RunArgs(C.Structure):
     _fields_ = [("n_epochs", C.c_int32), ("batch", C.c_int32),
                 ("perm_train", C.c_void_p), ("perm_dev", C.c_void_p),
                 ("step_size", C.c_void_p), ("bc2_sqrt", C.c_void_p),
-                ("adam_t0", C.c_int64), ("stats", C.c_void_p), ("best_acc", C.c_void_p), ("best_epoch", C.c_void_p)]
+                ("adam_t0", C.c_int64), ("stats", C.c_void_p), ("best_acc", C.c_void_p), ("best_epoch", C.c_void_p),
+                ("best_acc_init", C.c_void_p)]
 
 
 # every symbol include/mfas_b200.h declares: name -> (restype, argtypes)

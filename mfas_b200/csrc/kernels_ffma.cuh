@@ -630,12 +630,14 @@ k_fusion_bwd(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int 
       }
     }
   }
-  if (cd.flags & MFAS_FLAG_ALPHAS) {     // fixed-order reduction -> one partial per CTA; k_alpha_step finishes the sum
+  if (gated) {     // (CTA-uniform) fixed-order reduction -> one partial per feature-column CTA; k_alpha_step finishes the sum.
+    // Only the feature-column CTAs own a slot: blockIdx.x < (d_ske + d_rgb) / BWD_KT <= MFAS_DSP_SLOTS (mfas_group_create
+    // rejects alpha groups with wider taps); the hidden-column CTAs write nothing.
     __shared__ float dsw[8];
     dsum = warp_sum(dsum);
     if (lane == 0) dsw[warp] = dsum;
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && (int)blockIdx.x < MFAS_DSP_SLOTS) {
       float t = 0.f;
       for (int w = 0; w < 8; ++w) t += dsw[w];
       cd.dsp[layer * MFAS_DSP_SLOTS + blockIdx.x] = gsign * t;

@@ -431,6 +431,14 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       return code;
     }
     g->any_alphas = g->any_alphas || (g->lay[c].flags & MFAS_FLAG_ALPHAS);
+    if (g->lay[c].flags & MFAS_FLAG_ALPHAS)               // one d(sigmoid(alpha)) partial per 32 feature columns (DCand::dsp)
+      for (int l = 0; l < g->lay[c].L; ++l)
+        if ((g->lay[c].d_ske[l] + g->lay[c].d_rgb[l] + BWD_KT - 1) / BWD_KT > MFAS_DSP_SLOTS) {
+          int code = fail(MFAS_ERR_UNSUPPORTED, "alpha gates: the taps of candidate %d step %d are %d + %d columns wide, more than the %d the gate-gradient partials cover",
+                          c, l, g->lay[c].d_ske[l], g->lay[c].d_rgb[l], MFAS_DSP_SLOTS * BWD_KT);
+          mfas_group_destroy(g);
+          return code;
+        }
     // the multi-label (MM-IMDB) head lives in k_head: per-layer chain kernels (no fused chain, no tensor-core head), which
     // have no row / column masks for inner_repr 16 / 32
     tc_ok = tc_ok && (!(g->lay[c].flags & MFAS_FLAG_MULTILABEL) || g->lay[c].H % 64 == 0);
@@ -939,7 +947,10 @@ extern "C" int mfas_train_run(mfas_group_t g, const mfas_cache_desc* train, cons
 
   const int E = a->n_epochs;
   CUDA_TRY(cudaMemsetAsync(a->stats, 0, sizeof(double) * 4 * (size_t)E * g->n_cand, st));
-  CUDA_TRY(cudaMemsetAsync(a->best_acc, 0, sizeof(double) * g->n_cand, st));
+  if (a->best_acc_init)   // pageable source: staged before the call returns
+    CUDA_TRY(cudaMemcpyAsync(a->best_acc, a->best_acc_init, sizeof(double) * g->n_cand, cudaMemcpyHostToDevice, st));
+  else
+    CUDA_TRY(cudaMemsetAsync(a->best_acc, 0, sizeof(double) * g->n_cand, st));
   CUDA_TRY(cudaMemsetAsync(a->best_epoch, 0xFF, sizeof(int32_t) * g->n_cand, st));
   if ((rc = snapshot(g, 1, 0, st))) return rc;            // best_model_sd = deepcopy(state_dict)  (ntu.py:17)
   const long long stat_stride = 4LL * E;

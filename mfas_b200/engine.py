@@ -271,9 +271,10 @@ class CandidateGroup(GroupLayout):
         return logits[:, :n], loss, correct
 
     # ---- the production path ---------------------------------------------------------------------
-    def train_run(self, train_cache, dev_cache, perm_train, perm_dev, lrs, epochs, batch, beta1=0.9, beta2=0.999):
+    def train_run(self, train_cache, dev_cache, perm_train, perm_dev, lrs, epochs, batch, beta1=0.9, beta2=0.999, best_init=None):
         """epochs x (train pass + dev pass) for all candidates; returns device tensors
-        (stats [n, epochs, 4] f64, best_acc [n] f64, best_epoch [n] i32) without synchronising."""
+        (stats [n, epochs, 4] f64, best_acc [n] f64, best_epoch [n] i32) without synchronising.
+        ``best_init``: per-candidate value the best-dev tracking starts from (default 0; init_f1 of the MM-IMDB loop)."""
         n_tr, n_dv = len(train_cache), len(dev_cache)
         steps = math.ceil(n_tr / batch)
         assert len(lrs) == epochs * steps, (len(lrs), epochs, steps)
@@ -293,6 +294,10 @@ class CandidateGroup(GroupLayout):
         a.step_size, a.bc2_sqrt = ss.ctypes.data, b2.ctypes.data
         a.adam_t0 = self.adam_t
         a.stats, a.best_acc, a.best_epoch = stats.data_ptr(), best_acc.data_ptr(), best_epoch.data_ptr()
+        a.best_acc_init = None
+        if best_init is not None:
+            bi = np.ascontiguousarray(np.broadcast_to(np.asarray(best_init, dtype=np.float64), (self.n,)))
+            a.best_acc_init = bi.ctypes.data
         dtr, ddv = cache_desc(train_cache), cache_desc(dev_cache)
         _lib.check(_lib.lib().mfas_train_run(self._h, C.byref(dtr), C.byref(ddv), C.byref(a), self._stream()))
         self.adam_t += epochs * steps

@@ -47,10 +47,56 @@ def _self_check() -> int:
             got, got2 = torch.empty(3001, dtype=torch.float32), torch.empty(777, dtype=torch.float32)
             ok = _fill(st, [got.data_ptr(), got2.data_ptr()], [3001, 777], [-bound, -0.3], [bound, 0.3], fma)
             if ok and torch.equal(got, want) and torch.equal(got2, want2) and torch.equal(st, after):
-                return fma
+                return fma if _normal_path_matches(saved, fma) else -1
         return -1
     finally:
         torch.set_rng_state(saved)
+
+
+_OFF_CACHED, _OFF_VALID, _STATE_BYTES = 5024, 5040, 5056      # at::mt19937 state as torch serialises it (cached normal sample, its flag)
+
+
+def _box_muller(raw4):
+    """at::normal_distribution<double> on four generator words: (cos branch = the sample, sin branch = cached for the next draw)."""
+    r1, r2, r3, r4 = (int(x) for x in raw4)
+    u1 = (((r1 << 32) | r2) & ((1 << 53) - 1)) * (1.0 / (1 << 53))
+    u2 = (((r3 << 32) | r4) & ((1 << 53) - 1)) * (1.0 / (1 << 53))
+    r = math.sqrt(-2.0 * math.log1p(-u2))
+    theta = 2.0 * math.pi * u1
+    return r * math.cos(theta), r * math.sin(theta)
+
+
+def _normal_path_matches(saved: torch.Tensor, fma: int) -> bool:
+    """The scalar-normal emulation (raw words + Box-Muller + the cached-sample fields patched at fixed byte offsets of the
+    serialised generator state) against torch itself: 3 then 2 scalar ``normal_`` draws -- odd and even counts, so the
+    cache flag is exercised both ways -- must give the same values AND the same final generator state.  A torch build
+    with another state layout fails here and the whole helper is disabled (torch's own initialisers are used instead)."""
+    if saved.numel() != _STATE_BYTES:
+        return False
+    for n_draws in (3, 2):
+        torch.set_rng_state(saved.clone())
+        want = [float(torch.zeros(1, dtype=torch.float32).normal_(0.0, 0.1)) for _ in range(n_draws)]
+        after = torch.get_rng_state()
+        st = saved.clone()
+        sbuf = st.numpy()
+        valid = bool(struct.unpack_from("i", sbuf, _OFF_VALID)[0])
+        cached = struct.unpack_from("d", sbuf, _OFF_CACHED)[0]
+        got = []
+        for _ in range(n_draws):
+            if valid:
+                z, valid = cached, False
+            else:
+                raw = np.zeros(4, dtype=np.uint32)
+                if not _fill(st, [raw.ctypes.data], [-4], [0.0], [0.0], fma):
+                    return False
+                z, cached = _box_muller(raw)
+                valid = True
+            got.append(float(torch.zeros(1, dtype=torch.float32).fill_(z * 0.1 + 0.0)))
+        struct.pack_into("d", sbuf, _OFF_CACHED, cached if valid else 0.0)
+        struct.pack_into("i", sbuf, _OFF_VALID, 1 if valid else 0)
+        if got != want or not torch.equal(st, after):
+            return False
+    return True
 
 
 def kaiming_bound(fan_in: int) -> float:
@@ -102,8 +148,8 @@ def init_host_arenas_fast(group, host_p, host_b, visit, slots=None) -> bool:
     # fetched raw inside the same bulk fill and turned into samples afterwards, so one C call (and its thread pipeline)
     # covers every candidate of the slice.
     sbuf = state.numpy()
-    cache_valid = bool(struct.unpack_from("i", sbuf, 5040)[0])
-    cached = struct.unpack_from("d", sbuf, 5024)[0]
+    cache_valid = bool(struct.unpack_from("i", sbuf, _OFF_VALID)[0])
+    cached = struct.unpack_from("d", sbuf, _OFF_CACHED)[0]
     raw = np.zeros(4 * max(1, sum(int(group.layouts[c].L) for c in slot_list)), dtype=np.uint32)
     n_raw = 0
     normals = []                      # (tensor view, offset into raw or None when the cached sample serves it)
@@ -121,13 +167,7 @@ def init_host_arenas_fast(group, host_p, host_b, visit, slots=None) -> bool:
             if off is None:
                 z = cached
             else:
-                r1, r2, r3, r4 = (int(x) for x in raw[off:off + 4])
-                u1 = (((r1 << 32) | r2) & ((1 << 53) - 1)) * (1.0 / (1 << 53))
-                u2 = (((r3 << 32) | r4) & ((1 << 53) - 1)) * (1.0 / (1 << 53))
-                r = math.sqrt(-2.0 * math.log1p(-u2))
-                theta = 2.0 * math.pi * u1
-                cached = r * math.sin(theta)
-                z = r * math.cos(theta)
+                z, cached = _box_muller(raw[off:off + 4])
             t.fill_(z * 0.1 + 0.0)
         normals.clear()
 
@@ -160,17 +200,17 @@ def init_host_arenas_fast(group, host_p, host_b, visit, slots=None) -> bool:
                 t = (host_b if is_b else host_p)[o:o + n]
                 flush()
                 finish_normals()
-                struct.pack_into("d", sbuf, 5024, cached if cache_valid else 0.0)
-                struct.pack_into("i", sbuf, 5040, 1 if cache_valid else 0)
+                struct.pack_into("d", sbuf, _OFF_CACHED, cached if cache_valid else 0.0)
+                struct.pack_into("i", sbuf, _OFF_VALID, 1 if cache_valid else 0)
                 torch.set_rng_state(state)
                 nn.init.normal_(t.view(shape), 0.0, 0.1)
                 state = torch.get_rng_state()
                 sbuf = state.numpy()
-                cache_valid = bool(struct.unpack_from("i", sbuf, 5040)[0])
-                cached = struct.unpack_from("d", sbuf, 5024)[0]
+                cache_valid = bool(struct.unpack_from("i", sbuf, _OFF_VALID)[0])
+                cached = struct.unpack_from("d", sbuf, _OFF_CACHED)[0]
     flush()
     finish_normals()
-    struct.pack_into("d", sbuf, 5024, cached if cache_valid else 0.0)
-    struct.pack_into("i", sbuf, 5040, 1 if cache_valid else 0)
+    struct.pack_into("d", sbuf, _OFF_CACHED, cached if cache_valid else 0.0)
+    struct.pack_into("i", sbuf, _OFF_VALID, 1 if cache_valid else 0)
     torch.set_rng_state(state)
     return True

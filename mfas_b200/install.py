@@ -18,8 +18,11 @@ def install(shim_broken_imports: bool = True):
     if shim_broken_imports:
         # the reference as shipped does not import: matplotlib is an unused import of
         # models/utils.py:61, `models.aux` / `models.train` are dangling names in loops we never call
-        for n in ("matplotlib", "matplotlib.pyplot"):
-            sys.modules.setdefault(n, types.ModuleType(n))
+        try:                                       # a real matplotlib wins: the stub is only for boxes that have none
+            importlib.import_module("matplotlib.pyplot")
+        except ImportError:
+            for n in ("matplotlib", "matplotlib.pyplot"):
+                sys.modules.setdefault(n, types.ModuleType(n))
         try:
             ref_sched = importlib.import_module("models.auxiliary.scheduler")   # the reference's own class is fine:
         except ImportError:                                                       # train_ntu duck-types it

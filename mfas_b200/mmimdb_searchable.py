@@ -164,13 +164,14 @@ def _multilabel_cache_of(loader, what):
     return c
 
 
-def _final_f1(stats_c, best, init_f1, n_dev):
-    """Host-side epilogue of train_mmimdb_track_f1 for one candidate.  stats_c: [E, 4] (train loss sum, train F1 sum,
-    dev loss sum, dev F1 sum).  The device loop tracks the strict-'>' best dev F1 from 0; a NaN train loss makes the
-    reference return the best F1 seen BEFORE that epoch (:105-109) -- after a NaN every later dev F1 is 0 (sigmoid(nan) >
-    0.3 is False), so the device-side best is already that value.  ``init_f1`` only raises the floor."""
+def _final_f1(best):
+    """Host-side epilogue of train_mmimdb_track_f1 for one candidate (train_searchable/mmimdb.py:131-136).  The device loop
+    tracks the strict-'>' best dev F1 starting from init_f1 (mfas_run_args.best_acc_init) and snapshots only epochs that beat
+    it, so the rolled-back weights and the returned score always belong together; a NaN train loss makes the reference return
+    the best F1 seen BEFORE that epoch (:105-109) -- after a NaN every later dev F1 is 0 (sigmoid(nan) > 0.3 is False), so the
+    device-side best is already that value.  A NaN best (only possible through a NaN init_f1) is reported as 0.0 (:133-134)."""
     b = float(best)
-    return b if b > float(init_f1) else float(init_f1)
+    return 0.0 if b != b else b
 
 
 def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
@@ -239,12 +240,12 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
             torch.zeros(len(js), 0, n_train, dtype=torch.int32, device=device)
         pdv = torch.stack([pass_orders(dataloaders['dev'], first_dv + j * E, E, n_dev, device) for j in js]) if E else \
             torch.zeros(len(js), 0, n_dev, dtype=torch.int32, device=device)
-        stats, best, _ = g.train_run(train_dev, dev_dev, ptr, pdv, lrs, E, B)
+        stats, best, _ = g.train_run(train_dev, dev_dev, ptr, pdv, lrs, E, B, best_init=[init_f1[todo[j]] for j in js])
         stats, best = stats.cpu(), best.cpu()
         g.check()
         train_sampled_models.last_engine = g.engine
         for k, j in enumerate(js):
-            f1s[j] = _final_f1(stats[k], best[k], init_f1[todo[j]], n_dev)
+            f1s[j] = _final_f1(best[k])
             all_stats[j] = stats[k]
             if getattr(args, "verbose", False):
                 print('Now training: ')
@@ -263,6 +264,12 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
             run([j])
     elif mine:
         run(mine)
+    elif direct and todo:
+        # nothing to train on this rank: consume the constructor's draws all the same, so the CPU generators of the ranks
+        # stay in lockstep for the next call
+        full = GroupLayout(confs_of(range(len(todo))), args.inner_representation_size, args.num_outputs, flags, widths=WIDTHS)
+        hp, hb = _staging(int(full.p_off[-1]), int(full.b_off[-1]))
+        init_host_arenas(full, hp, hb)
     f1s = mdist.gather_results(f1s, len(todo))
     out = [f1s[j].clone() for j in range(len(todo))]
     train_sampled_models.last_stats = all_stats
@@ -306,6 +313,12 @@ def train_mmimdb_track_f1(model, criterion, optimizer, scheduler, dataloaders, d
             g.view(slot, name, "m").zero_()
             g.view(slot, name, "v").zero_()
     g.adam_t = t0
+    # a NaN init_f1 is never beaten; with num_epochs == 1 the reference then trains one more epoch before giving up (:22-24,
+    # :123-129: 'Recording a NaN F1, training for one more epoch.') and ends on the incoming weights with a score of 0.0
+    nan_init = float(init_f1) != float(init_f1)
+    if nan_init and num_epochs == 1:
+        print('Recording a NaN F1, training for one more epoch.')
+        num_epochs = 2
     lrs = []
     for _ in range(num_epochs):
         if not is_per_batch_cosine(scheduler):
@@ -320,7 +333,7 @@ def train_mmimdb_track_f1(model, criterion, optimizer, scheduler, dataloaders, d
     k_dv = _reserve_passes(dataloaders['dev'], num_epochs)
     ptr = pass_orders(dataloaders['train'], k_tr, num_epochs, n_train)[None]
     pdv = pass_orders(dataloaders['dev'], k_dv, num_epochs, n_dev)[None]
-    stats, best, _ = g.train_run(train_c, dev_c, ptr, pdv, lrs, num_epochs, B, b1, b2)
+    stats, best, _ = g.train_run(train_c, dev_c, ptr, pdv, lrs, num_epochs, B, b1, b2, best_init=[float(init_f1)])
     stats, best = stats.cpu(), best.cpu()
     g.check()
     if verbose:
@@ -335,4 +348,4 @@ def train_mmimdb_track_f1(model, criterion, optimizer, scheduler, dataloaders, d
                                   "exp_avg_sq": g.view(slot, name, "v").clone().reshape(p.shape)}
     model.train(False)
     train_mmimdb_track_f1.last_stats = stats[0]
-    return _final_f1(stats[0], best[0], init_f1, n_dev)
+    return _final_f1(best[0])

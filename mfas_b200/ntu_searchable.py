@@ -388,6 +388,31 @@ def cosine_lrs(args, n_train, n_steps):
     return [sched.step() for _ in range(n_steps)]
 
 
+def fanout_devices(args, device):
+    """CUDA devices a single-process ``train_sampled_models`` call spreads its candidates over.  Default: just ``device``.
+    ``args.fanout_gpus`` (or MFAS_FANOUT_GPUS in the environment) = N, "all" or a list of device indices turns the fan-out
+    on: the reference's driver is ONE unseeded process (models/searchable.py:48-137, models/search/tools.py:53), so this is
+    the mode in which an unmodified ``main_searchable_ntu.py`` uses the 8 GPUs of a box -- no torchrun, no collective: one
+    candidate group per device, enqueued from one host thread per device, results gathered by D2H copies."""
+    spec = getattr(args, "fanout_gpus", None)
+    if spec is None:
+        spec = os.environ.get("MFAS_FANOUT_GPUS")
+    if spec is None or spec in (0, 1, "", "0", "1"):
+        return [device]
+    n = torch.cuda.device_count()
+    if isinstance(spec, (list, tuple)):
+        ids = [int(i) for i in spec]
+    elif str(spec) == "all":
+        ids = list(range(n))
+    else:
+        ids = list(range(min(int(spec), n)))
+    first = device.index if device.index is not None else torch.cuda.current_device()
+    ids = [first] + [i for i in ids if i != first]
+    if any(i < 0 or i >= n for i in ids):
+        raise ValueError(f"fanout_gpus={spec!r}: this process sees {n} CUDA device(s)")
+    return [torch.device("cuda", i) for i in ids]
+
+
 def _print_epoch_logs(stats, n_train, n_dev):
     for e in range(stats.shape[0]):           # same lines as train_searchable/ntu.py:78-79
         print('{} Loss: {:.4f} Acc: {:.4f}'.format('train', stats[e, 0] / n_train, stats[e, 1] / n_train))
@@ -436,7 +461,12 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
     # is the searchable_type no nn.Module is built at all -- parameters are initialised straight into the arenas.
     direct = (searchable_type is Searchable_Skeleton_Image_Net and not premodels and not return_model
               and not args.weightsharing)
-    dev_init = bool(getattr(args, "init_on_device", world > 1)) and direct
+    devices = fanout_devices(args, device) if (direct and world == 1) else [device]
+    dev_init = bool(getattr(args, "init_on_device", world > 1 or len(devices) > 1)) and direct
+    base_seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if dev_init else 0      # torch.manual_seed governs it
+    if world > 1:
+        # one process per GPU (torchrun): every rank trains rank 0's list with rank 0's seed, whatever its own driver sampled
+        sampled_configurations, base_seed = mdist.sync_call_inputs(sampled_configurations, base_seed)
     models = {}
     if not direct:
         # every candidate is constructed here, in order, exactly like the reference does (RNG parity)
@@ -466,20 +496,43 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
     # with return_model every rank needs every trained model: no sharding then
     mine = mdist.my_share(len(todo)) if not (args.weightsharing or return_model) else list(range(len(todo)))
     lap("setup")
-    train_dev = train_host.to(device)
-    dev_dev = dev_host.to(device)
+    if world > 1 and getattr(args, "broadcast_cache", True):
+        # rank 0's split crosses PCIe once and NVLink once (NCCL broadcast); the copy is kept with the host cache, so later
+        # calls over the same loaders reuse it.  Every rank walks the same sequence of calls, so the collective stays matched.
+        def resident(host):
+            key = f"{device}|broadcast"
+            if key not in host._device_copies:
+                host._device_copies[key] = mdist.broadcast_cache(host if rank == 0 else None, device)
+            return host._device_copies[key]
+        train_dev, dev_dev = resident(train_host), resident(dev_host)
+    else:
+        train_dev = train_host.to(device)
+        dev_dev = dev_host.to(device)
     lap("feature cache H2D")
     accs = torch.zeros(len(todo), dtype=torch.float64)
     all_stats = torch.zeros(len(todo), max(E, 1), 4, dtype=torch.float64)
-    base_seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if dev_init else 0      # torch.manual_seed governs it
 
-    def make_group(js):
+    def make_group(js, device=device):
         confs = [np.asarray(sampled_configurations[todo[j]]).reshape(-1, 3) for j in js]
         g = CandidateGroup(confs, args.inner_representation_size, args.num_outputs, flags, device, batch_max=B,
                            drop_p=drop_p, drop_seed=int(getattr(args, "dropout_seed", 0)),
                            cand_ids=[todo[j] for j in js], vid_len_ske=args.vid_len[1])
         g.set_adam(0.9, 0.999, 1e-8, 1e-4)                                   # op.Adam(..., weight_decay=1e-4), :65
         return g
+
+    def orders_for(js, loader, first, n_rows, device):
+        if E == 0:
+            return torch.zeros(len(js), 0, n_rows, dtype=torch.int32, device=device)
+        if js == list(range(js[0], js[0] + len(js))):                   # contiguous share: one batched sort
+            return pass_orders(loader, first + js[0] * E, len(js) * E, n_rows, device).view(len(js), E, n_rows)
+        if hasattr(loader, "orders_of"):                                # round-robin share: one batched sort of exactly
+            ids = [first + j * E + e for j in js for e in range(E)]     # this rank's passes
+            return loader.orders_of(ids, device).to(torch.int32).view(len(js), E, n_rows)
+        if hasattr(loader, "orders"):                                   # sort the covering range once, then pick
+            lo, hi = min(js), max(js)
+            allp = pass_orders(loader, first + lo * E, (hi - lo + 1) * E, n_rows, device).view(hi - lo + 1, E, n_rows)
+            return allp[torch.tensor([j - lo for j in js], device=allp.device)]
+        return torch.stack([pass_orders(loader, first + j * E, E, n_rows, device) for j in js])
 
     def run(js, g=None):
         """train the candidates todo[j], j in js, as one group"""
@@ -489,21 +542,8 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
                 models[todo[j]].attach(g, k, copy_in=True)                   # rmode.to(device), :72
                 if args.weightsharing:
                     set_central_states(models[todo[j]], state_dict, args.use_dataparallel)
-        def orders_for(loader, first, n_rows):
-            if E == 0:
-                return torch.zeros(len(js), 0, n_rows, dtype=torch.int32, device=device)
-            if js == list(range(js[0], js[0] + len(js))):                   # contiguous share: one batched sort
-                return pass_orders(loader, first + js[0] * E, len(js) * E, n_rows, device).view(len(js), E, n_rows)
-            if hasattr(loader, "orders_of"):                                # round-robin share: one batched sort of exactly
-                ids = [first + j * E + e for j in js for e in range(E)]     # this rank's passes
-                return loader.orders_of(ids, device).to(torch.int32).view(len(js), E, n_rows)
-            if hasattr(loader, "orders"):                                   # sort the covering range once, then pick
-                lo, hi = min(js), max(js)
-                allp = pass_orders(loader, first + lo * E, (hi - lo + 1) * E, n_rows, device).view(hi - lo + 1, E, n_rows)
-                return allp[torch.tensor([j - lo for j in js], device=allp.device)]
-            return torch.stack([pass_orders(loader, first + j * E, E, n_rows, device) for j in js])
-        ptr = orders_for(dataloaders['train'], first_tr, n_train)
-        pdv = orders_for(dataloaders['dev'], first_dv, n_dev)
+        ptr = orders_for(js, dataloaders['train'], first_tr, n_train, device)
+        pdv = orders_for(js, dataloaders['dev'], first_dv, n_dev, device)
         lap("batch orders")
         stats, best, _ = g.train_run(train_dev, dev_dev, ptr, pdv, lrs, E, B)
         lap("train_run (enqueue + GPU)")
@@ -524,7 +564,70 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
                     get_central_states(m, state_dict, args.use_dataparallel)
         return g
 
-    if direct:
+    def full_layout():
+        return GroupLayout([np.asarray(sampled_configurations[i]).reshape(-1, 3) for i in todo], args.inner_representation_size,
+                           args.num_outputs, flags, args.vid_len[1])
+
+    if direct and len(devices) > 1:
+        # ---- single-process fan-out: candidate j -> devices[j % n] (the same round-robin as the multi-process mode, so both
+        # modes and the 1-GPU run train identical candidates: initial weights keyed by (seed, candidate) or drawn from the
+        # constructor's CPU stream, batch orders keyed by (loader seed, pass)); one host thread per device -- ctypes and the
+        # CUDA runtime release the GIL while they enqueue -- and one D2H copy of the results per device.
+        import threading
+        nd = len(devices)
+        shares = [mdist.shard(len(todo), r, nd) for r in range(nd)]
+        full = hp = hb = None
+        if not dev_init:
+            full = full_layout()
+            hp, hb = _staging(int(full.p_off[-1]), int(full.b_off[-1]))
+            init_host_arenas(full, hp, hb)
+        results, errors = [None] * nd, []
+
+        def worker(r):
+            try:
+                js, dev = shares[r], devices[r]
+                if not js:
+                    return
+                with torch.cuda.device(dev):
+                    g = make_group(js, dev)
+                    if dev_init:
+                        init_on_device(g, base_seed, [todo[j] for j in js])
+                    else:
+                        for k, j in enumerate(js):
+                            g.params[int(g.p_off[k]):int(g.p_off[k + 1])].copy_(hp[int(full.p_off[j]):int(full.p_off[j + 1])], non_blocking=True)
+                            g.bufs[int(g.b_off[k]):int(g.b_off[k + 1])].copy_(hb[int(full.b_off[j]):int(full.b_off[j + 1])], non_blocking=True)
+                    tr_d, dv_d = train_host.to(dev), dev_host.to(dev)
+                    ptr = orders_for(js, dataloaders['train'], first_tr, n_train, dev)
+                    pdv = orders_for(js, dataloaders['dev'], first_dv, n_dev, dev)
+                    stats, best, _ = g.train_run(tr_d, dv_d, ptr, pdv, lrs, E, B)
+                    results[r] = (stats.cpu(), best.cpu())
+                    g.check()
+                    g.close()
+            except BaseException as ex:          # re-raised on the calling thread
+                errors.append(ex)
+
+        threads = [threading.Thread(target=worker, args=(r,), name=f"mfas-fanout-{r}") for r in range(1, nd)]
+        for t in threads:
+            t.start()
+        worker(0)
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        for r in range(nd):
+            if results[r] is None:
+                continue
+            stats, best = results[r]
+            for k, j in enumerate(shares[r]):
+                accs[j] = best[k]
+                all_stats[j] = stats[k]
+        if args.verbose:
+            for j in range(len(todo)):
+                print('Now training: ')
+                print(sampled_configurations[todo[j]])
+                _print_epoch_logs(all_stats[j].numpy(), n_train, n_dev)
+        lap(f"fan-out over {nd} devices")
+    elif direct:
         if mine:
             g = make_group(mine)
             lap("group creation")
@@ -534,9 +637,7 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
                 # Reference-compatible initialisation: one pinned host arena per group, filled in the constructor's
                 # RNG order for EVERY candidate of the call (other ranks' draws are consumed and dropped, so a
                 # candidate gets the same weights wherever it runs), then a single H2D copy.
-                full = g if len(mine) == len(todo) else GroupLayout(
-                    [np.asarray(sampled_configurations[i]).reshape(-1, 3) for i in todo], args.inner_representation_size,
-                    args.num_outputs, flags, args.vid_len[1])
+                full = g if len(mine) == len(todo) else full_layout()
                 hp, hb = _staging(int(full.p_off[-1]), int(full.b_off[-1]))
                 if full is g:
                     # a quarter of the candidates at a time: the H2D copy of one slice overlaps the fill of the next
@@ -559,7 +660,11 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
             del g
             lap("group teardown")
         elif not dev_init:
-            pass   # nothing to train on this rank; RNG parity across ranks is not needed for results it never produces
+            # nothing to train on this rank, but the constructor's draws are consumed all the same: the CPU generators of the
+            # ranks stay in lockstep, so the NEXT call still gives a candidate the same weights wherever it runs
+            full = full_layout()
+            hp, hb = _staging(int(full.p_off[-1]), int(full.b_off[-1]))
+            init_host_arenas(full, hp, hb)
     elif args.weightsharing:               # candidates are chained through state_dict: one at a time
         for j in mine:
             run([j])

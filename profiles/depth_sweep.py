@@ -54,7 +54,7 @@ def main():
                 g.params.uniform_(-0.03, 0.03)
                 g.bufs.fill_(1.0)
                 gen = torch.Generator(device=dev).manual_seed(0)
-                rows = [torch.randint(0, 4096, (B,), device=dev, generator=gen, dtype=torch.int32) for _ in range(a.steps + 5)]
+                rows = [torch.randint(0, 4096, (a.cands, B), device=dev, generator=gen, dtype=torch.int32) for _ in range(a.steps + 5)]   # every candidate its own batch
                 for i in range(5):
                     g.train_step(cache, rows[i], lr=1e-3)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

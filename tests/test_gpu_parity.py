@@ -575,6 +575,38 @@ def test_results_do_not_depend_on_placement(monkeypatch, init_on_device):
         assert seen.all()
 
 
+@pytest.mark.parametrize("init_on_device", [True, False])
+def test_single_process_fanout_equals_one_group_bitwise(monkeypatch, init_on_device):
+    """args.fanout_gpus: one candidate group per device, one host thread each, inside ONE train_sampled_models call (the
+    mode an unmodified single-process search driver uses several GPUs in).  Must return bit-for-bit what the 1-device call
+    returns.  On a 1-GPU box the three 'devices' are the same GPU: the threading, the sharding and the library's
+    thread-safety are still exercised; on a multi-GPU box the real devices are used."""
+    import mfas_b200.ntu_searchable as ntu
+    args = make_args(64, 32, 2, bn=True)
+    args.init_on_device = init_on_device
+    train, dev = synthetic_ntu_cache(160, 5), synthetic_ntu_cache(96, 6)
+    confs = [np.array(FOUND_CONFS[4]), np.array([[0, 0, 0]]), np.array(FOUND_CONFS[1][:2]), np.array([[2, 3, 1], [1, 1, 0]]),
+             np.array(FOUND_CONFS[2][:3]), np.array([[1, 0, 1]]), np.array(FOUND_CONFS[3])]
+
+    def run(fan):
+        loaders = {"train": FeatureCacheLoader(train, 32, True, 1), "dev": FeatureCacheLoader(dev, 32, True, 2)}
+        torch.manual_seed(11)
+        args.fanout_gpus = fan
+        accs = ntu.train_sampled_models(confs, ntu.Searchable_Skeleton_Image_Net, loaders, args, torch.device(DEV))
+        return torch.stack(accs), ntu.train_sampled_models.last_stats.clone()
+
+    one, one_st = run(None)
+    n_gpu = torch.cuda.device_count()
+    if n_gpu >= 2:
+        fan, fan_st = run("all")
+    else:
+        monkeypatch.setattr(ntu, "fanout_devices", lambda a, d: [torch.device(DEV)] * 3)
+        fan, fan_st = run(3)
+    assert torch.equal(one, fan), (one, fan)
+    assert torch.equal(one_st, fan_st)
+    assert (one > 0).any()
+
+
 @pytest.mark.parametrize("H,B,confs,engine", [
     (128, 64, [FOUND_CONFS[4], FOUND_CONFS[1]], "tc"),           # k_tc_bwd_ws<false> vs <true>, tensor-core head tile included
     (16, 64, [[[3, 1, 1], [1, 3, 0]], [[0, 0, 1]]], "tc"),      # masked tiles of the search default

@@ -167,13 +167,23 @@ def _dist_worker(rank, world, port, q):
         for j in mine:
             vals[j] = 10.0 + j                     # "accuracy" of the candidates this rank trained
         full = mdist.gather_results(vals, n)
-        cache = synthetic_ntu_cache(16, 9) if rank == 0 else None
+        cache = synthetic_ntu_cache(16, 9, with_backbone_logits=True) if rank == 0 else None
         got = mdist.broadcast_cache(cache, "cpu")
+        assert got.logit_rgb is not None and got.logit_rgb.shape == (16, 60)      # multitask flows work on a broadcast cache
+        # the reference's driver samples with unseeded numpy: every rank draws its own list; rank 0's list and seed win
+        import warnings
+        rng = np.random.RandomState(100 + rank)
+        confs = [rng.randint(0, 4, size=(1 + rng.randint(3), 3)) for _ in range(5)]
+        with warnings.catch_warnings(record=True) as wlist:
+            warnings.simplefilter("always")
+            synced, seed = mdist.sync_call_inputs(confs, 1000 + rank)
+        assert (len(wlist) == 1) == (rank != 0)
         from mfas_b200.mmimdb_searchable import WIDTHS, synthetic_mmimdb_cache     # multi-hot targets + pos_weight ride along
         ml = mdist.broadcast_cache(synthetic_mmimdb_cache(12, 4) if rank == 0 else None, "cpu")
         assert ml.multilabel and ml.widths == WIDTHS and ml.labels.shape == (12, 23)
         q.put((rank, mine, full.tolist(), float(got.rgb_cat.sum()), int(got.labels.sum()),
-               float(ml.labels.sum() + ml.pos_weight.sum() + ml.ske_cat.sum())))
+               float(ml.labels.sum() + ml.pos_weight.sum() + ml.ske_cat.sum()), [c.tolist() for c in synced], seed,
+               float(got.logit_rgb.sum() + got.logit_ske.sum())))
     finally:
         td.destroy_process_group()
 
@@ -191,8 +201,12 @@ def test_sharding_and_gather_world2_gloo():
     res = sorted(q.get(timeout=120) for _ in procs)
     for p in procs:
         p.join(timeout=60)
-    ref = synthetic_ntu_cache(16, 9)
+    ref = synthetic_ntu_cache(16, 9, with_backbone_logits=True)
     assert res[0][1] == [0, 2, 4, 6] and res[1][1] == [1, 3, 5]
+    rng = np.random.RandomState(100)
+    want = [rng.randint(0, 4, size=(1 + rng.randint(3), 3)).tolist() for _ in range(5)]
+    assert res[0][6] == res[1][6] == want and res[0][7] == res[1][7] == 1000          # rank 0's list and seed on both ranks
+    assert res[0][8] == res[1][8] == pytest.approx(float(ref.logit_rgb.sum() + ref.logit_ske.sum()))
     for r in res:
         assert r[2] == [10.0 + j for j in range(7)]                      # every rank sees all results, in input order
         assert r[3] == pytest.approx(float(ref.rgb_cat.sum())) and r[4] == int(ref.labels.sum())
