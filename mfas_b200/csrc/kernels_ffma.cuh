@@ -290,9 +290,10 @@ __device__ __forceinline__ void head_rows(const DCand& cd, const DCache& cache, 
 //   metric  sigmoid(x) > 0.3 against z: true positives and |pred| + |true| of the row, from which the caller forms the
 //          per-sample F1 in fp64 (f1_score(average='samples'), train_searchable/mmimdb.py:84,101).
 // rowloss[r] = sum_c L[r][c]; rowok[r] = 1 when the thresholded set equals the label set; tpden[r] = tp | (den << 8).
+// dlog (global, [.][64], or null) receives a zero-padded copy of dlogits for the tensor-core consumers (see head_rows).
 template <bool TRAIN>
 __device__ __forceinline__ void head_rows_ml(const DCand& cd, const DCache& cache, int nrows, float* lg, int lg_ld,
-                                             float* rowloss, int* rowok, int* tpden, const int* grow) {
+                                             float* rowloss, int* rowok, int* tpden, const int* grow, float* dlog = nullptr) {
   const int C = cd.C, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float inv_bc = 1.f / ((float)nrows * (float)C);
   for (int r = warp; r < nrows; r += kHeadThreads / 32) {
@@ -313,7 +314,9 @@ __device__ __forceinline__ void head_rows_ml(const DCand& cd, const DCache& cach
       tp += __popc(pb & tb);
       den += __popc(pb) + __popc(tb);
       wrong += __popc(pb ^ tb);
-      if (TRAIN && ok) row[c] = (-q * z * (1.f - s) + (1.f - z) * s) * inv_bc;
+      const float dl = ok ? (-q * z * (1.f - s) + (1.f - z) * s) * inv_bc : 0.f;
+      if (TRAIN && ok) row[c] = dl;
+      if (TRAIN && dlog) dlog[r * 64 + c] = dl;                    // zero-padded to 64 columns
     }
     ls = warp_sum(ls);
     if (lane == 0) {

@@ -45,6 +45,20 @@ __host__ __device__ __forceinline__ void tc_fwd_range(int nkb, int split, int& k
   kb0 = split * per;
   kb1 = kb0 + per < nkb ? kb0 + per : nkb;
 }
+// Alpha-gated candidates (MFAS_FLAG_ALPHAS): forward work items never straddle the boundary between the two modalities -- the
+// first tc_fwd_items_of(d_ske) items of a layer cover the ske columns, the rest the rgb columns -- so the consumer of the partial
+// sums applies the gate of a modality as ONE factor per partial: z = s * (W_ske x_ske) + (1 - s) * (W_rgb x_rgb) + ...
+__host__ __device__ __forceinline__ int tc_fwd_items_of(int width) { return ((width >> 5) + TC_KB_PER_ITEM - 1) / TC_KB_PER_ITEM; }
+__host__ __device__ __forceinline__ int tc_fwd_items_g(int d_ske, int d_rgb, bool gated) {
+  return gated ? tc_fwd_items_of(d_ske) + tc_fwd_items_of(d_rgb) : tc_fwd_items(d_ske, d_rgb);
+}
+// k-block range of item `split` of a layer (gated: an even split of the item's own modality)
+__host__ __device__ __forceinline__ void tc_fwd_range_g(int d_ske, int d_rgb, int split, bool gated, int& kb0, int& kb1) {
+  if (!gated) { tc_fwd_range((d_ske + d_rgb) >> 5, split, kb0, kb1); return; }
+  const int ns = tc_fwd_items_of(d_ske);
+  if (split < ns) tc_fwd_range(d_ske >> 5, split, kb0, kb1);
+  else { tc_fwd_range(d_rgb >> 5, split - ns, kb0, kb1); kb0 += d_ske >> 5; kb1 += d_ske >> 5; }
+}
 __host__ __device__ __forceinline__ int tc_bwd_items(int K) { return (K + TC_BWD_KT - 1) / TC_BWD_KT; }
 
 __device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, float4 x) {
@@ -890,9 +904,14 @@ __device__ __forceinline__ void chain_fwd_layer(ChainCtx& cx, const DCand& cd, i
 #pragma unroll
   for (int b = 0; b < NB; ++b) z[b] = 0.f;
   if (mine) {      // feature partials of this layer: all requested at once (they fly while the MMAs run), summed in split order
+    // alpha gates (aux_models.py:103-111: ske * sigmoid(alpha), rgb * (1 - sigmoid(alpha))): the items of a gated candidate are
+    // cut at the modality boundary, so the gate is one factor per partial sum
+    const bool gated = (cd.flags & MFAS_FLAG_ALPHAS) != 0;
+    const float sg = gated ? gate_of(cd.p[ly.oalpha]) : 1.f;
+    const int n_ske = tc_fwd_items_of(ly.d_ske);
     int item0 = 0;
-    for (int l = 0; l < layer; ++l) item0 += tc_fwd_items(cd.layer[l].d_ske, cd.layer[l].d_rgb);
-    const int nsplit = tc_fwd_items(ly.d_ske, ly.d_rgb);
+    for (int l = 0; l < layer; ++l) item0 += tc_fwd_items_g(cd.layer[l].d_ske, cd.layer[l].d_rgb, gated);
+    const int nsplit = tc_fwd_items_g(ly.d_ske, ly.d_rgb, gated);
     const int Hp = ((H + 127) >> 7) << 7;
     const float4* part = reinterpret_cast<const float4*>(part_base + (long long)cand * part_stride_cand + (long long)item0 * Hp * NPAD) +
                          (long long)(b0 >> 2) * Hp + c;
@@ -908,8 +927,17 @@ __device__ __forceinline__ void chain_fwd_layer(ChainCtx& cx, const DCand& cd, i
 #pragma unroll
       for (int u = 0; u < SU; ++u) {
         if (s0 + u < nsplit) {
+          if (gated) {
+            const float gt = s0 + u < n_ske ? sg : 1.0f - sg;
 #pragma unroll
-          for (int k = 0; k < NB / 4; ++k) { z[4 * k] += v[u][k].x; z[4 * k + 1] += v[u][k].y; z[4 * k + 2] += v[u][k].z; z[4 * k + 3] += v[u][k].w; }
+            for (int k = 0; k < NB / 4; ++k) {
+              z[4 * k] = fmaf(gt, v[u][k].x, z[4 * k]); z[4 * k + 1] = fmaf(gt, v[u][k].y, z[4 * k + 1]);
+              z[4 * k + 2] = fmaf(gt, v[u][k].z, z[4 * k + 2]); z[4 * k + 3] = fmaf(gt, v[u][k].w, z[4 * k + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < NB / 4; ++k) { z[4 * k] += v[u][k].x; z[4 * k + 1] += v[u][k].y; z[4 * k + 2] += v[u][k].z; z[4 * k + 3] += v[u][k].w; }
+          }
         }
       }
     }
@@ -1220,7 +1248,9 @@ struct HeadRows {
 // the last fusion step's backward (chain_bwd_layer, head_up), and dW_c = dlogits^T h_L with its Adam step is one more
 // tile of the weight-streaming kernel (k_tc_bwd_ws, layer index L).  (r01 timeline: the CUDA-core head was 86 k of the
 // chain's 280 k cycles -- shared-memory bandwidth on dh/dW_c and the p/m/v round trip of W_c.)
-template <bool TRAIN, int NPAD>
+// ML: the multi-label head of the MM-IMDB network (head_rows_ml: weighted BCE-with-logits, per-sample F1 statistic) in place of
+// softmax-CE; hr.lab then carries tp | den << 8 per row.
+template <bool TRAIN, int NPAD, bool ML>
 __device__ __forceinline__ void chain_head_tc(ChainCtx& cx, const DCand& cd, int cand, const DCache& cache, const BatchRef& batch,
                                               int bmax, const AdamH& adam, float step_size, float bc2_sqrt, const HeadOut& out,
                                               HeadRows& hr) {
@@ -1257,22 +1287,31 @@ __device__ __forceinline__ void chain_head_tc(ChainCtx& cx, const DCand& cd, int
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
-  head_rows<TRAIN>(cd, cache, nrows, lg, LG_LD, hr.rowloss, hr.rowok, hr.lab, hr.grow, TRAIN ? cd.dlog : nullptr);
+  if (ML) head_rows_ml<TRAIN>(cd, cache, nrows, lg, LG_LD, hr.rowloss, hr.rowok, hr.lab, hr.grow, TRAIN ? cd.dlog : nullptr);
+  else head_rows<TRAIN>(cd, cache, nrows, lg, LG_LD, hr.rowloss, hr.rowok, hr.lab, hr.grow, TRAIN ? cd.dlog : nullptr);
   __syncthreads();
   if (warp == 0) {                                         // batch statistics: fixed-order tree (deterministic)
     float ls = 0.f;
     int ok = 0;
-    for (int r = lane; r < nrows; r += 32) { ls += hr.rowloss[r]; ok += hr.rowok[r]; }
+    double f1 = 0.0;                                       // ML: sum over rows of 2 tp / (|pred| + |true|), 0 when both are empty
+    for (int r = lane; r < nrows; r += 32) {
+      ls += hr.rowloss[r]; ok += hr.rowok[r];
+      if (ML) { const int tp = hr.lab[r] & 255, den = hr.lab[r] >> 8; f1 += den > 0 ? 2.0 * (double)tp / (double)den : 0.0; }
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { ls += __shfl_xor_sync(0xffffffffu, ls, o); ok += __shfl_xor_sync(0xffffffffu, ok, o); }
+    for (int o = 16; o > 0; o >>= 1) {
+      ls += __shfl_xor_sync(0xffffffffu, ls, o); ok += __shfl_xor_sync(0xffffffffu, ok, o);
+      if (ML) f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+    }
     if (lane == 0) {
-      const float mean_loss = ls / (float)nrows;                    // CrossEntropyLoss(reduction='mean')
+      // CrossEntropyLoss(reduction='mean'); ML: torch.mean over all B*C elements (aux_models.py:146)
+      const float mean_loss = ML ? ls / ((float)nrows * (float)cd.C) : ls / (float)nrows;
       if (out.loss) out.loss[cand] = mean_loss;
       if (out.correct) out.correct[cand] = ok;
-      if (out.stats) {                                              // running_loss += loss.item()*B (ntu.py:72-73)
+      if (out.stats) {                                              // running_loss += loss.item()*B (ntu.py:72-73, mmimdb.py:88)
         double* st = out.stats + (long long)cand * out.stat_stride + out.stat_off;
         st[0] += (double)mean_loss * (double)nrows;
-        st[1] += (double)ok;
+        st[1] += ML ? f1 : (double)ok;
       }
     }
   }
@@ -1286,7 +1325,7 @@ __device__ __forceinline__ void chain_head_tc(ChainCtx& cx, const DCand& cd, int
   }
 }
 
-template <bool TRAIN, int NPAD, bool TCHEAD>
+template <bool TRAIN, int NPAD, bool TCHEAD, bool ML = false>
 __global__ void __launch_bounds__(ChainCfg<NPAD>::THREADS)
 k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, const float* part_base,
             long long part_stride_cand, int hs_ld, int lg_ld, AdamH adam, float step_size, float bc2_sqrt,
@@ -1310,7 +1349,7 @@ k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
     for (int r = tid; r < nrows; r += ChainCfg<NPAD>::THREADS) {
       const int gr = batch_row(batch, cand, r);
       hr.grow[r] = gr;
-      hr.lab[r] = (int)cache.labels[gr];
+      if (!ML) hr.lab[r] = (int)cache.labels[gr];
     }
   }
   ChainCtx cx;
@@ -1327,31 +1366,37 @@ k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
     if (l < L) {
       const DLayer& ly = cd.layer[l];
       const float* Wh = cd.p + ly.oW + ly.d_ske + ly.d_rgb;
-      const int lsh = 31 - __clz(H >> 5) , lines = H >> 5;       // 128-byte lines per row (H in {64, 128}: 2 or 4)
+      const int lsh = 31 - __clz(H >> 5) , lines = H >> 5;       // 128-byte lines per row (H a power of two >= 64: 2, 4 or 8; below: no prefetch)
       for (int i = tid; i < H * lines; i += ChainCfg<NPAD>::THREADS) prefetch_l2(Wh + (long long)(i >> lsh) * ly.K + (i & (lines - 1)) * 32);
     } else {
       for (int i = tid; i < (cd.C * H) >> 5; i += ChainCfg<NPAD>::THREADS) prefetch_l2(cd.p + cd.oWc + i * 32);
     }
   };
 
+  // inner_repr 256: the CTA walks the two 128-column tiles of a layer one after the other (same accumulator, same operand
+  // tiles); both read h_{l-1} / dz_{l+1} in full and write disjoint columns, so the only ordering is layer by layer
   for (int l = 0; l < L; ++l) {
     prefetch_next(l + 1);
-    chain_fwd_layer<TRAIN, NPAD>(cx, cd, cand, l, 0, nrows, bmax, part_base, part_stride_cand, drop_seed, drop_p, step);
-    umma::tc_fence_before();
-    __syncthreads();                                             // h_l (global) and the TMEM reads are done
-    umma::tc_fence_after();
+    for (int m0 = 0; m0 < H; m0 += 128) {
+      chain_fwd_layer<TRAIN, NPAD>(cx, cd, cand, l, m0, nrows, bmax, part_base, part_stride_cand, drop_seed, drop_p, step);
+      umma::tc_fence_before();
+      __syncthreads();                                           // h_l (global) and the TMEM reads are done
+      umma::tc_fence_after();
+    }
     stamp();
   }
-  if (TCHEAD) chain_head_tc<TRAIN, NPAD>(cx, cd, cand, cache, batch, bmax, adam, step_size, bc2_sqrt, ho, hr);
-  else head_body<TRAIN>(cd, cand, cache, batch, bmax, hs_ld, lg_ld, adam, step_size, bc2_sqrt, ho, reinterpret_cast<float*>(cx.smem));
+  if (TCHEAD) chain_head_tc<TRAIN, NPAD, ML>(cx, cd, cand, cache, batch, bmax, adam, step_size, bc2_sqrt, ho, hr);
+  else head_body<TRAIN, ML>(cd, cand, cache, batch, bmax, hs_ld, lg_ld, adam, step_size, bc2_sqrt, ho, reinterpret_cast<float*>(cx.smem));
   stamp();
   if (TRAIN) {
     for (int l = L - 1; l >= 0; --l) {
-      __syncthreads();                                           // dlogits / dh_L / dz_{l+1} (global) visible, smem tiles free
-      chain_bwd_layer<NPAD>(cx, cd, l, 0, nrows, bmax, adam, step_size, bc2_sqrt, drop_seed, drop_p, step, TCHEAD);
-      umma::tc_fence_before();
-      __syncthreads();
-      umma::tc_fence_after();
+      for (int m0 = 0; m0 < H; m0 += 128) {
+        __syncthreads();                                         // dlogits / dh_L / dz_{l+1} (global) visible, smem tiles free
+        chain_bwd_layer<NPAD>(cx, cd, l, m0, nrows, bmax, adam, step_size, bc2_sqrt, drop_seed, drop_p, step, TCHEAD);
+        umma::tc_fence_before();
+        __syncthreads();
+        umma::tc_fence_after();
+      }
       stamp();
     }
   }
@@ -1513,7 +1558,8 @@ k_tc_bwd_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward, all layers, persistent + warp-specialised (BP = 64): one CTA per SM walks a static list of
+// backward, all layers, persistent + warp-specialised (operand stage of BP = 64 batch rows; batches up to 128 rows in two
+// passes over the stage into the same accumulator): one CTA per SM walks a static list of
 // tiles (the same 128 weight columns x 64 rows tile as k_tc_bwd_all) with three decoupled roles, so
 // the x/dz operand traffic, the tensor-core work and the Adam p/m/v stream of different tiles overlap
 // all the time instead of taking turns inside a CTA:
@@ -1540,7 +1586,10 @@ struct __align__(16) BwdTile {
   long long moff, voff, goff;     // adam_m - params, adam_v - params, grad - params (floats; goff 0 when no grad arena)
   int K, kw, rows, pad1;          // rows: valid rows of the 64 (64 for a fusion layer, C for the classifier tile)
   int cand, layer, kc0, h0;       // 16-byte aligned: the stagers read these four as one int4 (layer == L: the classifier)
+  const float* alpha;             // alpha gates: &params[oalpha] of the tile's layer (pre-update value: the step's last launch updates it)
+  int gate, slot;                 // gate: 0 none, 1 ske columns (x sigmoid(alpha)), 2 rgb columns (x (1 - sigmoid(alpha))); slot: tile index
 };
+constexpr int TC_DSP_PER_TILE = 8;                      // one d(loss)/d(sigmoid(alpha)) partial per Adam warp and tile
 constexpr int TC_WS_THREADS = 17 * 32;
 constexpr int WS_RING = 4;                              // ring slots per Adam warp (= batches per tile)
 constexpr int WS_SLOT = 3 * 8 * 128;                    // bytes: 3 arrays x 8 rows x 32 floats
@@ -1552,10 +1601,13 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, u
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <bool KEEP_GRAD>
+// ALPHA (groups with the modality gates on): the staged x is unscaled, so the accumulator holds G = dz^T x; the weight gradient
+// of a gated tile is gate * G, and d(loss)/d(sigmoid(alpha)) = +- sum(W o G) over the tile (pre-update W) -- summed per Adam warp
+// in a fixed order and left in dsp[tile][warp] for k_alpha_step_tc, which finishes the sum and updates alpha after this launch.
+template <bool KEEP_GRAD, bool ALPHA = false>
 __global__ void __launch_bounds__(TC_WS_THREADS, 1)
 k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, AdamH adam, float step_size,
-            float bc2_sqrt, const BwdTile* __restrict__ tiles, int n_tiles, TcErr err) {
+            float bc2_sqrt, const BwdTile* __restrict__ tiles, int n_tiles, TcErr err, float* __restrict__ dsp = nullptr) {
   constexpr int BP = 64;
   constexpr uint32_t BLK = BP * 128, A_TILE = 4 * BLK, B_TILE = 2 * BLK, STAGE = 2 * A_TILE + 2 * B_TILE;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1582,13 +1634,19 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
     // Two-deep software pipeline so that no wait sits on a chain of dependent loads: the tile descriptor
     // and the 8 gather indices of tile i+2 are fetched while the x / dz loads of tile i+1 are in flight
     // (r01 ncu: with index -> x load pairs issued one after the other the stagers, not HBM, set the pace).
-    struct Desc { const float* src; const float* dz; long long ld; int H, kw; int row[8]; };   // kw = valid x columns | valid dz columns (H < 64) << 16
+    // Batches above 64 rows: the batch is the reduction dimension of dW = x^T dz, so a tile is staged and multiplied in
+    // `npass` passes of <= 64 rows into the SAME accumulator (the 96 KB operand stage stays as it is); the unit the stagers and
+    // the MMA warp hand over is a "fill" f = tile * npass + pass.
+    struct Desc { const float* src; const float* dz; long long ld; int H, kw, row0; int row[8]; };   // kw = valid x columns | valid dz columns (H < 64) << 16; row0 = first batch row of this pass
     float4 xv[8], dv[4];
-    auto fetch_desc = [&](int i, Desc& d) {
+    const int npass = (nrows + BP - 1) / BP, n_fill = n_my * npass;
+    auto fetch_desc = [&](int f, Desc& d) {
+      const int i = npass == 1 ? f : (f >> 1), row0 = npass == 1 ? 0 : (f & 1) * BP;
       const int4 t = *reinterpret_cast<const int4*>(&tiles[blockIdx.x + i * gridDim.x].cand);   // {cand, layer, kc0, h0}
       const DCand& cd = cands[t.x];
       const int H = cd.H, kc0 = t.z;
       bool gather = true;
+      d.row0 = row0;
       if (t.y >= cd.L) {                                // the classifier as one more layer: x = h_L, dz = dlogits (zero-padded to 64 classes)
         d.src = cd.hid + (long long)(cd.L - 1) * bmax * H + kc0; d.ld = H; gather = false;
         d.H = TC_DLOG_LD; d.kw = min(TC_BWD_KT, H - kc0) | (TC_BWD_HT << 16);
@@ -1606,8 +1664,8 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
         d.dz = cd.dzs + (long long)t.y * bmax * H + t.w;
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {                     // rows warp, warp+8, ...: one index per warp and j
-        const int r = min(warp + 8 * j, nrows - 1);
+      for (int j = 0; j < 8; ++j) {                     // rows row0 + warp, row0 + warp + 8, ...: one index per warp and j
+        const int r = min(row0 + warp + 8 * j, nrows - 1);
         d.row[j] = gather ? batch_row(batch, t.x, r) : r;
       }
     };
@@ -1617,20 +1675,20 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 x = __ldg(reinterpret_cast<const float4*>(d.src + (long long)d.row[j] * d.ld + cc));
-        xv[j] = (warp + 8 * j < nrows && c4 * 4 < kw) ? x : make_float4(0.f, 0.f, 0.f, 0.f);
+        xv[j] = (d.row0 + warp + 8 * j < nrows && c4 * 4 < kw) ? x : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int idx = tid + 256 * j, r = idx >> 4, cd4 = idx & 15;
+        const int idx = tid + 256 * j, r = d.row0 + (idx >> 4), cd4 = idx & 15;
         const float4 x = *reinterpret_cast<const float4*>(d.dz + (long long)min(r, nrows - 1) * d.H + min(cd4 * 4, hw - 4));
         dv[j] = (r < nrows && cd4 * 4 < hw) ? x : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     Desc d1{};
-    if (n_my > 0) { fetch_desc(0, d1); issue_loads(d1); }
-    if (n_my > 1) fetch_desc(1, d1);
-    for (int i = 0; i < n_my; ++i) {
-      if (!umma::mbar_wait(&empty, (i & 1) ^ 1)) { ok = false; break; }   // MMAs of tile i-1 have read the stage
+    if (n_fill > 0) { fetch_desc(0, d1); issue_loads(d1); }
+    if (n_fill > 1) fetch_desc(1, d1);
+    for (int i = 0; i < n_fill; ++i) {
+      if (!umma::mbar_wait(&empty, (i & 1) ^ 1)) { ok = false; break; }   // MMAs of fill i-1 have read the stage
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int idx = tid + 256 * j, r = idx >> 5, c4 = idx & 31;
@@ -1644,33 +1702,34 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
       umma::fence_async_smem();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&full);
-      if (i + 1 < n_my) issue_loads(d1);               // in flight while this tile's MMAs and Adam pass run
-      if (i + 2 < n_my) fetch_desc(i + 2, d1);
+      if (i + 1 < n_fill) issue_loads(d1);             // in flight while this fill's MMAs and the Adam pass run
+      if (i + 2 < n_fill) fetch_desc(i + 2, d1);
     }
   } else if (warp == 8) {
     // ================================ MMA issuer ==================================================
     constexpr uint32_t idesc = umma::idesc_tf32(128, TC_BWD_HT, true, true);
-    const int ksteps = (nrows + 7) >> 3;
-    for (int i = 0; i < n_my; ++i) {
-      const int tb = i & 1;
-      if (!umma::mbar_wait(&full, i & 1)) { ok = false; break; }
-      if (!umma::mbar_wait(&tempty[tb], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
+    const int npass = (nrows + BP - 1) / BP, n_fill = n_my * npass;
+    for (int f = 0; f < n_fill; ++f) {
+      const int i = npass == 1 ? f : (f >> 1), pass = npass == 1 ? 0 : (f & 1), tb = i & 1;
+      if (!umma::mbar_wait(&full, f & 1)) { ok = false; break; }
+      if (pass == 0 && !umma::mbar_wait(&tempty[tb], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
       umma::tc_fence_after();
       if (umma::elect_one()) {
         const uint32_t a_hi = umma::smem_u32(smem), a_lo = a_hi + A_TILE, b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
         const uint32_t d = tm + tb * 64;
+        const int ksteps = (min(BP, nrows - pass * BP) + 7) >> 3;
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint32_t adv = ks * 1024u;
           const uint64_t dah = umma::smem_desc(a_hi + adv, BLK, 512, umma::kLayoutSw128Base32);
           const uint64_t dal = umma::smem_desc(a_lo + adv, BLK, 512, umma::kLayoutSw128Base32);
           const uint64_t dbh = umma::smem_desc(b_hi + adv, BLK, 512, umma::kLayoutSw128Base32);
           const uint64_t dbl = umma::smem_desc(b_lo + adv, BLK, 512, umma::kLayoutSw128Base32);
-          umma::mma_tf32(d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+          umma::mma_tf32(d, dal, dbh, idesc, (pass > 0 || ks > 0) ? 1u : 0u);
           umma::mma_tf32(d, dah, dbl, idesc, 1u);
           umma::mma_tf32(d, dah, dbh, idesc, 1u);
         }
         umma::mma_commit(&empty);                      // operand stage free once these MMAs have read it
-        umma::mma_commit(&tfull[tb]);                  // accumulator ready for the Adam warps
+        if (pass == npass - 1) umma::mma_commit(&tfull[tb]);   // accumulator ready for the Adam warps
       }
       __syncwarp();
     }
@@ -1683,11 +1742,12 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
     const uint32_t ring_u32 = umma::smem_u32(ring);
     const int srow = lane >> 3, schunk = lane & 7;     // cp.async: a lane moves 16 B of row (4*u + srow)
     const uint64_t stream_policy = l2_stream_policy((err.l2_hints & 2) != 0);
-    struct Tile { float* W; long long K, moff, voff, goff; int rc; };   // rc = rows | cols << 8: valid rows / columns of this warp's 32 x 32 (0 columns: nothing to do)   // rows: valid rows of this warp's 32 (64-row tiles: 32; the classifier tile: C - 32 cg, clamped)
-    struct Raw { int4 a, b, c; };                      // first 48 bytes of a BwdTile
+    struct Tile { float* W; long long K, moff, voff, goff; int rc; float gsc, gsign; int slot; };   // rc = rows | cols << 8: valid rows / columns of this warp's 32 x 32 (0 columns: nothing to do)
+    struct Raw { int4 a, b, c, d; };                   // first 48 bytes of a BwdTile (+ the gate record when ALPHA)
     auto fetch_raw = [&](int i) {
       const int4* r = reinterpret_cast<const int4*>(&tiles[blockIdx.x + i * gridDim.x]);
       Raw o; o.a = __ldg(r); o.b = __ldg(r + 1); o.c = __ldg(r + 2);
+      o.d = ALPHA ? __ldg(r + 4) : make_int4(0, 0, 0, 0);
       return o;
     };
     auto open_tile = [&](const Raw& r) {
@@ -1701,6 +1761,14 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
       // fewer columns in the last chunk of a layer (the 16 / 32 / 64 hidden columns)
       o.rc = min(32, max(0, r.c.z - cg * 32)) | (min(32, max(0, r.c.y - q * 32)) << 8);
       o.W = reinterpret_cast<float*>(Wbits) + (long long)(cg * 32) * o.K + q * 32;   // first row / column of this warp
+      o.gsc = 1.f; o.gsign = 0.f; o.slot = 0;
+      if (ALPHA && r.d.z) {
+        const float* ap = reinterpret_cast<const float*>(((long long)(uint32_t)r.d.y << 32) | (uint32_t)r.d.x);
+        const float sg = gate_of(__ldg(ap));
+        o.gsc = r.d.z == 1 ? sg : 1.0f - sg;
+        o.gsign = r.d.z == 1 ? 1.f : -1.f;
+        o.slot = r.d.w;
+      }
       return o;
     };
     // request batch j (rows 8j .. 8j+7 of this warp's 32) of tile t into ring slot j; always commits a group
@@ -1736,6 +1804,7 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
       if (i + 2 < n_my) ahead = fetch_raw(i + 2);
       if (!umma::mbar_wait(&tfull[tb], (i >> 1) & 1)) { ok = false; break; }
       umma::tc_fence_after();
+      float dsum = 0.f;                                // ALPHA: sum over this warp's part of the tile of W (pre-update) o G
 #pragma unroll
       for (int j = 0; j < WS_RING; ++j) {
         cp_async_wait<WS_RING - 1>();                  // the oldest outstanding batch (this one) has landed
@@ -1748,6 +1817,13 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
           float p[8], m[8], v[8];
 #pragma unroll
           for (int r = 0; r < 8; ++r) { p[r] = sp[r * 32]; m[r] = sp[256 + r * 32]; v[r] = sp[512 + r * 32]; }
+          if (ALPHA) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              if (8 * j + r < (cur.rc & 255) && lane < (cur.rc >> 8)) dsum = fmaf(p[r], g[r], dsum);   // (ring slots of masked elements hold stale bytes)
+              g[r] *= cur.gsc;
+            }
+          }
 #pragma unroll
           for (int r = 0; r < 8; ++r) adam_update_fast(g[r], p[r], m[r], v[r], adam, step_size, inv_bc2);
           if (cur.rc == (32 | (32 << 8))) {             // full 32 x 32 (always, except in the classifier tile and for inner_repr < 64)
@@ -1771,6 +1847,10 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
         __syncwarp();                                  // every lane has read slot j before it is refilled
         if (more) request(nxt, j); else cp_async_commit();
       }
+      if (ALPHA && cur.gsign != 0.f) {                 // (warp-uniform) fixed-order tree; k_alpha_step_tc adds the 8 x tiles partials in order
+        dsum = warp_sum(dsum);
+        if (lane == 0) dsp[(long long)cur.slot * TC_DSP_PER_TILE + aw] = cur.gsign * dsum;
+      }
       umma::tc_fence_before();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&tempty[tb]);   // this warp has drained its part of the accumulator
@@ -1782,6 +1862,29 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
   umma::tc_fence_before();
   __syncthreads();
   if (warp == 0) umma::tmem_free(tm, 128);
+}
+
+// ---------------------------------------------------------------------------------------------
+// alpha gates, tensor-core engine: d(alpha_l) = (sum of the per-tile, per-warp partials of k_tc_bwd_ws<., true>, fixed order)
+// * s (1 - s), then Adam (the arithmetic of k_alpha_step).  One thread per (candidate, layer); rng[cand][layer] = {first
+// tile, number of feature-column tiles} of the layer in the tile list.  Launched after the backward stream of every train step.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_alpha_step_tc(const DCand* __restrict__ cands, int n_cand, const int2* __restrict__ rng, const float* __restrict__ dsp,
+                                AdamH adam, float step_size, float bc2_sqrt) {
+  const int cand = blockIdx.x * (blockDim.x / MFAS_MAX_LAYERS) + threadIdx.x / MFAS_MAX_LAYERS, l = threadIdx.x % MFAS_MAX_LAYERS;
+  if (cand >= n_cand) return;
+  const DCand& cd = cands[cand];
+  if (l >= cd.L || !(cd.flags & MFAS_FLAG_ALPHAS)) return;
+  const int2 r = rng[cand * MFAS_MAX_LAYERS + l];
+  float ds = 0.f;
+  for (int i = 0; i < r.y * TC_DSP_PER_TILE; ++i) ds += dsp[(long long)r.x * TC_DSP_PER_TILE + i];
+  const DLayer& ly = cd.layer[l];
+  float p = cd.p[ly.oalpha], m = cd.m[ly.oalpha], v = cd.v[ly.oalpha];
+  const float sg = gate_of(p);
+  const float g = ds * sg * (1.0f - sg);
+  if (cd.grad) cd.grad[ly.oalpha] = g;
+  adam_update(g, p, m, v, adam, step_size, bc2_sqrt);
+  cd.p[ly.oalpha] = p; cd.m[ly.oalpha] = m; cd.v[ly.oalpha] = v;
 }
 
 }  // namespace mfas

@@ -258,6 +258,9 @@ struct mfas_group {
   bool ev128 = false;             // dev / test passes run 128 rows per step (tc engine, batch <= 64): W is read half as often
   long long part_stride_ev = 0;
   bool any_alphas = false;
+  float* dsp_tc = nullptr;        // alpha gates on the tc engine: [n_bwd_tiles][TC_DSP_PER_TILE] partials of d(loss)/d(sigmoid(alpha))
+  int2* alpha_rng = nullptr;      // [n_cand][MFAS_MAX_LAYERS] {first tile, feature-column tiles} of every layer in the tile list
+  size_t dsp_bytes = 0, rng_bytes = 0;
   int l2_hints = 1;
   bool tchead = false;            // classifier head on the tensor core inside k_chain_all (+ its dW as a k_tc_bwd_ws tile)
   cudaEvent_t prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // mfas_group_set_profiling: around fwd / chain / bwd of a step
@@ -295,6 +298,8 @@ extern "C" int mfas_group_destroy(mfas_group_t g) {
   for (auto& ev : g->prof_ev) if (ev) cudaEventDestroy(ev);
   pool_free(g->device, g->tc_err, g->err_bytes);
   pool_free(g->device, g->timeline, g->tl_bytes);
+  pool_free(g->device, g->dsp_tc, g->dsp_bytes);
+  pool_free(g->device, g->alpha_rng, g->rng_bytes);
   delete g;
   return MFAS_OK;
 }
@@ -416,13 +421,12 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
   // ---- engine selection: tensor cores whenever the shapes fit the MMA tiles -----------------------
   auto l_small_ok = [](const mfas_layout& l) { return l.C <= TC_DLOG_LD; };     // small inner_repr needs the tensor-core head
   bool tc_ok = true, ragged = false;
+  const bool stage_override = getenv("MFAS_BWD") || getenv("MFAS_FWD") || getenv("MFAS_CHAIN") || getenv("MFAS_HEAD");
   for (int c = 0; c < n_cand; ++c) {
     // inner_repr 16 / 32 (the search default) ride the same tiles with most rows masked; that needs the row / column
-    // masks of the persistent kernels and the fused chain, i.e. batch <= 64 and none of the stage-by-stage overrides
-    const bool small_ok = batch_max <= 64 && !getenv("MFAS_BWD") && !getenv("MFAS_FWD") && !getenv("MFAS_CHAIN") && !getenv("MFAS_HEAD") &&
-                          l_small_ok(g->lay[c]);
+    // masks of the persistent kernels and the fused chain with the tensor-core head, i.e. none of the stage-by-stage overrides
+    const bool small_ok = !stage_override && l_small_ok(g->lay[c]);
     tc_ok = tc_ok && (g->lay[c].H % 64 == 0 || ((g->lay[c].H == 16 || g->lay[c].H == 32) && small_ok));
-    tc_ok = tc_ok && !(g->lay[c].flags & MFAS_FLAG_ALPHAS);      // the modality gates are built in the CUDA-core engine only
     g->multilabel = g->multilabel || (g->lay[c].flags & MFAS_FLAG_MULTILABEL);
     if (((g->lay[c].flags ^ g->lay[0].flags) & MFAS_FLAG_MULTILABEL) ||
         ((g->lay[c].flags & MFAS_FLAG_MULTILABEL) && (g->lay[c].flags & MFAS_FLAG_MULTITASK))) {
@@ -439,18 +443,17 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
           mfas_group_destroy(g);
           return code;
         }
-    // the multi-label (MM-IMDB) head lives in k_head: per-layer chain kernels (no fused chain, no tensor-core head), which
-    // have no row / column masks for inner_repr 16 / 32
-    tc_ok = tc_ok && (!(g->lay[c].flags & MFAS_FLAG_MULTILABEL) || g->lay[c].H % 64 == 0);
     for (int l = 0; l < g->lay[c].L; ++l) ragged = ragged || g->lay[c].d_ske[l] % 128 || g->lay[c].d_rgb[l] % 128;
   }
   // Tap widths that are not multiples of the 128-column backward tile (the 64-wide MM-IMDB text tap): only the persistent
   // backward walks a host-built tile list, which is cut at the concat-source boundaries; the grid-indexed backward is not.
-  if (ragged && (batch_max > 64 || getenv("MFAS_BWD") || getenv("MFAS_FWD"))) tc_ok = false;
+  if (ragged && (getenv("MFAS_BWD") || getenv("MFAS_FWD"))) tc_ok = false;
+  // the modality gates ride the persistent kernels (item / tile lists cut at the source boundaries) and the fused chain
+  if (g->any_alphas && stage_override) tc_ok = false;
   const char* env = getenv("MFAS_ENGINE");
   if (env && !strcmp(env, "ffma")) tc_ok = false;
   if (env && !strcmp(env, "tc") && !tc_ok) {
-    int code = fail(MFAS_ERR_UNSUPPORTED, "MFAS_ENGINE=tc needs inner_representation_size 16, 32 or a multiple of 64 (a multiple of 64 with the multi-label head), alphas off, and tap widths %% 128 == 0 unless batch_max <= 64");
+    int code = fail(MFAS_ERR_UNSUPPORTED, "MFAS_ENGINE=tc needs inner_representation_size 16, 32 or a multiple of 64 (16 / 32 and the alpha gates: without the stage-by-stage overrides MFAS_FWD / MFAS_BWD / MFAS_CHAIN / MFAS_HEAD)");
     mfas_group_destroy(g);
     return code;
   }
@@ -460,7 +463,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     for (int c = 0; c < n_cand; ++c) {
       int nf = 0, nb = 0;
       for (int l = 0; l < g->lay[c].L; ++l) {
-        nf += tc_fwd_items(g->lay[c].d_ske[l], g->lay[c].d_rgb[l]);
+        nf += tc_fwd_items_g(g->lay[c].d_ske[l], g->lay[c].d_rgb[l], (g->lay[c].flags & MFAS_FLAG_ALPHAS) != 0);
         nb += tc_bwd_items(g->lay[c].K[l]);
       }
       g->items_fwd = nf > g->items_fwd ? nf : g->items_fwd;
@@ -497,32 +500,54 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     attr((const void*)k_chain_bwd<128>, ChainCfg<128>::SMEM);
     { int nsm = 0; if (e == cudaSuccess) e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device); if (nsm > 0) g->n_sms = nsm; }
     { const char* ce = getenv("MFAS_CHAIN"); if (ce && !strcmp(ce, "ffma")) g->chain = 0; if (ce && !strcmp(ce, "layers")) g->chain = 1; }
-    if (g->Hmax > 128 && g->chain == 2) g->chain = 1;                  // the fused kernel owns one 128-column tile per candidate
-    if (g->multilabel && g->chain == 2) g->chain = 1;                  // the multi-label head is k_head<., true> (see above)
-    g->smem_chain_all = g->smem_chain > 1024 + g->smem_head ? g->smem_chain : 1024 + g->smem_head;
-    if (g->smem_chain_all > 227 * 1024 && g->chain == 2) g->chain = 1;
-    if (g->chain == 2) {
-      attr((const void*)k_chain_all<true, 64, false>, g->smem_chain_all);
-      attr((const void*)k_chain_all<false, 64, false>, g->smem_chain_all);
-      attr((const void*)k_chain_all<true, 128, false>, g->smem_chain_all);
-      attr((const void*)k_chain_all<false, 128, false>, g->smem_chain_all);
-      attr((const void*)k_chain_all<true, 64, true>, g->smem_chain_all);
-      attr((const void*)k_chain_all<false, 64, true>, g->smem_chain_all);
-    }
+    // the fused kernel walks the 128-column tiles of a layer one after the other (inner_repr a power of two up to 256:
+    // its L2 prefetch indexes lines by shifts); inner_repr 192 takes the per-layer chain kernels
+    if ((g->Hmax > 256 || (g->Hmax & (g->Hmax - 1))) && g->chain == 2) g->chain = 1;
     { const char* be = getenv("MFAS_BWD"); if (be && !strcmp(be, "cta")) g->bwd_ws = 0; }
-    if (g->npad != 64) g->bwd_ws = 0;                   // the persistent kernel is sized for batch <= 64 (96 KB operand stage + p/m/v rings)
     // tensor-core head: needs the fused chain (its tiles and TMEM), the persistent backward (the classifier's dW + Adam
     // become one of its tiles) and C <= 64 (one 64-row tile; head_rows' two values per lane)
     g->tchead = g->chain == 2 && g->bwd_ws && g->Cmax <= TC_DLOG_LD;
     { const char* he = getenv("MFAS_HEAD"); if (he && !strcmp(he, "ffma")) g->tchead = false; }
+    // dynamic shared memory of the fused chain: its operand tiles, or -- only with the CUDA-core head inside it -- that head's
+    // tiles if they are larger; ~12 KB of the 227 KB are the kernel's static arrays (descriptor, row state, reductions)
+    g->smem_chain_all = (g->tchead || g->smem_chain > 1024 + g->smem_head) ? g->smem_chain : 1024 + g->smem_head;
+    if (g->smem_chain_all > 214 * 1024 && g->chain == 2) { g->chain = 1; g->tchead = false; }
+    if (g->chain == 2) {
+#define CHAIN_ATTR(ML) \
+      attr((const void*)k_chain_all<true, 64, false, ML>, g->smem_chain_all); attr((const void*)k_chain_all<false, 64, false, ML>, g->smem_chain_all); \
+      attr((const void*)k_chain_all<true, 128, false, ML>, g->smem_chain_all); attr((const void*)k_chain_all<false, 128, false, ML>, g->smem_chain_all); \
+      attr((const void*)k_chain_all<true, 64, true, ML>, g->smem_chain_all); attr((const void*)k_chain_all<false, 64, true, ML>, g->smem_chain_all); \
+      attr((const void*)k_chain_all<true, 128, true, ML>, g->smem_chain_all); attr((const void*)k_chain_all<false, 128, true, ML>, g->smem_chain_all);
+      if (g->multilabel) { CHAIN_ATTR(true) } else { CHAIN_ATTR(false) }
+#undef CHAIN_ATTR
+    }
     if (g->bwd_ws) {
       std::vector<int4> tl;
       g->n_bwd_layer_tiles = build_bwd_tiles(g->lay.data(), n_cand, g->tchead, tl);
       g->n_bwd_tiles = (int)tl.size();
       if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(BwdTile) * tl.size(), &g->bwd_tiles, &g->tiles_bytes);
       g->bwd_tl = std::move(tl);
-      attr((const void*)k_tc_bwd_ws<false>, TC_WS_SMEM);
-      attr((const void*)k_tc_bwd_ws<true>, TC_WS_SMEM);
+      attr((const void*)k_tc_bwd_ws<false, false>, TC_WS_SMEM);
+      attr((const void*)k_tc_bwd_ws<true, false>, TC_WS_SMEM);
+      if (g->any_alphas) {
+        attr((const void*)k_tc_bwd_ws<false, true>, TC_WS_SMEM);
+        attr((const void*)k_tc_bwd_ws<true, true>, TC_WS_SMEM);
+        std::vector<int2> rng((size_t)n_cand * MFAS_MAX_LAYERS, make_int2(0, 0));
+        for (int i = 0; i < g->n_bwd_layer_tiles; ++i) {         // tiles are listed candidate by candidate, layer by layer, feature columns first
+          const int4 t = g->bwd_tl[i];
+          int2& r = rng[(size_t)t.x * MFAS_MAX_LAYERS + t.y];
+          if (t.z < g->lay[t.x].d_ske[t.y] + g->lay[t.x].d_rgb[t.y]) { if (r.y == 0) r.x = i; ++r.y; }
+        }
+        if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(float) * TC_DSP_PER_TILE * g->bwd_tl.size(), &g->dsp_tc, &g->dsp_bytes);
+        if (e == cudaSuccess) e = cudaMemset(g->dsp_tc, 0, sizeof(float) * TC_DSP_PER_TILE * g->bwd_tl.size());
+        if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(int2) * rng.size(), &g->alpha_rng, &g->rng_bytes);
+        if (e == cudaSuccess) e = cudaMemcpy(g->alpha_rng, rng.data(), sizeof(int2) * rng.size(), cudaMemcpyHostToDevice);
+      }
+    }
+    if (g->any_alphas && (!g->bwd_ws || !g->chain)) {
+      int code = fail(MFAS_ERR_UNSUPPORTED, "alpha gates on the tensor-core engine need the persistent backward and the tensor-core chain kernels");
+      mfas_group_destroy(g);
+      return code;
     }
     if (getenv("MFAS_CHAIN_TIMELINE") && e == cudaSuccess) {
       e = pool_alloc_t(device, sizeof(long long) * 16 * n_cand, &g->timeline, &g->tl_bytes);
@@ -533,7 +558,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       int n = 0;
       for (int c = 0; c < n_cand; ++c)
         for (int l = 0; l < g->lay[c].L; ++l)
-          n += tc_fwd_items(g->lay[c].d_ske[l], g->lay[c].d_rgb[l]) * ((g->lay[c].H + 127) / 128);
+          n += tc_fwd_items_g(g->lay[c].d_ske[l], g->lay[c].d_rgb[l], (g->lay[c].flags & MFAS_FLAG_ALPHAS) != 0) * ((g->lay[c].H + 127) / 128);
       g->n_fwd_items = n;
       if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(FwdItem) * n, &g->fwd_items, &g->items_bytes);
       attr((const void*)k_tc_fwd_ws<64, 0>, FwdWs<64, 0>::SMEM);
@@ -550,7 +575,6 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       e = pool_alloc(device, sizeof(float) * (g->ev128 ? g->part_stride_ev : g->part_stride) * n_cand, (void**)&g->part, &g->part_bytes);
     if (g->ev128) {
       if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(FwdItem) * g->n_fwd_items, &g->fwd_items_ev, &g->items_ev_bytes);
-      attr((const void*)k_chain_all<false, 128, true>, g->smem_chain_all);
     }
     { const char* de = getenv("MFAS_TC_DEBUG"); if (de) g->dbg = atoi(de); }
     { const char* le = getenv("MFAS_L2_HINTS"); if (le) g->l2_hints = atoi(le) & 15; }
@@ -659,6 +683,12 @@ static int sync_descriptors(mfas_group* g, cudaStream_t st) {
           r.rows = d.H - t.w < TC_BWD_HT ? d.H - t.w : TC_BWD_HT;
         }
         r.cand = t.x; r.layer = t.y; r.kc0 = t.z; r.h0 = t.w; r.pad1 = 0;
+        r.alpha = nullptr; r.gate = 0; r.slot = (int)i;
+        if ((d.flags & MFAS_FLAG_ALPHAS) && t.y < d.L) {
+          const DLayer& ly = d.layer[t.y];
+          r.alpha = d.p + ly.oalpha;
+          r.gate = t.z < ly.d_ske ? 1 : (t.z < ly.d_ske + ly.d_rgb ? 2 : 0);
+        }
       }
       // pageable source: staged before the call returns
       CUDA_TRY(cudaMemcpyAsync(g->bwd_tiles, recs.data(), sizeof(BwdTile) * recs.size(), cudaMemcpyHostToDevice, st));
@@ -673,11 +703,12 @@ static int sync_descriptors(mfas_group* g, cudaStream_t st) {
         int item0 = 0;
         for (int l = 0; l < d.L; ++l) {
           const DLayer& ly = d.layer[l];
-          const int nkb = (ly.d_ske + ly.d_rgb) >> 5, ns = tc_fwd_items(ly.d_ske, ly.d_rgb);
+          const bool gated = (d.flags & MFAS_FLAG_ALPHAS) != 0;          // items cut at the modality boundary (tc_fwd_items_g)
+          const int ns = tc_fwd_items_g(ly.d_ske, ly.d_rgb, gated);
           for (int sp = 0; sp < ns; ++sp)
             for (int m0 = 0; m0 < d.H; m0 += 128) {
               FwdItem it;
-              tc_fwd_range(nkb, sp, it.kb0, it.kb1);
+              tc_fwd_range_g(ly.d_ske, ly.d_rgb, sp, gated, it.kb0, it.kb1);
               it.W = d.p + ly.oW + (long long)m0 * ly.K;
               it.part_off = (long long)c * g->part_stride + (long long)(item0 + sp) * Hp * g->npad + 4LL * m0;
               it.Hp = Hp; it.pad0 = it.pad1 = it.pad2 = 0;
@@ -766,12 +797,12 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
   for (int c = 0; c < g->n_cand; ++c) keep = keep || g->hc[c].grad != nullptr;
   if (prof) cudaEventRecord(g->prof_ev[1], st);
   if (g->chain == 2 && train == bn_train) {           // the whole serial chain in one launch
-#define CA(T, N, TH) k_chain_all<T, N, TH><<<g->n_cand, ChainCfg<N>::THREADS, g->smem_chain_all, st>>>(g->dc, cache, batch, g->bmax, g->part, g->part_stride, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, ho, terr)
-    if (wide)
-      k_chain_all<false, 128, true><<<g->n_cand, ChainCfg<128>::THREADS, g->smem_chain_all, st>>>(g->dc, cache, batch, 128, g->part, g->part_stride_ev, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, ho, terr);
-    else if (g->tchead) { if (train) CA(true, 64, true); else CA(false, 64, true); }
-    else if (g->npad == 64) { if (train) CA(true, 64, false); else CA(false, 64, false); }
-    else { if (train) CA(true, 128, false); else CA(false, 128, false); }
+#define CA_(T, N, TH, ML, BM, PS) k_chain_all<T, N, TH, ML><<<g->n_cand, ChainCfg<N>::THREADS, g->smem_chain_all, st>>>(g->dc, cache, batch, BM, g->part, PS, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, ho, terr)
+#define CA(T, N, TH) do { if (g->multilabel) CA_(T, N, TH, true, g->bmax, g->part_stride); else CA_(T, N, TH, false, g->bmax, g->part_stride); } while (0)
+    if (wide) { if (g->multilabel) CA_(false, 128, true, true, 128, g->part_stride_ev); else CA_(false, 128, true, false, 128, g->part_stride_ev); }
+    else if (g->npad == 64) { if (g->tchead) { if (train) CA(true, 64, true); else CA(false, 64, true); } else { if (train) CA(true, 64, false); else CA(false, 64, false); } }
+    else { if (g->tchead) { if (train) CA(true, 128, true); else CA(false, 128, true); } else { if (train) CA(true, 128, false); else CA(false, 128, false); } }
+#undef CA_
 #undef CA
     LAUNCH_CHECK(g);
     if (!train) return MFAS_OK;
@@ -826,9 +857,16 @@ static int launch_bwd_stream(mfas_group* g, const DCache& cache, const BatchRef&
   if (g->bwd_ws) {
     const int nt = head_tiles ? g->n_bwd_tiles : g->n_bwd_layer_tiles;
     const int grid = nt < g->n_sms ? nt : g->n_sms;
-    if (keep) k_tc_bwd_ws<true><<<grid, TC_WS_THREADS, TC_WS_SMEM, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, g->bwd_tiles, nt, terr);
-    else k_tc_bwd_ws<false><<<grid, TC_WS_THREADS, TC_WS_SMEM, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, g->bwd_tiles, nt, terr);
+#define BWS(KG, AL) k_tc_bwd_ws<KG, AL><<<grid, TC_WS_THREADS, TC_WS_SMEM, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, g->bwd_tiles, nt, terr, g->dsp_tc)
+    if (g->any_alphas) { if (keep) BWS(true, true); else BWS(false, true); }
+    else { if (keep) BWS(true, false); else BWS(false, false); }
+#undef BWS
     LAUNCH_CHECK(g);
+    if (g->any_alphas) {                                // the gates' own gradient + Adam step, after every use of the old alphas
+      const int per = 256 / MFAS_MAX_LAYERS;
+      k_alpha_step_tc<<<(g->n_cand + per - 1) / per, 256, 0, st>>>(g->dc, g->n_cand, g->alpha_rng, g->dsp_tc, g->adam, step_size, bc2_sqrt);
+      LAUNCH_CHECK(g);
+    }
     return MFAS_OK;
   }
 #define BW(BPV, KG) k_tc_bwd_all<BPV, KG><<<gb, TC_BWD_THREADS, g->smem_tc_bwd, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, terr, g->dbg)

@@ -49,6 +49,34 @@ def precision(dtype):
         yield
     finally:
         F32 = old
+GEMM_SPLITS = 1             # see summation_order() below
+
+
+@contextlib.contextmanager
+def summation_order(splits):
+    """Evaluate the fusion-step products x W^T as ``splits`` partial products over column ranges, added in order (what any
+    split-K GEMM does) -- the same arithmetic in another, equally valid, fp32 summation order.  tests/golden/noise_floor.py
+    uses it to measure how far two correct fp32 implementations of the reference algorithm may drift apart along a trajectory
+    (the rounding of a pre-activation decides e.g. on which side of the ReLU kink it falls)."""
+    global GEMM_SPLITS
+    old, GEMM_SPLITS = GEMM_SPLITS, int(splits)
+    try:
+        yield
+    finally:
+        GEMM_SPLITS = old
+
+
+def _xwt(x, W):
+    if GEMM_SPLITS <= 1:
+        return x @ W.T
+    K = x.shape[1]
+    edges = [K * i // GEMM_SPLITS for i in range(GEMM_SPLITS + 1)]
+    acc = (x[:, edges[0]:edges[1]] @ W[:, edges[0]:edges[1]].T).astype(F32)
+    for a, b in zip(edges[1:-1], edges[2:]):
+        acc = (acc + (x[:, a:b] @ W[:, a:b].T).astype(F32)).astype(F32)
+    return acc
+
+
 D_RGB = (512, 1024, 2048, 2048)            # ntu_searchable.py:292
 BN_EPS = 1e-5                              # torch.nn.BatchNorm1d default
 BN_MOMENTUM = 0.1
@@ -210,7 +238,7 @@ class FusionHead:
             parts = (xs_in, xr_in) if l == 0 else (xs_in, xr_in, h)   # ntu_searchable.py:235-239
             x = np.concatenate(parts, axis=1)
             W, b = s[f"fusion_layers.{l}.0.weight"], s[f"fusion_layers.{l}.0.bias"]
-            z = (x @ W.T + b).astype(F32)
+            z = (_xwt(x, W) + b).astype(F32)
             a = _act(z, act)
             rec = dict(x=x, z=z, a=a, xs=xs, xr=xr, gate=gate)
             out = a

@@ -27,7 +27,7 @@ B = 128
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dry", action="store_true")
-    ap.add_argument("--cands", type=int, default=64)
+    ap.add_argument("--cands", type=int, default=148, help="candidates per GPU (148 = one fused-chain CTA per SM)")
     ap.add_argument("--steps", type=int, default=20)
     a = ap.parse_args()
     peak = 6546.0
@@ -68,6 +68,15 @@ def main():
                 ms = e0.elapsed_time(e1) / a.steps
                 gbs = a.cands * cnt["train_bytes"] / ms / 1e6
                 row.update(engine=g.engine, candidates=a.cands, ms_per_step=ms, achieved_GBs=gbs, peak_GBs=peak, frac=gbs / peak)
+                try:                                            # the three kernels of the step, CUDA events on the launching stream
+                    g.set_profiling(True)
+                    acc = [0.0, 0.0, 0.0]
+                    for i in range(10):
+                        g.train_step(cache, rows[5 + i], lr=1e-3)
+                        acc = [x + y for x, y in zip(acc, g.last_step_ms())]
+                    row["kernel_ms"] = dict(zip(("k_tc_fwd_ws", "k_chain_all", "k_tc_bwd_ws"), [x / 10 for x in acc]))
+                except Exception as ex:
+                    row["kernel_ms"] = str(ex)
                 g.close()
             print(json.dumps(row))
 

@@ -141,3 +141,15 @@ def split_np(cache):
     if cache.logit_rgb is not None:
         d.update(logit_rgb=cache.logit_rgb.numpy(), logit_ske=cache.logit_ske.numpy())
     return d
+
+
+def report_traj(what, err, tol):
+    """Print an achieved trajectory error with its bound (pytest -rP / -s), append it to gpurun_out/traj_errors.txt when that
+    directory exists, and assert it."""
+    line = f"TRAJ {what}: achieved {err:.3e} (bound {tol:.1e})"
+    print(line)
+    log = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(log):
+        with open(os.path.join(log, "traj_errors.txt"), "a") as f:
+            f.write(line + "\n")
+    assert err <= tol, line

@@ -11,13 +11,20 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (D_IMAGE, D_TEXT, GOLDEN_DIR, MMIMDB_CASE, init_states, make_mmimdb_args, sample_tensor,
+from helpers import (D_IMAGE, D_TEXT, GOLDEN_DIR, MMIMDB_CASE, init_states, make_mmimdb_args, report_traj, sample_tensor,
                      split_np_mmimdb)
 from oracle import mfas_oracle as O
 from oracle import mmimdb_oracle as MO
 
+import json
+
 TOL = 1e-4
-TRAJ_LOSS = 1e-2
+# Trajectories (see tests/test_gpu_parity.py): epoch losses at 1e-4, trained weights at relative L2 1e-3, F1 at one borderline
+# sigmoid per epoch -- or 2 x the fp32 band of the reference algorithm itself on that trajectory where that is larger
+# (tests/golden/noise_floor.py, case "mmimdb": candidate 0 of the fixture, three fusion steps trained at eta_max = 1e-2, is
+# chaotic in float32 -- six correct summation orders end 1.3e-2 apart in the dev loss and 0.14 in the weights; candidate 1: 2e-6).
+TRAJ_LOSS, TRAJ_W = 1e-4, 1e-3
+_FLOOR = json.load(open(os.path.join(GOLDEN_DIR, "noise_floor.json")))["cases"]["mmimdb"]
 DEV = "cuda:0"
 WIDTHS = (D_TEXT, D_IMAGE)
 
@@ -25,6 +32,11 @@ WIDTHS = (D_TEXT, D_IMAGE)
 def _rel_l2(a, b):
     a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def _rel_max(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
 def _case():
@@ -67,13 +79,13 @@ def test_oracle_matches_reference_loop():
         orders = lambda ph, e: loaders["train" if ph == "train" else "dev"].order_for_pass(e).numpy()
         best, stats = MO.train_track_f1(head, sched, trs, dvs, cs["B"], orders, cs["epochs"])
         f1s = np.array([s["dev_f1"] for s in stats])
-        assert np.abs(f1s - gold[f"c{ci}/epoch_dev_f1"]).max() <= 0.75 / cs["n_dev"] + 1e-4, (f1s, gold[f"c{ci}/epoch_dev_f1"])
-        assert abs(float(best) - float(gold[f"c{ci}/best_f1"])) <= 0.75 / cs["n_dev"], (best, gold[f"c{ci}/best_f1"])
+        fl = _FLOOR[ci]
+        assert np.abs(f1s - gold[f"c{ci}/epoch_dev_f1"]).max() <= max(1.0 / cs["n_dev"], 2 * fl["dev_f1_diff"]) + 1e-4, (f1s, gold[f"c{ci}/epoch_dev_f1"])
+        assert abs(float(best) - float(gold[f"c{ci}/best_f1"])) <= max(1.0 / cs["n_dev"], 2 * fl["best_f1_diff"]), (best, gold[f"c{ci}/best_f1"])
         for k, v in head.state.items():
             if k.startswith("alphas") or k.endswith("num_batches_tracked") or k.endswith(".bias") or "running" in k:
                 continue
-            # 40 Adam steps at eta_max=1e-2: the sign-like update amplifies rounding, same band as TRAJ_W
-            assert _rel_l2(sample_tensor(v)["sample"], gold[f"c{ci}/final/{k}/sample"]) < 0.25, (ci, k)
+            assert _rel_l2(sample_tensor(v)["sample"], gold[f"c{ci}/final/{k}/sample"]) < max(TRAJ_W, 2 * fl["weights_rel_l2"]), (ci, k)
 
 
 def test_torch_port_matches_reference_fixture():
@@ -228,7 +240,7 @@ def test_gpu_single_step_vs_oracle(H, B, nrows, confs, engine, monkeypatch):
         for k, ref in ograds.items():
             gmax = max(np.abs(ref).max(), 1e-12)
             noise = float(np.abs(ref - g64[k]).max() / gmax)          # what fp32 rounding alone does to this tensor
-            tol = max(TOL, 4 * noise)
+            tol = max(TOL, 6 * noise)      # (NOISE_X of tests/test_gpu_parity.py)
             assert tol < 20 * TOL, (k, noise)
             assert _rel_l2(got[k], g64[k]) < tol, f"c{ci} grad {k}: rel L2 {_rel_l2(got[k], g64[k]):.2e} vs float64 ground truth"
             _close(got[k], g64[k], 3 * tol, f"c{ci} grad {k} vs float64 ground truth", scale=gmax)
@@ -274,16 +286,17 @@ def test_gpu_train_sampled_models_vs_reference_fixture():
                                              torch.device(DEV), return_model=[0])
         st = mm.train_sampled_models.last_stats.numpy()[0]
         assert f1[0].dtype == torch.float64 and f1[0].dim() == 0 and f1[0].device.type == "cpu"
-        slack = max(2.0, 0.03 * cs["n_dev"]) / cs["n_dev"]
-        assert np.abs(st[:, 3] / cs["n_dev"] - gold[f"c{ci}/epoch_dev_f1"]).max() <= slack + 1e-4, (st[:, 3] / cs["n_dev"])
-        assert abs(float(f1[0]) - float(gold[f"c{ci}/best_f1"])) <= slack
+        fl = _FLOOR[ci]
+        slack = max(1.0 / cs["n_dev"], 2 * fl["dev_f1_diff"])
+        report_traj(f"mmimdb c{ci} best dev F1 vs reference fixture", abs(float(f1[0]) - float(gold[f"c{ci}/best_f1"])), max(1.0 / cs["n_dev"], 2 * fl["best_f1_diff"]))
         # against the oracle trajectory: epoch losses
         head = MO.TextImageFusionHead(conf, cs["H"], 23, inits[ci], trs["pos_weight"])
         sched = O.CosineRestartLR(cs["eta_max"], 1e-6, cs["Ti"], 2, cs["n_train"] / cs["B"])
         orders = lambda ph, e: loaders["train" if ph == "train" else "dev"].order_for_pass(e).numpy()
         best, ostats = MO.train_track_f1(head, sched, trs, dvs, cs["B"], orders, cs["epochs"])
-        _close(st[:, 0] / cs["n_train"], [s["train_loss"] for s in ostats], TRAJ_LOSS, f"c{ci} epoch train loss")
-        _close(st[:, 2] / cs["n_dev"], [s["dev_loss"] for s in ostats], 3 * TRAJ_LOSS, f"c{ci} epoch dev loss")
+        report_traj(f"mmimdb c{ci} epoch train loss vs oracle", _rel_max(st[:, 0] / cs["n_train"], [s["train_loss"] for s in ostats]), max(TRAJ_LOSS, 2 * fl["loss_rel"]))
+        report_traj(f"mmimdb c{ci} epoch dev loss vs oracle", _rel_max(st[:, 2] / cs["n_dev"], [s["dev_loss"] for s in ostats]), max(TRAJ_LOSS, 2 * fl["loss_rel"]))
+        report_traj(f"mmimdb c{ci} epoch dev F1 vs reference fixture", float(np.abs(st[:, 3] / cs["n_dev"] - gold[f"c{ci}/epoch_dev_f1"]).max()), slack + 1e-4)
         m = models[0]
         assert not m.training
         sd = m.state_dict()
@@ -293,7 +306,7 @@ def test_gpu_train_sampled_models_vs_reference_fixture():
             for k, v in sd.items():
                 if k.startswith("alphas") or k.endswith("num_batches_tracked") or k.endswith(".bias") or "running" in k:
                     continue
-                assert _rel_l2(sample_tensor(v.cpu().numpy())["sample"], gold[f"c{ci}/final/{k}/sample"]) < 0.25, (ci, k)
+                report_traj(f"mmimdb c{ci} final {k}", _rel_l2(sample_tensor(v.cpu().numpy())["sample"], gold[f"c{ci}/final/{k}/sample"]), max(TRAJ_W, 2 * fl["weights_rel_l2"]))
         # the returned model is rolled back to its best epoch: an eval pass over dev reproduces the best F1
         out = m.native().eval_pass(dev.to(DEV), cs["B"]).cpu().numpy()
         assert abs(out[0, 1] / cs["n_dev"] - float(f1[0])) < 1e-12
@@ -358,5 +371,6 @@ def test_gpu_full_size_properties():
         orders = lambda ph, e: loaders["train" if ph == "train" else "dev"].order_for_pass(ci * 2 + e).numpy()
         best, ostats = MO.train_track_f1(head, sched, trs, dvs, 64, orders, 2)
         assert abs(float(f1s[ci]) - float(best)) < 0.03, (ci, float(f1s[ci]), float(best))
-        _close(st[ci, :, 0] / 15552, [s["train_loss"] for s in ostats], 2 * TRAJ_LOSS, f"c{ci} epoch train loss vs oracle")
-        _close(st[ci, :, 3] / 2608, [s["dev_f1"] for s in ostats], 0.05, f"c{ci} epoch dev F1 vs oracle")
+        report_traj(f"mmimdb full size c{ci} epoch train loss vs oracle", _rel_max(st[ci, :, 0] / 15552, [s["train_loss"] for s in ostats]), 1e-2)
+        report_traj(f"mmimdb full size c{ci} epoch dev F1 vs oracle", _rel_max(st[ci, :, 3] / 2608, [s["dev_f1"] for s in ostats]), 0.05)
+        report_traj(f"mmimdb full size c{ci} best F1 vs oracle", abs(float(f1s[ci]) - float(best)), 0.03)
