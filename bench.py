@@ -11,6 +11,11 @@ step   : one pass of the hot path = one train_run over all candidates of the ran
 value  : whole-job throughput with inputs resident in HBM (CUDA events, max over ranks).
 e2e    : the same metric through the public API `train_sampled_models` with HOST caches: model
          construction, H2D of cache / weights / batch orders and the D2H of the accuracies are timed.
+extras : (default run, outside the `value` timer) the other BASELINE.json configurations, sharded over the N ranks of the run
+         (strong scaling: the job is fixed, candidate j trains on rank j % N): `search256` (north_star's 256-candidate search
+         iteration), `search32` (configs[2]), `mmimdb64` (configs[3]), `depth` (configs[4]: 18 roofline points, 148 candidates
+         per point, points sharded over the ranks) -- each with `value` (device-resident), `e2e` (public API, host buffers) and the
+         per-GPU fraction of the HBM roofline.  `--workload X` makes X the main line instead.
 """
 import argparse
 import json
@@ -65,8 +70,9 @@ def parse():
     ap.add_argument("--cpu-sample-steps", type=int, default=48, help="train steps of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "search32", "search256"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "search32", "search256", "mmimdb64", "depth"],
                     help="cfg2 = BASELINE.json configs[1] (default, the metric's configuration); the others are reported extras")
+    ap.add_argument("--no-extras", action="store_true", help="skip the search256 / search32 / mmimdb64 / depth extras of the default run")
     return ap.parse_args()
 
 
@@ -202,6 +208,280 @@ def run_reference(a):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations, sharded over the ranks of the run (strong scaling)
+# ---------------------------------------------------------------------------------------------------------------------
+class Dist:
+    """rank / world plumbing shared by the measurements (one process per GPU; NCCL when world > 1)."""
+
+    def __init__(self, rank, world, device):
+        self.rank, self.world, self.device = rank, world, device
+
+    def barrier(self):
+        import torch
+        import torch.distributed as td
+        if self.world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        import torch
+        import torch.distributed as td
+        if self.world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=self.device)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather(self, obj):
+        import torch.distributed as td
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        td.all_gather_object(out, obj)
+        return out
+
+    def mine(self, n):
+        return [j for j in range(n) if j % self.world == self.rank]
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def _timed_runs(D, fn, steps, warmup):
+    """`steps` calls of fn() after `warmup`, CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    D.barrier()
+    return D.max_over_ranks(e0.elapsed_time(e1) / 1e3) / max(steps, 1), out
+
+
+def _timed_calls(D, fn, calls, warmup):
+    """Host-timed public-API calls (wall clock, barrier + synchronize on both sides, max over ranks)."""
+    for _ in range(warmup):
+        fn()
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        out = fn()
+    D.barrier()
+    return D.max_over_ranks((time.perf_counter() - t0) / max(calls, 1)), out
+
+
+def extra_search(name, a, D, host_train, host_dev, train_dev, dev_dev):
+    """BASELINE configs[2] (`search32`) / north_star's 256-candidate iteration (`search256`): the job is fixed, its candidates
+    are sharded over the ranks (candidate j -> rank j % N, as train_sampled_models shards them)."""
+    import copy
+    import numpy as np
+    import torch
+    from helpers import make_args
+    import mfas_b200.ntu_searchable as ntu
+    from mfas_b200 import _lib
+    from mfas_b200.cache import FeatureCacheLoader
+    from mfas_b200.engine import CandidateGroup, algorithmic_counts
+    a2 = copy.copy(a)
+    a2.workload = name
+    wl = workload_of(a2, 1)
+    n_total, E, Hw = wl["per_gpu"], wl["E"], wl["H"]
+    confs = wl["confs"](n_total)
+    mine = D.mine(n_total)
+    steps_tr, steps_dv = math.ceil(N_TRAIN / B), math.ceil(N_DEV / B)
+    args = make_args(Hw, B, E, bn=True, drpt=0.0, Ti=1)
+    args.init_on_device = True
+    peak, _ = hbm_peak()
+    cnts = [algorithmic_counts(l_, B) for l_ in CandidateGroup.plan(confs, Hw, C, _lib.FLAG_BN)]
+    job_bytes = sum(E * (steps_tr * c_["train_bytes"] + steps_dv * c_["eval_bytes"]) for c_ in cnts)
+    out = {"workload": wl["desc"].replace(f"{n_total} candidates/GPU", f"{n_total} candidates in all"), "scaling": "strong",
+           "n_candidates": n_total, "n_candidates_per_gpu": len(mine) if D.world == 1 else [len([j for j in range(n_total) if j % D.world == r]) for r in range(D.world)],
+           "epochs": E}
+    # device-resident: this rank's share as one group
+    g = None
+    if mine:
+        g = CandidateGroup([confs[j] for j in mine], Hw, C, _lib.FLAG_BN, D.device, batch_max=B, cand_ids=mine)
+        g.set_adam(0.9, 0.999, 1e-8, 1e-4)
+        ntu.init_on_device(g, 4242, mine)
+        ltr, ldv = FeatureCacheLoader(host_train, B, True, 100), FeatureCacheLoader(host_dev, B, True, 200)
+        ptr = ltr.orders_of([j * E + e for j in mine for e in range(E)], D.device).to(torch.int32).view(len(mine), E, N_TRAIN)
+        pdv = ldv.orders_of([j * E + e for j in mine for e in range(E)], D.device).to(torch.int32).view(len(mine), E, N_DEV)
+        lrs = ntu.cosine_lrs(args, N_TRAIN, E * steps_tr)
+    fn = (lambda: g.train_run(train_dev, dev_dev, ptr, pdv, lrs, E, B)) if mine else (lambda: None)
+    l0 = g.launches if g else 0
+    dt, _ = _timed_runs(D, fn, 2, 2)
+    out["gpu_launches_per_step"] = (g.launches - l0) // 4 if g else 0
+    out["engine"] = g.engine if g else None
+    if g:
+        g.check()
+        g.close()
+    out["value"] = n_total * E / dt
+    out["ms_per_step"] = dt * 1e3
+    out["frac"] = job_bytes / dt / 1e9 / (D.world * peak)            # per-GPU fraction of the HBM roofline over the whole call
+    # end to end through the public API: host caches in (H2D / broadcast inside the call), accuracies out
+    loaders = {"train": FeatureCacheLoader(host_train, B, True, 100), "dev": FeatureCacheLoader(host_dev, B, True, 200)}
+
+    def call():
+        host_train.drop_device_copies(); host_dev.drop_device_copies()
+        return ntu.train_sampled_models(confs, ntu.Searchable_Skeleton_Image_Net, loaders, args, D.device)
+
+    dte, accs = _timed_calls(D, call, 2, 2)
+    out["e2e"] = {"value": n_total * E / dte, "unit": UNIT, "ms_per_call": dte * 1e3, "frac": job_bytes / dte / 1e9 / (D.world * peak),
+                  "h2d_bytes_per_step": int(host_train.nbytes() + host_dev.nbytes()), "d2h_bytes_per_step": int(len(mine) * (E * 4 + 1) * 8),
+                  "init": "device generator keyed by (seed, candidate)", "accs_head": [float(x) for x in accs[:3]]}
+    return out
+
+
+def extra_mmimdb(a, D, n_total=64, E=3, Hm=256, Bm=64):
+    """BASELINE configs[3]: MM-IMDB text+image searchable fusion, 64 two-step candidates x 3 epochs, inner_repr=256, bs=64,
+    synthetic taps at the dataset's size (15552 train / 2608 dev rows), sharded over the ranks."""
+    import numpy as np
+    import torch
+    from helpers import make_mmimdb_args
+    import mfas_b200.mmimdb_searchable as mm
+    import mfas_b200.ntu_searchable as ntu
+    from mfas_b200 import _lib
+    from mfas_b200 import dist as mdist
+    from mfas_b200.engine import CandidateGroup, algorithmic_counts
+    n_tr, n_dv = 15552, 2608
+    host_train, host_dev = mm.synthetic_mmimdb_cache(n_tr, 1).pin(), mm.synthetic_mmimdb_cache(n_dv, 2).pin()
+    train_dev = mdist.broadcast_cache(host_train if D.rank == 0 else None, D.device)
+    dev_dev = mdist.broadcast_cache(host_dev if D.rank == 0 else None, D.device)
+    rows = mm.get_possible_layer_configurations(0)
+    rng = np.random.default_rng(0)
+    confs = [np.array([rows[i] for i in rng.integers(0, len(rows), size=2)]) for _ in range(n_total)]
+    mine = D.mine(n_total)
+    flags = _lib.FLAG_BN | _lib.FLAG_MULTILABEL
+    steps_tr, steps_dv = math.ceil(n_tr / Bm), math.ceil(n_dv / Bm)
+    peak, _ = hbm_peak()
+    cnts = [algorithmic_counts(l_, Bm) for l_ in CandidateGroup.plan(confs, Hm, 23, flags, widths=mm.WIDTHS)]
+    job_bytes = sum(E * (steps_tr * c_["train_bytes"] + steps_dv * c_["eval_bytes"]) for c_ in cnts)
+    args = make_mmimdb_args(Hm, Bm, E, Ti=1)
+    out = {"workload": f"MM-IMDB text+image searchable fusion (BASELINE configs[3]): {n_total} candidates x {E} epochs, inner_repr={Hm}, L=2, "
+                       f"bs={Bm}, {n_tr}/{n_dv} rows", "scaling": "strong", "n_candidates": n_total, "epochs": E,
+           "metric": "candidate-epochs/sec (MM-IMDB fusion, bs=64)"}
+    g = None
+    if mine:
+        g = CandidateGroup([confs[j] for j in mine], Hm, 23, flags, D.device, batch_max=Bm, cand_ids=mine, widths=mm.WIDTHS)
+        g.set_adam(0.9, 0.999, 1e-8, 1e-4)
+        ntu.init_on_device(g, 4243, mine)
+        ltr, ldv = mm.TextImageCacheLoader(host_train, Bm, True, 100), mm.TextImageCacheLoader(host_dev, Bm, True, 200)
+        ptr = ltr.orders_of([j * E + e for j in mine for e in range(E)], D.device).to(torch.int32).view(len(mine), E, n_tr)
+        pdv = ldv.orders_of([j * E + e for j in mine for e in range(E)], D.device).to(torch.int32).view(len(mine), E, n_dv)
+        lrs = ntu.cosine_lrs(args, n_tr, E * steps_tr)
+    fn = (lambda: g.train_run(train_dev, dev_dev, ptr, pdv, lrs, E, Bm)) if mine else (lambda: None)
+    dt, _ = _timed_runs(D, fn, 2, 2)
+    out["engine"] = g.engine if g else None
+    if g:
+        g.check()
+        g.close()
+    out["value"] = n_total * E / dt
+    out["ms_per_step"] = dt * 1e3
+    out["frac"] = job_bytes / dt / 1e9 / (D.world * peak)
+    loaders = {"train": mm.TextImageCacheLoader(host_train, Bm, True, 100), "dev": mm.TextImageCacheLoader(host_dev, Bm, True, 200)}
+
+    def call():
+        host_train.drop_device_copies(); host_dev.drop_device_copies()
+        return mm.train_sampled_models(confs, mm.Searchable_Text_Image_Net, loaders, args, D.device)
+
+    dte, f1s = _timed_calls(D, call, 2, 2)
+    n_params = sum(int(l_.n_params) for l_ in CandidateGroup.plan([confs[j] for j in mine], Hm, 23, flags, widths=mm.WIDTHS))
+    out["e2e"] = {"value": n_total * E / dte, "unit": UNIT, "ms_per_call": dte * 1e3, "frac": job_bytes / dte / 1e9 / (D.world * peak),
+                  "h2d_bytes_per_step": int(host_train.nbytes() + host_dev.nbytes() + 4 * n_params), "d2h_bytes_per_step": int(len(mine) * (E * 4 + 1) * 8),
+                  "init": "host, the constructor's CPU RNG stream", "dev_f1_head": [float(x) for x in f1s[:3]]}
+    return out
+
+
+def extra_depth(a, D, train_dev, cands=148, Bd=128, steps=20):
+    """BASELINE configs[4]: NTU fusion-depth sweep L in 1..6 x inner_repr in {64, 128, 256}, bs=128 -- the roofline fraction of
+    the fused train step at every point (148 candidates per GPU, every candidate its own batch).  The 18 points are sharded
+    over the ranks; every rank measures its points on its own GPU."""
+    import numpy as np
+    import torch
+    from mfas_b200 import _lib
+    from mfas_b200.engine import CandidateGroup, algorithmic_counts, plan_layout
+    peak, _ = hbm_peak()
+    points = [(H_, L_) for H_ in (64, 128, 256) for L_ in range(1, 7)]
+    rows_out = []
+    n_rows = len(train_dev)
+    for idx in D.mine(len(points)):
+        H_, L_ = points[idx]
+        conf = np.array([CONF4[l % 4] for l in range(L_)])
+        cnt = algorithmic_counts(plan_layout(conf, H_, C, _lib.FLAG_BN), Bd)
+        g = CandidateGroup([conf] * cands, H_, C, _lib.FLAG_BN, D.device, batch_max=Bd)
+        g.set_adam(0.9, 0.999, 1e-8, 1e-4)
+        g.params.uniform_(-0.03, 0.03)
+        g.bufs.fill_(1.0)
+        gen = torch.Generator(device=D.device).manual_seed(idx)
+        rws = [torch.randint(0, n_rows, (cands, Bd), device=D.device, generator=gen, dtype=torch.int32) for _ in range(steps + 5)]
+        for i in range(5):
+            g.train_step(train_dev, rws[i], lr=1e-3)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(steps):
+            g.train_step(train_dev, rws[5 + i], lr=1e-3)
+        e1.record()
+        torch.cuda.synchronize()
+        g.check()
+        ms = e0.elapsed_time(e1) / steps
+        gbs = cands * cnt["train_bytes"] / ms / 1e6
+        rows_out.append({"L": L_, "inner_repr": H_, "batch": Bd, "candidates": cands, "engine": g.engine, "train_MB_per_candidate_step": cnt["train_bytes"] / 1e6,
+                         "flop_per_byte": (cnt["fwd_flops"] + cnt["bwd_flops"]) / cnt["train_bytes"], "ms_per_step": ms,
+                         "achieved_GBs": gbs, "frac": gbs / peak, "rank": D.rank})
+        g.close()
+    allrows = sorted([r for part in D.gather(rows_out) for r in part], key=lambda r: (r["inner_repr"], r["L"]))
+    return {"workload": "NTU fusion-depth sweep (BASELINE configs[4]): L in 1..6 x inner_repr in {64,128,256}, rows conf4[l mod 4], bs=128, "
+                        f"{cands} candidates per point, fused train step", "peak_GBs": peak, "points": allrows,
+            "frac_min": min(r["frac"] for r in allrows), "frac_max": max(r["frac"] for r in allrows),
+            "frac_mean": sum(r["frac"] for r in allrows) / len(allrows)}
+
+
+def run_other_main(a, D, saved_stdout):
+    """--workload mmimdb64 | depth as the main line (reported extras of BASELINE configs[3] / configs[4])."""
+    import torch
+    import torch.distributed as td
+    from mfas_b200 import dist as mdist
+    from mfas_b200.cache import synthetic_ntu_cache
+    clocks = ClockSampler(D.device.index or 0)
+    if D.rank == 0:
+        clocks.start()
+    if a.workload == "mmimdb64":
+        r = extra_mmimdb(a, D)
+        line = {"metric": r["metric"], "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "scaling": "strong",
+                "e2e": r["e2e"], "roofline": {"bound": "hbm", "achieved": r["frac"] * hbm_peak()[0], "peak": hbm_peak()[0], "unit": "GB/s",
+                                              "frac": r["frac"], "traffic": None, "kernel": "whole call (train + eval steps), per GPU"},
+                "config": {"workload": r["workload"], "l2": "inputs exceed L2"}, "engine": r["engine"]}
+    else:
+        host = synthetic_ntu_cache(4096, 1).pin() if D.rank == 0 else None
+        r = extra_depth(a, D, mdist.broadcast_cache(host, D.device))
+        line = {"metric": "fused-step HBM GB/s (NTU fusion-depth sweep, bs=128)", "value": sum(p_["achieved_GBs"] for p_ in r["points"]) / len(r["points"]),
+                "unit": "GB/s (mean over the 18 points)", "ms_per_step": sum(p_["ms_per_step"] for p_ in r["points"]), "scaling": "weak", "e2e": None,
+                "roofline": {"bound": "hbm", "achieved": r["frac_mean"] * r["peak_GBs"], "peak": r["peak_GBs"], "unit": "GB/s", "frac": r["frac_mean"],
+                             "traffic": None, "kernel": "fused train step, mean over the sweep"},
+                "config": {"workload": r["workload"], "l2": "inputs exceed L2"}, "points": r["points"]}
+    clk = clocks.stop() if D.rank == 0 else None
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    if D.rank == 0:
+        line.update({"n_gpus": D.world, "steps": a.steps, "warmup": a.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "f32",
+                     "data": "synthetic", "clocks": clk, "gpu_launches": None})
+        print(json.dumps(line))
+    if D.world > 1:
+        td.destroy_process_group()
+
+
 def run_ours(a):
     import numpy as np
     import torch
@@ -227,18 +507,12 @@ def run_ours(a):
         os.dup2(2, 1)
         td.init_process_group("nccl", device_id=device)
     n_gpus = world
+    D = Dist(rank, world, device)
+    barrier, max_over_ranks = D.barrier, D.max_over_ranks
 
-    def barrier():
-        if world > 1:
-            td.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=device)
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-        return float(t.item())
+    if a.workload in ("mmimdb64", "depth"):
+        run_other_main(a, D, saved_stdout)
+        return
 
     wl = workload_of(a, n_gpus)
     M, E, Hw = wl["per_gpu"], wl["E"], wl["H"]
@@ -378,11 +652,11 @@ def run_ours(a):
 
     # ---- e2e: the public API with HOST buffers ---------------------------------------------------
     e2e = None
-    e2e_dev = None
+    e2e_host = None
+    if rank != 0 and (not a.no_e2e or not a.no_extras):       # every rank owns a host copy, as a real multi-process search would
+        host_train = synthetic_ntu_cache(N_TRAIN, 1).pin()
+        host_dev = synthetic_ntu_cache(N_DEV, 2).pin()
     if not a.no_e2e:
-        if rank != 0:       # every rank owns a host copy, as a real multi-process search would
-            host_train = synthetic_ntu_cache(N_TRAIN, 1).pin()
-            host_dev = synthetic_ntu_cache(N_DEV, 2).pin()
         loaders = {"train": FeatureCacheLoader(host_train, B, True, 100), "dev": FeatureCacheLoader(host_dev, B, True, 200)}
         n_params = int(g_n_params)
 
@@ -408,7 +682,7 @@ def run_ours(a):
                 calls.append((time.perf_counter() - tc0) * 1e3)
             barrier()
             dte = max_over_ranks((time.perf_counter() - t0) / n_it)
-            on_dev = bool(getattr(a2, "init_on_device", n_gpus > 1))
+            on_dev = bool(init_on_device)
             h2d = host_train.nbytes() + host_dev.nbytes() + (0 if on_dev else M * n_params * 4)
             return {"value": M * E * n_gpus / dte, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(M * (E * 4 + 1) * 8), "ms_per_step": dte * 1e3, "ms_per_call": calls,
@@ -419,9 +693,25 @@ def run_ours(a):
                            "generation and the accuracy read-back are all inside the timed region",
                     "accs_head": [float(x) for x in accs[:3]]}
 
-        e2e = measure(None)                 # the default drop-in path
-        if n_gpus == 1:
-            e2e_dev = measure(True)         # opt-in args.init_on_device=True (default when sharded over ranks)
+        # the SAME two modes at every N: `e2e` = args.init_on_device=True (initial weights from a device generator keyed by
+        # (seed, candidate): the work per rank does not depend on N); `e2e_host_init` = the reference-compatible constructor
+        # stream (every rank draws the stream of the WHOLE call and keeps its share: that cost grows with N)
+        e2e = measure(True)
+        e2e_host = measure(False)
+
+    extras = None
+    if wl["name"] == "cfg2" and not a.no_extras:
+        extras = {}
+        for nm in ("search256", "search32"):
+            try:
+                extras[nm] = extra_search(nm, a, D, host_train, host_dev, train_dev, dev_dev)
+            except Exception as ex:                      # an extra never takes the main line down
+                extras[nm] = {"error": repr(ex)}
+        for nm, fn in (("mmimdb64", lambda: extra_mmimdb(a, D)), ("depth", lambda: extra_depth(a, D, train_dev))):
+            try:
+                extras[nm] = fn()
+            except Exception as ex:
+                extras[nm] = {"error": repr(ex)}
 
     cpu = None
     gpu_eager = None
@@ -440,7 +730,8 @@ def run_ours(a):
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(a, n_gpus), "clocks": clk, "e2e": e2e, "e2e_device_init": e2e_dev, "gpu_launches": int(launches),
+            "data": "synthetic", "config": workload_config(a, n_gpus), "clocks": clk, "e2e": e2e, "e2e_host_init": e2e_host, "gpu_launches": int(launches),
+            "extras": extras,
             "roofline": roofline, "cpu_baseline": cpu, "reference_gpu_eager": gpu_eager, "finite": finite,
             "hbm_ceiling_cand_epochs_per_s_per_gpu": peak * 1e9 / (steps_tr * cnt["train_bytes"] + steps_dv * cnt["eval_bytes"])}))
     if world > 1:

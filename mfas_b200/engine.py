@@ -127,6 +127,11 @@ class GroupLayout:
 class CandidateGroup(GroupLayout):
     """n candidates with their parameter / Adam / BN arenas resident on one CUDA device."""
 
+    @staticmethod
+    def plan(confs, H, C_out, flags, vid_len_ske=32, widths=None):
+        """The layouts of ``confs`` without creating a group (host only)."""
+        return [plan_layout(c, H, C_out, flags, vid_len_ske, widths) for c in confs]
+
     def __init__(self, confs, H, C_out, flags, device, batch_max, drop_p=0.0, drop_seed=0, cand_ids=None,
                  vid_len_ske=32, keep_grads=False, widths=None):
         device = torch.device(device)

@@ -318,6 +318,24 @@ def init_host_arenas(group, host_p, host_b, slots=None):
         _init_tensors(group, c, fill)
 
 
+class _ShareLayout:
+    """A full call's GroupLayout with its arena offsets remapped for ONE rank's share: candidate ``mine[k]`` of the call sits
+    at candidate k of ``group``; every other candidate shares one scratch slot behind the share (its draws are consumed --
+    the constructor's RNG order is that of the whole call -- and overwritten by the next)."""
+
+    def __init__(self, full, mine, group):
+        self.n, self.layouts, self.slots = full.n, full.layouts, full.slots
+        n_p = int(group.p_off[-1]) if group is not None else 0
+        n_b = int(group.b_off[-1]) if group is not None else 0
+        where = {j: k for k, j in enumerate(mine)}
+        sizes_p = [int(full.p_off[c + 1] - full.p_off[c]) for c in range(full.n)]
+        sizes_b = [int(full.b_off[c + 1] - full.b_off[c]) for c in range(full.n)]
+        self.p_off = np.array([int(group.p_off[where[c]]) if c in where else n_p for c in range(full.n)] + [0], dtype=np.int64)
+        self.b_off = np.array([int(group.b_off[where[c]]) if c in where else n_b for c in range(full.n)] + [0], dtype=np.int64)
+        self.n_p = n_p + max([sizes_p[c] for c in range(full.n) if c not in where], default=0)
+        self.n_b = n_b + max([sizes_b[c] for c in range(full.n) if c not in where], default=0)
+
+
 _STAGING = {}
 
 
@@ -578,9 +596,9 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
         shares = [mdist.shard(len(todo), r, nd) for r in range(nd)]
         full = hp = hb = None
         if not dev_init:
-            full = full_layout()
-            hp, hb = _staging(int(full.p_off[-1]), int(full.b_off[-1]))
-            init_host_arenas(full, hp, hb)
+            remap = _ShareLayout(full_layout(), [], None)
+            hp, hb = _staging(remap.n_p, remap.n_b)
+            init_host_arenas(remap, hp, hb)
         results, errors = [None] * nd, []
 
         def worker(r):
@@ -638,8 +656,8 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
                 # RNG order for EVERY candidate of the call (other ranks' draws are consumed and dropped, so a
                 # candidate gets the same weights wherever it runs), then a single H2D copy.
                 full = g if len(mine) == len(todo) else full_layout()
-                hp, hb = _staging(int(full.p_off[-1]), int(full.b_off[-1]))
                 if full is g:
+                    hp, hb = _staging(int(full.p_off[-1]), int(full.b_off[-1]))
                     # a quarter of the candidates at a time: the H2D copy of one slice overlaps the fill of the next
                     step_c = max(1, (g.n + 3) // 4)
                     for c0 in range(0, g.n, step_c):
@@ -650,10 +668,16 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
                         g.params[pa:pb].copy_(hp[pa:pb], non_blocking=True)
                         g.bufs[ba:bb].copy_(hb[ba:bb], non_blocking=True)
                 else:
-                    init_host_arenas(full, hp, hb)
-                    for k, j in enumerate(mine):
-                        g.params[int(g.p_off[k]):int(g.p_off[k + 1])].copy_(hp[int(full.p_off[j]):int(full.p_off[j + 1])], non_blocking=True)
-                        g.bufs[int(g.b_off[k]):int(g.b_off[k + 1])].copy_(hb[int(full.b_off[j]):int(full.b_off[j + 1])], non_blocking=True)
+                    # a share of the call: this rank's candidates are written where its group's arenas expect them, every
+                    # other candidate's draws land in one scratch slot behind them -- the staging arena stays the size of the
+                    # share (+ one candidate) however many ranks there are, and the upload is one copy per arena
+                    remap = _ShareLayout(full, mine, g)
+                    hp, hb = _staging(remap.n_p, remap.n_b)
+                    init_host_arenas(remap, hp, hb)
+                    g.params.copy_(hp[:int(g.p_off[-1])], non_blocking=True)
+                    g.bufs.copy_(hb[:int(g.b_off[-1])], non_blocking=True)
+                    hp[int(g.p_off[-1]):].zero_()       # the scratch slot: the staging arenas keep zeros wherever no parameter lives
+                    hb[int(g.b_off[-1]):].zero_()
             lap("parameter initialisation + H2D")
             run(mine, g)
             g.close()                       # the driver never sees the models of the direct path: free the workspace now
@@ -662,9 +686,11 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
         elif not dev_init:
             # nothing to train on this rank, but the constructor's draws are consumed all the same: the CPU generators of the
             # ranks stay in lockstep, so the NEXT call still gives a candidate the same weights wherever it runs
-            full = full_layout()
-            hp, hb = _staging(int(full.p_off[-1]), int(full.b_off[-1]))
-            init_host_arenas(full, hp, hb)
+            remap = _ShareLayout(full_layout(), [], None)
+            hp, hb = _staging(remap.n_p, remap.n_b)
+            init_host_arenas(remap, hp, hb)
+            hp.zero_()
+            hb.zero_()
     elif args.weightsharing:               # candidates are chained through state_dict: one at a time
         for j in mine:
             run([j])

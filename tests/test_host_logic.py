@@ -328,3 +328,31 @@ def test_backward_tile_list_covers_every_weight_once_and_never_straddles_a_sourc
                     assert kw > 0 and kw % 16 == 0
                     cover[h0:h0 + 64, kc0:kc0 + kw] += 1
                 assert (cover == 1).all(), (trial, c, l)
+
+
+def test_share_sized_initialisation_equals_the_full_call():
+    """A rank that trains a share of a call draws the constructor's stream for EVERY candidate of the call (so a candidate gets
+    the same weights wherever it runs) but stages only its own: same bytes as the matching slices of a full fill, same
+    generator state afterwards, staging arena of the share's size (+ one scratch candidate)."""
+    import mfas_b200.ntu_searchable as ntu
+    from mfas_b200 import _lib
+    from mfas_b200.engine import GroupLayout
+    confs = [np.array(FOUND_CONFS[4]), np.array([[0, 0, 0]]), np.array(FOUND_CONFS[1][:2]), np.array([[2, 3, 1], [1, 1, 0]]),
+             np.array(FOUND_CONFS[2][:3])]
+    flags = _lib.FLAG_BN | _lib.FLAG_ALPHAS
+    full = GroupLayout(confs, 64, 60, flags)
+    torch.manual_seed(3)
+    hp, hb = torch.zeros(int(full.p_off[-1])), torch.zeros(int(full.b_off[-1]))
+    ntu.init_host_arenas(full, hp, hb)
+    state_full = torch.get_rng_state()
+    for mine in ([0, 2, 4], [1, 3], []):
+        g = GroupLayout([confs[i] for i in mine], 64, 60, flags) if mine else None
+        rm = ntu._ShareLayout(full, mine, g)
+        assert rm.n_p < int(full.p_off[-1])
+        torch.manual_seed(3)
+        p2, b2 = torch.zeros(rm.n_p), torch.zeros(rm.n_b)
+        ntu.init_host_arenas(rm, p2, b2)
+        assert torch.equal(torch.get_rng_state(), state_full)
+        for k, j in enumerate(mine):
+            assert torch.equal(p2[int(g.p_off[k]):int(g.p_off[k + 1])], hp[int(full.p_off[j]):int(full.p_off[j + 1])]), (mine, k)
+            assert torch.equal(b2[int(g.b_off[k]):int(g.b_off[k + 1])], hb[int(full.b_off[j]):int(full.b_off[j + 1])]), (mine, k)
