@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MFAS_ABI_VERSION 3
+#define MFAS_ABI_VERSION 4
 
 #define MFAS_MAX_LAYERS 8     /* fusion steps per candidate (reference max_fusions default 4)   */
 #define MFAS_MAX_BATCH 128    /* rows per batch (BASELINE configs use 8, 64, 128)               */
@@ -159,6 +159,13 @@ int mfas_group_destroy(mfas_group_t g);
 int mfas_release_cached_memory(void);
 int mfas_group_bind(mfas_group_t g, int32_t cand, const mfas_arenas* arenas);
 int mfas_group_set_adam(mfas_group_t g, const mfas_adam_hparams* hp);
+/* Initial weights of every candidate of the group in ONE launch, the distributions of the reference constructor
+ * (ntu_searchable.py:200, :267-282 via nn.Linear.reset_parameters / nn.BatchNorm1d, :202-204): Linear weight and bias
+ * U(-1/sqrt(fan_in), 1/sqrt(fan_in)), BatchNorm weight 1 / bias 0 / running_mean 0 / running_var 1 / num_batches_tracked 0,
+ * alpha N(0, 0.1) -- drawn from a counter-based generator keyed by (seed, candidate id, tensor, element), so a candidate
+ * gets the same weights whichever group / rank / device trains it.  NOT the CPU stream of the reference constructor (for
+ * seed parity with it the caller fills the arenas itself, mfas_host_uniform_fill).  Adam moments are zeroed. */
+int mfas_group_init_params(mfas_group_t g, uint64_t seed, void* stream);
 int mfas_group_num_launches(mfas_group_t g, int64_t* out);   /* kernels launched through g so far */
 /* Which kernels serve this group: 1 = "tc" (tcgen05 tensor cores, 3xTF32; inner_representation_size a
  * multiple of 64), 0 = "ffma" (fp32 CUDA cores; any multiple of 16). Both are sm_100a CUDA in this

@@ -17,7 +17,7 @@ SOURCES = [os.path.join(HERE, "csrc", "mfas_abi.cu"), os.path.join(HERE, "csrc",
 HEADERS = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "kernels_ffma.cuh", "kernels_tc.cuh", "kernels_pool.cuh", "umma.cuh")] + [
     os.path.join(ROOT, "include", "mfas_b200.h")]
 
-ABI_VERSION = 3          # MFAS_ABI_VERSION of include/mfas_b200.h
+ABI_VERSION = 4          # MFAS_ABI_VERSION of include/mfas_b200.h
 MAX_LAYERS, MAX_BATCH, MAX_HIDDEN, MAX_CLASSES, NUM_TAPS = 8, 128, 256, 64, 4
 FLAG_BN, FLAG_DROPOUT, FLAG_ALPHAS, FLAG_MULTITASK, FLAG_MULTILABEL = 1, 2, 4, 8, 16
 ERRORS = {0: "MFAS_OK", -1: "MFAS_ERR_INVALID", -2: "MFAS_ERR_CUDA", -3: "MFAS_ERR_UNSUPPORTED",
@@ -84,6 +84,7 @@ SYMBOLS = {
     "mfas_release_cached_memory": (C.c_int, []),
     "mfas_group_bind": (C.c_int, [_P, C.c_int32, C.POINTER(Arenas)]),
     "mfas_group_set_adam": (C.c_int, [_P, C.POINTER(AdamHParams)]),
+    "mfas_group_init_params": (C.c_int, [_P, C.c_uint64, _P]),
     "mfas_group_num_launches": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "mfas_group_engine": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "mfas_group_status": (C.c_int, [_P]),

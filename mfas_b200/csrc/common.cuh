@@ -139,6 +139,14 @@ __device__ __forceinline__ void adam_update_fast(float g, float& p, float& m, fl
   p = fmaf(-step_size * m, r, p);
 }
 
+// Programmatic dependent launch (the hot kernels of a step are launched with cudaLaunchAttributeProgrammaticStreamSerialization):
+// griddep_launch() lets the NEXT kernel of the stream be scheduled on SMs as this grid's CTAs leave them -- its prologue
+// (barrier init, TMEM allocation, descriptor fetch) then overlaps this grid's tail instead of waiting for a full drain plus a
+// launch; griddep_wait() blocks until the PREVIOUS kernel of the stream has completed and its writes are visible.  Both are
+// no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);

@@ -682,6 +682,46 @@ __global__ void k_best_update(int n_cand, const double* stats, long long stat_st
   else improved[c] = 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Initial weights of a whole group in one launch (mfas_group_init_params): counter-based draws keyed by (seed, candidate id,
+// tensor, element) -- placement independent.  grid = (tiles, candidates); every thread walks the candidate's tensors.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float unit_uniform(uint32_t key, uint32_t i) {          // [0, 1): 24 bits
+  return (float)(mix32(key + i * 0x9E3779B9u) >> 8) * (1.0f / 16777216.0f);
+}
+__global__ void __launch_bounds__(kThreads)
+k_init_params(const DCand* __restrict__ cands, uint32_t seed_lo, uint32_t seed_hi) {
+  const DCand& cd = cands[blockIdx.y];
+  const uint32_t base = mix32(mix32(seed_lo ^ 0xA511E9B3u) + seed_hi * 0x85EBCA6Bu + (uint32_t)cd.cand_id * 0xC2B2AE35u);
+  const long long t0 = (long long)blockIdx.x * kThreads + threadIdx.x, stride = (long long)gridDim.x * kThreads;
+  const bool bn = (cd.flags & MFAS_FLAG_BN) != 0;
+  auto uniform = [&](long long off, long long n, float bound, uint32_t tensor) {
+    const uint32_t key = mix32(base + tensor * 0x27D4EB2Fu);
+    for (long long i = t0; i < n; i += stride) cd.p[off + i] = bound * (2.0f * unit_uniform(key, (uint32_t)i) - 1.0f);
+  };
+  auto fill = [&](float* dst, long long off, long long n, float v) { for (long long i = t0; i < n; i += stride) dst[off + i] = v; };
+  for (int l = 0; l < cd.L; ++l) {
+    const DLayer& ly = cd.layer[l];
+    const float bound = rsqrtf((float)ly.K);                      // kaiming_uniform_(a = sqrt(5)) and the bias bound: both 1 / sqrt(fan_in)
+    uniform(ly.oW, (long long)cd.H * ly.K, bound, 4u * l);
+    uniform(ly.ob, cd.H, bound, 4u * l + 1u);
+    if (bn) {
+      fill(cd.p, ly.og, cd.H, 1.f); fill(cd.p, ly.obe, cd.H, 0.f);
+      fill(cd.bufs, ly.orm, cd.H, 0.f); fill(cd.bufs, ly.orv, cd.H, 1.f);
+      if (t0 == 0) cd.nbt[l] = 0;
+    }
+    if (t0 == 0) {                                                // alpha ~ N(0, 0.1): Box-Muller on two draws
+      const uint32_t key = mix32(base + (4u * l + 2u) * 0x27D4EB2Fu);
+      const float u1 = 1.0f - unit_uniform(key, 0u), u2 = unit_uniform(key, 1u);
+      cd.p[ly.oalpha] = 0.1f * sqrtf(-2.0f * logf(u1)) * cosf(6.2831853071795864f * u2);
+    }
+  }
+  const float cb = rsqrtf((float)cd.H);
+  uniform(cd.oWc, (long long)cd.C * cd.H, cb, 4u * MFAS_MAX_LAYERS);
+  uniform(cd.obc, cd.C, cb, 4u * MFAS_MAX_LAYERS + 1u);
+  for (long long i = t0; i < cd.n_params; i += stride) { cd.m[i] = 0.f; cd.v[i] = 0.f; }
+}
+
 // dir = 0: params -> best (when force or improved[c]);  dir = 1: best -> params
 __global__ void __launch_bounds__(kThreads)
 k_snapshot(const DCand* __restrict__ cands, const int* improved, int force, int dir) {

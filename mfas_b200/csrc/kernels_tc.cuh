@@ -298,6 +298,8 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
+  griddep_launch();
+  griddep_wait();                                                  // the weights come from the previous step's backward stream
   const uint32_t tm = tmem_slot;
   const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   bool ok = true;
@@ -1357,6 +1359,8 @@ k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
   auto stamp = [&]() { if (err.timeline && tid == 0 && stamp_i < 16) err.timeline[cand * 16 + stamp_i] = clock64(); ++stamp_i; };
   stamp();
   chain_ctx_open<NPAD>(cx, smem_raw, &bar, &tmem_slot, &ok_flag);      // (__syncthreads inside: scd is visible)
+  griddep_launch();
+  griddep_wait();                                                      // the partial sums come from the forward stream
   const DCand& cd = scd;
   const int L = cd.L, H = cd.H;
   if (err.timeline) { cx.tl = err.timeline + cand * 16; cx.tl_layer = L > 1 ? 1 : 0; }
@@ -1625,6 +1629,8 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
+  griddep_launch();
+  griddep_wait();                                                  // dz / activations / dlogits come from the chain kernel
   const uint32_t tm = tmem_slot;
   const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   bool ok = true;

@@ -623,6 +623,25 @@ extern "C" int mfas_group_bind(mfas_group_t g, int32_t cand, const mfas_arenas* 
   return MFAS_OK;
 }
 
+static int sync_descriptors(mfas_group* g, cudaStream_t st);
+
+extern "C" int mfas_group_init_params(mfas_group_t g, uint64_t seed, void* stream) {
+  if (!g) return fail(MFAS_ERR_INVALID, "null group");
+  DeviceGuard dg(g->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = sync_descriptors(g, st);
+  if (rc) return rc;
+  long long nmax = 0;
+  for (int c = 0; c < g->n_cand; ++c) nmax = g->lay[c].n_params > nmax ? g->lay[c].n_params : nmax;
+  int tiles = (int)((nmax + kThreads * 8 - 1) / (kThreads * 8));
+  tiles = tiles < 1 ? 1 : (tiles > 64 ? 64 : tiles);
+  k_init_params<<<dim3(tiles, g->n_cand), kThreads, 0, st>>>(g->dc, (uint32_t)seed, (uint32_t)(seed >> 32));
+  ++g->launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MFAS_ERR_CUDA, "k_init_params launch failed: %s", cudaGetErrorString(e));
+  return MFAS_OK;
+}
+
 extern "C" int mfas_group_num_launches(mfas_group_t g, int64_t* out) {
   if (!g || !out) return fail(MFAS_ERR_INVALID, "null argument");
   *out = g->launches;
@@ -764,6 +783,25 @@ static int to_dcache(const mfas_group* g, const mfas_cache_desc* c, DCache* out)
   return MFAS_OK;
 }
 
+// Launch with (or, MFAS_PDL=0, without) programmatic stream serialization: see griddep_wait / griddep_launch in common.cuh.
+// MFAS_PDL: bit 0 = the forward stream, bit 1 = the chain, bit 2 = the backward stream; 0 = plain launches.  Default 3:
+// measured on B200 (profiles/r02i_pdl_ablation.txt) the forward stream and the chain as dependent launches take 3-5 % off
+// the latency-bound steps (32 candidates: 98.7 -> 94 us; eval steps 64 -> 60 us) and nothing off the HBM-bound ones, while
+// the backward stream as a dependent launch LOSES 12 % at 148 candidates (941 -> 1062 us): its CTAs then land on SMs in
+// the order the chain's CTAs leave them instead of in blockIdx order, and neighbouring tiles of the list (which share
+// their x columns through L2) end up on different dies.
+static int pdl_mask() { static const int m = [] { const char* e = getenv("MFAS_PDL"); return e ? atoi(e) : 3; }(); return m; }
+template <class... KArgs, class... Args>
+static void launch_k(int which, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (pdl_mask() & which) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);      // errors surface through cudaGetLastError (LAUNCH_CHECK)
+}
+
 #define LAUNCH_CHECK(g)                                                                       \
   do {                                                                                        \
     ++(g)->launches;                                                                          \
@@ -785,7 +823,7 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
   if (g->fwd_ws) {
     const int grid = g->n_fwd_items < g->n_sms ? g->n_fwd_items : g->n_sms;
     const FwdItem* items = wide ? g->fwd_items_ev : g->fwd_items;
-#define FW(N, X) k_tc_fwd_ws<N, X><<<grid, FwdWs<N, X>::THREADS, FwdWs<N, X>::SMEM, st>>>(items, g->n_fwd_items, cache, batch, g->part, terr)
+#define FW(N, X) launch_k(1, k_tc_fwd_ws<N, X>, dim3(grid), dim3(FwdWs<N, X>::THREADS), FwdWs<N, X>::SMEM, st, items, g->n_fwd_items, cache, batch, g->part, terr)
     if (g->npad == 64 && !wide) { if (g->fwd_xr) FW(64, 1); else FW(64, 0); }
     else { if (g->fwd_xr) FW(128, 1); else FW(128, 0); }
 #undef FW
@@ -797,7 +835,7 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
   for (int c = 0; c < g->n_cand; ++c) keep = keep || g->hc[c].grad != nullptr;
   if (prof) cudaEventRecord(g->prof_ev[1], st);
   if (g->chain == 2 && train == bn_train) {           // the whole serial chain in one launch
-#define CA_(T, N, TH, ML, BM, PS) k_chain_all<T, N, TH, ML><<<g->n_cand, ChainCfg<N>::THREADS, g->smem_chain_all, st>>>(g->dc, cache, batch, BM, g->part, PS, g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, ho, terr)
+#define CA_(T, N, TH, ML, BM, PS) launch_k(2, k_chain_all<T, N, TH, ML>, dim3(g->n_cand), dim3(ChainCfg<N>::THREADS), g->smem_chain_all, st, (const DCand*)g->dc, cache, batch, (int)(BM), (const float*)g->part, (long long)(PS), g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, ho, terr)
 #define CA(T, N, TH) do { if (g->multilabel) CA_(T, N, TH, true, g->bmax, g->part_stride); else CA_(T, N, TH, false, g->bmax, g->part_stride); } while (0)
     if (wide) { if (g->multilabel) CA_(false, 128, true, true, 128, g->part_stride_ev); else CA_(false, 128, true, false, 128, g->part_stride_ev); }
     else if (g->npad == 64) { if (g->tchead) { if (train) CA(true, 64, true); else CA(false, 64, true); } else { if (train) CA(true, 64, false); else CA(false, 64, false); } }
@@ -857,7 +895,7 @@ static int launch_bwd_stream(mfas_group* g, const DCache& cache, const BatchRef&
   if (g->bwd_ws) {
     const int nt = head_tiles ? g->n_bwd_tiles : g->n_bwd_layer_tiles;
     const int grid = nt < g->n_sms ? nt : g->n_sms;
-#define BWS(KG, AL) k_tc_bwd_ws<KG, AL><<<grid, TC_WS_THREADS, TC_WS_SMEM, st>>>(g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, g->bwd_tiles, nt, terr, g->dsp_tc)
+#define BWS(KG, AL) launch_k(4, k_tc_bwd_ws<KG, AL>, dim3(grid), dim3(TC_WS_THREADS), TC_WS_SMEM, st, (const DCand*)g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, (const BwdTile*)g->bwd_tiles, nt, terr, g->dsp_tc)
     if (g->any_alphas) { if (keep) BWS(true, true); else BWS(false, true); }
     else { if (keep) BWS(true, false); else BWS(false, false); }
 #undef BWS

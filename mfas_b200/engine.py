@@ -210,6 +210,11 @@ class CandidateGroup(GroupLayout):
             out[name] = self.view(c, name, arena).detach().cpu().numpy().copy()
         return out
 
+    def init_params(self, seed):
+        """Initial weights of every candidate in one launch, keyed by (seed, candidate id) -- see mfas_group_init_params."""
+        _lib.check(_lib.lib().mfas_group_init_params(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, self._stream()))
+        self.adam_t = 0
+
     def set_adam(self, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-4):
         hp = _lib.AdamHParams(beta1, beta2, eps, weight_decay)
         self.betas = (beta1, beta2)

@@ -350,26 +350,12 @@ def _staging(n_p, n_b):
     return hp[:n_p], hb[:n_b]
 
 
-def init_on_device(group, base_seed, cand_ids):
-    """Same distributions, drawn on the GPU from a generator keyed by (base_seed, candidate id): the
-    result does not depend on which rank / group a candidate lands in.  Not bit-compatible with the
-    reference constructor's CPU stream (use the default host initialisation for seed parity)."""
-    gen = torch.Generator(device=group.device)
-    for c in range(group.n):
-        gen.manual_seed((int(base_seed) * 1000003 + int(cand_ids[c])) & 0x7FFFFFFFFFFFFFFF)
-
-        def fill(name, kind, fan_in, c=c):
-            t = group.view(c, name)
-            if kind in ("kaiming", "uniform"):
-                bound = 1 / math.sqrt(fan_in)
-                t.uniform_(-bound, bound, generator=gen)
-            elif kind == "ones":
-                t.fill_(1.0)
-            elif kind == "zeros":
-                t.zero_()
-            elif kind == "normal":
-                t.normal_(0.0, 0.1, generator=gen)
-        _init_tensors(group, c, fill)
+def init_on_device(group, base_seed, cand_ids=None):
+    """Same distributions as the reference constructor, drawn on the GPU by ONE launch of the library's counter-based
+    generator keyed by (base_seed, candidate id, tensor, element) (mfas_group_init_params; the ids are the ``cand_ids`` the
+    group was created with): the result does not depend on which rank / group / device a candidate lands in.  Not
+    bit-compatible with the reference constructor's CPU stream (use the default host initialisation for seed parity)."""
+    group.init_params(base_seed)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -595,10 +581,10 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
         nd = len(devices)
         shares = [mdist.shard(len(todo), r, nd) for r in range(nd)]
         full = hp = hb = None
-        if not dev_init:
-            remap = _ShareLayout(full_layout(), [], None)
-            hp, hb = _staging(remap.n_p, remap.n_b)
-            init_host_arenas(remap, hp, hb)
+        if not dev_init:                # this process trains every candidate of the call: the whole call is staged once
+            full = full_layout()
+            hp, hb = _staging(int(full.p_off[-1]), int(full.b_off[-1]))
+            init_host_arenas(full, hp, hb)
         results, errors = [None] * nd, []
 
         def worker(r):
