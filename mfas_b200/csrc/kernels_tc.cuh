@@ -19,6 +19,8 @@
 // shared-memory tiles the tensor core reads (umma.cuh).
 // Shapes: H multiple of 64 (<= 256), tap widths multiples of 128, batch <= 128.
 #pragma once
+#include <cuda.h>      // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint, nothing links libcuda)
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -276,9 +278,21 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
 }
 
+// TMA operand staging of the forward stream (default; MFAS_FWD_TMA=0 keeps the cp.async loaders):
+//   W tile  : one cp.async.bulk.tensor.2d per k-block -- box {32 columns, 128 rows} of the work item's own tensor map (base =
+//             first row of the item's 128-row tile, extent = its valid rows, so rows beyond inner_repr arrive as zeros),
+//             SWIZZLE_128B: exactly the K-major operand tile the MMA descriptors describe;
+//   x tile  : tile::gather4 -- four batch rows per instruction from the tap's tensor map (box {32 columns, 1 row}), one
+//             instruction per lane of the loader warp, row indices = the candidate's batch order; rows beyond the batch name
+//             a row outside the tensor and arrive as zeros.
+// All of a stage's copies complete on landed[stage] through complete_tx; the 16 x (NPAD / 4 + 1) address computations and
+// issue slots per k-block that 4 loader warps spent on cp.async become NPAD / 4 + 1 instructions of one warp.
+struct TapMaps { CUtensorMap ske[MFAS_NUM_TAPS], rgb[MFAS_NUM_TAPS]; };      // feature taps of one cache: dims {width, n_rows}, box {32, 1}
+
 template <int NPAD, int XR>
 __global__ void __launch_bounds__((FwdWs<NPAD, XR>::THREADS), 1)
-k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchRef batch, float* part_base, TcErr err) {
+k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchRef batch, float* part_base, TcErr err,
+            const CUtensorMap* __restrict__ wmaps, const __grid_constant__ TapMaps taps, int use_tma) {
   using Cfg = FwdWs<NPAD, XR>;
   constexpr int R = Cfg::RAW, LQ = Cfg::LO;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -290,7 +304,8 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
   const int nrows = batch.n_rows;
   if (warp == 0) umma::tmem_alloc(&tmem_slot, 4 * NPAD);
   if (tid == 32) {
-    for (int i = 0; i < R; ++i) { umma::mbar_init(&landed[i], Cfg::LOADERS); umma::mbar_init(&rawfree[i], 1); }
+    // use_tma: 0 = cp.async loaders, 1 = W tiles through TMA + x through cp.async, 2 = W through TMA + x through tile::gather4
+    for (int i = 0; i < R; ++i) { umma::mbar_init(&landed[i], use_tma == 2 ? 1 : Cfg::LOADERS + (use_tma ? 1 : 0)); umma::mbar_init(&rawfree[i], 1); }
     for (int i = 0; i < LQ; ++i) { umma::mbar_init(&lofull[i], Cfg::CONVERTERS / 32); umma::mbar_init(&lofree[i], 1); }
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 4); }
     umma::fence_mbar_init();
@@ -304,8 +319,54 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
   const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   bool ok = true;
 
-  if (warp < 4) {
-    // ================================ loaders =====================================================
+  if (warp < 4 && use_tma == 2) {
+    // ================================ loader (TMA): warp 0 =========================================
+    if (warp == 0) {
+      const uint32_t s0 = umma::smem_u32(smem);
+      const uint64_t stream_policy = l2_stream_policy((err.l2_hints & 1) != 0);
+      const uint64_t x_policy = (err.l2_hints & 8) ? l2_keep_policy() : (err.l2_hints & 4) ? l2_stream_policy(false) : stream_policy;
+      const int oob_row = (int)cache.n_rows;                       // a row index outside every tap tensor: arrives as zeros
+      auto load_rows = [&](const FwdItem& it, int* rows) {         // lane j gathers batch rows 4j .. 4j+3
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int row = 4 * lane + q;
+          rows[q] = (row < nrows && row < NPAD) ? batch_row(batch, it.cand, row) : oob_row;
+        }
+      };
+      FwdItem cur{}, nxt{};
+      int rows_cur[4] = {0, 0, 0, 0}, rows_nxt[4] = {0, 0, 0, 0};
+      if (n_my > 0) { cur = items[blockIdx.x]; load_rows(cur, rows_cur); }
+      int n = 0;
+      for (int i = 0; i < n_my && ok; ++i) {
+        const int idx = blockIdx.x + i * gridDim.x;
+        if (i + 1 < n_my) { nxt = items[idx + gridDim.x]; load_rows(nxt, rows_nxt); }      // in flight while this item's k-blocks are issued
+        const CUtensorMap* wm = wmaps + idx;
+        const CUtensorMap* sm = &taps.ske[cur.ske_tap];
+        const CUtensorMap* rm = &taps.rgb[cur.rgb_tap];
+        if (lane == 0) umma::tmap_acquire(wm);
+#pragma unroll 1
+        for (int kb = cur.kb0; kb < cur.kb1; ++kb, ++n) {
+          const int sg = n % R;
+          if (n >= R && !umma::mbar_wait(&rawfree[sg], ((n / R) & 1) ^ 1)) { ok = false; break; }
+          const uint32_t a = s0 + sg * Cfg::TILE, b = a + Cfg::A_BYTES;
+          if (lane == 0) {
+            umma::mbar_arrive_expect_tx(&landed[sg], Cfg::TILE);
+            umma::tma_load_2d(a, wm, 32 * kb, 0, &landed[sg], stream_policy);
+          }
+          __syncwarp();
+          if (lane < NPAD / 4) {
+            const bool ske = kb < cur.fs_kb;
+            umma::tma_gather4(b + lane * 512, ske ? sm : rm, 32 * (ske ? kb : kb - cur.fs_kb), rows_cur[0], rows_cur[1], rows_cur[2],
+                              rows_cur[3], &landed[sg], x_policy);
+          }
+        }
+        cur = nxt;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rows_cur[q] = rows_nxt[q];
+      }
+    }
+  } else if (warp < 4) {
+    // ================================ loaders (cp.async) ==========================================
     constexpr int WJ = 8, XJ = NPAD / 16;                          // rows r + 16 j of the W / x tile
     const int r = tid >> 3, c = tid & 7;                           // 16-byte chunk c of the 128-byte row
     const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);   // sw128(r + 16 j, 16 c) = off + 2048 j
@@ -337,6 +398,8 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
       const FwdItem& it = cur;
       const long long wstride = 16LL * it.K;
       const float* wp = it.W + (long long)r * it.K + c * 4;        // &W[m0 + r][4 c]
+      const CUtensorMap* wm = wmaps + (blockIdx.x + i * gridDim.x);
+      if (use_tma && tid == 0) umma::tmap_acquire(wm);
       const float* xs[XJ]; const float* xr[XJ];                    // gathered rows of the two taps, indexed by concat column
 #pragma unroll
       for (int j = 0; j < XJ; ++j) {
@@ -350,8 +413,15 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
         if (n >= R && !umma::mbar_wait(&rawfree[sg], ((n / R) & 1) ^ 1)) { ok = false; break; }
         const uint32_t a = s0 + sg * Cfg::TILE + off, b = a + Cfg::A_BYTES;
         const float* w = wp + 32LL * kb;
+        if (use_tma) {                                             // the W tile: one TMA box, issued by one thread
+          if (tid == 0) {
+            umma::mbar_arrive_expect_tx(&landed[sg], Cfg::A_BYTES);
+            umma::tma_load_2d(s0 + sg * Cfg::TILE, wm, 32 * kb, 0, &landed[sg], stream_policy);
+          }
+        } else {
 #pragma unroll
-        for (int j = 0; j < WJ; ++j) cp_async16_zfill(a + j * 2048, w + j * wstride, r + 16 * j < it.rows_valid, stream_policy);
+          for (int j = 0; j < WJ; ++j) cp_async16_zfill(a + j * 2048, w + j * wstride, r + 16 * j < it.rows_valid, stream_policy);
+        }
         const bool ske = kb < it.fs_kb;
 #pragma unroll
         for (int j = 0; j < XJ; ++j) cp_async16_zfill(b + j * 2048, (ske ? xs[j] : xr[j]) + 32LL * kb, r + 16 * j < nrows, x_policy);

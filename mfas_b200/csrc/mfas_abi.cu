@@ -35,6 +35,32 @@ static int fail(int code, const char* fmt, ...) {
       return fail(MFAS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// ---------------------------------------------------------------------------------------------
+// TMA tensor maps (cuTensorMapEncodeTiled is a driver entry point: fetched at run time, nothing links libcuda)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    cudaGetLastError();
+    return (TmapEncodeFn)p;
+  }();
+  return fn;
+}
+// row-major fp32 matrix [rows][cols] with row stride ld (floats) -> SWIZZLE_128B tiles of {32 columns, box_rows rows}
+static bool encode_tile_map(CUtensorMap* out, const float* base, long long cols, long long rows, long long ld, int box_rows) {
+  TmapEncodeFn enc = tmap_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows}, strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows}, es[2] = {1, 1};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = true;
@@ -253,6 +279,17 @@ struct mfas_group {
   int n_bwd_tiles = 0, n_bwd_layer_tiles = 0, n_sms = 148, bwd_ws = 1;
   FwdItem* fwd_items = nullptr;   // item list of the persistent forward kernel (device), rebuilt when arenas are rebound
   int n_fwd_items = 0, fwd_ws = 1, fwd_xr = 0;
+  CUtensorMap* fwd_wmaps = nullptr; // one tensor map per forward item (its W tile rows), same order as fwd_items (device)
+  size_t wmaps_bytes = 0;
+  int fwd_tma = 1;                 // forward stream operands: 1 = W tiles through TMA (cp.async.bulk.tensor.2d) + gathered x rows through
+                                   // cp.async (default); 2 = x through tile::gather4 as well; 0 = cp.async loaders only (MFAS_FWD_TMA).
+                                   // r02l on B200, 148 cfg2 candidates: forward stream 196 us (0) / 196 us (1) / 259 us (2) -- sixteen
+                                   // 512-byte gather4 requests per k-block are slower than 512 cp.async chunks from 4 warps; the kernel
+                                   // is bound by shared-memory bandwidth (144 KB of traffic per 24 KB k-block), not by the loaders' issue
+  struct TapKey { const float* ske[MFAS_NUM_TAPS]; const float* rgb[MFAS_NUM_TAPS]; long long n_rows, ske_ld[MFAS_NUM_TAPS], rgb_ld[MFAS_NUM_TAPS]; };
+  TapKey tap_key[4];               // small cache of feature-tap tensor maps: train / dev / test caches alternate
+  TapMaps tap_maps[4];
+  int tap_used[4] = {0, 0, 0, 0}, tap_clock = 0;
   FwdItem* fwd_items_ev = nullptr; // the same items with the partial-sum offsets of the 128-row eval layout
   size_t items_ev_bytes = 0;
   bool ev128 = false;             // dev / test passes run 128 rows per step (tc engine, batch <= 64): W is read half as often
@@ -295,6 +332,7 @@ extern "C" int mfas_group_destroy(mfas_group_t g) {
   pool_free(g->device, g->bwd_tiles, g->tiles_bytes);
   pool_free(g->device, g->fwd_items, g->items_bytes);
   pool_free(g->device, g->fwd_items_ev, g->items_ev_bytes);
+  pool_free(g->device, g->fwd_wmaps, g->wmaps_bytes);
   for (auto& ev : g->prof_ev) if (ev) cudaEventDestroy(ev);
   pool_free(g->device, g->tc_err, g->err_bytes);
   pool_free(g->device, g->timeline, g->tl_bytes);
@@ -566,6 +604,9 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       attr((const void*)k_tc_fwd_ws<64, 1>, FwdWs<64, 1>::SMEM);
       attr((const void*)k_tc_fwd_ws<128, 1>, FwdWs<128, 1>::SMEM);
       { const char* xe = getenv("MFAS_FWD_XR"); if (xe) g->fwd_xr = atoi(xe) ? 1 : 0; }
+      { const char* te = getenv("MFAS_FWD_TMA"); if (te) g->fwd_tma = atoi(te) < 0 ? 0 : (atoi(te) > 2 ? 2 : atoi(te)); }
+      if (!tmap_encoder()) g->fwd_tma = 0;
+      if (g->fwd_tma && e == cudaSuccess) e = pool_alloc_t(device, sizeof(CUtensorMap) * n, &g->fwd_wmaps, &g->wmaps_bytes);
     }
     // wide eval: needs the persistent forward (its item list carries the partial-sum offsets) and the tensor-core head
     g->ev128 = g->fwd_ws && g->tchead && g->npad == 64;
@@ -742,6 +783,13 @@ static int sync_descriptors(mfas_group* g, cudaStream_t st) {
       std::stable_sort(its.begin(), its.end(), [](const FwdItem& a, const FwdItem& b) { return a.kb1 - a.kb0 > b.kb1 - b.kb0; });
       if ((int)its.size() != g->n_fwd_items) return fail(MFAS_ERR_INVALID, "internal: forward item count changed");
       CUDA_TRY(cudaMemcpyAsync(g->fwd_items, its.data(), sizeof(FwdItem) * its.size(), cudaMemcpyHostToDevice, st));
+      if (g->fwd_tma) {                                 // the W tile of item i: rows [m0, m0 + rows_valid) of its layer, all K columns
+        std::vector<CUtensorMap> maps(its.size());
+        for (size_t i = 0; i < its.size(); ++i)
+          if (!encode_tile_map(&maps[i], its[i].W, its[i].K, its[i].rows_valid, its[i].K, 128))
+            return fail(MFAS_ERR_CUDA, "cuTensorMapEncodeTiled failed for forward item %zu (K=%d, rows=%d)", i, its[i].K, its[i].rows_valid);
+        CUDA_TRY(cudaMemcpyAsync(g->fwd_wmaps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice, st));
+      }
       if (g->fwd_items_ev) {                            // same items, partial sums laid out for 128 batch rows
         for (FwdItem& it : its) {
           const long long rel = it.part_off - (long long)it.cand * g->part_stride;     // (item index) * Hp * npad + 4 m0
@@ -812,6 +860,37 @@ static void launch_k(int which, void (*kern)(KArgs...), dim3 grid, dim3 block, s
 static int launch_bwd_stream(mfas_group* g, const DCache& cache, const BatchRef& batch, float step_size, float bc2_sqrt,
                              bool keep, bool head_tiles, cudaStream_t st);
 
+// Tensor maps of the 8 feature taps of a cache (tile::gather4 source of the forward stream), cached per (pointers, strides, rows)
+static const TapMaps* tap_maps_of(mfas_group* g, const DCache& c) {
+  mfas_group::TapKey k;
+  memset(&k, 0, sizeof(k));
+  k.n_rows = c.n_rows;
+  for (int t = 0; t < MFAS_NUM_TAPS; ++t) { k.ske[t] = c.ske[t]; k.rgb[t] = c.rgb[t]; k.ske_ld[t] = c.ske_ld[t]; k.rgb_ld[t] = c.rgb_ld[t]; }
+  ++g->tap_clock;
+  int slot = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (g->tap_used[i] && !memcmp(&g->tap_key[i], &k, sizeof(k))) { g->tap_used[i] = g->tap_clock; return &g->tap_maps[i]; }
+    if (g->tap_used[i] < g->tap_used[slot]) slot = i;
+  }
+  // widths: the widest layer that reads a tap decides nothing here -- a tap's tensor spans [n_rows][ld - offset] at most; its
+  // true width is not in the descriptor, and columns past it belong to the next tap of the same matrix, which no item addresses
+  for (int t = 0; t < MFAS_NUM_TAPS; ++t) {
+    long long ws = 0, wr = 0;
+    for (int cnd = 0; cnd < g->n_cand; ++cnd)
+      for (int l = 0; l < g->lay[cnd].L; ++l) {
+        if (g->lay[cnd].conf[l][0] == t) ws = g->lay[cnd].d_ske[l];
+        if (g->lay[cnd].conf[l][1] == t) wr = g->lay[cnd].d_rgb[l];
+      }
+    if (ws == 0) ws = 32;                               // a tap no candidate reads: any valid extent
+    if (wr == 0) wr = 32;
+    if (!encode_tile_map(&g->tap_maps[slot].ske[t], c.ske[t], ws, c.n_rows, c.ske_ld[t], 1)) return nullptr;
+    if (!encode_tile_map(&g->tap_maps[slot].rgb[t], c.rgb[t], wr, c.n_rows, c.rgb_ld[t], 1)) return nullptr;
+  }
+  g->tap_key[slot] = k;
+  g->tap_used[slot] = g->tap_clock;
+  return &g->tap_maps[slot];
+}
+
 // tc engine: one launch covers the feature columns of every layer, small per-layer kernels carry the chain
 static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& batch, bool train, bool bn_train,
                           float step_size, float bc2_sqrt, uint32_t step, const HeadOut& ho, cudaStream_t st) {
@@ -823,7 +902,9 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
   if (g->fwd_ws) {
     const int grid = g->n_fwd_items < g->n_sms ? g->n_fwd_items : g->n_sms;
     const FwdItem* items = wide ? g->fwd_items_ev : g->fwd_items;
-#define FW(N, X) launch_k(1, k_tc_fwd_ws<N, X>, dim3(grid), dim3(FwdWs<N, X>::THREADS), FwdWs<N, X>::SMEM, st, items, g->n_fwd_items, cache, batch, g->part, terr)
+    const TapMaps* tm = g->fwd_tma ? tap_maps_of(g, cache) : &g->tap_maps[0];
+    if (!tm) return fail(MFAS_ERR_CUDA, "cuTensorMapEncodeTiled failed for the feature taps (pointer %p, ld %lld)", (const void*)cache.ske[0], cache.ske_ld[0]);
+#define FW(N, X) launch_k(1, k_tc_fwd_ws<N, X>, dim3(grid), dim3(FwdWs<N, X>::THREADS), FwdWs<N, X>::SMEM, st, items, g->n_fwd_items, cache, batch, g->part, terr, (const CUtensorMap*)g->fwd_wmaps, *tm, g->fwd_tma)
     if (g->npad == 64 && !wide) { if (g->fwd_xr) FW(64, 1); else FW(64, 0); }
     else { if (g->fwd_xr) FW(128, 1); else FW(128, 0); }
 #undef FW

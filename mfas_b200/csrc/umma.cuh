@@ -19,7 +19,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) { return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u); }
 
 // byte offset of (row, byte_in_row) inside a SWIZZLE_128B tile whose base is 1024-byte aligned
-__device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t byte_in_row) {
+__host__ __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t byte_in_row) {
   return row * 128u + ((((byte_in_row >> 4) ^ (row & 7u)) << 4) | (byte_in_row & 15u));
 }
 
@@ -93,6 +93,28 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// ---- TMA (cp.async.bulk.tensor): operand tiles straight from a CUtensorMap into SWIZZLE_128B shared memory -------------
+// The tensor maps live in global memory (one per work item, written by the host): the issuing thread acquires a map through
+// the tensormap proxy once before its first use.
+__device__ __forceinline__ void tmap_acquire(const void* tmap) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
+}
+// this thread arrives on the mbarrier and announces `bytes` of asynchronous-copy traffic that will complete on it
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 2-D box {c0.., c1..} (c0 = innermost coordinate, elements) -> shared memory; out-of-bounds elements arrive as zeros
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap, int c0, int c1, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+               ::"r"(dst_smem), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+// four rows r0..r3 of a 2-D tensor, box-width columns from column c0 -> four consecutive 128-byte rows of shared memory
+__device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const void* tmap, int c0, int r0, int r1, int r2, int r3, uint64_t* bar,
+                                            uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;"
+               ::"r"(dst_smem), "l"(tmap), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
