@@ -531,6 +531,211 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
 }
 
 // ---------------------------------------------------------------------------------------------
+// forward, all layers, inner_repr 16 / 32 (the search default): the same persistent, warp-specialised stream as
+// k_tc_fwd_ws with the product TRANSPOSED -- z[b, h] = sum_k x[b, k] W[h, k]: A = the gathered x tile (M = NPAD batch rows),
+// B = the W tile (N = HN = 16 or 32 rows).  With W as the M operand (k_tc_fwd_ws) 112 or 96 of the 128 MMA rows are zeros,
+// yet every k-block moves the full 24 KB tile six times through shared memory and costs 12 x 32 tensor-pipe cycles (the
+// pipe's floor is max(M, 128) N / 256 cycles per MMA: N = 64 there, N = HN here): search256 on one B200 spent 174 us per
+// step in a forward stream whose bytes take 38 us.  Here a k-block is NPAD x 128 + HN x 128 bytes (10 KB at 64 x 16),
+// 12 x 8 cycles, and the ring holds 12 raw + 6 lo stages instead of 5 + 3.
+//   M = 64: the accumulator row b sits in TMEM lane 32 (b / 16) + b % 16 (tests/cuda/m64_test.cu); M = 128: lane b.
+// Work items, partial-sum layout (part[item][NPAD/4][Hp][4]: element (b, h) at ((b >> 2) Hp + h) 4 + (b & 3)) and the
+// consumers (chain kernels) are unchanged.
+// ---------------------------------------------------------------------------------------------
+template <int NPAD, int HN> struct FwdSmall {
+  static constexpr uint32_t A_BYTES = NPAD * 128, B_BYTES = HN * 128, TILE = A_BYTES + B_BYTES;
+  static constexpr int RAW = (int)(122880 / TILE), LO = (int)(61440 / TILE);
+  static constexpr size_t SMEM = 1024 + (size_t)(RAW + LO) * TILE;
+  static constexpr int LOADERS = 128, CONVERTERS = 256, THREADS = 17 * 32;
+};
+
+template <int NPAD, int HN>
+__global__ void __launch_bounds__((FwdSmall<NPAD, HN>::THREADS), 1)
+k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchRef batch, float* part_base, TcErr err) {
+  using Cfg = FwdSmall<NPAD, HN>;
+  constexpr int R = Cfg::RAW, LQ = Cfg::LO;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = umma::align1024(smem_raw);
+  uint8_t* lo_base = smem + R * Cfg::TILE;
+  __shared__ uint64_t landed[R], rawfree[R], lofull[LQ], lofree[LQ], tfull[2], tempty[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nrows = batch.n_rows;
+  constexpr uint32_t TM_COLS = 4 * HN < 32 ? 32 : 4 * HN;          // two accumulator buffers x (main + correction)
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, TM_COLS);
+  if (tid == 32) {
+    for (int i = 0; i < R; ++i) { umma::mbar_init(&landed[i], Cfg::LOADERS); umma::mbar_init(&rawfree[i], 1); }
+    for (int i = 0; i < LQ; ++i) { umma::mbar_init(&lofull[i], Cfg::CONVERTERS / 32); umma::mbar_init(&lofree[i], 1); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 4); }
+    umma::fence_mbar_init();
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  griddep_launch();
+  griddep_wait();                                                  // the weights come from the previous step's backward stream
+  const uint32_t tm = tmem_slot;
+  const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  bool ok = true;
+
+  if (warp < 4) {
+    // ================================ loaders (cp.async) ==========================================
+    constexpr int XJ = NPAD / 16;                                  // x rows r + 16 j; W rows r + 16 j for j < HN / 16
+    const int r = tid >> 3, c = tid & 7;
+    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);   // sw128(r + 16 j, 16 c) = off + 2048 j
+    const uint32_t s0 = umma::smem_u32(smem);
+    const uint64_t stream_policy = l2_stream_policy((err.l2_hints & 1) != 0);
+    const uint64_t x_policy = (err.l2_hints & 8) ? l2_keep_policy() : (err.l2_hints & 4) ? l2_stream_policy(false) : stream_policy;
+    auto load_rows = [&](const FwdItem& it, int* rows) {
+#pragma unroll
+      for (int j = 0; j < XJ; ++j) {
+        const int row = r + 16 * j;
+        rows[j] = batch_row(batch, it.cand, row < nrows ? row : 0);
+      }
+    };
+    FwdItem cur{}, nxt{};
+    int rows_cur[XJ], rows_nxt[XJ];
+#pragma unroll
+    for (int j = 0; j < XJ; ++j) rows_cur[j] = rows_nxt[j] = 0;
+    if (n_my > 0) { cur = items[blockIdx.x]; load_rows(cur, rows_cur); }
+    if (n_my > 1) nxt = items[blockIdx.x + gridDim.x];
+    int n = 0;
+    for (int i = 0; i < n_my && ok; ++i) {
+      if (i + 1 < n_my) load_rows(nxt, rows_nxt);
+      FwdItem nx2{};
+      if (i + 2 < n_my) nx2 = items[blockIdx.x + (i + 2) * gridDim.x];
+      const FwdItem& it = cur;
+      const long long wstride = 16LL * it.K;
+      const float* wp = it.W + (long long)r * it.K + c * 4;        // &W[r][4 c]
+      const float* xs[XJ]; const float* xr[XJ];
+#pragma unroll
+      for (int j = 0; j < XJ; ++j) {
+        const long long gr = rows_cur[j];
+        xs[j] = cache.ske[it.ske_tap] + gr * cache.ske_ld[it.ske_tap] + c * 4;
+        xr[j] = cache.rgb[it.rgb_tap] + gr * cache.rgb_ld[it.rgb_tap] + c * 4 - 32LL * it.fs_kb;
+      }
+#pragma unroll 1
+      for (int kb = it.kb0; kb < it.kb1; ++kb, ++n) {
+        const int sg = n % R;
+        if (n >= R && !umma::mbar_wait(&rawfree[sg], ((n / R) & 1) ^ 1)) { ok = false; break; }
+        const uint32_t a = s0 + sg * Cfg::TILE + off, b = a + Cfg::A_BYTES;
+        const bool ske = kb < it.fs_kb;
+#pragma unroll
+        for (int j = 0; j < XJ; ++j) cp_async16_zfill(a + j * 2048, (ske ? xs[j] : xr[j]) + 32LL * kb, r + 16 * j < nrows, x_policy);
+        const float* w = wp + 32LL * kb;
+#pragma unroll
+        for (int j = 0; j < HN / 16; ++j) cp_async16_zfill(b + j * 2048, w + j * wstride, r + 16 * j < it.rows_valid, stream_policy);
+        cp_async_arrive_noinc(&landed[sg]);
+      }
+      cur = nxt; nxt = nx2;
+#pragma unroll
+      for (int j = 0; j < XJ; ++j) rows_cur[j] = rows_nxt[j];
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp < 12) {
+    // ================================ converters ==================================================
+    const int ct = tid - 128;
+    constexpr int NCH = (int)(Cfg::TILE / 16);                     // 16-byte chunks of a stage (elementwise: linear order)
+    int total = 0;
+    for (int i = 0; i < n_my; ++i) { const FwdItem& it = items[blockIdx.x + i * gridDim.x]; total += it.kb1 - it.kb0; }
+#pragma unroll 1
+    for (int n = 0; n < total; ++n) {
+      const int sg = n % R, sl = n % LQ;
+      if (!umma::mbar_wait(&landed[sg], (n / R) & 1)) { ok = false; break; }
+      if (n >= LQ && !umma::mbar_wait(&lofree[sl], ((n / LQ) & 1) ^ 1)) { ok = false; break; }
+      const float4* src = reinterpret_cast<const float4*>(smem + sg * Cfg::TILE);
+      float4* dst = reinterpret_cast<float4*>(lo_base + sl * Cfg::TILE);
+#pragma unroll
+      for (int j = 0; j < (NCH + Cfg::CONVERTERS - 1) / Cfg::CONVERTERS; ++j) {
+        const int ch = ct + j * Cfg::CONVERTERS;
+        if (ch < NCH) {
+          const float4 x = src[ch];
+          float4 l;
+          l.x = umma::round_tf32(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
+          l.y = umma::round_tf32(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+          l.z = umma::round_tf32(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
+          l.w = umma::round_tf32(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+          dst[ch] = l;
+        }
+      }
+      umma::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&lofull[sl]);
+    }
+  } else if (warp == 12) {
+    // ================================ MMA issuer ==================================================
+    constexpr uint32_t idesc = umma::idesc_tf32(NPAD, HN, false, false);
+    int n = 0;
+    auto nkb_of = [&](int i) { const FwdItem& it = items[blockIdx.x + i * gridDim.x]; return it.kb1 - it.kb0; };
+    int nkb_next = n_my > 0 ? nkb_of(0) : 0;
+    for (int i = 0; i < n_my && ok; ++i) {
+      const int nkb = nkb_next, tb = i & 1;
+      if (i + 1 < n_my) nkb_next = nkb_of(i + 1);
+      if (!umma::mbar_wait(&tempty[tb], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
+      for (int k = 0; k < nkb; ++k, ++n) {
+        const int sg = n % R, sl = n % LQ;
+        if (!umma::mbar_wait(&lofull[sl], (n / LQ) & 1)) { ok = false; break; }
+        umma::tc_fence_after();
+        if (umma::elect_one()) {
+          const uint32_t a_hi = umma::smem_u32(smem) + sg * Cfg::TILE, b_hi = a_hi + Cfg::A_BYTES;
+          const uint32_t a_lo = umma::smem_u32(lo_base) + sl * Cfg::TILE, b_lo = a_lo + Cfg::A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t adv = ks * 32u;
+            const uint64_t dah = umma::smem_desc(a_hi + adv, 16, 1024), dal = umma::smem_desc(a_lo + adv, 16, 1024);
+            const uint64_t dbh = umma::smem_desc(b_hi + adv, 16, 1024), dbl = umma::smem_desc(b_lo + adv, 16, 1024);
+            const uint32_t acc = (k > 0 || ks > 0) ? 1u : 0u;
+            umma::mma_tf32(tm + tb * 2 * HN, dah, dbh, idesc, acc);               // main accumulator: hi*hi only
+            umma::mma_tf32(tm + tb * 2 * HN + HN, dal, dbh, idesc, acc);          // correction accumulator
+            umma::mma_tf32(tm + tb * 2 * HN + HN, dah, dbl, idesc, 1u);
+          }
+          umma::mma_commit(&rawfree[sg]);
+          umma::mma_commit(&lofree[sl]);
+          if (k == nkb - 1) umma::mma_commit(&tfull[tb]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================ epilogue ====================================================
+    const int q = warp & 3;                                        // TMEM lane quarter this warp may read
+    // batch row of this thread's lane: M = 128 -> lane; M = 64 -> 16 rows in the first 16 lanes of every quarter
+    const int brow = NPAD == 128 ? q * 32 + lane : (lane < 16 ? q * 16 + lane : -1);
+    struct Ep { long long part_off; int rows_valid, Hp; };
+    auto ep_of = [&](int i) { const FwdItem& f = items[blockIdx.x + i * gridDim.x]; return Ep{f.part_off, f.rows_valid, f.Hp}; };
+    Ep ep_next = n_my > 0 ? ep_of(0) : Ep{0, 0, 0};
+    for (int i = 0; i < n_my; ++i) {
+      const Ep it = ep_next;
+      if (i + 1 < n_my) ep_next = ep_of(i + 1);
+      const int tb = i & 1;
+      if (!umma::mbar_wait(&tfull[tb], (i >> 1) & 1)) { ok = false; break; }
+      umma::tc_fence_after();
+      float v[HN], w[HN];
+      if (HN == 16) {
+        umma::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 2 * HN), v);
+        umma::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 2 * HN + HN), w);
+      } else {
+        umma::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 2 * HN), v);
+        umma::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 2 * HN + HN), w);
+      }
+      if (brow >= 0 && brow < nrows) {
+        float* dst = part_base + it.part_off + ((long long)(brow >> 2) * it.Hp) * 4 + (brow & 3);
+#pragma unroll
+        for (int h = 0; h < HN; ++h)
+          if (h < it.rows_valid) dst[h * 4] = v[h] + w[h];
+      }
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&tempty[tb]);
+    }
+  }
+  if (!ok) atomicExch(err.flag, 6);
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_free(tm, TM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
 // forward, one layer: z = (sum of this layer's feature partials, fixed order) + h_{l-1} W[:,hid]^T + b,
 // activation, BatchNorm over the batch (train: batch statistics + running-stat update; eval: running
 // statistics), dropout.  These kernels sit on the serial chain h_0 -> h_1 -> ..., so they are cut fine

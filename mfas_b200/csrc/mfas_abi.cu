@@ -281,6 +281,7 @@ struct mfas_group {
   int n_fwd_items = 0, fwd_ws = 1, fwd_xr = 0;
   CUtensorMap* fwd_wmaps = nullptr; // one tensor map per forward item (its W tile rows), same order as fwd_items (device)
   size_t wmaps_bytes = 0;
+  int fwd_small = 1;               // inner_repr <= 32: the transposed forward stream k_tc_fwd_small (MFAS_FWD_SMALL=0: k_tc_fwd_ws with masked rows)
   int fwd_tma = 1;                 // forward stream operands: 1 = W tiles through TMA (cp.async.bulk.tensor.2d) + gathered x rows through
                                    // cp.async (default); 2 = x through tile::gather4 as well; 0 = cp.async loaders only (MFAS_FWD_TMA).
                                    // r02l on B200, 148 cfg2 candidates: forward stream 196 us (0) / 196 us (1) / 259 us (2) -- sixteen
@@ -604,6 +605,12 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       attr((const void*)k_tc_fwd_ws<64, 1>, FwdWs<64, 1>::SMEM);
       attr((const void*)k_tc_fwd_ws<128, 1>, FwdWs<128, 1>::SMEM);
       { const char* xe = getenv("MFAS_FWD_XR"); if (xe) g->fwd_xr = atoi(xe) ? 1 : 0; }
+      { const char* se = getenv("MFAS_FWD_SMALL"); if (se) g->fwd_small = atoi(se) ? 1 : 0; }
+      if (g->Hmax > 32) g->fwd_small = 0;
+      if (g->fwd_small) {
+        attr((const void*)k_tc_fwd_small<64, 16>, FwdSmall<64, 16>::SMEM); attr((const void*)k_tc_fwd_small<64, 32>, FwdSmall<64, 32>::SMEM);
+        attr((const void*)k_tc_fwd_small<128, 16>, FwdSmall<128, 16>::SMEM); attr((const void*)k_tc_fwd_small<128, 32>, FwdSmall<128, 32>::SMEM);
+      }
       { const char* te = getenv("MFAS_FWD_TMA"); if (te) g->fwd_tma = atoi(te) < 0 ? 0 : (atoi(te) > 2 ? 2 : atoi(te)); }
       if (!tmap_encoder()) g->fwd_tma = 0;
       if (g->fwd_tma && e == cudaSuccess) e = pool_alloc_t(device, sizeof(CUtensorMap) * n, &g->fwd_wmaps, &g->wmaps_bytes);
@@ -905,8 +912,14 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
     const TapMaps* tm = g->fwd_tma ? tap_maps_of(g, cache) : &g->tap_maps[0];
     if (!tm) return fail(MFAS_ERR_CUDA, "cuTensorMapEncodeTiled failed for the feature taps (pointer %p, ld %lld)", (const void*)cache.ske[0], cache.ske_ld[0]);
 #define FW(N, X) launch_k(1, k_tc_fwd_ws<N, X>, dim3(grid), dim3(FwdWs<N, X>::THREADS), FwdWs<N, X>::SMEM, st, items, g->n_fwd_items, cache, batch, g->part, terr, (const CUtensorMap*)g->fwd_wmaps, *tm, g->fwd_tma)
-    if (g->npad == 64 && !wide) { if (g->fwd_xr) FW(64, 1); else FW(64, 0); }
+#define FS(N, HN_) launch_k(1, k_tc_fwd_small<N, HN_>, dim3(grid), dim3(FwdSmall<N, HN_>::THREADS), FwdSmall<N, HN_>::SMEM, st, items, g->n_fwd_items, cache, batch, g->part, terr)
+    if (g->fwd_small) {
+      if (g->npad == 64 && !wide) { if (g->Hmax <= 16) FS(64, 16); else FS(64, 32); }
+      else { if (g->Hmax <= 16) FS(128, 16); else FS(128, 32); }
+    }
+    else if (g->npad == 64 && !wide) { if (g->fwd_xr) FW(64, 1); else FW(64, 0); }
     else { if (g->fwd_xr) FW(128, 1); else FW(128, 0); }
+#undef FS
 #undef FW
   } else if (g->npad == 64) k_tc_fwd_all<64><<<gf, TC_THREADS, g->smem_tc_fwd, st>>>(g->dc, cache, batch, g->part, g->part_stride, terr);
   else k_tc_fwd_all<128><<<gf, TC_THREADS, g->smem_tc_fwd, st>>>(g->dc, cache, batch, g->part, g->part_stride, terr);
