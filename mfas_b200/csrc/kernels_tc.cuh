@@ -2146,6 +2146,293 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
 }
 
 // ---------------------------------------------------------------------------------------------
+// backward, all layers, inner_repr 16 / 32 (the search default): the persistent weight-gradient + Adam stream with the
+// operand staging of the forward stream.  A tile is 128 weight columns x HN rows: its p / m / v bytes are 1/4 or 1/8 of a
+// k_tc_bwd_ws tile, so what is left is the x tile (64 gathered rows x 512 bytes) -- and k_tc_bwd_ws keeps exactly ONE such
+// tile in flight per SM (registers of its stager warps): search256 on one B200 took 5 us per tile, 203 us per step, for bytes
+// that take 75 us.  Here the gathered x rows and the dz slice go global -> shared with cp.async straight into the MN-major
+// operand layout (the raw tile IS the hi operand), three stages deep; converters derive the lo tile; the MMA is N = HN wide:
+//   warps 0-3   loaders    : cp.async into raw stage f % 3                  (rawfree <- MMA; landed -> converters)
+//   warps 4-11  converters : lo = rna_tf32(x - trunc_tf32(x)) into the lo stage       (lofree <- MMA; lofull -> MMA)
+//   warp  12    MMA        : 3 x tcgen05.mma per 8 batch rows, M = 128 columns, N = HN (tfull[t] -> Adam)
+//   warps 13-16 Adam       : one TMEM lane quarter each (32 columns x HN rows); p / m / v through a per-warp cp.async ring
+//                            requested one tile ahead; gradient straight out of TMEM       (tempty[t] -> MMA)
+// Tile list: as k_tc_bwd_ws with row tiles of HN (the classifier's C rows are HN-row tiles h0 = 0, HN, ...).
+// Batches above 64 rows: two passes over the 64-row stage into the same accumulator.
+// ---------------------------------------------------------------------------------------------
+template <int HN> struct BwdSmall {
+  static constexpr int BP = 64, RAW = 3, NB = HN / 8;               // NB: 8-row p / m / v batches per tile and warp = ring slots
+  static constexpr uint32_t A_BLK = BP * 128, A_BYTES = 4 * A_BLK, B_BYTES = BP * 128, TILE = A_BYTES + B_BYTES;
+  static constexpr size_t SMEM = 1024 + (size_t)(RAW + 1) * TILE + 4 * (size_t)NB * WS_SLOT;
+  static constexpr int THREADS = 17 * 32;
+};
+
+template <int HN, bool KEEP_GRAD, bool ALPHA>
+__global__ void __launch_bounds__((BwdSmall<HN>::THREADS), 1)
+k_tc_bwd_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, AdamH adam, float step_size,
+               float bc2_sqrt, const BwdTile* __restrict__ tiles, int n_tiles, TcErr err, float* __restrict__ dsp) {
+  using Cfg = BwdSmall<HN>;
+  constexpr int R = Cfg::RAW, BP = Cfg::BP, NB = Cfg::NB;
+  constexpr uint32_t A_BLK = Cfg::A_BLK, A_BYTES = Cfg::A_BYTES, TILE = Cfg::TILE;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = umma::align1024(smem_raw);
+  uint8_t* lo_base = smem + R * TILE;
+  __shared__ uint64_t landed[R], rawfree[R], lofull, lofree, tfull[2], tempty[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nrows = batch.n_rows;
+  constexpr uint32_t TM_COLS = 2 * HN < 32 ? 32 : 2 * HN;
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, TM_COLS);
+  if (tid == 32) {
+    for (int i = 0; i < R; ++i) { umma::mbar_init(&landed[i], 128); umma::mbar_init(&rawfree[i], 1); }
+    umma::mbar_init(&lofull, 8); umma::mbar_init(&lofree, 1);
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 4); }
+    umma::fence_mbar_init();
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  griddep_launch();
+  griddep_wait();                                                  // dz / activations / dlogits come from the chain kernel
+  const uint32_t tm = tmem_slot;
+  const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int npass = (nrows + BP - 1) / BP, n_fill = n_my * npass;
+  bool ok = true;
+
+  if (warp < 4) {
+    // ================================ loaders =====================================================
+    // warp w moves batch rows w, w + 4, ... of the pass: a row of the x tile is 512 contiguous bytes = one 16-byte chunk per lane
+    struct Desc { const float* src; const float* dz; long long ld; int H, kw, hw, row0; int row[16]; };
+    const uint32_t s0 = umma::smem_u32(smem);
+    const uint64_t x_policy = l2_stream_policy(false);
+    auto fetch_desc = [&](int f, Desc& d) {
+      const int i = npass == 1 ? f : (f >> 1), row0 = npass == 1 ? 0 : (f & 1) * BP;
+      const int4 t = *reinterpret_cast<const int4*>(&tiles[blockIdx.x + i * gridDim.x].cand);   // {cand, layer, kc0, h0}
+      const DCand& cd = cands[t.x];
+      const int H = cd.H, kc0 = t.z;
+      bool gather = true;
+      d.row0 = row0;
+      if (t.y >= cd.L) {                                // the classifier as one more layer: x = h_L, dz = dlogits[:, h0 : h0 + HN]
+        d.src = cd.hid + (long long)(cd.L - 1) * bmax * H + kc0; d.ld = H; gather = false;
+        d.H = TC_DLOG_LD; d.kw = min(TC_BWD_KT, H - kc0); d.hw = min(HN, TC_DLOG_LD - t.w);
+        d.dz = cd.dlog + t.w;
+      } else {
+        const DLayer& ly = cd.layer[t.y];
+        const int fs = ly.d_ske, fr = ly.d_rgb;
+        int seg_end = ly.K;
+        if (kc0 < fs) { d.src = cache.ske[ly.ske_tap] + kc0; d.ld = cache.ske_ld[ly.ske_tap]; seg_end = fs; }
+        else if (kc0 < fs + fr) { d.src = cache.rgb[ly.rgb_tap] + (kc0 - fs); d.ld = cache.rgb_ld[ly.rgb_tap]; seg_end = fs + fr; }
+        else { d.src = cd.hid + (long long)(t.y - 1) * bmax * H + (kc0 - fs - fr); d.ld = H; gather = false; }
+        d.H = H; d.kw = min(TC_BWD_KT, seg_end - kc0); d.hw = min(HN, H - t.w);
+        d.dz = cd.dzs + (long long)t.y * bmax * H + t.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int r = min(row0 + warp + 4 * j, nrows - 1);
+        d.row[j] = gather ? batch_row(batch, t.x, r) : r;
+      }
+    };
+    Desc d{};
+    if (n_fill > 0) fetch_desc(0, d);
+    for (int f = 0; f < n_fill; ++f) {
+      const int sg = f % R;
+      if (f >= R && !umma::mbar_wait(&rawfree[sg], ((f / R) & 1) ^ 1)) { ok = false; break; }
+      const uint32_t a = s0 + sg * TILE, b = a + A_BYTES;
+      const int c4 = lane;                              // x: 16-byte chunk c4 of the row's 512 bytes
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int r = warp + 4 * j;                     // row of the stage
+        // sw128_b32(r, 16 (c4 & 7)) = r 128 + (((c4 & 7) >> 1) ^ (r & 3)) 32 + (c4 & 1) 16
+        const uint32_t dst = a + (uint32_t)(c4 >> 3) * A_BLK + (uint32_t)r * 128u + (uint32_t)(((((c4 & 7) >> 1) ^ (r & 3))) << 5) + (uint32_t)((c4 & 1) << 4);
+        cp_async16_zfill(dst, d.src + (long long)d.row[j] * d.ld + min(c4 * 4, d.kw - 4), d.row0 + r < nrows && c4 * 4 < d.kw, x_policy);
+      }
+      {   // dz slice: 64 rows x HN floats: HN / 4 chunks per row, 64 * HN / 4 chunks over 128 threads
+        constexpr int CPR = HN / 4, PER = 64 * CPR / 128;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+          const int idx = tid + 128 * j, r = idx / CPR, cd4 = idx % CPR;
+          const uint32_t dst = b + (uint32_t)r * 128u + (uint32_t)((((cd4 >> 1) ^ (r & 3))) << 5) + (uint32_t)((cd4 & 1) << 4);
+          cp_async16_zf(dst, d.dz + (long long)min(d.row0 + r, nrows - 1) * d.H + min(cd4 * 4, d.hw - 4), d.row0 + r < nrows && cd4 * 4 < d.hw);
+        }
+      }
+      cp_async_arrive_noinc(&landed[sg]);
+      if (f + 1 < n_fill) fetch_desc(f + 1, d);         // descriptor + gather indices of the next fill while this one flies
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp < 12) {
+    // ================================ converters ==================================================
+    const int ct = tid - 128;
+    constexpr int NCH = (int)(TILE / 16);
+#pragma unroll 1
+    for (int f = 0; f < n_fill; ++f) {
+      const int sg = f % R;
+      if (!umma::mbar_wait(&landed[sg], (f / R) & 1)) { ok = false; break; }
+      if (f >= 1 && !umma::mbar_wait(&lofree, (f & 1) ^ 1)) { ok = false; break; }
+      const float4* src = reinterpret_cast<const float4*>(smem + sg * TILE);
+      float4* dst = reinterpret_cast<float4*>(lo_base);
+#pragma unroll
+      for (int j = 0; j < NCH / 256; ++j) {
+        const float4 x = src[ct + j * 256];
+        float4 l;
+        l.x = umma::round_tf32(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
+        l.y = umma::round_tf32(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+        l.z = umma::round_tf32(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
+        l.w = umma::round_tf32(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+        dst[ct + j * 256] = l;
+      }
+      umma::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&lofull);
+    }
+  } else if (warp == 12) {
+    // ================================ MMA issuer ==================================================
+    constexpr uint32_t idesc = umma::idesc_tf32(128, HN, true, true);
+    for (int f = 0; f < n_fill; ++f) {
+      const int i = npass == 1 ? f : (f >> 1), pass = npass == 1 ? 0 : (f & 1), tb = i & 1, sg = f % R;
+      if (!umma::mbar_wait(&lofull, f & 1)) { ok = false; break; }
+      if (pass == 0 && !umma::mbar_wait(&tempty[tb], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
+      umma::tc_fence_after();
+      if (umma::elect_one()) {
+        const uint32_t a_hi = umma::smem_u32(smem) + sg * TILE, b_hi = a_hi + A_BYTES;
+        const uint32_t a_lo = umma::smem_u32(lo_base), b_lo = a_lo + A_BYTES;
+        const uint32_t dt = tm + tb * HN;
+        const int ksteps = (min(BP, nrows - pass * BP) + 7) >> 3;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t adv = ks * 1024u;               // 8 batch rows = two 512-byte swizzle atoms
+          const uint64_t dah = umma::smem_desc(a_hi + adv, A_BLK, 512, umma::kLayoutSw128Base32);
+          const uint64_t dal = umma::smem_desc(a_lo + adv, A_BLK, 512, umma::kLayoutSw128Base32);
+          const uint64_t dbh = umma::smem_desc(b_hi + adv, A_BLK, 512, umma::kLayoutSw128Base32);
+          const uint64_t dbl = umma::smem_desc(b_lo + adv, A_BLK, 512, umma::kLayoutSw128Base32);
+          umma::mma_tf32(dt, dal, dbh, idesc, (pass > 0 || ks > 0) ? 1u : 0u);
+          umma::mma_tf32(dt, dah, dbl, idesc, 1u);
+          umma::mma_tf32(dt, dah, dbh, idesc, 1u);
+        }
+        umma::mma_commit(&rawfree[sg]);
+        umma::mma_commit(&lofree);
+        if (pass == npass - 1) umma::mma_commit(&tfull[tb]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================ Adam warps ==================================================
+    const int q = warp & 3;                            // TMEM lane quarter this warp may read = 32 weight columns of the tile
+    const int aw = warp - 13;
+    const float inv_bc2 = 1.f / bc2_sqrt;
+    uint8_t* ring = smem + (R + 1) * TILE + (size_t)aw * NB * WS_SLOT;
+    const uint32_t ring_u32 = umma::smem_u32(ring);
+    const int srow = lane >> 3, schunk = lane & 7;
+    const uint64_t stream_policy = l2_stream_policy((err.l2_hints & 2) != 0);
+    struct Tile { float* W; long long K, moff, voff, goff; int rc; float gsc, gsign; int slot; };
+    struct Raw { int4 a, b, c, d; };
+    auto fetch_raw = [&](int i) {
+      const int4* r = reinterpret_cast<const int4*>(&tiles[blockIdx.x + i * gridDim.x]);
+      Raw o; o.a = __ldg(r); o.b = __ldg(r + 1); o.c = __ldg(r + 2);
+      o.d = ALPHA ? __ldg(r + 4) : make_int4(0, 0, 0, 0);
+      return o;
+    };
+    auto open_tile = [&](const Raw& r) {
+      Tile o;
+      const long long Wbits = ((long long)(uint32_t)r.a.y << 32) | (uint32_t)r.a.x;
+      o.moff = ((long long)(uint32_t)r.a.w << 32) | (uint32_t)r.a.z;
+      o.voff = ((long long)(uint32_t)r.b.y << 32) | (uint32_t)r.b.x;
+      o.goff = KEEP_GRAD ? (((long long)(uint32_t)r.b.w << 32) | (uint32_t)r.b.z) : 0;
+      o.K = r.c.x;
+      o.rc = min(HN, max(0, r.c.z)) | (min(32, max(0, r.c.y - q * 32)) << 8);       // valid rows | valid columns of this warp's HN x 32
+      o.W = reinterpret_cast<float*>(Wbits) + q * 32;
+      o.gsc = 1.f; o.gsign = 0.f; o.slot = 0;
+      if (ALPHA && r.d.z) {
+        const float* ap = reinterpret_cast<const float*>(((long long)(uint32_t)r.d.y << 32) | (uint32_t)r.d.x);
+        const float sg = gate_of(__ldg(ap));
+        o.gsc = r.d.z == 1 ? sg : 1.0f - sg;
+        o.gsign = r.d.z == 1 ? 1.f : -1.f;
+        o.slot = r.d.w;
+      }
+      return o;
+    };
+    auto request = [&](const Tile& t, int j) {           // batch j (rows 8j .. 8j+7) of tile t into ring slot j; always commits a group
+      if (t.rc >> 8) {
+        const int rows = t.rc & 255, cols = t.rc >> 8;
+        const uint32_t dst = ring_u32 + j * WS_SLOT + srow * 128 + schunk * 16;
+        const float* w = t.W + (long long)(8 * j + srow) * t.K + schunk * 4;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (8 * j + 4 * u + srow < rows && schunk * 4 < cols) {
+            const float* wu = w + (long long)(4 * u) * t.K;
+            cp_async16(dst + u * 512, wu, stream_policy);
+            cp_async16(dst + 1024 + u * 512, wu + t.moff, stream_policy);
+            cp_async16(dst + 2048 + u * 512, wu + t.voff, stream_policy);
+          }
+        }
+      }
+      cp_async_commit();
+    };
+    Tile cur{}, nxt{};
+    Raw ahead{};
+    if (n_my > 0) {
+      cur = open_tile(fetch_raw(0));
+#pragma unroll
+      for (int j = 0; j < NB; ++j) request(cur, j);
+    }
+    if (n_my > 1) ahead = fetch_raw(1);
+    for (int i = 0; i < n_my; ++i) {
+      const int tb = i & 1;
+      const bool more = i + 1 < n_my;
+      if (more) nxt = open_tile(ahead);
+      if (i + 2 < n_my) ahead = fetch_raw(i + 2);
+      if (!umma::mbar_wait(&tfull[tb], (i >> 1) & 1)) { ok = false; break; }
+      umma::tc_fence_after();
+      float dsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        cp_async_wait<NB - 1>();
+        __syncwarp();
+        float g[8];
+        umma::tmem_ld8(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * HN + 8 * j), g);
+        if (cur.rc >> 8) {
+          const float* sp = reinterpret_cast<const float*>(ring + j * WS_SLOT) + lane;
+          float* w = cur.W + (long long)(8 * j) * cur.K + lane;
+          float p[8], m[8], v[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) { p[r] = sp[r * 32]; m[r] = sp[256 + r * 32]; v[r] = sp[512 + r * 32]; }
+          if (ALPHA) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              if (8 * j + r < (cur.rc & 255) && lane < (cur.rc >> 8)) dsum = fmaf(p[r], g[r], dsum);
+              g[r] *= cur.gsc;
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) adam_update_fast(g[r], p[r], m[r], v[r], adam, step_size, inv_bc2);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            if (8 * j + r < (cur.rc & 255) && lane < (cur.rc >> 8)) {
+              if (KEEP_GRAD) w[cur.goff] = g[r];
+              w[0] = p[r]; w[cur.moff] = m[r]; w[cur.voff] = v[r];
+            }
+            w += cur.K;
+          }
+        }
+        __syncwarp();
+        if (more) request(nxt, j); else cp_async_commit();
+      }
+      if (ALPHA && cur.gsign != 0.f) {
+        dsum = warp_sum(dsum);
+        if (lane == 0) dsp[(long long)cur.slot * TC_DSP_PER_TILE + aw] = cur.gsign * dsum;
+      }
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&tempty[tb]);
+      cur = nxt;
+    }
+    cp_async_wait<0>();
+  }
+  if (!ok) atomicExch(err.flag, 5);
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_free(tm, TM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
 // alpha gates, tensor-core engine: d(alpha_l) = (sum of the per-tile, per-warp partials of k_tc_bwd_ws<., true>, fixed order)
 // * s (1 - s), then Adam (the arithmetic of k_alpha_step).  One thread per (candidate, layer); rng[cand][layer] = {first
 // tile, number of feature-column tiles} of the layer in the tile list.  Launched after the backward stream of every train step.

@@ -216,16 +216,18 @@ extern "C" int mfas_release_cached_memory(void) {
 // a tile reads its x columns from ONE source (a tap narrower than / not a multiple of 128 columns is a short tile) --
 // followed, when the classifier head runs on the tensor core, by the classifier tiles (layer == L).  Returns the number
 // of fusion-layer tiles.  Host only.
-static int build_bwd_tiles(const mfas_layout* lay, int n_cand, bool head_tiles, std::vector<int4>& tl) {
+// ht: rows per tile -- TC_BWD_HT (64) for k_tc_bwd_ws, 16 / 32 for k_tc_bwd_small (whose classifier tiles are cut in ht-row pieces too)
+static int build_bwd_tiles(const mfas_layout* lay, int n_cand, bool head_tiles, std::vector<int4>& tl, int ht = TC_BWD_HT) {
   for (int c = 0; c < n_cand; ++c)
     for (int l = 0; l < lay[c].L; ++l)
       for (int s0 = 0; s0 < lay[c].K[l]; s0 = tc_bwd_seg_end(lay[c].d_ske[l], lay[c].d_rgb[l], lay[c].K[l], s0))
         for (int kc0 = s0; kc0 < tc_bwd_seg_end(lay[c].d_ske[l], lay[c].d_rgb[l], lay[c].K[l], s0); kc0 += TC_BWD_KT)
-          for (int h0 = 0; h0 < lay[c].H; h0 += TC_BWD_HT) tl.push_back(make_int4(c, l, kc0, h0));
+          for (int h0 = 0; h0 < lay[c].H; h0 += ht) tl.push_back(make_int4(c, l, kc0, h0));
   const int n_layer_tiles = (int)tl.size();
   if (head_tiles)                                       // classifier tiles last: a step that ran k_head instead simply stops short of them
     for (int c = 0; c < n_cand; ++c)
-      for (int kc0 = 0; kc0 < lay[c].H; kc0 += TC_BWD_KT) tl.push_back(make_int4(c, lay[c].L, kc0, 0));
+      for (int kc0 = 0; kc0 < lay[c].H; kc0 += TC_BWD_KT)
+        for (int c0 = 0; c0 < (ht < TC_BWD_HT ? lay[c].C : 1); c0 += ht) tl.push_back(make_int4(c, lay[c].L, kc0, c0));
   return n_layer_tiles;
 }
 
@@ -281,6 +283,7 @@ struct mfas_group {
   int n_fwd_items = 0, fwd_ws = 1, fwd_xr = 0;
   CUtensorMap* fwd_wmaps = nullptr; // one tensor map per forward item (its W tile rows), same order as fwd_items (device)
   size_t wmaps_bytes = 0;
+  int bwd_small = 0;               // inner_repr <= 32: the persistent backward k_tc_bwd_small, rows per tile (16 / 32; 0 = k_tc_bwd_ws; MFAS_BWD_SMALL=0)
   int fwd_small = 1;               // inner_repr <= 32: the transposed forward stream k_tc_fwd_small (MFAS_FWD_SMALL=0: k_tc_fwd_ws with masked rows)
   int fwd_tma = 1;                 // forward stream operands: 1 = W tiles through TMA (cp.async.bulk.tensor.2d) + gathered x rows through
                                    // cp.async (default); 2 = x through tile::gather4 as well; 0 = cp.async loaders only (MFAS_FWD_TMA).
@@ -562,7 +565,14 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     }
     if (g->bwd_ws) {
       std::vector<int4> tl;
-      g->n_bwd_layer_tiles = build_bwd_tiles(g->lay.data(), n_cand, g->tchead, tl);
+      { const char* se = getenv("MFAS_BWD_SMALL"); if (g->Hmax <= 32 && g->tchead && !(se && !atoi(se))) g->bwd_small = g->Hmax <= 16 ? 16 : 32; }
+      g->n_bwd_layer_tiles = build_bwd_tiles(g->lay.data(), n_cand, g->tchead, tl, g->bwd_small ? g->bwd_small : TC_BWD_HT);
+      if (g->bwd_small) {
+#define BS_ATTR(HN_) attr((const void*)k_tc_bwd_small<HN_, false, false>, BwdSmall<HN_>::SMEM); attr((const void*)k_tc_bwd_small<HN_, true, false>, BwdSmall<HN_>::SMEM); \
+                     attr((const void*)k_tc_bwd_small<HN_, false, true>, BwdSmall<HN_>::SMEM); attr((const void*)k_tc_bwd_small<HN_, true, true>, BwdSmall<HN_>::SMEM);
+        BS_ATTR(16) BS_ATTR(32)
+#undef BS_ATTR
+      }
       g->n_bwd_tiles = (int)tl.size();
       if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(BwdTile) * tl.size(), &g->bwd_tiles, &g->tiles_bytes);
       g->bwd_tl = std::move(tl);
@@ -739,15 +749,17 @@ static int sync_descriptors(mfas_group* g, cudaStream_t st) {
         BwdTile& r = recs[i];
         r.moff = (long long)(d.m - d.p); r.voff = (long long)(d.v - d.p);
         r.goff = d.grad ? (long long)(d.grad - d.p) : 0;
-        if (t.y >= d.L) {                               // classifier tile (tensor-core head): W_c [C][H], columns t.z..
-          r.W = d.p + d.oWc + t.z;
-          r.K = d.H; r.kw = d.H - t.z < TC_BWD_KT ? d.H - t.z : TC_BWD_KT; r.rows = d.C;
+        const int ht = g->bwd_small ? g->bwd_small : TC_BWD_HT;
+        if (t.y >= d.L) {                               // classifier tile (tensor-core head): W_c [C][H], columns t.z.., rows t.w..
+          r.W = d.p + d.oWc + (long long)t.w * d.H + t.z;
+          r.K = d.H; r.kw = d.H - t.z < TC_BWD_KT ? d.H - t.z : TC_BWD_KT;
+          r.rows = g->bwd_small ? (d.C - t.w < ht ? d.C - t.w : ht) : d.C;
         } else {
           const DLayer& ly = d.layer[t.y];
           r.W = d.p + ly.oW + (long long)t.w * ly.K + t.z;
           const int seg_end = tc_bwd_seg_end(ly.d_ske, ly.d_rgb, ly.K, t.z);
           r.K = ly.K; r.kw = seg_end - t.z < TC_BWD_KT ? seg_end - t.z : TC_BWD_KT;
-          r.rows = d.H - t.w < TC_BWD_HT ? d.H - t.w : TC_BWD_HT;
+          r.rows = d.H - t.w < ht ? d.H - t.w : ht;
         }
         r.cand = t.x; r.layer = t.y; r.kc0 = t.z; r.h0 = t.w; r.pad1 = 0;
         r.alpha = nullptr; r.gate = 0; r.slot = (int)i;
@@ -989,10 +1001,18 @@ static int launch_bwd_stream(mfas_group* g, const DCache& cache, const BatchRef&
   if (g->bwd_ws) {
     const int nt = head_tiles ? g->n_bwd_tiles : g->n_bwd_layer_tiles;
     const int grid = nt < g->n_sms ? nt : g->n_sms;
+#define BSM(HN_, KG, AL) launch_k(4, k_tc_bwd_small<HN_, KG, AL>, dim3(grid), dim3(BwdSmall<HN_>::THREADS), BwdSmall<HN_>::SMEM, st, (const DCand*)g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, (const BwdTile*)g->bwd_tiles, nt, terr, g->dsp_tc)
+#define BSM2(KG, AL) do { if (g->bwd_small == 16) BSM(16, KG, AL); else BSM(32, KG, AL); } while (0)
+    if (g->bwd_small) {
+      if (g->any_alphas) { if (keep) BSM2(true, true); else BSM2(false, true); }
+      else { if (keep) BSM2(true, false); else BSM2(false, false); }
+    } else
 #define BWS(KG, AL) launch_k(4, k_tc_bwd_ws<KG, AL>, dim3(grid), dim3(TC_WS_THREADS), TC_WS_SMEM, st, (const DCand*)g->dc, cache, batch, g->bmax, g->adam, step_size, bc2_sqrt, (const BwdTile*)g->bwd_tiles, nt, terr, g->dsp_tc)
     if (g->any_alphas) { if (keep) BWS(true, true); else BWS(false, true); }
     else { if (keep) BWS(true, false); else BWS(false, false); }
 #undef BWS
+#undef BSM2
+#undef BSM
     LAUNCH_CHECK(g);
     if (g->any_alphas) {                                // the gates' own gradient + Adam step, after every use of the old alphas
       const int per = 256 / MFAS_MAX_LAYERS;

@@ -70,14 +70,15 @@ def _relmax(a, b):
 
 def floor_of(cs, **kw):
     a64, s64, w64 = run(cs, np.float64, **kw)
-    out = [dict(weights_rel_l2=0.0, loss_rel=0.0, train_loss_rel=0.0, dev_loss_rel=0.0, dev_correct_diff=0.0, train_correct_diff=0.0,
-                best_acc_diff=0.0) for _ in cs["confs"]]
+    out = [dict(weights_rel_l2=0.0, vectors_rel_l2=0.0, loss_rel=0.0, train_loss_rel=0.0, dev_loss_rel=0.0, dev_correct_diff=0.0,
+                train_correct_diff=0.0, best_acc_diff=0.0) for _ in cs["confs"]]
     for sp in SPLITS:
         a32, s32, w32 = run(cs, np.float32, splits=sp, **kw)
         for ci, o in enumerate(out):
             col = lambda st, k: [e[k] for e in st[ci]]
             real = dict(
                 weights_rel_l2=max(rel_l2(w32[ci][k], w64[ci][k]) for k in w32[ci] if WEIGHTS(k)),
+                vectors_rel_l2=max(rel_l2(w32[ci][k], w64[ci][k]) for k in w32[ci] if k.endswith(".bias") or "running" in k),
                 train_loss_rel=_relmax(col(s32, "train_loss"), col(s64, "train_loss")),          # the tests' metric: max |diff| / max |ref|
                 dev_loss_rel=_relmax(col(s32, "dev_loss"), col(s64, "dev_loss")),
                 dev_correct_diff=float(np.abs(np.array(col(s32, "dev_acc")) - np.array(col(s64, "dev_acc"))).max() * cs["n_dev"]),

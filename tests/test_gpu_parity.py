@@ -47,6 +47,13 @@ def _loss_tol(case, ci, key=None):
     return max(TRAJ_LOSS, 2.0 * _FLOOR[case][ci]["loss_rel"])
 
 
+def _w_tol(case, ci, vec=False):
+    """TRAJ_W (TRAJ_V for the near-zero vectors), or 2 x the measured fp32 band of the reference algorithm on this trajectory if
+    that is larger -- one candidate: wsh c3, whose step-1 weights end 3.2e-2 apart between correct fp32 summation orders (a unit
+    whose gradient is ~0 moves by +-lr per step under Adam: tests/golden/noise_floor.json)."""
+    return max(TRAJ_V if vec else TRAJ_W, 2.0 * _FLOOR[case][ci]["vectors_rel_l2" if vec else "weights_rel_l2"])
+
+
 _report = report_traj
 
 
@@ -268,7 +275,7 @@ def test_train_sampled_models_vs_reference_fixture(name):
                 continue
             fx = gold[f"c{ci}/final/{k}/sample"]
             vec = k.endswith(".bias") or "running" in k   # near-zero vectors (biases start at +-1/sqrt(K), BN shifts at 0): looser, reported
-            _report(f"{name} c{ci} final {k}", _rel_l2(sample_tensor(v.cpu().numpy())["sample"], fx), TRAJ_V if vec else TRAJ_W)
+            _report(f"{name} c{ci} final {k}", _rel_l2(sample_tensor(v.cpu().numpy())["sample"], fx), _w_tol(name, ci, vec))
         # num_batches_tracked follows the rollback too
         if float(gold[f"c{ci}/best_acc"]) > 0:
             k = "fusion_layers.0.2.num_batches_tracked"
@@ -308,7 +315,7 @@ def test_run_vs_oracle_trajectory_cfg2_shapes():
         if k.endswith("num_batches_tracked") or k.startswith("alphas"):
             continue
         vec = k.endswith(".bias") or "running" in k
-        _report(f"traj_cfg2 rolled-back {k}", _rel_l2(got[k], ref), TRAJ_V if vec else TRAJ_W)
+        _report(f"traj_cfg2 rolled-back {k}", _rel_l2(got[k], ref), _w_tol("traj_cfg2", 0, vec))
     # (The Adam moments after the last step are not compared along a free trajectory: six correct fp32 summation orders of the
     #  oracle end 2e-2 .. 1.3e-1 (exp_avg) and 2e-3 .. 3.6e-2 (exp_avg_sq) apart in relative L2 on this very run -- a gradient
     #  EMA over ten steps follows every ReLU flip.  They are held bitwise by test_train_run_equals_train_step_driven_with_the_
@@ -779,13 +786,14 @@ def test_weightsharing_vs_reference_fixture(capsys):
                 assert int(v) == int(gold[f"c{ci}/final/{k}/sample"][0]), (ci, k)          # the counter is shared with the layer (BatchNorm buffer)
                 continue
             vec = k.endswith(".bias") or "running" in k
-            _report(f"wsh c{ci} final {k}", _rel_l2(sample_tensor(v.cpu().numpy())["sample"], gold[f"c{ci}/final/{k}/sample"]), TRAJ_V if vec else TRAJ_W)
+            _report(f"wsh c{ci} final {k}", _rel_l2(sample_tensor(v.cpu().numpy())["sample"], gold[f"c{ci}/final/{k}/sample"]), _w_tol(name, ci, vec))
     for key, sd in shared.items():
         for k, v in sd.items():
             if k.endswith("num_batches_tracked"):
                 assert int(v) == int(gold[f"shared/{key}/{k}/sample"][0]), (key, k)
             elif k.endswith("weight"):
-                _report(f"wsh shared['{key}']['{k}']", _rel_l2(sample_tensor(v.cpu().numpy())["sample"], gold[f"shared/{key}/{k}/sample"]), TRAJ_W)
+                _report(f"wsh shared['{key}']['{k}']", _rel_l2(sample_tensor(v.cpu().numpy())["sample"], gold[f"shared/{key}/{k}/sample"]),
+                        max(_w_tol(name, ci) for ci in range(len(confs))))
 
 
 @pytest.mark.parametrize("H,B,L", [(64, 128, 5), (128, 128, 6), (256, 128, 6), (128, 64, 5), (16, 64, 6)])
