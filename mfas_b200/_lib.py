@@ -12,7 +12,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "_mfas_b200.so")
+# MFAS_LIB_PATH: another build of the SAME sources (profiles/run_gpu_sanitize.sh: barrier-wait bounds raised for compute-sanitizer)
+LIB_PATH = os.environ.get("MFAS_LIB_PATH") or os.path.join(HERE, "_mfas_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "mfas_abi.cu"), os.path.join(HERE, "csrc", "host_init.cpp")]
 HEADERS = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "kernels_ffma.cuh", "kernels_tc.cuh", "kernels_pool.cuh", "umma.cuh")] + [
     os.path.join(ROOT, "include", "mfas_b200.h")]

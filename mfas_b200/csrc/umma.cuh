@@ -120,12 +120,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// bounded wait (~2 s of SM clock at most); returns false if the phase never completed
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t max_spins = 1u << 24) {
+// bounded wait (~2 s of SM clock at most); returns false if the phase never completed.  Under compute-sanitizer every
+// instrumented access is orders of magnitude slower: profiles/run_gpu_sanitize.sh builds the library with both bounds raised.
+#ifndef MFAS_WAIT_SPINS
+#define MFAS_WAIT_SPINS (1u << 24)
+#endif
+#ifndef MFAS_WAIT_CYCLES
+#define MFAS_WAIT_CYCLES 4000000000LL
+#endif
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t max_spins = MFAS_WAIT_SPINS) {
   const uint32_t a = smem_u32(bar);
   const long long t0 = clock64();
   for (uint32_t i = 0; i < max_spins; ++i) {
-    if ((i & 1023u) == 1023u && clock64() - t0 > 4000000000LL) return false;
+    if ((i & 1023u) == 1023u && clock64() - t0 > MFAS_WAIT_CYCLES) return false;
     uint32_t done;
     asm volatile(
         "{\n\t"

@@ -30,8 +30,8 @@ import torch
 from . import _lib
 from .cache import FeatureCache, FeatureCacheLoader
 from .engine import CandidateGroup, GroupLayout, flags_from_args
-from .ntu_searchable import (Searchable_Skeleton_Image_Net, _feature_cache_of, _reserve_passes, _staging, cosine_lrs,
-                             get_central_states, init_host_arenas, pass_orders, set_central_states)
+from .ntu_searchable import (Searchable_Skeleton_Image_Net, TrainerSpec, _feature_cache_of, _reserve_passes, cosine_lrs,
+                             get_central_states, pass_orders, set_central_states, train_sampled)
 from .scheduler import is_per_batch_cosine
 
 D_TEXT = (64, 128)
@@ -174,6 +174,36 @@ def _final_f1(best):
     return 0.0 if b != b else b
 
 
+class _MMIMDBSpec(TrainerSpec):
+    widths = WIDTHS
+
+    def cache_of(self, loader, what):
+        return _multilabel_cache_of(loader, what)
+
+    def flags(self, args):
+        return _flags(args)
+
+    def check(self, args, flags, preaccuracies):
+        if flags & _lib.FLAG_MULTITASK:
+            raise ValueError("the MM-IMDB head has no multitask variant")
+
+    def best_init(self, preaccuracies, idx):
+        return float(preaccuracies[idx]) if preaccuracies else 0.0          # init_f1=preaccuracies[idx], ntu_searchable.py:88
+
+    def result(self, best):
+        return _final_f1(best)
+
+    def load_backbones(self, rmode, args):
+        pass                                                               # cached taps: there are no backbones to load
+
+    def log_epochs(self, stats, n_train, n_dev):
+        for e in range(stats.shape[0]):                                    # train_searchable/mmimdb.py:102-103
+            print('epoch #{} {} F1: {:.4f} '.format(e, 'dev', float(stats[e, 3]) / n_dev))
+
+    def vid_len(self, args):
+        return 32
+
+
 def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
                          args, device,
                          return_model=[], premodels=[], preaccuracies=[],
@@ -182,100 +212,14 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
     """Train every sampled configuration; returns its best dev F1-samples, in input order (and the models when
     ``return_model``).  Signature of /root/reference/models/search/ntu_searchable.py:23-27; recipe of that function with
     the MM-IMDB loop: Adam(lr=eta_max, weight_decay=1e-4), per-batch cosine LR, ``args.epochs`` x (train pass, dev pass),
-    strict-'>' best-dev tracking and rollback.  All candidates of the call train concurrently (one at a time only when
-    ``args.weightsharing`` chains them through ``state_dict``); with torch.distributed initialised they are sharded."""
-    from . import dist as mdist
-    device = torch.device(device)
-    if device.type != "cuda":
-        raise RuntimeError("mfas_b200.train_sampled_models needs a CUDA device (no CPU fallback)")
-    train_host = _multilabel_cache_of(dataloaders['train'], 'train')
-    dev_host = _multilabel_cache_of(dataloaders['dev'], 'dev')
-    n_train, n_dev = len(train_host), len(dev_host)
-    E, B = int(args.epochs), int(args.batchsize)
-    steps = math.ceil(n_train / B)
-    todo = [i for i in range(len(sampled_configurations)) if not return_model or i in return_model]
-    init_f1 = {i: (float(preaccuracies[i]) if preaccuracies else 0.0) for i in todo}     # init_f1=preaccuracies[idx], :88
-    weightsharing = bool(getattr(args, "weightsharing", False))
-    direct = searchable_type is Searchable_Text_Image_Net and not premodels and not return_model and not weightsharing
-    models = {}
-    if not direct:
-        for idx in todo:                                   # constructed in order, like the reference (RNG parity)
-            m = searchable_type(args, sampled_configurations[idx])
-            if premodels:
-                m.load_state_dict(premodels[idx].state_dict())
-            models[idx] = m
-    first_tr = _reserve_passes(dataloaders['train'], len(todo) * E)
-    first_dv = _reserve_passes(dataloaders['dev'], len(todo) * E)
-    lrs = cosine_lrs(args, n_train, E * steps)
-    flags = _flags(args)
-    drop_p = float(args.drpt) if args.drpt > 1e-10 else 0.0
-    mine = mdist.my_share(len(todo)) if not (weightsharing or return_model) else list(range(len(todo)))
-    train_dev, dev_dev = train_host.to(device), dev_host.to(device)
-    f1s = torch.zeros(len(todo), dtype=torch.float64)
-    all_stats = torch.zeros(len(todo), max(E, 1), 4, dtype=torch.float64)
-
-    def confs_of(js):
-        return [np.asarray(sampled_configurations[todo[j]]).reshape(-1, 3) for j in js]
-
-    def run(js):
-        g = CandidateGroup(confs_of(js), args.inner_representation_size, args.num_outputs, flags, device, batch_max=B,
-                           drop_p=drop_p, drop_seed=int(getattr(args, "dropout_seed", 0)), cand_ids=[todo[j] for j in js],
-                           widths=WIDTHS)
-        g.set_adam(0.9, 0.999, 1e-8, 1e-4)
-        if direct:
-            # the constructor's RNG order for EVERY candidate of the call (other ranks' draws are consumed and dropped)
-            full = g if len(js) == len(todo) else GroupLayout(confs_of(range(len(todo))), args.inner_representation_size,
-                                                              args.num_outputs, flags, widths=WIDTHS)
-            hp, hb = _staging(int(full.p_off[-1]), int(full.b_off[-1]))
-            init_host_arenas(full, hp, hb)
-            for k, j in enumerate(js):
-                g.params[int(g.p_off[k]):int(g.p_off[k + 1])].copy_(hp[int(full.p_off[j]):int(full.p_off[j + 1])], non_blocking=True)
-                g.bufs[int(g.b_off[k]):int(g.b_off[k + 1])].copy_(hb[int(full.b_off[j]):int(full.b_off[j + 1])], non_blocking=True)
-        else:
-            for k, j in enumerate(js):
-                models[todo[j]].attach(g, k, copy_in=True)
-                if weightsharing:
-                    set_central_states(models[todo[j]], state_dict, getattr(args, "use_dataparallel", False))
-        ptr = torch.stack([pass_orders(dataloaders['train'], first_tr + j * E, E, n_train, device) for j in js]) if E else \
-            torch.zeros(len(js), 0, n_train, dtype=torch.int32, device=device)
-        pdv = torch.stack([pass_orders(dataloaders['dev'], first_dv + j * E, E, n_dev, device) for j in js]) if E else \
-            torch.zeros(len(js), 0, n_dev, dtype=torch.int32, device=device)
-        stats, best, _ = g.train_run(train_dev, dev_dev, ptr, pdv, lrs, E, B, best_init=[init_f1[todo[j]] for j in js])
-        stats, best = stats.cpu(), best.cpu()
-        g.check()
-        train_sampled_models.last_engine = g.engine
-        for k, j in enumerate(js):
-            f1s[j] = _final_f1(best[k])
-            all_stats[j] = stats[k]
-            if getattr(args, "verbose", False):
-                print('Now training: ')
-                print(sampled_configurations[todo[j]])
-                for e in range(E):
-                    print('epoch #{} {} F1: {:.4f} '.format(e, 'dev', float(stats[k, e, 3]) / n_dev))
-            if not direct:
-                models[todo[j]].train(False)
-                if weightsharing:
-                    get_central_states(models[todo[j]], state_dict, getattr(args, "use_dataparallel", False))
-        if direct:
-            g.close()
-
-    if weightsharing:
-        for j in mine:
-            run([j])
-    elif mine:
-        run(mine)
-    elif direct and todo:
-        # nothing to train on this rank: consume the constructor's draws all the same, so the CPU generators of the ranks
-        # stay in lockstep for the next call
-        full = GroupLayout(confs_of(range(len(todo))), args.inner_representation_size, args.num_outputs, flags, widths=WIDTHS)
-        hp, hb = _staging(int(full.p_off[-1]), int(full.b_off[-1]))
-        init_host_arenas(full, hp, hb)
-    f1s = mdist.gather_results(f1s, len(todo))
-    out = [f1s[j].clone() for j in range(len(todo))]
-    train_sampled_models.last_stats = all_stats
-    if return_model:
-        return out, [models[i] for i in todo]
-    return out
+    strict-'>' best-dev tracking (starting from ``preaccuracies[idx]`` = init_f1) and rollback.  The body is the one of the NTU
+    trainer (mfas_b200.ntu_searchable.train_sampled): all candidates of the call train concurrently (one at a time only when
+    ``args.weightsharing`` chains them through ``state_dict``), sharded over torch.distributed ranks or, with
+    ``args.fanout_gpus``, over the devices of this process."""
+    spec = _MMIMDBSpec()
+    spec.own_class = Searchable_Text_Image_Net
+    return train_sampled(spec, train_sampled_models, sampled_configurations, searchable_type, dataloaders, args, device,
+                         return_model, premodels, preaccuracies, state_dict)
 
 
 def train_mmimdb_track_f1(model, criterion, optimizer, scheduler, dataloaders, dataset_sizes,

@@ -423,6 +423,51 @@ def _print_epoch_logs(stats, n_train, n_dev):
         print('{} Loss: {:.4f} Acc: {:.4f}'.format('dev', stats[e, 2] / n_dev, stats[e, 3] / n_dev))
 
 
+class TrainerSpec:
+    """What distinguishes the candidate trainers of the tap sets (NTU here, MM-IMDB / AV-MNIST in their modules): everything
+    else -- grouping, initialisation, sharding over ranks or devices, the device-side epoch loop -- is shared."""
+    own_class = None                 # searchable_type for which no nn.Module needs to be built
+    widths = None                    # (first-modality tap widths, second-modality tap widths); None = the NTU taps
+    metric_name = "Acc"
+
+    def cache_of(self, loader, what):
+        return _feature_cache_of(loader, what)
+
+    def flags(self, args):
+        return flags_from_args(args)
+
+    def check(self, args, flags, preaccuracies):
+        if preaccuracies:   # the reference passes init_f1=..., which train_ntu_track_acc does not accept (:85-89)
+            raise TypeError("train_ntu_track_acc() got an unexpected keyword argument 'init_f1'")
+        if flags & _lib.FLAG_MULTITASK:
+            # the reference calls train_ntu_track_acc WITHOUT multitask= (ntu_searchable.py:81-83) while the model returns a
+            # 3-tuple (:244-247), so torch.max(output, 1) raises there; multitask training goes through train_ntu_track_acc
+            raise TypeError("max() received an invalid combination of arguments - got (tuple, int): train_sampled_models "
+                            "does not pass multitask to the training loop (use train_ntu_track_acc(..., multitask=True))")
+
+    def best_init(self, preaccuracies, idx):
+        return 0.0
+
+    def result(self, best):
+        return best
+
+    def load_backbones(self, rmode, args):
+        for net, cp in ((rmode.skenet, args.ske_cp), (rmode.rgbnet, args.rgb_cp)):
+            fn = os.path.join(args.checkpointdir, cp)
+            if os.path.isfile(fn):          # backbone weights are irrelevant once taps are cached
+                net.load_state_dict(torch.load(fn))
+
+    def log_epochs(self, stats, n_train, n_dev):
+        _print_epoch_logs(stats, n_train, n_dev)
+
+    def vid_len(self, args):
+        return getattr(args, "vid_len", (8, 32))[1]
+
+
+class _NTUSpec(TrainerSpec):
+    pass
+
+
 def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
                          args, device,
                          return_model=[], premodels=[], preaccuracies=[],
@@ -434,8 +479,18 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
     weight_decay=1e-4) with the per-batch cosine LR, ``args.epochs`` x (train pass, dev pass), strict-'>'
     best-dev tracking and rollback to the best weights.  All candidates of the call are trained
     concurrently by the CUDA library (sequentially only when ``args.weightsharing`` chains them
-    through ``state_dict``); with torch.distributed initialised they are sharded over ranks.
+    through ``state_dict``); with torch.distributed initialised they are sharded over ranks, with
+    ``args.fanout_gpus`` over the devices of this process.
     """
+    spec = _NTUSpec()
+    spec.own_class = Searchable_Skeleton_Image_Net
+    return train_sampled(spec, train_sampled_models, sampled_configurations, searchable_type, dataloaders, args, device,
+                         return_model, premodels, preaccuracies, state_dict)
+
+
+def train_sampled(spec, entry, sampled_configurations, searchable_type, dataloaders, args, device,
+                  return_model, premodels, preaccuracies, state_dict):
+    """The body shared by the ``train_sampled_models`` of every tap set (``entry`` = that function: it receives ``last_stats``)."""
     from . import dist as mdist
     device = torch.device(device)
     if device.type != "cuda":
@@ -451,10 +506,10 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
             import sys
             sys.stderr.write(f"[mfas timing] {what}: {(now - t_last[0]) * 1e3:.1f} ms\n")
             t_last[0] = now
-    if preaccuracies:   # the reference passes init_f1=..., which train_ntu_track_acc does not accept (:85-89)
-        raise TypeError("train_ntu_track_acc() got an unexpected keyword argument 'init_f1'")
-    train_host = _feature_cache_of(dataloaders['train'], 'train')
-    dev_host = _feature_cache_of(dataloaders['dev'], 'dev')
+    flags = spec.flags(args)
+    spec.check(args, flags, preaccuracies)
+    train_host = spec.cache_of(dataloaders['train'], 'train')
+    dev_host = spec.cache_of(dataloaders['dev'], 'dev')
     n_train, n_dev = len(train_host), len(dev_host)
     E, B = int(args.epochs), int(args.batchsize)
     steps = math.ceil(n_train / B)
@@ -463,8 +518,9 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
     rank, world = mdist.world()
     # Fast path: the driver never looks at the model objects (models/searchable.py:90,120), so when our own class
     # is the searchable_type no nn.Module is built at all -- parameters are initialised straight into the arenas.
-    direct = (searchable_type is Searchable_Skeleton_Image_Net and not premodels and not return_model
-              and not args.weightsharing)
+    weightsharing = bool(getattr(args, "weightsharing", False))
+    use_dp = bool(getattr(args, "use_dataparallel", False))
+    direct = (searchable_type is spec.own_class and not premodels and not return_model and not weightsharing)
     devices = fanout_devices(args, device) if (direct and world == 1) else [device]
     dev_init = bool(getattr(args, "init_on_device", world > 1 or len(devices) > 1)) and direct
     base_seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if dev_init else 0      # torch.manual_seed governs it
@@ -477,28 +533,20 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
         for idx in todo:
             rmode = searchable_type(args, sampled_configurations[idx])
             if not premodels:
-                for net, cp in ((rmode.skenet, args.ske_cp), (rmode.rgbnet, args.rgb_cp)):
-                    fn = os.path.join(args.checkpointdir, cp)
-                    if os.path.isfile(fn):          # backbone weights are irrelevant once taps are cached
-                        net.load_state_dict(torch.load(fn))
+                spec.load_backbones(rmode, args)
             else:
-                src = premodels[idx].module if args.use_dataparallel else premodels[idx]
+                src = premodels[idx].module if use_dp else premodels[idx]
                 rmode.load_state_dict(src.state_dict())
             models[idx] = rmode
 
     first_tr = _reserve_passes(dataloaders['train'], len(todo) * E)
     first_dv = _reserve_passes(dataloaders['dev'], len(todo) * E)
     lrs = cosine_lrs(args, n_train, E * steps)
-    flags = flags_from_args(args)
-    if flags & _lib.FLAG_MULTITASK:
-        # the reference calls train_ntu_track_acc WITHOUT multitask= (ntu_searchable.py:81-83) while the model returns a
-        # 3-tuple (:244-247), so torch.max(output, 1) raises there; multitask training goes through train_ntu_track_acc
-        raise TypeError("max() received an invalid combination of arguments - got (tuple, int): train_sampled_models "
-                        "does not pass multitask to the training loop (use train_ntu_track_acc(..., multitask=True))")
     drop_p = float(args.drpt) if args.drpt > 1e-10 else 0.0
+    init_best = [spec.best_init(preaccuracies, i) for i in todo]        # MM-IMDB: init_f1 = preaccuracies[idx]
 
     # with return_model every rank needs every trained model: no sharding then
-    mine = mdist.my_share(len(todo)) if not (args.weightsharing or return_model) else list(range(len(todo)))
+    mine = mdist.my_share(len(todo)) if not (weightsharing or return_model) else list(range(len(todo)))
     lap("setup")
     if world > 1 and getattr(args, "broadcast_cache", True):
         # rank 0's split crosses PCIe once and NVLink once (NCCL broadcast); the copy is kept with the host cache, so later
@@ -520,7 +568,7 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
         confs = [np.asarray(sampled_configurations[todo[j]]).reshape(-1, 3) for j in js]
         g = CandidateGroup(confs, args.inner_representation_size, args.num_outputs, flags, device, batch_max=B,
                            drop_p=drop_p, drop_seed=int(getattr(args, "dropout_seed", 0)),
-                           cand_ids=[todo[j] for j in js], vid_len_ske=args.vid_len[1])
+                           cand_ids=[todo[j] for j in js], vid_len_ske=spec.vid_len(args), widths=spec.widths)
         g.set_adam(0.9, 0.999, 1e-8, 1e-4)                                   # op.Adam(..., weight_decay=1e-4), :65
         return g
 
@@ -544,33 +592,34 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
         for k, j in enumerate(js):
             if not direct:
                 models[todo[j]].attach(g, k, copy_in=True)                   # rmode.to(device), :72
-                if args.weightsharing:
-                    set_central_states(models[todo[j]], state_dict, args.use_dataparallel)
+                if weightsharing:
+                    set_central_states(models[todo[j]], state_dict, use_dp)
         ptr = orders_for(js, dataloaders['train'], first_tr, n_train, device)
         pdv = orders_for(js, dataloaders['dev'], first_dv, n_dev, device)
         lap("batch orders")
-        stats, best, _ = g.train_run(train_dev, dev_dev, ptr, pdv, lrs, E, B)
+        stats, best, _ = g.train_run(train_dev, dev_dev, ptr, pdv, lrs, E, B, best_init=[init_best[j] for j in js])
+        entry.last_engine = g.engine
         lap("train_run (enqueue + GPU)")
         stats, best = stats.cpu(), best.cpu()                               # the one D2H of the call
         g.check()
         lap("D2H of the results")
         for k, j in enumerate(js):
-            accs[j] = best[k]
+            accs[j] = spec.result(float(best[k]))
             all_stats[j] = stats[k]
             if args.verbose:
                 print('Now training: ')
                 print(sampled_configurations[todo[j]])
-                _print_epoch_logs(stats[k].numpy(), n_train, n_dev)
+                spec.log_epochs(stats[k].numpy(), n_train, n_dev)
             if not direct:
                 m = models[todo[j]]
                 m.train(False)                                               # train_searchable/ntu.py:87
-                if args.weightsharing:
-                    get_central_states(m, state_dict, args.use_dataparallel)
+                if weightsharing:
+                    get_central_states(m, state_dict, use_dp)
         return g
 
     def full_layout():
         return GroupLayout([np.asarray(sampled_configurations[i]).reshape(-1, 3) for i in todo], args.inner_representation_size,
-                           args.num_outputs, flags, args.vid_len[1])
+                           args.num_outputs, flags, spec.vid_len(args), spec.widths)
 
     if direct and len(devices) > 1:
         # ---- single-process fan-out: candidate j -> devices[j % n] (the same round-robin as the multi-process mode, so both
@@ -603,7 +652,8 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
                     tr_d, dv_d = train_host.to(dev), dev_host.to(dev)
                     ptr = orders_for(js, dataloaders['train'], first_tr, n_train, dev)
                     pdv = orders_for(js, dataloaders['dev'], first_dv, n_dev, dev)
-                    stats, best, _ = g.train_run(tr_d, dv_d, ptr, pdv, lrs, E, B)
+                    stats, best, _ = g.train_run(tr_d, dv_d, ptr, pdv, lrs, E, B, best_init=[init_best[j] for j in js])
+                    entry.last_engine = g.engine
                     results[r] = (stats.cpu(), best.cpu())
                     g.check()
                     g.close()
@@ -623,13 +673,13 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
                 continue
             stats, best = results[r]
             for k, j in enumerate(shares[r]):
-                accs[j] = best[k]
+                accs[j] = spec.result(float(best[k]))
                 all_stats[j] = stats[k]
         if args.verbose:
             for j in range(len(todo)):
                 print('Now training: ')
                 print(sampled_configurations[todo[j]])
-                _print_epoch_logs(all_stats[j].numpy(), n_train, n_dev)
+                spec.log_epochs(all_stats[j].numpy(), n_train, n_dev)
         lap(f"fan-out over {nd} devices")
     elif direct:
         if mine:
@@ -677,7 +727,7 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
             init_host_arenas(remap, hp, hb)
             hp.zero_()
             hb.zero_()
-    elif args.weightsharing:               # candidates are chained through state_dict: one at a time
+    elif weightsharing:                    # candidates are chained through state_dict: one at a time
         for j in mine:
             run([j])
     elif mine:
@@ -686,7 +736,7 @@ def train_sampled_models(sampled_configurations, searchable_type, dataloaders,
     accs = mdist.gather_results(accs, len(todo))
     lap("gather")
     real_accuracies = [accs[j].clone() for j in range(len(todo))]
-    train_sampled_models.last_stats = all_stats
+    entry.last_stats = all_stats
     if return_model:
         return real_accuracies, [models[i] for i in todo]
     return real_accuracies

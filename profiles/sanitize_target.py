@@ -55,6 +55,8 @@ def main():
     run([FOUND_CONFS[4][:2]], 128, 128)
     run([FOUND_CONFS[0][:2]], 48, 16, engine="ffma")
     run([[[3, 1, 1], [1, 3, 0]]], 64, 32, flags=_lib.FLAG_BN | _lib.FLAG_ALPHAS)
+    run([[[3, 1, 1], [1, 3, 0]], [[2, 2, 0]]], 16, 32, flags=_lib.FLAG_BN | _lib.FLAG_ALPHAS)      # the small-inner_repr kernels with the gates
+    run([[[0, 1, 1], [1, 0, 0]]], 32, 128)                                                             # ... at 128-row batches
     # multi-label head (MM-IMDB tap set) and the pooling kernel
     import mfas_b200.mmimdb_searchable as mm
     tr, dv = mm.synthetic_mmimdb_cache(70, 1).to(DEV), mm.synthetic_mmimdb_cache(40, 2).to(DEV)
