@@ -599,10 +599,10 @@ def run_ours(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = M * cnt["train_bytes"] / t_step / 1e9
-    # ncu --set full capture of the same step (dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/)
+    # ncu --set full capture of the same step (dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r02_ncu_traffic.json: a committed capture, not measured in this run)
     traffic, per_kernel_traffic = None, {}
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
         if tj.get("workload") == "cfg2" and wl["name"] == "cfg2":
             per_kernel_traffic = {k: v * M for k, v in tj["dram_bytes_per_launch_per_candidate"].items()}
             traffic = float(sum(per_kernel_traffic.values()))
@@ -639,6 +639,7 @@ def run_ours(a):
         except Exception as ex:                      # profiling is an aid, never the measurement itself
             kernels = [{"error": str(ex)}]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "profiles/r02_ncu_traffic.json (ncu --set full capture r02u of this command line's kernels, committed; not re-measured in this run)",
                 "kernel": f"fused train step of {M} candidates (" + ("tc engine: k_tc_fwd_ws -> k_chain_all -> k_tc_bwd_ws, 3 launches; " if engine == "tc" else
                                                                        "ffma engine (inner_repr below the MMA tiles): per-layer CUDA-core kernels; ") +
                           "achieved = SURVEY 8(d) algorithmic bytes of the whole step / CUDA-event time of the whole step)",

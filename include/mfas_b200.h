@@ -27,13 +27,13 @@
 extern "C" {
 #endif
 
-#define MFAS_ABI_VERSION 4
+#define MFAS_ABI_VERSION 5
 
 #define MFAS_MAX_LAYERS 8     /* fusion steps per candidate (reference max_fusions default 4)   */
 #define MFAS_MAX_BATCH 128    /* rows per batch (BASELINE configs use 8, 64, 128)               */
 #define MFAS_MAX_HIDDEN 256   /* inner_representation_size                                       */
 #define MFAS_MAX_CLASSES 64   /* num_outputs (60 NTU)                                            */
-#define MFAS_NUM_TAPS 4       /* backbone taps per modality, ntu_searchable.py:291-292           */
+#define MFAS_NUM_TAPS 8       /* tap slots per modality: NTU 4 + 4 (ntu_searchable.py:291-292), MM-IMDB 2 + 4, AV-MNIST 5 + 3 */
 
 enum {
   MFAS_OK = 0,
@@ -49,10 +49,12 @@ enum {
   MFAS_FLAG_DROPOUT = 2,   /* args.drpt>1e-10: ... -> Dropout(p)                (ntu_searchable.py:274-279) */
   MFAS_FLAG_ALPHAS = 4,    /* args.alphas    : AlphaScalarMultiplication gate   (aux_models.py:94-111)      */
   MFAS_FLAG_MULTITASK = 8, /* args.multitask : + cached backbone logits         (train_searchable/ntu.py:59-61) */
-  MFAS_FLAG_MULTILABEL = 16 /* MM-IMDB head: WeightedCrossEntropyWithLogits (aux_models.py:129-147) on multi-hot
+  MFAS_FLAG_MULTILABEL = 16, /* MM-IMDB head: WeightedCrossEntropyWithLogits (aux_models.py:129-147) on multi-hot
                               * targets instead of softmax-CE; the per-batch statistic is the sum of per-sample F1 of
                               * sigmoid(logits) > 0.3 (train_searchable/mmimdb.py:84,101) instead of #correct.  All candidates
-                              * of a group share this flag; such groups run on the CUDA-core engine. */
+                              * of a group share this flag. */
+  MFAS_FLAG_PLAIN = 32      /* the AV-MNIST recipe (avmnist_searchable.py:276-285): Linear -> act [-> Dropout], never a BatchNorm;
+                              * with it mfas_plan_layout accepts "no BatchNorm, no Dropout" (which the NTU network rejects) */
 };
 
 enum { MFAS_ACT_RELU = 0, MFAS_ACT_SIGMOID = 1, MFAS_ACT_LRELU = 2 };  /* conf[:,2], ntu_searchable.py:267-272 */

@@ -18,9 +18,9 @@ SOURCES = [os.path.join(HERE, "csrc", "mfas_abi.cu"), os.path.join(HERE, "csrc",
 HEADERS = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "kernels_ffma.cuh", "kernels_tc.cuh", "kernels_pool.cuh", "umma.cuh")] + [
     os.path.join(ROOT, "include", "mfas_b200.h")]
 
-ABI_VERSION = 4          # MFAS_ABI_VERSION of include/mfas_b200.h
-MAX_LAYERS, MAX_BATCH, MAX_HIDDEN, MAX_CLASSES, NUM_TAPS = 8, 128, 256, 64, 4
-FLAG_BN, FLAG_DROPOUT, FLAG_ALPHAS, FLAG_MULTITASK, FLAG_MULTILABEL = 1, 2, 4, 8, 16
+ABI_VERSION = 5          # MFAS_ABI_VERSION of include/mfas_b200.h
+MAX_LAYERS, MAX_BATCH, MAX_HIDDEN, MAX_CLASSES, NUM_TAPS = 8, 128, 256, 64, 8
+FLAG_BN, FLAG_DROPOUT, FLAG_ALPHAS, FLAG_MULTITASK, FLAG_MULTILABEL, FLAG_PLAIN = 1, 2, 4, 8, 16, 32
 ERRORS = {0: "MFAS_OK", -1: "MFAS_ERR_INVALID", -2: "MFAS_ERR_CUDA", -3: "MFAS_ERR_UNSUPPORTED",
           -4: "MFAS_ERR_NOMEM", -5: "MFAS_ERR_UNBOUND"}
 

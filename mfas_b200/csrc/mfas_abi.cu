@@ -88,7 +88,9 @@ extern "C" int mfas_plan_layout(int32_t L, const int32_t* conf, int32_t H, int32
     return fail(MFAS_ERR_INVALID, "inner_representation_size=%d must be a multiple of 16 in [16,%d]", H, MFAS_MAX_HIDDEN);
   if (C < 2 || C > MFAS_MAX_CLASSES) return fail(MFAS_ERR_INVALID, "num_outputs=%d outside [2,%d]", C, MFAS_MAX_CLASSES);
   const bool bn = flags & MFAS_FLAG_BN, drop = flags & MFAS_FLAG_DROPOUT;
-  if (!bn && !drop)   // ntu_searchable.py:274-284: no branch assigns `op` -> UnboundLocalError
+  if ((flags & MFAS_FLAG_PLAIN) && bn)   // avmnist_searchable.py:276-285: the BatchNorm branches are commented out there
+    return fail(MFAS_ERR_INVALID, "MFAS_FLAG_PLAIN (the AV-MNIST recipe Linear -> act [-> Dropout]) excludes MFAS_FLAG_BN");
+  if (!bn && !drop && !(flags & MFAS_FLAG_PLAIN))   // ntu_searchable.py:274-284: no branch assigns `op` -> UnboundLocalError
     return fail(MFAS_ERR_UNSUPPORTED, "no layer recipe for drpt<1e-10 and batchnorm=False (reference raises UnboundLocalError)");
   for (int t = 0; t < MFAS_NUM_TAPS; ++t)
     if (d_ske[t] <= 0 || d_rgb[t] <= 0 || d_ske[t] % 32 || d_rgb[t] % 32)

@@ -29,8 +29,8 @@ def flags_from_args(args) -> int:
 
 
 def _four(widths):
-    """The ABI carries MFAS_NUM_TAPS = 4 taps per modality; a shorter tap set (the 2 MM-IMDB text taps) is repeated to fill
-    the unused slots -- ``plan_layout`` rejects a conf row that points at one of them."""
+    """The ABI carries MFAS_NUM_TAPS = 8 tap slots per modality; a shorter tap set (NTU 4 + 4, MM-IMDB 2 + 4, AV-MNIST 5 + 3) is
+    repeated to fill the unused slots -- ``plan_layout`` rejects a conf row that points at one of them."""
     w = [int(x) for x in widths]
     if not 1 <= len(w) <= _lib.NUM_TAPS:
         raise ValueError(f"a modality has 1..{_lib.NUM_TAPS} taps, got {len(w)}")
@@ -45,8 +45,8 @@ def plan_layout(conf, H, C_out, flags, vid_len_ske=32, widths=None) -> _lib.Layo
     for col, d in ((0, d0), (1, d1)):           # slots a shorter tap set leaves unused (the library checks the range [0, 4))
         if conf.shape[0] and len(d) <= conf[:, col].max() < _lib.NUM_TAPS:
             raise ValueError(f"conf tap index out of range for a ({len(d0)}, {len(d1)})-tap set: {conf.tolist()}")
-    ds = (C.c_int32 * 4)(*_four(d0))
-    dr = (C.c_int32 * 4)(*_four(d1))
+    ds = (C.c_int32 * _lib.NUM_TAPS)(*_four(d0))
+    dr = (C.c_int32 * _lib.NUM_TAPS)(*_four(d1))
     _lib.check(_lib.lib().mfas_plan_layout(conf.shape[0], conf.ctypes.data_as(C.POINTER(C.c_int32)), int(H),
                                            int(C_out), int(flags), ds, dr, C.byref(lay)))
     return lay

@@ -14,7 +14,7 @@ import types
 def install(shim_broken_imports: bool = True):
     """Call once, after the reference root is on sys.path and before `import models.searchable`."""
     import importlib
-    from . import ntu_searchable, scheduler, train_ntu
+    from . import avmnist_searchable, ntu_searchable, scheduler, train_ntu
     if shim_broken_imports:
         # the reference as shipped does not import (SURVEY.md D7): matplotlib is an unused import of
         # models/utils.py:61, `models.aux` / `models.train` are dangling names in loops we never call
@@ -33,7 +33,9 @@ def install(shim_broken_imports: bool = True):
             sys.modules.setdefault(n, pkg)
             sys.modules.setdefault(n + ".scheduler", ref_sched)
     for name, mod in (("models.search.ntu_searchable", ntu_searchable),
-                      ("models.search.train_searchable.ntu", train_ntu)):
+                      ("models.search.train_searchable.ntu", train_ntu),
+                      ("models.search.avmnist_searchable", avmnist_searchable),          # the AV-MNIST twin: module + its loops
+                      ("models.search.train_searchable.avmnist", avmnist_searchable)):
         sys.modules[name] = mod
         parent, _, leaf = name.rpartition(".")
         try:

@@ -69,6 +69,8 @@ class CachedTaps(nn.Module):
         taps = torch.split(x[:, :n], self.widths, 1)
         if self.kind == "rgb":                       # Visual.forward 6-tuple, central/ntu.py:50
             return (None, *taps, logits)
+        if self.kind == "lenet":                     # GP_LeNet / GP_LeNet_Deeper.forward, central/avmnist.py:57,112: (logits, gp1, gp2, ...)
+            return (logits, *taps)
         return [None] * 4 + list(taps), logits       # Skeleton.forward, central/ntu.py:183
 
     def load_state_dict(self, state_dict, strict=True, assign=False):
@@ -189,7 +191,10 @@ class Searchable_Skeleton_Image_Net(nn.Module):
             return g
         a = self.args
         cf = np.asarray(self.conf).reshape(-1, 3)
-        g = CandidateGroup([cf], a.inner_representation_size, a.num_outputs, flags_from_args(a) | self._extra_flags, device,
+        fl = flags_from_args(a) | self._extra_flags
+        if fl & _lib.FLAG_PLAIN:
+            fl &= ~_lib.FLAG_BN                        # the AV-MNIST recipe has no BatchNorm whatever args.batchnorm says
+        g = CandidateGroup([cf], a.inner_representation_size, a.num_outputs, fl, device,
                            batch_max=int(batch_max or _lib.MAX_BATCH), drop_p=float(a.drpt) if a.drpt > 1e-10 else 0.0,
                            drop_seed=int(getattr(a, "dropout_seed", 0)), vid_len_ske=getattr(a, "vid_len", (8, 32))[1],
                            widths=self._widths_kw)
@@ -199,9 +204,9 @@ class Searchable_Skeleton_Image_Net(nn.Module):
     # ---- forward ----------------------------------------------------------------------------
     def forward(self, tensor_tuple):
         rgb, ske = tensor_tuple[0], tensor_tuple[1]          # caller passes (rgb, ske), ntu_searchable.py:208
+        nr, ns = sum(self.rgbnet.widths), sum(self.skenet.widths)
         if rgb.dim() != 2 or ske.dim() != 2:
-            raise ValueError("expected cached taps: rgb [B, %d], ske [B, %d]" % (sum(D_RGB), sum(self.skenet.widths)))
-        nr, ns = sum(D_RGB), sum(self.skenet.widths)
+            raise ValueError("expected cached taps: [B, %d] for the second modality, [B, %d] for the first" % (nr, ns))
         multitask = bool(getattr(self.args, "multitask", False))
         vis_logits = rgb[:, nr:] if rgb.shape[1] > nr else None      # visual_classifier / skel_classifier, :213,:217
         ske_logits = ske[:, ns:] if ske.shape[1] > ns else None
@@ -215,8 +220,9 @@ class Searchable_Skeleton_Image_Net(nn.Module):
         if B > g.batch_max:                                # the group was sized by a training loop with a smaller batch
             g = self.native(rgb.device, batch_max=_lib.MAX_BATCH)
         cache = FeatureCache(ske[:, :ns].contiguous(), rgb[:, :nr].contiguous(),
-                             torch.zeros(B, dtype=torch.int64, device=rgb.device), self.args.vid_len[1],
-                             vis_logits.contiguous() if multitask else None, ske_logits.contiguous() if multitask else None)
+                             torch.zeros(B, dtype=torch.int64, device=rgb.device), getattr(self.args, "vid_len", (8, 32))[1],
+                             vis_logits.contiguous() if multitask else None, ske_logits.contiguous() if multitask else None,
+                             widths=self._widths_kw)
         rows = torch.arange(B, dtype=torch.int32, device=rgb.device)
         logits, _, _ = g.forward(cache, rows, train=self.training, step=self._fwd_steps)
         if self.training:

@@ -40,6 +40,11 @@ def train_ntu_track_acc(model, criteria, optimizer, scheduler, dataloaders, data
     (/root/reference/models/search/train_searchable/ntu.py:14-89).  ``criteria`` must be cross-entropy
     (what every caller passes); the LR of every batch comes from ``scheduler`` exactly as in the
     reference (per-batch for LRCosineAnnealingScheduler, otherwise stepped once per epoch)."""
+    return _train_track_acc(train_ntu_track_acc, model, optimizer, scheduler, dataloaders, device, num_epochs, multitask, with_loss=True)
+
+
+def _train_track_acc(entry, model, optimizer, scheduler, dataloaders, device, num_epochs, multitask, with_loss):
+    """Body shared with train_avmnist_track_acc (whose loop prints '<phase> Acc: ...' only, train_searchable/avmnist.py:79)."""
     net = model.module if isinstance(model, torch.nn.DataParallel) else model
     _check_multitask(net, multitask, dataloaders, ('train', 'dev'))
     B = int(getattr(dataloaders['train'], 'batch_size', None) or net.args.batchsize)
@@ -87,9 +92,13 @@ def train_ntu_track_acc(model, criteria, optimizer, scheduler, dataloaders, data
     pdv = pass_orders(dataloaders['dev'], k_dv, num_epochs, n_dev)[None]
     stats, best, _ = g.train_run(train_c, dev_c, ptr, pdv, lrs, num_epochs, B, b1, b2)
     stats, best = stats.cpu(), best.cpu()
-    for e in range(num_epochs):                               # ntu.py:78-79 prints unconditionally
-        print('{} Loss: {:.4f} Acc: {:.4f}'.format('train', stats[0, e, 0] / n_train, stats[0, e, 1] / n_train))
-        print('{} Loss: {:.4f} Acc: {:.4f}'.format('dev', stats[0, e, 2] / n_dev, stats[0, e, 3] / n_dev))
+    for e in range(num_epochs):                               # ntu.py:78-79 / avmnist.py:79 print unconditionally
+        if with_loss:
+            print('{} Loss: {:.4f} Acc: {:.4f}'.format('train', stats[0, e, 0] / n_train, stats[0, e, 1] / n_train))
+            print('{} Loss: {:.4f} Acc: {:.4f}'.format('dev', stats[0, e, 2] / n_dev, stats[0, e, 3] / n_dev))
+        else:
+            print('{} Acc: {:.4f}'.format('train', stats[0, e, 1] / n_train))
+            print('{} Acc: {:.4f}'.format('dev', stats[0, e, 3] / n_dev))
 
     # arenas -> optimiser state, so a caller inspecting / reusing the optimiser sees torch's layout
     for name, p in named.items():
@@ -100,7 +109,7 @@ def train_ntu_track_acc(model, criteria, optimizer, scheduler, dataloaders, data
                                   "exp_avg": g.view(slot, name, "m").clone().reshape(p.shape),
                                   "exp_avg_sq": g.view(slot, name, "v").clone().reshape(p.shape)}
     model.train(False)
-    train_ntu_track_acc.last_stats = stats[0]
+    entry.last_stats = stats[0]
     return best[0].clone()
 
 

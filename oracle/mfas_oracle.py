@@ -189,18 +189,19 @@ class FusionHead:
     """
 
     def __init__(self, conf, H, C, state, batchnorm=True, drpt=0.0, alphas=False,
-                 vid_len_ske=32, dropout_seed=0, cand_index=0):
+                 vid_len_ske=32, dropout_seed=0, cand_index=0, plain=False, widths=None):
         self.conf = np.asarray(conf, dtype=np.int64).reshape(-1, 3)
         self.L = len(self.conf)
         self.H, self.C = int(H), int(C)
         self.bn = bool(batchnorm)
         self.drpt = float(drpt)
         self.use_alphas = bool(alphas)
-        self.ds, self.dr = d_ske(vid_len_ske), D_RGB          # tap widths of the two modalities (subclasses: other tap sets)
+        self.ds, self.dr = widths if widths is not None else (d_ske(vid_len_ske), D_RGB)   # tap widths of the two modalities
         self.K = [self.ds[int(c[0])] + self.dr[int(c[1])] + (self.H if l > 0 else 0) for l, c in enumerate(self.conf)]
         self.dropout_seed, self.cand_index = dropout_seed, cand_index
-        if self.drpt < 1e-10 and not self.bn:
-            # ntu_searchable.py:274-284 has no branch for this combination
+        if self.drpt < 1e-10 and not self.bn and not plain:
+            # ntu_searchable.py:274-284 has no branch for this combination (plain: the AV-MNIST recipe Linear -> act,
+            # avmnist_searchable.py:276-285, oracle/avmnist_oracle.py)
             raise UnboundLocalError("no layer recipe for drpt<1e-10 and batchnorm=False")
         self.state = {k: np.array(v, copy=True) for k, v in state.items()}
         self.adam = {}       # name -> (m, v)

@@ -48,6 +48,10 @@ WS_CASES = {
                 H=32, B=16, n_train=112, n_dev=120, epochs=2, bn=True, drpt=0.0, Ti=1, model_seed=6, data_seed=71, weightsharing=True),
 }
 
+# AV-MNIST searchable fusion: the reference's own class + loop on cached taps, tests/golden/gen_golden_avmnist.py
+AVMNIST_CASE = dict(confs=[[[4, 2, 0], [1, 0, 1]], [[0, 1, 1]], [[3, 2, 2], [2, 1, 0], [4, 0, 1]]], H=32, B=16, channels=32, n_train=112, n_dev=120,
+                    epochs=2, Ti=1, alphas=True, model_seed=8, data_seed=81, loader_seed=500)
+
 # main_found_ntu.py flow (multitask + alphas, two training stages, test pass): tests/golden/gen_golden_found.py
 FOUND_MT_CASE = dict(conf=FOUND_CONFS[3][:3], H=32, B=16, n_train=96, n_dev=48, n_test=40, epochs=2, Ti=1, alphas=True,
                      model_seed=9, data_seed=51, loader_seed=300)

@@ -84,6 +84,7 @@ def test_reference_epnas_runs_over_the_ntu_module(ref_searchable, monkeypatch):
 
 @pytest.mark.parametrize("script,fixtures", [("gen_golden_pooling.py", ["pooling.npz"]), ("gen_golden_mmimdb.py", ["mmimdb_head.npz"]),
                                              ("gen_golden_mmimdb_path.py", ["mmimdb_path.npz"]), ("gen_golden_found.py", ["found_mt.npz"]),
+                                             ("gen_golden_avmnist.py", ["avmnist.npz"]),
                                              ("gen_golden.py", ["cfg1.npz", "cfg2.npz", "mixL.npz", "alph.npz", "wsh.npz"])])
 def test_committed_fixtures_are_what_executing_the_reference_produces(script, fixtures, tmp_path):
     """Provenance of the golden vectors: re-run the committed generator (it executes the reference's own classes / loop)

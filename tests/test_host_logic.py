@@ -53,7 +53,12 @@ def test_layout_matches_reference_shapes():
     with pytest.raises(_lib.MfasError):
         plan_layout([[0, 0, 0]], 16, 60, 0)          # drpt<1e-10 and no BN: the reference has no recipe
     with pytest.raises(_lib.MfasError):
-        plan_layout([[4, 0, 0]], 16, 60, _lib.FLAG_BN)
+        plan_layout([[_lib.NUM_TAPS, 0, 0]], 16, 60, _lib.FLAG_BN)      # beyond the ABI's tap slots: the library's range error
+    with pytest.raises(ValueError):
+        plan_layout([[4, 0, 0]], 16, 60, _lib.FLAG_BN)                  # a slot the 4-tap NTU set leaves unused
+    with pytest.raises(_lib.MfasError):
+        plan_layout([[0, 0, 0]], 16, 60, _lib.FLAG_BN | _lib.FLAG_PLAIN)      # the AV-MNIST recipe has no BatchNorm
+    assert plan_layout([[0, 0, 0]], 16, 10, _lib.FLAG_PLAIN).off_gamma[0] == -1      # ... and allows "no BatchNorm, no Dropout"
 
 
 def test_module_has_reference_state_dict_and_init():
@@ -279,7 +284,7 @@ def test_argument_errors_need_no_gpu():
     assert b"out_ld" in lib.mfas_last_error()
     assert lib.mfas_group_create(0, 0, None, 64, 0.0, 0, None, None) == -1
     lay = _lib.Layout()
-    d = (C.c_int32 * 4)(64, 128, 64, 128)
+    d = (C.c_int32 * _lib.NUM_TAPS)(*([64, 128] * (_lib.NUM_TAPS // 2)))
     conf = (C.c_int32 * 3)(0, 0, 7)
     assert lib.mfas_plan_layout(1, conf, 64, 23, _lib.FLAG_BN | _lib.FLAG_MULTILABEL, d, d, C.byref(lay)) == -1      # activation 7
     assert b"activation" in lib.mfas_last_error()
