@@ -42,6 +42,11 @@ def install(shim_broken_imports: bool = True):
             setattr(importlib.import_module(parent), leaf, mod)
         except ImportError:
             pass
+    try:                                       # K x 32 surrogate evaluations per search step as one batch (tools.py:22-30)
+        from . import search_tools
+        importlib.import_module("models.search.tools").predict_accuracies_with_surrogate = search_tools.predict_accuracies_with_surrogate
+    except ImportError:
+        pass
     return ntu_searchable
 
 

@@ -82,6 +82,26 @@ def test_reference_epnas_runs_over_the_ntu_module(ref_searchable, monkeypatch):
     assert calls[0] == 32 and all(c == 3 for c in calls[1:]) and len(calls) == 4
 
 
+def test_batched_surrogate_evaluation_equals_the_reference_loop(ref_searchable):
+    """mfas_b200.search_tools.predict_accuracies_with_surrogate (one surrogate forward per depth) against the reference's
+    one-by-one loop (models/search/tools.py:22-30 over surrogate.eval_model) on the reference's own surrogate module."""
+    S, b200 = ref_searchable
+    import importlib
+    import models.search.surrogate as surr
+    from mfas_b200.search_tools import predict_accuracies_with_surrogate as batched
+    tools = importlib.import_module("models.search.tools")
+    assert tools.predict_accuracies_with_surrogate is batched                      # install() rebinds it
+    torch.manual_seed(3)
+    surrogate = surr.SimpleRecurrentSurrogate(100, 3, 100)
+    rng = np.random.RandomState(0)
+    confs = [rng.randint(0, 4, size=(L, 3)) for L in (1, 2, 2, 3, 1, 2, 4, 3, 2)] + [rng.randint(0, 4, size=(2, 3)) for _ in range(96)]
+    want = [surrogate.eval_model(c, torch.device("cpu")) for c in confs]
+    got = batched(confs, surrogate, torch.device("cpu"))
+    assert len(got) == len(want) and all(isinstance(g, np.floating) or np.ndim(g) == 0 for g in got)
+    assert np.abs(np.array(got, np.float64) - np.array(want, np.float64)).max() < 1e-6
+    assert np.array(got).shape == (len(confs),)                                     # np.array(accs) as the driver does (tools.py:47)
+
+
 @pytest.mark.parametrize("script,fixtures", [("gen_golden_pooling.py", ["pooling.npz"]), ("gen_golden_mmimdb.py", ["mmimdb_head.npz"]),
                                              ("gen_golden_mmimdb_path.py", ["mmimdb_path.npz"]), ("gen_golden_found.py", ["found_mt.npz"]),
                                              ("gen_golden_avmnist.py", ["avmnist.npz"]),
