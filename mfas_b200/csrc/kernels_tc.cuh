@@ -1602,11 +1602,21 @@ __device__ __forceinline__ void chain_head_tc(ChainCtx& cx, const DCand& cd, int
   }
 }
 
+// all threads of all CTAs of the cluster: global writes made before it are visible to the whole cluster after it
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// cl: CTAs per candidate.  1: one CTA walks every 128-column tile of a layer in turn.  2 (inner_repr 256 and at most half as
+// many candidates as SMs, e.g. MM-IMDB configs[3]): a 2-CTA thread-block cluster per candidate, one tile each, a cluster
+// barrier (release / acquire: the tiles exchange h_l and dz_l through global memory) where the single CTA has __syncthreads;
+// the head runs on rank 0.  The chain is latency-bound, so two tiles side by side take the time of one.
 template <bool TRAIN, int NPAD, bool TCHEAD, bool ML = false>
 __global__ void __launch_bounds__(ChainCfg<NPAD>::THREADS)
 k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, const float* part_base,
             long long part_stride_cand, int hs_ld, int lg_ld, AdamH adam, float step_size, float bc2_sqrt,
-            uint32_t drop_seed, float drop_p, uint32_t step, HeadOut ho, TcErr err) {
+            uint32_t drop_seed, float drop_p, uint32_t step, HeadOut ho, TcErr err, int cl) {
   static_assert(ChainCfg<NPAD>::THREADS == kHeadThreads, "the head body is written for the chain CTA size");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t bar;
@@ -1614,7 +1624,7 @@ k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
   __shared__ int ok_flag;
   __shared__ DCand scd;            // this candidate's descriptor: every field access below is an LDS, not a dependent global load
   __shared__ HeadRows hr;
-  const int cand = blockIdx.x, tid = threadIdx.x;
+  const int cand = (int)blockIdx.x / cl, rank = (int)blockIdx.x % cl, tid = threadIdx.x;
   {
     static_assert(sizeof(DCand) % 4 == 0, "DCand is copied as words");
     const int* src = reinterpret_cast<const int*>(cands + cand);
@@ -1631,14 +1641,14 @@ k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
   }
   ChainCtx cx;
   int stamp_i = 0;
-  auto stamp = [&]() { if (err.timeline && tid == 0 && stamp_i < 16) err.timeline[cand * 16 + stamp_i] = clock64(); ++stamp_i; };
+  auto stamp = [&]() { if (err.timeline && tid == 0 && rank == 0 && stamp_i < 16) err.timeline[cand * 16 + stamp_i] = clock64(); ++stamp_i; };
   stamp();
   chain_ctx_open<NPAD>(cx, smem_raw, &bar, &tmem_slot, &ok_flag);      // (__syncthreads inside: scd is visible)
   griddep_launch();
   griddep_wait();                                                      // the partial sums come from the forward stream
   const DCand& cd = scd;
   const int L = cd.L, H = cd.H;
-  if (err.timeline) { cx.tl = err.timeline + cand * 16; cx.tl_layer = L > 1 ? 1 : 0; }
+  if (err.timeline && rank == 0) { cx.tl = err.timeline + cand * 16; cx.tl_layer = L > 1 ? 1 : 0; }
   // L2 prefetch, one phase ahead, of what the next phase reads from HBM: the hidden columns of W_{l+1} (H rows x H
   // floats), then W_c.  (Issued all at once at kernel start the 29 MB burst of 128 CTAs delayed the first layer by 3 us.)
   auto prefetch_next = [&](int l) {
@@ -1652,24 +1662,29 @@ k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
     }
   };
 
-  // inner_repr 256: the CTA walks the two 128-column tiles of a layer one after the other (same accumulator, same operand
-  // tiles); both read h_{l-1} / dz_{l+1} in full and write disjoint columns, so the only ordering is layer by layer
+  // inner_repr 256: two 128-column tiles per layer -- walked in turn by one CTA (cl = 1) or one per CTA of the cluster (cl = 2);
+  // both read h_{l-1} / dz_{l+1} in full and write disjoint columns, so the only ordering is layer by layer
+  const int m_first = rank * 128, m_step = 128 * cl;
   for (int l = 0; l < L; ++l) {
     prefetch_next(l + 1);
-    for (int m0 = 0; m0 < H; m0 += 128) {
+    for (int m0 = m_first; m0 < H; m0 += m_step) {
       chain_fwd_layer<TRAIN, NPAD>(cx, cd, cand, l, m0, nrows, bmax, part_base, part_stride_cand, drop_seed, drop_p, step);
       umma::tc_fence_before();
       __syncthreads();                                           // h_l (global) and the TMEM reads are done
       umma::tc_fence_after();
     }
+    if (cl > 1) cluster_sync_all();                              // ... in every tile of the layer
     stamp();
   }
-  if (TCHEAD) chain_head_tc<TRAIN, NPAD, ML>(cx, cd, cand, cache, batch, bmax, adam, step_size, bc2_sqrt, ho, hr);
-  else head_body<TRAIN, ML>(cd, cand, cache, batch, bmax, hs_ld, lg_ld, adam, step_size, bc2_sqrt, ho, reinterpret_cast<float*>(cx.smem));
+  if (rank == 0) {
+    if (TCHEAD) chain_head_tc<TRAIN, NPAD, ML>(cx, cd, cand, cache, batch, bmax, adam, step_size, bc2_sqrt, ho, hr);
+    else head_body<TRAIN, ML>(cd, cand, cache, batch, bmax, hs_ld, lg_ld, adam, step_size, bc2_sqrt, ho, reinterpret_cast<float*>(cx.smem));
+  }
   stamp();
   if (TRAIN) {
     for (int l = L - 1; l >= 0; --l) {
-      for (int m0 = 0; m0 < H; m0 += 128) {
+      if (cl > 1) { __syncthreads(); cluster_sync_all(); }       // dlogits / dh_L / dz_{l+1} of every tile (global) visible
+      for (int m0 = m_first; m0 < H; m0 += m_step) {
         __syncthreads();                                         // dlogits / dh_L / dz_{l+1} (global) visible, smem tiles free
         chain_bwd_layer<NPAD>(cx, cd, l, m0, nrows, bmax, adam, step_size, bc2_sqrt, drop_seed, drop_p, step, TCHEAD);
         umma::tc_fence_before();

@@ -309,6 +309,7 @@ struct mfas_group {
   cudaEvent_t prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // mfas_group_set_profiling: around fwd / chain / bwd of a step
   bool prof = false, prof_valid = false;
   int dbg = 0;                    // MFAS_TC_DEBUG bit 0: skip the Adam epilogue, bit 1: skip operand staging (timing experiments only)
+  int chain_cl = 1;               // CTAs (thread-block cluster size) per candidate in the fused chain: 2 for inner_repr 256 with <= n_sms / 2 candidates
   int chain = 2;                  // 2: fused chain kernel (H <= 128), 1: per-layer tensor-core chain kernels (MFAS_CHAIN=layers),
                                   // 0: per-layer CUDA-core chain kernels (MFAS_CHAIN=ffma)
   size_t smem_chain_all = 0;
@@ -556,6 +557,10 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     // tiles if they are larger; ~12 KB of the 227 KB are the kernel's static arrays (descriptor, row state, reductions)
     g->smem_chain_all = (g->tchead || g->smem_chain > 1024 + g->smem_head) ? g->smem_chain : 1024 + g->smem_head;
     if (g->smem_chain_all > 214 * 1024 && g->chain == 2) { g->chain = 1; g->tchead = false; }
+    if (g->chain == 2 && g->Hmax > 128 && 2 * n_cand <= g->n_sms) {
+      const char* ce = getenv("MFAS_CHAIN_CLUSTER");
+      g->chain_cl = (ce && !atoi(ce)) ? 1 : 2;
+    }
     if (g->chain == 2) {
 #define CHAIN_ATTR(ML) \
       attr((const void*)k_chain_all<true, 64, false, ML>, g->smem_chain_all); attr((const void*)k_chain_all<false, 64, false, ML>, g->smem_chain_all); \
@@ -860,14 +865,24 @@ static int to_dcache(const mfas_group* g, const mfas_cache_desc* c, DCache* out)
 // the order the chain's CTAs leave them instead of in blockIdx order, and neighbouring tiles of the list (which share
 // their x columns through L2) end up on different dies.
 static int pdl_mask() { static const int m = [] { const char* e = getenv("MFAS_PDL"); return e ? atoi(e) : 3; }(); return m; }
+static thread_local int g_launch_cluster = 1;       // thread-block cluster size of the next launch_k (set and reset by the chain launch)
 template <class... KArgs, class... Args>
 static void launch_k(int which, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = (pdl_mask() & which) ? 1 : 0;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (pdl_mask() & which) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (g_launch_cluster > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = g_launch_cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
   cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);      // errors surface through cudaGetLastError (LAUNCH_CHECK)
 }
 
@@ -943,12 +958,14 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
   for (int c = 0; c < g->n_cand; ++c) keep = keep || g->hc[c].grad != nullptr;
   if (prof) cudaEventRecord(g->prof_ev[1], st);
   if (g->chain == 2 && train == bn_train) {           // the whole serial chain in one launch
-#define CA_(T, N, TH, ML, BM, PS) launch_k(2, k_chain_all<T, N, TH, ML>, dim3(g->n_cand), dim3(ChainCfg<N>::THREADS), g->smem_chain_all, st, (const DCand*)g->dc, cache, batch, (int)(BM), (const float*)g->part, (long long)(PS), g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, ho, terr)
+    g_launch_cluster = g->chain_cl;
+#define CA_(T, N, TH, ML, BM, PS) launch_k(2, k_chain_all<T, N, TH, ML>, dim3(g->n_cand * g->chain_cl), dim3(ChainCfg<N>::THREADS), g->smem_chain_all, st, (const DCand*)g->dc, cache, batch, (int)(BM), (const float*)g->part, (long long)(PS), g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, ho, terr, g->chain_cl)
 #define CA(T, N, TH) do { if (g->multilabel) CA_(T, N, TH, true, g->bmax, g->part_stride); else CA_(T, N, TH, false, g->bmax, g->part_stride); } while (0)
     if (wide) { if (g->multilabel) CA_(false, 128, true, true, 128, g->part_stride_ev); else CA_(false, 128, true, false, 128, g->part_stride_ev); }
     else if (g->npad == 64) { if (g->tchead) { if (train) CA(true, 64, true); else CA(false, 64, true); } else { if (train) CA(true, 64, false); else CA(false, 64, false); } }
     else { if (g->tchead) { if (train) CA(true, 128, true); else CA(false, 128, true); } else { if (train) CA(true, 128, false); else CA(false, 128, false); } }
 #undef CA_
+    g_launch_cluster = 1;
 #undef CA
     LAUNCH_CHECK(g);
     if (!train) return MFAS_OK;
