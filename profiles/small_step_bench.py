@@ -42,3 +42,28 @@ for name, confs, H in cases:
     print(json.dumps({"case": name, "n": n, "H": H, "train_step_us": ms * 1e3, "kernels_us": [round(x / 20 * 1e3, 1) for x in acc], "eval_step128_us": ev * 1e3,
                       "train_MB": byt / 1e6, "frac": byt / ms / 1e6 / 6550.1}))
     g.close()
+
+# MM-IMDB configs[3] step (64 two-step candidates, inner_repr 256, bs 64): per-kernel times
+import mfas_b200.mmimdb_searchable as mm
+mcache = mm.synthetic_mmimdb_cache(4096, 1).to(dev)
+rows_mm = mm.get_possible_layer_configurations(0)
+rng = np.random.default_rng(0)
+for n in (64, 8):
+    confs = [np.array([rows_mm[i] for i in rng.integers(0, len(rows_mm), size=2)]) for _ in range(n)]
+    g = CandidateGroup(confs, 256, 23, _lib.FLAG_BN | _lib.FLAG_MULTILABEL, dev, batch_max=64, widths=mm.WIDTHS)
+    g.set_adam(0.9, 0.999, 1e-8, 1e-4); g.params.uniform_(-0.03, 0.03); g.bufs.fill_(1.0)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    rws = [torch.randint(0, 4096, (n, 64), device=dev, generator=gen, dtype=torch.int32) for _ in range(45)]
+    for i in range(5): g.train_step(mcache, rws[i], lr=1e-3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for i in range(40): g.train_step(mcache, rws[5 + i], lr=1e-3)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 40
+    g.set_profiling(True); acc = [0, 0, 0]
+    for i in range(20):
+        g.train_step(mcache, rws[5 + i], lr=1e-3); acc = [x + y for x, y in zip(acc, g.last_step_ms())]
+    byt = sum(algorithmic_counts(l, 64)["train_bytes"] for l in g.layouts)
+    print(json.dumps({"case": f"mmimdb64/{64 // n}gpu", "n": n, "H": 256, "train_step_us": ms * 1e3, "kernels_us": [round(x / 20 * 1e3, 1) for x in acc], "eval_step128_us": 0.0,
+                      "train_MB": byt / 1e6, "frac": byt / ms / 1e6 / 6550.1}))
+    g.close()

@@ -7,8 +7,8 @@ import numpy as np, torch
 from mfas_b200 import _lib
 from mfas_b200.cache import synthetic_ntu_cache
 from mfas_b200.engine import CandidateGroup
-conf = [[3, 1, 1], [1, 3, 0], [1, 1, 1], [3, 3, 0]]
-M, H, B = 128, 128, 64
+conf = [[3, 1, 1], [1, 3, 0], [1, 1, 1], [3, 3, 0]][:int(os.environ.get("TL_L", "4"))]
+M, H, B = int(os.environ.get("TL_M", "128")), int(os.environ.get("TL_H", "128")), 64
 train = synthetic_ntu_cache(4096, 3).to("cuda:0")
 g = CandidateGroup([conf] * M, H, 60, _lib.FLAG_BN, "cuda:0", batch_max=B)
 g.set_adam(0.9, 0.999, 1e-8, 1e-4)
@@ -24,12 +24,13 @@ for it in range(6):
     g.train_step(train, rows, 1e-4)
 out = np.zeros((M, 16), np.int64)
 _lib.check(_lib.lib().mfas_group_chain_timeline(g._h, out.ctypes.data, M))
-d = np.diff(out[:, :10], axis=1)
-names = ["open+fwd0", "fwd1", "fwd2", "fwd3", "head", "bwd3", "bwd2", "bwd1", "bwd0"]
+L = len(conf)
+d = np.diff(out[:, :2 * L + 2], axis=1)
+names = ["open+fwd0"] + [f"fwd{l}" for l in range(1, L)] + ["head"] + [f"bwd{l}" for l in range(L - 1, -1, -1)]
 print("phase: median / max cycles over candidates (1 us ~ 1900 cycles)")
 for i, n in enumerate(names):
     print(f"  {n:10s} {np.median(d[:, i]):9.0f} {d[:, i].max():9.0f}")
-print("  total      %9.0f %9.0f" % (np.median(out[:, 9] - out[:, 0]), (out[:, 9] - out[:, 0]).max()))
+print("  total      %9.0f %9.0f" % (np.median(out[:, 2 * L + 1] - out[:, 0]), (out[:, 2 * L + 1] - out[:, 0]).max()))
 inner = out[:, 10:16]
 t0 = inner[:, 0]
 print("inside forward layer 1 (cycles since the layer was entered, median): raw operand tiles landed (cp.async) %d | lo tiles written %d | MMAs issued %d | z complete (partials, MMA, bias, act) %d | BN stats %d | (layer end %d)" % (
