@@ -1699,6 +1699,436 @@ k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_chain_small: the serial chain of one step for inner_repr 16 / 32, on the CUDA cores, ENTIRELY ON CHIP.
+// A 64 x 16 hidden state does not need a tensor core: k_chain_all spends 11-14 k cycles per phase on it (operand
+// staging -> fence -> MMA -> commit -> tcgen05.ld, and a global-memory round trip of h_l / a_l / dz_l between phases;
+// profiles/r02z_chain_timeline_search.txt), 16 warps with 16 useful lanes in 4 of them, one CTA per SM.  Here the hidden
+// columns of W_1.., the classifier, every per-column vector with its Adam state, h_l, a_l and dz_l live in shared memory from
+// the first phase to the last; a phase is H (or C) FMAs per output element, a fixed-order column reduction through shared
+// memory and one or two __syncthreads; two CTAs fit an SM, so 256 candidates are one wave.  Same inputs (the forward
+// stream's partial sums) and the same outputs for the backward stream (h_l, dz_l, dlogits in global memory) as k_chain_all.
+//   thread = (column c = tid % HN, row-group slot tid / HN): G groups of 4 consecutive batch rows (the float4 of the
+//   partial-sum layout); HN == cd.H.
+// dynamic smem (floats): h[L][NPAD][HN] | a[L][NPAD][HN] (TRAIN) | dz[2][NPAD][HN] (TRAIN) | W_hid[L][HN][HN+1] |
+//                        W_c[64][HN+1] | lg[NPAD][64] | vec[L][NV][HN] | red[4][16][32]
+// ---------------------------------------------------------------------------------------------
+template <int NPAD, int HN> struct ChainSmall {
+  static constexpr int THREADS = kHeadThreads;
+  static constexpr int SLOTS = THREADS / HN;               // row-group slots
+  static constexpr int NG = NPAD / 4;                      // groups of 4 batch rows
+  static constexpr int G = NG > SLOTS ? NG / SLOTS : 1;    // groups per thread
+  static constexpr int WLD = HN + 1;                       // row stride of the weight tiles: conflict-free by row AND by column
+  static constexpr int LG_LD = TC_DLOG_LD;
+  static constexpr int H_L = NPAD * HN;
+  static constexpr int NV = 13;    // b g be | m_b v_b m_g v_g m_be v_be | running mean, var | batch mean, invstd
+  static constexpr size_t smem(int L, bool train) {
+    return sizeof(float) * ((size_t)L * H_L * (train ? 2 : 1) + (train ? 2 * H_L : 0) + (size_t)L * HN * WLD + 64 * WLD +
+                            NPAD * LG_LD + (size_t)L * NV * HN + 4 * 16 * 32);
+  }
+};
+
+// sum over the batch rows of one column: lanes of a warp hold different columns (HN = 32) or two row-group slots of 16
+// columns (HN = 16); fixed order: slot pair, then warp 0..15.  Every thread of the CTA calls it (idle slots pass 0).
+template <int HN>
+__device__ __forceinline__ float col_sum(float v, float* red, int c) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (HN == 16) v += __shfl_xor_sync(0xffffffffu, v, 16);
+  if (lane < HN) red[warp * 32 + lane] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 16; ++w) t += red[w * 32 + c];
+  return t;
+}
+template <int HN>
+__device__ __forceinline__ void col_sum2(float& v1, float& v2, float* red1, float* red2, int c) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (HN == 16) { v1 += __shfl_xor_sync(0xffffffffu, v1, 16); v2 += __shfl_xor_sync(0xffffffffu, v2, 16); }
+  if (lane < HN) { red1[warp * 32 + lane] = v1; red2[warp * 32 + lane] = v2; }
+  __syncthreads();
+  float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+  for (int w = 0; w < 16; ++w) { t1 += red1[w * 32 + c]; t2 += red2[w * 32 + c]; }
+  v1 = t1; v2 = t2;
+}
+
+template <bool TRAIN, int NPAD, int HN, bool ML>
+__global__ void __launch_bounds__((ChainSmall<NPAD, HN>::THREADS), 2)
+k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, const float* __restrict__ part_base,
+              long long part_stride_cand, AdamH adam, float step_size, float bc2_sqrt, uint32_t drop_seed, float drop_p,
+              uint32_t step, HeadOut ho, TcErr err) {
+  using Cfg = ChainSmall<NPAD, HN>;
+  constexpr int THREADS = Cfg::THREADS, G = Cfg::G, WLD = Cfg::WLD, LG_LD = Cfg::LG_LD, H_L = Cfg::H_L, NV = Cfg::NV;
+  extern __shared__ __align__(16) float csm[];
+  __shared__ DCand scd;
+  __shared__ HeadRows hr;
+  const int cand = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {
+    const int* src = reinterpret_cast<const int*>(cands + cand);
+    int* dst = reinterpret_cast<int*>(&scd);
+    for (int i = tid; i < (int)(sizeof(DCand) / 4); i += THREADS) dst[i] = src[i];
+  }
+  const int nrows = batch.n_rows;
+  for (int r = tid; r < nrows; r += THREADS) {
+    const int gr = batch_row(batch, cand, r);
+    hr.grow[r] = gr;
+    if (!ML) hr.lab[r] = (int)cache.labels[gr];
+  }
+  int stamp_i = 0;
+  auto stamp = [&]() { if (err.timeline && tid == 0 && stamp_i < 16) err.timeline[cand * 16 + stamp_i] = clock64(); ++stamp_i; };
+  stamp();
+  __syncthreads();
+  griddep_launch();
+  griddep_wait();                                    // the partial sums come from the forward stream; the weights from the last step
+  const DCand& cd = scd;
+  const int L = cd.L, C = cd.C;
+  const bool bn = (cd.flags & MFAS_FLAG_BN) != 0;
+  const bool drop = TRAIN && (cd.flags & MFAS_FLAG_DROPOUT);
+  const bool gated = (cd.flags & MFAS_FLAG_ALPHAS) != 0;
+  const float dscale = drop ? 1.f / (1.f - drop_p) : 1.f;
+  float* h_s = csm;
+  float* a_s = h_s + (size_t)L * H_L;
+  float* dz_s = a_s + (TRAIN ? (size_t)L * H_L : 0);
+  float* wh_s = dz_s + (TRAIN ? 2 * H_L : 0);
+  float* wc_s = wh_s + (size_t)L * HN * WLD;
+  float* lg = wc_s + 64 * WLD;
+  float* vec = lg + NPAD * LG_LD;
+  float* red = vec + (size_t)L * NV * HN;
+  const int c = tid % HN, slot = tid / HN;
+  const bool active = slot < Cfg::NG;                // inner_repr 16 with 64 rows: the upper 8 warps only help with staging and the head
+
+  // ---- stage everything the chain reads from global memory, all requests in flight together ----------------------
+  for (int i = tid; i < L * HN; i += THREADS) {      // per-column vectors and their Adam state
+    const int l = i / HN, cc = i % HN;
+    const DLayer& ly = cd.layer[l];
+    float* vv = vec + (size_t)l * NV * HN + cc;
+    vv[0] = cd.p[ly.ob + cc];
+    if (TRAIN) { vv[3 * HN] = cd.m[ly.ob + cc]; vv[4 * HN] = cd.v[ly.ob + cc]; }
+    if (bn) {
+      vv[1 * HN] = cd.p[ly.og + cc]; vv[2 * HN] = cd.p[ly.obe + cc];
+      vv[9 * HN] = cd.bufs[ly.orm + cc]; vv[10 * HN] = cd.bufs[ly.orv + cc];
+      if (TRAIN) { vv[5 * HN] = cd.m[ly.og + cc]; vv[6 * HN] = cd.v[ly.og + cc]; vv[7 * HN] = cd.m[ly.obe + cc]; vv[8 * HN] = cd.v[ly.obe + cc]; }
+    }
+  }
+  for (int l = 1; l < L; ++l) {                      // hidden columns of W_l
+    const DLayer& ly = cd.layer[l];
+    const float* Wh = cd.p + ly.oW + ly.d_ske + ly.d_rgb;
+    for (int i = tid; i < HN * HN; i += THREADS) wh_s[(size_t)l * HN * WLD + (i / HN) * WLD + (i % HN)] = Wh[(long long)(i / HN) * ly.K + (i % HN)];
+  }
+  for (int i = tid; i < 64 * HN; i += THREADS) wc_s[(i / HN) * WLD + (i % HN)] = (i / HN) < C ? cd.p[cd.oWc + i] : 0.f;
+  if (TRAIN) for (int i = tid; i < NPAD * LG_LD; i += THREADS) lg[i] = 0.f;         // columns >= C stay zero (dh_L reads whole float4s)
+  // classifier-bias Adam state for the threads that will apply it (warps 2-3)
+  const int cb = tid - 64;
+  const bool bias_thread = TRAIN && cb >= 0 && cb < C;
+  float pbc = 0.f, mbc = 0.f, vbc = 0.f;
+  if (bias_thread) { pbc = cd.p[cd.obc + cb]; mbc = cd.m[cd.obc + cb]; vbc = cd.v[cd.obc + cb]; }
+  if (active) {                                      // feature partial sums of every layer, summed in split order (gated: one factor per partial)
+    int item0 = 0;
+    const float4* pc = reinterpret_cast<const float4*>(part_base + (long long)cand * part_stride_cand) + c;
+    for (int l = 0; l < L; ++l) {
+      const DLayer& ly = cd.layer[l];
+      const float sg = gated ? gate_of(cd.p[ly.oalpha]) : 1.f;
+      const int n_ske = tc_fwd_items_of(ly.d_ske), nsplit = tc_fwd_items_g(ly.d_ske, ly.d_rgb, gated);
+      float4 z[G];
+#pragma unroll
+      for (int k = 0; k < G; ++k) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s0 = 0; s0 < nsplit; s0 += 4) {
+        float4 v[4][G];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4* p4 = pc + (long long)(item0 + min(s0 + u, nsplit - 1)) * 128 * (NPAD / 4);
+#pragma unroll
+          for (int k = 0; k < G; ++k) v[u][k] = p4[(long long)(slot + k * Cfg::SLOTS) * 128];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (s0 + u < nsplit) {
+            const float gt = !gated ? 1.f : (s0 + u < n_ske ? sg : 1.0f - sg);
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+              if (gated) { z[k].x = fmaf(gt, v[u][k].x, z[k].x); z[k].y = fmaf(gt, v[u][k].y, z[k].y); z[k].z = fmaf(gt, v[u][k].z, z[k].z); z[k].w = fmaf(gt, v[u][k].w, z[k].w); }
+              else { z[k].x += v[u][k].x; z[k].y += v[u][k].y; z[k].z += v[u][k].z; z[k].w += v[u][k].w; }
+            }
+          }
+        }
+      }
+      float* zs = (TRAIN ? a_s : h_s) + (size_t)l * H_L + c;          // parked where this thread's a_l (eval: h_l) goes
+#pragma unroll
+      for (int k = 0; k < G; ++k) {
+        const int b = 4 * (slot + k * Cfg::SLOTS);
+        zs[(b + 0) * HN] = z[k].x; zs[(b + 1) * HN] = z[k].y; zs[(b + 2) * HN] = z[k].z; zs[(b + 3) * HN] = z[k].w;
+      }
+      item0 += nsplit;
+    }
+  }
+  __syncthreads();
+
+  // ---- forward ------------------------------------------------------------------------------------------------------
+  for (int l = 0; l < L; ++l) {
+    const DLayer& ly = cd.layer[l];
+    float* vv = vec + (size_t)l * NV * HN + c;
+    float a[G][4];
+    if (active) {
+      const float* zs = (TRAIN ? a_s : h_s) + (size_t)l * H_L + c;
+#pragma unroll
+      for (int k = 0; k < G; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[k][i] = zs[(4 * (slot + k * Cfg::SLOTS) + i) * HN];
+      if (l > 0) {                                   // + W_hid h_{l-1}
+        const float* w = wh_s + (size_t)l * HN * WLD + c * WLD;
+        const float* hp = h_s + (size_t)(l - 1) * H_L;
+        float acc[G][4];
+#pragma unroll
+        for (int k = 0; k < G; ++k)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
+#pragma unroll 2
+        for (int j = 0; j < HN; j += 4) {
+          const float w0 = w[j], w1 = w[j + 1], w2 = w[j + 2], w3 = w[j + 3];
+#pragma unroll
+          for (int k = 0; k < G; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 hv = *reinterpret_cast<const float4*>(hp + (4 * (slot + k * Cfg::SLOTS) + i) * HN + j);
+              acc[k][i] = fmaf(hv.x, w0, acc[k][i]); acc[k][i] = fmaf(hv.y, w1, acc[k][i]);
+              acc[k][i] = fmaf(hv.z, w2, acc[k][i]); acc[k][i] = fmaf(hv.w, w3, acc[k][i]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < G; ++k)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[k][i] += acc[k][i];
+      }
+      const float bias = vv[0];
+#pragma unroll
+      for (int k = 0; k < G; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[k][i] = (4 * (slot + k * Cfg::SLOTS) + i < nrows) ? act_fwd(a[k][i] + bias, ly.act) : 0.f;
+    } else {
+#pragma unroll
+      for (int k = 0; k < G; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[k][i] = 0.f;
+    }
+    float mean = 0.f, istd = 1.f;
+    if (bn) {
+      if (TRAIN) {
+        float s1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < G; ++k)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) s1 += a[k][i];
+        mean = col_sum<HN>(s1, red, c) / (float)nrows;
+        float qq = 0.f;
+#pragma unroll
+        for (int k = 0; k < G; ++k)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (4 * (slot + k * Cfg::SLOTS) + i < nrows) { const float d = a[k][i] - mean; qq = fmaf(d, d, qq); }
+        const float var = col_sum<HN>(qq, red + 512, c) / (float)nrows;
+        istd = 1.f / sqrtf(var + kBnEps);
+        if (slot == 0) {
+          vv[11 * HN] = mean; vv[12 * HN] = istd;
+          const float n = (float)nrows;
+          cd.bufs[ly.orm + c] = (1.f - kBnMomentum) * vv[9 * HN] + kBnMomentum * mean;
+          cd.bufs[ly.orv + c] = (1.f - kBnMomentum) * vv[10 * HN] + kBnMomentum * (var * (n / (n - 1.f)));
+          if (c == 0) cd.nbt[l] += 1;
+        }
+      } else {
+        mean = vv[9 * HN];
+        istd = 1.f / sqrtf(vv[10 * HN] + kBnEps);
+      }
+    }
+    if (active) {
+      const float gamma = bn ? vv[1 * HN] : 1.f, beta = bn ? vv[2 * HN] : 0.f;
+      const uint32_t dkey = drop ? dropout_key(drop_seed, (uint32_t)cd.cand_id, step, (uint32_t)l) : 0u;
+      float* hs = h_s + (size_t)l * H_L + c;
+      float* as = a_s + (size_t)l * H_L + c;
+      float* hg = cd.hid + (long long)l * bmax * HN + c;
+#pragma unroll
+      for (int k = 0; k < G; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int b = 4 * (slot + k * Cfg::SLOTS) + i;
+          float h = bn ? (a[k][i] - mean) * istd * gamma + beta : a[k][i];
+          if (drop) h = dropout_keep(dkey, (uint32_t)(b * HN + c), drop_p) ? h * dscale : 0.f;
+          if (b >= nrows) h = 0.f;
+          hs[b * HN] = h;
+          if (TRAIN) as[b * HN] = a[k][i];
+          if (b < nrows) hg[(long long)b * HN] = h;                    // the backward stream's x operand (hidden columns)
+        }
+    }
+    __syncthreads();
+    stamp();
+  }
+
+  // ---- head: logits = h_L W_c^T + b_c; thread = (class k = tid % 64, rows tid / 64 + 8 i) ---------------------------
+  {
+    const int k = tid & 63, r0 = tid >> 6;
+    constexpr int NR = NPAD / 8;
+    const float* hp = h_s + (size_t)(L - 1) * H_L;
+    const float* w = wc_s + k * WLD;
+    float acc[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) acc[i] = 0.f;
+#pragma unroll 2
+    for (int j = 0; j < HN; j += 4) {
+      const float w0 = w[j], w1 = w[j + 1], w2 = w[j + 2], w3 = w[j + 3];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const float4 hv = *reinterpret_cast<const float4*>(hp + (r0 + 8 * i) * HN + j);
+        acc[i] = fmaf(hv.x, w0, acc[i]); acc[i] = fmaf(hv.y, w1, acc[i]); acc[i] = fmaf(hv.z, w2, acc[i]); acc[i] = fmaf(hv.w, w3, acc[i]);
+      }
+    }
+    if (k < C) {
+      const float bias = cd.p[cd.obc + k];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const int b = r0 + 8 * i;
+        if (b < nrows) {
+          const float s = acc[i] + bias;
+          lg[b * LG_LD + k] = s;
+          cd.logits[b * C + k] = s;
+          if (ho.logits) ho.logits[((long long)cand * bmax + b) * C + k] = s;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (ML) head_rows_ml<TRAIN>(cd, cache, nrows, lg, LG_LD, hr.rowloss, hr.rowok, hr.lab, hr.grow, TRAIN ? cd.dlog : nullptr);
+  else head_rows<TRAIN>(cd, cache, nrows, lg, LG_LD, hr.rowloss, hr.rowok, hr.lab, hr.grow, TRAIN ? cd.dlog : nullptr);
+  __syncthreads();
+  if (warp == 0) {                                         // batch statistics: fixed-order tree (see chain_head_tc)
+    float ls = 0.f;
+    int ok = 0;
+    double f1 = 0.0;
+    for (int r = lane; r < nrows; r += 32) {
+      ls += hr.rowloss[r]; ok += hr.rowok[r];
+      if (ML) { const int tp = hr.lab[r] & 255, den = hr.lab[r] >> 8; f1 += den > 0 ? 2.0 * (double)tp / (double)den : 0.0; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ls += __shfl_xor_sync(0xffffffffu, ls, o); ok += __shfl_xor_sync(0xffffffffu, ok, o);
+      if (ML) f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+    }
+    if (lane == 0) {
+      const float mean_loss = ML ? ls / ((float)nrows * (float)cd.C) : ls / (float)nrows;
+      if (ho.loss) ho.loss[cand] = mean_loss;
+      if (ho.correct) ho.correct[cand] = ok;
+      if (ho.stats) {
+        double* st = ho.stats + (long long)cand * ho.stat_stride + ho.stat_off;
+        st[0] += (double)mean_loss * (double)nrows;
+        st[1] += ML ? f1 : (double)ok;
+      }
+    }
+  }
+  if (bias_thread) {                                       // db_c = sum_b dlogits, in row order
+    float g = 0.f;
+    for (int b = 0; b < nrows; ++b) g += lg[b * LG_LD + cb];
+    const long long o = cd.obc + cb;
+    if (cd.grad) cd.grad[o] = g;
+    adam_update(g, pbc, mbc, vbc, adam, step_size, bc2_sqrt);
+    cd.p[o] = pbc; cd.m[o] = mbc; cd.v[o] = vbc;
+  }
+  stamp();
+
+  // ---- backward (pre-update weights: W_hid and W_c are stepped by the backward stream after this kernel) -------------
+  if (TRAIN) {
+    for (int l = L - 1; l >= 0; --l) {
+      const DLayer& ly = cd.layer[l];
+      float* vv = vec + (size_t)l * NV * HN + c;
+      float* dz_cur = dz_s + ((l + 1) & 1) * H_L;          // dz_{l+1}
+      float* dz_nxt = dz_s + (l & 1) * H_L;
+      float dh[G][4], av[G][4];
+#pragma unroll
+      for (int k = 0; k < G; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { dh[k][i] = 0.f; av[k][i] = 0.f; }
+      if (active) {
+        if (l == L - 1) {                                  // dh_L = dlogits W_c
+          const float* w = wc_s + c;
+          const int C4 = (C + 3) & ~3;
+          for (int k4 = 0; k4 < C4; k4 += 4) {
+            const float w0 = w[k4 * WLD], w1 = w[(k4 + 1) * WLD], w2 = w[(k4 + 2) * WLD], w3 = w[(k4 + 3) * WLD];
+#pragma unroll
+            for (int k = 0; k < G; ++k)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 d = *reinterpret_cast<const float4*>(lg + (4 * (slot + k * Cfg::SLOTS) + i) * LG_LD + k4);
+                dh[k][i] = fmaf(d.x, w0, dh[k][i]); dh[k][i] = fmaf(d.y, w1, dh[k][i]); dh[k][i] = fmaf(d.z, w2, dh[k][i]); dh[k][i] = fmaf(d.w, w3, dh[k][i]);
+              }
+          }
+        } else {                                           // dh_l = dz_{l+1} W_hid,l+1
+          const float* w = wh_s + (size_t)(l + 1) * HN * WLD + c;
+#pragma unroll 2
+          for (int h4 = 0; h4 < HN; h4 += 4) {
+            const float w0 = w[h4 * WLD], w1 = w[(h4 + 1) * WLD], w2 = w[(h4 + 2) * WLD], w3 = w[(h4 + 3) * WLD];
+#pragma unroll
+            for (int k = 0; k < G; ++k)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 d = *reinterpret_cast<const float4*>(dz_cur + (4 * (slot + k * Cfg::SLOTS) + i) * HN + h4);
+                dh[k][i] = fmaf(d.x, w0, dh[k][i]); dh[k][i] = fmaf(d.y, w1, dh[k][i]); dh[k][i] = fmaf(d.z, w2, dh[k][i]); dh[k][i] = fmaf(d.w, w3, dh[k][i]);
+              }
+          }
+        }
+        const float* as = a_s + (size_t)l * H_L + c;
+        const uint32_t dkey = drop ? dropout_key(drop_seed, (uint32_t)cd.cand_id, step, (uint32_t)l) : 0u;
+#pragma unroll
+        for (int k = 0; k < G; ++k)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int b = 4 * (slot + k * Cfg::SLOTS) + i;
+            av[k][i] = as[b * HN];
+            if (b >= nrows) dh[k][i] = 0.f;
+            else if (drop) dh[k][i] = dropout_keep(dkey, (uint32_t)(b * HN + c), drop_p) ? dh[k][i] * dscale : 0.f;
+          }
+      }
+      const float mu = bn ? vv[11 * HN] : 0.f, istd = bn ? vv[12 * HN] : 1.f, gam = bn ? vv[1 * HN] : 1.f;
+      float S1 = 0.f, S2 = 0.f;
+      if (bn) {
+#pragma unroll
+        for (int k = 0; k < G; ++k)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (4 * (slot + k * Cfg::SLOTS) + i < nrows) { S1 += dh[k][i]; S2 = fmaf(dh[k][i], (av[k][i] - mu) * istd, S2); }
+        col_sum2<HN>(S1, S2, red, red + 512, c);
+      }
+      const float m1 = S1 / (float)nrows, m2 = S2 / (float)nrows;
+      float db = 0.f;
+      if (active) {
+        float* dzg = cd.dzs + (long long)l * bmax * HN + c;
+#pragma unroll
+        for (int k = 0; k < G; ++k)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int b = 4 * (slot + k * Cfg::SLOTS) + i;
+            float dz = 0.f;
+            if (b < nrows) {
+              float da = dh[k][i];
+              if (bn) { const float ah = (av[k][i] - mu) * istd; da = gam * istd * (dh[k][i] - m1 - ah * m2); }
+              dz = da * act_bwd(av[k][i], ly.act);
+              dzg[(long long)b * HN] = dz;
+              db += dz;
+            }
+            dz_nxt[b * HN + c] = dz;
+          }
+      }
+      db = col_sum<HN>(db, red + 1024 + (l & 1) * 512, c); // (its barrier also publishes dz_l for the layer below; two buffers in turn:
+                                                           //  without BatchNorm it is the only barrier of a layer)
+      if (slot == 0) {
+        auto upd = [&](long long o, float g, float p, float m, float v) {
+          if (cd.grad) cd.grad[o] = g;
+          adam_update(g, p, m, v, adam, step_size, bc2_sqrt);
+          cd.p[o] = p; cd.m[o] = m; cd.v[o] = v;
+        };
+        upd(ly.ob + c, db, vv[0], vv[3 * HN], vv[4 * HN]);
+        if (bn) { upd(ly.og + c, S2, gam, vv[5 * HN], vv[6 * HN]); upd(ly.obe + c, S1, vv[2 * HN], vv[7 * HN], vv[8 * HN]); }
+      }
+      stamp();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // backward, all layers: one work item = 128 weight columns (k) x 64 output rows (h) of one layer.
 //   dW^T[k,h] = sum_b x[b,k] dz[b,h]      A = x chunk (MN-major, M = k), B = dz slice (MN-major, N = h)
 // TMEM lane = weight column k, so for a fixed h the 32 lanes of a warp touch 32 consecutive floats of
