@@ -573,9 +573,9 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
   __syncthreads();
   umma::tc_fence_after();
   griddep_launch();
+  const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   griddep_wait();                                                  // the weights come from the previous step's backward stream
   const uint32_t tm = tmem_slot;
-  const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   bool ok = true;
 
   if (warp < 4) {
@@ -621,7 +621,7 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
         const uint32_t a = s0 + sg * Cfg::TILE + off, b = a + Cfg::A_BYTES;
         const bool ske = kb < it.fs_kb;
 #pragma unroll
-        for (int j = 0; j < XJ; ++j) cp_async16_zfill(a + j * 2048, (ske ? xs[j] : xr[j]) + 32LL * kb, r + 16 * j < nrows, x_policy);
+        for (int j = 0; j < XJ; ++j) if (!(err.l2_hints & 64)) cp_async16_zfill(a + j * 2048, (ske ? xs[j] : xr[j]) + 32LL * kb, r + 16 * j < nrows, x_policy);
         const float* w = wp + 32LL * kb;
 #pragma unroll
         for (int j = 0; j < HN / 16; ++j) cp_async16_zfill(b + j * 2048, w + j * wstride, r + 16 * j < it.rows_valid, stream_policy);
@@ -648,7 +648,7 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
 #pragma unroll
       for (int j = 0; j < (NCH + Cfg::CONVERTERS - 1) / Cfg::CONVERTERS; ++j) {
         const int ch = ct + j * Cfg::CONVERTERS;
-        if (ch < NCH) {
+        if (ch < NCH && !(err.l2_hints & 16)) {
           const float4 x = src[ch];
           float4 l;
           l.x = umma::round_tf32(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
@@ -686,8 +686,10 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
             const uint64_t dbh = umma::smem_desc(b_hi + adv, 16, 1024), dbl = umma::smem_desc(b_lo + adv, 16, 1024);
             const uint32_t acc = (k > 0 || ks > 0) ? 1u : 0u;
             umma::mma_tf32(tm + tb * 2 * HN, dah, dbh, idesc, acc);               // main accumulator: hi*hi only
+            if (!(err.l2_hints & 32)) {
             umma::mma_tf32(tm + tb * 2 * HN + HN, dal, dbh, idesc, acc);          // correction accumulator
             umma::mma_tf32(tm + tb * 2 * HN + HN, dah, dbl, idesc, 1u);
+            }
           }
           umma::mma_commit(&rawfree[sg]);
           umma::mma_commit(&lofree[sl]);
@@ -1702,15 +1704,17 @@ k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
 // k_chain_small: the serial chain of one step for inner_repr 16 / 32, on the CUDA cores, ENTIRELY ON CHIP.
 // A 64 x 16 hidden state does not need a tensor core: k_chain_all spends 11-14 k cycles per phase on it (operand
 // staging -> fence -> MMA -> commit -> tcgen05.ld, and a global-memory round trip of h_l / a_l / dz_l between phases;
-// profiles/r02z_chain_timeline_search.txt), 16 warps with 16 useful lanes in 4 of them, one CTA per SM.  Here the hidden
-// columns of W_1.., the classifier, every per-column vector with its Adam state, h_l, a_l and dz_l live in shared memory from
-// the first phase to the last; a phase is H (or C) FMAs per output element, a fixed-order column reduction through shared
-// memory and one or two __syncthreads; two CTAs fit an SM, so 256 candidates are one wave.  Same inputs (the forward
-// stream's partial sums) and the same outputs for the backward stream (h_l, dz_l, dlogits in global memory) as k_chain_all.
+// profiles/r02z_chain_timeline_search.txt), 16 warps with 16 useful lanes in 4 of them, one CTA per SM.  Here ONE round
+// of cp.async brings everything the chain reads -- the forward stream's partial sums, the hidden columns of W_1.., the
+// classifier, every per-column vector with its Adam state -- into shared memory, where h_l, a_l and dz_l stay from the
+// first phase to the last; a phase is H (or C) FMAs per output element, a fixed-order column reduction and one or two
+// __syncthreads; the Adam steps of all b / gamma / beta / b_c run side by side after the last phase instead of on each
+// phase's critical path; two CTAs fit an SM, so 256 candidates are one wave.  Same inputs and the same outputs for the
+// backward stream (h_l, dz_l, dlogits in global memory) as k_chain_all.
 //   thread = (column c = tid % HN, row-group slot tid / HN): G groups of 4 consecutive batch rows (the float4 of the
 //   partial-sum layout); HN == cd.H.
 // dynamic smem (floats): h[L][NPAD][HN] | a[L][NPAD][HN] (TRAIN) | dz[2][NPAD][HN] (TRAIN) | W_hid[L][HN][HN+1] |
-//                        W_c[64][HN+1] | lg[NPAD][64] | vec[L][NV][HN] | red[4][16][32]
+//                        W_c[64][HN+1] | lg[NPAD][64] | vec[L][NV][HN] | red[5][16][32] | partial sums [items][NPAD/4][HN] float4
 // ---------------------------------------------------------------------------------------------
 template <int NPAD, int HN> struct ChainSmall {
   static constexpr int THREADS = kHeadThreads;
@@ -1720,12 +1724,22 @@ template <int NPAD, int HN> struct ChainSmall {
   static constexpr int WLD = HN + 1;                       // row stride of the weight tiles: conflict-free by row AND by column
   static constexpr int LG_LD = TC_DLOG_LD;
   static constexpr int H_L = NPAD * HN;
-  static constexpr int NV = 13;    // b g be | m_b v_b m_g v_g m_be v_be | running mean, var | batch mean, invstd
-  static constexpr size_t smem(int L, bool train) {
-    return sizeof(float) * ((size_t)L * H_L * (train ? 2 : 1) + (train ? 2 * H_L : 0) + (size_t)L * HN * WLD + 64 * WLD +
-                            NPAD * LG_LD + (size_t)L * NV * HN + 4 * 16 * 32);
+  // b g be | m_b v_b m_g v_g m_be v_be | running mean, var | batch mean, invstd | d b, d gamma, d beta
+  static constexpr int NV = 16;
+  static constexpr size_t smem(int L, bool train, int items) {
+    // the partial sums share their space with what is written after they are consumed: a_l (layer l's items end at or after
+    // (l + 1) H_L) and dz (backward only); evaluation: with h_l
+    const size_t state = train ? (size_t)L * H_L + (size_t)(items > L + 2 ? items : L + 2) * H_L : (size_t)(items > L ? items : L) * H_L;
+    return sizeof(float) * (state + (size_t)L * HN * WLD + 64 * WLD + NPAD * LG_LD + (size_t)L * NV * HN + 5 * 16 * 32);
   }
 };
+
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
 
 // sum over the batch rows of one column: lanes of a warp hold different columns (HN = 32) or two row-group slots of 16
 // columns (HN = 16); fixed order: slot pair, then warp 0..15.  Every thread of the CTA calls it (idle slots pass 0).
@@ -1752,16 +1766,77 @@ __device__ __forceinline__ void col_sum2(float& v1, float& v2, float* red1, floa
   v1 = t1; v2 = t2;
 }
 
+// head_rows (kernels_ffma.cuh) for four rows of a warp at once -- rows warp + 16 i of the round: the same arithmetic per
+// row, but the four dependent shuffle trees are interleaved instead of run one after the other (the chain's longest phase
+// at inner_repr 16).  Single-task softmax-CE only; multitask and the multi-label head take the row-at-a-time functions.
+template <bool TRAIN, int NPAD>
+__device__ __forceinline__ void head_rows_x4(const DCand& cd, int nrows, float* lg, int lg_ld, float* rowloss, int* rowok,
+                                             const int* lab, float* dlog) {
+  const int C = cd.C, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int rb = 0; rb < NPAD; rb += 64) {
+    if (rb >= nrows) break;
+    float v0[4], v1[4], mx[4];
+    int am[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rb + warp + 16 * i;
+      const bool ok = r < nrows;
+      const float* row = lg + r * lg_ld;
+      v0[i] = (ok && lane < C) ? row[lane] : -INFINITY; v1[i] = (ok && lane + 32 < C) ? row[lane + 32] : -INFINITY;
+      mx[i] = fmaxf(v0[i], v1[i]);
+      am[i] = (v1[i] > v0[i]) ? lane + 32 : lane;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx[i], o);
+        const int oa = __shfl_xor_sync(0xffffffffu, am[i], o);
+        if (om > mx[i] || (om == mx[i] && oa < am[i])) { mx[i] = om; am[i] = oa; }
+      }
+    }
+    float se[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) se[i] = (lane < C ? expf(v0[i] - mx[i]) : 0.f) + (lane + 32 < C ? expf(v1[i] - mx[i]) : 0.f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) se[i] += __shfl_xor_sync(0xffffffffu, se[i], o);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rb + warp + 16 * i;
+      if (r < nrows) {                                                  // (warp-uniform)
+        float* row = lg + r * lg_ld;
+        const float lse = logf(se[i]);
+        const int y = lab[r];
+        const float vy = __shfl_sync(0xffffffffu, y < 32 ? v0[i] : v1[i], y & 31);
+        if (lane == 0) { rowloss[r] = -((vy - mx[i]) - lse); rowok[r] = (am[i] == y) ? 1 : 0; }
+        if (TRAIN) {
+          const float inv_n = 1.f / (float)nrows;
+          const float d0 = lane < C ? (expf((v0[i] - mx[i]) - lse) - (lane == y ? 1.f : 0.f)) * inv_n : 0.f;
+          const float d1 = lane + 32 < C ? (expf((v1[i] - mx[i]) - lse) - (lane + 32 == y ? 1.f : 0.f)) * inv_n : 0.f;
+          if (lane < C) row[lane] = d0;
+          if (lane + 32 < C) row[lane + 32] = d1;
+          if (dlog) { dlog[r * 64 + lane] = d0; dlog[r * 64 + 32 + lane] = d1; }
+        }
+      }
+    }
+  }
+}
+
 template <bool TRAIN, int NPAD, int HN, bool ML>
 __global__ void __launch_bounds__((ChainSmall<NPAD, HN>::THREADS), 2)
 k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int bmax, const float* __restrict__ part_base,
               long long part_stride_cand, AdamH adam, float step_size, float bc2_sqrt, uint32_t drop_seed, float drop_p,
-              uint32_t step, HeadOut ho, TcErr err) {
+              uint32_t step, HeadOut ho, TcErr err, int raw_items) {
   using Cfg = ChainSmall<NPAD, HN>;
-  constexpr int THREADS = Cfg::THREADS, G = Cfg::G, WLD = Cfg::WLD, LG_LD = Cfg::LG_LD, H_L = Cfg::H_L, NV = Cfg::NV;
+  constexpr int THREADS = Cfg::THREADS, G = Cfg::G, WLD = Cfg::WLD, LG_LD = Cfg::LG_LD, H_L = Cfg::H_L, NV = Cfg::NV, NG = Cfg::NG;
   extern __shared__ __align__(16) float csm[];
   __shared__ DCand scd;
   __shared__ HeadRows hr;
+  __shared__ long long nbt_s[MFAS_MAX_LAYERS];
+  __shared__ float bc_s[4][64];                      // classifier bias: p, m, v, gradient
   const int cand = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {
     const int* src = reinterpret_cast<const int*>(cands + cand);
@@ -1775,105 +1850,103 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
     if (!ML) hr.lab[r] = (int)cache.labels[gr];
   }
   int stamp_i = 0;
-  auto stamp = [&]() { if (err.timeline && tid == 0 && stamp_i < 16) err.timeline[cand * 16 + stamp_i] = clock64(); ++stamp_i; };
+  auto stamp = [&]() { if (err.timeline && tid == 0 && stamp_i < 10) err.timeline[cand * 16 + stamp_i] = clock64(); ++stamp_i; };
+  auto stamp_at = [&](int i) { if (err.timeline && tid == 0) err.timeline[cand * 16 + i] = clock64(); };      // slots 10..: inside the phases
   stamp();
   __syncthreads();
-  griddep_launch();
-  griddep_wait();                                    // the partial sums come from the forward stream; the weights from the last step
   const DCand& cd = scd;
   const int L = cd.L, C = cd.C;
   const bool bn = (cd.flags & MFAS_FLAG_BN) != 0;
   const bool drop = TRAIN && (cd.flags & MFAS_FLAG_DROPOUT);
   const bool gated = (cd.flags & MFAS_FLAG_ALPHAS) != 0;
   const float dscale = drop ? 1.f / (1.f - drop_p) : 1.f;
+  int n_items = 0;
+  for (int l = 0; l < L; ++l) n_items += tc_fwd_items_g(cd.layer[l].d_ske, cd.layer[l].d_rgb, gated);
   float* h_s = csm;
-  float* a_s = h_s + (size_t)L * H_L;
-  float* dz_s = a_s + (TRAIN ? (size_t)L * H_L : 0);
-  float* wh_s = dz_s + (TRAIN ? 2 * H_L : 0);
+  float* a_s = h_s + (TRAIN ? (size_t)L * H_L : 0);
+  float* raw = a_s;                                  // the forward stream's partial sums, [item][NPAD/4][HN] float4 (see ChainSmall::smem)
+  float* dz_s = a_s + (size_t)L * H_L;
+  // raw_items: the partial sums the launch has room for (the group's largest candidate, or 0 when that does not fit: the
+  // layers then read them from global memory -- the same sums in the same order)
+  const bool staged = n_items <= raw_items;
+  float* wh_s = TRAIN ? a_s + (size_t)max(L + 2, raw_items) * H_L : h_s + (size_t)max(L, raw_items) * H_L;
   float* wc_s = wh_s + (size_t)L * HN * WLD;
   float* lg = wc_s + 64 * WLD;
   float* vec = lg + NPAD * LG_LD;
   float* red = vec + (size_t)L * NV * HN;
   const int c = tid % HN, slot = tid / HN;
-  const bool active = slot < Cfg::NG;                // inner_repr 16 with 64 rows: the upper 8 warps only help with staging and the head
-
-  // ---- stage everything the chain reads from global memory, all requests in flight together ----------------------
-  for (int i = tid; i < L * HN; i += THREADS) {      // per-column vectors and their Adam state
-    const int l = i / HN, cc = i % HN;
-    const DLayer& ly = cd.layer[l];
-    float* vv = vec + (size_t)l * NV * HN + cc;
-    vv[0] = cd.p[ly.ob + cc];
-    if (TRAIN) { vv[3 * HN] = cd.m[ly.ob + cc]; vv[4 * HN] = cd.v[ly.ob + cc]; }
-    if (bn) {
-      vv[1 * HN] = cd.p[ly.og + cc]; vv[2 * HN] = cd.p[ly.obe + cc];
-      vv[9 * HN] = cd.bufs[ly.orm + cc]; vv[10 * HN] = cd.bufs[ly.orv + cc];
-      if (TRAIN) { vv[5 * HN] = cd.m[ly.og + cc]; vv[6 * HN] = cd.v[ly.og + cc]; vv[7 * HN] = cd.m[ly.obe + cc]; vv[8 * HN] = cd.v[ly.obe + cc]; }
-    }
-  }
-  for (int l = 1; l < L; ++l) {                      // hidden columns of W_l
-    const DLayer& ly = cd.layer[l];
-    const float* Wh = cd.p + ly.oW + ly.d_ske + ly.d_rgb;
-    for (int i = tid; i < HN * HN; i += THREADS) wh_s[(size_t)l * HN * WLD + (i / HN) * WLD + (i % HN)] = Wh[(long long)(i / HN) * ly.K + (i % HN)];
-  }
-  for (int i = tid; i < 64 * HN; i += THREADS) wc_s[(i / HN) * WLD + (i % HN)] = (i / HN) < C ? cd.p[cd.oWc + i] : 0.f;
+  const bool active = slot < NG;                     // inner_repr 16 with 64 rows: the upper 8 warps only help with staging and the head
   if (TRAIN) for (int i = tid; i < NPAD * LG_LD; i += THREADS) lg[i] = 0.f;         // columns >= C stay zero (dh_L reads whole float4s)
-  // classifier-bias Adam state for the threads that will apply it (warps 2-3)
-  const int cb = tid - 64;
-  const bool bias_thread = TRAIN && cb >= 0 && cb < C;
-  float pbc = 0.f, mbc = 0.f, vbc = 0.f;
-  if (bias_thread) { pbc = cd.p[cd.obc + cb]; mbc = cd.m[cd.obc + cb]; vbc = cd.v[cd.obc + cb]; }
-  if (active) {                                      // feature partial sums of every layer, summed in split order (gated: one factor per partial)
-    int item0 = 0;
-    const float4* pc = reinterpret_cast<const float4*>(part_base + (long long)cand * part_stride_cand) + c;
-    for (int l = 0; l < L; ++l) {
-      const DLayer& ly = cd.layer[l];
-      const float sg = gated ? gate_of(cd.p[ly.oalpha]) : 1.f;
-      const int n_ske = tc_fwd_items_of(ly.d_ske), nsplit = tc_fwd_items_g(ly.d_ske, ly.d_rgb, gated);
-      float4 z[G];
-#pragma unroll
-      for (int k = 0; k < G; ++k) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int s0 = 0; s0 < nsplit; s0 += 4) {
-        float4 v[4][G];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float4* p4 = pc + (long long)(item0 + min(s0 + u, nsplit - 1)) * 128 * (NPAD / 4);
-#pragma unroll
-          for (int k = 0; k < G; ++k) v[u][k] = p4[(long long)(slot + k * Cfg::SLOTS) * 128];
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (s0 + u < nsplit) {
-            const float gt = !gated ? 1.f : (s0 + u < n_ske ? sg : 1.0f - sg);
-#pragma unroll
-            for (int k = 0; k < G; ++k) {
-              if (gated) { z[k].x = fmaf(gt, v[u][k].x, z[k].x); z[k].y = fmaf(gt, v[u][k].y, z[k].y); z[k].z = fmaf(gt, v[u][k].z, z[k].z); z[k].w = fmaf(gt, v[u][k].w, z[k].w); }
-              else { z[k].x += v[u][k].x; z[k].y += v[u][k].y; z[k].z += v[u][k].z; z[k].w += v[u][k].w; }
-            }
-          }
-        }
-      }
-      float* zs = (TRAIN ? a_s : h_s) + (size_t)l * H_L + c;          // parked where this thread's a_l (eval: h_l) goes
-#pragma unroll
-      for (int k = 0; k < G; ++k) {
-        const int b = 4 * (slot + k * Cfg::SLOTS);
-        zs[(b + 0) * HN] = z[k].x; zs[(b + 1) * HN] = z[k].y; zs[(b + 2) * HN] = z[k].z; zs[(b + 3) * HN] = z[k].w;
-      }
-      item0 += nsplit;
+  for (int i = C * HN + tid; i < 64 * HN; i += THREADS) wc_s[(i / HN) * WLD + (i % HN)] = 0.f;
+  griddep_launch();
+  griddep_wait();                                    // the partial sums come from the forward stream; the weights from the last step
+  stamp_at(10);
+
+  // ---- stage everything the chain reads from global memory: one round of cp.async ----------------------------------
+  {
+    const float4* pc = reinterpret_cast<const float4*>(part_base + (long long)cand * part_stride_cand);
+    for (int i = tid; i < (staged ? n_items * NG * HN : 0); i += THREADS) {
+      const int cc = i % HN, grp = (i / HN) % NG, item = i / (HN * NG);
+      cp_async16_ca(umma::smem_u32(raw + 4 * (size_t)i), pc + ((long long)item * NG + grp) * 128 + cc);
     }
+    for (int i = tid; i < L * HN; i += THREADS) {      // per-column vectors and their Adam state
+      const int l = i / HN, cc = i % HN;
+      const DLayer& ly = cd.layer[l];
+      const uint32_t vv = umma::smem_u32(vec + (size_t)l * NV * HN + cc);
+      cp_async4(vv, cd.p + ly.ob + cc);
+      if (TRAIN) { cp_async4(vv + 4 * 3 * HN, cd.m + ly.ob + cc); cp_async4(vv + 4 * 4 * HN, cd.v + ly.ob + cc); }
+      if (bn) {
+        cp_async4(vv + 4 * 1 * HN, cd.p + ly.og + cc); cp_async4(vv + 4 * 2 * HN, cd.p + ly.obe + cc);
+        cp_async4(vv + 4 * 9 * HN, cd.bufs + ly.orm + cc); cp_async4(vv + 4 * 10 * HN, cd.bufs + ly.orv + cc);
+        if (TRAIN) {
+          cp_async4(vv + 4 * 5 * HN, cd.m + ly.og + cc); cp_async4(vv + 4 * 6 * HN, cd.v + ly.og + cc);
+          cp_async4(vv + 4 * 7 * HN, cd.m + ly.obe + cc); cp_async4(vv + 4 * 8 * HN, cd.v + ly.obe + cc);
+        }
+      }
+    }
+    for (int i = tid; i < (L - 1) * HN * HN; i += THREADS) {      // hidden columns of W_1..
+      const int l = 1 + i / (HN * HN), r = (i / HN) % HN, j = i % HN;
+      const DLayer& ly = cd.layer[l];
+      cp_async4(umma::smem_u32(wh_s + (size_t)l * HN * WLD + r * WLD + j), cd.p + ly.oW + (long long)r * ly.K + ly.d_ske + ly.d_rgb + j);
+    }
+    for (int i = tid; i < C * HN; i += THREADS) cp_async4(umma::smem_u32(wc_s + (i / HN) * WLD + (i % HN)), cd.p + cd.oWc + i);
+    if (tid < C) {
+      cp_async4(umma::smem_u32(&bc_s[0][tid]), cd.p + cd.obc + tid);
+      if (TRAIN) { cp_async4(umma::smem_u32(&bc_s[1][tid]), cd.m + cd.obc + tid); cp_async4(umma::smem_u32(&bc_s[2][tid]), cd.v + cd.obc + tid); }
+    }
+    if (TRAIN && bn && tid < L) nbt_s[tid] = cd.nbt[tid];
+    cp_async_wait_all();
   }
   __syncthreads();
+  stamp_at(11);
 
   // ---- forward ------------------------------------------------------------------------------------------------------
+  int item0 = 0;
   for (int l = 0; l < L; ++l) {
     const DLayer& ly = cd.layer[l];
     float* vv = vec + (size_t)l * NV * HN + c;
+    const int nsplit = tc_fwd_items_g(ly.d_ske, ly.d_rgb, gated);
     float a[G][4];
+#pragma unroll
+    for (int k = 0; k < G; ++k)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[k][i] = 0.f;
     if (active) {
-      const float* zs = (TRAIN ? a_s : h_s) + (size_t)l * H_L + c;
+      // feature partial sums of this layer, in split order (alpha gates: one factor per partial, see chain_fwd_layer)
+      const float sg = gated ? gate_of(cd.p[ly.oalpha]) : 1.f;
+      const int n_ske = tc_fwd_items_of(ly.d_ske);
+      const float4* ps = staged ? reinterpret_cast<const float4*>(raw) + c
+                                : reinterpret_cast<const float4*>(part_base + (long long)cand * part_stride_cand) + c;
+      const int pstr = staged ? HN : 128;            // float4s per row group: packed in shared memory, Hp = 128 in the forward stream's layout
+      for (int s = 0; s < nsplit; ++s) {
+        const float gt = !gated ? 1.f : (s < n_ske ? sg : 1.0f - sg);
 #pragma unroll
-      for (int k = 0; k < G; ++k)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[k][i] = zs[(4 * (slot + k * Cfg::SLOTS) + i) * HN];
+        for (int k = 0; k < G; ++k) {
+          const float4 v = ps[((long long)(item0 + s) * NG + slot + k * Cfg::SLOTS) * pstr];
+          if (gated) { a[k][0] = fmaf(gt, v.x, a[k][0]); a[k][1] = fmaf(gt, v.y, a[k][1]); a[k][2] = fmaf(gt, v.z, a[k][2]); a[k][3] = fmaf(gt, v.w, a[k][3]); }
+          else { a[k][0] += v.x; a[k][1] += v.y; a[k][2] += v.z; a[k][3] += v.w; }
+        }
+      }
       if (l > 0) {                                   // + W_hid h_{l-1}
         const float* w = wh_s + (size_t)l * HN * WLD + c * WLD;
         const float* hp = h_s + (size_t)(l - 1) * H_L;
@@ -1882,7 +1955,7 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
         for (int k = 0; k < G; ++k)
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
-#pragma unroll 2
+#pragma unroll 4
         for (int j = 0; j < HN; j += 4) {
           const float w0 = w[j], w1 = w[j + 1], w2 = w[j + 2], w3 = w[j + 3];
 #pragma unroll
@@ -1904,12 +1977,9 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
       for (int k = 0; k < G; ++k)
 #pragma unroll
         for (int i = 0; i < 4; ++i) a[k][i] = (4 * (slot + k * Cfg::SLOTS) + i < nrows) ? act_fwd(a[k][i] + bias, ly.act) : 0.f;
-    } else {
-#pragma unroll
-      for (int k = 0; k < G; ++k)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[k][i] = 0.f;
     }
+    item0 += nsplit;
+    if (l == 1) stamp_at(14);
     float mean = 0.f, istd = 1.f;
     if (bn) {
       if (TRAIN) {
@@ -1926,18 +1996,20 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
           for (int i = 0; i < 4; ++i) if (4 * (slot + k * Cfg::SLOTS) + i < nrows) { const float d = a[k][i] - mean; qq = fmaf(d, d, qq); }
         const float var = col_sum<HN>(qq, red + 512, c) / (float)nrows;
         istd = 1.f / sqrtf(var + kBnEps);
-        if (slot == 0) {
+        if (tid >= THREADS - HN) {                   // one thread per column, in the last warp (idle at inner_repr 16, and never the slowest)
           vv[11 * HN] = mean; vv[12 * HN] = istd;
           const float n = (float)nrows;
           cd.bufs[ly.orm + c] = (1.f - kBnMomentum) * vv[9 * HN] + kBnMomentum * mean;
           cd.bufs[ly.orv + c] = (1.f - kBnMomentum) * vv[10 * HN] + kBnMomentum * (var * (n / (n - 1.f)));
-          if (c == 0) cd.nbt[l] += 1;
+          if (c == 0) cd.nbt[l] = nbt_s[l] + 1;
         }
       } else {
         mean = vv[9 * HN];
         istd = 1.f / sqrtf(vv[10 * HN] + kBnEps);
       }
     }
+    if (l == 1) stamp_at(15);
+    if (!(TRAIN && bn)) __syncthreads();             // a_l / h_l overwrite partial sums of this layer that another thread may still be reading
     if (active) {
       const float gamma = bn ? vv[1 * HN] : 1.f, beta = bn ? vv[2 * HN] : 0.f;
       const uint32_t dkey = drop ? dropout_key(drop_seed, (uint32_t)cd.cand_id, step, (uint32_t)l) : 0u;
@@ -1970,7 +2042,7 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
     float acc[NR];
 #pragma unroll
     for (int i = 0; i < NR; ++i) acc[i] = 0.f;
-#pragma unroll 2
+#pragma unroll 4
     for (int j = 0; j < HN; j += 4) {
       const float w0 = w[j], w1 = w[j + 1], w2 = w[j + 2], w3 = w[j + 3];
 #pragma unroll
@@ -1980,7 +2052,7 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
       }
     }
     if (k < C) {
-      const float bias = cd.p[cd.obc + k];
+      const float bias = bc_s[0][k];
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
         const int b = r0 + 8 * i;
@@ -1994,10 +2066,14 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
     }
   }
   __syncthreads();
+  stamp_at(12);
   if (ML) head_rows_ml<TRAIN>(cd, cache, nrows, lg, LG_LD, hr.rowloss, hr.rowok, hr.lab, hr.grow, TRAIN ? cd.dlog : nullptr);
-  else head_rows<TRAIN>(cd, cache, nrows, lg, LG_LD, hr.rowloss, hr.rowok, hr.lab, hr.grow, TRAIN ? cd.dlog : nullptr);
+  else if ((cd.flags & MFAS_FLAG_MULTITASK) && cache.logit_rgb && cache.logit_ske)
+    head_rows<TRAIN>(cd, cache, nrows, lg, LG_LD, hr.rowloss, hr.rowok, hr.lab, hr.grow, TRAIN ? cd.dlog : nullptr);
+  else head_rows_x4<TRAIN, NPAD>(cd, nrows, lg, LG_LD, hr.rowloss, hr.rowok, hr.lab, TRAIN ? cd.dlog : nullptr);
   __syncthreads();
-  if (warp == 0) {                                         // batch statistics: fixed-order tree (see chain_head_tc)
+  stamp_at(13);
+  if (warp == 15) {                                        // batch statistics: fixed-order tree (see chain_head_tc)
     float ls = 0.f;
     int ok = 0;
     double f1 = 0.0;
@@ -2021,110 +2097,126 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
       }
     }
   }
-  if (bias_thread) {                                       // db_c = sum_b dlogits, in row order
-    float g = 0.f;
-    for (int b = 0; b < nrows; ++b) g += lg[b * LG_LD + cb];
-    const long long o = cd.obc + cb;
-    if (cd.grad) cd.grad[o] = g;
-    adam_update(g, pbc, mbc, vbc, adam, step_size, bc2_sqrt);
-    cd.p[o] = pbc; cd.m[o] = mbc; cd.v[o] = vbc;
-  }
   stamp();
+  if (!TRAIN) return;
 
   // ---- backward (pre-update weights: W_hid and W_c are stepped by the backward stream after this kernel) -------------
-  if (TRAIN) {
-    for (int l = L - 1; l >= 0; --l) {
-      const DLayer& ly = cd.layer[l];
-      float* vv = vec + (size_t)l * NV * HN + c;
-      float* dz_cur = dz_s + ((l + 1) & 1) * H_L;          // dz_{l+1}
-      float* dz_nxt = dz_s + (l & 1) * H_L;
-      float dh[G][4], av[G][4];
+  {                                                        // db_c = sum_b dlogits: 8 partial sums per class, combined after the last phase
+    const int k = tid & 63, r0 = tid >> 6;
+    float g = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPAD / 8; ++i) g += lg[(r0 + 8 * i) * LG_LD + k];      // (rows >= nrows and columns >= C are zero)
+    red[4 * 512 + r0 * 64 + k] = g;
+  }
+  for (int l = L - 1; l >= 0; --l) {
+    const DLayer& ly = cd.layer[l];
+    float* vv = vec + (size_t)l * NV * HN + c;
+    float* dz_cur = dz_s + ((l + 1) & 1) * H_L;            // dz_{l+1}
+    float* dz_nxt = dz_s + (l & 1) * H_L;
+    float dh[G][4], av[G][4];
+#pragma unroll
+    for (int k = 0; k < G; ++k)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { dh[k][i] = 0.f; av[k][i] = 0.f; }
+    if (active) {
+      if (l == L - 1) {                                    // dh_L = dlogits W_c
+        const float* w = wc_s + c;
+        const int C4 = (C + 3) & ~3;
+#pragma unroll 4
+        for (int k4 = 0; k4 < C4; k4 += 4) {
+          const float w0 = w[k4 * WLD], w1 = w[(k4 + 1) * WLD], w2 = w[(k4 + 2) * WLD], w3 = w[(k4 + 3) * WLD];
+#pragma unroll
+          for (int k = 0; k < G; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 d = *reinterpret_cast<const float4*>(lg + (4 * (slot + k * Cfg::SLOTS) + i) * LG_LD + k4);
+              dh[k][i] = fmaf(d.x, w0, dh[k][i]); dh[k][i] = fmaf(d.y, w1, dh[k][i]); dh[k][i] = fmaf(d.z, w2, dh[k][i]); dh[k][i] = fmaf(d.w, w3, dh[k][i]);
+            }
+        }
+      } else {                                             // dh_l = dz_{l+1} W_hid,l+1
+        const float* w = wh_s + (size_t)(l + 1) * HN * WLD + c;
+#pragma unroll 4
+        for (int h4 = 0; h4 < HN; h4 += 4) {
+          const float w0 = w[h4 * WLD], w1 = w[(h4 + 1) * WLD], w2 = w[(h4 + 2) * WLD], w3 = w[(h4 + 3) * WLD];
+#pragma unroll
+          for (int k = 0; k < G; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 d = *reinterpret_cast<const float4*>(dz_cur + (4 * (slot + k * Cfg::SLOTS) + i) * HN + h4);
+              dh[k][i] = fmaf(d.x, w0, dh[k][i]); dh[k][i] = fmaf(d.y, w1, dh[k][i]); dh[k][i] = fmaf(d.z, w2, dh[k][i]); dh[k][i] = fmaf(d.w, w3, dh[k][i]);
+            }
+        }
+      }
+      const float* as = a_s + (size_t)l * H_L + c;
+      const uint32_t dkey = drop ? dropout_key(drop_seed, (uint32_t)cd.cand_id, step, (uint32_t)l) : 0u;
 #pragma unroll
       for (int k = 0; k < G; ++k)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { dh[k][i] = 0.f; av[k][i] = 0.f; }
-      if (active) {
-        if (l == L - 1) {                                  // dh_L = dlogits W_c
-          const float* w = wc_s + c;
-          const int C4 = (C + 3) & ~3;
-          for (int k4 = 0; k4 < C4; k4 += 4) {
-            const float w0 = w[k4 * WLD], w1 = w[(k4 + 1) * WLD], w2 = w[(k4 + 2) * WLD], w3 = w[(k4 + 3) * WLD];
-#pragma unroll
-            for (int k = 0; k < G; ++k)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 d = *reinterpret_cast<const float4*>(lg + (4 * (slot + k * Cfg::SLOTS) + i) * LG_LD + k4);
-                dh[k][i] = fmaf(d.x, w0, dh[k][i]); dh[k][i] = fmaf(d.y, w1, dh[k][i]); dh[k][i] = fmaf(d.z, w2, dh[k][i]); dh[k][i] = fmaf(d.w, w3, dh[k][i]);
-              }
-          }
-        } else {                                           // dh_l = dz_{l+1} W_hid,l+1
-          const float* w = wh_s + (size_t)(l + 1) * HN * WLD + c;
-#pragma unroll 2
-          for (int h4 = 0; h4 < HN; h4 += 4) {
-            const float w0 = w[h4 * WLD], w1 = w[(h4 + 1) * WLD], w2 = w[(h4 + 2) * WLD], w3 = w[(h4 + 3) * WLD];
-#pragma unroll
-            for (int k = 0; k < G; ++k)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 d = *reinterpret_cast<const float4*>(dz_cur + (4 * (slot + k * Cfg::SLOTS) + i) * HN + h4);
-                dh[k][i] = fmaf(d.x, w0, dh[k][i]); dh[k][i] = fmaf(d.y, w1, dh[k][i]); dh[k][i] = fmaf(d.z, w2, dh[k][i]); dh[k][i] = fmaf(d.w, w3, dh[k][i]);
-              }
-          }
+        for (int i = 0; i < 4; ++i) {
+          const int b = 4 * (slot + k * Cfg::SLOTS) + i;
+          av[k][i] = as[b * HN];
+          if (b >= nrows) dh[k][i] = 0.f;
+          else if (drop) dh[k][i] = dropout_keep(dkey, (uint32_t)(b * HN + c), drop_p) ? dh[k][i] * dscale : 0.f;
         }
-        const float* as = a_s + (size_t)l * H_L + c;
-        const uint32_t dkey = drop ? dropout_key(drop_seed, (uint32_t)cd.cand_id, step, (uint32_t)l) : 0u;
-#pragma unroll
-        for (int k = 0; k < G; ++k)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int b = 4 * (slot + k * Cfg::SLOTS) + i;
-            av[k][i] = as[b * HN];
-            if (b >= nrows) dh[k][i] = 0.f;
-            else if (drop) dh[k][i] = dropout_keep(dkey, (uint32_t)(b * HN + c), drop_p) ? dh[k][i] * dscale : 0.f;
-          }
-      }
-      const float mu = bn ? vv[11 * HN] : 0.f, istd = bn ? vv[12 * HN] : 1.f, gam = bn ? vv[1 * HN] : 1.f;
-      float S1 = 0.f, S2 = 0.f;
-      if (bn) {
-#pragma unroll
-        for (int k = 0; k < G; ++k)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) if (4 * (slot + k * Cfg::SLOTS) + i < nrows) { S1 += dh[k][i]; S2 = fmaf(dh[k][i], (av[k][i] - mu) * istd, S2); }
-        col_sum2<HN>(S1, S2, red, red + 512, c);
-      }
-      const float m1 = S1 / (float)nrows, m2 = S2 / (float)nrows;
-      float db = 0.f;
-      if (active) {
-        float* dzg = cd.dzs + (long long)l * bmax * HN + c;
-#pragma unroll
-        for (int k = 0; k < G; ++k)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int b = 4 * (slot + k * Cfg::SLOTS) + i;
-            float dz = 0.f;
-            if (b < nrows) {
-              float da = dh[k][i];
-              if (bn) { const float ah = (av[k][i] - mu) * istd; da = gam * istd * (dh[k][i] - m1 - ah * m2); }
-              dz = da * act_bwd(av[k][i], ly.act);
-              dzg[(long long)b * HN] = dz;
-              db += dz;
-            }
-            dz_nxt[b * HN + c] = dz;
-          }
-      }
-      db = col_sum<HN>(db, red + 1024 + (l & 1) * 512, c); // (its barrier also publishes dz_l for the layer below; two buffers in turn:
-                                                           //  without BatchNorm it is the only barrier of a layer)
-      if (slot == 0) {
-        auto upd = [&](long long o, float g, float p, float m, float v) {
-          if (cd.grad) cd.grad[o] = g;
-          adam_update(g, p, m, v, adam, step_size, bc2_sqrt);
-          cd.p[o] = p; cd.m[o] = m; cd.v[o] = v;
-        };
-        upd(ly.ob + c, db, vv[0], vv[3 * HN], vv[4 * HN]);
-        if (bn) { upd(ly.og + c, S2, gam, vv[5 * HN], vv[6 * HN]); upd(ly.obe + c, S1, vv[2 * HN], vv[7 * HN], vv[8 * HN]); }
-      }
-      stamp();
     }
+    const float mu = bn ? vv[11 * HN] : 0.f, istd = bn ? vv[12 * HN] : 1.f, gam = bn ? vv[1 * HN] : 1.f;
+    float S1 = 0.f, S2 = 0.f;
+    if (bn) {
+#pragma unroll
+      for (int k = 0; k < G; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (4 * (slot + k * Cfg::SLOTS) + i < nrows) { S1 += dh[k][i]; S2 = fmaf(dh[k][i], (av[k][i] - mu) * istd, S2); }
+      col_sum2<HN>(S1, S2, red, red + 512, c);
+    }
+    const float m1 = S1 / (float)nrows, m2 = S2 / (float)nrows;
+    float db = 0.f;
+    if (active) {
+      float* dzg = cd.dzs + (long long)l * bmax * HN + c;
+#pragma unroll
+      for (int k = 0; k < G; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int b = 4 * (slot + k * Cfg::SLOTS) + i;
+          float dz = 0.f;
+          if (b < nrows) {
+            float da = dh[k][i];
+            if (bn) { const float ah = (av[k][i] - mu) * istd; da = gam * istd * (dh[k][i] - m1 - ah * m2); }
+            dz = da * act_bwd(av[k][i], ly.act);
+            dzg[(long long)b * HN] = dz;
+            db += dz;
+          }
+          dz_nxt[b * HN + c] = dz;
+        }
+    }
+    db = col_sum<HN>(db, red + 1024 + (l & 1) * 512, c);   // (its barrier also publishes dz_l for the layer below; two buffers in turn:
+                                                           //  without BatchNorm it is the only barrier of a layer)
+    if (tid >= THREADS - HN) { vv[13 * HN] = db; vv[14 * HN] = S2; vv[15 * HN] = S1; }
+    stamp();
+  }
+  __syncthreads();
+  // ---- Adam of every per-column vector, side by side: b_l, gamma_l, beta_l (gradients: sum dz, sum dh a_hat, sum dh) and b_c
+  for (int t = tid; t < L * HN * 3; t += THREADS) {
+    const int l = t / (3 * HN), which = (t / HN) % 3, cc = t % HN;
+    if (which > 0 && !bn) continue;
+    const DLayer& ly = cd.layer[l];
+    const float* vv = vec + (size_t)l * NV * HN + cc;
+    const long long o = (which == 0 ? ly.ob : which == 1 ? ly.og : ly.obe) + cc;
+    const float g = vv[(13 + which) * HN];
+    float p = vv[which * HN], m = vv[(3 + 2 * which) * HN], v = vv[(4 + 2 * which) * HN];
+    if (cd.grad) cd.grad[o] = g;
+    adam_update(g, p, m, v, adam, step_size, bc2_sqrt);
+    cd.p[o] = p; cd.m[o] = m; cd.v[o] = v;
+  }
+  if (tid >= THREADS - 64 && tid - (THREADS - 64) < C) {
+    const int k = tid - (THREADS - 64);
+    float g = 0.f;
+#pragma unroll
+    for (int r0 = 0; r0 < 8; ++r0) g += red[4 * 512 + r0 * 64 + k];
+    float p = bc_s[0][k], m = bc_s[1][k], v = bc_s[2][k];
+    const long long o = cd.obc + k;
+    if (cd.grad) cd.grad[o] = g;
+    adam_update(g, p, m, v, adam, step_size, bc2_sqrt);
+    cd.p[o] = p; cd.m[o] = m; cd.v[o] = v;
   }
 }
 

@@ -309,6 +309,7 @@ struct mfas_group {
   cudaEvent_t prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // mfas_group_set_profiling: around fwd / chain / bwd of a step
   bool prof = false, prof_valid = false;
   int dbg = 0;                    // MFAS_TC_DEBUG bit 0: skip the Adam epilogue, bit 1: skip operand staging (timing experiments only)
+  int chain_small_items = 0;      // partial sums per candidate staged by k_chain_small (largest of the group)
   int chain_small = 0;            // 16 / 32: the chain of a step runs in k_chain_small (inner_repr 16 / 32, on-chip, CUDA cores)
   int chain_cl = 1;               // CTAs (thread-block cluster size) per candidate in the fused chain: 2 for inner_repr 256 with <= n_sms / 2 candidates
   int chain = 2;                  // 2: fused chain kernel (H <= 128), 1: per-layer tensor-core chain kernels (MFAS_CHAIN=layers),
@@ -567,14 +568,24 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       bool same = true;
       for (int c = 0; c < n_cand; ++c) same = same && g->lay[c].H == g->Hmax;
       const char* se = getenv("MFAS_CHAIN_SMALL");
-      auto need_of = [&](int npad, bool tr) {
-        return g->Hmax == 16 ? (npad == 64 ? ChainSmall<64, 16>::smem(g->Lmax, tr) : ChainSmall<128, 16>::smem(g->Lmax, tr))
-                             : (npad == 64 ? ChainSmall<64, 32>::smem(g->Lmax, tr) : ChainSmall<128, 32>::smem(g->Lmax, tr));
+      int items = 0;                                      // most partial sums of a candidate (all staged in shared memory)
+      for (int c = 0; c < n_cand; ++c) {
+        int n = 0;
+        for (int l = 0; l < g->lay[c].L; ++l) n += tc_fwd_items_g(g->lay[c].d_ske[l], g->lay[c].d_rgb[l], (g->lay[c].flags & MFAS_FLAG_ALPHAS) != 0);
+        items = std::max(items, n);
+      }
+      auto need_of = [&](int npad, bool tr, int it) {
+        return g->Hmax == 16 ? (npad == 64 ? ChainSmall<64, 16>::smem(g->Lmax, tr, it) : ChainSmall<128, 16>::smem(g->Lmax, tr, it))
+                             : (npad == 64 ? ChainSmall<64, 32>::smem(g->Lmax, tr, it) : ChainSmall<128, 32>::smem(g->Lmax, tr, it));
       };
-      const size_t need = std::max(need_of(g->npad, true), need_of(128, false));     // training steps; a 128-row dev / test step
-      if (same && !(se && !atoi(se)) && need <= 200 * 1024) {
+      // training steps at the group's row padding; a 128-row dev / test step.  Partial sums that do not fit are read from global memory.
+      auto need_all = [&](int it) { return std::max(need_of(g->npad, true, it), need_of(128, false, it)); };
+      if (need_all(items) > 216 * 1024) items = 0;
+      g->chain_small_items = items;
+      const size_t need = need_all(items);
+      if (same && !(se && !atoi(se)) && need <= 216 * 1024) {
         g->chain_small = g->Hmax;
-#define CS_ATTR(T, N, HN_) attr((const void*)k_chain_small<T, N, HN_, false>, ChainSmall<N, HN_>::smem(g->Lmax, T)); attr((const void*)k_chain_small<T, N, HN_, true>, ChainSmall<N, HN_>::smem(g->Lmax, T));
+#define CS_ATTR(T, N, HN_) attr((const void*)k_chain_small<T, N, HN_, false>, ChainSmall<N, HN_>::smem(g->Lmax, T, g->chain_small_items)); attr((const void*)k_chain_small<T, N, HN_, true>, ChainSmall<N, HN_>::smem(g->Lmax, T, g->chain_small_items));
         // the variants this group launches: training and dev steps at its own row padding, 128-row dev / test steps
         if (g->Hmax == 16) { if (g->npad == 64) { CS_ATTR(true, 64, 16) CS_ATTR(false, 64, 16) } else { CS_ATTR(true, 128, 16) } CS_ATTR(false, 128, 16) }
         else { if (g->npad == 64) { CS_ATTR(true, 64, 32) CS_ATTR(false, 64, 32) } else { CS_ATTR(true, 128, 32) } CS_ATTR(false, 128, 32) }
@@ -662,7 +673,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(FwdItem) * g->n_fwd_items, &g->fwd_items_ev, &g->items_ev_bytes);
     }
     { const char* de = getenv("MFAS_TC_DEBUG"); if (de) g->dbg = atoi(de); }
-    { const char* le = getenv("MFAS_L2_HINTS"); if (le) g->l2_hints = atoi(le) & 15; }
+    { const char* le = getenv("MFAS_L2_HINTS"); if (le) g->l2_hints = atoi(le) & 255; }
     if (e != cudaSuccess) {
       int code = fail(MFAS_ERR_CUDA, "tc engine setup: %s", cudaGetErrorString(e));
       mfas_group_destroy(g);
@@ -981,7 +992,7 @@ static int launch_step_tc(mfas_group* g, const DCache& cache, const BatchRef& ba
     g_launch_cluster = g->chain_cl;
 #define CA_(T, N, TH, ML, BM, PS) launch_k(2, k_chain_all<T, N, TH, ML>, dim3(g->n_cand * g->chain_cl), dim3(ChainCfg<N>::THREADS), g->smem_chain_all, st, (const DCand*)g->dc, cache, batch, (int)(BM), (const float*)g->part, (long long)(PS), g->hs_ld, g->lg_ld, g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, ho, terr, g->chain_cl)
 #define CA(T, N, TH) do { if (g->multilabel) CA_(T, N, TH, true, g->bmax, g->part_stride); else CA_(T, N, TH, false, g->bmax, g->part_stride); } while (0)
-#define CS_(T, N, HN_, ML, BM, PS) launch_k(2, k_chain_small<T, N, HN_, ML>, dim3(g->n_cand), dim3(ChainSmall<N, HN_>::THREADS), ChainSmall<N, HN_>::smem(g->Lmax, T), st, (const DCand*)g->dc, cache, batch, (int)(BM), (const float*)g->part, (long long)(PS), g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, ho, terr)
+#define CS_(T, N, HN_, ML, BM, PS) launch_k(2, k_chain_small<T, N, HN_, ML>, dim3(g->n_cand), dim3(ChainSmall<N, HN_>::THREADS), ChainSmall<N, HN_>::smem(g->Lmax, T, g->chain_small_items), st, (const DCand*)g->dc, cache, batch, (int)(BM), (const float*)g->part, (long long)(PS), g->adam, step_size, bc2_sqrt, g->drop_seed, g->drop_p, step, ho, terr, g->chain_small_items)
 #define CS(T, N, BM, PS) do { if (g->chain_small == 16) { if (g->multilabel) CS_(T, N, 16, true, BM, PS); else CS_(T, N, 16, false, BM, PS); } else { if (g->multilabel) CS_(T, N, 32, true, BM, PS); else CS_(T, N, 32, false, BM, PS); } } while (0)
     if (g->chain_small) {
       g_launch_cluster = 1;

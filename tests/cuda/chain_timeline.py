@@ -33,6 +33,15 @@ for i, n in enumerate(names):
 print("  total      %9.0f %9.0f" % (np.median(out[:, 2 * L + 1] - out[:, 0]), (out[:, 2 * L + 1] - out[:, 0]).max()))
 inner = out[:, 10:16]
 t0 = inner[:, 0]
+if H <= 32 and os.environ.get("MFAS_CHAIN_SMALL", "1") != "0":      # k_chain_small stamps (cycles since the kernel was entered)
+    k0 = out[:, 0]
+    print("k_chain_small, cycles since kernel entry (median): forward stream complete (griddepcontrol.wait) %d | weights, vectors, partial sums staged %d | fwd layers done %d | logits %d | head rows (softmax-CE, dlogits) %d | head done %d | end %d" % (
+        np.median(inner[:, 0] - k0), np.median(inner[:, 1] - k0), np.median(out[:, L] - k0), np.median(inner[:, 2] - k0), np.median(inner[:, 3] - k0),
+        np.median(out[:, L + 1] - k0), np.median(out[:, 2 * L + 1] - k0)))
+    if L > 1:
+        print("  inside forward layer 1 (cycles since the layer was entered, median): partial sums + W_hid h + bias + activation %d | BatchNorm statistics %d | layer end %d" % (
+            np.median(inner[:, 4] - out[:, 1]), np.median(inner[:, 5] - out[:, 1]), np.median(out[:, 2] - out[:, 1])))
+    sys.exit(0)
 print("inside forward layer 1 (cycles since the layer was entered, median): raw operand tiles landed (cp.async) %d | lo tiles written %d | MMAs issued %d | z complete (partials, MMA, bias, act) %d | BN stats %d | (layer end %d)" % (
     np.median(inner[:, 1] - t0), np.median(inner[:, 2] - t0), np.median(inner[:, 3] - t0), np.median(inner[:, 4] - t0),
     np.median(inner[:, 5] - t0), np.median(out[:, 2] - t0)))
