@@ -274,6 +274,8 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* 
   asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst_smem), "l"(src), "r"(n), "l"(policy) : "memory");
 }
 // the mbarrier receives one arrival from this thread once all of its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
 }
@@ -532,40 +534,54 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
 
 // ---------------------------------------------------------------------------------------------
 // forward, all layers, inner_repr 16 / 32 (the search default): the same persistent, warp-specialised stream as
-// k_tc_fwd_ws with the product TRANSPOSED -- z[b, h] = sum_k x[b, k] W[h, k]: A = the gathered x tile (M = NPAD batch rows),
+// k_tc_fwd_ws with the product TRANSPOSED -- z[b, h] = sum_k x[b, k] W[h, k]: A = the gathered x tile (batch rows),
 // B = the W tile (N = HN = 16 or 32 rows).  With W as the M operand (k_tc_fwd_ws) 112 or 96 of the 128 MMA rows are zeros,
-// yet every k-block moves the full 24 KB tile six times through shared memory and costs 12 x 32 tensor-pipe cycles (the
-// pipe's floor is max(M, 128) N / 256 cycles per MMA: N = 64 there, N = HN here): search256 on one B200 spent 174 us per
-// step in a forward stream whose bytes take 38 us.  Here a k-block is NPAD x 128 + HN x 128 bytes (10 KB at 64 x 16),
-// 12 x 8 cycles, and the ring holds 12 raw + 6 lo stages instead of 5 + 3.
-//   M = 64: the accumulator row b sits in TMEM lane 32 (b / 16) + b % 16 (tests/cuda/m64_test.cu); M = 128: lane b.
+// yet every k-block moves the full 24 KB tile six times through shared memory: search256 on one B200 spent 174 us per
+// step in a forward stream whose bytes take 38 us.
+// What a k-block costs here is not bytes but the fixed price of its steps -- ~40 cycles per tcgen05.mma on the issuing
+// thread however small the MMA, ~500 cycles for a converter pass (two barrier waits, a shared-memory round trip, a proxy
+// fence, an arrive) -- measured per role with clock stamps (tests/cuda/fwd_small_timeline.py,
+// profiles/r02dd_fwd_small_roles.txt: 12 MMAs = 518 cycles, a converter pass by all eight warps 1150).  So:
+//   * hi and lo tiles of a stage are ADJACENT, [x_hi | x_lo | W_hi | W_lo], and the split products are ONE MMA per 8 columns:
+//     64 batch rows:  A' = [x_hi; x_lo] (M = 128), B' = [W_hi; W_lo] (N = 2 HN): D = [hi hi | hi lo ; lo hi | lo lo] --
+//                     4 MMAs per k-block instead of 12 (lo lo comes for free); the epilogue adds the two column halves,
+//                     and the lo rows (TMEM lanes 64..127) to the hi rows through a 4 KB shared-memory exchange;
+//     128 batch rows: x_hi B' (N = 2 HN), then x_lo W_hi into the first HN columns: 8 MMAs per k-block;
+//   * the converter warps work in four pairs, each pair a k-block of its own (pair g: k-blocks g, g + 4, ...);
+//   * a loader warp signals "landed" once per stage (cp.async groups complete in order: the stage issued LAG k-blocks ago),
+//     not once per thread.
 // Work items, partial-sum layout (part[item][NPAD/4][Hp][4]: element (b, h) at ((b >> 2) Hp + h) 4 + (b & 3)) and the
 // consumers (chain kernels) are unchanged.
 // ---------------------------------------------------------------------------------------------
 template <int NPAD, int HN> struct FwdSmall {
-  static constexpr uint32_t A_BYTES = NPAD * 128, B_BYTES = HN * 128, TILE = A_BYTES + B_BYTES;
-  static constexpr int RAW = (int)(122880 / TILE), LO = (int)(61440 / TILE);
-  static constexpr size_t SMEM = 1024 + (size_t)(RAW + LO) * TILE;
-  static constexpr int LOADERS = 128, CONVERTERS = 256, THREADS = 17 * 32;
+  static constexpr uint32_t A_BYTES = NPAD * 128, B_BYTES = HN * 128, TILE = 2 * (A_BYTES + B_BYTES);
+  static constexpr uint32_t EX_BYTES = NPAD == 64 ? 2 * 64 * (HN + 1) * 4 : 0;       // lo-row sums of the two accumulator buffers
+  static constexpr int STAGES = (int)((230000 - EX_BYTES) / TILE);
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * TILE + EX_BYTES;
+  static constexpr int LOADERS = 128, CONVERTERS = 256, CGROUPS = 4, THREADS = 17 * 32;
 };
+
+#ifdef MFAS_KSTAMPS
+#define MFAS_KSTAMP(first, n, e) do { if (err.timeline && blockIdx.x == 0 && (n) >= (first) && (n) < (first) + 16) err.timeline[(first == 32 ? 0 : 128) + ((n) - (first)) * 8 + (e)] = clock64(); } while (0)
+#else
+#define MFAS_KSTAMP(first, n, e) do { } while (0)
+#endif
 
 template <int NPAD, int HN>
 __global__ void __launch_bounds__((FwdSmall<NPAD, HN>::THREADS), 1)
 k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchRef batch, float* part_base, TcErr err) {
   using Cfg = FwdSmall<NPAD, HN>;
-  constexpr int R = Cfg::RAW, LQ = Cfg::LO;
+  constexpr int S = Cfg::STAGES, CG = Cfg::CGROUPS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = umma::align1024(smem_raw);
-  uint8_t* lo_base = smem + R * Cfg::TILE;
-  __shared__ uint64_t landed[R], rawfree[R], lofull[LQ], lofree[LQ], tfull[2], tempty[2];
+  __shared__ uint64_t landed[S], split[S], sfree[S], tfull[2], tempty[2];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nrows = batch.n_rows;
-  constexpr uint32_t TM_COLS = 4 * HN < 32 ? 32 : 4 * HN;          // two accumulator buffers x (main + correction)
+  constexpr uint32_t TM_COLS = 4 * HN < 32 ? 32 : 4 * HN;          // two accumulator buffers x 2 HN columns
   if (warp == 0) umma::tmem_alloc(&tmem_slot, TM_COLS);
   if (tid == 32) {
-    for (int i = 0; i < R; ++i) { umma::mbar_init(&landed[i], Cfg::LOADERS); umma::mbar_init(&rawfree[i], 1); }
-    for (int i = 0; i < LQ; ++i) { umma::mbar_init(&lofull[i], Cfg::CONVERTERS / 32); umma::mbar_init(&lofree[i], 1); }
+    for (int i = 0; i < S; ++i) { umma::mbar_init(&landed[i], Cfg::LOADERS / 32); umma::mbar_init(&split[i], Cfg::CONVERTERS / 32 / CG); umma::mbar_init(&sfree[i], 1); }
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 4); }
     umma::fence_mbar_init();
   }
@@ -581,6 +597,7 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
   if (warp < 4) {
     // ================================ loaders (cp.async) ==========================================
     constexpr int XJ = NPAD / 16;                                  // x rows r + 16 j; W rows r + 16 j for j < HN / 16
+    constexpr int LAG = S / 2;                                     // stages a loader warp keeps in flight behind its completion signal
     const int r = tid >> 3, c = tid & 7;
     const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);   // sw128(r + 16 j, 16 c) = off + 2048 j
     const uint32_t s0 = umma::smem_u32(smem);
@@ -616,55 +633,68 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
       }
 #pragma unroll 1
       for (int kb = it.kb0; kb < it.kb1; ++kb, ++n) {
-        const int sg = n % R;
-        if (n >= R && !umma::mbar_wait(&rawfree[sg], ((n / R) & 1) ^ 1)) { ok = false; break; }
-        const uint32_t a = s0 + sg * Cfg::TILE + off, b = a + Cfg::A_BYTES;
+        const int sg = n % S;
+        if (n >= S && !umma::mbar_wait(&sfree[sg], ((n / S) & 1) ^ 1)) { ok = false; break; }
+        if (tid == 0) MFAS_KSTAMP(32, n, 7);
+        const uint32_t a = s0 + sg * Cfg::TILE + off, b = a + 2 * Cfg::A_BYTES;
         const bool ske = kb < it.fs_kb;
 #pragma unroll
-        for (int j = 0; j < XJ; ++j) if (!(err.l2_hints & 64)) cp_async16_zfill(a + j * 2048, (ske ? xs[j] : xr[j]) + 32LL * kb, r + 16 * j < nrows, x_policy);
+        for (int j = 0; j < XJ; ++j) cp_async16_zfill(a + j * 2048, (ske ? xs[j] : xr[j]) + 32LL * kb, r + 16 * j < nrows, x_policy);
         const float* w = wp + 32LL * kb;
 #pragma unroll
         for (int j = 0; j < HN / 16; ++j) cp_async16_zfill(b + j * 2048, w + j * wstride, r + 16 * j < it.rows_valid, stream_policy);
-        cp_async_arrive_noinc(&landed[sg]);
+        cp_async_commit();
+        if (tid == 0) MFAS_KSTAMP(32, n, 0);
+        if (n >= LAG) {
+          cp_async_wait<LAG>();
+          __syncwarp();
+          if (lane == 0) umma::mbar_arrive(&landed[(n - LAG) % S]);
+          if (tid == 0) MFAS_KSTAMP(32, n - LAG, 1);
+        }
       }
       cur = nxt; nxt = nx2;
 #pragma unroll
       for (int j = 0; j < XJ; ++j) rows_cur[j] = rows_nxt[j];
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) for (int m = max(0, n - LAG); m < n; ++m) umma::mbar_arrive(&landed[m % S]);
   } else if (warp < 12) {
     // ================================ converters ==================================================
+    // lo = rna_tf32(x - trunc_tf32(x)) of the x tile and of the W tile, into the same stage
     const int ct = tid - 128;
-    constexpr int NCH = (int)(Cfg::TILE / 16);                     // 16-byte chunks of a stage (elementwise: linear order)
+    constexpr int TG = Cfg::CONVERTERS / CG, NA = (int)(Cfg::A_BYTES / 16), NCH = (int)((Cfg::A_BYTES + Cfg::B_BYTES) / 16);
+    const int grp = ct / TG, gt = ct % TG;
     int total = 0;
     for (int i = 0; i < n_my; ++i) { const FwdItem& it = items[blockIdx.x + i * gridDim.x]; total += it.kb1 - it.kb0; }
 #pragma unroll 1
-    for (int n = 0; n < total; ++n) {
-      const int sg = n % R, sl = n % LQ;
-      if (!umma::mbar_wait(&landed[sg], (n / R) & 1)) { ok = false; break; }
-      if (n >= LQ && !umma::mbar_wait(&lofree[sl], ((n / LQ) & 1) ^ 1)) { ok = false; break; }
-      const float4* src = reinterpret_cast<const float4*>(smem + sg * Cfg::TILE);
-      float4* dst = reinterpret_cast<float4*>(lo_base + sl * Cfg::TILE);
+    for (int n = grp; n < total; n += CG) {
+      const int sg = n % S;
+      if (!umma::mbar_wait(&landed[sg], (n / S) & 1)) { ok = false; break; }
+      if (gt == 0) MFAS_KSTAMP(32, n, 2);
+      uint8_t* st = smem + sg * Cfg::TILE;
 #pragma unroll
-      for (int j = 0; j < (NCH + Cfg::CONVERTERS - 1) / Cfg::CONVERTERS; ++j) {
-        const int ch = ct + j * Cfg::CONVERTERS;
-        if (ch < NCH && !(err.l2_hints & 16)) {
-          const float4 x = src[ch];
+      for (int j = 0; j < (NCH + TG - 1) / TG; ++j) {
+        const int ch = gt + j * TG;
+        if (ch < NCH) {
+          const uint32_t so = ch < NA ? (uint32_t)ch * 16u : 2 * Cfg::A_BYTES + (uint32_t)(ch - NA) * 16u;
+          const float4 x = *reinterpret_cast<const float4*>(st + so);
           float4 l;
           l.x = umma::round_tf32(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
           l.y = umma::round_tf32(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
           l.z = umma::round_tf32(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
           l.w = umma::round_tf32(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
-          dst[ch] = l;
+          *reinterpret_cast<float4*>(st + so + (ch < NA ? Cfg::A_BYTES : Cfg::B_BYTES)) = l;
         }
       }
       umma::fence_async_smem();
       __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&lofull[sl]);
+      if (lane == 0) umma::mbar_arrive(&split[sg]);
+      if (gt == 0) MFAS_KSTAMP(32, n, 3);
     }
   } else if (warp == 12) {
     // ================================ MMA issuer ==================================================
-    constexpr uint32_t idesc = umma::idesc_tf32(NPAD, HN, false, false);
+    constexpr uint32_t idesc_cat = umma::idesc_tf32(128, 2 * HN, false, false), idesc_lo = umma::idesc_tf32(128, HN, false, false);
     int n = 0;
     auto nkb_of = [&](int i) { const FwdItem& it = items[blockIdx.x + i * gridDim.x]; return it.kb1 - it.kb0; };
     int nkb_next = n_my > 0 ? nkb_of(0) : 0;
@@ -673,36 +703,37 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
       if (i + 1 < n_my) nkb_next = nkb_of(i + 1);
       if (!umma::mbar_wait(&tempty[tb], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
       for (int k = 0; k < nkb; ++k, ++n) {
-        const int sg = n % R, sl = n % LQ;
-        if (!umma::mbar_wait(&lofull[sl], (n / LQ) & 1)) { ok = false; break; }
+        const int sg = n % S;
+        if (!umma::mbar_wait(&split[sg], (n / S) & 1)) { ok = false; break; }
+        if (lane == 0) MFAS_KSTAMP(32, n, 4);
         umma::tc_fence_after();
         if (umma::elect_one()) {
-          const uint32_t a_hi = umma::smem_u32(smem) + sg * Cfg::TILE, b_hi = a_hi + Cfg::A_BYTES;
-          const uint32_t a_lo = umma::smem_u32(lo_base) + sl * Cfg::TILE, b_lo = a_lo + Cfg::A_BYTES;
+          const uint32_t a_hi = umma::smem_u32(smem) + sg * Cfg::TILE, b_hi = a_hi + 2 * Cfg::A_BYTES;
+          const uint64_t da0 = umma::smem_desc(a_hi, 16, 1024), db0 = umma::smem_desc(b_hi, 16, 1024);
+          const uint32_t dt = tm + tb * 2 * HN;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t adv = ks * 32u;
-            const uint64_t dah = umma::smem_desc(a_hi + adv, 16, 1024), dal = umma::smem_desc(a_lo + adv, 16, 1024);
-            const uint64_t dbh = umma::smem_desc(b_hi + adv, 16, 1024), dbl = umma::smem_desc(b_lo + adv, 16, 1024);
             const uint32_t acc = (k > 0 || ks > 0) ? 1u : 0u;
-            umma::mma_tf32(tm + tb * 2 * HN, dah, dbh, idesc, acc);               // main accumulator: hi*hi only
-            if (!(err.l2_hints & 32)) {
-            umma::mma_tf32(tm + tb * 2 * HN + HN, dal, dbh, idesc, acc);          // correction accumulator
-            umma::mma_tf32(tm + tb * 2 * HN + HN, dah, dbl, idesc, 1u);
+            if (NPAD == 64) {
+              umma::mma_tf32(dt, da0 + 2 * ks, db0 + 2 * ks, idesc_cat, acc);               // [x_hi; x_lo] [W_hi; W_lo]^T
+            } else {
+              umma::mma_tf32(dt, da0 + 2 * ks, db0 + 2 * ks, idesc_cat, acc);               // x_hi [W_hi; W_lo]^T
+              umma::mma_tf32(dt, da0 + (Cfg::A_BYTES >> 4) + 2 * ks, db0 + 2 * ks, idesc_lo, 1u);   // x_lo W_hi^T into the first HN columns
             }
           }
-          umma::mma_commit(&rawfree[sg]);
-          umma::mma_commit(&lofree[sl]);
+          umma::mma_commit(&sfree[sg]);
           if (k == nkb - 1) umma::mma_commit(&tfull[tb]);
         }
         __syncwarp();
+        if (lane == 0) MFAS_KSTAMP(32, n, 5);
       }
     }
   } else {
     // ================================ epilogue ====================================================
     const int q = warp & 3;                                        // TMEM lane quarter this warp may read
-    // batch row of this thread's lane: M = 128 -> lane; M = 64 -> 16 rows in the first 16 lanes of every quarter
-    const int brow = NPAD == 128 ? q * 32 + lane : (lane < 16 ? q * 16 + lane : -1);
+    // 64 batch rows: lanes 0..63 hold the x_hi rows, 64..127 the x_lo rows of the same batch rows; 128: lane = batch row
+    const int brow = NPAD == 128 ? q * 32 + lane : (q & 1) * 32 + lane;
+    float* ex = reinterpret_cast<float*>(smem + (size_t)S * Cfg::TILE);          // [2][64][HN + 1]
     struct Ep { long long part_off; int rows_valid, Hp; };
     auto ep_of = [&](int i) { const FwdItem& f = items[blockIdx.x + i * gridDim.x]; return Ep{f.part_off, f.rows_valid, f.Hp}; };
     Ep ep_next = n_my > 0 ? ep_of(0) : Ep{0, 0, 0};
@@ -710,7 +741,7 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
       const Ep it = ep_next;
       if (i + 1 < n_my) ep_next = ep_of(i + 1);
       const int tb = i & 1;
-      if (!umma::mbar_wait(&tfull[tb], (i >> 1) & 1)) { ok = false; break; }
+      if (!umma::mbar_wait(&tfull[tb], (i >> 1) & 1)) ok = false;   // (no early exit: the four warps meet at the exchange barrier)
       umma::tc_fence_after();
       float v[HN], w[HN];
       if (HN == 16) {
@@ -720,15 +751,30 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
         umma::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 2 * HN), v);
         umma::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 2 * HN + HN), w);
       }
-      if (brow >= 0 && brow < nrows) {
-        float* dst = part_base + it.part_off + ((long long)(brow >> 2) * it.Hp) * 4 + (brow & 3);
-#pragma unroll
-        for (int h = 0; h < HN; ++h)
-          if (h < it.rows_valid) dst[h * 4] = v[h] + w[h];
-      }
       umma::tc_fence_before();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&tempty[tb]);
+#pragma unroll
+      for (int h = 0; h < HN; ++h) v[h] += w[h];
+      if (NPAD == 64) {
+        float* e = ex + ((size_t)tb * 64 + brow) * (HN + 1);
+        if (q >= 2) {
+#pragma unroll
+          for (int h = 0; h < HN; ++h) e[h] = v[h];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");              // the four epilogue warps (ex[tb] is next written two items on)
+        if (q < 2) {
+#pragma unroll
+          for (int h = 0; h < HN; ++h) v[h] += e[h];
+        }
+      }
+      if ((NPAD == 128 || q < 2) && brow < nrows) {
+        float* dst = part_base + it.part_off + ((long long)(brow >> 2) * it.Hp) * 4 + (brow & 3);
+#pragma unroll
+        for (int h = 0; h < HN; ++h)
+          if (h < it.rows_valid) dst[h * 4] = v[h];
+      }
+      if (!ok) break;
     }
   }
   if (!ok) atomicExch(err.flag, 6);
@@ -1850,8 +1896,9 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
     if (!ML) hr.lab[r] = (int)cache.labels[gr];
   }
   int stamp_i = 0;
-  auto stamp = [&]() { if (err.timeline && tid == 0 && stamp_i < 10) err.timeline[cand * 16 + stamp_i] = clock64(); ++stamp_i; };
-  auto stamp_at = [&](int i) { if (err.timeline && tid == 0) err.timeline[cand * 16 + i] = clock64(); };      // slots 10..: inside the phases
+  const bool tl_on = err.timeline && !(err.l2_hints & 2048);
+  auto stamp = [&]() { if (tl_on && tid == 0 && stamp_i < 10) err.timeline[cand * 16 + stamp_i] = clock64(); ++stamp_i; };
+  auto stamp_at = [&](int i) { if (tl_on && tid == 0) err.timeline[cand * 16 + i] = clock64(); };      // slots 10..: inside the phases
   stamp();
   __syncthreads();
   const DCand& cd = scd;
@@ -2042,7 +2089,7 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
     float acc[NR];
 #pragma unroll
     for (int i = 0; i < NR; ++i) acc[i] = 0.f;
-#pragma unroll 4
+#pragma unroll 1
     for (int j = 0; j < HN; j += 4) {
       const float w0 = w[j], w1 = w[j + 1], w2 = w[j + 2], w3 = w[j + 3];
 #pragma unroll
@@ -2404,7 +2451,13 @@ struct __align__(16) BwdTile {
   int cand, layer, kc0, h0;       // 16-byte aligned: the stagers read these four as one int4 (layer == L: the classifier)
   const float* alpha;             // alpha gates: &params[oalpha] of the tile's layer (pre-update value: the step's last launch updates it)
   int gate, slot;                 // gate: 0 none, 1 ske columns (x sigmoid(alpha)), 2 rgb columns (x (1 - sigmoid(alpha))); slot: tile index
+  // operand sources, resolved on the host (k_tc_bwd_small's loaders: no walk tile -> candidate -> layer per fill)
+  const float* xsrc;              // xkind 0: &hid[layer - 1][0][kc0 - d_ske - d_rgb] (classifier: &hid[L - 1][0][kc0]); else unused
+  const float* dz;                // &dzs[layer][0][h0] (classifier: &dlog[0][h0])
+  int xkind, xtap, xcol, xld;     // xkind 1 / 2: columns xcol.. of ske / rgb tap xtap, rows gathered by the batch; xld: row stride of xsrc
+  int dzld, hw, pad2, pad3;       // row stride of dz; valid dz columns of the tile
 };
+static_assert(sizeof(BwdTile) == 128, "one 128-byte line per tile record");
 constexpr int TC_DSP_PER_TILE = 8;                      // one d(loss)/d(sigmoid(alpha)) partial per Adam warp and tile
 constexpr int TC_WS_THREADS = 17 * 32;
 constexpr int WS_RING = 4;                              // ring slots per Adam warp (= batches per tile)
@@ -2414,8 +2467,6 @@ constexpr size_t TC_WS_SMEM = 1024 + 98304 + 8 * (size_t)WS_RING * WS_SLOT;
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint64_t policy) {
   asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(policy) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ALPHA (groups with the modality gates on): the staged x is unscaled, so the accumulator holds G = dz^T x; the weight gradient
 // of a gated tile is gate * G, and d(loss)/d(sigmoid(alpha)) = +- sum(W o G) over the tile (pre-update W) -- summed per Adam warp
@@ -2698,9 +2749,9 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
 // Batches above 64 rows: two passes over the 64-row stage into the same accumulator.
 // ---------------------------------------------------------------------------------------------
 template <int HN> struct BwdSmall {
-  static constexpr int BP = 64, RAW = 3, NB = HN / 8;               // NB: 8-row p / m / v batches per tile and warp = ring slots
+  static constexpr int BP = 64, RAW = HN <= 16 ? 3 : 2, LO = 2, NB = HN / 8;   // NB: 8-row p / m / v batches per tile and warp = ring slots
   static constexpr uint32_t A_BLK = BP * 128, A_BYTES = 4 * A_BLK, B_BYTES = BP * 128, TILE = A_BYTES + B_BYTES;
-  static constexpr size_t SMEM = 1024 + (size_t)(RAW + 1) * TILE + 4 * (size_t)NB * WS_SLOT;
+  static constexpr size_t SMEM = 1024 + (size_t)(RAW + LO) * TILE + 4 * (size_t)NB * WS_SLOT;
   static constexpr int THREADS = 17 * 32;
 };
 
@@ -2714,15 +2765,15 @@ k_tc_bwd_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, in
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = umma::align1024(smem_raw);
   uint8_t* lo_base = smem + R * TILE;
-  __shared__ uint64_t landed[R], rawfree[R], lofull, lofree, tfull[2], tempty[2];
+  __shared__ uint64_t landed[R], rawfree[R], lofull[2], lofree[2], tfull[2], tempty[2];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nrows = batch.n_rows;
-  constexpr uint32_t TM_COLS = 2 * HN < 32 ? 32 : 2 * HN;
+  constexpr uint32_t TM_COLS = 128;                                // two accumulator buffers x 64 columns (see the MMA issuer)
   if (warp == 0) umma::tmem_alloc(&tmem_slot, TM_COLS);
   if (tid == 32) {
     for (int i = 0; i < R; ++i) { umma::mbar_init(&landed[i], 128); umma::mbar_init(&rawfree[i], 1); }
-    umma::mbar_init(&lofull, 8); umma::mbar_init(&lofree, 1);
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&lofull[i], 4); umma::mbar_init(&lofree[i], 1); }
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 4); }
     umma::fence_mbar_init();
   }
@@ -2740,40 +2791,37 @@ k_tc_bwd_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, in
     // ================================ loaders =====================================================
     // warp w moves batch rows w, w + 4, ... of the pass: a row of the x tile is 512 contiguous bytes = one 16-byte chunk per lane
     struct Desc { const float* src; const float* dz; long long ld; int H, kw, hw, row0; int row[16]; };
+    struct Rec { int4 shape, id, ptrs, x, z; };          // the tile record's loader fields (one 128-byte line, fetched two fills ahead)
     const uint32_t s0 = umma::smem_u32(smem);
     const uint64_t x_policy = l2_stream_policy(false);
-    auto fetch_desc = [&](int f, Desc& d) {
-      const int i = npass == 1 ? f : (f >> 1), row0 = npass == 1 ? 0 : (f & 1) * BP;
-      const int4 t = *reinterpret_cast<const int4*>(&tiles[blockIdx.x + i * gridDim.x].cand);   // {cand, layer, kc0, h0}
-      const DCand& cd = cands[t.x];
-      const int H = cd.H, kc0 = t.z;
-      bool gather = true;
-      d.row0 = row0;
-      if (t.y >= cd.L) {                                // the classifier as one more layer: x = h_L, dz = dlogits[:, h0 : h0 + HN]
-        d.src = cd.hid + (long long)(cd.L - 1) * bmax * H + kc0; d.ld = H; gather = false;
-        d.H = TC_DLOG_LD; d.kw = min(TC_BWD_KT, H - kc0); d.hw = min(HN, TC_DLOG_LD - t.w);
-        d.dz = cd.dlog + t.w;
-      } else {
-        const DLayer& ly = cd.layer[t.y];
-        const int fs = ly.d_ske, fr = ly.d_rgb;
-        int seg_end = ly.K;
-        if (kc0 < fs) { d.src = cache.ske[ly.ske_tap] + kc0; d.ld = cache.ske_ld[ly.ske_tap]; seg_end = fs; }
-        else if (kc0 < fs + fr) { d.src = cache.rgb[ly.rgb_tap] + (kc0 - fs); d.ld = cache.rgb_ld[ly.rgb_tap]; seg_end = fs + fr; }
-        else { d.src = cd.hid + (long long)(t.y - 1) * bmax * H + (kc0 - fs - fr); d.ld = H; gather = false; }
-        d.H = H; d.kw = min(TC_BWD_KT, seg_end - kc0); d.hw = min(HN, H - t.w);
-        d.dz = cd.dzs + (long long)t.y * bmax * H + t.w;
-      }
+    auto fetch_rec = [&](int f) {
+      const int i = npass == 1 ? f : (f >> 1);
+      const int4* r = reinterpret_cast<const int4*>(tiles + blockIdx.x + (long long)i * gridDim.x);
+      Rec o; o.shape = __ldg(r + 2); o.id = __ldg(r + 3); o.ptrs = __ldg(r + 5); o.x = __ldg(r + 6); o.z = __ldg(r + 7);
+      return o;
+    };
+    auto open_desc = [&](int f, const Rec& rc, Desc& d) {
+      d.row0 = npass == 1 ? 0 : (f & 1) * BP;
+      const bool gather = rc.x.x != 0;
+      if (rc.x.x == 1) { d.src = cache.ske[rc.x.y] + rc.x.z; d.ld = cache.ske_ld[rc.x.y]; }
+      else if (rc.x.x == 2) { d.src = cache.rgb[rc.x.y] + rc.x.z; d.ld = cache.rgb_ld[rc.x.y]; }
+      else { d.src = reinterpret_cast<const float*>(((long long)(uint32_t)rc.ptrs.y << 32) | (uint32_t)rc.ptrs.x); d.ld = rc.x.w; }
+      d.dz = reinterpret_cast<const float*>(((long long)(uint32_t)rc.ptrs.w << 32) | (uint32_t)rc.ptrs.z);
+      d.H = rc.z.x; d.hw = rc.z.y; d.kw = rc.shape.y;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int r = min(row0 + warp + 4 * j, nrows - 1);
-        d.row[j] = gather ? batch_row(batch, t.x, r) : r;
+        const int r = min(d.row0 + warp + 4 * j, nrows - 1);
+        d.row[j] = gather ? batch_row(batch, rc.id.x, r) : r;
       }
     };
     Desc d{};
-    if (n_fill > 0) fetch_desc(0, d);
+    Rec rnext{};
+    if (n_fill > 0) open_desc(0, fetch_rec(0), d);
+    if (n_fill > 1) rnext = fetch_rec(1);
     for (int f = 0; f < n_fill; ++f) {
       const int sg = f % R;
       if (f >= R && !umma::mbar_wait(&rawfree[sg], ((f / R) & 1) ^ 1)) { ok = false; break; }
+      if (tid == 0) MFAS_KSTAMP(16, f, 7);
       const uint32_t a = s0 + sg * TILE, b = a + A_BYTES;
       const int c4 = lane;                              // x: 16-byte chunk c4 of the row's 512 bytes
 #pragma unroll
@@ -2793,69 +2841,82 @@ k_tc_bwd_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, in
         }
       }
       cp_async_arrive_noinc(&landed[sg]);
-      if (f + 1 < n_fill) fetch_desc(f + 1, d);         // descriptor + gather indices of the next fill while this one flies
+      if (tid == 0) MFAS_KSTAMP(16, f, 0);
+      if (f + 1 < n_fill) open_desc(f + 1, rnext, d);   // gather indices of the next fill (one load deep) while this one flies
+      if (f + 2 < n_fill) rnext = fetch_rec(f + 2);
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp < 12) {
     // ================================ converters ==================================================
-    const int ct = tid - 128;
+    // two groups of four warps, each with a lo stage of its own and every other fill: the split of fill f + 1 runs while the
+    // MMAs of fill f are issued (one lo stage and all eight warps on the same fill made split and MMA issue strictly alternate:
+    // 3900 cycles per tile)
+    const int ct = tid - 128, grp = ct >> 7, gt = ct & 127;
     constexpr int NCH = (int)(TILE / 16);
 #pragma unroll 1
-    for (int f = 0; f < n_fill; ++f) {
-      const int sg = f % R;
+    for (int f = grp; f < n_fill; f += 2) {
+      const int sg = f % R, k = f >> 1;
       if (!umma::mbar_wait(&landed[sg], (f / R) & 1)) { ok = false; break; }
-      if (f >= 1 && !umma::mbar_wait(&lofree, (f & 1) ^ 1)) { ok = false; break; }
+      if (gt == 0) MFAS_KSTAMP(16, f, 1);
+      if (k >= 1 && !umma::mbar_wait(&lofree[grp], (k & 1) ^ 1)) { ok = false; break; }
       const float4* src = reinterpret_cast<const float4*>(smem + sg * TILE);
-      float4* dst = reinterpret_cast<float4*>(lo_base);
-#pragma unroll
-      for (int j = 0; j < NCH / 256; ++j) {
-        const float4 x = src[ct + j * 256];
+      float4* dst = reinterpret_cast<float4*>(lo_base + grp * TILE);
+#pragma unroll 5
+      for (int j = 0; j < NCH / 128; ++j) {
+        const float4 x = src[gt + j * 128];
         float4 l;
         l.x = umma::round_tf32(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
         l.y = umma::round_tf32(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
         l.z = umma::round_tf32(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
         l.w = umma::round_tf32(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
-        dst[ct + j * 256] = l;
+        dst[gt + j * 128] = l;
       }
       umma::fence_async_smem();
       __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&lofull);
+      if (lane == 0) umma::mbar_arrive(&lofull[grp]);
+      if (gt == 0) MFAS_KSTAMP(16, f, 2);
     }
   } else if (warp == 12) {
     // ================================ MMA issuer ==================================================
-    constexpr uint32_t idesc = umma::idesc_tf32(128, HN, true, true);
+    // Two products per 8 batch rows instead of three: B' = [dz_hi | dz_lo] as ONE N = 32 + HN operand -- the MN-major
+    // descriptor's leading-dimension offset reaches from the raw stage's dz tile (columns 0..31) to the lo stage's (columns
+    // 32..) -- so x_hi is read from shared memory once for x_hi dz_hi (accumulator columns [0, HN)) and x_hi dz_lo (columns
+    // [32, 32 + HN)); x_lo dz_hi adds into [0, HN).  The Adam warps add the two column ranges.  (Issue of these small MMAs, ~40
+    // cycles each, is what the tile costs on this warp; columns [HN, 32) of the raw dz tile are never written nor read back.)
+    constexpr uint32_t idesc = umma::idesc_tf32(128, HN, true, true), idesc_cat = umma::idesc_tf32(128, 32 + HN, true, true);
     for (int f = 0; f < n_fill; ++f) {
-      const int i = npass == 1 ? f : (f >> 1), pass = npass == 1 ? 0 : (f & 1), tb = i & 1, sg = f % R;
-      if (!umma::mbar_wait(&lofull, f & 1)) { ok = false; break; }
+      const int i = npass == 1 ? f : (f >> 1), pass = npass == 1 ? 0 : (f & 1), tb = i & 1, sg = f % R, sl = f & 1;
+      if (!umma::mbar_wait(&lofull[sl], (f >> 1) & 1)) { ok = false; break; }
+      if (lane == 0) MFAS_KSTAMP(16, f, 3);
       if (pass == 0 && !umma::mbar_wait(&tempty[tb], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
       umma::tc_fence_after();
       if (umma::elect_one()) {
         const uint32_t a_hi = umma::smem_u32(smem) + sg * TILE, b_hi = a_hi + A_BYTES;
-        const uint32_t a_lo = umma::smem_u32(lo_base), b_lo = a_lo + A_BYTES;
-        const uint32_t dt = tm + tb * HN;
+        const uint32_t a_lo = umma::smem_u32(lo_base) + sl * TILE, b_lo = a_lo + A_BYTES;
+        const uint32_t dt = tm + tb * 64;
         const int ksteps = (min(BP, nrows - pass * BP) + 7) >> 3;
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint32_t adv = ks * 1024u;               // 8 batch rows = two 512-byte swizzle atoms
           const uint64_t dah = umma::smem_desc(a_hi + adv, A_BLK, 512, umma::kLayoutSw128Base32);
           const uint64_t dal = umma::smem_desc(a_lo + adv, A_BLK, 512, umma::kLayoutSw128Base32);
           const uint64_t dbh = umma::smem_desc(b_hi + adv, A_BLK, 512, umma::kLayoutSw128Base32);
-          const uint64_t dbl = umma::smem_desc(b_lo + adv, A_BLK, 512, umma::kLayoutSw128Base32);
-          umma::mma_tf32(dt, dal, dbh, idesc, (pass > 0 || ks > 0) ? 1u : 0u);
-          umma::mma_tf32(dt, dah, dbl, idesc, 1u);
-          umma::mma_tf32(dt, dah, dbh, idesc, 1u);
+          const uint64_t dbc = umma::smem_desc(b_hi + adv, b_lo - b_hi, 512, umma::kLayoutSw128Base32);
+          umma::mma_tf32(dt, dah, dbc, idesc_cat, (pass > 0 || ks > 0) ? 1u : 0u);
+          umma::mma_tf32(dt, dal, dbh, idesc, 1u);
         }
         umma::mma_commit(&rawfree[sg]);
-        umma::mma_commit(&lofree);
+        umma::mma_commit(&lofree[sl]);
         if (pass == npass - 1) umma::mma_commit(&tfull[tb]);
       }
       __syncwarp();
+      if (lane == 0) MFAS_KSTAMP(16, f, 4);
     }
   } else {
     // ================================ Adam warps ==================================================
     const int q = warp & 3;                            // TMEM lane quarter this warp may read = 32 weight columns of the tile
     const int aw = warp - 13;
     const float inv_bc2 = 1.f / bc2_sqrt;
-    uint8_t* ring = smem + (R + 1) * TILE + (size_t)aw * NB * WS_SLOT;
+    uint8_t* ring = smem + (R + Cfg::LO) * TILE + (size_t)aw * NB * WS_SLOT;
     const uint32_t ring_u32 = umma::smem_u32(ring);
     const int srow = lane >> 3, schunk = lane & 7;
     const uint64_t stream_policy = l2_stream_policy((err.l2_hints & 2) != 0);
@@ -2903,28 +2964,61 @@ k_tc_bwd_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, in
       }
       cp_async_commit();
     };
+    // The ring holds ONE tile of p / m / v ahead (3 x HN x 128 bytes per warp): a request issued while tile i is processed has
+    // one tile time to come back from HBM, so the tile time could not drop below the HBM latency (~2 us = the 3900 cycles per tile
+    // measured).  L2 is asked for the lines of the tile PF tiles ahead (prefetch.global.L2, one per 128-byte row segment), so
+    // the ring's own requests are L2 hits.
+    constexpr int PF = 4;
+    auto prefetch_tile = [&](const Raw& r) {
+      const float* W = reinterpret_cast<const float*>(((long long)(uint32_t)r.a.y << 32) | (uint32_t)r.a.x) + q * 32;
+      const long long moff = ((long long)(uint32_t)r.a.w << 32) | (uint32_t)r.a.z, voff = ((long long)(uint32_t)r.b.y << 32) | (uint32_t)r.b.x;
+      const int rows = min(HN, max(0, r.c.z));
+      if (r.c.y > q * 32) {
+        for (int t = lane; t < 3 * HN; t += 32) {
+          const int arr = t / HN, row = t % HN;
+          if (row < rows) prefetch_l2(W + (long long)row * r.c.x + (arr == 1 ? moff : arr == 2 ? voff : 0));
+        }
+      }
+    };
+    const bool pf_on = !(err.l2_hints & 128);
     Tile cur{}, nxt{};
-    Raw ahead{};
+    Raw ahead{}, far{};
+    if (pf_on) {
+      Raw r1{}, r2{}, r3{};
+      if (n_my > 1) r1 = fetch_raw(1);
+      if (n_my > 2) r2 = fetch_raw(2);
+      if (n_my > 3) r3 = fetch_raw(3);
+      if (n_my > 1) prefetch_tile(r1);
+      if (n_my > 2) prefetch_tile(r2);
+      if (n_my > 3) prefetch_tile(r3);
+    }
     if (n_my > 0) {
       cur = open_tile(fetch_raw(0));
 #pragma unroll
       for (int j = 0; j < NB; ++j) request(cur, j);
     }
     if (n_my > 1) ahead = fetch_raw(1);
+    if (n_my > PF) far = fetch_raw(PF);
     for (int i = 0; i < n_my; ++i) {
       const int tb = i & 1;
       const bool more = i + 1 < n_my;
       if (more) nxt = open_tile(ahead);
       if (i + 2 < n_my) ahead = fetch_raw(i + 2);
+      if (pf_on && i + PF < n_my) prefetch_tile(far);
+      if (i + PF + 1 < n_my) far = fetch_raw(i + PF + 1);
       if (!umma::mbar_wait(&tfull[tb], (i >> 1) & 1)) { ok = false; break; }
+      if (aw == 0 && lane == 0) MFAS_KSTAMP(16, i, 5);
       umma::tc_fence_after();
       float dsum = 0.f;
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         cp_async_wait<NB - 1>();
         __syncwarp();
-        float g[8];
-        umma::tmem_ld8(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * HN + 8 * j), g);
+        float g[8], g2[8];
+        umma::tmem_ld8(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 64 + 8 * j), g);
+        umma::tmem_ld8(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 64 + 32 + 8 * j), g2);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) g[r] += g2[r];
         if (cur.rc >> 8) {
           const float* sp = reinterpret_cast<const float*>(ring + j * WS_SLOT) + lane;
           float* w = cur.W + (long long)(8 * j) * cur.K + lane;
@@ -2959,6 +3053,7 @@ k_tc_bwd_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, in
       umma::tc_fence_before();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&tempty[tb]);
+      if (aw == 0 && lane == 0) MFAS_KSTAMP(16, i, 6);
       cur = nxt;
     }
     cp_async_wait<0>();

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -524,8 +525,18 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     g->smem_dzx = sizeof(float) * ((size_t)batch_max * g->Hmax + (TC_CB + 1) * (size_t)g->Hmax);
     e = pool_alloc_t(device, sizeof(int), &g->tc_err, &g->err_bytes);
     if (e == cudaSuccess) e = cudaMemset(g->tc_err, 0, sizeof(int));
+    // The limit is a property of the FUNCTION (per device), not of the group: groups whose kernels need different amounts
+    // (k_chain_small's depends on the deepest candidate, k_chain_all's on the head) may be alive together, on any host thread
+    // (fan-out) -- so the limit only ever grows: the largest request seen for (device, function) stays in force.
     auto attr = [&](const void* f, size_t bytes) {
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      static std::mutex mu;
+      static std::map<std::pair<int, const void*>, size_t> seen;
+      std::lock_guard<std::mutex> lk(mu);
+      size_t& cur = seen[std::make_pair(device, f)];
+      if (bytes > cur && e == cudaSuccess) {
+        e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess) cur = bytes;
+      }
     };
     attr((const void*)k_tc_fwd_all<64>, 1024 + 32768 + 2 * 64 * 128);
     attr((const void*)k_tc_fwd_all<128>, 1024 + 32768 + 2 * 128 * 128);
@@ -673,7 +684,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(FwdItem) * g->n_fwd_items, &g->fwd_items_ev, &g->items_ev_bytes);
     }
     { const char* de = getenv("MFAS_TC_DEBUG"); if (de) g->dbg = atoi(de); }
-    { const char* le = getenv("MFAS_L2_HINTS"); if (le) g->l2_hints = atoi(le) & 255; }
+    { const char* le = getenv("MFAS_L2_HINTS"); if (le) g->l2_hints = atoi(le) & 4095; }
     if (e != cudaSuccess) {
       int code = fail(MFAS_ERR_CUDA, "tc engine setup: %s", cudaGetErrorString(e));
       mfas_group_destroy(g);
@@ -788,16 +799,23 @@ static int sync_descriptors(mfas_group* g, cudaStream_t st) {
         r.moff = (long long)(d.m - d.p); r.voff = (long long)(d.v - d.p);
         r.goff = d.grad ? (long long)(d.grad - d.p) : 0;
         const int ht = g->bwd_small ? g->bwd_small : TC_BWD_HT;
+        r.xsrc = nullptr; r.xkind = 0; r.xtap = 0; r.xcol = 0; r.xld = d.H; r.pad2 = r.pad3 = 0;
         if (t.y >= d.L) {                               // classifier tile (tensor-core head): W_c [C][H], columns t.z.., rows t.w..
           r.W = d.p + d.oWc + (long long)t.w * d.H + t.z;
           r.K = d.H; r.kw = d.H - t.z < TC_BWD_KT ? d.H - t.z : TC_BWD_KT;
           r.rows = g->bwd_small ? (d.C - t.w < ht ? d.C - t.w : ht) : d.C;
+          r.xsrc = d.hid + (long long)(d.L - 1) * g->bmax * d.H + t.z;
+          r.dz = d.dlog + t.w; r.dzld = TC_DLOG_LD; r.hw = TC_DLOG_LD - t.w < ht ? TC_DLOG_LD - t.w : ht;
         } else {
           const DLayer& ly = d.layer[t.y];
           r.W = d.p + ly.oW + (long long)t.w * ly.K + t.z;
           const int seg_end = tc_bwd_seg_end(ly.d_ske, ly.d_rgb, ly.K, t.z);
           r.K = ly.K; r.kw = seg_end - t.z < TC_BWD_KT ? seg_end - t.z : TC_BWD_KT;
           r.rows = d.H - t.w < ht ? d.H - t.w : ht;
+          if (t.z < ly.d_ske) { r.xkind = 1; r.xtap = ly.ske_tap; r.xcol = t.z; }
+          else if (t.z < ly.d_ske + ly.d_rgb) { r.xkind = 2; r.xtap = ly.rgb_tap; r.xcol = t.z - ly.d_ske; }
+          else r.xsrc = d.hid + (long long)(t.y - 1) * g->bmax * d.H + (t.z - ly.d_ske - ly.d_rgb);
+          r.dz = d.dzs + (long long)t.y * g->bmax * d.H + t.w; r.dzld = d.H; r.hw = r.rows;
         }
         r.cand = t.x; r.layer = t.y; r.kc0 = t.z; r.h0 = t.w; r.pad1 = 0;
         r.alpha = nullptr; r.gate = 0; r.slot = (int)i;
