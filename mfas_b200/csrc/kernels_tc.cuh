@@ -248,11 +248,17 @@ struct __align__(16) FwdItem {
   int Hp, pad0, pad1, pad2;       // H rounded up to 128: rows of the partial-sum tile
 };
 
-template <int NPAD, int XR = 0> struct FwdWs {     // XR: extra raw stages (XR = 1 fills the 227 KB of an SM)
-  static constexpr int RAW = (NPAD == 64 ? 5 : 4) + XR, LO = NPAD == 64 ? 3 : 2;
-  static constexpr uint32_t A_BYTES = 16384, B_BYTES = NPAD * 128, TILE = A_BYTES + B_BYTES;
-  static constexpr size_t SMEM = 1024 + (size_t)(RAW + LO) * TILE;
-  static constexpr int LOADERS = 128, CONVERTERS = 256, THREADS = 17 * 32;
+// Stage layout (r02): raw stage = [W_hi 16 KB | x_hi | x_lo] -- the x halves ADJACENT, so that [x_hi; x_lo] is one N = 2 NPAD
+// operand -- and a ring of W_lo tiles.  Per 8 columns: W_hi [x_hi; x_lo]^T -> [main | correction] accumulator columns in ONE MMA
+// (W_hi is read from shared memory once instead of twice), W_lo x_hi^T -> correction: 8 MMAs per k-block instead of 12 (what a
+// k-block cost on the issuing thread: ~70 cycles per MMA, profiles/r02dk_roles.txt).  The converter warps work in two groups of
+// four, each with a W_lo stage of its own and every other k-block (a pass is two barrier waits, a shared-memory round trip, a
+// proxy fence and an arrive: its latency, not its bytes, was the converters' rate).
+template <int NPAD, int XR = 0> struct FwdWs {     // XR = 1: one raw stage less, one W_lo stage more (A/B switch MFAS_FWD_XR)
+  static constexpr int RAW = (NPAD == 64 ? 6 : 4) - XR, LO = 2 + XR;
+  static constexpr uint32_t A_BYTES = 16384, B_BYTES = NPAD * 128, TILE = A_BYTES + 2 * B_BYTES, LO_TILE = A_BYTES;
+  static constexpr size_t SMEM = 1024 + (size_t)RAW * TILE + (size_t)LO * LO_TILE;
+  static constexpr int LOADERS = 128, CONVERTERS = 256, CGROUPS = 2, THREADS = 17 * 32;
 };
 
 // L2 eviction priority for the streams that are read exactly once per launch (weights, Adam moments, gathered feature
@@ -289,6 +295,12 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
 //             a row outside the tensor and arrive as zeros.
 // All of a stage's copies complete on landed[stage] through complete_tx; the 16 x (NPAD / 4 + 1) address computations and
 // issue slots per k-block that 4 loader warps spent on cp.async become NPAD / 4 + 1 instructions of one warp.
+// role clock stamps of the persistent streams (diagnostic builds only: tests/cuda/fwd_small_timeline.py): event e of step n of CTA 0
+#ifdef MFAS_KSTAMPS
+#define MFAS_KSTAMP(first, n, e) do { if (err.timeline && blockIdx.x == 0 && (n) >= (first) && (n) < (first) + 16) err.timeline[(first == 32 ? 0 : 128) + ((n) - (first)) * 8 + (e)] = clock64(); } while (0)
+#else
+#define MFAS_KSTAMP(first, n, e) do { } while (0)
+#endif
 struct TapMaps { CUtensorMap ske[MFAS_NUM_TAPS], rgb[MFAS_NUM_TAPS]; };      // feature taps of one cache: dims {width, n_rows}, box {32, 1}
 
 template <int NPAD, int XR>
@@ -308,7 +320,7 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
   if (tid == 32) {
     // use_tma: 0 = cp.async loaders, 1 = W tiles through TMA + x through cp.async, 2 = W through TMA + x through tile::gather4
     for (int i = 0; i < R; ++i) { umma::mbar_init(&landed[i], use_tma == 2 ? 1 : Cfg::LOADERS + (use_tma ? 1 : 0)); umma::mbar_init(&rawfree[i], 1); }
-    for (int i = 0; i < LQ; ++i) { umma::mbar_init(&lofull[i], Cfg::CONVERTERS / 32); umma::mbar_init(&lofree[i], 1); }
+    for (int i = 0; i < LQ; ++i) { umma::mbar_init(&lofull[i], Cfg::CONVERTERS / 32 / Cfg::CGROUPS); umma::mbar_init(&lofree[i], 1); }
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 4); }
     umma::fence_mbar_init();
   }
@@ -352,7 +364,7 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
           if (n >= R && !umma::mbar_wait(&rawfree[sg], ((n / R) & 1) ^ 1)) { ok = false; break; }
           const uint32_t a = s0 + sg * Cfg::TILE, b = a + Cfg::A_BYTES;
           if (lane == 0) {
-            umma::mbar_arrive_expect_tx(&landed[sg], Cfg::TILE);
+            umma::mbar_arrive_expect_tx(&landed[sg], Cfg::A_BYTES + Cfg::B_BYTES);
             umma::tma_load_2d(a, wm, 32 * kb, 0, &landed[sg], stream_policy);
           }
           __syncwarp();
@@ -413,6 +425,7 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
       for (int kb = it.kb0; kb < it.kb1; ++kb, ++n) {
         const int sg = n % R;
         if (n >= R && !umma::mbar_wait(&rawfree[sg], ((n / R) & 1) ^ 1)) { ok = false; break; }
+        if (tid == 0) MFAS_KSTAMP(32, n, 7);
         const uint32_t a = s0 + sg * Cfg::TILE + off, b = a + Cfg::A_BYTES;
         const float* w = wp + 32LL * kb;
         if (use_tma) {                                             // the W tile: one TMA box, issued by one thread
@@ -428,6 +441,7 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
 #pragma unroll
         for (int j = 0; j < XJ; ++j) cp_async16_zfill(b + j * 2048, (ske ? xs[j] : xr[j]) + 32LL * kb, r + 16 * j < nrows, x_policy);
         cp_async_arrive_noinc(&landed[sg]);
+        if (tid == 0) MFAS_KSTAMP(32, n, 0);
       }
       cur = nxt; nxt = nx2;
 #pragma unroll
@@ -436,36 +450,44 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
     asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp < 12) {
     // ================================ converters ==================================================
+    // group g: k-blocks g, g + CG, ...; x_lo goes next to x_hi in the raw stage, W_lo into the group's turn of the W_lo ring
     const int ct = tid - 128;
-    constexpr int CJ = (int)(Cfg::TILE / 16) / Cfg::CONVERTERS;    // 16-byte chunks per thread (elementwise: linear order)
+    constexpr int CG = Cfg::CGROUPS, TG = Cfg::CONVERTERS / CG;
+    constexpr int NA = (int)(Cfg::A_BYTES / 16), NCH = (int)((Cfg::A_BYTES + Cfg::B_BYTES) / 16), CJ = NCH / TG;
+    const int grp = ct / TG, gt = ct % TG;
     int total = 0;
     for (int i = 0; i < n_my; ++i) { const FwdItem& it = items[blockIdx.x + i * gridDim.x]; total += it.kb1 - it.kb0; }
 #pragma unroll 1
-    for (int n = 0; n < total; ++n) {
+    for (int n = grp; n < total; n += CG) {
       const int sg = n % R, sl = n % LQ;
       if (!umma::mbar_wait(&landed[sg], (n / R) & 1)) { ok = false; break; }
+      if (gt == 0) MFAS_KSTAMP(32, n, 2);
       if (n >= LQ && !umma::mbar_wait(&lofree[sl], ((n / LQ) & 1) ^ 1)) { ok = false; break; }
-      const float4* src = reinterpret_cast<const float4*>(smem + sg * Cfg::TILE) + ct;
-      float4* dst = reinterpret_cast<float4*>(lo_base + sl * Cfg::TILE) + ct;
+      if (gt == 0) MFAS_KSTAMP(32, n, 6);
+      uint8_t* st = smem + sg * Cfg::TILE;
+      uint8_t* wl = lo_base + sl * Cfg::LO_TILE;
       float4 x[CJ];
 #pragma unroll
-      for (int j = 0; j < CJ; ++j) x[j] = src[j * Cfg::CONVERTERS];
+      for (int j = 0; j < CJ; ++j) x[j] = *reinterpret_cast<const float4*>(st + (size_t)(gt + j * TG) * 16);      // W_hi then x_hi: contiguous
 #pragma unroll
       for (int j = 0; j < CJ; ++j) {
+        const int ch = gt + j * TG;
         float4 l;
         l.x = umma::round_tf32(x[j].x - __uint_as_float(__float_as_uint(x[j].x) & 0xFFFFE000u));
         l.y = umma::round_tf32(x[j].y - __uint_as_float(__float_as_uint(x[j].y) & 0xFFFFE000u));
         l.z = umma::round_tf32(x[j].z - __uint_as_float(__float_as_uint(x[j].z) & 0xFFFFE000u));
         l.w = umma::round_tf32(x[j].w - __uint_as_float(__float_as_uint(x[j].w) & 0xFFFFE000u));
-        dst[j * Cfg::CONVERTERS] = l;
+        if (ch < NA) *reinterpret_cast<float4*>(wl + (size_t)ch * 16) = l;
+        else *reinterpret_cast<float4*>(st + Cfg::B_BYTES + (size_t)ch * 16) = l;
       }
       umma::fence_async_smem();                                    // lo (generic proxy) and the landed raw tile -> tensor core
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&lofull[sl]);
+      if (gt == 0) MFAS_KSTAMP(32, n, 3);
     }
   } else if (warp == 12) {
     // ================================ MMA issuer ==================================================
-    constexpr uint32_t idesc = umma::idesc_tf32(128, NPAD, false, false);
+    constexpr uint32_t idesc = umma::idesc_tf32(128, NPAD, false, false), idesc_cat = umma::idesc_tf32(128, 2 * NPAD, false, false);
     int n = 0;
     auto nkb_of = [&](int i) { const FwdItem& it = items[blockIdx.x + i * gridDim.x]; return it.kb1 - it.kb0; };
     int nkb_next = n_my > 0 ? nkb_of(0) : 0;                       // one item ahead: the issue loop never waits for a descriptor
@@ -476,25 +498,25 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
       for (int k = 0; k < nkb; ++k, ++n) {
         const int sg = n % R, sl = n % LQ;
         if (!umma::mbar_wait(&lofull[sl], (n / LQ) & 1)) { ok = false; break; }
+        if (lane == 0) MFAS_KSTAMP(32, n, 4);
         umma::tc_fence_after();
         if (umma::elect_one()) {
           const uint32_t a_hi = umma::smem_u32(smem) + sg * Cfg::TILE, b_hi = a_hi + Cfg::A_BYTES;
-          const uint32_t a_lo = umma::smem_u32(lo_base) + sl * Cfg::TILE, b_lo = a_lo + Cfg::A_BYTES;
+          const uint32_t a_lo = umma::smem_u32(lo_base) + sl * Cfg::LO_TILE;
+          const uint64_t dah0 = umma::smem_desc(a_hi, 16, 1024), dal0 = umma::smem_desc(a_lo, 16, 1024), dbh0 = umma::smem_desc(b_hi, 16, 1024);
+          const uint32_t dt = tm + tb * 2 * NPAD;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t adv = ks * 32u;
-            const uint64_t dah = umma::smem_desc(a_hi + adv, 16, 1024), dal = umma::smem_desc(a_lo + adv, 16, 1024);
-            const uint64_t dbh = umma::smem_desc(b_hi + adv, 16, 1024), dbl = umma::smem_desc(b_lo + adv, 16, 1024);
             const uint32_t acc = (k > 0 || ks > 0) ? 1u : 0u;
-            umma::mma_tf32(tm + tb * 2 * NPAD, dah, dbh, idesc, acc);             // main accumulator: hi*hi only
-            umma::mma_tf32(tm + tb * 2 * NPAD + NPAD, dal, dbh, idesc, acc);      // correction accumulator
-            umma::mma_tf32(tm + tb * 2 * NPAD + NPAD, dah, dbl, idesc, 1u);
+            umma::mma_tf32(dt, dah0 + 2 * ks, dbh0 + 2 * ks, idesc_cat, acc);     // W_hi [x_hi; x_lo]^T -> [main | correction]
+            umma::mma_tf32(dt + NPAD, dal0 + 2 * ks, dbh0 + 2 * ks, idesc, 1u);   // W_lo x_hi^T -> correction
           }
           umma::mma_commit(&rawfree[sg]);
           umma::mma_commit(&lofree[sl]);
           if (k == nkb - 1) umma::mma_commit(&tfull[tb]);
         }
         __syncwarp();
+        if (lane == 0) MFAS_KSTAMP(32, n, 5);
       }
     }
   } else {
@@ -546,7 +568,7 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
 //     64 batch rows:  A' = [x_hi; x_lo] (M = 128), B' = [W_hi; W_lo] (N = 2 HN): D = [hi hi | hi lo ; lo hi | lo lo] --
 //                     4 MMAs per k-block instead of 12 (lo lo comes for free); the epilogue adds the two column halves,
 //                     and the lo rows (TMEM lanes 64..127) to the hi rows through a 4 KB shared-memory exchange;
-//     128 batch rows: x_hi B' (N = 2 HN), then x_lo W_hi into the first HN columns: 8 MMAs per k-block;
+//     128 batch rows: x_hi B' (N = 2 HN), then x_lo W_hi into the second half: 8 MMAs per k-block;
 //   * the converter warps work in four pairs, each pair a k-block of its own (pair g: k-blocks g, g + 4, ...);
 //   * a loader warp signals "landed" once per stage (cp.async groups complete in order: the stage issued LAG k-blocks ago),
 //     not once per thread.
@@ -561,11 +583,6 @@ template <int NPAD, int HN> struct FwdSmall {
   static constexpr int LOADERS = 128, CONVERTERS = 256, CGROUPS = 4, THREADS = 17 * 32;
 };
 
-#ifdef MFAS_KSTAMPS
-#define MFAS_KSTAMP(first, n, e) do { if (err.timeline && blockIdx.x == 0 && (n) >= (first) && (n) < (first) + 16) err.timeline[(first == 32 ? 0 : 128) + ((n) - (first)) * 8 + (e)] = clock64(); } while (0)
-#else
-#define MFAS_KSTAMP(first, n, e) do { } while (0)
-#endif
 
 template <int NPAD, int HN>
 __global__ void __launch_bounds__((FwdSmall<NPAD, HN>::THREADS), 1)
@@ -581,7 +598,7 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
   constexpr uint32_t TM_COLS = 4 * HN < 32 ? 32 : 4 * HN;          // two accumulator buffers x 2 HN columns
   if (warp == 0) umma::tmem_alloc(&tmem_slot, TM_COLS);
   if (tid == 32) {
-    for (int i = 0; i < S; ++i) { umma::mbar_init(&landed[i], Cfg::LOADERS / 32); umma::mbar_init(&split[i], Cfg::CONVERTERS / 32 / CG); umma::mbar_init(&sfree[i], 1); }
+    for (int i = 0; i < S; ++i) { umma::mbar_init(&landed[i], Cfg::LOADERS); umma::mbar_init(&split[i], Cfg::CONVERTERS / 32 / CG); umma::mbar_init(&sfree[i], 1); }
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 4); }
     umma::fence_mbar_init();
   }
@@ -597,7 +614,6 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
   if (warp < 4) {
     // ================================ loaders (cp.async) ==========================================
     constexpr int XJ = NPAD / 16;                                  // x rows r + 16 j; W rows r + 16 j for j < HN / 16
-    constexpr int LAG = S / 2;                                     // stages a loader warp keeps in flight behind its completion signal
     const int r = tid >> 3, c = tid & 7;
     const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);   // sw128(r + 16 j, 16 c) = off + 2048 j
     const uint32_t s0 = umma::smem_u32(smem);
@@ -643,22 +659,17 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
         const float* w = wp + 32LL * kb;
 #pragma unroll
         for (int j = 0; j < HN / 16; ++j) cp_async16_zfill(b + j * 2048, w + j * wstride, r + 16 * j < it.rows_valid, stream_policy);
-        cp_async_commit();
+        // completion: every thread's cp.async.mbarrier.arrive fires when ITS copies have landed -- the loaders never wait for
+        // data, so all S stages can be in flight (a gathered row takes ~3500 cycles under load; a per-warp signal behind
+        // cp.async.wait_group held the stream to wait-depth / latency, profiles/r02dk_roles.txt)
+        cp_async_arrive_noinc(&landed[sg]);
         if (tid == 0) MFAS_KSTAMP(32, n, 0);
-        if (n >= LAG) {
-          cp_async_wait<LAG>();
-          __syncwarp();
-          if (lane == 0) umma::mbar_arrive(&landed[(n - LAG) % S]);
-          if (tid == 0) MFAS_KSTAMP(32, n - LAG, 1);
-        }
       }
       cur = nxt; nxt = nx2;
 #pragma unroll
       for (int j = 0; j < XJ; ++j) rows_cur[j] = rows_nxt[j];
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncwarp();
-    if (lane == 0) for (int m = max(0, n - LAG); m < n; ++m) umma::mbar_arrive(&landed[m % S]);
   } else if (warp < 12) {
     // ================================ converters ==================================================
     // lo = rna_tf32(x - trunc_tf32(x)) of the x tile and of the W tile, into the same stage
@@ -718,7 +729,7 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
               umma::mma_tf32(dt, da0 + 2 * ks, db0 + 2 * ks, idesc_cat, acc);               // [x_hi; x_lo] [W_hi; W_lo]^T
             } else {
               umma::mma_tf32(dt, da0 + 2 * ks, db0 + 2 * ks, idesc_cat, acc);               // x_hi [W_hi; W_lo]^T
-              umma::mma_tf32(dt, da0 + (Cfg::A_BYTES >> 4) + 2 * ks, db0 + 2 * ks, idesc_lo, 1u);   // x_lo W_hi^T into the first HN columns
+              umma::mma_tf32(dt + HN, da0 + (Cfg::A_BYTES >> 4) + 2 * ks, db0 + 2 * ks, idesc_lo, 1u);   // x_lo W_hi^T -> the second (correction) half
             }
           }
           umma::mma_commit(&sfree[sg]);
@@ -1689,6 +1700,9 @@ k_chain_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
   }
   ChainCtx cx;
   int stamp_i = 0;
+#ifdef MFAS_KSTAMPS
+  err.timeline = nullptr;          // the buffer belongs to the streams' role stamps in such a build
+#endif
   auto stamp = [&]() { if (err.timeline && tid == 0 && rank == 0 && stamp_i < 16) err.timeline[cand * 16 + stamp_i] = clock64(); ++stamp_i; };
   stamp();
   chain_ctx_open<NPAD>(cx, smem_raw, &bar, &tmem_slot, &ok_flag);      // (__syncthreads inside: scd is visible)
@@ -1896,7 +1910,11 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
     if (!ML) hr.lab[r] = (int)cache.labels[gr];
   }
   int stamp_i = 0;
-  const bool tl_on = err.timeline && !(err.l2_hints & 2048);
+#ifdef MFAS_KSTAMPS
+  const bool tl_on = false;                          // the buffer belongs to the streams' role stamps in such a build
+#else
+  const bool tl_on = err.timeline != nullptr;
+#endif
   auto stamp = [&]() { if (tl_on && tid == 0 && stamp_i < 10) err.timeline[cand * 16 + stamp_i] = clock64(); ++stamp_i; };
   auto stamp_at = [&](int i) { if (tl_on && tid == 0) err.timeline[cand * 16 + i] = clock64(); };      // slots 10..: inside the phases
   stamp();
@@ -2964,48 +2982,19 @@ k_tc_bwd_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, in
       }
       cp_async_commit();
     };
-    // The ring holds ONE tile of p / m / v ahead (3 x HN x 128 bytes per warp): a request issued while tile i is processed has
-    // one tile time to come back from HBM, so the tile time could not drop below the HBM latency (~2 us = the 3900 cycles per tile
-    // measured).  L2 is asked for the lines of the tile PF tiles ahead (prefetch.global.L2, one per 128-byte row segment), so
-    // the ring's own requests are L2 hits.
-    constexpr int PF = 4;
-    auto prefetch_tile = [&](const Raw& r) {
-      const float* W = reinterpret_cast<const float*>(((long long)(uint32_t)r.a.y << 32) | (uint32_t)r.a.x) + q * 32;
-      const long long moff = ((long long)(uint32_t)r.a.w << 32) | (uint32_t)r.a.z, voff = ((long long)(uint32_t)r.b.y << 32) | (uint32_t)r.b.x;
-      const int rows = min(HN, max(0, r.c.z));
-      if (r.c.y > q * 32) {
-        for (int t = lane; t < 3 * HN; t += 32) {
-          const int arr = t / HN, row = t % HN;
-          if (row < rows) prefetch_l2(W + (long long)row * r.c.x + (arr == 1 ? moff : arr == 2 ? voff : 0));
-        }
-      }
-    };
-    const bool pf_on = !(err.l2_hints & 128);
     Tile cur{}, nxt{};
-    Raw ahead{}, far{};
-    if (pf_on) {
-      Raw r1{}, r2{}, r3{};
-      if (n_my > 1) r1 = fetch_raw(1);
-      if (n_my > 2) r2 = fetch_raw(2);
-      if (n_my > 3) r3 = fetch_raw(3);
-      if (n_my > 1) prefetch_tile(r1);
-      if (n_my > 2) prefetch_tile(r2);
-      if (n_my > 3) prefetch_tile(r3);
-    }
+    Raw ahead{};
     if (n_my > 0) {
       cur = open_tile(fetch_raw(0));
 #pragma unroll
       for (int j = 0; j < NB; ++j) request(cur, j);
     }
     if (n_my > 1) ahead = fetch_raw(1);
-    if (n_my > PF) far = fetch_raw(PF);
     for (int i = 0; i < n_my; ++i) {
       const int tb = i & 1;
       const bool more = i + 1 < n_my;
       if (more) nxt = open_tile(ahead);
       if (i + 2 < n_my) ahead = fetch_raw(i + 2);
-      if (pf_on && i + PF < n_my) prefetch_tile(far);
-      if (i + PF + 1 < n_my) far = fetch_raw(i + PF + 1);
       if (!umma::mbar_wait(&tfull[tb], (i >> 1) & 1)) { ok = false; break; }
       if (aw == 0 && lane == 0) MFAS_KSTAMP(16, i, 5);
       umma::tc_fence_after();

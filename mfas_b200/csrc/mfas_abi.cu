@@ -684,7 +684,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(FwdItem) * g->n_fwd_items, &g->fwd_items_ev, &g->items_ev_bytes);
     }
     { const char* de = getenv("MFAS_TC_DEBUG"); if (de) g->dbg = atoi(de); }
-    { const char* le = getenv("MFAS_L2_HINTS"); if (le) g->l2_hints = atoi(le) & 4095; }
+    { const char* le = getenv("MFAS_L2_HINTS"); if (le) g->l2_hints = atoi(le) & 15; }
     if (e != cudaSuccess) {
       int code = fail(MFAS_ERR_CUDA, "tc engine setup: %s", cudaGetErrorString(e));
       mfas_group_destroy(g);

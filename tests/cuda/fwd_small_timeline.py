@@ -1,20 +1,27 @@
-"""Diagnostic (GPU box): per-k-block clock stamps of the roles of k_tc_fwd_small (CTA 0, k-blocks 32..47), in SM clocks."""
-import os, sys
+"""Diagnostic (GPU box): clock stamps of the roles (loader, converter, MMA issuer, epilogue / Adam) of k_tc_fwd_small (CTA 0,
+k-blocks 32..47) and k_tc_bwd_small (CTA 0, fills 16..31), in SM clocks.  The stamps are compiled in with -DMFAS_KSTAMPS only:
+the same sources are built into /tmp and loaded through MFAS_LIB_PATH (as profiles/run_gpu_sanitize.sh does)."""
+import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 os.environ["MFAS_CHAIN_TIMELINE"] = "1"
-os.environ["MFAS_L2_HINTS"] = str(int(os.environ.get("MFAS_L2_HINTS", "1")) | 2048)
+LIB = "/tmp/_mfas_kstamps.so"
+subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "--cudart", "static",
+                "-DMFAS_KSTAMPS", "-w", "-o", LIB, os.path.join(ROOT, "mfas_b200/csrc/mfas_abi.cu"), os.path.join(ROOT, "mfas_b200/csrc/host_init.cpp")], check=True)
+os.environ["MFAS_LIB_PATH"] = LIB
 import numpy as np, torch
 from mfas_b200 import _lib
 from mfas_b200.cache import synthetic_ntu_cache
 from mfas_b200.engine import CandidateGroup
 rows32 = [[i, j, k] for i in range(4) for j in range(4) for k in range(2)]
 parents = [[3, 1, 1], [1, 3, 0], [1, 1, 1], [3, 3, 0], [2, 2, 0], [0, 0, 1], [3, 2, 0], [2, 3, 1]]
-M = int(os.environ.get("TL_M", "256"))
+M, H = int(os.environ.get("TL_M", "256")), int(os.environ.get("TL_H", "16"))
 confs = [np.array([p, r]) for p in parents for r in rows32][:M]
+if H > 32:                                            # cfg2: the stamps are then those of k_tc_fwd_ws (the backward table stays empty)
+    confs = [np.array([[3, 1, 1], [1, 3, 0], [1, 1, 1], [3, 3, 0]])] * M
 B = 64
 train = synthetic_ntu_cache(4096, 3).to("cuda:0")
-g = CandidateGroup(confs, 16, 60, _lib.FLAG_BN, "cuda:0", batch_max=B)
+g = CandidateGroup(confs, H, 60, _lib.FLAG_BN, "cuda:0", batch_max=B)
 g.set_adam(0.9, 0.999, 1e-8, 1e-4); g.params.uniform_(-0.03, 0.03); g.bufs.fill_(1.0)
 rows = torch.stack([torch.randperm(4096)[:B] for _ in range(M)]).to("cuda:0", torch.int32)
 for it in range(6):
@@ -23,8 +30,8 @@ out = np.zeros((M, 16), np.int64)
 _lib.check(_lib.lib().mfas_group_chain_timeline(g._h, out.ctypes.data, M))
 t = out.reshape(-1)[:128].reshape(16, 8)
 t0 = t[0, 0]
-names = ["ld issued", "ld landed*", "cv saw landed", "cv arrived lofull", "mma saw lofull", "mma issued", "cv saw lofree", "ld saw rawfree"]
-print("k-block | " + " | ".join(names[:8]) + "   (cycles since k-block 32 was issued; * = signalled by the loader warp, LAG k-blocks later)")
+names = ["ld issued", "-", "cv saw landed", "cv split done", "mma saw split", "mma issued", "(fwd_ws: cv saw lofree)", "ld saw free"]
+print("k-block | " + " | ".join(names[:8]) + "   (cycles since k-block 32 was issued)")
 for i in range(16):
     print("%7d | " % (32 + i) + " | ".join("%8d" % (t[i, e] - t0) for e in range(8)))
 d = np.diff(t[:, 5])
