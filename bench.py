@@ -639,7 +639,7 @@ def run_ours(a):
         except Exception as ex:                      # profiling is an aid, never the measurement itself
             kernels = [{"error": str(ex)}]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "profiles/r02_ncu_traffic.json (ncu --set full capture r02u of this command line's kernels, committed; not re-measured in this run)",
+                "traffic_source": "profiles/r02_ncu_traffic.json (ncu --set full capture r02fc of this command line's kernels, committed; not re-measured in this run)",
                 "kernel": f"fused train step of {M} candidates (" + ("tc engine: k_tc_fwd_ws -> k_chain_all -> k_tc_bwd_ws, 3 launches; " if engine == "tc" else
                                                                        "ffma engine (inner_repr below the MMA tiles): per-layer CUDA-core kernels; ") +
                           "achieved = SURVEY 8(d) algorithmic bytes of the whole step / CUDA-event time of the whole step)",
