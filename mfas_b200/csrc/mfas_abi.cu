@@ -591,6 +591,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       };
       // training steps at the group's row padding; a 128-row dev / test step.  Partial sums that do not fit are read from global memory.
       auto need_all = [&](int it) { return std::max(need_of(g->npad, true, it), need_of(128, false, it)); };
+      { const char* st = getenv("MFAS_CHAIN_SMALL_STAGE"); if (st && !atoi(st)) items = 0; }      // (test switch: the global-memory path)
       if (need_all(items) > 216 * 1024) items = 0;
       g->chain_small_items = items;
       const size_t need = need_all(items);

@@ -325,6 +325,37 @@ def test_run_vs_oracle_trajectory_cfg2_shapes():
     assert int(got["fusion_layers.0.2.num_batches_tracked"]) == (best_epoch + 1) * steps_ep
 
 
+def test_small_chain_partial_sums_staged_or_read_from_global_memory_bitwise(monkeypatch):
+    """k_chain_small stages the forward stream's partial sums in shared memory when the group's deepest candidate fits and reads
+    them from global memory otherwise: the same sums in the same order, so a group is bit-identical either way (and to itself
+    trained inside a group whose other members change the decision)."""
+    confs = [FOUND_CONFS[4], [[3, 1, 1], [2, 2, 2]]]
+    H, B, E, ntr, ndv = 16, 64, 2, 200, 130
+    train, dev = synthetic_ntu_cache(ntr, 21).to(DEV), synthetic_ntu_cache(ndv, 22).to(DEV)
+    inits = init_states(confs, H, 60, True, 0.0, 5)
+    lrs = [1e-3] * (E * math.ceil(ntr / B))
+    gen = torch.Generator().manual_seed(4)
+    ptr = torch.stack([torch.stack([torch.randperm(ntr, generator=gen) for _ in range(E)]) for _ in confs])
+    pdv = torch.stack([torch.stack([torch.randperm(ndv, generator=gen) for _ in range(E)]) for _ in confs])
+
+    def run():
+        g = _group(confs, H, B)
+        for k in range(len(confs)):
+            g.load_state(k, inits[k])
+        st, best, be = g.train_run(train, dev, ptr, pdv, lrs, E, B)
+        torch.cuda.synchronize()
+        g.check()
+        return st.cpu(), best.cpu(), g.params.clone()
+
+    a = run()
+    monkeypatch.setenv("MFAS_CHAIN_SMALL_STAGE", "0")
+    b = run()
+    monkeypatch.setenv("MFAS_CHAIN_SMALL", "0")              # the tensor-core chain: the same step within the usual tolerance
+    c = run()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert torch.allclose(a[0], c[0], rtol=2e-3, atol=1e-6) and (a[2] - c[2]).norm() <= 2e-2 * a[2].norm()
+
+
 def test_batched_candidates_equal_solo_runs_bitwise():
     """Training M candidates in one group must give exactly what each gives alone (no cross-talk),
     and two identical runs must be bit-identical (fixed-order reductions, no atomics)."""
