@@ -2501,7 +2501,7 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nrows = batch.n_rows;
-  if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 256);
   if (tid == 32) {
     umma::mbar_init(&full, 8); umma::mbar_init(&empty, 1);
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 8); }
@@ -2521,6 +2521,8 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
     // Two-deep software pipeline so that no wait sits on a chain of dependent loads: the tile descriptor
     // and the 8 gather indices of tile i+2 are fetched while the x / dz loads of tile i+1 are in flight
     // (r01 ncu: with index -> x load pairs issued one after the other the stagers, not HBM, set the pace).
+    // (r02fj: host-resolved tile records as in k_tc_bwd_small -- the descriptor walk gone, the x loads issued ~6000 cycles
+    //  earlier -- made this kernel 12 % SLOWER: the gathers then queue behind the Adam warps' ring requests for ~10 k cycles.)
     // Batches above 64 rows: the batch is the reduction dimension of dW = x^T dz, so a tile is staged and multiplied in
     // `npass` passes of <= 64 rows into the SAME accumulator (the 96 KB operand stage stays as it is); the unit the stagers and
     // the MMA warp hand over is a "fill" f = tile * npass + pass.
@@ -2576,6 +2578,7 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
     if (n_fill > 1) fetch_desc(1, d1);
     for (int i = 0; i < n_fill; ++i) {
       if (!umma::mbar_wait(&empty, (i & 1) ^ 1)) { ok = false; break; }   // MMAs of fill i-1 have read the stage
+      if (tid == 0) MFAS_KSTAMP(16, i, 7);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int idx = tid + 256 * j, r = idx >> 5, c4 = idx & 31;
@@ -2589,36 +2592,44 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
       umma::fence_async_smem();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&full);
+      if (tid == 0) MFAS_KSTAMP(16, i, 0);
       if (i + 1 < n_fill) issue_loads(d1);             // in flight while this fill's MMAs and the Adam pass run
       if (i + 2 < n_fill) fetch_desc(i + 2, d1);
     }
   } else if (warp == 8) {
     // ================================ MMA issuer ==================================================
-    constexpr uint32_t idesc = umma::idesc_tf32(128, TC_BWD_HT, true, true);
+    // Two products per 8 batch rows instead of three (r02): dz_hi and dz_lo are adjacent tiles with the same block stride, so
+    // [dz_hi | dz_lo] is ONE N = 128 operand: x_hi [dz_hi | dz_lo] -> accumulator columns [0, 64) and [64, 128) (x_hi read from
+    // shared memory once), x_lo dz_hi -> [0, 64).  The Adam warps add the two column ranges.  These MN-major tf32 MMAs cost
+    // ~170-250 cycles each, and with ONE operand stage their issue alternates with the stagers' stores: under the power cap
+    // (1.6 GHz) that serial chain, not HBM, was the tile time.
+    constexpr uint32_t idesc = umma::idesc_tf32(128, TC_BWD_HT, true, true), idesc_cat = umma::idesc_tf32(128, 2 * TC_BWD_HT, true, true);
     const int npass = (nrows + BP - 1) / BP, n_fill = n_my * npass;
     for (int f = 0; f < n_fill; ++f) {
       const int i = npass == 1 ? f : (f >> 1), pass = npass == 1 ? 0 : (f & 1), tb = i & 1;
       if (!umma::mbar_wait(&full, f & 1)) { ok = false; break; }
+      if (lane == 0) MFAS_KSTAMP(16, f, 3);
       if (pass == 0 && !umma::mbar_wait(&tempty[tb], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
+      if (lane == 0) MFAS_KSTAMP(16, f, 1);
       umma::tc_fence_after();
       if (umma::elect_one()) {
-        const uint32_t a_hi = umma::smem_u32(smem), a_lo = a_hi + A_TILE, b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
-        const uint32_t d = tm + tb * 64;
+        const uint32_t a_hi = umma::smem_u32(smem), a_lo = a_hi + A_TILE, b_hi = a_lo + A_TILE;      // b_lo = b_hi + B_TILE: the next two blocks
+        static_assert(B_TILE == 2 * BLK, "[dz_hi | dz_lo] must be four blocks of one stride");
+        const uint32_t d = tm + tb * 128;
         const int ksteps = (min(BP, nrows - pass * BP) + 7) >> 3;
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint32_t adv = ks * 1024u;
           const uint64_t dah = umma::smem_desc(a_hi + adv, BLK, 512, umma::kLayoutSw128Base32);
           const uint64_t dal = umma::smem_desc(a_lo + adv, BLK, 512, umma::kLayoutSw128Base32);
           const uint64_t dbh = umma::smem_desc(b_hi + adv, BLK, 512, umma::kLayoutSw128Base32);
-          const uint64_t dbl = umma::smem_desc(b_lo + adv, BLK, 512, umma::kLayoutSw128Base32);
-          umma::mma_tf32(d, dal, dbh, idesc, (pass > 0 || ks > 0) ? 1u : 0u);
-          umma::mma_tf32(d, dah, dbl, idesc, 1u);
-          umma::mma_tf32(d, dah, dbh, idesc, 1u);
+          umma::mma_tf32(d, dah, dbh, idesc_cat, (pass > 0 || ks > 0) ? 1u : 0u);
+          umma::mma_tf32(d, dal, dbh, idesc, 1u);
         }
         umma::mma_commit(&empty);                      // operand stage free once these MMAs have read it
         if (pass == npass - 1) umma::mma_commit(&tfull[tb]);   // accumulator ready for the Adam warps
       }
       __syncwarp();
+      if (lane == 0) MFAS_KSTAMP(16, f, 4);
     }
   } else {
     // ================================ Adam warps ==================================================
@@ -2690,14 +2701,18 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
       if (more) nxt = open_tile(ahead);
       if (i + 2 < n_my) ahead = fetch_raw(i + 2);
       if (!umma::mbar_wait(&tfull[tb], (i >> 1) & 1)) { ok = false; break; }
+      if (aw == 0 && lane == 0) MFAS_KSTAMP(16, i, 5);
       umma::tc_fence_after();
       float dsum = 0.f;                                // ALPHA: sum over this warp's part of the tile of W (pre-update) o G
 #pragma unroll
       for (int j = 0; j < WS_RING; ++j) {
         cp_async_wait<WS_RING - 1>();                  // the oldest outstanding batch (this one) has landed
         __syncwarp();
-        float g[8];
-        umma::tmem_ld8(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 64 + cg * 32 + 8 * j), g);
+        float g[8], g2[8];
+        umma::tmem_ld8(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 128 + cg * 32 + 8 * j), g);
+        umma::tmem_ld8(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 128 + 64 + cg * 32 + 8 * j), g2);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) g[r] += g2[r];
         if (cur.rc >> 8) {
           const float* sp = reinterpret_cast<const float*>(ring + j * WS_SLOT) + lane;
           float* w = cur.W + (long long)(8 * j) * cur.K + lane;
@@ -2741,6 +2756,7 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
       umma::tc_fence_before();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&tempty[tb]);   // this warp has drained its part of the accumulator
+      if (aw == 0 && lane == 0) MFAS_KSTAMP(16, i, 6);
       cur = nxt;
     }
     cp_async_wait<0>();
@@ -2748,7 +2764,7 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
   if (!ok) atomicExch(err.flag, 5);
   umma::tc_fence_before();
   __syncthreads();
-  if (warp == 0) umma::tmem_free(tm, 128);
+  if (warp == 0) umma::tmem_free(tm, 256);
 }
 
 // ---------------------------------------------------------------------------------------------

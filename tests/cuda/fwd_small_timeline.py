@@ -40,7 +40,8 @@ print("mma issue interval: median %d cycles; loader issue interval: median %d" %
 t = out.reshape(-1)[128:256].reshape(16, 8)
 t0 = t[0, 0]
 names = ["ld issued", "cv saw landed", "cv arrived lofull", "mma saw lofull", "mma issued", "adam saw tfull", "adam done", "ld saw rawfree"]
-print("k_tc_bwd_small, CTA 0, fills 16..31 (cycles since fill 16 was issued)")
+if H > 32: names = ["stage stored (full)", "mma saw tempty", "-", "mma saw full", "mma issued", "adam saw tfull", "adam done", "stagers saw empty"]
+print(("k_tc_bwd_ws" if H > 32 else "k_tc_bwd_small") + ", CTA 0, fills 16..31 (cycles since fill 16 was issued / stored)")
 print("   fill | " + " | ".join(names))
 for i in range(16):
     print("%7d | " % (16 + i) + " | ".join("%8d" % (t[i, e] - t0) for e in range(8)))
