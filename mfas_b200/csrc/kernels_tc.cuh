@@ -1809,10 +1809,10 @@ __device__ __forceinline__ float col_sum(float v, float* red, int c) {
   if (HN == 16) v += __shfl_xor_sync(0xffffffffu, v, 16);
   if (lane < HN) red[warp * 32 + lane] = v;
   __syncthreads();
-  float t = 0.f;
+  float t[4] = {0.f, 0.f, 0.f, 0.f};           // fixed order, four chains of four (not one chain of sixteen dependent adds)
 #pragma unroll
-  for (int w = 0; w < 16; ++w) t += red[w * 32 + c];
-  return t;
+  for (int w = 0; w < 16; ++w) t[w & 3] += red[w * 32 + c];
+  return (t[0] + t[1]) + (t[2] + t[3]);
 }
 template <int HN>
 __device__ __forceinline__ void col_sum2(float& v1, float& v2, float* red1, float* red2, int c) {
@@ -1820,10 +1820,10 @@ __device__ __forceinline__ void col_sum2(float& v1, float& v2, float* red1, floa
   if (HN == 16) { v1 += __shfl_xor_sync(0xffffffffu, v1, 16); v2 += __shfl_xor_sync(0xffffffffu, v2, 16); }
   if (lane < HN) { red1[warp * 32 + lane] = v1; red2[warp * 32 + lane] = v2; }
   __syncthreads();
-  float t1 = 0.f, t2 = 0.f;
+  float t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int w = 0; w < 16; ++w) { t1 += red1[w * 32 + c]; t2 += red2[w * 32 + c]; }
-  v1 = t1; v2 = t2;
+  for (int w = 0; w < 16; ++w) { t1[w & 3] += red1[w * 32 + c]; t2[w & 3] += red2[w * 32 + c]; }
+  v1 = (t1[0] + t1[1]) + (t1[2] + t1[3]); v2 = (t2[0] + t2[1]) + (t2[2] + t2[3]);
 }
 
 // head_rows (kernels_ffma.cuh) for four rows of a warp at once -- rows warp + 16 i of the round: the same arithmetic per
@@ -1833,6 +1833,7 @@ template <bool TRAIN, int NPAD>
 __device__ __forceinline__ void head_rows_x4(const DCand& cd, int nrows, float* lg, int lg_ld, float* rowloss, int* rowok,
                                              const int* lab, float* dlog) {
   const int C = cd.C, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float inv_n = 1.f / (float)nrows;
   for (int rb = 0; rb < NPAD; rb += 64) {
     if (rb >= nrows) break;
     float v0[4], v1[4], mx[4];
@@ -1873,7 +1874,6 @@ __device__ __forceinline__ void head_rows_x4(const DCand& cd, int nrows, float* 
         const float vy = __shfl_sync(0xffffffffu, y < 32 ? v0[i] : v1[i], y & 31);
         if (lane == 0) { rowloss[r] = -((vy - mx[i]) - lse); rowok[r] = (am[i] == y) ? 1 : 0; }
         if (TRAIN) {
-          const float inv_n = 1.f / (float)nrows;
           const float d0 = lane < C ? (expf((v0[i] - mx[i]) - lse) - (lane == y ? 1.f : 0.f)) * inv_n : 0.f;
           const float d1 = lane + 32 < C ? (expf((v1[i] - mx[i]) - lse) - (lane + 32 == y ? 1.f : 0.f)) * inv_n : 0.f;
           if (lane < C) row[lane] = d0;
@@ -1925,6 +1925,7 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
   const bool drop = TRAIN && (cd.flags & MFAS_FLAG_DROPOUT);
   const bool gated = (cd.flags & MFAS_FLAG_ALPHAS) != 0;
   const float dscale = drop ? 1.f / (1.f - drop_p) : 1.f;
+  const float inv_n = 1.f / (float)nrows;            // the batch means below are sum * (1 / n): one division per launch on the chain
   int n_items = 0;
   for (int l = 0; l < L; ++l) n_items += tc_fwd_items_g(cd.layer[l].d_ske, cd.layer[l].d_rgb, gated);
   float* h_s = csm;
@@ -2053,14 +2054,17 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
         for (int k = 0; k < G; ++k)
 #pragma unroll
           for (int i = 0; i < 4; ++i) s1 += a[k][i];
-        mean = col_sum<HN>(s1, red, c) / (float)nrows;
+        mean = col_sum<HN>(s1, red, c) * inv_n;
+        if (l == 1) stamp_at(6);
         float qq = 0.f;
 #pragma unroll
         for (int k = 0; k < G; ++k)
 #pragma unroll
           for (int i = 0; i < 4; ++i) if (4 * (slot + k * Cfg::SLOTS) + i < nrows) { const float d = a[k][i] - mean; qq = fmaf(d, d, qq); }
-        const float var = col_sum<HN>(qq, red + 512, c) / (float)nrows;
-        istd = 1.f / sqrtf(var + kBnEps);
+        if (l == 1) stamp_at(7);
+        const float var = col_sum<HN>(qq, red + 512, c) * inv_n;
+        if (l == 1) stamp_at(8);
+        istd = rsqrtf(var + kBnEps);
         if (tid >= THREADS - HN) {                   // one thread per column, in the last warp (idle at inner_repr 16, and never the slowest)
           vv[11 * HN] = mean; vv[12 * HN] = istd;
           const float n = (float)nrows;
@@ -2070,7 +2074,7 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
         }
       } else {
         mean = vv[9 * HN];
-        istd = 1.f / sqrtf(vv[10 * HN] + kBnEps);
+        istd = rsqrtf(vv[10 * HN] + kBnEps);
       }
     }
     if (l == 1) stamp_at(15);
@@ -2233,7 +2237,7 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
         for (int i = 0; i < 4; ++i) if (4 * (slot + k * Cfg::SLOTS) + i < nrows) { S1 += dh[k][i]; S2 = fmaf(dh[k][i], (av[k][i] - mu) * istd, S2); }
       col_sum2<HN>(S1, S2, red, red + 512, c);
     }
-    const float m1 = S1 / (float)nrows, m2 = S2 / (float)nrows;
+    const float m1 = S1 * inv_n, m2 = S2 * inv_n;
     float db = 0.f;
     if (active) {
       float* dzg = cd.dzs + (long long)l * bmax * HN + c;

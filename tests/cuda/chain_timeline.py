@@ -41,6 +41,9 @@ if H <= 32 and os.environ.get("MFAS_CHAIN_SMALL", "1") != "0":      # k_chain_sm
     if L > 1:
         print("  inside forward layer 1 (cycles since the layer was entered, median): partial sums + W_hid h + bias + activation %d | BatchNorm statistics %d | layer end %d" % (
             np.median(inner[:, 4] - out[:, 1]), np.median(inner[:, 5] - out[:, 1]), np.median(out[:, 2] - out[:, 1])))
+        if L == 2:      # (slots 6..8 are free at L = 2: inside the BatchNorm statistics)
+            print("    BatchNorm statistics: first column sum %d | squares %d | second column sum %d | invstd, running stats %d" % (
+                np.median(out[:, 6] - inner[:, 4]), np.median(out[:, 7] - out[:, 6]), np.median(out[:, 8] - out[:, 7]), np.median(inner[:, 5] - out[:, 8])))
     sys.exit(0)
 print("inside forward layer 1 (cycles since the layer was entered, median): raw operand tiles landed (cp.async) %d | lo tiles written %d | MMAs issued %d | z complete (partials, MMA, bias, act) %d | BN stats %d | (layer end %d)" % (
     np.median(inner[:, 1] - t0), np.median(inner[:, 2] - t0), np.median(inner[:, 3] - t0), np.median(inner[:, 4] - t0),
