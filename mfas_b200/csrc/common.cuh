@@ -23,6 +23,7 @@ struct DLayer {
 struct DCand {
   int L, H, C, flags;
   int cand_id;                         // global candidate index (dropout key)
+  int kb_item;                         // k-blocks per forward work item of this candidate's group (kernels_tc.cuh: tc_fwd_items)
   DLayer layer[MFAS_MAX_LAYERS];
   long long oWc, obc;
   long long n_params, n_bufs;

@@ -38,28 +38,31 @@ struct TcErr {
                                       // (MFAS_L2_HINTS; default 1 -- on the backward's read-modify-write stream the hint costs 55 %, r01n)
 };
 
-__host__ __device__ __forceinline__ int tc_fwd_items(int d_ske, int d_rgb) {
-  return (((d_ske + d_rgb) >> 5) + TC_KB_PER_ITEM - 1) / TC_KB_PER_ITEM;
+// `per`: k-blocks per work item at most.  TC_KB_PER_ITEM unless the group chose a smaller one (DCand::kb_item: small groups of the
+// inner_repr 16 / 32 path, so that every SM gets about the same number of k-blocks); every producer and consumer of a group's
+// partial sums uses the group's value.
+__host__ __device__ __forceinline__ int tc_fwd_items(int d_ske, int d_rgb, int per = TC_KB_PER_ITEM) {
+  return (((d_ske + d_rgb) >> 5) + per - 1) / per;
 }
 // k-block range of split `split` of a layer with nkb feature k-blocks (even split over tc_fwd_items pieces)
-__host__ __device__ __forceinline__ void tc_fwd_range(int nkb, int split, int& kb0, int& kb1) {
-  const int n = (nkb + TC_KB_PER_ITEM - 1) / TC_KB_PER_ITEM, per = (nkb + n - 1) / n;
-  kb0 = split * per;
-  kb1 = kb0 + per < nkb ? kb0 + per : nkb;
+__host__ __device__ __forceinline__ void tc_fwd_range(int nkb, int split, int& kb0, int& kb1, int per = TC_KB_PER_ITEM) {
+  const int n = (nkb + per - 1) / per, each = (nkb + n - 1) / n;
+  kb0 = split * each;
+  kb1 = kb0 + each < nkb ? kb0 + each : nkb;
 }
 // Alpha-gated candidates (MFAS_FLAG_ALPHAS): forward work items never straddle the boundary between the two modalities -- the
 // first tc_fwd_items_of(d_ske) items of a layer cover the ske columns, the rest the rgb columns -- so the consumer of the partial
 // sums applies the gate of a modality as ONE factor per partial: z = s * (W_ske x_ske) + (1 - s) * (W_rgb x_rgb) + ...
-__host__ __device__ __forceinline__ int tc_fwd_items_of(int width) { return ((width >> 5) + TC_KB_PER_ITEM - 1) / TC_KB_PER_ITEM; }
-__host__ __device__ __forceinline__ int tc_fwd_items_g(int d_ske, int d_rgb, bool gated) {
-  return gated ? tc_fwd_items_of(d_ske) + tc_fwd_items_of(d_rgb) : tc_fwd_items(d_ske, d_rgb);
+__host__ __device__ __forceinline__ int tc_fwd_items_of(int width, int per = TC_KB_PER_ITEM) { return ((width >> 5) + per - 1) / per; }
+__host__ __device__ __forceinline__ int tc_fwd_items_g(int d_ske, int d_rgb, bool gated, int per = TC_KB_PER_ITEM) {
+  return gated ? tc_fwd_items_of(d_ske, per) + tc_fwd_items_of(d_rgb, per) : tc_fwd_items(d_ske, d_rgb, per);
 }
 // k-block range of item `split` of a layer (gated: an even split of the item's own modality)
-__host__ __device__ __forceinline__ void tc_fwd_range_g(int d_ske, int d_rgb, int split, bool gated, int& kb0, int& kb1) {
-  if (!gated) { tc_fwd_range((d_ske + d_rgb) >> 5, split, kb0, kb1); return; }
-  const int ns = tc_fwd_items_of(d_ske);
-  if (split < ns) tc_fwd_range(d_ske >> 5, split, kb0, kb1);
-  else { tc_fwd_range(d_rgb >> 5, split - ns, kb0, kb1); kb0 += d_ske >> 5; kb1 += d_ske >> 5; }
+__host__ __device__ __forceinline__ void tc_fwd_range_g(int d_ske, int d_rgb, int split, bool gated, int& kb0, int& kb1, int per = TC_KB_PER_ITEM) {
+  if (!gated) { tc_fwd_range((d_ske + d_rgb) >> 5, split, kb0, kb1, per); return; }
+  const int ns = tc_fwd_items_of(d_ske, per);
+  if (split < ns) tc_fwd_range(d_ske >> 5, split, kb0, kb1, per);
+  else { tc_fwd_range(d_rgb >> 5, split - ns, kb0, kb1, per); kb0 += d_ske >> 5; kb1 += d_ske >> 5; }
 }
 __host__ __device__ __forceinline__ int tc_bwd_items(int K) { return (K + TC_BWD_KT - 1) / TC_BWD_KT; }
 
@@ -95,7 +98,7 @@ k_tc_fwd_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, floa
   // decode the work item -> (layer, split)
   int layer = 0, split = blockIdx.x;
   for (; layer < cd.L; ++layer) {
-    const int n = tc_fwd_items(cd.layer[layer].d_ske, cd.layer[layer].d_rgb);
+    const int n = tc_fwd_items(cd.layer[layer].d_ske, cd.layer[layer].d_rgb, cd.kb_item);
     if (split < n) break;
     split -= n;
   }
@@ -104,7 +107,7 @@ k_tc_fwd_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, floa
   const int K = ly.K, fs = ly.d_ske, fr = ly.d_rgb;
   const int nkb = (fs + fr) >> 5;
   int kb0, kb1;
-  tc_fwd_range(nkb, split, kb0, kb1);
+  tc_fwd_range(nkb, split, kb0, kb1, cd.kb_item);
   const int nrows = batch.n_rows, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   uint8_t* a_hi = smem;
@@ -817,8 +820,8 @@ k_fwd_layer(const DCand* __restrict__ cands, int layer, int nrows, int bmax, con
   const DLayer& ly = cd.layer[layer];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int item0 = 0;
-  for (int l = 0; l < layer; ++l) item0 += tc_fwd_items(cd.layer[l].d_ske, cd.layer[l].d_rgb);
-  const int nsplit = tc_fwd_items(ly.d_ske, ly.d_rgb);
+  for (int l = 0; l < layer; ++l) item0 += tc_fwd_items(cd.layer[l].d_ske, cd.layer[l].d_rgb, cd.kb_item);
+  const int nsplit = tc_fwd_items(ly.d_ske, ly.d_rgb, cd.kb_item);
   const int Hp = ((H + 127) >> 7) << 7;
   const float* part = part_base + (long long)blockIdx.y * part_stride_cand + (long long)item0 * Hp * NPAD;
   const bool bn = (cd.flags & MFAS_FLAG_BN) != 0;
@@ -1244,10 +1247,10 @@ __device__ __forceinline__ void chain_fwd_layer(ChainCtx& cx, const DCand& cd, i
     // cut at the modality boundary, so the gate is one factor per partial sum
     const bool gated = (cd.flags & MFAS_FLAG_ALPHAS) != 0;
     const float sg = gated ? gate_of(cd.p[ly.oalpha]) : 1.f;
-    const int n_ske = tc_fwd_items_of(ly.d_ske);
+    const int n_ske = tc_fwd_items_of(ly.d_ske, cd.kb_item);
     int item0 = 0;
-    for (int l = 0; l < layer; ++l) item0 += tc_fwd_items_g(cd.layer[l].d_ske, cd.layer[l].d_rgb, gated);
-    const int nsplit = tc_fwd_items_g(ly.d_ske, ly.d_rgb, gated);
+    for (int l = 0; l < layer; ++l) item0 += tc_fwd_items_g(cd.layer[l].d_ske, cd.layer[l].d_rgb, gated, cd.kb_item);
+    const int nsplit = tc_fwd_items_g(ly.d_ske, ly.d_rgb, gated, cd.kb_item);
     const int Hp = ((H + 127) >> 7) << 7;
     const float4* part = reinterpret_cast<const float4*>(part_base + (long long)cand * part_stride_cand + (long long)item0 * Hp * NPAD) +
                          (long long)(b0 >> 2) * Hp + c;
@@ -1927,7 +1930,7 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
   const float dscale = drop ? 1.f / (1.f - drop_p) : 1.f;
   const float inv_n = 1.f / (float)nrows;            // the batch means below are sum * (1 / n): one division per launch on the chain
   int n_items = 0;
-  for (int l = 0; l < L; ++l) n_items += tc_fwd_items_g(cd.layer[l].d_ske, cd.layer[l].d_rgb, gated);
+  for (int l = 0; l < L; ++l) n_items += tc_fwd_items_g(cd.layer[l].d_ske, cd.layer[l].d_rgb, gated, cd.kb_item);
   float* h_s = csm;
   float* a_s = h_s + (TRAIN ? (size_t)L * H_L : 0);
   float* raw = a_s;                                  // the forward stream's partial sums, [item][NPAD/4][HN] float4 (see ChainSmall::smem)
@@ -1991,7 +1994,7 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
   for (int l = 0; l < L; ++l) {
     const DLayer& ly = cd.layer[l];
     float* vv = vec + (size_t)l * NV * HN + c;
-    const int nsplit = tc_fwd_items_g(ly.d_ske, ly.d_rgb, gated);
+    const int nsplit = tc_fwd_items_g(ly.d_ske, ly.d_rgb, gated, cd.kb_item);
     float a[G][4];
 #pragma unroll
     for (int k = 0; k < G; ++k)
@@ -2000,7 +2003,7 @@ k_chain_small(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int
     if (active) {
       // feature partial sums of this layer, in split order (alpha gates: one factor per partial, see chain_fwd_layer)
       const float sg = gated ? gate_of(cd.p[ly.oalpha]) : 1.f;
-      const int n_ske = tc_fwd_items_of(ly.d_ske);
+      const int n_ske = tc_fwd_items_of(ly.d_ske, cd.kb_item);
       const float4* ps = staged ? reinterpret_cast<const float4*>(raw) + c
                                 : reinterpret_cast<const float4*>(part_base + (long long)cand * part_stride_cand) + c;
       const int pstr = staged ? HN : 128;            // float4s per row group: packed in shared memory, Hp = 128 in the forward stream's layout

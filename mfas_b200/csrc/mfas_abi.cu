@@ -310,6 +310,7 @@ struct mfas_group {
   cudaEvent_t prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // mfas_group_set_profiling: around fwd / chain / bwd of a step
   bool prof = false, prof_valid = false;
   int dbg = 0;                    // MFAS_TC_DEBUG bit 0: skip the Adam epilogue, bit 1: skip operand staging (timing experiments only)
+  int kb_item = TC_KB_PER_ITEM;   // k-blocks per forward work item (smaller for small groups of the inner_repr 16 / 32 path)
   int chain_small_items = 0;      // partial sums per candidate staged by k_chain_small (largest of the group)
   int chain_small = 0;            // 16 / 32: the chain of a step runs in k_chain_small (inner_repr 16 / 32, on-chip, CUDA cores)
   int chain_cl = 1;               // CTAs (thread-block cluster size) per candidate in the fused chain: 2 for inner_repr 256 with <= n_sms / 2 candidates
@@ -350,6 +351,54 @@ extern "C" int mfas_group_destroy(mfas_group_t g) {
   pool_free(g->device, g->alpha_rng, g->rng_bytes);
   delete g;
   return MFAS_OK;
+}
+
+// Forward work items of a small inner_repr-16 / 32 group: with items of up to 32 k-blocks, 32 two-step candidates are ~230 items on
+// 148 persistent CTAs -- 82 CTAs get two, the launch takes two rounds.  The item size that minimises the busiest CTA's k-blocks
+// (items dealt biggest first, round robin, as the launch does; 2 k-blocks of overhead per item) is chosen per group -- if the
+// partial sums of the deepest candidate still fit k_chain_small's shared-memory stage.
+static int choose_kb_item(const std::vector<mfas_layout>& lay, int n_cand, int n_sms, int Hmax, int Lmax, int npad) {
+  auto sizes_of = [&](int per, std::vector<int>& sz, int& per_cand_max) {
+    sz.clear(); per_cand_max = 0;
+    for (int c = 0; c < n_cand; ++c) {
+      int n_c = 0;
+      const bool gated = (lay[c].flags & MFAS_FLAG_ALPHAS) != 0;
+      for (int l = 0; l < lay[c].L; ++l) {
+        const int ns = tc_fwd_items_g(lay[c].d_ske[l], lay[c].d_rgb[l], gated, per);
+        for (int sp = 0; sp < ns; ++sp) {
+          int kb0, kb1;
+          tc_fwd_range_g(lay[c].d_ske[l], lay[c].d_rgb[l], sp, gated, kb0, kb1, per);
+          sz.push_back(kb1 - kb0);
+        }
+        n_c += ns;
+      }
+      per_cand_max = std::max(per_cand_max, n_c);
+    }
+    std::sort(sz.begin(), sz.end(), std::greater<int>());
+  };
+  auto busiest = [&](const std::vector<int>& sz) {
+    std::vector<int> load(n_sms, 0);
+    for (size_t i = 0; i < sz.size(); ++i) load[i % n_sms] += sz[i] + 2;
+    return *std::max_element(load.begin(), load.end());
+  };
+  auto fits = [&](int items) {
+    const size_t tr = Hmax == 16 ? (npad == 64 ? ChainSmall<64, 16>::smem(Lmax, true, items) : ChainSmall<128, 16>::smem(Lmax, true, items))
+                                 : (npad == 64 ? ChainSmall<64, 32>::smem(Lmax, true, items) : ChainSmall<128, 32>::smem(Lmax, true, items));
+    const size_t ev = Hmax == 16 ? ChainSmall<128, 16>::smem(Lmax, false, items) : ChainSmall<128, 32>::smem(Lmax, false, items);
+    return std::max(tr, ev) <= 216 * 1024;
+  };
+  std::vector<int> sz;
+  int pc = 0;
+  sizes_of(TC_KB_PER_ITEM, sz, pc);
+  if ((int)sz.size() >= 6 * n_sms) return TC_KB_PER_ITEM;          // many items per CTA: the imbalance is a fraction of one item
+  int best = TC_KB_PER_ITEM, best_load = busiest(sz);
+  for (int per : {28, 24, 20, 16, 14, 12, 10, 8}) {
+    sizes_of(per, sz, pc);
+    if (!fits(pc)) continue;
+    const int b = busiest(sz);
+    if (b * 100 < best_load * 95) { best = per; best_load = b; }
+  }
+  return best;
 }
 
 extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layout* layouts, int32_t batch_max,
@@ -426,6 +475,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
     memset(&d, 0, sizeof(d));
     d.L = l.L; d.H = l.H; d.C = l.C; d.flags = l.flags;
     d.cand_id = cand_ids ? cand_ids[c] : c;
+    d.kb_item = TC_KB_PER_ITEM;
     for (int k = 0; k < l.L; ++k) {
       DLayer& y = d.layer[k];
       y.ske_tap = l.conf[k][0]; y.rgb_tap = l.conf[k][1]; y.act = l.conf[k][2];
@@ -508,10 +558,23 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
   if (tc_ok) {
     g->engine = 1;
     g->npad = batch_max <= 64 ? 64 : 128;
+    { int nsm = 0; if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && nsm > 0) g->n_sms = nsm; }
+    {
+      bool same = true;
+      for (int c = 0; c < n_cand; ++c) same = same && g->lay[c].H == g->Hmax;
+      // MFAS_KB_ITEM: a fixed item size, or "auto" = choose_kb_item.  NOT the default: the split of a layer's columns decides the
+      // order in which its partial products are rounded, so a size chosen from the group would make a candidate's numbers depend
+      // on how many candidates share the GPU -- and 1-GPU, N-rank and fan-out runs are bit-identical by contract (measured with
+      // "auto": forward stream 20.3 -> 18.6 us at 32 candidates, 21.6 -> 15.9 us at 32 one-step candidates, r02fo).
+      const char* ke = getenv("MFAS_KB_ITEM");
+      if (ke && !strcmp(ke, "auto")) { if (same && (g->Hmax == 16 || g->Hmax == 32)) g->kb_item = choose_kb_item(g->lay, n_cand, g->n_sms, g->Hmax, g->Lmax, g->npad); }
+      else if (ke && atoi(ke) >= 4 && atoi(ke) <= TC_KB_PER_ITEM) g->kb_item = atoi(ke);
+      for (int c = 0; c < n_cand; ++c) g->hc[c].kb_item = g->kb_item;
+    }
     for (int c = 0; c < n_cand; ++c) {
       int nf = 0, nb = 0;
       for (int l = 0; l < g->lay[c].L; ++l) {
-        nf += tc_fwd_items_g(g->lay[c].d_ske[l], g->lay[c].d_rgb[l], (g->lay[c].flags & MFAS_FLAG_ALPHAS) != 0);
+        nf += tc_fwd_items_g(g->lay[c].d_ske[l], g->lay[c].d_rgb[l], (g->lay[c].flags & MFAS_FLAG_ALPHAS) != 0, g->kb_item);
         nb += tc_bwd_items(g->lay[c].K[l]);
       }
       g->items_fwd = nf > g->items_fwd ? nf : g->items_fwd;
@@ -582,7 +645,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       int items = 0;                                      // most partial sums of a candidate (all staged in shared memory)
       for (int c = 0; c < n_cand; ++c) {
         int n = 0;
-        for (int l = 0; l < g->lay[c].L; ++l) n += tc_fwd_items_g(g->lay[c].d_ske[l], g->lay[c].d_rgb[l], (g->lay[c].flags & MFAS_FLAG_ALPHAS) != 0);
+        for (int l = 0; l < g->lay[c].L; ++l) n += tc_fwd_items_g(g->lay[c].d_ske[l], g->lay[c].d_rgb[l], (g->lay[c].flags & MFAS_FLAG_ALPHAS) != 0, g->kb_item);
         items = std::max(items, n);
       }
       auto need_of = [&](int npad, bool tr, int it) {
@@ -657,7 +720,7 @@ extern "C" int mfas_group_create(int32_t device, int32_t n_cand, const mfas_layo
       int n = 0;
       for (int c = 0; c < n_cand; ++c)
         for (int l = 0; l < g->lay[c].L; ++l)
-          n += tc_fwd_items_g(g->lay[c].d_ske[l], g->lay[c].d_rgb[l], (g->lay[c].flags & MFAS_FLAG_ALPHAS) != 0) * ((g->lay[c].H + 127) / 128);
+          n += tc_fwd_items_g(g->lay[c].d_ske[l], g->lay[c].d_rgb[l], (g->lay[c].flags & MFAS_FLAG_ALPHAS) != 0, g->kb_item) * ((g->lay[c].H + 127) / 128);
       g->n_fwd_items = n;
       if (e == cudaSuccess) e = pool_alloc_t(device, sizeof(FwdItem) * n, &g->fwd_items, &g->items_bytes);
       attr((const void*)k_tc_fwd_ws<64, 0>, FwdWs<64, 0>::SMEM);
@@ -840,11 +903,11 @@ static int sync_descriptors(mfas_group* g, cudaStream_t st) {
         for (int l = 0; l < d.L; ++l) {
           const DLayer& ly = d.layer[l];
           const bool gated = (d.flags & MFAS_FLAG_ALPHAS) != 0;          // items cut at the modality boundary (tc_fwd_items_g)
-          const int ns = tc_fwd_items_g(ly.d_ske, ly.d_rgb, gated);
+          const int ns = tc_fwd_items_g(ly.d_ske, ly.d_rgb, gated, g->kb_item);
           for (int sp = 0; sp < ns; ++sp)
             for (int m0 = 0; m0 < d.H; m0 += 128) {
               FwdItem it;
-              tc_fwd_range_g(ly.d_ske, ly.d_rgb, sp, gated, it.kb0, it.kb1);
+              tc_fwd_range_g(ly.d_ske, ly.d_rgb, sp, gated, it.kb0, it.kb1, g->kb_item);
               it.W = d.p + ly.oW + (long long)m0 * ly.K;
               it.part_off = (long long)c * g->part_stride + (long long)(item0 + sp) * Hp * g->npad + 4LL * m0;
               it.Hp = Hp; it.pad0 = it.pad1 = it.pad2 = 0;
