@@ -356,6 +356,32 @@ def test_small_chain_partial_sums_staged_or_read_from_global_memory_bitwise(monk
     assert torch.allclose(a[0], c[0], rtol=2e-3, atol=1e-6) and (a[2] - c[2]).norm() <= 2e-2 * a[2].norm()
 
 
+@pytest.mark.parametrize("kb", ["8", "20", "auto"])
+def test_forward_work_item_size_is_a_group_parameter(monkeypatch, kb):
+    """MFAS_KB_ITEM cuts the feature columns of a layer into more, smaller forward work items (producers and consumers of the
+    partial sums all read the group's value): the same step up to the rounding order of the partial products."""
+    confs = [FOUND_CONFS[4][:2], [[3, 1, 1]], [[1, 2, 0], [2, 3, 1], [0, 0, 0]]]
+    train = synthetic_ntu_cache(96, 31).to(DEV)
+    rows = torch.stack([torch.randperm(96)[:64] for _ in confs]).to(DEV, torch.int32)
+
+    def run(H):
+        g = _group(confs, H, 64, keep_grads=True)
+        for k, st in enumerate(init_states(confs, H, 60, True, 0.0, 9)):
+            g.load_state(k, st)
+        logits, loss, _ = g.train_step(train, rows, lr=1e-3)
+        torch.cuda.synchronize()
+        g.check()
+        return logits.clone(), loss.clone(), g.params.clone()
+
+    for H in (16, 128):
+        monkeypatch.delenv("MFAS_KB_ITEM", raising=False)
+        a = run(H)
+        monkeypatch.setenv("MFAS_KB_ITEM", kb)
+        b = run(H)
+        assert (a[0] - b[0]).abs().max() <= 2e-5 * a[0].abs().max() and torch.allclose(a[1], b[1], rtol=1e-5)
+        assert (a[2] - b[2]).norm() <= 1e-4 * a[2].norm()
+
+
 def test_batched_candidates_equal_solo_runs_bitwise():
     """Training M candidates in one group must give exactly what each gives alone (no cross-talk),
     and two identical runs must be bit-identical (fixed-order reductions, no atomics)."""
