@@ -257,11 +257,13 @@ struct __align__(16) FwdItem {
 // k-block cost on the issuing thread: ~70 cycles per MMA, profiles/r02dk_roles.txt).  The converter warps work in two groups of
 // four, each with a W_lo stage of its own and every other k-block (a pass is two barrier waits, a shared-memory round trip, a
 // proxy fence and an arrive: its latency, not its bytes, was the converters' rate).
-template <int NPAD, int XR = 0> struct FwdWs {     // XR = 1: one raw stage less, one W_lo stage more (A/B switch MFAS_FWD_XR)
-  static constexpr int RAW = (NPAD == 64 ? 6 : 4) - XR, LO = 2 + XR;
-  static constexpr uint32_t A_BYTES = 16384, B_BYTES = NPAD * 128, TILE = A_BYTES + 2 * B_BYTES, LO_TILE = A_BYTES;
-  static constexpr size_t SMEM = 1024 + (size_t)RAW * TILE + (size_t)LO * LO_TILE;
-  static constexpr int LOADERS = 128, CONVERTERS = 256, CGROUPS = 2, THREADS = 17 * 32;
+template <int NPAD, int XR = 0> struct FwdWs {     // XR = 1: W ring 8 deep, x ring 4 (A/B switch MFAS_FWD_XR; default 7 / 5)
+  // three rings: W_hi tiles (the stream's HBM bytes: as deep as shared memory allows -- what bounds the stream is loaded HBM
+  // latency x tiles in flight), [x_hi | x_lo] tiles (gathered rows, mostly L2 hits), W_lo tiles
+  static constexpr int WR = NPAD == 64 ? 7 + XR : 6, XS = NPAD == 64 ? 5 - XR : 3, LO = 2;
+  static constexpr uint32_t A_BYTES = 16384, B_BYTES = NPAD * 128, X_TILE = 2 * B_BYTES, LO_TILE = A_BYTES;
+  static constexpr size_t SMEM = 1024 + (size_t)WR * A_BYTES + (size_t)XS * X_TILE + (size_t)LO * LO_TILE;
+  static constexpr int LOADERS = 128, CONVERTERS = 256, CGROUPS = 2, THREADS = 18 * 32;     // + one W-producer warp (TMA)
 };
 
 // L2 eviction priority for the streams that are read exactly once per launch (weights, Adam moments, gathered feature
@@ -311,18 +313,20 @@ __global__ void __launch_bounds__((FwdWs<NPAD, XR>::THREADS), 1)
 k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchRef batch, float* part_base, TcErr err,
             const CUtensorMap* __restrict__ wmaps, const __grid_constant__ TapMaps taps, int use_tma) {
   using Cfg = FwdWs<NPAD, XR>;
-  constexpr int R = Cfg::RAW, LQ = Cfg::LO;
+  constexpr int WR = Cfg::WR, XS = Cfg::XS, LQ = Cfg::LO;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = umma::align1024(smem_raw);
-  uint8_t* lo_base = smem + R * Cfg::TILE;
-  __shared__ uint64_t landed[R], rawfree[R], lofull[LQ], lofree[LQ], tfull[2], tempty[2];
+  uint8_t* smem = umma::align1024(smem_raw);                       // W ring
+  uint8_t* x_base = smem + WR * Cfg::A_BYTES;                      // [x_hi | x_lo] ring
+  uint8_t* lo_base = x_base + XS * Cfg::X_TILE;                    // W_lo ring
+  __shared__ uint64_t wland[WR], wfree[WR], xland[XS], xfree[XS], lofull[LQ], lofree[LQ], tfull[2], tempty[2];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nrows = batch.n_rows;
   if (warp == 0) umma::tmem_alloc(&tmem_slot, 4 * NPAD);
   if (tid == 32) {
     // use_tma: 0 = cp.async loaders, 1 = W tiles through TMA + x through cp.async, 2 = W through TMA + x through tile::gather4
-    for (int i = 0; i < R; ++i) { umma::mbar_init(&landed[i], use_tma == 2 ? 1 : Cfg::LOADERS + (use_tma ? 1 : 0)); umma::mbar_init(&rawfree[i], 1); }
+    for (int i = 0; i < WR; ++i) { umma::mbar_init(&wland[i], use_tma ? 1 : Cfg::LOADERS); umma::mbar_init(&wfree[i], 1); }
+    for (int i = 0; i < XS; ++i) { umma::mbar_init(&xland[i], use_tma == 2 ? 1 : Cfg::LOADERS); umma::mbar_init(&xfree[i], 1); }
     for (int i = 0; i < LQ; ++i) { umma::mbar_init(&lofull[i], Cfg::CONVERTERS / 32 / Cfg::CGROUPS); umma::mbar_init(&lofree[i], 1); }
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 4); }
     umma::fence_mbar_init();
@@ -336,10 +340,31 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
   const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   bool ok = true;
 
-  if (warp < 4 && use_tma == 2) {
-    // ================================ loader (TMA): warp 0 =========================================
-    if (warp == 0) {
+  if (warp == 17) {
+    // ================================ W producer (TMA): one thread ================================
+    // runs ahead of the x loaders by the difference of the ring depths: W_hi tiles are the HBM bytes of the stream
+    if (use_tma && lane == 0) {
       const uint32_t s0 = umma::smem_u32(smem);
+      const uint64_t stream_policy = l2_stream_policy((err.l2_hints & 1) != 0);
+      int n = 0;
+      for (int i = 0; i < n_my && ok; ++i) {
+        const int idx = blockIdx.x + i * gridDim.x;
+        const int kb0 = items[idx].kb0, kb1 = items[idx].kb1;
+        const CUtensorMap* wm = wmaps + idx;
+        umma::tmap_acquire(wm);
+        for (int kb = kb0; kb < kb1; ++kb, ++n) {
+          const int sw = n % WR;
+          if (n >= WR && !umma::mbar_wait(&wfree[sw], ((n / WR) & 1) ^ 1)) { ok = false; break; }
+          umma::mbar_arrive_expect_tx(&wland[sw], Cfg::A_BYTES);
+          umma::tma_load_2d(s0 + sw * Cfg::A_BYTES, wm, 32 * kb, 0, &wland[sw], stream_policy);
+          MFAS_KSTAMP(32, n, 1);
+        }
+      }
+    }
+  } else if (warp < 4 && use_tma == 2) {
+    // ================================ x loader (TMA gather4): warp 0 ===============================
+    if (warp == 0) {
+      const uint32_t x0 = umma::smem_u32(x_base);
       const uint64_t stream_policy = l2_stream_policy((err.l2_hints & 1) != 0);
       const uint64_t x_policy = (err.l2_hints & 8) ? l2_keep_policy() : (err.l2_hints & 4) ? l2_stream_policy(false) : stream_policy;
       const int oob_row = (int)cache.n_rows;                       // a row index outside every tap tensor: arrives as zeros
@@ -357,24 +382,19 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
       for (int i = 0; i < n_my && ok; ++i) {
         const int idx = blockIdx.x + i * gridDim.x;
         if (i + 1 < n_my) { nxt = items[idx + gridDim.x]; load_rows(nxt, rows_nxt); }      // in flight while this item's k-blocks are issued
-        const CUtensorMap* wm = wmaps + idx;
         const CUtensorMap* sm = &taps.ske[cur.ske_tap];
         const CUtensorMap* rm = &taps.rgb[cur.rgb_tap];
-        if (lane == 0) umma::tmap_acquire(wm);
 #pragma unroll 1
         for (int kb = cur.kb0; kb < cur.kb1; ++kb, ++n) {
-          const int sg = n % R;
-          if (n >= R && !umma::mbar_wait(&rawfree[sg], ((n / R) & 1) ^ 1)) { ok = false; break; }
-          const uint32_t a = s0 + sg * Cfg::TILE, b = a + Cfg::A_BYTES;
-          if (lane == 0) {
-            umma::mbar_arrive_expect_tx(&landed[sg], Cfg::A_BYTES + Cfg::B_BYTES);
-            umma::tma_load_2d(a, wm, 32 * kb, 0, &landed[sg], stream_policy);
-          }
+          const int sx = n % XS;
+          if (n >= XS && !umma::mbar_wait(&xfree[sx], ((n / XS) & 1) ^ 1)) { ok = false; break; }
+          const uint32_t b = x0 + sx * Cfg::X_TILE;
+          if (lane == 0) umma::mbar_arrive_expect_tx(&xland[sx], Cfg::B_BYTES);
           __syncwarp();
           if (lane < NPAD / 4) {
             const bool ske = kb < cur.fs_kb;
             umma::tma_gather4(b + lane * 512, ske ? sm : rm, 32 * (ske ? kb : kb - cur.fs_kb), rows_cur[0], rows_cur[1], rows_cur[2],
-                              rows_cur[3], &landed[sg], x_policy);
+                              rows_cur[3], &xland[sx], x_policy);
           }
         }
         cur = nxt;
@@ -387,7 +407,7 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
     constexpr int WJ = 8, XJ = NPAD / 16;                          // rows r + 16 j of the W / x tile
     const int r = tid >> 3, c = tid & 7;                           // 16-byte chunk c of the 128-byte row
     const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);   // sw128(r + 16 j, 16 c) = off + 2048 j
-    const uint32_t s0 = umma::smem_u32(smem);
+    const uint32_t s0 = umma::smem_u32(smem), x0 = umma::smem_u32(x_base);
     const uint64_t stream_policy = l2_stream_policy((err.l2_hints & 1) != 0);
     // the gathered x rows are read again by the backward stream of the same step: bit 2 = default priority, bit 3 = evict-last
     const uint64_t x_policy = (err.l2_hints & 8) ? l2_keep_policy() : (err.l2_hints & 4) ? l2_stream_policy(false) : stream_policy;
@@ -415,8 +435,6 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
       const FwdItem& it = cur;
       const long long wstride = 16LL * it.K;
       const float* wp = it.W + (long long)r * it.K + c * 4;        // &W[m0 + r][4 c]
-      const CUtensorMap* wm = wmaps + (blockIdx.x + i * gridDim.x);
-      if (use_tma && tid == 0) umma::tmap_acquire(wm);
       const float* xs[XJ]; const float* xr[XJ];                    // gathered rows of the two taps, indexed by concat column
 #pragma unroll
       for (int j = 0; j < XJ; ++j) {
@@ -426,24 +444,23 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
       }
 #pragma unroll 1
       for (int kb = it.kb0; kb < it.kb1; ++kb, ++n) {
-        const int sg = n % R;
-        if (n >= R && !umma::mbar_wait(&rawfree[sg], ((n / R) & 1) ^ 1)) { ok = false; break; }
-        if (tid == 0) MFAS_KSTAMP(32, n, 7);
-        const uint32_t a = s0 + sg * Cfg::TILE + off, b = a + Cfg::A_BYTES;
-        const float* w = wp + 32LL * kb;
-        if (use_tma) {                                             // the W tile: one TMA box, issued by one thread
-          if (tid == 0) {
-            umma::mbar_arrive_expect_tx(&landed[sg], Cfg::A_BYTES);
-            umma::tma_load_2d(s0 + sg * Cfg::TILE, wm, 32 * kb, 0, &landed[sg], stream_policy);
-          }
-        } else {
+        const int sx = n % XS;
+        if (!use_tma) {                                            // the W tile by cp.async too (no TMA descriptor encoder)
+          const int sw = n % WR;
+          if (n >= WR && !umma::mbar_wait(&wfree[sw], ((n / WR) & 1) ^ 1)) { ok = false; break; }
+          const uint32_t a = s0 + sw * Cfg::A_BYTES + off;
+          const float* w = wp + 32LL * kb;
 #pragma unroll
           for (int j = 0; j < WJ; ++j) cp_async16_zfill(a + j * 2048, w + j * wstride, r + 16 * j < it.rows_valid, stream_policy);
+          cp_async_arrive_noinc(&wland[sw]);
         }
+        if (n >= XS && !umma::mbar_wait(&xfree[sx], ((n / XS) & 1) ^ 1)) { ok = false; break; }
+        if (tid == 0) MFAS_KSTAMP(32, n, 7);
+        const uint32_t b = x0 + sx * Cfg::X_TILE + off;
         const bool ske = kb < it.fs_kb;
 #pragma unroll
         for (int j = 0; j < XJ; ++j) cp_async16_zfill(b + j * 2048, (ske ? xs[j] : xr[j]) + 32LL * kb, r + 16 * j < nrows, x_policy);
-        cp_async_arrive_noinc(&landed[sg]);
+        cp_async_arrive_noinc(&xland[sx]);
         if (tid == 0) MFAS_KSTAMP(32, n, 0);
       }
       cur = nxt; nxt = nx2;
@@ -453,7 +470,7 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
     asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp < 12) {
     // ================================ converters ==================================================
-    // group g: k-blocks g, g + CG, ...; x_lo goes next to x_hi in the raw stage, W_lo into the group's turn of the W_lo ring
+    // group g: k-blocks g, g + CG, ...; x_lo goes next to x_hi in the x stage, W_lo into the group's turn of the W_lo ring
     const int ct = tid - 128;
     constexpr int CG = Cfg::CGROUPS, TG = Cfg::CONVERTERS / CG;
     constexpr int NA = (int)(Cfg::A_BYTES / 16), NCH = (int)((Cfg::A_BYTES + Cfg::B_BYTES) / 16), CJ = NCH / TG;
@@ -462,16 +479,21 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
     for (int i = 0; i < n_my; ++i) { const FwdItem& it = items[blockIdx.x + i * gridDim.x]; total += it.kb1 - it.kb0; }
 #pragma unroll 1
     for (int n = grp; n < total; n += CG) {
-      const int sg = n % R, sl = n % LQ;
-      if (!umma::mbar_wait(&landed[sg], (n / R) & 1)) { ok = false; break; }
+      const int sw = n % WR, sx = n % XS, sl = n % LQ;
+      if (!umma::mbar_wait(&wland[sw], (n / WR) & 1)) { ok = false; break; }
+      if (!umma::mbar_wait(&xland[sx], (n / XS) & 1)) { ok = false; break; }
       if (gt == 0) MFAS_KSTAMP(32, n, 2);
       if (n >= LQ && !umma::mbar_wait(&lofree[sl], ((n / LQ) & 1) ^ 1)) { ok = false; break; }
       if (gt == 0) MFAS_KSTAMP(32, n, 6);
-      uint8_t* st = smem + sg * Cfg::TILE;
+      const uint8_t* wh = smem + sw * Cfg::A_BYTES;
+      uint8_t* xh = x_base + sx * Cfg::X_TILE;
       uint8_t* wl = lo_base + sl * Cfg::LO_TILE;
       float4 x[CJ];
 #pragma unroll
-      for (int j = 0; j < CJ; ++j) x[j] = *reinterpret_cast<const float4*>(st + (size_t)(gt + j * TG) * 16);      // W_hi then x_hi: contiguous
+      for (int j = 0; j < CJ; ++j) {
+        const int ch = gt + j * TG;
+        x[j] = ch < NA ? *reinterpret_cast<const float4*>(wh + (size_t)ch * 16) : *reinterpret_cast<const float4*>(xh + (size_t)(ch - NA) * 16);
+      }
 #pragma unroll
       for (int j = 0; j < CJ; ++j) {
         const int ch = gt + j * TG;
@@ -481,9 +503,9 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
         l.z = umma::round_tf32(x[j].z - __uint_as_float(__float_as_uint(x[j].z) & 0xFFFFE000u));
         l.w = umma::round_tf32(x[j].w - __uint_as_float(__float_as_uint(x[j].w) & 0xFFFFE000u));
         if (ch < NA) *reinterpret_cast<float4*>(wl + (size_t)ch * 16) = l;
-        else *reinterpret_cast<float4*>(st + Cfg::B_BYTES + (size_t)ch * 16) = l;
+        else *reinterpret_cast<float4*>(xh + Cfg::B_BYTES + (size_t)(ch - NA) * 16) = l;
       }
-      umma::fence_async_smem();                                    // lo (generic proxy) and the landed raw tile -> tensor core
+      umma::fence_async_smem();                                    // lo (generic proxy) and the landed raw tiles -> tensor core
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&lofull[sl]);
       if (gt == 0) MFAS_KSTAMP(32, n, 3);
@@ -499,12 +521,12 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
       if (i + 1 < n_my) nkb_next = nkb_of(i + 1);
       if (!umma::mbar_wait(&tempty[tb], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
       for (int k = 0; k < nkb; ++k, ++n) {
-        const int sg = n % R, sl = n % LQ;
+        const int sw = n % WR, sx = n % XS, sl = n % LQ;
         if (!umma::mbar_wait(&lofull[sl], (n / LQ) & 1)) { ok = false; break; }
         if (lane == 0) MFAS_KSTAMP(32, n, 4);
         umma::tc_fence_after();
         if (umma::elect_one()) {
-          const uint32_t a_hi = umma::smem_u32(smem) + sg * Cfg::TILE, b_hi = a_hi + Cfg::A_BYTES;
+          const uint32_t a_hi = umma::smem_u32(smem) + sw * Cfg::A_BYTES, b_hi = umma::smem_u32(x_base) + sx * Cfg::X_TILE;
           const uint32_t a_lo = umma::smem_u32(lo_base) + sl * Cfg::LO_TILE;
           const uint64_t dah0 = umma::smem_desc(a_hi, 16, 1024), dal0 = umma::smem_desc(a_lo, 16, 1024), dbh0 = umma::smem_desc(b_hi, 16, 1024);
           const uint32_t dt = tm + tb * 2 * NPAD;
@@ -514,7 +536,8 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
             umma::mma_tf32(dt, dah0 + 2 * ks, dbh0 + 2 * ks, idesc_cat, acc);     // W_hi [x_hi; x_lo]^T -> [main | correction]
             umma::mma_tf32(dt + NPAD, dal0 + 2 * ks, dbh0 + 2 * ks, idesc, 1u);   // W_lo x_hi^T -> correction
           }
-          umma::mma_commit(&rawfree[sg]);
+          umma::mma_commit(&wfree[sw]);
+          umma::mma_commit(&xfree[sx]);
           umma::mma_commit(&lofree[sl]);
           if (k == nkb - 1) umma::mma_commit(&tfull[tb]);
         }
@@ -522,7 +545,7 @@ k_tc_fwd_ws(const FwdItem* __restrict__ items, int n_items, DCache cache, BatchR
         if (lane == 0) MFAS_KSTAMP(32, n, 5);
       }
     }
-  } else {
+  } else if (warp < 17) {
     // ================================ epilogue ====================================================
     const int q = warp & 3;                                        // TMEM lane quarter this warp may read
     struct Ep { long long part_off; int rows_valid, Hp; };
