@@ -67,7 +67,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--candidates", type=int, default=148, help="candidates per GPU (weak scaling); 148 = one fused-chain CTA per SM")
     ap.add_argument("--epochs", type=int, default=3, help="epochs per candidate per step (search driver default: --epochs 3)")
-    ap.add_argument("--cpu-sample-steps", type=int, default=48, help="train steps of the CPU baseline sample")
+    ap.add_argument("--cpu-sample-steps", type=int, default=3200, help="train steps of the CPU baseline sample (3200 = 20 candidate-epochs of one candidate: 10-15 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "search32", "search256", "mmimdb64", "depth"],
@@ -130,8 +130,11 @@ def cpu_reference_sample(train_steps, threads=None):
     from oracle.torch_port import FusionHeadTorch, train_candidate
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    dev_steps = max(1, train_steps // 2)
-    train = synthetic_ntu_cache(max(train_steps * B, 2 * B), 1)
+    per_epoch = math.ceil(N_TRAIN / B)                          # 160 train (+ 80 eval) steps = one candidate-epoch of cfg2
+    epochs = max(1, train_steps // per_epoch)                   # whole epochs over the full-size split once the sample is that long
+    ts = min(train_steps, per_epoch)
+    dev_steps = max(1, ts // 2)
+    train = synthetic_ntu_cache(max(ts * B, 2 * B), 1)
     dev = synthetic_ntu_cache(max(dev_steps * B, B), 2)
     torch.manual_seed(0)
     model = FusionHeadTorch(CONF4, H, C, batchnorm=True)
@@ -139,13 +142,14 @@ def cpu_reference_sample(train_steps, threads=None):
     orders = lambda ph, e: torch.randperm(len(train) if ph == "train" else len(dev))
     train_candidate(model, tr, dv, orders, B, 1, max_train_steps=4, max_dev_steps=2)        # warm-up
     t0 = time.perf_counter()
-    _, st = train_candidate(model, tr, dv, orders, B, 1, max_train_steps=train_steps, max_dev_steps=dev_steps)
+    _, st = train_candidate(model, tr, dv, orders, B, epochs, max_train_steps=ts, max_dev_steps=dev_steps)
     dt = time.perf_counter() - t0
-    frac = st[0]["train_steps"] / math.ceil(N_TRAIN / B)        # fraction of a candidate-epoch that was run
+    n_tr, n_dv = sum(r["train_steps"] for r in st), sum(r["dev_steps"] for r in st)
+    frac = n_tr / per_epoch                                     # candidate-epochs that were run
     return {"value": frac / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"oracle/torch_port.py (PyTorch CPU restatement of the reference path), 1 candidate, "
-                      f"{st[0]['train_steps']} train + {st[0]['dev_steps']} eval steps of cfg2 in {dt:.2f} s, "
-                      f"scaled to a {math.ceil(N_TRAIN / B)}+{math.ceil(N_DEV / B)}-step candidate-epoch"}
+                      f"{n_tr} train + {n_dv} eval steps of cfg2 ({epochs} epoch(s)) in {dt:.2f} s, "
+                      f"scaled to a {per_epoch}+{math.ceil(N_DEV / B)}-step candidate-epoch"}
 
 
 def gpu_eager_reference_sample(device, train_steps=80):
@@ -185,8 +189,8 @@ def run_reference(a):
     from oracle.torch_port import FusionHeadTorch, train_candidate
     threads = os.cpu_count()
     torch.set_num_threads(threads)
-    # each step: a bounded sample = 1/4 candidate-epoch (40 train + 20 eval steps) of one candidate
-    ts, ds = 40, 20
+    # each step: a bounded sample = one candidate-epoch (160 train + 80 eval steps) of one candidate, ~0.6 s on 16 cores
+    ts, ds = math.ceil(N_TRAIN / B), math.ceil(N_DEV / B)
     train, dev = synthetic_ntu_cache(ts * B, 1), synthetic_ntu_cache(ds * B, 2)
     tr, dv = (train.ske_cat, train.rgb_cat, train.labels), (dev.ske_cat, dev.rgb_cat, dev.labels)
     orders = lambda ph, e: torch.randperm(len(train) if ph == "train" else len(dev))
@@ -199,7 +203,7 @@ def run_reference(a):
         train_candidate(model, tr, dv, orders, B, 1)
     dt = (time.perf_counter() - t0) / max(a.steps, 1)
     value = (ts / math.ceil(N_TRAIN / B)) / dt
-    sample = f"oracle/torch_port.py on {threads} host threads; each step = {ts} train + {ds} eval steps of one cfg2 candidate (1/4 candidate-epoch)"
+    sample = f"oracle/torch_port.py on {threads} host threads; each step = {ts} train + {ds} eval steps of one cfg2 candidate (one candidate-epoch)"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
