@@ -2811,6 +2811,9 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
 //                            requested one tile ahead; gradient straight out of TMEM       (tempty[t] -> MMA)
 // Tile list: as k_tc_bwd_ws with row tiles of HN (the classifier's C rows are HN-row tiles h0 = 0, HN, ...).
 // Batches above 64 rows: two passes over the 64-row stage into the same accumulator.
+// (Measured and kept out, r02fv: converter warps that TRANSPOSE while they split, so that both operands are K-major tiles -- correct,
+//  MMA issue 2760 -> ~1600 cycles per tile, but the transposed hi tile can no longer be the raw stage, the operand stage is then
+//  72 KB and fits only once next to three raw stages: split and MMA issue alternate again, 157 us against 140.)
 // ---------------------------------------------------------------------------------------------
 template <int HN> struct BwdSmall {
   static constexpr int BP = 64, RAW = HN <= 16 ? 3 : 2, LO = 2, NB = HN / 8;   // NB: 8-row p / m / v batches per tile and warp = ring slots
