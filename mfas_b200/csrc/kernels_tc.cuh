@@ -257,10 +257,10 @@ struct __align__(16) FwdItem {
 // k-block cost on the issuing thread: ~70 cycles per MMA, profiles/r02dk_roles.txt).  The converter warps work in two groups of
 // four, each with a W_lo stage of its own and every other k-block (a pass is two barrier waits, a shared-memory round trip, a
 // proxy fence and an arrive: its latency, not its bytes, was the converters' rate).
-template <int NPAD, int XR = 0> struct FwdWs {     // XR = 1: W ring 8 deep, x ring 4 (A/B switch MFAS_FWD_XR; default 7 / 5)
+template <int NPAD, int XR = 0> struct FwdWs {     // XR = 1: W / x rings 8 / 4 deep instead of 7 / 5 (128 batch rows: 6 / 3 instead of 4 / 4); A/B switch MFAS_FWD_XR
   // three rings: W_hi tiles (the stream's HBM bytes: as deep as shared memory allows -- what bounds the stream is loaded HBM
   // latency x tiles in flight), [x_hi | x_lo] tiles (gathered rows, mostly L2 hits), W_lo tiles
-  static constexpr int WR = NPAD == 64 ? 7 + XR : 6, XS = NPAD == 64 ? 5 - XR : 3, LO = 2;
+  static constexpr int WR = NPAD == 64 ? 7 + XR : 4 + 2 * XR, XS = NPAD == 64 ? 5 - XR : 4 - XR, LO = 2;
   static constexpr uint32_t A_BYTES = 16384, B_BYTES = NPAD * 128, X_TILE = 2 * B_BYTES, LO_TILE = A_BYTES;
   static constexpr size_t SMEM = 1024 + (size_t)WR * A_BYTES + (size_t)XS * X_TILE + (size_t)LO * LO_TILE;
   static constexpr int LOADERS = 128, CONVERTERS = 256, CGROUPS = 2, THREADS = 18 * 32;     // + one W-producer warp (TMA)
