@@ -305,7 +305,7 @@ struct mfas_group {
   float* dsp_tc = nullptr;        // alpha gates on the tc engine: [n_bwd_tiles][TC_DSP_PER_TILE] partials of d(loss)/d(sigmoid(alpha))
   int2* alpha_rng = nullptr;      // [n_cand][MFAS_MAX_LAYERS] {first tile, feature-column tiles} of every layer in the tile list
   size_t dsp_bytes = 0, rng_bytes = 0;
-  int l2_hints = 1;
+  int l2_hints = 9;               // bit 0: the forward's weight stream evict-first; bit 3: its gathered x rows evict-last (the backward stream of the same step re-reads them: r02gc)
   bool tchead = false;            // classifier head on the tensor core inside k_chain_all (+ its dW as a k_tc_bwd_ws tile)
   cudaEvent_t prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // mfas_group_set_profiling: around fwd / chain / bwd of a step
   bool prof = false, prof_valid = false;
