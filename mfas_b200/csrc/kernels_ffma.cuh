@@ -333,7 +333,7 @@ template <bool TRAIN, bool ML = false>
 __device__ __forceinline__ void head_body(const DCand& cd, int cand, const DCache& cache, const BatchRef& batch, int bmax,
                                           int hs_ld, int lg_ld, const AdamH& adam, float step_size, float bc2_sqrt,
                                           const HeadOut& out, float* smem) {
-  const int H = cd.H, C = cd.C, nrows = batch.n_rows, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = cd.H, C = cd.C, nrows = batch.n_rows, tid = threadIdx.x;
   const int H4 = H >> 2;
   float* hs = smem;                         // [bmax][hs_ld]
   float* wcs = hs + (size_t)bmax * hs_ld;   // [C][hs_ld]

@@ -1224,8 +1224,6 @@ template <bool TRAIN, int NPAD>
 __device__ __forceinline__ void chain_fwd_layer(ChainCtx& cx, const DCand& cd, int cand, int layer, int m0, int nrows, int bmax,
                                                 const float* part_base, long long part_stride_cand, uint32_t drop_seed,
                                                 float drop_p, uint32_t step) {
-  constexpr int THREADS = ChainCfg<NPAD>::THREADS;
-  uint8_t* smem = cx.smem;
   const int H = cd.H;
   const DLayer& ly = cd.layer[layer];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
