@@ -606,7 +606,7 @@ template <int NPAD, int HN> struct FwdSmall {
   static constexpr uint32_t EX_BYTES = NPAD == 64 ? 2 * 64 * (HN + 1) * 4 : 0;       // lo-row sums of the two accumulator buffers
   static constexpr int STAGES = (int)((230000 - EX_BYTES) / TILE);
   static constexpr size_t SMEM = 1024 + (size_t)STAGES * TILE + EX_BYTES;
-  static constexpr int LOADERS = 128, CONVERTERS = 256, CGROUPS = 4, THREADS = 17 * 32;
+  static constexpr int LOADERS = 128, CONVERTERS = 256, CGROUPS = 4, THREADS = 18 * 32;     // warps 12 and 17: MMA issuers
 };
 
 
@@ -621,11 +621,11 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nrows = batch.n_rows;
-  constexpr uint32_t TM_COLS = 4 * HN < 32 ? 32 : 4 * HN;          // two accumulator buffers x 2 HN columns
+  constexpr uint32_t TM_COLS = 8 * HN;                             // two accumulator buffers x two MMA warps x 2 HN columns
   if (warp == 0) umma::tmem_alloc(&tmem_slot, TM_COLS);
   if (tid == 32) {
     for (int i = 0; i < S; ++i) { umma::mbar_init(&landed[i], Cfg::LOADERS); umma::mbar_init(&split[i], Cfg::CONVERTERS / 32 / CG); umma::mbar_init(&sfree[i], 1); }
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 2); umma::mbar_init(&tempty[i], 4); }
     umma::fence_mbar_init();
   }
   umma::tc_fence_before();
@@ -729,28 +729,32 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
       if (lane == 0) umma::mbar_arrive(&split[sg]);
       if (gt == 0) MFAS_KSTAMP(32, n, 3);
     }
-  } else if (warp == 12) {
-    // ================================ MMA issuer ==================================================
+  } else if (warp == 12 || warp == 17) {
+    // ================================ MMA issuers =================================================
+    // Two warps, every other k-block of an item each, an accumulator of its own each (the epilogue adds them in a fixed order):
+    // the issue loop of one warp -- barrier poll, fence, 4 MMAs, commits: ~600 cycles per k-block -- was the stream's rate.
     constexpr uint32_t idesc_cat = umma::idesc_tf32(128, 2 * HN, false, false), idesc_lo = umma::idesc_tf32(128, HN, false, false);
-    int n = 0;
+    const int mw = warp == 12 ? 0 : 1;
+    int n0 = 0;
     auto nkb_of = [&](int i) { const FwdItem& it = items[blockIdx.x + i * gridDim.x]; return it.kb1 - it.kb0; };
     int nkb_next = n_my > 0 ? nkb_of(0) : 0;
     for (int i = 0; i < n_my && ok; ++i) {
       const int nkb = nkb_next, tb = i & 1;
       if (i + 1 < n_my) nkb_next = nkb_of(i + 1);
       if (!umma::mbar_wait(&tempty[tb], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
-      for (int k = 0; k < nkb; ++k, ++n) {
-        const int sg = n % S;
+      if (mw >= nkb) { if (lane == 0) umma::mbar_arrive(&tfull[tb]); }      // a one-k-block item: nothing for the second warp
+      for (int k = mw; k < nkb; k += 2) {
+        const int n = n0 + k, sg = n % S;
         if (!umma::mbar_wait(&split[sg], (n / S) & 1)) { ok = false; break; }
         if (lane == 0) MFAS_KSTAMP(32, n, 4);
         umma::tc_fence_after();
         if (umma::elect_one()) {
           const uint32_t a_hi = umma::smem_u32(smem) + sg * Cfg::TILE, b_hi = a_hi + 2 * Cfg::A_BYTES;
           const uint64_t da0 = umma::smem_desc(a_hi, 16, 1024), db0 = umma::smem_desc(b_hi, 16, 1024);
-          const uint32_t dt = tm + tb * 2 * HN;
+          const uint32_t dt = tm + tb * 4 * HN + mw * 2 * HN;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t acc = (k > 0 || ks > 0) ? 1u : 0u;
+            const uint32_t acc = (k > mw || ks > 0) ? 1u : 0u;
             if (NPAD == 64) {
               umma::mma_tf32(dt, da0 + 2 * ks, db0 + 2 * ks, idesc_cat, acc);               // [x_hi; x_lo] [W_hi; W_lo]^T
             } else {
@@ -759,11 +763,12 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
             }
           }
           umma::mma_commit(&sfree[sg]);
-          if (k == nkb - 1) umma::mma_commit(&tfull[tb]);
+          if (k + 2 >= nkb) umma::mma_commit(&tfull[tb]);
         }
         __syncwarp();
         if (lane == 0) MFAS_KSTAMP(32, n, 5);
       }
+      n0 += nkb;
     }
   } else {
     // ================================ epilogue ====================================================
@@ -771,9 +776,9 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
     // 64 batch rows: lanes 0..63 hold the x_hi rows, 64..127 the x_lo rows of the same batch rows; 128: lane = batch row
     const int brow = NPAD == 128 ? q * 32 + lane : (q & 1) * 32 + lane;
     float* ex = reinterpret_cast<float*>(smem + (size_t)S * Cfg::TILE);          // [2][64][HN + 1]
-    struct Ep { long long part_off; int rows_valid, Hp; };
-    auto ep_of = [&](int i) { const FwdItem& f = items[blockIdx.x + i * gridDim.x]; return Ep{f.part_off, f.rows_valid, f.Hp}; };
-    Ep ep_next = n_my > 0 ? ep_of(0) : Ep{0, 0, 0};
+    struct Ep { long long part_off; int rows_valid, Hp, nkb; };
+    auto ep_of = [&](int i) { const FwdItem& f = items[blockIdx.x + i * gridDim.x]; return Ep{f.part_off, f.rows_valid, f.Hp, f.kb1 - f.kb0}; };
+    Ep ep_next = n_my > 0 ? ep_of(0) : Ep{0, 0, 0, 0};
     for (int i = 0; i < n_my; ++i) {
       const Ep it = ep_next;
       if (i + 1 < n_my) ep_next = ep_of(i + 1);
@@ -781,18 +786,24 @@ k_tc_fwd_small(const FwdItem* __restrict__ items, int n_items, DCache cache, Bat
       if (!umma::mbar_wait(&tfull[tb], (i >> 1) & 1)) ok = false;   // (no early exit: the four warps meet at the exchange barrier)
       umma::tc_fence_after();
       float v[HN], w[HN];
-      if (HN == 16) {
-        umma::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 2 * HN), v);
-        umma::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 2 * HN + HN), w);
-      } else {
-        umma::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 2 * HN), v);
-        umma::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * 2 * HN + HN), w);
+      auto ld_acc = [&](uint32_t col, float* o) {
+        if (HN == 16) umma::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + col, o);
+        else umma::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + col, o);
+      };
+      ld_acc((uint32_t)(tb * 4 * HN), v);                           // first MMA warp: k-blocks 0, 2, ...
+      ld_acc((uint32_t)(tb * 4 * HN + HN), w);
+#pragma unroll
+      for (int h = 0; h < HN; ++h) v[h] += w[h];
+      if (it.nkb > 1) {                                             // second MMA warp: k-blocks 1, 3, ...
+        float v2[HN];
+        ld_acc((uint32_t)(tb * 4 * HN + 2 * HN), v2);
+        ld_acc((uint32_t)(tb * 4 * HN + 3 * HN), w);
+#pragma unroll
+        for (int h = 0; h < HN; ++h) v[h] += v2[h] + w[h];
       }
       umma::tc_fence_before();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&tempty[tb]);
-#pragma unroll
-      for (int h = 0; h < HN; ++h) v[h] += w[h];
       if (NPAD == 64) {
         float* e = ex + ((size_t)tb * 64 + brow) * (HN + 1);
         if (q >= 2) {
