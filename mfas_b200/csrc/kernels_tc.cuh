@@ -227,15 +227,16 @@ k_tc_fwd_all(const DCand* __restrict__ cands, DCache cache, BatchRef batch, floa
 // forward, all layers, persistent + warp-specialised.  Same work items and partial-sum layout as
 // k_tc_fwd_all, but one CTA per SM walks a static list of items, the bytes in flight are bounded by
 // shared memory instead of registers, and no role ever waits for another inside a k-block:
-//   warps 0-3   loaders    : cp.async (16 B per lane, swizzle applied to the destination) of the raw fp32 W
-//                            and gathered x tiles straight into canonical SW128 K-major tiles, a ring of
-//                            RAW stages.  The raw tiles ARE the "hi" operands: kind::tf32 reads the top 19
-//                            bits of each 32-bit container, i.e. hi = trunc_tf32(x) for free.
-//                            (rawfree[s] <- MMA; landed[s] -> converters, signalled by cp.async itself)
-//   warps 4-11  converters : lo = rna_tf32(x - trunc_tf32(x)) (the subtraction is exact in fp32) into a
-//                            shorter ring of LO stages                     (lofree[s] <- MMA; lofull[s] -> MMA)
-//   warp  12    MMA        : per k-block 4 x {A_hi*B_hi -> main accumulator; A_lo*B_hi, A_hi*B_lo -> a second,
-//                            correction accumulator}.  The tensor core truncates when it adds into the fp32
+//   warp  17    W producer : one thread issues the W_hi tiles by TMA into their own ring (7 deep; cp.async by the loaders when
+//                            no tensor-map encoder is available)                       (wfree[s] <- MMA; wland[s] -> converters)
+//   warps 0-3   loaders    : cp.async (16 B per lane, swizzle applied to the destination) of the gathered x rows straight into
+//                            canonical SW128 K-major tiles, a ring of [x_hi | x_lo] stages (5 deep).  The raw tiles ARE the "hi"
+//                            operands: kind::tf32 reads the top 19 bits of each 32-bit container, i.e. hi = trunc_tf32(x) for free.
+//                            (xfree[s] <- MMA; xland[s] -> converters, signalled by cp.async itself)
+//   warps 4-11  converters : two groups of four warps, every other k-block: lo = rna_tf32(x - trunc_tf32(x)) (the subtraction is
+//                            exact in fp32): x_lo next to x_hi, W_lo into a ring of two            (lofree[s] <- MMA; lofull[s] -> MMA)
+//   warp  12    MMA        : per k-block 4 x {W_hi [x_hi; x_lo]^T -> [main | correction] accumulator columns (ONE N = 2 NPAD MMA);
+//                            W_lo x_hi^T -> correction}.  The tensor core truncates when it adds into the fp32
 //                            accumulator, so the long chain of adds is the dominant error (measured 5e-6..1e-5
 //                            of max|logit| against 1e-6 for the fp32 reference); keeping the small cross terms
 //                            out of the main chain cuts its length by three            (tfull[t] -> epilogue)
@@ -2812,12 +2813,14 @@ k_tc_bwd_ws(const DCand* __restrict__ cands, DCache cache, BatchRef batch, int b
 // k_tc_bwd_ws tile, so what is left is the x tile (64 gathered rows x 512 bytes) -- and k_tc_bwd_ws keeps exactly ONE such
 // tile in flight per SM (registers of its stager warps): search256 on one B200 took 5 us per tile, 203 us per step, for bytes
 // that take 75 us.  Here the gathered x rows and the dz slice go global -> shared with cp.async straight into the MN-major
-// operand layout (the raw tile IS the hi operand), three stages deep; converters derive the lo tile; the MMA is N = HN wide:
-//   warps 0-3   loaders    : cp.async into raw stage f % 3                  (rawfree <- MMA; landed -> converters)
-//   warps 4-11  converters : lo = rna_tf32(x - trunc_tf32(x)) into the lo stage       (lofree <- MMA; lofull -> MMA)
-//   warp  12    MMA        : 3 x tcgen05.mma per 8 batch rows, M = 128 columns, N = HN (tfull[t] -> Adam)
+// operand layout (the raw tile IS the hi operand), three raw stages deep; converters derive the lo tiles (two lo stages); per 8 batch
+// rows the MMA warp issues x_hi [dz_hi | dz_lo] (N = 32 + HN, one operand across the raw and the lo stage) and x_lo dz_hi:
+//   warps 0-3   loaders    : cp.async into raw stage f % RAW, sources from the host-resolved tile record   (rawfree <- MMA; landed -> converters)
+//   warps 4-11  converters : two groups of four warps, every other fill: lo = rna_tf32(x - trunc_tf32(x)) into the group's lo stage
+//                                                                                         (lofree[g] <- MMA; lofull[g] -> MMA)
+//   warp  12    MMA        : 2 x tcgen05.mma per 8 batch rows, M = 128 columns             (tfull[t] -> Adam)
 //   warps 13-16 Adam       : one TMEM lane quarter each (32 columns x HN rows); p / m / v through a per-warp cp.async ring
-//                            requested one tile ahead; gradient straight out of TMEM       (tempty[t] -> MMA)
+//                            requested one tile ahead; gradient straight out of TMEM (the two column ranges added)   (tempty[t] -> MMA)
 // Tile list: as k_tc_bwd_ws with row tiles of HN (the classifier's C rows are HN-row tiles h0 = 0, HN, ...).
 // Batches above 64 rows: two passes over the 64-row stage into the same accumulator.
 // (Measured and kept out, r02fv: converter warps that TRANSPOSE while they split, so that both operands are K-major tiles -- correct,
